@@ -1,0 +1,167 @@
+"""ctypes harness around oracle/libc2d_oracle.so (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module; nothing under compton2d_b200/ does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+LIB = HERE / "libc2d_oracle.so"
+
+
+def build(force: bool = False) -> Path:
+    srcs = [HERE / "c2d_oracle.c", HERE / "c2d_oracle_fp.c", HERE / "c2d_oracle.h"]
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in srcs):
+        subprocess.check_call(["make", "-s", "-C", str(HERE)])
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(str(LIB))
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [C.c_int] * 9 + [C.c_int64, C.c_int64]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_array.restype = C.c_void_p
+        L.orc_array.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int64), C.POINTER(C.c_int)]
+        L.orc_set_scalar.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+        L.orc_get_scalar.argtypes = [C.c_void_p, C.c_char_p]
+        L.orc_get_scalar.restype = C.c_double
+        L.orc_ran1_seed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        L.orc_ran1_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.orc_philox_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_mix64.restype = C.c_uint64
+        L.orc_mix64.argtypes = [C.c_uint64, C.c_uint64]
+        L.orc_philox_uniform.restype = C.c_double
+        L.orc_philox_uniform.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32]
+        L.orc_philox4x32.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for fn in ("orc_dilog", "orc_intg_v", "orc_gammln", "orc_gamma_bar"):
+            getattr(L, fn).restype = C.c_double
+            getattr(L, fn).argtypes = [C.c_double]
+        L.orc_McDonald.restype = C.c_double
+        L.orc_McDonald.argtypes = [C.c_double, C.c_double]
+        L.orc_comtot.restype = C.c_double
+        L.orc_comtot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
+        L.orc_vol_calc.argtypes = [C.c_void_p, C.c_int]
+        L.orc_field_calc.argtypes = [C.c_void_p]
+        L.orc_step_zero_worker.argtypes = [C.c_void_p]
+        L.orc_imctrk2d.argtypes = [C.c_void_p, C.c_int]
+        L.orc_IC_loss.argtypes = [C.c_void_p]
+        L.orc_fp_calc.argtypes = [C.c_void_p, C.c_int]
+        L.orc_tridag.argtypes = [C.c_int] + [C.c_void_p] * 5
+        _lib = L
+    return _lib
+
+
+class Oracle:
+    """One orc_state.  Arrays are numpy views into the C allocation: `o.a.edep[...]`;
+    scalars via `o["dt"] = ...` / `o["ndxout"]`."""
+
+    def __init__(self, nz, nr, n_vol=400, num_nt=200, nphfield=400, n_gg=100, nphtotal=128,
+                 nph_lc=5, nmu=1, cens_cap=200000, ev_cap=200000):
+        self.L = lib()
+        self.dims = dict(nz=nz, nr=nr, nzone=nz * nr, n_vol=n_vol, num_nt=num_nt, nphfield=nphfield,
+                         n_gg=n_gg, nphtotal=nphtotal, nph_lc=nph_lc, nmu=nmu)
+        self.p = self.L.orc_create(nz, nr, n_vol, num_nt, nphfield, n_gg, nphtotal, nph_lc, nmu,
+                                   cens_cap, ev_cap)
+        self.cens_cap, self.ev_cap = cens_cap, ev_cap
+        self.a = _Arrays(self)
+
+    def __del__(self):
+        try:
+            self.L.orc_destroy(self.p)
+        except Exception:
+            pass
+
+    def array(self, name):
+        n, es = C.c_int64(), C.c_int()
+        ptr = self.L.orc_array(self.p, name.encode(), C.byref(n), C.byref(es))
+        if not ptr:
+            raise KeyError(name)
+        ints64 = ("npcen", "nelectron", "sidout", "sidin")
+        dt = {8: np.float64, 4: np.int32}[es.value]
+        if name in ints64:
+            dt = np.uint64 if name.startswith("sid") else np.int64
+        buf = (C.c_char * (n.value * es.value)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt)
+
+    def __setitem__(self, k, v):
+        if self.L.orc_set_scalar(self.p, k.encode(), float(v)) != 0:
+            raise KeyError(k)
+
+    def __getitem__(self, k):
+        v = self.L.orc_get_scalar(self.p, k.encode())
+        if v != v:
+            raise KeyError(k)
+        return v
+
+    # -- RNG
+    def ran1_seed(self, idum, iv, iy):
+        iv = np.ascontiguousarray(iv, dtype=np.int32)
+        self.L.orc_ran1_seed(self.p, int(idum), iv.ctypes.data, int(iy))
+
+    def ran1_get(self):
+        idum, iy = C.c_int(), C.c_int()
+        iv = np.zeros(32, np.int32)
+        self.L.orc_ran1_get(self.p, C.byref(idum), iv.ctypes.data, C.byref(iy))
+        return idum.value, iv, iy.value
+
+    def philox_key(self, seed, cycle):
+        self.L.orc_philox_key(self.p, int(seed), int(cycle))
+
+    # -- phases
+    def field_calc(self):
+        self.L.orc_field_calc(self.p)
+
+    def vol_calc(self, zone):
+        self.L.orc_vol_calc(self.p, int(zone))
+
+    def vol_all(self):
+        for zone in range(1, self.dims["nzone"] + 1):
+            self.vol_calc(zone)
+
+    def fp_calc(self, zone):
+        self.L.orc_fp_calc(self.p, int(zone))
+
+    def step_zero(self):
+        self.L.orc_step_zero_worker(self.p)
+
+    def comtot(self, j, k, xnu):
+        return self.L.orc_comtot(self.p, j, k, float(xnu))
+
+    def census(self):
+        n = int(self["ndxout"])
+        return (self.a.dbufout[: 6 * n].reshape(n, 6).copy(), self.a.ibufout[: 6 * n].reshape(n, 6).copy(),
+                self.a.sidout[:n].copy())
+
+    def events(self):
+        n = min(int(self["nev"]), self.ev_cap)
+        return self.a.events[: 7 * n].reshape(n, 7).copy()
+
+
+class _Arrays:
+    def __init__(self, o):
+        object.__setattr__(self, "_o", o)
+        object.__setattr__(self, "_c", {})
+
+    def __getattr__(self, name):
+        c = self._c
+        if name not in c:
+            c[name] = self._o.array(name)
+        return c[name]
+
+    def __setattr__(self, name, val):
+        a = getattr(self, name)
+        v = np.asarray(val).ravel()
+        a[: v.size] = v

@@ -1,0 +1,140 @@
+"""Glue between the reference-binary snapshots (tests/golden/refbin_*.npz) and the
+CPU oracle (oracle/orc.py): load a snapshot into an orc_state, compare a state with a snapshot."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+REPO = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(REPO / "oracle"))
+sys.path.insert(0, str(REPO / "tests"))
+import orc  # noqa: E402
+from golden_util import Golden  # noqa: E402
+
+NLC = 16
+
+ZONE_D = ["f_pair", "n_e", "tea", "ewsv", "eloss_th", "eloss_tot", "zsurf", "edep", "prdep", "ecens",
+          "tna", "b_field", "vol", "eloss_sy", "eloss_br", "ec_old", "q_turb", "turb_lev", "amxwl",
+          "gmin", "gmax", "p_nth", "te_new"]
+ZONE_BIN_LAST = ["f_nt", "pnt", "n_pos", "dn_pp", "dne_pa", "dnp_pa"]          # golden [j,k,i]
+ZONE_BIN_FIRST = ["kappa_tot", "eps_tot", "eps_th", "k_gg", "n_field", "n_ph"]  # golden [i,j,k]
+NAME = {"e_ph": "E_ph", "e_field": "E_field", "e_gg": "E_gg", "pnt": "Pnt", "elcmin": "Elcmin",
+        "elcmax": "Elcmax", "eloss_th": "Eloss_th", "eloss_tot": "Eloss_tot", "e_ic": "E_IC",
+        "ed_in": "Ed_in", "ed_ref": "Ed_ref", "b_field": "B_field", "eloss_sy": "Eloss_sy",
+        "eloss_br": "Eloss_br", "te_new": "Te_new", "f_ic": "F_IC"}
+SCALARS = {"pair_switch": "pair_switch", "cr_sent": "cr_sent", "spec_switch": "spec_switch",
+           "ncycle": "ncycle", "split1": "split1", "split2": "split2", "split3": "split3",
+           "spl3_trg": "spl3_trg", "inj_switch": "inj_switch", "inj_dis": "inj_dis",
+           "g2var_switch": "g2var_switch", "pick_sw": "pick_sw", "cf_sentinel": "cf_sentinel",
+           "rmin": "rmin", "zmin": "zmin", "time": "time", "inj_g1": "inj_g1", "inj_g2": "inj_g2",
+           "inj_p": "inj_p", "inj_t": "inj_t", "inj_gg": "inj_gg", "inj_sigma": "inj_sigma",
+           "inj_l": "inj_L", "inj_v": "inj_v", "pick_rate": "pick_rate", "r_esc": "r_esc",
+           "r_acc": "r_acc", "lnl": "lnL", "r_flare": "r_flare", "z_flare": "z_flare",
+           "t_flare": "t_flare", "sigma_r": "sigma_r", "sigma_z": "sigma_z", "sigma_t": "sigma_t",
+           "flare_amp": "flare_amp", "e_tot_old": "E_tot_old", "e_tot_new": "E_tot_new",
+           "hr_total": "hr_total", "hr_st_total": "hr_st_total", "f_t_implicit": "f_t_implicit",
+           "dt_max": "dT_max", "dr": "dr", "dz": "dz", "t_bound": "t_bound",
+           "incounter": "incounter", "outcounter": "outcounter", "cmcount1": "cmcount1",
+           "cmcount2": "cmcount2", "lkcount": "lkcount"}
+
+
+def cname(v):
+    return NAME.get(v, v)
+
+
+def new_oracle(snap, cens_cap=60000, ev_cap=60000):
+    nz, nr = int(snap.nz), int(snap.nr)
+    return orc.Oracle(nz, nr, nphtotal=max(int(snap.nphtotal), 1), nph_lc=int(snap.nph_lc), nmu=max(int(snap.nmu), 1),
+                      cens_cap=cens_cap, ev_cap=ev_cap)
+
+
+def load_snapshot(o, snap):
+    """Copy every hot-path input and tally of a reference-binary snapshot into the oracle state."""
+    nz, nr = o.dims["nz"], o.dims["nr"]
+    a = o.a
+    a.z = snap.z; a.r = snap.r
+    for v in ("e_ph", "e_field", "e_gg", "gnt", "elcmin", "elcmax", "mu", "e_ic", "erlki", "erlko",
+              "erlku", "erlkl", "ed_in", "ed_ref"):
+        setattr(a, cname(v), snap[v])
+    a.hu = snap.hu[: o.dims["nphtotal"] + 1]
+    for v in ZONE_D:
+        setattr(a, cname(v), snap[v])
+    for v in ZONE_BIN_LAST:
+        setattr(a, cname(v), snap[v])
+    for v in ZONE_BIN_FIRST:
+        setattr(a, cname(v), np.transpose(snap[v], (1, 2, 0)))
+    a.nsv = snap.nsv
+    a.npcen = snap.npcen.astype(np.int64)
+    a.nelectron[:] = 0
+    a.nelectron[1:201] = snap.nelectron
+    a.tbbl = snap.tbbl[:, 0]; a.tbbu = snap.tbbu[:, 0]
+    a.F_IC = np.transpose(snap.f_ic, (0, 1))          # golden [i_e, i_ph] -> [i_e][i_ph]
+    fo = np.zeros((32, o.dims["nphtotal"])); fo[: snap.fout.shape[0], :] = snap.fout[:, : o.dims["nphtotal"]]
+    a.fout = fo
+    ed = np.zeros((32, NLC)); ed[: snap.edout.shape[0], : snap.edout.shape[1]] = snap.edout
+    a.edout = ed
+    for g, c in SCALARS.items():
+        o[c] = float(snap[g])
+    o["dt"] = float(snap.dt[0])
+    o["rand_switch"] = int(snap.rand_switch)
+    o["nph_lc"] = int(snap.nph_lc); o["nmu"] = int(snap.nmu); o["nphtotal"] = int(snap.nphtotal)
+    n = int(snap.ndxout)
+    o["ndxout"] = n
+    a.dbufout[: 6 * n] = snap.dbufout[: 6 * n]
+    a.ibufout[: 6 * n] = snap.ibufout[: 6 * n]
+    o["nev"] = 0
+    o.ran1_seed(int(snap.rseed), snap.ran1_iv, int(snap.ran1_iy))
+
+
+def rel(a, b):
+    a = np.asarray(a, float); b = np.asarray(b, float)
+    sc = np.maximum(np.abs(b).max() if b.size else 0.0, 1e-300)
+    return float(np.abs(a - b).max() / sc) if a.size else 0.0
+
+
+def compare_tracking(o, snap, tol=1e-11):
+    """-> dict of mismatches between the oracle state and a reference-binary snapshot."""
+    bad = {}
+    nz, nr = o.dims["nz"], o.dims["nr"]
+    a = o.a
+    idum, iv, iy = o.ran1_get()
+    if idum != int(snap.rseed) or iy != int(snap.ran1_iy) or not np.array_equal(iv, snap.ran1_iv):
+        bad["ran1_state"] = (idum, int(snap.rseed))
+    for c in ("incounter", "outcounter", "cmcount1", "cmcount2", "lkcount"):
+        if int(o[c]) != int(snap[c]):
+            bad[c] = (int(o[c]), int(snap[c]))
+    n = int(snap.ndxout)
+    if int(o["ndxout"]) != n:
+        bad["ndxout"] = (int(o["ndxout"]), n)
+    else:
+        if not np.array_equal(a.ibufout[: 6 * n], snap.ibufout[: 6 * n]):
+            bad["ibufout"] = int((a.ibufout[: 6 * n] != snap.ibufout[: 6 * n]).sum())
+        d0 = a.dbufout[: 6 * n].reshape(n, 6); d1 = snap.dbufout[: 6 * n].reshape(n, 6)
+        r = np.abs(d0 - d1) / np.maximum(np.abs(d1), 1e-300)
+        if n and r.max() > 1e-9:
+            bad["dbufout"] = float(r.max())
+    if not np.array_equal(a.npcen[: nz * nr].reshape(nz, nr), snap.npcen):
+        bad["npcen"] = "differs"
+    if not np.array_equal(a.nelectron[1:201], snap.nelectron):
+        bad["nelectron"] = "differs"
+    for v in ("edep", "prdep", "ecens"):
+        e = rel(getattr(a, v)[: nz * nr].reshape(nz, nr), snap[v])
+        if e > tol:
+            bad[v] = e
+    for v in ("n_field", "n_ph"):
+        g = np.transpose(snap[v], (1, 2, 0))
+        e = rel(getattr(a, v)[: g.size].reshape(g.shape), g)
+        if e > tol:
+            bad[v] = e
+    for v in ("erlki", "erlko", "erlku", "erlkl", "ed_in", "e_ic"):
+        e = rel(getattr(a, cname(v))[: snap[v].size], snap[v])
+        if e > tol:
+            bad[v] = e
+    npt = o.dims["nphtotal"]
+    e = rel(a.fout.reshape(32, npt)[: snap.fout.shape[0]], snap.fout[:, :npt])
+    if e > tol:
+        bad["fout"] = e
+    e = rel(a.edout.reshape(32, NLC)[: snap.edout.shape[0], : snap.edout.shape[1]], snap.edout)
+    if e > tol:
+        bad["edout"] = e
+    return bad
