@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- photon histories/s tracked + tallied (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA library through its C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU build (prebuilt binary
+                                                           under oracle/refbin/fakempi.c) on the host cores
+
+Workload (config.workload): BASELINE.json configs[1] -- Mrk 421-style SSC blob, 16x16 zones, 100 photon
+energy groups, 1e7 volume sources per step and GPU (nst = 2e7), split1/2/3 = 1000/1000/300, plus the census
+photons the previous steps left (weak scaling: every GPU sources 1e7 histories per step).
+A step = one IMC time step of the hot path: imcfield2d (census re-track) + imcvol2d (volume sources) +
+scattering queue + the packed tally all-reduce.  value = histories of all ranks / max-over-ranks device time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+for p in (ROOT, ROOT / "tests", ROOT / "oracle", ROOT / "oracle" / "refbin"):
+    if str(p) not in sys.path:
+        sys.path.insert(0, str(p))
+
+METRIC = "photon_histories_per_s"
+UNIT = "histories/s"
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu=0):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference (CPU) arm
+def run_reference_sample(nst, ncores=1, warm=0, timed=2, workdir=None, fp=False, nz=16, nr=16):
+    """Time the UNMODIFIED reference binary (oracle/_ref/compton2d, staged by __graft_entry__.build()) on a
+    bounded sample of the workload: one launch of a 16x16-zone, 100-group run with `nst` particles per cycle,
+    cycles 0 .. warm+timed; `ncores` independent single-worker instances in parallel (distinct rseed,
+    SURVEY.md 8c item 1).  A "step" of the reference is one cycle; the timed window of a cycle is the worker's
+    tracking phase (imcfield2d + imcvol2d + imcsurf2d) taken from the MPI trace.  Cycle 0 never counts: the
+    worker's dt is still zero there.  -> dict(value, seconds per cycle, ...)"""
+    import math
+    import refrun
+    from make_golden import snapshot_points
+    if not (refrun.REFDIR / "compton2d").exists():
+        return None
+    refrun.build_shim()
+    base = Path(workdir or tempfile.mkdtemp(prefix="c2d_ref_"))
+    ncyc = warm + timed                                   # cycles 1..ncyc are tracked with dt > 0
+    inj_v = 2.9979245620e10 * math.sqrt(1.0 - 1.0 / 33.0 ** 2)
+    dt = min(0.75e16 / nr, 1.0e16 / nz) / inj_v           # setup2d.f:50-52 with the shipped z(nz), r(nr), mcdt, g_bulk
+    # master continues after cycle c while (c-1)*dt < tstop (xec2d.f:109); so does the worker (xec2d.f:189)
+    over = dict(nz=nz, nr=nr, nst=int(nst), tstop=f"{(ncyc - 0.5) * dt:.6e}".replace("e", "d"), pair_switch=0,
+                T_const=0 if fp else 1)
+    over["nphbins(1)"] = 30
+    over["nphbins(2)"] = 40          # 30 + 40 + 30 = 100 groups (the shipped file reuses the key nphbins(1) for region 3)
+    dirs = []
+    for c in range(ncores):
+        rd = base / f"inst{c}"
+        shutil.rmtree(rd, ignore_errors=True)
+        rd.mkdir(parents=True)
+        refrun.write_inputs(rd, dict(over, rseed=9857 + 101 * c), {}, staged=refrun.REFDIR)
+        dirs.append(rd)
+    t0 = time.time()
+    res = [None] * ncores
+
+    def work(c):
+        res[c] = refrun.run(dirs[c], trace=True, staged=refrun.REFDIR, cpu=None, timeout=3000)
+
+    th = [threading.Thread(target=work, args=(c,)) for c in range(ncores)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    wall = time.time() - t0
+    hist, cyc_secs, fp_steps, fp_secs = 0, [0.0] * timed, 0, []
+    for c, rd in enumerate(dirs):
+        if res[c] is None or res[c].returncode != 0:
+            return {"error": (rd / "stdout.txt").read_text()[-400:]}
+        tr = refrun.read_trace(rd, 1)
+        pts = dict((lab, idx) for idx, lab in snapshot_points(tr))
+        tt = {t["idx"]: t["t"] for t in tr}
+        out = (rd / "stdout.txt").read_text()
+        nct = [int(l.split("=")[-1]) for l in out.splitlines() if "nctot=" in l]
+        if len(nct) < ncyc + 1 or f"c{ncyc}_D" not in pts:
+            return {"error": f"expected {ncyc + 1} cycles, saw {len(nct)}: " + out[-300:]}
+        # cycle c tracks the census of cycle c-1 (nctot printed by imcredist) + the volume sources, whose
+        # number per cycle equals cycle 0's census (cycle-0 photons are banked unflown)
+        for k, cyc in enumerate(range(warm + 1, ncyc + 1)):
+            hist += nct[cyc - 1] + nct[0]
+            cyc_secs[k] = max(cyc_secs[k], tt[pts[f"c{cyc}_D"]] - tt[pts[f"c{cyc}_A"]])
+        if fp and "c1_F" in pts:
+            fp_secs.append(tt[pts["c1_F"]] - tt[pts["c1_E"]])
+            fp_steps += 5 * nz * nr
+    shutil.rmtree(base, ignore_errors=True)
+    secs = sum(cyc_secs)
+    r = {"histories": hist, "seconds": secs, "value": hist / secs, "wall_s": wall, "cores": ncores,
+         "ms_per_step": 1e3 * secs / timed}
+    if fp_secs:
+        r["fp_zone_steps_per_s"] = fp_steps / max(fp_secs)
+    return r
+
+
+def reference_arm(args):
+    """--impl reference: the reference's own CPU implementation of the path on this box's host cores.  One
+    launch per core of the prebuilt binary; its cycles are the steps (warm-up cycles 1..W, timed W+1..W+K)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = min(max(1, (os.cpu_count() or 2) - 1), 64)
+    nst = args.ref_nst
+    r = run_reference_sample(nst, ncores=ncores, warm=args.warmup, timed=args.steps)
+    if r is None or "error" in r:
+        print(json.dumps({"impl": "reference", "unavailable": "reference binary not staged in oracle/_ref or run failed: "
+                          + str((r or {}).get("error", ""))[:200].replace("\n", " ")}))
+        return
+    sample = (f"cycles {args.warmup + 1}-{args.warmup + args.steps} (census + volume sources each) of {ncores} independent "
+              f"single-worker instances of the prebuilt ifort binary, 16x16 zones, 100 groups, nst={nst} per instance, "
+              f"T_const=1 (FP off), split 1000/1000/300; {r['histories']} histories in {r['seconds']:.1f} s")
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": workload_config(args, ref=True),
+                      "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
+                      "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                      "gpu_launches": 0}))
+
+
+def workload_config(args, ref=False):
+    return {"workload": "BASELINE configs[1]: Mrk 421-style SSC blob, 16x16 zones, 100 photon energy groups, "
+                        "1e7 volume sources/step/GPU (nst=2e7) + census, split1/2/3=1000/1000/300, pair_switch=0",
+            "nz": 16, "nr": 16, "groups": 100, "nst_per_gpu": args.nst, "split": [1000, 1000, 300, 10],
+            "sigma_mode": args.sigma_mode, "l2": "inputs larger than L2 (census bank >= 0.6 GB/step after warm-up)",
+            "step": "imcfield2d + imcvol2d + scattering queue + tally all-reduce"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def our_arm(args):
+    import numpy as np
+    import torch
+    from compton2d_b200.host import Compton2d  # noqa: F401  (fails loudly without the CUDA library)
+    from parity_util import make_gpu
+    from synth import make_problem
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        dist = None
+
+    # weak scaling: nst grows with the GPU count, every rank tracks h = rank (mod world)
+    P = make_problem(nz=16, nr=16, nst=args.nst * world, ngroups=100)
+    per_step = int(P["nsv"].sum()) // world + 1
+    cap = int(per_step * (args.steps + args.warmup + 2) * 1.1) + 1000
+    g = make_gpu(P, sigma_mode=args.sigma_mode, census_capacity=cap, event_capacity=max(per_step // 2, 1000),
+                 device=local, rank=rank, world=world, collision_capacity=1 << 18)
+    g.timing(True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(cyc, e2e):
+        """-> (histories of this rank, device ms of the tracked region, host seconds of the whole call)"""
+        t0 = time.perf_counter()
+        if e2e:
+            g.timing_reset()
+        g.imcgen2d(ncycle=cyc, time=cyc * P["dt"], dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"],
+                   eps_th=P["eps_th"], f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"], f_pair=P["f_pair"],
+                   k_gg=P["k_gg"], nsv=P["nsv"], ewsv=P["ewsv"], Eloss_th=P["Eloss_th"], Eloss_tot=P["Eloss_tot"],
+                   zsurf=P["zsurf"], tbbl=P["tbbl"])
+        if not e2e:
+            g.timing_reset()
+        g.imcfield2d()
+        g.imcvol2d()
+        g.graphics_collect()
+        ms = g.kernel_time(0)[0] + g.kernel_time(1)[0]
+        nl = g.kernel_time(0)[1] + g.kernel_time(1)[1]
+        t = g.tallies() if e2e else None
+        return ms, nl, time.perf_counter() - t0, t
+
+    cyc = 1
+    for _ in range(args.warmup):
+        step(cyc, False); cyc += 1
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- timed: K steps, inputs resident (tables uploaded before the timed bracket of each step)
+    barrier()
+    dev_ms, launches, hist = 0.0, 0, 0
+    wall0 = time.perf_counter()
+    hist_ms = coll_ms = 0.0
+    for _ in range(args.steps):
+        h0 = g.census_count()
+        ms, nl, _, _ = step(cyc, False); cyc += 1
+        hist_ms += g.kernel_time(0)[0]; coll_ms += g.kernel_time(1)[0]
+        dev_ms += ms; launches += nl
+        hist += h0 + (int(P["nsv"].sum()) - rank + world - 1) // world
+    barrier()
+    wall = time.perf_counter() - wall0
+    t_last = g.tallies()
+    # ---- e2e: the same steps through the public call sequence with host buffers: per-step table upload (H2D)
+    #      and tally read-back (D2H) inside the timed region, host wall clock
+    barrier()
+    e_hist, e0 = 0, time.perf_counter()
+    for _ in range(max(1, args.steps // 2)):
+        h0 = g.census_count()
+        step(cyc, True); cyc += 1
+        e_hist += h0 + (int(P["nsv"].sum()) - rank + world - 1) // world
+    barrier()
+    e_wall = time.perf_counter() - e0
+    clocks = sampler.stop() if rank == 0 else None
+
+    red = torch.tensor([dev_ms, wall, e_wall], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([hist, e_hist, launches], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, wall, e_wall = red.tolist()
+    hist_all, e_hist_all, launches_all = cnt.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    c = t_last["counters"]
+    nfl = P["E_field"].size
+    # algorithmic bytes of the history kernel per step on this rank (DESIGN.md "bytes per history"):
+    #   census record read 68 B, census record written 68 B, deposition RMW 2 x 16 B per zone crossing,
+    #   census tallies (npcen, ecens, n_field) 3 x 16 B, escape (erlk, fout, edout RMW + 56 B record)
+    n_in = hist / args.steps - per_step
+    seg = c.get("segments", 0) or 1.5 * (hist / args.steps)
+    bytes_step = 68.0 * n_in + 68.0 * c["ndxout"] + 32.0 * seg + 48.0 * c["ndxout"] + (48.0 + 56.0) * c["nevents"]
+    k_ms = hist_ms / max(1, args.steps)
+    achieved = bytes_step / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    value = hist_all / (dev_ms * 1e-3)
+    h2d = 8 * sum(int(np.asarray(P[k]).size) for k in ("kappa_tot", "eps_tot", "eps_th", "f_nt", "Pnt", "n_e", "tea",
+                                                       "f_pair", "k_gg", "ewsv", "Eloss_th", "Eloss_tot", "zsurf",
+                                                       "tbbl")) + 4 * P["nsv"].size
+    d2h = 8 * (P["nzone"] * (4 + nfl + P["E_gg"].size) + P["gnt"].size * 2 + 32 * (P["hu"].size - 1 + 16) + 64)
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f64", "data": "synthetic", "config": workload_config(args),
+           "histories_per_step": hist_all / args.steps, "trial_flights_per_s": value * 1000,
+           "wall_ms_per_step": 1e3 * wall / args.steps,
+           "e2e": {"value": e_hist_all / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches_all),
+           "kernel_ms_per_step": {"k_history": hist_ms / args.steps, "k_collisions": coll_ms / args.steps},
+           "roofline": {"bound": "hbm", "kernel": "k_history", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                        "frac": achieved / hbm, "traffic": None,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
+                        "bytes_per_step": bytes_step},
+           "counters": c, "clocks": clocks}
+    if not args.no_cpu_baseline and world == 1:
+        r = run_reference_sample(args.cpu_nst, ncores=1, warm=0, timed=2)
+        if r and "error" not in r:
+            out["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": 1, "kind": "reference",
+                                   "sample": f"cycles 1-2 of the prebuilt reference binary, 16x16 zones, 100 groups, nst={args.cpu_nst}, "
+                                             f"{r['histories']} histories in {r['seconds']:.1f} s on 1 worker core"}
+        else:
+            out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "unavailable: " + str(r)[:200]}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nst", type=int, default=20_000_000, help="particles per photon cycle per GPU (nst; sources = nst/2)")
+    ap.add_argument("--sigma-mode", type=int, default=0)
+    ap.add_argument("--ref-nst", type=int, default=6_000, help="--impl reference: nst per instance (census grows every cycle)")
+    ap.add_argument("--cpu-nst", type=int, default=30_000, help="nst of the bounded cpu_baseline sample (cycles 1-2, one core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,565 @@
+// c2d_abi.cu -- the C ABI of include/compton2d_b200.h: context, uploads, step driver, tallies, census I/O.
+// Host code only; the kernels live in c2d_track.cu / c2d_fp.cu.  There is no CPU fallback: every
+// entry point needs the CUDA device the context was created on.
+#include "c2d_ctx.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+namespace c2d {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(C2D_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+static int upload(Ctx *c, double *dst, const double *src, size_t n, double fill = 0.0)
+{
+    if (!src) {
+        std::vector<double> tmp(n, fill);
+        CU(cudaMemcpyAsync(dst, tmp.data(), n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+    }
+    CU(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+static int alloc_bank(Bank &b, size_t cap)
+{
+    CU(cudaMalloc(&b.rpre, cap * 8)); CU(cudaMalloc(&b.zpre, cap * 8)); CU(cudaMalloc(&b.wmu, cap * 8));
+    CU(cudaMalloc(&b.phi, cap * 8)); CU(cudaMalloc(&b.ew, cap * 8)); CU(cudaMalloc(&b.xnu, cap * 8));
+    CU(cudaMalloc(&b.bins, cap * 4)); CU(cudaMalloc(&b.zone, cap * 4)); CU(cudaMalloc(&b.seed, cap * 4));
+    CU(cudaMalloc(&b.sid, cap * 8));
+    return 0;
+}
+static void free_bank(Bank &b)
+{
+    cudaFree(b.rpre); cudaFree(b.zpre); cudaFree(b.wmu); cudaFree(b.phi); cudaFree(b.ew); cudaFree(b.xnu);
+    cudaFree(b.bins); cudaFree(b.zone); cudaFree(b.seed); cudaFree(b.sid);
+    memset(&b, 0, sizeof b);
+}
+
+void Ctx::timer_begin(int which)
+{
+    if (!timing) return;
+    if (ev_pool.size() < ev_used + 2) {
+        cudaEvent_t a, b;
+        cudaEventCreate(&a); cudaEventCreate(&b);
+        ev_pool.push_back(a); ev_pool.push_back(b);
+    }
+    cudaEventRecord(ev_pool[ev_used], stream);
+    ev_which.push_back(which);
+}
+void Ctx::timer_end()
+{
+    if (!timing) return;
+    cudaEventRecord(ev_pool[ev_used + 1], stream);
+    ev_used += 2;
+}
+void Ctx::timer_collect()
+{
+    if (!ev_used) return;
+    cudaStreamSynchronize(stream);
+    for (size_t i = 0; i < ev_used; i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev_pool[i], ev_pool[i + 1]);
+        const int w = ev_which[i / 2];
+        k_ms[w] += ms; k_launches[w]++;
+    }
+    ev_used = 0; ev_which.clear();
+}
+
+// run the scattering work queue dry: every generation of collisions spawns split2 children whose own
+// collisions ('multiple scattering', imctrk2d.f:614) form the next generation
+static int drain_queue(Ctx *c)
+{
+    for (int gen = 0; gen < 1000; gen++) {
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, c->d_qcount + c->q_cur, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (n == 0) return 0;
+        if (n > (unsigned long long)c->q_cap)
+            return fail(C2D_EINVAL, "collision queue overflow: %llu tasks > collision_capacity %lld", n, (long long)c->q_cap);
+        c->q_peak = std::max<long long>(c->q_peak, (long long)n);
+        const int other = c->q_cur ^ 1;
+        CU(cudaMemsetAsync(c->d_qcount + other, 0, 8, c->stream));
+        Params p = c->P;
+        p.q_out = c->d_q[other]; p.q_out_count = c->d_qcount + other;
+        c->timer_begin(1);
+        launch_collisions(p, c->d_q[c->q_cur], (long long)n, c->stream);
+        c->timer_end();
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(c->d_qcount + c->q_cur, 0, 8, c->stream));
+        c->q_cur = other;
+        c->P.q_out = c->d_q[c->q_cur]; c->P.q_out_count = c->d_qcount + c->q_cur;
+    }
+    return fail(C2D_EINVAL, "scattering cascade did not terminate after 1000 generations");
+}
+
+static int check_fatal(Ctx *c)
+{
+    unsigned long long cnt[CNT_N];
+    CU(cudaMemcpyAsync(cnt, c->P.counters, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (cnt[CNT_NDXOUT] > (unsigned long long)c->census_cap)
+        return fail(C2D_ECENSUS, "too many photons: census needs %llu records, capacity %lld (imctrk2d.f:581-585)",
+                    cnt[CNT_NDXOUT], (long long)c->census_cap);
+    if (cnt[CNT_FATAL]) return fail(C2D_EINVAL, "device reported %llu fatal conditions (queue overflow or scat_flag=0 collision)", cnt[CNT_FATAL]);
+    return 0;
+}
+
+}  // namespace c2d
+
+using namespace c2d;
+
+extern "C" {
+
+const char *c2d_last_error(void) { return g_err; }
+int c2d_version(void) { return 100; }
+
+int c2d_create(c2d_ctx **out, int device)
+{
+    if (!out) return fail(C2D_EINVAL, "ctx pointer is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(C2D_ENODEV, "no CUDA device: compton2d_b200 has no CPU path");
+    if (device < 0 || device >= ndev) return fail(C2D_ENODEV, "device %d out of range (%d visible)", device, ndev);
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(C2D_ENODEV, "device %d is sm_%d%d; this library is built for sm_100a (B200)", device, prop.major, prop.minor);
+    CU(cudaSetDevice(device));
+    Ctx *c = new Ctx();
+    c->device = device;
+    c->n_sm = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = reinterpret_cast<c2d_ctx *>(c);
+    return 0;
+}
+
+int c2d_destroy(c2d_ctx *h)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_f64); cudaFree(c->d_i64);
+    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_qcount); cudaFree(c->d_sig);
+    cudaFree(c->d_sigS);
+    free_bank(c->bank[0]); free_bank(c->bank[1]);
+    c->fp_free();
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+int c2d_init(c2d_ctx *h, const c2d_dims *d)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !d) return fail(C2D_EINVAL, "NULL argument");
+    if (c->inited) return fail(C2D_ESTATE, "context already initialised");
+    if (d->cr_sent != 0) return fail(C2D_EINVAL, "cr_sent = %d: Compton reflection (imcleak2d.f:107-165,216-273) is not built", d->cr_sent);
+    if (d->nz < 1 || d->nr < 1 || d->nz > 65535 || d->nr > 65535) return fail(C2D_EINVAL, "bad grid %d x %d", d->nz, d->nr);
+    if (d->nmu < 1 || d->nmu > C2D_NMUMAX || d->nph_lc < 0 || d->nph_lc > C2D_NLCMAX || d->nphtotal < 1 || d->nphtotal > 65535)
+        return fail(C2D_EINVAL, "bad bin counts nmu=%d nph_lc=%d nphtotal=%d", d->nmu, d->nph_lc, d->nphtotal);
+    if (d->n_vol < 2 || d->num_nt < 3 || d->nphfield < 2 || d->n_gg < 2) return fail(C2D_EINVAL, "bad table sizes");
+    if (d->split1 < 1 || d->split2 < 1 || d->split3 < 1) return fail(C2D_EINVAL, "split factors must be >= 1");
+    if (!d->z || !d->r || !d->E_ph || !d->E_field || !d->gnt || !d->hu || !d->mu) return fail(C2D_EINVAL, "missing static table");
+    CU(cudaSetDevice(c->device));
+    c->dims = *d;
+    const int nzone = d->nz * d->nr;
+    c->nzone = nzone;
+    c->census_cap = std::max<int64_t>(d->census_capacity, 1);
+    c->event_cap = std::max<int64_t>(d->event_capacity, 1);
+    c->q_cap = std::max<int64_t>(d->collision_capacity, 1024);
+
+    // ---- static tables, one blob
+    std::vector<double> hs;
+    auto put = [&](const double *src, int n, double fill = 0.0) {
+        size_t off = hs.size();
+        for (int i = 0; i < n; i++) hs.push_back(src ? src[i] : fill);
+        while (hs.size() % 2) hs.push_back(0.0);
+        return off;
+    };
+    const size_t o_z = put(d->z, d->nz), o_r = put(d->r, d->nr), o_Eph = put(d->E_ph, d->n_vol);
+    const size_t o_Ef = put(d->E_field, d->nphfield), o_Egg = put(d->E_gg, d->n_gg), o_gnt = put(d->gnt, d->num_nt);
+    std::vector<double> gam0(d->num_nt), beta(d->num_nt), dgam(d->num_nt, 0.0);
+    for (int i = 0; i < d->num_nt; i++) {
+        gam0[i] = d->gnt[i] + 1.0;                                   // comtot2d.f:223-224
+        beta[i] = std::sqrt(1.0 - 1.0 / (gam0[i] * gam0[i]));
+        if (i + 1 < d->num_nt) dgam[i] = d->gnt[i + 1] - d->gnt[i];
+    }
+    const size_t o_g0 = put(gam0.data(), d->num_nt), o_be = put(beta.data(), d->num_nt), o_dg = put(dgam.data(), d->num_nt);
+    const size_t o_hu = put(d->hu, d->nphtotal + 1);
+    const size_t o_lmin = put(d->Elcmin, d->nph_lc), o_lmax = put(d->Elcmax, d->nph_lc), o_mu = put(d->mu, d->nmu);
+    CU(cudaMalloc(&c->d_static, hs.size() * 8));
+    CU(cudaMemcpy(c->d_static, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
+    c->h_gnt.assign(d->gnt, d->gnt + d->num_nt);
+    c->h_Efield.assign(d->E_field, d->E_field + d->nphfield);
+    c->h_z.assign(d->z, d->z + d->nz); c->h_r.assign(d->r, d->r + d->nr);
+
+    // ---- per-step tables, one blob
+    size_t n = 0;
+    auto take = [&](size_t cnt) { size_t o = n; n += (cnt + 1) & ~size_t(1); return o; };
+    c->o_kappa = take((size_t)nzone * d->n_vol); c->o_epstot = take((size_t)nzone * d->n_vol);
+    c->o_epsth = take((size_t)nzone * d->n_vol); c->o_fnt = take((size_t)nzone * d->num_nt);
+    c->o_pnt = take((size_t)nzone * d->num_nt); c->o_ne = take(nzone); c->o_fpair = take(nzone);
+    c->o_kgg = take((size_t)nzone * d->n_gg); c->o_tbbl = take(d->nr); c->o_ewsv = take(nzone);
+    c->o_elth = take(nzone); c->o_eltot = take(nzone); c->o_zsurf = take(nzone); c->o_tea = take(nzone);
+    c->n_step = n;
+    CU(cudaMalloc(&c->d_step, n * 8));
+    CU(cudaMemset(c->d_step, 0, n * 8));
+    CU(cudaMalloc(&c->d_prefix, (size_t)(nzone + 1) * 8));
+
+    // ---- tallies: one packed FP64 buffer + one packed int64 buffer (one all-reduce each)
+    n = 0;
+    c->t_edep = take(nzone); c->t_prdep = take(nzone); c->t_ecens = take(nzone);
+    c->t_nfield = take((size_t)nzone * d->nphfield); c->t_nph = take((size_t)nzone * d->n_gg);
+    c->t_EIC = take(d->num_nt); c->t_fout = take((size_t)C2D_NMUMAX * d->nphtotal);
+    c->t_edout = take((size_t)C2D_NMUMAX * C2D_NLCMAX);
+    c->t_erlki = take(d->nz); c->t_erlko = take(d->nz); c->t_erlku = take(d->nr); c->t_erlkl = take(d->nr);
+    c->t_Edin = take(d->nr); c->t_Edref = take(d->nr);
+    c->n_f64 = n;
+    CU(cudaMalloc(&c->d_f64, n * 8));
+    CU(cudaMemset(c->d_f64, 0, n * 8));
+    c->i_npcen = 0; c->i_nel = nzone; c->i_cnt = nzone + d->num_nt + 2;
+    c->n_i64 = c->i_cnt + CNT_N;
+    CU(cudaMalloc(&c->d_i64, c->n_i64 * 8));
+    CU(cudaMemset(c->d_i64, 0, c->n_i64 * 8));
+
+    // ---- banks, events, collision queues
+    for (int b = 0; b < 2; b++) { int rc = alloc_bank(c->bank[b], c->census_cap); if (rc) return rc; }
+    CU(cudaMalloc(&c->d_events, (size_t)c->event_cap * 7 * 8));
+    for (int b = 0; b < 2; b++) CU(cudaMalloc(&c->d_q[b], (size_t)c->q_cap * sizeof(CollTask)));
+    CU(cudaMalloc(&c->d_qcount, 16));
+    CU(cudaMemset(c->d_qcount, 0, 16));
+
+    Params &P = c->P;
+    memset(&P, 0, sizeof P);
+    P.nz = d->nz; P.nr = d->nr; P.nzone = nzone; P.n_vol = d->n_vol; P.num_nt = d->num_nt; P.nphfield = d->nphfield;
+    P.n_gg = d->n_gg; P.nphtotal = d->nphtotal; P.nph_lc = d->nph_lc; P.nmu = d->nmu;
+    P.pair_switch = d->pair_switch; P.spec_switch = d->spec_switch;
+    P.split1 = d->split1; P.split2 = d->split2; P.split3 = d->split3; P.spl3_trg = d->spl3_trg;
+    P.sigma_mode = d->sigma_mode;
+    P.key0 = d->rseed; P.rmin = d->rmin; P.zmin = d->zmin;
+    const double *S = c->d_static;
+    P.z = S + o_z; P.r = S + o_r; P.E_ph = S + o_Eph; P.E_field = S + o_Ef; P.E_gg = S + o_Egg; P.gnt = S + o_gnt;
+    P.gam0 = S + o_g0; P.beta = S + o_be; P.dgam = S + o_dg; P.hu = S + o_hu; P.Elcmin = S + o_lmin; P.Elcmax = S + o_lmax;
+    P.mu = S + o_mu;
+    const double *T = c->d_step;
+    P.kappa_tot = T + c->o_kappa; P.eps_tot = T + c->o_epstot; P.eps_th = T + c->o_epsth; P.f_nt = T + c->o_fnt;
+    P.Pnt = T + c->o_pnt; P.n_e = T + c->o_ne; P.f_pair = T + c->o_fpair; P.k_gg = T + c->o_kgg; P.tbbl = T + c->o_tbbl;
+    P.ewsv = T + c->o_ewsv; P.Eloss_th = T + c->o_elth; P.Eloss_tot = T + c->o_eltot; P.zsurf = T + c->o_zsurf;
+    P.nsv_prefix = c->d_prefix;
+    double *F = c->d_f64;
+    P.edep = F + c->t_edep; P.prdep = F + c->t_prdep; P.ecens = F + c->t_ecens; P.n_field = F + c->t_nfield;
+    P.n_ph = F + c->t_nph; P.E_IC = F + c->t_EIC; P.fout = F + c->t_fout; P.edout = F + c->t_edout;
+    P.erlki = F + c->t_erlki; P.erlko = F + c->t_erlko; P.erlku = F + c->t_erlku; P.erlkl = F + c->t_erlkl;
+    P.Ed_in = F + c->t_Edin; P.Ed_ref = F + c->t_Edref;
+    P.npcen = c->d_i64 + c->i_npcen; P.nelectron = c->d_i64 + c->i_nel; P.counters = c->d_i64 + c->i_cnt;
+    c->cur_out = 0;
+    P.out = c->bank[0]; P.in = c->bank[1];
+    P.census_cap = c->census_cap; P.events = c->d_events; P.event_cap = c->event_cap;
+    c->q_cur = 0;
+    P.q_out = c->d_q[0]; P.q_out_count = c->d_qcount; P.q_cap = c->q_cap;
+    c->n_census = 0;
+
+    if (d->sigma_mode == 1) { int rc = c->sigma_setup(); if (rc) return rc; }
+    c->inited = true;
+    return 0;
+}
+
+int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !in) return fail(C2D_EINVAL, "NULL argument");
+    if (!c->inited) return fail(C2D_ESTATE, "c2d_init has not been called");
+    CU(cudaSetDevice(c->device));
+    const c2d_dims &d = c->dims;
+    const int nzone = c->nzone;
+    if (!in->kappa_tot || !in->f_nt || !in->Pnt || !in->n_e) return fail(C2D_EINVAL, "missing per-step table");
+    if (!(in->dt >= 0.0)) return fail(C2D_EINVAL, "dt = %g", in->dt);
+    // the photon count in flight: take over what the previous step wrote
+    {
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, c->P.counters + CNT_NDXOUT, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->n_census = (int64_t)std::min<unsigned long long>(n, (unsigned long long)c->census_cap);
+    }
+    double *T = c->d_step;
+    int rc = 0;
+    rc |= upload(c, T + c->o_kappa, in->kappa_tot, (size_t)nzone * d.n_vol);
+    rc |= upload(c, T + c->o_epstot, in->eps_tot, (size_t)nzone * d.n_vol);
+    rc |= upload(c, T + c->o_epsth, in->eps_th, (size_t)nzone * d.n_vol);
+    rc |= upload(c, T + c->o_fnt, in->f_nt, (size_t)nzone * d.num_nt);
+    rc |= upload(c, T + c->o_pnt, in->Pnt, (size_t)nzone * d.num_nt);
+    rc |= upload(c, T + c->o_ne, in->n_e, nzone);
+    rc |= upload(c, T + c->o_fpair, in->f_pair, nzone);
+    rc |= upload(c, T + c->o_kgg, in->k_gg, (size_t)nzone * d.n_gg);
+    rc |= upload(c, T + c->o_tbbl, in->tbbl, d.nr);
+    rc |= upload(c, T + c->o_ewsv, in->ewsv, nzone);
+    rc |= upload(c, T + c->o_elth, in->Eloss_th, nzone);
+    rc |= upload(c, T + c->o_eltot, in->Eloss_tot, nzone, 1.0);
+    rc |= upload(c, T + c->o_zsurf, in->zsurf, nzone, 1.0);
+    rc |= upload(c, T + c->o_tea, in->tea, nzone);
+    if (rc) return rc;
+    c->h_prefix.assign(nzone + 1, 0);
+    for (int zi = 0; zi < nzone; zi++) {
+        const int nsv = in->nsv ? in->nsv[zi] : 0;
+        if (nsv < 0) return fail(C2D_EINVAL, "nsv[%d] = %d", zi, nsv);
+        c->h_prefix[zi + 1] = c->h_prefix[zi] + nsv;
+    }
+    CU(cudaMemcpyAsync(c->d_prefix, c->h_prefix.data(), (size_t)(nzone + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    // zero the per-step tallies (imcgen2d.f:87-104,534-551,559-601)
+    CU(cudaMemsetAsync(c->d_f64, 0, c->n_f64 * 8, c->stream));
+    CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
+    // census: last step's output bank becomes this step's input (no 360 MB copy as in imcfield2d.f:96-97)
+    c->cur_out ^= 1;
+    c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
+    c->P.ncycle = in->ncycle; c->P.key1 = (uint32_t)in->ncycle; c->P.dt = in->dt; c->P.time = in->time;
+    c->field_done = false; c->vol_next = 0;
+    if (d.sigma_mode == 1) { rc = c->sigma_build(); if (rc) return rc; }
+    CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its host arrays
+    c->step_open = true;
+    return 0;
+}
+
+int c2d_imcfield(c2d_ctx *h)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
+    if (c->field_done) return fail(C2D_ESTATE, "c2d_imcfield called twice in one step");
+    CU(cudaSetDevice(c->device));
+    c->field_done = true;
+    c->timer_begin(0);
+    launch_history_census(c->P, 0, c->n_census, 1, c->stream);
+    c->timer_end();
+    CU(cudaGetLastError());
+    c->histories += c->n_census;
+    c->n_census = 0;
+    return drain_queue(c);
+}
+
+int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
+    CU(cudaSetDevice(c->device));
+    const int64_t total = c->h_prefix.back();
+    if (stride < 1 || first < 0) return fail(C2D_EINVAL, "bad shard first=%lld stride=%lld", (long long)first, (long long)stride);
+    int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
+    if (count < 0 || count > avail) count = avail;
+    const int64_t chunk = (int64_t)1 << 30;
+    for (int64_t done = 0; done < count; done += chunk) {
+        const int64_t n = std::min(chunk, count - done);
+        c->timer_begin(0);
+        launch_history_volume(c->P, first + done * stride, n, stride, c->stream);
+        c->timer_end();
+        CU(cudaGetLastError());
+    }
+    c->histories += count;
+    return drain_queue(c);
+}
+
+int c2d_sync(c2d_ctx *h)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    CU(cudaSetDevice(c->device));
+    int rc = drain_queue(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return check_fatal(c);
+}
+
+int c2d_tally_device(c2d_ctx *h, double **f, int64_t *nf, int64_t **i, int64_t *ni)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (f) *f = c->d_f64;
+    if (nf) *nf = (int64_t)c->n_f64;
+    if (i) *i = reinterpret_cast<int64_t *>(c->d_i64);
+    if (ni) *ni = (int64_t)c->n_i64;
+    return 0;
+}
+
+int c2d_tally_read(c2d_ctx *h, c2d_tallies *t)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited || !t) return fail(C2D_ESTATE, "context not initialised");
+    CU(cudaSetDevice(c->device));
+    c->h_f64.resize(c->n_f64); c->h_i64.resize(c->n_i64);
+    CU(cudaMemcpyAsync(c->h_f64.data(), c->d_f64, c->n_f64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_i64.data(), c->d_i64, c->n_i64 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const c2d_dims &d = c->dims;
+    const int nzone = c->nzone;
+    auto cp = [&](double *dst, size_t off, size_t n) { if (dst) memcpy(dst, c->h_f64.data() + off, n * 8); };
+    cp(t->edep, c->t_edep, nzone); cp(t->prdep, c->t_prdep, nzone); cp(t->ecens, c->t_ecens, nzone);
+    cp(t->n_field, c->t_nfield, (size_t)nzone * d.nphfield); cp(t->n_ph, c->t_nph, (size_t)nzone * d.n_gg);
+    cp(t->E_IC, c->t_EIC, d.num_nt); cp(t->fout, c->t_fout, (size_t)C2D_NMUMAX * d.nphtotal);
+    cp(t->edout, c->t_edout, (size_t)C2D_NMUMAX * C2D_NLCMAX);
+    cp(t->erlki, c->t_erlki, d.nz); cp(t->erlko, c->t_erlko, d.nz); cp(t->erlku, c->t_erlku, d.nr);
+    cp(t->erlkl, c->t_erlkl, d.nr); cp(t->Ed_in, c->t_Edin, d.nr); cp(t->Ed_ref, c->t_Edref, d.nr);
+    if (t->npcen) memcpy(t->npcen, c->h_i64.data() + c->i_npcen, (size_t)nzone * 8);
+    if (t->nelectron) memcpy(t->nelectron, c->h_i64.data() + c->i_nel, (size_t)(d.num_nt + 2) * 8);
+    for (int k = 0; k < 16; k++) t->counters[k] = (k < CNT_N) ? (int64_t)c->h_i64[c->i_cnt + k] : 0;
+    t->counters[C2D_CNT_QPEAK] = c->q_peak;
+    return 0;
+}
+
+int c2d_census_count(c2d_ctx *h, int64_t *n)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited || !n) return fail(C2D_ESTATE, "context not initialised");
+    CU(cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->P.counters + CNT_NDXOUT, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n = (int64_t)v;
+    return 0;
+}
+
+int c2d_census_export(c2d_ctx *h, double *dbuf, int32_t *ibuf, uint64_t *sid, int64_t cap, int64_t *n_out)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    int64_t n = 0;
+    int rc = c2d_census_count(h, &n);
+    if (rc) return rc;
+    if (n > c->census_cap) return fail(C2D_ECENSUS, "too many photons: %lld > %lld", (long long)n, (long long)c->census_cap);
+    if (n_out) *n_out = n;
+    if (n > cap) return fail(C2D_EINVAL, "export buffer holds %lld records, census has %lld", (long long)cap, (long long)n);
+    if (n == 0) return 0;
+    const Bank &b = c->bank[c->cur_out];
+    std::vector<double> col(n);
+    const double *cols[6] = {b.rpre, b.zpre, b.wmu, b.phi, b.ew, b.xnu};
+    if (dbuf)
+        for (int k = 0; k < 6; k++) {
+            CU(cudaMemcpy(col.data(), cols[k], n * 8, cudaMemcpyDeviceToHost));
+            for (int64_t i = 0; i < n; i++) dbuf[6 * i + k] = col[i];
+        }
+    if (ibuf) {
+        std::vector<uint32_t> bins(n), zone(n);
+        std::vector<int32_t> seed(n);
+        CU(cudaMemcpy(bins.data(), b.bins, n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(zone.data(), b.zone, n * 4, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(seed.data(), b.seed, n * 4, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; i++) {
+            ibuf[6 * i + 0] = bins[i] & 0xFFFF; ibuf[6 * i + 1] = (bins[i] >> 16) & 0xFF; ibuf[6 * i + 2] = bins[i] >> 24;
+            ibuf[6 * i + 3] = zone[i] & 0xFFFF; ibuf[6 * i + 4] = zone[i] >> 16; ibuf[6 * i + 5] = seed[i];
+        }
+    }
+    if (sid) CU(cudaMemcpy(sid, b.sid, n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int c2d_census_import(c2d_ctx *h, const double *dbuf, const int32_t *ibuf, const uint64_t *sid, int64_t n)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (n < 0 || n > c->census_cap) return fail(C2D_ECENSUS, "too many photons needed to read: %lld > %lld (imcfield2d.f:84-86)", (long long)n, (long long)c->census_cap);
+    if (n && (!dbuf || !ibuf)) return fail(C2D_EINVAL, "NULL census buffers");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    Bank &b = c->bank[c->cur_out];
+    if (n) {
+        std::vector<double> col(n);
+        double *cols[6] = {b.rpre, b.zpre, b.wmu, b.phi, b.ew, b.xnu};
+        for (int k = 0; k < 6; k++) {
+            for (int64_t i = 0; i < n; i++) col[i] = dbuf[6 * i + k];
+            CU(cudaMemcpy(cols[k], col.data(), n * 8, cudaMemcpyHostToDevice));
+        }
+        std::vector<uint32_t> bins(n), zone(n);
+        std::vector<int32_t> seed(n);
+        std::vector<uint64_t> sd(n);
+        for (int64_t i = 0; i < n; i++) {
+            bins[i] = (uint32_t)ibuf[6 * i] | ((uint32_t)ibuf[6 * i + 1] << 16) | ((uint32_t)ibuf[6 * i + 2] << 24);
+            zone[i] = (uint32_t)ibuf[6 * i + 3] | ((uint32_t)ibuf[6 * i + 4] << 16);
+            seed[i] = ibuf[6 * i + 5];
+            // without a replay id (a census written by the reference), derive one from the record's seed and slot
+            sd[i] = sid ? sid[i] : (0x63656E73ull << 32 | (uint64_t)i) * 0x9E3779B97F4A7C15ull + (uint64_t)(uint32_t)ibuf[6 * i + 5];
+        }
+        CU(cudaMemcpy(b.bins, bins.data(), n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(b.zone, zone.data(), n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(b.seed, seed.data(), n * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(b.sid, sd.data(), n * 8, cudaMemcpyHostToDevice));
+    }
+    unsigned long long v = (unsigned long long)n;
+    CU(cudaMemcpy(c->P.counters + CNT_NDXOUT, &v, 8, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int c2d_events_drain(c2d_ctx *h, c2d_event *buf, int64_t cap, int64_t *n_out)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    CU(cudaSetDevice(c->device));
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->P.counters + CNT_NEVENTS, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (n_out) *n_out = (int64_t)v;
+    const int64_t stored = std::min<int64_t>((int64_t)v, c->event_cap);
+    const int64_t n = std::min<int64_t>(stored, cap);
+    if (n && buf) CU(cudaMemcpy(buf, c->d_events, (size_t)n * 7 * 8, cudaMemcpyDeviceToHost));
+    if ((int64_t)v > c->event_cap) return fail(C2D_EEVENTS, "%llu escape records produced, event_capacity %lld", v, (long long)c->event_cap);
+    return 0;
+}
+
+int c2d_kernel_time_ms(c2d_ctx *h, int which, float *ms, int64_t *launches)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c) return fail(C2D_EINVAL, "NULL ctx");
+    if (which == -1) { c->timing = true; return 0; }          // enable
+    if (which == -2) { c->timer_collect(); for (int k = 0; k < 8; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return 0; }   // reset
+    if (which < 0 || which >= 8) return fail(C2D_EINVAL, "kernel family %d", which);
+    c->timer_collect();
+    if (ms) *ms = (float)c->k_ms[which];
+    if (launches) *launches = c->k_launches[which];
+    return 0;
+}
+
+void c2d_pack_bin_first(const double *common, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *dense)
+{   // COMMON a(nbin_pad, jmax, kmax) column-major -> dense [zone][bin]
+    (void)kmax;
+    for (int j = 0; j < nz; j++)
+        for (int k = 0; k < nr; k++)
+            for (int i = 0; i < nbin; i++)
+                dense[((size_t)j * nr + k) * nbin + i] = common[((size_t)k * jmax + j) * nbin_pad + i];
+}
+void c2d_pack_bin_last(const double *common, int jmax, int kmax, int nbin, int nz, int nr, double *dense)
+{   // COMMON a(jmax, kmax, nbin) column-major -> dense [zone][bin]
+    for (int j = 0; j < nz; j++)
+        for (int k = 0; k < nr; k++)
+            for (int i = 0; i < nbin; i++)
+                dense[((size_t)j * nr + k) * nbin + i] = common[((size_t)i * kmax + k) * jmax + j];
+}
+void c2d_unpack_bin_first(const double *dense, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *common)
+{
+    (void)kmax;
+    for (int j = 0; j < nz; j++)
+        for (int k = 0; k < nr; k++)
+            for (int i = 0; i < nbin; i++)
+                common[((size_t)k * jmax + j) * nbin_pad + i] = dense[((size_t)j * nr + k) * nbin + i];
+}
+void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int nz, int nr, double *common)
+{
+    for (int j = 0; j < nz; j++)
+        for (int k = 0; k < nr; k++)
+            for (int i = 0; i < nbin; i++)
+                common[((size_t)i * kmax + k) * jmax + j] = dense[((size_t)j * nr + k) * nbin + i];
+}
+
+}  // extern "C"

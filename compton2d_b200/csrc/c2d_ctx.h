@@ -1,0 +1,59 @@
+// c2d_ctx.h -- the context behind the opaque c2d_ctx handle (host side)
+#pragma once
+#include <vector>
+
+#include "../../include/compton2d_b200.h"
+#include "c2d_host.h"
+
+namespace c2d {
+
+int fail(int code, const char *fmt, ...);
+
+struct FpState;
+
+struct Ctx {
+    int device = 0, n_sm = 0;
+    cudaStream_t stream = nullptr;
+    c2d_dims dims{};
+    int nzone = 0;
+    bool inited = false, step_open = false, field_done = false;
+    int64_t census_cap = 0, event_cap = 0, q_cap = 0, n_census = 0, vol_next = 0, histories = 0;
+    long long q_peak = 0;
+    // device memory
+    double *d_static = nullptr, *d_step = nullptr, *d_f64 = nullptr, *d_events = nullptr;
+    double *d_sig = nullptr, *d_sigS = nullptr;
+    int64_t *d_prefix = nullptr;
+    unsigned long long *d_i64 = nullptr, *d_qcount = nullptr;
+    CollTask *d_q[2] = {nullptr, nullptr};
+    Bank bank[2]{};
+    int cur_out = 0, q_cur = 0;
+    // offsets (in doubles) into d_step / d_f64, (in int64) into d_i64
+    size_t o_kappa = 0, o_epstot = 0, o_epsth = 0, o_fnt = 0, o_pnt = 0, o_ne = 0, o_fpair = 0, o_kgg = 0, o_tbbl = 0,
+           o_ewsv = 0, o_elth = 0, o_eltot = 0, o_zsurf = 0, o_tea = 0, n_step = 0;
+    size_t t_edep = 0, t_prdep = 0, t_ecens = 0, t_nfield = 0, t_nph = 0, t_EIC = 0, t_fout = 0, t_edout = 0, t_erlki = 0,
+           t_erlko = 0, t_erlku = 0, t_erlkl = 0, t_Edin = 0, t_Edref = 0, n_f64 = 0;
+    size_t i_npcen = 0, i_nel = 0, i_cnt = 0, n_i64 = 0;
+    Params P{};
+    std::vector<int64_t> h_prefix;
+    std::vector<double> h_f64, h_gnt, h_Efield, h_z, h_r;
+    std::vector<unsigned long long> h_i64;
+    // sigma(zone, E) table (sigma_mode 1)
+    int n_sig = 0;
+    int sigma_setup();
+    int sigma_build();
+    // Fokker-Planck state (c2d_fp.cu)
+    FpState *fp = nullptr;
+    void fp_free();
+    // CUDA-event timing per kernel family: 0 history, 1 collisions, 2 sigma table, 3 FP, 4 tally bench
+    bool timing = false;
+    std::vector<cudaEvent_t> ev_pool;
+    std::vector<int> ev_which;
+    size_t ev_used = 0;
+    double k_ms[8] = {0};
+    int64_t k_launches[8] = {0};
+    void timer_begin(int which);
+    void timer_end();
+    void timer_collect();
+};
+
+}  // namespace c2d

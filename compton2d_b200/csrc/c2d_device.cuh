@@ -1,0 +1,695 @@
+// c2d_device.cuh -- device-side physics of the Compton2d hot path for sm_100a.
+//
+// One thread owns one photon history; every random number is a pure function of
+// (rseed, ncycle, stream id, draw index) through Philox-4x32-10, where the stream id encodes the
+// history's ancestry (source zone/index -> trial -> scattered child ...), so results do not depend
+// on thread scheduling, launch geometry or GPU count.
+//
+// Reference parity (file:line relative to /root/reference/src_20121026/):
+//   fly<MODE>()      imctrk2d.f:158-586   one flight from label 110 to census / leak / collision
+//   sigma_kn_bins()  comtot2d.f:219-247   angle-averaged K-N cross section per electron bin
+//   dilog_neg()      comtot2d.f:356-433   CERNLIB C332 dilogarithm (argument -x, x > 0)
+//   compb2d()        compb_2d.f:1-318     one Compton scattering
+//   nth2d()          nontherm2d.f:159-183 electron draw from Pnt
+//   imcleak()        imcleak2d.f:2-320    boundary tallies + escape record (cr_sent = 0)
+//   source_volume()  imcvol2d_para.f:157-389
+// The arithmetic follows the reference expression by expression (REAL*4 literals included) so that
+// integer outcomes replay exactly against the CPU oracle; compile with -fmad=false.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace c2d {
+
+constexpr double kPi = 3.1415926536e0;        // general.pa:25
+constexpr double kRadCp = 3.333564097e-11;    // general.pa:24
+constexpr double kCLight = 2.9979245620e10;   // general.pa:26
+constexpr int kMaxSeg = 12;                   // zone crossings held by the fast path of one history
+constexpr int kNmuMax = 32;
+constexpr int kNlcMax = 16;
+
+constexpr uint64_t kTagTrials = 0xA1ull;
+constexpr uint64_t kTagF0 = 0xF0ull;
+constexpr uint64_t kTagVol = 0x766F6Cull;
+
+enum { MODE_PRE = 2, MODE_TRIAL = -1, MODE_TRIAL_SLOW = -2, MODE_F0 = 0, MODE_CHILD = 1 };
+enum { END_KILLED = 0, END_CENSUS = 1, END_LEAK = 2, END_DROPPED = 3, END_COLLISION = 4, END_LOWEW = 5,
+       END_OVERFLOW = 6, END_FATAL = 7 };
+enum { CNT_NDXOUT = 0, CNT_CMCOUNT1, CNT_CMCOUNT2, CNT_LKCOUNT, CNT_NEVENTS, CNT_HISTORIES, CNT_TRIALS,
+       CNT_MULTIPLE, CNT_KILLED, CNT_SEGOVF, CNT_LITERAL, CNT_QPEAK, CNT_FATAL, CNT_SEGMENTS, CNT_PAD1, CNT_PAD2, CNT_N };   // CNT_N == 16
+
+struct Photon {
+    double xnu, wmu, phi, rpre, zpre, dcen, ew;
+    int jph, kph, jgpsp, jgplc, jgpmu;
+};
+
+struct CollTask {            // a Compton collision waiting for its split2 children (imctrk2d.f:588-689)
+    Photon p;
+    int pad;
+    uint64_t sid;            // stream of the flight that collided
+};
+
+struct Bank {                // census bank, SoA (commonblock.f:8,72 dbuf/ibuf record, imctrk2d.f:566-580)
+    double *rpre, *zpre, *wmu, *phi, *ew, *xnu;
+    uint32_t *bins;          // jgpsp | jgplc << 16 | jgpmu << 24
+    uint32_t *zone;          // jph | kph << 16
+    int32_t *seed;
+    uint64_t *sid;
+};
+
+struct Seg {                 // one zone crossing of the collision-free ray of a history
+    int zi;
+    double sigsc, sigabs, L, trldb, dcen, ew, dele, rpre;
+};
+
+struct Params {
+    int nz, nr, nzone, n_vol, num_nt, nphfield, n_gg, nphtotal, nph_lc, nmu;
+    int pair_switch, spec_switch, split1, split2, split3, spl3_trg, ncycle, sigma_mode;
+    uint32_t key0, key1;
+    double rmin, zmin, dt, time;
+    // static tables
+    const double *z, *r, *E_ph, *E_field, *E_gg, *gnt, *gam0, *beta, *dgam, *hu, *Elcmin, *Elcmax, *mu;
+    // per-step tables
+    const double *kappa_tot, *eps_tot, *eps_th, *f_nt, *Pnt, *n_e, *f_pair, *k_gg, *tbbl;
+    const double *ewsv, *Eloss_th, *Eloss_tot, *zsurf;
+    const int64_t *nsv_prefix;         // [nzone+1]
+    const double *sig_table;           // sigma_mode 1: [nzone][n_sig] ln(sigma) on the ln(E) grid
+    int n_sig; double sig_lnE0, sig_inv_dlnE;
+    // tallies
+    double *edep, *prdep, *ecens, *n_field, *n_ph, *E_IC, *fout, *edout, *erlki, *erlko, *erlku, *erlkl,
+        *Ed_in, *Ed_ref;
+    unsigned long long *npcen, *nelectron, *counters;
+    // banks
+    Bank in, out;
+    unsigned long long census_cap;
+    double *events;                    // 7 doubles per record
+    unsigned long long event_cap;
+    CollTask *q_out;                   // collision tasks produced by this launch
+    unsigned long long *q_out_count;
+    unsigned long long q_cap;
+};
+
+// ------------------------------------------------------------------------------------------ RNG
+__device__ __forceinline__ uint64_t mix64(uint64_t a, uint64_t b)
+{
+    uint64_t x = a ^ (b + 0x9E3779B97F4A7C15ull + (a << 6) + (a >> 2));
+    x ^= x >> 33; x *= 0xFF51AFD7ED558CCDull;
+    x ^= x >> 33; x *= 0xC4CEB9FE1A85EC53ull;
+    x ^= x >> 33;
+    return x;
+}
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&o)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
+}
+
+__device__ __forceinline__ double u52(uint32_t lo, uint32_t hi)
+{   // 52-bit uniform in (0,1): ((w >> 12) + 0.5) * 2^-52, exactly representable
+    const uint64_t w = ((uint64_t)hi << 32) | lo;
+    return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+// draw d of stream sid = word pair (d & 1) of philox(ctr = (sid_lo, sid_hi, d >> 1, 0))
+__device__ __forceinline__ double rng_uniform(const Params &p, uint64_t sid, uint32_t d)
+{
+    uint32_t o[4];
+    philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), d >> 1, 0u, p.key0, p.key1, o);
+    return (d & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
+}
+
+struct Rng {
+    uint64_t sid;
+    uint32_t d;
+    __device__ __forceinline__ void stream(uint64_t s) { sid = s; d = 0; }
+    __device__ __forceinline__ double next(const Params &p) { return rng_uniform(p, sid, d++); }
+};
+
+// ------------------------------------------------------------------------------------------ small helpers
+__device__ __forceinline__ void atomic_add_f64(double *a, double v) { atomicAdd(a, v); }
+__device__ __forceinline__ void count(const Params &p, int which, unsigned long long n = 1ull)
+{
+    atomicAdd(p.counters + which, n);
+}
+
+#define C2D_CLAMP8(v) do { if ((v) > 9.9999999e-1) (v) = 9.9999999e-1; if ((v) < -9.9999999e-1) (v) = -9.9999999e-1; } while (0)
+
+// first index i in [1, n-1] with x < E[i] (0-based E), else n  == the linear scans of imctrk2d.f:387-389,555-557
+__device__ __forceinline__ int scan_lt(const double *E, int n, double x)
+{
+    int lo = 1, hi = n;               // answer in [1, n]
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (x < E[mid]) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// spectrum group: compb_2d.f:249-274 / imcleak2d.f:345-370 / imcvol2d_para.f:334-359
+__device__ __forceinline__ int sp_group(const Params &p, double x, double hubot_f, double hutop_f, int top_value)
+{
+    int jbot = 1, jtop = p.nphtotal + 1, jmid;
+    const double hubot = hubot_f * p.hu[0], hutop = hutop_f * p.hu[jtop - 1];
+    if (x >= hutop) return top_value;
+    if (x <= hubot) return 0;
+    for (;;) {
+        jmid = (jbot + jtop) / 2;
+        if (jmid == jbot) break;
+        const double h = p.hu[jmid - 1];
+        if (x == h) break;
+        if (x < h) jtop = jmid; else jbot = jmid;
+    }
+    return jmid;
+}
+__device__ __forceinline__ int lc_group(const Params &p, double x)
+{
+    for (int m = 1; m <= p.nph_lc; m++)
+        if (x > p.Elcmin[m - 1] && x <= p.Elcmax[m - 1]) return m;
+    return 0;
+}
+__device__ __forceinline__ int mu_group(const Params &p, double w)
+{
+    for (int n = 1; n <= p.nmu; n++)
+        if (w <= p.mu[n - 1]) return n;
+    return p.nmu;
+}
+
+// ------------------------------------------------------------------------------------------ comtot
+// comtot2d.f:356-433 for argument -x with x > 0 (the only call pattern: intg_v -> dilog(-x))
+__device__ __forceinline__ double dilog_neg(double x)
+{
+    const double C[20] = {0.42996693560813697e0, 0.40975987533077105e0,
+        -0.01858843665014592e0, 0.00145751084062268e0, -0.00014304184442340e0,
+        0.1588415541880e-4, -0.190784959387e-5, 0.024195180854e-5,
+        -0.003193341274e-5, 0.000434545063e-5, -0.000060578480e-5,
+        0.000008612098e-5, -0.000001244332e-5, 0.000000182256e-5,
+        -0.000000027007e-5, 0.000000004042e-5, -0.000000000610e-5,
+        0.000000000093e-5, -0.000000000014e-5, 0.000000000002e-5};
+    const double PI2 = kPi * kPi, PI6 = PI2 / 6, PI12 = PI2 / 12;
+    if (x == 1.0) return -PI12;                 // dilog(-1)
+    const double T = x;
+    double Y, S, A;
+    if (T <= 1) { Y = T; S = 1; A = 0; }
+    else { Y = 1 / T; S = -1; const double B1 = log(T); A = PI6 + 0.5 * B1 * B1; }
+    const double H = Y + Y - 1, ALFA = H + H;
+    double B0 = 0, B1 = 0, B2 = 0;
+#pragma unroll
+    for (int i = 19; i >= 0; i--) {
+        B0 = C[i] + ALFA * B1 - B2;
+        B2 = B1; B1 = B0;
+    }
+    return -(S * (B0 - H * B2) + A);
+}
+
+// comtot2d.f:337-352
+__device__ __forceinline__ double intg_v(double x)
+{
+    const double intg_1 = -x / 2.0 + 0.5 / (1.0 + x);
+    const double intg_2 = 4.0 * dilog_neg(x);
+    const double intg_3 = (9.0 + x + 8.0 / x) * log(1.0 + x);
+    return (intg_1 + intg_2 + intg_3);
+}
+
+// sigma_E of comtot2d.f:234-239 for electron bin i (0-based) and x = xnu/511
+__device__ __forceinline__ double sigma_kn_bin(const Params &p, int i, double x)
+{
+    const double sigthom = 6.6516e-25;
+    const double gamma0 = p.gam0[i], betta = p.beta[i];
+    if (x * gamma0 * (1 + betta) < 1.e-2) return sigthom * (1.0 - 2.0 * x * gamma0);
+    return 9.375e-2 * sigthom / (gamma0 * gamma0) / betta / (x * x) *
+           (intg_v(2 * gamma0 * (1 + betta) * x) - intg_v(2 * gamma0 * (1 - betta) * x));
+}
+
+// comac for up to four zones at once (one pass over the electron bins): comtot2d.f:219-247
+static __device__ __noinline__ void comtot_zones(const Params &p, double xnu, const int *zi, int nzn, double *comac)
+{
+    const double x = xnu / 5.11e2;
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const double *f0 = p.f_nt + (size_t)zi[0] * p.num_nt;
+    const double *f1 = p.f_nt + (size_t)zi[nzn > 1 ? 1 : 0] * p.num_nt;
+    const double *f2 = p.f_nt + (size_t)zi[nzn > 2 ? 2 : 0] * p.num_nt;
+    const double *f3 = p.f_nt + (size_t)zi[nzn > 3 ? 3 : 0] * p.num_nt;
+    for (int i = 0; i < p.num_nt - 1; i++) {
+        const double sE = sigma_kn_bin(p, i, x), dg = p.dgam[i];
+        c0 = c0 + sE * f0[i] * dg;
+        c1 = c1 + sE * f1[i] * dg;
+        c2 = c2 + sE * f2[i] * dg;
+        c3 = c3 + sE * f3[i] * dg;
+    }
+    const double c[4] = {c0, c1, c2, c3};
+    for (int m = 0; m < nzn; m++) comac[m] = (c[m] < 1.e-40) ? 1.e-40 : p.n_e[zi[m]] * c[m];
+}
+
+// sigma_mode 1: per-step table ln sigma(zone, ln E), Catmull-Rom cubic in ln E
+__device__ __forceinline__ double comtot_table(const Params &p, int zi, double xnu)
+{
+    const double t = (log(xnu) - p.sig_lnE0) * p.sig_inv_dlnE;
+    int i = (int)floor(t);
+    if (i < 1) i = 1;
+    if (i > p.n_sig - 3) i = p.n_sig - 3;
+    const double u = t - i;
+    const double *y = p.sig_table + (size_t)zi * p.n_sig + i;
+    const double ym = y[-1], y0 = y[0], y1 = y[1], y2 = y[2];
+    const double a = -0.5 * ym + 1.5 * y0 - 1.5 * y1 + 0.5 * y2;
+    const double b = ym - 2.5 * y0 + 2.0 * y1 - 0.5 * y2;
+    const double c = -0.5 * ym + 0.5 * y1;
+    return exp(((a * u + b) * u + c) * u + y0);
+}
+
+__device__ __forceinline__ double comtot_one(const Params &p, int zi, double xnu)
+{
+    if (p.sigma_mode == 1) return comtot_table(p, zi, xnu);
+    double c;
+    comtot_zones(p, xnu, &zi, 1, &c);
+    return c;
+}
+
+// ------------------------------------------------------------------------------------------ scattering
+// nontherm2d.f:159-183
+__device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double &gamm, double &betb, int &ibin)
+{
+    const double *P = p.Pnt + (size_t)zi * p.num_nt;
+    double rnum = rng.next(p);
+    rnum = (double)(int)(rnum * 1.e6) / 1.e6 + 1.e-6 * rng.next(p);
+    // first i in [2, num_nt] (1-based) with Pnt(i) > rnum; Pnt is a CDF (non-decreasing)
+    int lo = 2, hi = p.num_nt;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (P[mid - 1] > rnum) hi = mid; else lo = mid + 1;
+    }
+    const int i = lo;
+    gamm = sqrt(p.gnt[i - 1] * p.gnt[i - 2]) + 1.0;
+    betb = sqrt(1.0 - 1.0 / (gamm * gamm));
+    atomicAdd(p.nelectron + i, 1ull);
+    ibin = i;
+}
+
+// compb_2d.f:1-318; P.jph/kph give the zone
+static __device__ __noinline__ void compb2d(const Params &p, Rng &rng, Photon &P, int &i_gam)
+{
+    const double fuzz = 1.e-10, emasskev = 5.11e2;
+    const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
+    const double znu = P.xnu / emasskev;
+    double gamm, betb, omeg, znue, xknot, betz, sz, games, znues;
+    for (;;) {                                       // label 100
+        nth2d(p, rng, zi, gamm, betb, i_gam);
+        omeg = 2.0 * rng.next(p) - 1.0;
+        C2D_CLAMP8(omeg);
+        const double tl = rng.next(p);
+        const double tr = 0.5 * (1.0 - betb * omeg);
+        if (tl > tr) omeg = -omeg;
+        C2D_CLAMP8(omeg);
+        znue = (1. - betb * omeg) * znu * gamm;
+        if (znue < 1.e-10) continue;
+        if (znue <= 1.e-2) {
+            xknot = 1.0 - znue * (2.0 - znue * (5.2 - znue * (13.3 - 1.144e3 * znue / 3.5e1)));
+        } else {
+            const double znue3 = znue * znue * znue;
+            betz = 1.0 + 2.0 * znue;
+            const double gamz = znue * (znue - 2.0) - 2.0;
+            const double xxx = 4.0 * znue + 2.0 * znue3 * (1.0 + znue) / (betz * betz) + gamz * log(betz);
+            xknot = 3.75e-1 * xxx / znue3;
+        }
+        if (rng.next(p) > xknot) continue;
+        break;
+    }
+    betz = 1.0 + 2.0 * znue;
+    for (;;) {                                       // labels 200/202
+        sz = (1.0 + 2.0 * znue * rng.next(p)) / betz;
+        games = 1.0 + (1.0 - 1.0 / sz) / znue;
+        if ((1.0 - games * games) < 0.) continue;
+        const double tr = games * games - 1.0 + sz + 1.0 / sz;
+        const double phat = betz + 1.0 / betz;
+        if (rng.next(p) * phat > tr) continue;
+        break;
+    }
+    znues = znue * sz;
+    double wa, wb, swa;
+    do {                                             // label 210
+        wa = rng.next(p);
+        wb = 2.0 * rng.next(p) - 1.0;
+        swa = wa * wa + wb * wb;
+    } while (swa >= 1.0 || swa <= 1.e-20);
+    const double cazes = (wa * wa - wb * wb) / swa;
+    double omege = (omeg - betb) / (1. - betb * omeg);
+    C2D_CLAMP8(omege);
+    double omeges = games * omege + cazes * sqrt((1. - omege * omege + fuzz) * (1. - games * games));
+    C2D_CLAMP8(omeges);
+    const double znus = (1.0 + betb * omeges) * gamm * znues;
+    double gams = 1.0 - (znue - znues) / (znu * znus);
+    C2D_CLAMP8(gams);
+    do {                                             // label 220
+        wa = rng.next(p);
+        wb = 2.0 * rng.next(p) - 1.0;
+        swa = wa * wa + wb * wb;
+    } while (swa >= 1.0 || swa <= 1.e-20);
+    double cazs = (wa * wa - wb * wb) / swa;
+    C2D_CLAMP8(cazs);
+    double wmus = P.wmu * gams + cazs * sqrt((1.0 - gams * gams) * (1.0 - P.wmu * P.wmu + fuzz));
+    C2D_CLAMP8(wmus);
+    const double xnus = znus * emasskev;
+    double cosdphi = (gams - P.wmu * wmus) / sqrt((1.0 - P.wmu * P.wmu) * (1.0 - wmus * wmus));
+    C2D_CLAMP8(cosdphi);
+    const double dphi = acos(cosdphi);
+    const double phis = P.phi + dphi;
+    P.jgpsp = sp_group(p, xnus, 1.000001e0, .999999e0, 0);
+    P.jgplc = lc_group(p, xnus);
+    P.jgpmu = mu_group(p, wmus);
+    P.ew = P.ew * xnus / P.xnu;
+    P.xnu = xnus;
+    P.wmu = wmus;
+    P.phi = phis;
+}
+
+// ------------------------------------------------------------------------------------------ imcleak
+__device__ __forceinline__ void escape_tally(const Params &p, const Photon &P, double t_bound)
+{   // imcleak2d.f:171-175
+    const unsigned long long n = atomicAdd(p.counters + CNT_NEVENTS, 1ull);
+    if (n < p.event_cap) {
+        double *e = p.events + 7 * n;
+        e[0] = t_bound; e[1] = P.xnu; e[2] = P.ew; e[3] = P.rpre; e[4] = P.zpre; e[5] = P.wmu; e[6] = P.phi;
+    }
+    if (P.jgplc > 0) atomic_add_f64(p.edout + (P.jgpmu - 1) * kNlcMax + (P.jgplc - 1), P.ew / p.dt);
+    if (P.jgpsp > 0 && p.spec_switch == 0) atomic_add_f64(p.fout + (P.jgpmu - 1) * p.nphtotal + (P.jgpsp - 1), P.ew);
+}
+
+// imcleak2d.f:2-320 with cr_sent = 0.  Returns idead.
+__device__ __forceinline__ int imcleak(const Params &p, Photon &P)
+{
+    const double t_bound = p.time + p.dt - kRadCp * P.dcen;     // l.203,302 (lower face: see DESIGN.md)
+    if (P.kph == 0) {
+        if (p.rmin > 1.e-10) { atomic_add_f64(p.erlki + (P.jph - 1), P.ew); return 1; }
+        P.phi = 1.e-6; P.kph = 1;
+        return 0;
+    }
+    if (!(P.jph > 0)) {
+        if (p.tbbl[P.kph - 1] > 0.0) {
+            atomic_add_f64(p.Ed_in + (P.kph - 1), P.ew);
+            atomic_add_f64(p.erlkl + (P.kph - 1), P.ew);
+        }
+        if (p.ncycle > 0) escape_tally(p, P, t_bound);
+        return 1;
+    }
+    if (P.jph != p.nz + 1) {
+        atomic_add_f64(p.erlko + (P.jph - 1), P.ew);
+        if (p.ncycle > 0) escape_tally(p, P, t_bound);
+        return 1;
+    }
+    atomic_add_f64(p.erlku + (P.kph - 1), P.ew);
+    if (p.ncycle > 0 && P.wmu < (double)0.98f) escape_tally(p, P, t_bound);
+    return 1;
+}
+
+// census append: imctrk2d.f:541-586
+__device__ __forceinline__ bool census_write(const Params &p, const Photon &P, Rng &rng)
+{
+    const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
+    atomicAdd(p.npcen + zi, 1ull);
+    atomic_add_f64(p.ecens + zi, P.ew);
+    if (p.pair_switch == 1) {
+        int i_gg;
+        for (i_gg = 1; i_gg <= p.n_gg; i_gg++)
+            if (P.xnu < p.E_gg[i_gg - 1]) break;
+        const double Egg_min = (p.E_gg[0] * p.E_gg[0]) / p.E_gg[1];
+        if (P.xnu > Egg_min) {
+            const double v = (P.ew * 6.25e8) / P.xnu;
+            if (i_gg <= p.n_gg) atomic_add_f64(p.n_ph + (size_t)zi * p.n_gg + (i_gg - 1), v);
+            else if (P.jph + 1 <= p.nz)   // n_ph(n_gg+1,j,k) aliases n_ph(1,j+1,k) in COMMON /photonfield/
+                atomic_add_f64(p.n_ph + (size_t)(zi + p.nr) * p.n_gg, v);
+        }
+    }
+    {
+        const int i_f = scan_lt(p.E_field, p.nphfield, P.xnu);
+        const double Egg_min = (p.E_field[0] * p.E_field[0]) / p.E_field[1];
+        if (P.xnu > Egg_min) atomic_add_f64(p.n_field + (size_t)zi * p.nphfield + (i_f - 1), 6.25e8 * P.ew / P.xnu);
+    }
+    const unsigned long long n = atomicAdd(p.counters + CNT_NDXOUT, 1ull);
+    if (n >= p.census_cap) { count(p, CNT_FATAL); return false; }
+    p.out.rpre[n] = P.rpre; p.out.zpre[n] = P.zpre; p.out.wmu[n] = P.wmu; p.out.phi[n] = P.phi;
+    p.out.ew[n] = P.ew; p.out.xnu[n] = P.xnu;
+    p.out.bins[n] = (uint32_t)P.jgpsp | ((uint32_t)P.jgplc << 16) | ((uint32_t)P.jgpmu << 24);
+    p.out.zone[n] = (uint32_t)P.jph | ((uint32_t)P.kph << 16);
+    p.out.sid[n] = rng.sid;
+    p.out.seed[n] = (int)(rng.next(p) * 1.e5);
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------ the flight
+// One imctrk2d flight from label 110 (imctrk2d.f:158) until it ends.
+//   MODE_PRE    collision-free ray of a history: no tallies, no draws; records the zone crossings
+//   MODE_TRIAL  scat_flag = -1 trial with a given colmfp: deposits absorption, stops at collision
+//   MODE_F0     scat_flag =  0 recombined flight: census / leak tallies, no deposition
+//   MODE_CHILD  scat_flag =  1 scattered photon: everything
+template <int MODE>
+__device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtmin, double colmfp, Seg *segs,
+                                int &nseg)
+{
+    // energy bins are constant along a flight (xnu only changes in compb2d)
+    const int i_e = scan_lt(p.E_ph, p.n_vol, P.xnu);
+    int i_gg = 0;
+    if (p.pair_switch == 1)
+        for (i_gg = 1; i_gg <= p.n_gg; i_gg++)
+            if (P.xnu < p.E_gg[i_gg - 1]) break;
+    const double dcol_f0 = 100 * fmax(p.r[p.nr - 1], p.z[p.nz - 1]);
+    int s = 0;
+    for (;;) {                                                    // label 110
+        if (P.ew < 1.e-40) return END_LOWEW;
+        if (P.wmu > 1.0) P.wmu = 1.0;
+        if (P.wmu < -1.0) P.wmu = -1.0;
+        const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
+        const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
+        double sigsc;
+        if (MODE == MODE_TRIAL) sigsc = segs[s].sigsc;
+        else if (MODE == MODE_CHILD || MODE == MODE_TRIAL_SLOW) sigsc = 1.0 * comtot_one(p, zi, P.xnu) * pair_enhance;
+        else sigsc = 0.0;
+        const double xqsqleft = (P.kph == 1) ? p.rmin * p.rmin : p.r[P.kph - 2] * p.r[P.kph - 2];
+        double dcol;
+        if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) dcol = colmfp / sigsc;
+        else if (MODE == MODE_F0) dcol = dcol_f0;
+        else dcol = INFINITY;
+        double trld; int ikind;
+        if (P.dcen <= dcol) { trld = P.dcen; ikind = 2; } else { trld = dcol; ikind = 3; }
+        // geometry, imctrk2d.f:233-365
+        double Eta = cos(P.phi);
+        const int Eta_switch = (P.phi <= kPi && P.phi >= 1.e-10) ? 1 : -1;
+        const double disp = Eta * P.rpre;
+        const double psq = P.rpre * P.rpre * (1. - Eta * Eta);
+        int kbnd, inout; double rbnd;
+        if (Eta < 0.0 && psq < xqsqleft) {
+            kbnd = P.kph - 1; inout = -1;
+            rbnd = (P.kph > 1) ? p.r[P.kph - 2] : p.rmin;
+        } else {
+            kbnd = P.kph; inout = 1;
+            rbnd = p.r[P.kph - 1];
+        }
+        double dpbsq = rbnd * rbnd - psq;
+        if (dpbsq < 1.e-6) dpbsq = 1.e-6;
+        const double disbr = (double)inout * sqrt(dpbsq) - disp;
+        double trldb = disbr / sqrt(1.0 - (P.wmu * P.wmu));
+        double f = disbr;
+        const double Zr = P.zpre + P.wmu * trldb;
+        const double zhigh = p.z[P.jph - 1], zlow = (P.jph == 1) ? p.zmin : p.z[P.jph - 2];
+        int knew, jnew; double Zbnd;
+        if (Zr > zhigh || Zr < zlow) {
+            const bool up = (Zr > zhigh);
+            Zbnd = up ? zhigh : zlow; knew = P.kph; jnew = up ? P.jph + 1 : P.jph - 1;
+            f = (Zbnd - P.zpre) * sqrt(1.0 - P.wmu * P.wmu) / P.wmu;
+            rbnd = sqrt(P.rpre * P.rpre + f * f + 2.0 * P.rpre * f * Eta);
+            trldb = sqrt(f * f + (Zbnd - P.zpre) * (Zbnd - P.zpre));
+        } else {
+            knew = P.kph + inout; jnew = P.jph;
+            rbnd = (kbnd > 0) ? p.r[kbnd - 1] : p.rmin;
+            Zbnd = Zr;
+        }
+        const double trldb_rec = trldb;
+        double rnew, znew;
+        if (trldb < trld) {
+            ikind = 1; trld = trldb; rnew = rbnd; znew = Zbnd;
+        } else {
+            jnew = P.jph; knew = P.kph;
+            f = trld * sqrt(1.0 - P.wmu * P.wmu);
+            rnew = sqrt(f * f + P.rpre * P.rpre + 2.0 * f * P.rpre * Eta);
+            znew = P.zpre + trld * P.wmu;
+        }
+        // absorption, imctrk2d.f:397-460
+        double sigabs = 1.e-40;
+        sigabs = sigabs + pair_enhance * p.kappa_tot[(size_t)zi * p.n_vol + (i_e - 1)];
+        double kgg_i = 0.0;
+        if (p.pair_switch == 1) {
+            const double *kg = p.k_gg + (size_t)zi * p.n_gg;
+            double kgg;
+            if (i_gg <= p.n_gg) kgg_i = kg[i_gg - 1];
+            if (P.xnu < p.E_gg[0]) kgg = (P.xnu / p.E_gg[0]) * kg[0];
+            else if (i_gg == p.n_gg) kgg = kg[p.n_gg - 1];
+            else if (i_gg > p.n_gg) kgg = 0.0;
+            else {
+                const double kgg0 = kg[i_gg - 1], kgg1 = kg[i_gg];
+                kgg = kgg0 + (P.xnu - p.E_gg[i_gg - 1]) * (kgg1 - kgg0) / (p.E_gg[i_gg] - p.E_gg[i_gg - 1]);
+            }
+            sigabs = sigabs + kgg;
+        }
+        if (sigabs < 1.e-40) sigabs = 1.e-40;
+        const double xabs = sigabs * trld;
+        const double ewnew = (xabs < 100.) ? P.ew * exp(-xabs) : 0.;
+        double deleabs;
+        if (P.xnu > 47.0 && sigabs > 1.e-40 && p.pair_switch == 1) deleabs = (P.ew - ewnew) * (sigabs - kgg_i) / sigabs;
+        else deleabs = P.ew - ewnew;
+        if (deleabs < 1.e-50) deleabs = 1.e-50;
+        if (MODE == MODE_PRE) {
+            if (s >= kMaxSeg) return END_OVERFLOW;
+            Seg &g = segs[s];
+            g.zi = zi; g.sigabs = sigabs; g.L = trld; g.trldb = trldb_rec; g.dcen = P.dcen; g.ew = P.ew;
+            g.dele = deleabs; g.rpre = P.rpre; g.sigsc = pair_enhance;    // sigsc := comac * pair_enhance later
+            nseg = s + 1;
+        } else {
+            double wmustar = P.wmu;
+            if (!(xabs <= .00001)) {
+                if (MODE == MODE_F0) rng.d++;                               // draw consumed, value unused (no deposit)
+                else {
+                    const double mb_ran = rng.next(p);                      // always < ew/deleabs (>= 1)
+                    const double sstar = -log(1. - mb_ran * deleabs / P.ew) / sigabs;
+                    const double denom = sqrt(P.rpre * P.rpre + 2. * P.wmu * P.rpre * sstar + sstar * sstar);
+                    wmustar = (P.wmu * P.rpre + sstar) / denom;
+                }
+            }
+            if (MODE != MODE_F0) {
+                atomic_add_f64(p.edep + zi, deleabs);
+                atomic_add_f64(p.prdep + zi, deleabs * wmustar * kCLight);
+            }
+        }
+        s++;
+        if (ewnew <= wtmin) { if (MODE != MODE_PRE) count(p, CNT_KILLED); return END_KILLED; }
+        P.ew = ewnew;
+        P.dcen = P.dcen - trld;
+        Eta = (f + Eta * P.rpre) / rnew;
+        if (Eta > 1.0) Eta = 1.0;
+        if (Eta < -1.0) Eta = -1.0;
+        P.phi = acos(Eta);
+        if (Eta_switch == -1) P.phi = 2.0 * kPi - P.phi;
+        P.rpre = rnew;
+        P.zpre = znew;
+        if (ikind == 1) {
+            colmfp = colmfp - sigsc * trld;
+            if (jnew == p.nz + 1 || jnew == 0 || knew == p.nr + 1 || knew == 0) {
+                P.jph = jnew; P.kph = knew;
+                if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
+                const int idead = imcleak(p, P);
+                count(p, CNT_LKCOUNT);
+                if (idead == 1) return END_LEAK;
+                continue;
+            }
+            P.kph = knew; P.jph = jnew;
+            continue;
+        }
+        if (ikind == 2) {
+            if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
+            return census_write(p, P, rng) ? END_CENSUS : END_FATAL;
+        }
+        return END_COLLISION;                                       // ikind == 3
+    }
+}
+
+// ------------------------------------------------------------------------------------------ sources
+#define C2D_F4(x) ((double)(x##f))
+
+// imcvol2d_para.f:157-389: photon number ivol (1-based) of zone `zone` (1-based)
+__device__ __forceinline__ void source_volume(const Params &p, Rng &rng, int zone, Photon &P)
+{
+    const int jv = (zone - 1) / p.nr + 1, kv = zone - p.nr * (jv - 1), zi = zone - 1;
+    const double rlo = (kv == 1) ? p.rmin : p.r[kv - 2], rhi = p.r[kv - 1];
+    const double zhi = p.z[jv - 1], zlo_tab = (jv == 1) ? 0.0 : p.z[jv - 2];
+    const double f_thermal = p.Eloss_th[zi] / p.Eloss_tot[zi];
+    const double delz = (jv == 1) ? p.z[0] : zhi - zlo_tab;
+    const double zs = p.zsurf[zi];
+    const double f_inn = (4.4e1 / 7.0 * rlo * delz) / zs;
+    double f_outer = (4.4e1 / 7.0 * rhi * delz) / zs;
+    double f_upper = (2.2e1 / 7.0 * (rhi * rhi - rlo * rlo)) / zs;
+    f_outer = f_inn + f_outer;
+    f_upper = f_outer + f_upper;
+    P.jph = jv; P.kph = kv;
+    P.ew = p.ewsv[zi];
+    P.dcen = kCLight * p.dt * rng.next(p);
+    double rnum = rng.next(p);
+    const bool thermal = (rnum < f_thermal);
+    const double *eps = (thermal ? p.eps_th : p.eps_tot) + (size_t)zi * p.n_vol;
+    rnum = rng.next(p);
+    {   // first i (1-based) with eps(i) >= rnum, capped at n_vol (the CDF is non-decreasing)
+        int lo = 1, hi = p.n_vol;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (eps[mid - 1] < rnum) lo = mid + 1; else hi = mid;
+        }
+        const int i = lo;
+        if (i < p.n_vol) P.xnu = p.E_ph[i - 1] + rng.next(p) * (p.E_ph[i] - p.E_ph[i - 1]);
+        else P.xnu = p.E_ph[i - 1];
+    }
+    if (thermal) {
+        const double rnum0 = rng.next(p);
+        if (rnum0 < f_inn) {
+            P.wmu = 2.0 * rng.next(p) - 1.0;
+            C2D_CLAMP8(P.wmu);
+            const double x1 = rng.next(p), x2 = rng.next(p);
+            if (x1 < 0.5) {
+                P.phi = 1.1e1 / 7.0 + (1.1e1 / 7.0) * x2;
+                if (P.phi < 1.57079638e0) P.phi = 1.57079638e0;
+            } else {
+                P.phi = -1.1e1 / 7.0 - (1.1e1 / 7.0) * x2;
+                if (P.phi > -1.57079638e0) P.phi = -1.57079638e0;
+            }
+            P.rpre = C2D_F4(1.00001) * rlo;
+            if (jv == 1) P.zpre = p.z[0] * rng.next(p);
+            else P.zpre = zlo_tab + rng.next(p) * (zhi - zlo_tab);
+        } else if (rnum0 < f_outer) {
+            P.wmu = 2.0 * rng.next(p) - 1.0;
+            C2D_CLAMP8(P.wmu);
+            P.rpre = C2D_F4(0.999999) * rhi;
+            if (jv == 1) P.zpre = p.z[0] * rng.next(p);
+            else P.zpre = zlo_tab + rng.next(p) * (zhi - zlo_tab);
+            P.phi = -1.1e1 / 7.0 + 2.2e1 / 7.0 * rng.next(p);
+            if (P.phi < -1.5707963e0) P.phi = -1.57079063e0;
+            if (P.phi > 1.5707963e0) P.phi = 1.5707963e0;
+        } else if (rnum0 < f_upper) {
+            P.wmu = rng.next(p);
+            if (P.wmu > 9.9999999e-1) P.wmu = 9.9999999e-1;
+            if (P.wmu < 0.0) P.wmu = 0.0;
+            P.phi = 4.4e1 / 7.0 * rng.next(p);
+            if (P.phi > 2.0 * kPi) P.phi = 2.0 * kPi;
+            const double psi = rng.next(p);
+            P.zpre = C2D_F4(0.999999) * zhi;
+            P.rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+        } else {
+            P.wmu = -rng.next(p);
+            P.phi = 4.4e1 / 7.0 * rng.next(p);
+            if (P.wmu > 0.0) P.wmu = 0.0;
+            if (P.wmu < -9.9999999e-1) P.wmu = -9.9999999e-1;
+            if (P.phi > 2.0 * kPi) P.phi = 2.0 * kPi;
+            const double zl = (jv == 1) ? p.zmin : zlo_tab;
+            P.zpre = C2D_F4(1.000001) * zl;
+            if (P.zpre <= zl) P.zpre = zl + 1.e-6;
+            const double psi = rng.next(p);
+            P.rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+        }
+    } else {
+        P.wmu = 2.0 * rng.next(p) - 1.0;
+        P.phi = 4.4e1 / 7.0 * rng.next(p);
+        C2D_CLAMP8(P.wmu);
+        if (P.phi > 2.0 * kPi) P.phi = 2.0 * kPi;
+        if (jv == 1) P.zpre = p.z[0] * rng.next(p);
+        else P.zpre = zlo_tab + rng.next(p) * (zhi - zlo_tab);
+        const double psi = rng.next(p);
+        P.rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+    }
+    P.jgpsp = sp_group(p, P.xnu, C2D_F4(1.000001), C2D_F4(.999999), p.nphtotal);
+    P.jgplc = lc_group(p, P.xnu);
+    P.jgpmu = mu_group(p, P.wmu);
+}
+
+}  // namespace c2d

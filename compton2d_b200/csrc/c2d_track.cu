@@ -1,0 +1,288 @@
+// c2d_track.cu -- history kernels of the Compton2d hot path (sm_100a) and their launchers.
+//
+//   k_history<SRC>   one thread per top-level history = one imctrk2d(-1) call of the reference
+//                    (imcvol2d_para.f:392 for volume sources, imcfield2d.f:128 for census photons):
+//                    source sampling, the collision-free ray, split1 trial draws, absorption
+//                    deposition, the recombined scat_flag = 0 flight with its census / leak tallies.
+//   k_collisions     one block per Compton collision found by any flight: the split2 (and split3)
+//                    children of imctrk2d.f:619-689, each scattered by compb2d and flown with
+//                    scat_flag = 1; collisions of those flights go to the next generation's queue.
+#include "c2d_host.h"
+
+namespace c2d {
+
+__device__ __forceinline__ void push_collision(const Params &p, const Photon &P, uint64_t sid)
+{
+    const unsigned long long n = atomicAdd(p.q_out_count, 1ull);
+    if (n >= p.q_cap) { count(p, CNT_FATAL); return; }
+    CollTask &t = p.q_out[n];
+    t.p = P; t.pad = 0; t.sid = sid;
+}
+
+// exact replay of the collision decision of imctrk2d.f:214-227,370 along the recorded ray
+__device__ __forceinline__ bool trial_collides(const Seg *segs, int nseg, double colmfp)
+{
+    for (int s = 0; s < nseg; s++) {
+        const double dcol = colmfp / segs[s].sigsc;
+        if (!(segs[s].dcen <= dcol) && !(segs[s].trldb < dcol)) return true;
+        colmfp = colmfp - segs[s].sigsc * segs[s].L;
+    }
+    return false;
+}
+
+// one trial flight executed literally (imctrk2d.f:126-695 body for scat_flag = -1)
+static __device__ __noinline__ int literal_trial(const Params &p, const Photon &T0, uint64_t S_trials, int t, double u,
+                                          double wtmin, Seg *segs, int nseg)
+{
+    Rng rng; rng.stream(mix64(S_trials, (uint64_t)(t + 1)));
+    Photon P = T0;
+    int ns = nseg;
+    count(p, CNT_LITERAL);
+    const int end = fly<MODE_TRIAL>(p, P, rng, wtmin, -log(u), segs, ns);
+    if (end == END_COLLISION) {
+        count(p, CNT_CMCOUNT1);
+        push_collision(p, P, rng.sid);
+        return 1;
+    }
+    return 0;
+}
+
+// slow path for rays that cross more than kMaxSeg zones: the trial is flown with comtot evaluated
+// per crossing (same values as the per-history cache, imctrk2d.f:175-183)
+static __device__ __noinline__ int literal_trial_slow(const Params &p, const Photon &T0, uint64_t S_trials, int t, double u,
+                                               double wtmin)
+{
+    Rng rng; rng.stream(mix64(S_trials, (uint64_t)(t + 1)));
+    Photon P = T0;
+    int ns = 0;
+    count(p, CNT_LITERAL);
+    const int end = fly<MODE_TRIAL_SLOW>(p, P, rng, wtmin, -log(u), nullptr, ns);
+    if (end == END_COLLISION) {
+        count(p, CNT_CMCOUNT1);
+        push_collision(p, P, rng.sid);
+        return 1;
+    }
+    return 0;
+}
+
+__device__ __forceinline__ void history(const Params &p, const Photon &P0, uint64_t S_entry)
+{
+    const double wtmin = 1.e-10 * P0.ew;                          // imctrk2d.f:82,92
+    Photon T0 = P0;
+    T0.ew = P0.ew / p.split1;                                     // l.110
+    const uint64_t S_trials = mix64(S_entry, kTagTrials);
+    count(p, CNT_HISTORIES);
+
+    // A: the collision-free ray
+    Seg segs[kMaxSeg];
+    int nseg = 0, nscat = 0, nlit = 0;
+    bool overflow = false;
+    {
+        Photon Q = T0; Rng dummy; dummy.stream(0);
+        const int endA = fly<MODE_PRE>(p, Q, dummy, wtmin, 0.0, segs, nseg);
+        overflow = (endA == END_OVERFLOW);
+        if (endA == END_LOWEW && nseg == 0) return;   // ew < 1e-40 at entry: nothing is tallied (l.161)
+    }
+    if (overflow) {
+        count(p, CNT_SEGOVF);
+        for (int t = 0; t < p.split1; t++)
+            nscat += literal_trial_slow(p, T0, S_trials, t, rng_uniform(p, S_trials, (uint32_t)t), wtmin);
+        count(p, CNT_TRIALS, (unsigned long long)p.split1);
+    } else {
+    // B: sigma_sc per crossing (comac_ar cache of l.175-183: one comtot per zone and history)
+    if (p.sigma_mode == 1) {
+        for (int s = 0; s < nseg; s++) segs[s].sigsc = 1.0 * comtot_table(p, segs[s].zi, T0.xnu) * segs[s].sigsc;
+    } else {
+        unsigned have = 0u;
+        for (int s0 = 0; s0 < nseg; s0++) {
+            if (have & (1u << s0)) continue;
+            int zl[4], nzn = 0;
+            for (int s = s0; s < nseg && nzn < 4; s++) {
+                if (have & (1u << s)) continue;
+                bool seen = false;
+                for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
+                if (!seen) zl[nzn++] = segs[s].zi;
+            }
+            double cm[4];
+            comtot_zones(p, T0.xnu, zl, nzn, cm);
+            for (int s = s0; s < nseg; s++) {
+                if (have & (1u << s)) continue;
+                for (int m = 0; m < nzn; m++)
+                    if (zl[m] == segs[s].zi) { segs[s].sigsc = 1.0 * cm[m] * segs[s].sigsc; have |= (1u << s); break; }
+            }
+        }
+    }
+    // C: the split1 trial draws (l.126-156).  A trial collides only if -ln(u) is within the ray's
+    // scattering depth, i.e. u >= thr; everything below thr provably does not (margins >> rounding).
+    double tau = 0.0; bool has_rand = false;
+    for (int s = 0; s < nseg; s++) { tau += segs[s].sigsc * segs[s].L; has_rand |= !(segs[s].sigabs * segs[s].L <= .00001); }
+    const double thr = exp(-tau * (1.0 + 1.e-12)) * (1.0 - 1.e-12);
+    double pr_acc[kMaxSeg];
+    if (has_rand) for (int s = 0; s < nseg; s++) pr_acc[s] = 0.0;
+    const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
+    for (int t2 = 0; 2 * t2 < p.split1; t2++) {
+        uint32_t o[4];
+        philox4x32_10(s_lo, s_hi, (uint32_t)t2, 0u, p.key0, p.key1, o);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int t = 2 * t2 + h;
+            if (t >= p.split1) break;
+            const double u = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
+            if (u >= thr && trial_collides(segs, nseg, -log(u))) {
+                nlit++;
+                nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
+                continue;
+            }
+            if (has_rand) {       // absorption-point draws of l.451-459 (they only move prdep)
+                const uint64_t S_t = mix64(S_trials, (uint64_t)(t + 1));
+                uint32_t k = 0;
+                for (int s = 0; s < nseg; s++) {
+                    const Seg &g = segs[s];
+                    if (g.sigabs * g.L <= .00001) continue;
+                    const double mb_ran = rng_uniform(p, S_t, k++);
+                    const double sstar = -log(1. - mb_ran * g.dele / g.ew) / g.sigabs;
+                    const double denom = sqrt(g.rpre * g.rpre + 2. * T0.wmu * g.rpre * sstar + sstar * sstar);
+                    pr_acc[s] += g.dele * ((T0.wmu * g.rpre + sstar) / denom) * kCLight;
+                }
+            }
+        }
+    }
+    count(p, CNT_TRIALS, (unsigned long long)p.split1);
+    count(p, CNT_SEGMENTS, (unsigned long long)nseg);
+    // D: absorption deposition of the non-colliding trials (l.465-466), identical per trial
+    {
+        const double n_nc = (double)(p.split1 - nlit);
+        double wmu = T0.wmu;
+        if (wmu > 1.0) wmu = 1.0;
+        if (wmu < -1.0) wmu = -1.0;
+        if (n_nc > 0)
+            for (int s = 0; s < nseg; s++) {
+                const Seg &g = segs[s];
+                atomic_add_f64(p.edep + g.zi, n_nc * g.dele);
+                if (g.sigabs * g.L <= .00001) atomic_add_f64(p.prdep + g.zi, n_nc * (g.dele * wmu * kCLight));
+                else atomic_add_f64(p.prdep + g.zi, pr_acc[s]);
+            }
+    }
+    }   // !overflow
+    // E: recombined flight of the unscattered weight (l.698-712)
+    if (p.split1 - nscat > 0) {
+        Photon F = P0;
+        F.ew = (p.split1 - nscat) * T0.ew;
+        Rng rng; rng.stream(mix64(S_entry, kTagF0));
+        int dummy = 0;
+        const int end = fly<MODE_F0>(p, F, rng, 1.e-10 * F.ew, 0.0, nullptr, dummy);
+        if (end == END_COLLISION) count(p, CNT_FATAL);
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(128) k_history(const Params p, long long first, long long n, long long stride)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    Photon P0;
+    uint64_t S_entry;
+    if (SRC == 0) {
+        const long long h = first + idx * stride;
+        // zone (1-based) with nsv_prefix[zone-1] <= h < nsv_prefix[zone]
+        int lo = 0, hi = p.nzone;            // invariant: prefix[lo] <= h < prefix[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (p.nsv_prefix[mid] <= h) lo = mid; else hi = mid;
+        }
+        const int zone = lo + 1;
+        const long long ivol = h - p.nsv_prefix[lo] + 1;
+        S_entry = mix64(mix64(kTagVol, (uint64_t)zone), (uint64_t)ivol);
+        Rng rng; rng.stream(S_entry);
+        source_volume(p, rng, zone, P0);
+    } else {
+        const long long h = first + idx * stride;
+        P0.rpre = p.in.rpre[h]; P0.zpre = p.in.zpre[h]; P0.wmu = p.in.wmu[h]; P0.phi = p.in.phi[h];
+        P0.ew = p.in.ew[h]; P0.xnu = p.in.xnu[h];
+        const uint32_t b = p.in.bins[h], zz = p.in.zone[h];
+        P0.jgpsp = b & 0xFFFF; P0.jgplc = (b >> 16) & 0xFF; P0.jgpmu = b >> 24;
+        P0.jph = zz & 0xFFFF; P0.kph = zz >> 16;
+        P0.dcen = kCLight * p.dt;                                 // imcfield2d.f:117
+        if (P0.wmu > 1.0) P0.wmu = 1.0;
+        if (P0.wmu < -1.0) P0.wmu = -1.0;
+        S_entry = p.in.sid[h];
+    }
+    history(p, P0, S_entry);
+}
+
+__global__ void __launch_bounds__(128) k_collisions(const Params p, const CollTask *q_in, long long n_in)
+{
+    const long long b = blockIdx.x;
+    if (b >= n_in) return;
+    const CollTask task = q_in[b];
+    const double ewcsv = task.p.ew / p.split2;                    // l.617
+    const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
+    for (int ii = threadIdx.x + 1; ii <= p.split2; ii += blockDim.x) {
+        const uint64_t S_child = mix64(task.sid, (uint64_t)ii);
+        Rng rng; rng.stream(S_child);
+        Photon P = task.p;
+        P.ew = ewcsv;
+        double ewold = P.ew;
+        int i_gam = 0, dummy = 0;
+        compb2d(p, rng, P, i_gam);
+        if (P.ew > ewold * p.split2 * p.split1 * p.spl3_trg) {     // 3rd split, l.639-669
+            ewold = ewcsv / p.split3;
+            for (int ii2 = 1; ii2 <= p.split3; ii2++) {
+                rng.stream(mix64(S_child, (uint64_t)ii2));
+                do {
+                    P = task.p;
+                    P.ew = ewcsv / p.split3;
+                    compb2d(p, rng, P, i_gam);
+                } while (P.ew <= ewold * p.split2 * p.split1 * p.spl3_trg);
+                atomic_add_f64(p.edep + zi, P.ew - ewold);
+                atomic_add_f64(p.E_IC + (i_gam - 1), P.ew - ewold);
+                count(p, CNT_CMCOUNT2);
+                if (P.phi > 2.0 * kPi) P.phi = P.phi - 2.0 * kPi;
+                const double wt = 1.e-10 * P.ew;
+                const double colmfp = -log(rng.next(p));
+                const int end = fly<MODE_CHILD>(p, P, rng, wt, colmfp, nullptr, dummy);
+                if (end == END_COLLISION) {
+                    count(p, CNT_MULTIPLE); count(p, CNT_CMCOUNT1);
+                    push_collision(p, P, rng.sid);
+                }
+            }
+        } else {
+            atomic_add_f64(p.edep + zi, P.ew - ewold);
+            atomic_add_f64(p.E_IC + (i_gam - 1), P.ew - ewold);
+            count(p, CNT_CMCOUNT2);
+            if (P.phi > 2.0 * kPi) P.phi = P.phi - 2.0 * kPi;
+            const double wt = 1.e-10 * P.ew;
+            const double colmfp = -log(rng.next(p));
+            const int end = fly<MODE_CHILD>(p, P, rng, wt, colmfp, nullptr, dummy);
+            if (end == END_COLLISION) {
+                count(p, CNT_MULTIPLE); count(p, CNT_CMCOUNT1);
+                push_collision(p, P, rng.sid);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ launchers
+#ifndef C2D_EMU
+void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
+{
+    if (n <= 0) return;
+    const int threads = 128;
+    const long long blocks = (n + threads - 1) / threads;
+    k_history<0><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
+}
+void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
+{
+    if (n <= 0) return;
+    const int threads = 128;
+    const long long blocks = (n + threads - 1) / threads;
+    k_history<1><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
+}
+void launch_collisions(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st)
+{
+    if (n_in <= 0) return;
+    k_collisions<<<(unsigned)n_in, 128, 0, st>>>(p, q_in, n_in);
+}
+#endif  // C2D_EMU
+
+}  // namespace c2d

@@ -1,0 +1,116 @@
+"""ctypes binding of libcompton2d_b200.so (the C ABI in include/compton2d_b200.h).
+
+The library is the product; this module only loads it.  It fails loudly when the
+shared object is missing -- there is no Python/CPU fallback of any kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+HERE = Path(__file__).resolve().parent
+LIBPATH = HERE / "libcompton2d_b200.so"
+
+NMUMAX = 32
+NLCMAX = 16
+dp = C.POINTER(C.c_double)
+ip = C.POINTER(C.c_int32)
+lp = C.POINTER(C.c_int64)
+
+
+class Dims(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("nz", "nr", "n_vol", "num_nt", "nphfield", "n_gg", "nphtotal", "nph_lc",
+                                       "nmu", "pair_switch", "cr_sent", "spec_switch", "split1", "split2",
+                                       "split3", "spl3_trg")] + \
+        [("census_capacity", C.c_int64), ("event_capacity", C.c_int64), ("collision_capacity", C.c_int64),
+         ("rseed", C.c_uint32), ("sigma_mode", C.c_int), ("rmin", C.c_double), ("zmin", C.c_double)] + \
+        [(n, dp) for n in ("z", "r", "E_ph", "E_field", "E_gg", "gnt", "hu", "Elcmin", "Elcmax", "mu")]
+
+
+class StepIn(C.Structure):
+    _fields_ = [("ncycle", C.c_int), ("time", C.c_double), ("dt", C.c_double)] + \
+        [(n, dp) for n in ("kappa_tot", "eps_tot", "eps_th", "f_nt", "Pnt", "n_e", "tea", "f_pair", "k_gg")] + \
+        [("nsv", ip)] + [(n, dp) for n in ("ewsv", "Eloss_th", "Eloss_tot", "zsurf", "tbbl")]
+
+
+class Tallies(C.Structure):
+    _fields_ = [("edep", dp), ("prdep", dp), ("ecens", dp), ("npcen", lp), ("n_field", dp), ("n_ph", dp),
+                ("E_IC", dp), ("nelectron", lp), ("fout", dp), ("edout", dp), ("erlki", dp), ("erlko", dp),
+                ("erlku", dp), ("erlkl", dp), ("Ed_in", dp), ("Ed_ref", dp), ("counters", C.c_int64 * 16)]
+
+
+class FpIn(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("first_zone", "n_zones", "zone_stride", "inj_switch", "inj_dis",
+                                       "g2var_switch", "pick_sw")] + \
+        [(n, C.c_double) for n in ("time", "dt", "inj_g1", "inj_g2", "inj_p", "inj_t", "inj_gg", "inj_sigma",
+                                   "inj_L", "inj_v", "pick_rate", "r_esc", "r_acc", "r_flare", "z_flare",
+                                   "t_flare", "sigma_r", "sigma_z", "sigma_t", "flare_amp")] + \
+        [("cf_sentinel", C.c_int)] + \
+        [(n, dp) for n in ("f_nt", "n_field", "n_e", "B_field", "tea", "tna", "vol", "F_IC")]
+
+
+class FpOut(C.Structure):
+    _fields_ = [(n, dp) for n in ("f_nt", "Pnt", "n_e", "Te_new", "gmin", "gmax", "p_nth", "amxwl")] + \
+        [("fp_steps", ip)] + \
+        [(n, C.c_double) for n in ("dT_max", "E_tot_old", "E_tot_new", "hr_total", "hr_st_total")]
+
+
+COUNTERS = ["ndxout", "cmcount1", "cmcount2", "lkcount", "nevents", "histories", "trials", "multiple", "killed",
+            "segovf", "literal", "qpeak", "fatal", "segments"]
+
+EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_version", "c2d_step_begin",
+           "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",
+           "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
+           "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
+           "c2d_kernel_time_ms", "c2d_tally_bench"]
+
+_lib = None
+
+
+class C2dError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"compton2d_b200 error {code}: {msg}")
+        self.code = code
+
+
+def load():
+    """dlopen the in-tree CUDA library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIBPATH.exists():
+        raise ImportError(f"{LIBPATH} is missing: build it with `python compton2d_b200/build.py` "
+                          "(nvcc, sm_100a). compton2d_b200 has no CPU fallback.")
+    L = C.CDLL(str(LIBPATH))
+    vp = C.c_void_p
+    L.c2d_last_error.restype = C.c_char_p
+    L.c2d_create.argtypes = [C.POINTER(vp), C.c_int]
+    L.c2d_init.argtypes = [vp, C.POINTER(Dims)]
+    L.c2d_destroy.argtypes = [vp]
+    L.c2d_step_begin.argtypes = [vp, C.POINTER(StepIn)]
+    L.c2d_imcfield.argtypes = [vp]
+    L.c2d_imcvol.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
+    L.c2d_sync.argtypes = [vp]
+    L.c2d_tally_read.argtypes = [vp, C.POINTER(Tallies)]
+    L.c2d_tally_device.argtypes = [vp, C.POINTER(vp), lp, C.POINTER(vp), lp]
+    L.c2d_census_count.argtypes = [vp, lp]
+    L.c2d_census_export.argtypes = [vp, vp, vp, vp, C.c_int64, lp]
+    L.c2d_census_import.argtypes = [vp, vp, vp, vp, C.c_int64]
+    L.c2d_events_drain.argtypes = [vp, vp, C.c_int64, lp]
+    L.c2d_ic_loss.argtypes = [vp, vp]
+    L.c2d_update_fp.argtypes = [vp, C.POINTER(FpIn), C.POINTER(FpOut)]
+    L.c2d_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), lp]
+    L.c2d_tally_bench.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(C.c_float), lp]
+    for fn in ("c2d_pack_bin_first", "c2d_unpack_bin_first"):
+        getattr(L, fn).argtypes = [vp] + [C.c_int] * 6 + [vp]
+        getattr(L, fn).restype = None
+    for fn in ("c2d_pack_bin_last", "c2d_unpack_bin_last"):
+        getattr(L, fn).argtypes = [vp] + [C.c_int] * 5 + [vp]
+        getattr(L, fn).restype = None
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise C2dError(rc, load().c2d_last_error().decode())

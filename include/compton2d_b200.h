@@ -1,0 +1,188 @@
+/*
+ * compton2d_b200.h -- C ABI of the B200-native hot path of Compton2d.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: its
+ * "interface" is `call name` with no arguments plus ~90 COMMON blocks
+ * (src_20121026/commonblock.f:118-219).  A thin ISO_C_BINDING Fortran shim that
+ * keeps the reference's subroutine names (imcfield2d, imcvol2d, imcsurf2d, update, ...)
+ * packs the COMMON members listed below into dense arrays and calls these entry
+ * points (INTEGRATION.md shows the shim).  Plain C types only; every function
+ * returns 0 on success and a non-zero C2D_E* code otherwise -- the shim prints
+ * c2d_last_error() and STOPs, which is the reference's own error behaviour
+ * (e.g. imctrk2d.f:583-584 `write(*,*) 'too many photons'; stop`).
+ *
+ * Layout convention of every per-zone table: dense, row-major [zone][bin], with
+ *   zone = (k-1) + nr*(j-1),  j = z index 1..nz,  k = r index 1..nr
+ * (fp_mpi.f:333-352 get_j_k/get_zone, 0-based).  c2d_pack_bin_first/_bin_last convert from
+ * the padded column-major COMMON arrays (kappa_tot(n_vol,jmax,kmax) / f_nt(jmax,kmax,num_nt)).
+ *
+ * There is NO CPU fallback: without a CUDA device c2d_create fails with C2D_ENODEV.
+ */
+#ifndef COMPTON2D_B200_H
+#define COMPTON2D_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define C2D_NMUMAX 32      /* general.pa:20 nmumax */
+#define C2D_NLCMAX 16      /* >= general.pa:22 nphlcmax = 10 */
+
+enum {
+    C2D_OK = 0,
+    C2D_ENODEV = 1,        /* no CUDA device / wrong architecture */
+    C2D_EINVAL = 2,        /* bad argument or unsupported switch (cr_sent != 0, ...) */
+    C2D_ECUDA = 3,         /* CUDA runtime error (message in c2d_last_error) */
+    C2D_ECENSUS = 4,       /* census bank full: the reference's 'too many photons' STOP (imctrk2d.f:581-585) */
+    C2D_EEVENTS = 5,       /* event buffer full (records beyond capacity were counted, not stored) */
+    C2D_ESTATE = 6         /* call order violated (step_begin before init, ...) */
+};
+
+typedef struct c2d_ctx c2d_ctx;      /* opaque; one per GPU / per reference worker rank */
+
+/* Static problem description: replaces setup_bcast (fp_mpi.f:12-319) + the grid part of
+ * z_surf_bcast (surf_mpi.f:18-98).  Arrays are copied; the caller keeps ownership. */
+typedef struct {
+    int nz, nr;                       /* commonblock.f /zones/ */
+    int n_vol, num_nt, nphfield, n_gg; /* general.pa:13-18 (400, 200, 400, 100 in the reference build) */
+    int nphtotal, nph_lc, nmu;        /* spectrum groups, light-curve bands, angle bins (setup2d.f:148-173) */
+    int pair_switch, cr_sent, spec_switch;   /* reader.f sentinels; cr_sent must be 0 */
+    int split1, split2, split3, spl3_trg;    /* reader.f:587-590 */
+    int64_t census_capacity;          /* ucens (general.pa:7), photons */
+    int64_t event_capacity;           /* escape records kept per step */
+    int64_t collision_capacity;       /* pending Compton-collision tasks (scattering work queue) */
+    uint32_t rseed;                   /* reader.f:466; Philox key word 0 (key word 1 = ncycle) */
+    int sigma_mode;                   /* 0: comtot evaluated exactly per history (comtot2d.f:219-247)
+                                         1: per-step sigma(zone,E) table, log-log cubic interpolation */
+    double rmin, zmin;
+    const double *z;                  /* [nz]  upper faces */
+    const double *r;                  /* [nr]  outer faces */
+    const double *E_ph;               /* [n_vol]    volume2d.f:112-113 */
+    const double *E_field;            /* [nphfield] setup2d.f:217-222 */
+    const double *E_gg;               /* [n_gg]     setup2d.f:199-202 */
+    const double *gnt;                /* [num_nt]   gamma-1 grid, nontherm2d.f:52-54 */
+    const double *hu;                 /* [nphtotal+1] */
+    const double *Elcmin, *Elcmax;    /* [nph_lc] */
+    const double *mu;                 /* [nmu] */
+} c2d_dims;
+
+/* Per-step inputs: what imcgen2d (imcgen2d.f) leaves in COMMON for the workers, i.e. the union of
+ * vol_bcast (vol_mpi.f:39-45), the per-zone volume job (vol_mpi.f:100-119), z_surf_bcast
+ * (surf_mpi.f:18-98) and xec_bcast (xec2d.f:293-318). */
+typedef struct {
+    int ncycle;
+    double time, dt;                  /* dt(1) */
+    const double *kappa_tot;          /* [zone][n_vol] */
+    const double *eps_tot, *eps_th;   /* [zone][n_vol] emission CDFs */
+    const double *f_nt, *Pnt;         /* [zone][num_nt] */
+    const double *n_e, *tea, *f_pair; /* [zone] */
+    const double *k_gg;               /* [zone][n_gg] (may be NULL when pair_switch = 0) */
+    const int32_t *nsv;               /* [zone] volume photons to source */
+    const double *ewsv;               /* [zone] their energy weight */
+    const double *Eloss_th, *Eloss_tot, *zsurf;   /* [zone] */
+    const double *tbbl;               /* [nr] lower-boundary temperature of the current time interval tbbl(k,ti) */
+} c2d_step_in;
+
+/* All tallies of one step, dense.  Filled by c2d_tally_read. */
+typedef struct {
+    double *edep, *prdep, *ecens;     /* [zone] */
+    int64_t *npcen;                   /* [zone] */
+    double *n_field;                  /* [zone][nphfield] */
+    double *n_ph;                     /* [zone][n_gg] */
+    double *E_IC;                     /* [num_nt] */
+    int64_t *nelectron;               /* [num_nt+2], index = electron bin i (1-based as in nth2d) */
+    double *fout;                     /* [C2D_NMUMAX][nphtotal]  (cumulative over the run, as on the reference's workers) */
+    double *edout;                    /* [C2D_NMUMAX][C2D_NLCMAX] */
+    double *erlki, *erlko;            /* [nz] */
+    double *erlku, *erlkl;            /* [nr] */
+    double *Ed_in, *Ed_ref;           /* [nr] */
+    int64_t counters[16];             /* see C2D_CNT_* */
+} c2d_tallies;
+
+enum {
+    C2D_CNT_NDXOUT = 0,      /* census photons written this step (ndxout) */
+    C2D_CNT_CMCOUNT1 = 1,    /* Compton collisions (imctrk2d.f:615) */
+    C2D_CNT_CMCOUNT2 = 2,    /* scattered children tracked (imctrk2d.f:661,677) */
+    C2D_CNT_LKCOUNT = 3,     /* imcleak calls (imctrk2d.f:517) */
+    C2D_CNT_NEVENTS = 4,     /* escape records produced */
+    C2D_CNT_HISTORIES = 5,   /* top-level imctrk2d(-1) calls */
+    C2D_CNT_TRIALS = 6,      /* split1 trial flights evaluated */
+    C2D_CNT_MULTIPLE = 7,    /* 'multiple scattering' events (imctrk2d.f:614) */
+    C2D_CNT_KILLED = 8,      /* flights ended by ew <= wtmin (imctrk2d.f:470) */
+    C2D_CNT_SEGOVF = 9,      /* histories whose ray crossed more zones than the fast path holds */
+    C2D_CNT_LITERAL = 10,    /* trial flights executed literally (collision candidates) */
+    C2D_CNT_QPEAK = 11,      /* peak number of queued collision tasks */
+    C2D_CNT_FATAL = 12,      /* device-side fatal conditions (0 on success) */
+    C2D_CNT_SEGMENTS = 13    /* zone crossings of the collision-free rays */
+};
+
+/* Escape record: the 7 doubles of imcleak2d.f:171,181 (t_bound,xnu,ew,rpre,zpre,wmu,phi). */
+typedef struct { double t_bound, xnu, ew, rpre, zpre, wmu, phi; } c2d_event;
+
+/* ---- life cycle --------------------------------------------------------------------------- */
+int c2d_create(c2d_ctx **ctx, int device);                 /* binds the context to a CUDA device */
+int c2d_init(c2d_ctx *ctx, const c2d_dims *dims);          /* after setup / read_record */
+int c2d_destroy(c2d_ctx *ctx);
+const char *c2d_last_error(void);
+int c2d_version(void);
+
+/* ---- one IMC time step: same order as xec (xec2d.f:141-193) --------------------------------- */
+int c2d_step_begin(c2d_ctx *ctx, const c2d_step_in *in);   /* replaces imcgen2d's worker branch + the broadcasts */
+int c2d_imcfield(c2d_ctx *ctx);                            /* == field_calc (imcfield2d.f:57-148) on the resident bank */
+int c2d_imcvol(c2d_ctx *ctx, int64_t first, int64_t count, int64_t stride);
+        /* == sum over zones of vol_calc (imcvol2d_para.f:90-414); this context tracks the volume
+           histories with global index first, first+stride, ... (count of them; count<0 = all that remain),
+           which is how histories shard over GPUs */
+int c2d_sync(c2d_ctx *ctx);                                /* drains the scattering queue, waits for the device */
+int c2d_tally_read(c2d_ctx *ctx, c2d_tallies *out);        /* D2H copy of this context's (or the reduced) tallies */
+int c2d_tally_device(c2d_ctx *ctx, double **fp64_buf, int64_t *n_fp64, int64_t **i64_buf, int64_t *n_i64);
+        /* device pointers of the packed tally buffers, for the per-step all-reduce
+           (cens_add_up + E_add_up + xec_add + graphics_collect: update2d.f:1931-2083, xec2d.f:325-394) */
+
+/* ---- census bank: write_record / read_record contract (census2d.f:1-76) ---------------------- */
+int c2d_census_count(c2d_ctx *ctx, int64_t *n);
+int c2d_census_export(c2d_ctx *ctx, double *dbuf, int32_t *ibuf, uint64_t *sid, int64_t cap, int64_t *n);
+        /* dbuf[6n] = rpre,zpre,wmu,phi,ew,xnu ; ibuf[6n] = jgpsp,jgplc,jgpmu,jph,kph,seed (imctrk2d.f:566-580);
+           sid[n] = replay stream id (may be NULL) */
+int c2d_census_import(c2d_ctx *ctx, const double *dbuf, const int32_t *ibuf, const uint64_t *sid, int64_t n);
+int c2d_events_drain(c2d_ctx *ctx, c2d_event *buf, int64_t cap, int64_t *n);
+
+/* ---- Fokker-Planck update (update2d.f:337-1741 FP_calc, batched over zones) ------------------- */
+typedef struct {
+    int first_zone, n_zones, zone_stride;       /* this context's share of the zones (0-based zone ids) */
+    int inj_switch, inj_dis, g2var_switch, pick_sw;
+    double time, dt;
+    double inj_g1, inj_g2, inj_p, inj_t, inj_gg, inj_sigma, inj_L, inj_v, pick_rate;
+    double r_esc, r_acc;
+    double r_flare, z_flare, t_flare, sigma_r, sigma_z, sigma_t, flare_amp; int cf_sentinel;
+    const double *f_nt;                         /* [zone][num_nt] */
+    const double *n_field;                      /* [zone][nphfield]; NULL = use this step's device tally */
+    const double *n_e, *B_field, *tea, *tna, *vol;   /* [zone] */
+    const double *F_IC;                         /* [num_nt][nphfield] (icloss2d.f); NULL = build on device */
+} c2d_fp_in;
+
+typedef struct {
+    double *f_nt, *Pnt;                         /* [zone][num_nt] */
+    double *n_e, *Te_new, *gmin, *gmax, *p_nth, *amxwl;   /* [zone] */
+    int32_t *fp_steps;                          /* [zone] sub-steps taken */
+    double dT_max, E_tot_old, E_tot_new, hr_total, hr_st_total;
+} c2d_fp_out;
+
+int c2d_ic_loss(c2d_ctx *ctx, double *F_IC_out);           /* == IC_loss (icloss2d.f:1-125); F_IC_out may be NULL */
+int c2d_update_fp(c2d_ctx *ctx, const c2d_fp_in *in, c2d_fp_out *out);
+
+/* ---- COMMON <-> dense packing helpers (host code) ------------------------------------------- */
+void c2d_pack_bin_first(const double *common, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *dense);
+void c2d_pack_bin_last(const double *common, int jmax, int kmax, int nbin, int nz, int nr, double *dense);
+void c2d_unpack_bin_first(const double *dense, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *common);
+void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int nz, int nr, double *common);
+
+/* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
+int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);   /* CUDA-event time per kernel family */
+int c2d_tally_bench(c2d_ctx *ctx, int64_t n_events, int kind, float *ms, int64_t *bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,28 @@
+// tests/emu/emu_launch.cpp -- TEST INFRASTRUCTURE ONLY: serial "launches" of the kernels for the g++ build.
+#include "cuda_runtime.h"
+EmuDim blockIdx, threadIdx, blockDim, gridDim;
+#include "../../compton2d_b200/csrc/c2d_track.cu"
+
+namespace c2d {
+template <int SRC> static void run_hist(const Params &p, long long first, long long n, long long stride)
+{
+    blockDim.x = 128;
+    const long long blocks = (n + 127) / 128;
+    for (long long b = 0; b < blocks; b++)
+        for (unsigned t = 0; t < 128; t++) {
+            blockIdx.x = (unsigned)b; threadIdx.x = t;
+            k_history<SRC>(p, first, n, stride);
+        }
+}
+void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<0>(p, first, n, stride); }
+void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<1>(p, first, n, stride); }
+void launch_collisions(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t)
+{
+    blockDim.x = 128;
+    for (long long b = 0; b < n_in; b++)
+        for (unsigned t = 0; t < 128; t++) {
+            blockIdx.x = (unsigned)b; threadIdx.x = t;
+            k_collisions(p, q_in, n_in);
+        }
+}
+}  // namespace c2d
