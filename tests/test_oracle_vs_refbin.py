@@ -93,3 +93,45 @@ def test_ran1_lattice():
     assert (u >= 0).all() and (u < 1).all()
     assert np.allclose(u * 1e7, np.round(u * 1e7), atol=1e-6)
     assert 0.45 < u.mean() < 0.55
+
+
+# ------------------------------------------------------------------------------------------ Fokker-Planck
+@pytest.mark.parametrize("name,cyc", [("small", 1), ("small", 2), ("annulus", 1), ("annulus", 2)])
+def test_fp_calc_matches_reference_binary(name, cyc):
+    """FP_calc (update2d.f:337-1741) over all zones: snapshot E (before the FP farm) -> F (after).
+    The per-zone job message (fp_mpi.f:612-700) delivers the master's tea, tna, B_field, Eloss_*, ecens,
+    ec_old, n_field, ... so those inputs are read from F; what FP_calc itself overwrites (f_nt, Pnt, n_e,
+    amxwl, gmin, gmax, p_nth, Te_new, f_pair) starts from E."""
+    from oracle_golden import rel
+    g = Golden(name)
+    E, F = g.snap(f"c{cyc}_E"), g.snap(f"c{cyc}_F")
+    o = new_oracle(E)
+    load_snapshot(o, F)
+    a = o.a
+    for v in ("f_nt", "pnt", "n_e", "amxwl", "gmin", "gmax", "p_nth", "te_new", "f_pair"):
+        setattr(a, cname(v), E[v])
+    for s_ in ("E_tot_old", "E_tot_new", "hr_total", "hr_st_total", "dT_max"):
+        o[s_] = 0.0
+    nz, nr = o.dims["nz"], o.dims["nr"]
+    for zone in range(1, nz * nr + 1):
+        o.fp_calc(zone)
+    assert (a.fp_steps[: nz * nr] == 5).all()
+    for v, tol in (("f_nt", 1e-12), ("pnt", 1e-12)):
+        assert rel(getattr(a, cname(v))[: nz * nr * 200].reshape(nz, nr, 200), F[v]) < tol, v
+    for v, tol in (("n_e", 1e-14), ("amxwl", 1e-11), ("gmin", 0.0), ("gmax", 0.0), ("p_nth", 0.0), ("te_new", 1e-14)):
+        assert rel(getattr(a, cname(v))[: nz * nr].reshape(nz, nr), F[v]) <= tol, v
+    for gk, ck in (("e_tot_old", "E_tot_old"), ("e_tot_new", "E_tot_new"), ("hr_total", "hr_total"),
+                   ("hr_st_total", "hr_st_total"), ("dt_max", "dT_max"), ("f_t_implicit", "f_t_implicit")):
+        assert abs(o[ck] - float(F[gk])) <= 1e-12 * abs(float(F[gk])), ck
+
+
+def test_ic_loss_matches_reference_binary():
+    """IC_loss (icloss2d.f) vs the F_IC table in the reference binary's COMMON /icl/."""
+    g = Golden("small")
+    F = g.snap("c1_F")
+    o = new_oracle(F)
+    load_snapshot(o, F)
+    o.a.F_IC[:] = 0
+    o.L.orc_IC_loss(o.p)
+    fic = o.a.F_IC[: 200 * 400].reshape(200, 400)
+    assert np.abs(fic / F.f_ic - 1).max() < 1e-8      # f_Li series stops at |term/sum| < 1e-10
