@@ -98,10 +98,22 @@ static int drain_queue(Ctx *c)
         CU(cudaMemsetAsync(c->d_qcount + other, 0, 8, c->stream));
         Params p = c->P;
         p.q_out = c->d_q[other]; p.q_out_count = c->d_qcount + other;
+        CU(cudaMemsetAsync(c->d_qcount + 2, 0, 8, c->stream));
         c->timer_begin(1);
-        launch_collisions(p, c->d_q[c->q_cur], (long long)n, c->stream);
+        launch_children(p, c->d_q[c->q_cur], (long long)n, c->stream);
         c->timer_end();
         CU(cudaGetLastError());
+        unsigned long long n3 = 0;
+        CU(cudaMemcpyAsync(&n3, c->d_qcount + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (n3 > (unsigned long long)c->q_cap)
+            return fail(C2D_EINVAL, "split3 queue overflow: %llu tasks > collision_capacity %lld", n3, (long long)c->q_cap);
+        if (n3) {
+            c->timer_begin(2);
+            launch_split3(p, c->d_q3, (long long)n3, c->stream);
+            c->timer_end();
+            CU(cudaGetLastError());
+        }
         CU(cudaMemsetAsync(c->d_qcount + c->q_cur, 0, 8, c->stream));
         c->q_cur = other;
         c->P.q_out = c->d_q[c->q_cur]; c->P.q_out_count = c->d_qcount + c->q_cur;
@@ -156,7 +168,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_f64); cudaFree(c->d_i64);
-    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_qcount); cudaFree(c->d_sig);
+    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_qcount); cudaFree(c->d_sig);
     cudaFree(c->d_sigS);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
     c->fp_free();
@@ -244,8 +256,9 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     for (int b = 0; b < 2; b++) { int rc = alloc_bank(c->bank[b], c->census_cap); if (rc) return rc; }
     CU(cudaMalloc(&c->d_events, (size_t)c->event_cap * 7 * 8));
     for (int b = 0; b < 2; b++) CU(cudaMalloc(&c->d_q[b], (size_t)c->q_cap * sizeof(CollTask)));
-    CU(cudaMalloc(&c->d_qcount, 16));
-    CU(cudaMemset(c->d_qcount, 0, 16));
+    CU(cudaMalloc(&c->d_q3, (size_t)c->q_cap * sizeof(CollTask)));
+    CU(cudaMalloc(&c->d_qcount, 32));
+    CU(cudaMemset(c->d_qcount, 0, 32));
 
     Params &P = c->P;
     memset(&P, 0, sizeof P);
@@ -275,6 +288,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     P.census_cap = c->census_cap; P.events = c->d_events; P.event_cap = c->event_cap;
     c->q_cur = 0;
     P.q_out = c->d_q[0]; P.q_out_count = c->d_qcount; P.q_cap = c->q_cap;
+    P.q3 = c->d_q3; P.q3_count = c->d_qcount + 2;
     c->n_census = 0;
 
     if (d->sigma_mode == 1) { int rc = c->sigma_setup(); if (rc) return rc; }

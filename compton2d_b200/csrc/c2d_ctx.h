@@ -24,7 +24,7 @@ struct Ctx {
     double *d_sig = nullptr, *d_sigS = nullptr;
     int64_t *d_prefix = nullptr;
     unsigned long long *d_i64 = nullptr, *d_qcount = nullptr;
-    CollTask *d_q[2] = {nullptr, nullptr};
+    CollTask *d_q[2] = {nullptr, nullptr}, *d_q3 = nullptr;
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;
     // offsets (in doubles) into d_step / d_f64, (in int64) into d_i64
@@ -44,7 +44,7 @@ struct Ctx {
     // Fokker-Planck state (c2d_fp.cu)
     FpState *fp = nullptr;
     void fp_free();
-    // CUDA-event timing per kernel family: 0 history, 1 collisions, 2 sigma table, 3 FP, 4 tally bench
+    // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3, 3 FP, 4 sigma table, 5 tally bench
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_which;

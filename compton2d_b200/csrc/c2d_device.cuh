@@ -86,6 +86,8 @@ struct Params {
     unsigned long long event_cap;
     CollTask *q_out;                   // collision tasks produced by this launch
     unsigned long long *q_out_count;
+    CollTask *q3;                      // children that triggered the 3rd split (imctrk2d.f:639)
+    unsigned long long *q3_count;
     unsigned long long q_cap;
 };
 

@@ -4,9 +4,10 @@
 //                    (imcvol2d_para.f:392 for volume sources, imcfield2d.f:128 for census photons):
 //                    source sampling, the collision-free ray, split1 trial draws, absorption
 //                    deposition, the recombined scat_flag = 0 flight with its census / leak tallies.
-//   k_collisions     one block per Compton collision found by any flight: the split2 (and split3)
-//                    children of imctrk2d.f:619-689, each scattered by compb2d and flown with
-//                    scat_flag = 1; collisions of those flights go to the next generation's queue.
+//   k_children       one thread per (Compton collision, child): the split2 loop of imctrk2d.f:619-689 --
+//                    compb2d, then the scat_flag = 1 flight; collisions of those flights go to the next
+//                    generation's queue, children that trigger the 3rd split go to the split3 queue.
+//   k_split3         one thread per (3rd-split child, ii2): imctrk2d.f:641-669.
 #include "c2d_host.h"
 
 namespace c2d {
@@ -210,56 +211,69 @@ __global__ void __launch_bounds__(128) k_history(const Params p, long long first
     history(p, P0, S_entry);
 }
 
-__global__ void __launch_bounds__(128) k_collisions(const Params p, const CollTask *q_in, long long n_in)
+// scattered photon after compb2d: tallies of imctrk2d.f:657-661 / 672-677, then the scat_flag = 1 flight
+__device__ __forceinline__ void child_flight(const Params &p, Photon &P, Rng &rng, int zi, double ewold, int i_gam)
 {
-    const long long b = blockIdx.x;
-    if (b >= n_in) return;
-    const CollTask task = q_in[b];
+    int dummy = 0;
+    atomic_add_f64(p.edep + zi, P.ew - ewold);
+    atomic_add_f64(p.E_IC + (i_gam - 1), P.ew - ewold);
+    count(p, CNT_CMCOUNT2);
+    if (P.phi > 2.0 * kPi) P.phi = P.phi - 2.0 * kPi;
+    const double wt = 1.e-10 * P.ew;                               // wtmin of the new imctrk2d(1) frame
+    const double colmfp = -log(rng.next(p));
+    const int end = fly<MODE_CHILD>(p, P, rng, wt, colmfp, nullptr, dummy);
+    if (end == END_COLLISION) {
+        count(p, CNT_MULTIPLE); count(p, CNT_CMCOUNT1);
+        push_collision(p, P, rng.sid);
+    }
+}
+
+// one thread per (collision, child ii): the split2 loop of imctrk2d.f:619-689.  Children that trigger
+// the 3rd split (l.639) are queued for k_split3 instead of looping split3 times in one thread.
+__global__ void __launch_bounds__(128) k_children(const Params p, const CollTask *q_in, long long n_in)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_in * p.split2) return;
+    const CollTask &task = q_in[idx / p.split2];
+    const int ii = (int)(idx % p.split2) + 1;
     const double ewcsv = task.p.ew / p.split2;                    // l.617
     const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
-    for (int ii = threadIdx.x + 1; ii <= p.split2; ii += blockDim.x) {
-        const uint64_t S_child = mix64(task.sid, (uint64_t)ii);
-        Rng rng; rng.stream(S_child);
-        Photon P = task.p;
-        P.ew = ewcsv;
-        double ewold = P.ew;
-        int i_gam = 0, dummy = 0;
-        compb2d(p, rng, P, i_gam);
-        if (P.ew > ewold * p.split2 * p.split1 * p.spl3_trg) {     // 3rd split, l.639-669
-            ewold = ewcsv / p.split3;
-            for (int ii2 = 1; ii2 <= p.split3; ii2++) {
-                rng.stream(mix64(S_child, (uint64_t)ii2));
-                do {
-                    P = task.p;
-                    P.ew = ewcsv / p.split3;
-                    compb2d(p, rng, P, i_gam);
-                } while (P.ew <= ewold * p.split2 * p.split1 * p.spl3_trg);
-                atomic_add_f64(p.edep + zi, P.ew - ewold);
-                atomic_add_f64(p.E_IC + (i_gam - 1), P.ew - ewold);
-                count(p, CNT_CMCOUNT2);
-                if (P.phi > 2.0 * kPi) P.phi = P.phi - 2.0 * kPi;
-                const double wt = 1.e-10 * P.ew;
-                const double colmfp = -log(rng.next(p));
-                const int end = fly<MODE_CHILD>(p, P, rng, wt, colmfp, nullptr, dummy);
-                if (end == END_COLLISION) {
-                    count(p, CNT_MULTIPLE); count(p, CNT_CMCOUNT1);
-                    push_collision(p, P, rng.sid);
-                }
-            }
-        } else {
-            atomic_add_f64(p.edep + zi, P.ew - ewold);
-            atomic_add_f64(p.E_IC + (i_gam - 1), P.ew - ewold);
-            count(p, CNT_CMCOUNT2);
-            if (P.phi > 2.0 * kPi) P.phi = P.phi - 2.0 * kPi;
-            const double wt = 1.e-10 * P.ew;
-            const double colmfp = -log(rng.next(p));
-            const int end = fly<MODE_CHILD>(p, P, rng, wt, colmfp, nullptr, dummy);
-            if (end == END_COLLISION) {
-                count(p, CNT_MULTIPLE); count(p, CNT_CMCOUNT1);
-                push_collision(p, P, rng.sid);
-            }
-        }
+    const uint64_t S_child = mix64(task.sid, (uint64_t)ii);
+    Rng rng; rng.stream(S_child);
+    Photon P = task.p;
+    P.ew = ewcsv;
+    const double ewold = P.ew;
+    int i_gam = 0;
+    compb2d(p, rng, P, i_gam);
+    if (P.ew > ewold * p.split2 * p.split1 * p.spl3_trg) {         // 3rd split, l.639-669
+        const unsigned long long n = atomicAdd(p.q3_count, 1ull);
+        if (n >= p.q_cap) { count(p, CNT_FATAL); return; }
+        CollTask &t = p.q3[n];
+        t.p = task.p; t.pad = 0; t.sid = S_child;
+        return;
     }
+    child_flight(p, P, rng, zi, ewold, i_gam);
+}
+
+// one thread per (3rd-split child, ii2): imctrk2d.f:641-669
+__global__ void __launch_bounds__(128) k_split3(const Params p, const CollTask *q3_in, long long n_in)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n_in * p.split3) return;
+    const CollTask &task = q3_in[idx / p.split3];
+    const int ii2 = (int)(idx % p.split3) + 1;
+    const double ewcsv = task.p.ew / p.split2;
+    const double ewold = ewcsv / p.split3;
+    const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
+    Rng rng; rng.stream(mix64(task.sid, (uint64_t)ii2));
+    Photon P;
+    int i_gam = 0;
+    do {
+        P = task.p;
+        P.ew = ewcsv / p.split3;
+        compb2d(p, rng, P, i_gam);
+    } while (P.ew <= ewold * p.split2 * p.split1 * p.spl3_trg);
+    child_flight(p, P, rng, zi, ewold, i_gam);
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -278,10 +292,17 @@ void launch_history_census(const Params &p, long long first, long long n, long l
     const long long blocks = (n + threads - 1) / threads;
     k_history<1><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
 }
-void launch_collisions(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st)
+void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st)
 {
     if (n_in <= 0) return;
-    k_collisions<<<(unsigned)n_in, 128, 0, st>>>(p, q_in, n_in);
+    const long long n = n_in * p.split2;
+    k_children<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q_in, n_in);
+}
+void launch_split3(const Params &p, const CollTask *q3_in, long long n_in, cudaStream_t st)
+{
+    if (n_in <= 0) return;
+    const long long n = n_in * p.split3;
+    k_split3<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q3_in, n_in);
 }
 #endif  // C2D_EMU
 

@@ -16,13 +16,16 @@ template <int SRC> static void run_hist(const Params &p, long long first, long l
 }
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<0>(p, first, n, stride); }
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<1>(p, first, n, stride); }
-void launch_collisions(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t)
+template <class K> static void run_flat(K kern, const Params &p, const CollTask *q, long long n_in, long long per)
 {
     blockDim.x = 128;
-    for (long long b = 0; b < n_in; b++)
+    const long long n = n_in * per, blocks = (n + 127) / 128;
+    for (long long b = 0; b < blocks; b++)
         for (unsigned t = 0; t < 128; t++) {
             blockIdx.x = (unsigned)b; threadIdx.x = t;
-            k_collisions(p, q_in, n_in);
+            kern(p, q, n_in);
         }
 }
+void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t) { if (n_in > 0) run_flat(k_children, p, q_in, n_in, p.split2); }
+void launch_split3(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t) { if (n_in > 0) run_flat(k_split3, p, q_in, n_in, p.split3); }
 }  // namespace c2d
