@@ -68,7 +68,7 @@ struct Params {
     uint32_t key0, key1;
     double rmin, zmin, dt, time;
     // static tables
-    const double *z, *r, *E_ph, *E_field, *E_gg, *gnt, *gam0, *beta, *dgam, *hu, *Elcmin, *Elcmax, *mu;
+    const double *z, *r, *E_ph, *E_field, *E_gg, *gnt, *gam0, *opb, *dgam, *kn_pref, *kn_a1, *kn_a2, *hu, *Elcmin, *Elcmax, *mu;
     // per-step tables
     const double *kappa_tot, *eps_tot, *eps_th, *f_nt, *Pnt, *n_e, *f_pair, *k_gg, *tbbl;
     const double *ewsv, *Eloss_th, *Eloss_tot, *zsurf;
@@ -185,52 +185,53 @@ __device__ __forceinline__ int mu_group(const Params &p, double w)
 }
 
 // ------------------------------------------------------------------------------------------ comtot
-// comtot2d.f:356-433 for argument -x with x > 0 (the only call pattern: intg_v -> dilog(-x))
-__device__ __forceinline__ double dilog_neg(double x)
+// Chebyshev coefficients of CERNLIB C332 (comtot2d.f:371-378)
+static __device__ __constant__ double kDilogC[20] = {0.42996693560813697e0, 0.40975987533077105e0,
+    -0.01858843665014592e0, 0.00145751084062268e0, -0.00014304184442340e0,
+    0.1588415541880e-4, -0.190784959387e-5, 0.024195180854e-5,
+    -0.003193341274e-5, 0.000434545063e-5, -0.000060578480e-5,
+    0.000008612098e-5, -0.000001244332e-5, 0.000000182256e-5,
+    -0.000000027007e-5, 0.000000004042e-5, -0.000000000610e-5,
+    0.000000000093e-5, -0.000000000014e-5, 0.000000000002e-5};
+
+// intg_v(xa) - intg_v(xb) of comtot2d.f:238, with both dilogarithms (comtot2d.f:356-433, argument -x, x > 0:
+// only the branches T <= 1 and T > 1 are reachable) evaluated side by side: two independent Clenshaw
+// recurrences keep the FP64 pipe busy.  The recurrence uses explicit FMAs (the only place the tracker departs
+// from the reference's operation-by-operation arithmetic; it moves sigma by <= 1 ulp).
+__device__ __forceinline__ double intg_v_diff(double xa, double xb)
 {
-    const double C[20] = {0.42996693560813697e0, 0.40975987533077105e0,
-        -0.01858843665014592e0, 0.00145751084062268e0, -0.00014304184442340e0,
-        0.1588415541880e-4, -0.190784959387e-5, 0.024195180854e-5,
-        -0.003193341274e-5, 0.000434545063e-5, -0.000060578480e-5,
-        0.000008612098e-5, -0.000001244332e-5, 0.000000182256e-5,
-        -0.000000027007e-5, 0.000000004042e-5, -0.000000000610e-5,
-        0.000000000093e-5, -0.000000000014e-5, 0.000000000002e-5};
     const double PI2 = kPi * kPi, PI6 = PI2 / 6, PI12 = PI2 / 12;
-    if (x == 1.0) return -PI12;                 // dilog(-1)
-    const double T = x;
-    double Y, S, A;
-    if (T <= 1) { Y = T; S = 1; A = 0; }
-    else { Y = 1 / T; S = -1; const double B1 = log(T); A = PI6 + 0.5 * B1 * B1; }
-    const double H = Y + Y - 1, ALFA = H + H;
-    double B0 = 0, B1 = 0, B2 = 0;
+    double Ya, Sa, Aa, Yb, Sb, Ab;
+    if (xa <= 1) { Ya = xa; Sa = 1; Aa = 0; } else { Ya = 1 / xa; Sa = -1; const double l = log(xa); Aa = PI6 + 0.5 * l * l; }
+    if (xb <= 1) { Yb = xb; Sb = 1; Ab = 0; } else { Yb = 1 / xb; Sb = -1; const double l = log(xb); Ab = PI6 + 0.5 * l * l; }
+    const double Ha = Ya + Ya - 1, ALa = Ha + Ha, Hb = Yb + Yb - 1, ALb = Hb + Hb;
+    double B0a = 0, B1a = 0, B2a = 0, B0b = 0, B1b = 0, B2b = 0;
 #pragma unroll
     for (int i = 19; i >= 0; i--) {
-        B0 = C[i] + ALFA * B1 - B2;
-        B2 = B1; B1 = B0;
+        const double c = kDilogC[i];
+        B0a = fma(ALa, B1a, c) - B2a; B2a = B1a; B1a = B0a;
+        B0b = fma(ALb, B1b, c) - B2b; B2b = B1b; B1b = B0b;
     }
-    return -(S * (B0 - H * B2) + A);
+    double da = -(Sa * (B0a - Ha * B2a) + Aa), db = -(Sb * (B0b - Hb * B2b) + Ab);
+    if (xa == 1.0) da = -PI12;                  // dilog(-1), comtot2d.f:385-386
+    if (xb == 1.0) db = -PI12;
+    const double va = (-xa / 2.0 + 0.5 / (1.0 + xa)) + 4.0 * da + (9.0 + xa + 8.0 / xa) * log(1.0 + xa);
+    const double vb = (-xb / 2.0 + 0.5 / (1.0 + xb)) + 4.0 * db + (9.0 + xb + 8.0 / xb) * log(1.0 + xb);
+    return va - vb;
 }
 
-// comtot2d.f:337-352
-__device__ __forceinline__ double intg_v(double x)
-{
-    const double intg_1 = -x / 2.0 + 0.5 / (1.0 + x);
-    const double intg_2 = 4.0 * dilog_neg(x);
-    const double intg_3 = (9.0 + x + 8.0 / x) * log(1.0 + x);
-    return (intg_1 + intg_2 + intg_3);
-}
-
-// sigma_E of comtot2d.f:234-239 for electron bin i (0-based) and x = xnu/511
+// sigma_E of comtot2d.f:234-239 for electron bin i (0-based) and x = xnu/511.  kn_pref = 9.375e-2 sigma_T /
+// gamma^2 / beta, kn_a1 = 2 gamma (1 + beta), kn_a2 = 2 gamma (1 - beta) are the reference's own
+// left-to-right products, formed once on the host.
 __device__ __forceinline__ double sigma_kn_bin(const Params &p, int i, double x)
 {
     const double sigthom = 6.6516e-25;
-    const double gamma0 = p.gam0[i], betta = p.beta[i];
-    if (x * gamma0 * (1 + betta) < 1.e-2) return sigthom * (1.0 - 2.0 * x * gamma0);
-    return 9.375e-2 * sigthom / (gamma0 * gamma0) / betta / (x * x) *
-           (intg_v(2 * gamma0 * (1 + betta) * x) - intg_v(2 * gamma0 * (1 - betta) * x));
+    const double gamma0 = p.gam0[i];
+    if (x * gamma0 * p.opb[i] < 1.e-2) return sigthom * (1.0 - 2.0 * x * gamma0);
+    return p.kn_pref[i] / (x * x) * intg_v_diff(p.kn_a1[i] * x, p.kn_a2[i] * x);
 }
 
-// comac for up to four zones at once (one pass over the electron bins): comtot2d.f:219-247
+// comac for up to four zones, one thread walking all electron bins: comtot2d.f:219-247
 static __device__ __noinline__ void comtot_zones(const Params &p, double xnu, const int *zi, int nzn, double *comac)
 {
     const double x = xnu / 5.11e2;
@@ -249,6 +250,39 @@ static __device__ __noinline__ void comtot_zones(const Params &p, double xnu, co
     const double c[4] = {c0, c1, c2, c3};
     for (int m = 0; m < nzn; m++) comac[m] = (c[m] < 1.e-40) ? 1.e-40 : p.n_e[zi[m]] * c[m];
 }
+
+#ifndef C2D_EMU
+// The same sum with the warp cooperating on ONE photon energy: electron bins strided over the lanes
+// (coalesced f_nt rows, one K-N evaluation per lane and bin, no divergence on the photon energy), then a
+// butterfly reduction.  Every lane of the warp must call it; returns comac[0..3] for the zones zi[0..nzn).
+__device__ __forceinline__ void comtot_zones_warp(const Params &p, double xnu, int z0, int z1, int z2, int z3, int nzn,
+                                                  double (&comac)[4])
+{
+    const int lane = threadIdx.x & 31;
+    const double x = xnu / 5.11e2;
+    double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    const double *f0 = p.f_nt + (size_t)z0 * p.num_nt, *f1 = p.f_nt + (size_t)z1 * p.num_nt;
+    const double *f2 = p.f_nt + (size_t)z2 * p.num_nt, *f3 = p.f_nt + (size_t)z3 * p.num_nt;
+    for (int i = lane; i < p.num_nt - 1; i += 32) {
+        const double sE = sigma_kn_bin(p, i, x), dg = p.dgam[i];
+        c0 = c0 + sE * f0[i] * dg;
+        if (nzn > 1) c1 = c1 + sE * f1[i] * dg;
+        if (nzn > 2) c2 = c2 + sE * f2[i] * dg;
+        if (nzn > 3) c3 = c3 + sE * f3[i] * dg;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+        c3 += __shfl_xor_sync(0xffffffffu, c3, o);
+    }
+    comac[0] = (c0 < 1.e-40) ? 1.e-40 : p.n_e[z0] * c0;
+    comac[1] = (c1 < 1.e-40) ? 1.e-40 : p.n_e[z1] * c1;
+    comac[2] = (c2 < 1.e-40) ? 1.e-40 : p.n_e[z2] * c2;
+    comac[3] = (c3 < 1.e-40) ? 1.e-40 : p.n_e[z3] * c3;
+}
+#endif
 
 // sigma_mode 1: per-step table ln sigma(zone, ln E), Catmull-Rom cubic in ln E
 __device__ __forceinline__ double comtot_table(const Params &p, int zi, double xnu)

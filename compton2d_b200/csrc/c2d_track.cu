@@ -66,60 +66,87 @@ static __device__ __noinline__ int literal_trial_slow(const Params &p, const Pho
     return 0;
 }
 
-__device__ __forceinline__ void history(const Params &p, const Photon &P0, uint64_t S_entry)
+// One top-level history = one imctrk2d(-1) call.  Every lane of the warp runs this function (inactive lanes
+// carry `active = false`) because step B evaluates comtot warp-cooperatively.
+__device__ __forceinline__ void history(const Params &p, bool active, const Photon &P0, uint64_t S_entry)
 {
     const double wtmin = 1.e-10 * P0.ew;                          // imctrk2d.f:82,92
     Photon T0 = P0;
     T0.ew = P0.ew / p.split1;                                     // l.110
     const uint64_t S_trials = mix64(S_entry, kTagTrials);
-    count(p, CNT_HISTORIES);
+    if (active) count(p, CNT_HISTORIES);
 
     // A: the collision-free ray
     Seg segs[kMaxSeg];
     int nseg = 0, nscat = 0, nlit = 0;
     bool overflow = false;
-    {
+    if (active) {
         Photon Q = T0; Rng dummy; dummy.stream(0);
         const int endA = fly<MODE_PRE>(p, Q, dummy, wtmin, 0.0, segs, nseg);
         overflow = (endA == END_OVERFLOW);
-        if (endA == END_LOWEW && nseg == 0) return;   // ew < 1e-40 at entry: nothing is tallied (l.161)
+        if (endA == END_LOWEW && nseg == 0) active = false;   // ew < 1e-40 at entry: nothing is tallied (l.161)
     }
-    if (overflow) {
+    if (active && overflow) {
         count(p, CNT_SEGOVF);
         for (int t = 0; t < p.split1; t++)
             nscat += literal_trial_slow(p, T0, S_trials, t, rng_uniform(p, S_trials, (uint32_t)t), wtmin);
         count(p, CNT_TRIALS, (unsigned long long)p.split1);
-    } else {
+    }
+    const bool fast = active && !overflow;
     // B: sigma_sc per crossing (comac_ar cache of l.175-183: one comtot per zone and history)
     if (p.sigma_mode == 1) {
-        for (int s = 0; s < nseg; s++) segs[s].sigsc = 1.0 * comtot_table(p, segs[s].zi, T0.xnu) * segs[s].sigsc;
+        if (fast) for (int s = 0; s < nseg; s++) segs[s].sigsc = 1.0 * comtot_table(p, segs[s].zi, T0.xnu) * segs[s].sigsc;
     } else {
-        unsigned have = 0u;
-        for (int s0 = 0; s0 < nseg; s0++) {
-            if (have & (1u << s0)) continue;
-            int zl[4], nzn = 0;
-            for (int s = s0; s < nseg && nzn < 4; s++) {
+        unsigned have = fast ? 0u : 0xffffffffu;
+        for (;;) {
+            // up to four not-yet-evaluated distinct zones of this lane's ray
+            int zl[4] = {0, 0, 0, 0}, nzn = 0;
+            for (int s = 0; s < nseg && nzn < 4; s++) {
                 if (have & (1u << s)) continue;
                 bool seen = false;
                 for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
                 if (!seen) zl[nzn++] = segs[s].zi;
             }
-            double cm[4];
+            double cm[4] = {0, 0, 0, 0};
+#ifndef C2D_EMU
+            unsigned todo = __ballot_sync(0xffffffffu, nzn > 0);
+            if (!todo) break;
+            while (todo) {                                         // the warp serves one lane's photon at a time
+                const int src = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const double xs = __shfl_sync(0xffffffffu, T0.xnu, src);
+                const int a0 = __shfl_sync(0xffffffffu, zl[0], src), a1 = __shfl_sync(0xffffffffu, zl[1], src);
+                const int a2 = __shfl_sync(0xffffffffu, zl[2], src), a3 = __shfl_sync(0xffffffffu, zl[3], src);
+                const int an = __shfl_sync(0xffffffffu, nzn, src);
+                double r[4];
+                comtot_zones_warp(p, xs, a0, a1, a2, a3, an, r);
+                if ((int)(threadIdx.x & 31) == src) { cm[0] = r[0]; cm[1] = r[1]; cm[2] = r[2]; cm[3] = r[3]; }
+            }
+#else
+            if (nzn == 0) break;
             comtot_zones(p, T0.xnu, zl, nzn, cm);
-            for (int s = s0; s < nseg; s++) {
+#endif
+            for (int s = 0; s < nseg; s++) {
                 if (have & (1u << s)) continue;
                 for (int m = 0; m < nzn; m++)
                     if (zl[m] == segs[s].zi) { segs[s].sigsc = 1.0 * cm[m] * segs[s].sigsc; have |= (1u << s); break; }
             }
         }
     }
+    if (fast) {
     // C: the split1 trial draws (l.126-156).  A trial collides only if -ln(u) is within the ray's
     // scattering depth, i.e. u >= thr; everything below thr provably does not (margins >> rounding).
     double tau = 0.0; bool has_rand = false;
     for (int s = 0; s < nseg; s++) { tau += segs[s].sigsc * segs[s].L; has_rand |= !(segs[s].sigabs * segs[s].L <= .00001); }
     const double thr = exp(-tau * (1.0 + 1.e-12)) * (1.0 - 1.e-12);
+    // u = (K + 0.5) 2^-52 >= thr  <=>  K >= ceil(thr 2^52 - 0.5): the filter runs on integers
+    const double tk = thr * 4503599627370496.0 - 0.5;
+    const uint64_t Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
     double pr_acc[kMaxSeg];
     if (has_rand) for (int s = 0; s < nseg; s++) pr_acc[s] = 0.0;
+    double wmu_c = T0.wmu;
+    if (wmu_c > 1.0) wmu_c = 1.0;
+    if (wmu_c < -1.0) wmu_c = -1.0;
     const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
     for (int t2 = 0; 2 * t2 < p.split1; t2++) {
         uint32_t o[4];
@@ -128,11 +155,14 @@ __device__ __forceinline__ void history(const Params &p, const Photon &P0, uint6
         for (int h = 0; h < 2; h++) {
             const int t = 2 * t2 + h;
             if (t >= p.split1) break;
-            const double u = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
-            if (u >= thr && trial_collides(segs, nseg, -log(u))) {
-                nlit++;
-                nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
-                continue;
+            const uint64_t K = ((((uint64_t)(h ? o[3] : o[1])) << 32) | (h ? o[2] : o[0])) >> 12;
+            if (K >= Kthr) {
+                const double u = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
+                if (trial_collides(segs, nseg, -log(u))) {
+                    nlit++;
+                    nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
+                    continue;
+                }
             }
             if (has_rand) {       // absorption-point draws of l.451-459 (they only move prdep)
                 const uint64_t S_t = mix64(S_trials, (uint64_t)(t + 1));
@@ -142,8 +172,8 @@ __device__ __forceinline__ void history(const Params &p, const Photon &P0, uint6
                     if (g.sigabs * g.L <= .00001) continue;
                     const double mb_ran = rng_uniform(p, S_t, k++);
                     const double sstar = -log(1. - mb_ran * g.dele / g.ew) / g.sigabs;
-                    const double denom = sqrt(g.rpre * g.rpre + 2. * T0.wmu * g.rpre * sstar + sstar * sstar);
-                    pr_acc[s] += g.dele * ((T0.wmu * g.rpre + sstar) / denom) * kCLight;
+                    const double denom = sqrt(g.rpre * g.rpre + 2. * wmu_c * g.rpre * sstar + sstar * sstar);
+                    pr_acc[s] += g.dele * ((wmu_c * g.rpre + sstar) / denom) * kCLight;
                 }
             }
         }
@@ -153,20 +183,17 @@ __device__ __forceinline__ void history(const Params &p, const Photon &P0, uint6
     // D: absorption deposition of the non-colliding trials (l.465-466), identical per trial
     {
         const double n_nc = (double)(p.split1 - nlit);
-        double wmu = T0.wmu;
-        if (wmu > 1.0) wmu = 1.0;
-        if (wmu < -1.0) wmu = -1.0;
         if (n_nc > 0)
             for (int s = 0; s < nseg; s++) {
                 const Seg &g = segs[s];
                 atomic_add_f64(p.edep + g.zi, n_nc * g.dele);
-                if (g.sigabs * g.L <= .00001) atomic_add_f64(p.prdep + g.zi, n_nc * (g.dele * wmu * kCLight));
+                if (g.sigabs * g.L <= .00001) atomic_add_f64(p.prdep + g.zi, n_nc * (g.dele * wmu_c * kCLight));
                 else atomic_add_f64(p.prdep + g.zi, pr_acc[s]);
             }
     }
-    }   // !overflow
+    }   // fast
     // E: recombined flight of the unscattered weight (l.698-712)
-    if (p.split1 - nscat > 0) {
+    if (active && p.split1 - nscat > 0) {
         Photon F = P0;
         F.ew = (p.split1 - nscat) * T0.ew;
         Rng rng; rng.stream(mix64(S_entry, kTagF0));
@@ -180,10 +207,11 @@ template <int SRC>
 __global__ void __launch_bounds__(128) k_history(const Params p, long long first, long long n, long long stride)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n) return;
-    Photon P0;
-    uint64_t S_entry;
-    if (SRC == 0) {
+    const bool active = idx < n;
+    Photon P0 = {1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1, 1, 0, 0, 1};
+    uint64_t S_entry = 0;
+    if (!active) {
+    } else if (SRC == 0) {
         const long long h = first + idx * stride;
         // zone (1-based) with nsv_prefix[zone-1] <= h < nsv_prefix[zone]
         int lo = 0, hi = p.nzone;            // invariant: prefix[lo] <= h < prefix[hi]
@@ -208,7 +236,7 @@ __global__ void __launch_bounds__(128) k_history(const Params p, long long first
         if (P0.wmu < -1.0) P0.wmu = -1.0;
         S_entry = p.in.sid[h];
     }
-    history(p, P0, S_entry);
+    history(p, active, P0, S_entry);
 }
 
 // scattered photon after compb2d: tallies of imctrk2d.f:657-661 / 672-677, then the scat_flag = 1 flight

@@ -154,6 +154,91 @@ class Compton2d:
         _l.check(self.L.c2d_tally_device(self.h, C.byref(pf), C.byref(nf), C.byref(pi), C.byref(ni)))
         return _CudaView(pf.value, nf.value, "<f8"), _CudaView(pi.value, ni.value, "<i8")
 
+    # ------------------------------------------------------------------ Fokker-Planck
+    def IC_loss(self):
+        """== IC_loss (icloss2d.f:1-125): build F_IC[num_nt][nphfield] on the device and return it."""
+        F = np.zeros((self.num_nt, self.nphfield))
+        _l.check(self.L.c2d_ic_loss(self.h, F.ctypes.data))
+        return F
+
+    def update(self, *, time, dt, f_nt, Pnt, n_e, B_field, tea, tna, vol, Eloss_sy, ec_old, turb_lev, gmin, gmax,
+               p_nth, amxwl, f_pair=None, n_field=None, ecens=None, F_IC=None, lnL=20.0, r_esc=0.3, r_acc=1.0,
+               inj=None, flare=None, group=None):
+        """== update minus MPI (update2d.f:7-334): FP_calc for this rank's zones (zone % world == rank), then
+        the exchange of the updated electron state (FP_recv_result + FP_end_bcast, fp_mpi.f:926,1017-1079).
+        `n_field` / `ecens` default to this step's tallies on the device (after graphics_collect they are
+        the reduced ones).  Returns a dict of the FP outputs for all zones."""
+        nzn, N = self.nzone, self.num_nt
+        inj = dict(inj or {})
+        flare = dict(flare or {})
+        keep = dict(f_nt=_d(f_nt, nzn * N, "f_nt"), Pnt=_d(Pnt, nzn * N, "Pnt"), n_field=_d(n_field, nzn * self.nphfield, "n_field"),
+                    ecens=_d(ecens, nzn, "ecens"), n_e=_d(n_e, nzn, "n_e"), B_field=_d(B_field, nzn, "B_field"),
+                    tea=_d(tea, nzn, "tea"), tna=_d(tna, nzn, "tna"), vol=_d(vol, nzn, "vol"), f_pair=_d(f_pair, nzn, "f_pair"),
+                    Eloss_sy=_d(Eloss_sy, nzn, "Eloss_sy"), ec_old=_d(ec_old, nzn, "ec_old"), turb_lev=_d(turb_lev, nzn, "turb_lev"),
+                    F_IC=_d(F_IC, N * self.nphfield, "F_IC"))
+        fi = _l.FpIn(first_zone=self.rank, n_zones=-1, zone_stride=self.world, inj_switch=int(inj.get("inj_switch", 0)),
+                     inj_dis=int(inj.get("inj_dis", 2)), g2var_switch=int(inj.get("g2var_switch", 0)),
+                     pick_sw=int(inj.get("pick_sw", 0)), cf_sentinel=int(flare.get("cf_sentinel", 0)), ncycle=self.ncycle,
+                     time=float(time), dt=float(dt), lnL=float(lnL), inj_g1=float(inj.get("inj_g1", 1e2)),
+                     inj_g2=float(inj.get("inj_g2", 3e4)), inj_p=float(inj.get("inj_p", 1.0)), inj_t=float(inj.get("inj_t", 1.2e6)),
+                     inj_gg=float(inj.get("inj_gg", 1e2)), inj_sigma=float(inj.get("inj_sigma", 1e1)),
+                     inj_L=float(inj.get("inj_L", 5e40)), inj_v=float(inj.get("inj_v", 2.9965e10)),
+                     pick_rate=float(inj.get("pick_rate", 0.8e-3)), r_esc=float(r_esc), r_acc=float(r_acc),
+                     r_flare=float(flare.get("r_flare", 0.0)), z_flare=float(flare.get("z_flare", 0.0)),
+                     t_flare=float(flare.get("t_flare", 1e6)), sigma_r=float(flare.get("sigma_r", 1e15)),
+                     sigma_z=float(flare.get("sigma_z", 1e15)), sigma_t=float(flare.get("sigma_t", 1e6)),
+                     flare_amp=float(flare.get("flare_amp", 10.0)))
+        for k, v in keep.items():
+            setattr(fi, k, _p(v))
+        out = dict(f_nt=np.zeros((nzn, N)), Pnt=np.zeros((nzn, N)), n_e=np.zeros(nzn), Te_new=np.zeros(nzn),
+                   gmin=np.array(gmin, dtype=_F).ravel().copy(), gmax=np.array(gmax, dtype=_F).ravel().copy(),
+                   p_nth=np.array(p_nth, dtype=_F).ravel().copy(), amxwl=np.array(amxwl, dtype=_F).ravel().copy(),
+                   f_pair=np.zeros(nzn), zone_E_old=np.zeros(nzn), zone_E_new=np.zeros(nzn), zone_hr=np.zeros(nzn),
+                   zone_hr_st=np.zeros(nzn), zone_dT=np.zeros(nzn))
+        steps = np.zeros(nzn, np.int32)
+        fo = _l.FpOut()
+        for k, v in out.items():
+            setattr(fo, k, _p(v))
+        fo.fp_steps = steps.ctypes.data_as(_l.ip)
+        _l.check(self.L.c2d_update_fp(self.h, C.byref(fi), C.byref(fo)))
+        out["fp_steps"] = steps
+        if self.world > 1:
+            self._exchange_fp(out, group)
+        # totals over all zones in zone order (E_add_up, update2d.f:2002-2083)
+        out.update(E_tot_old=float(np.sum(out["zone_E_old"])), E_tot_new=float(np.sum(out["zone_E_new"])),
+                   hr_total=float(np.sum(out["zone_hr"])), hr_st_total=float(np.sum(out["zone_hr_st"])),
+                   dT_max=float(np.max(out["zone_dT"])), dr=fo.dr, dz=fo.dz, f_t_implicit=fo.f_t_implicit)
+        # update2d.f:268-274: the temperature carried to the next step is clamped to [5, 1000] keV
+        out["tea"] = np.minimum(1.0e3, np.maximum(5.0, out["Te_new"]))
+        return out
+
+    def _exchange_fp(self, out, group=None):
+        """Every rank owns zones rank::world; a sum over ranks of the zero-padded outputs is the all-gather
+        of the updated electron state (the reference's FP_recv_result + FP_end_bcast)."""
+        import torch
+        import torch.distributed as dist
+        own = np.zeros(self.nzone, bool)
+        own[self.rank::self.world] = True
+        keys = ["f_nt", "Pnt", "n_e", "Te_new", "gmin", "gmax", "p_nth", "amxwl", "f_pair", "zone_E_old", "zone_E_new",
+                "zone_hr", "zone_hr_st", "zone_dT"]
+        parts = []
+        for k in keys:
+            a = out[k].reshape(self.nzone, -1).astype(_F).copy()
+            a[~own] = 0.0
+            parts.append(a.ravel())
+        parts.append(np.where(own, out["fp_steps"], 0).astype(_F))
+        flat = np.concatenate(parts)
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.from_numpy(flat).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        flat = t.cpu().numpy()
+        off = 0
+        for k in keys:
+            n = out[k].size
+            out[k] = flat[off: off + n].reshape(out[k].shape).copy()
+            off += n
+        out["fp_steps"] = flat[off: off + self.nzone].astype(np.int32)
+
     # ------------------------------------------------------------------ results
     def tallies(self):
         nzn = self.nzone

@@ -41,18 +41,20 @@ class Tallies(C.Structure):
 
 class FpIn(C.Structure):
     _fields_ = [(n, C.c_int) for n in ("first_zone", "n_zones", "zone_stride", "inj_switch", "inj_dis",
-                                       "g2var_switch", "pick_sw")] + \
-        [(n, C.c_double) for n in ("time", "dt", "inj_g1", "inj_g2", "inj_p", "inj_t", "inj_gg", "inj_sigma",
+                                       "g2var_switch", "pick_sw", "cf_sentinel", "ncycle")] + \
+        [(n, C.c_double) for n in ("time", "dt", "lnL", "inj_g1", "inj_g2", "inj_p", "inj_t", "inj_gg", "inj_sigma",
                                    "inj_L", "inj_v", "pick_rate", "r_esc", "r_acc", "r_flare", "z_flare",
                                    "t_flare", "sigma_r", "sigma_z", "sigma_t", "flare_amp")] + \
-        [("cf_sentinel", C.c_int)] + \
-        [(n, dp) for n in ("f_nt", "n_field", "n_e", "B_field", "tea", "tna", "vol", "F_IC")]
+        [(n, dp) for n in ("f_nt", "Pnt", "n_field", "ecens", "n_e", "B_field", "tea", "tna", "vol", "f_pair",
+                           "Eloss_sy", "ec_old", "turb_lev", "F_IC")]
 
 
 class FpOut(C.Structure):
-    _fields_ = [(n, dp) for n in ("f_nt", "Pnt", "n_e", "Te_new", "gmin", "gmax", "p_nth", "amxwl")] + \
+    _fields_ = [(n, dp) for n in ("f_nt", "Pnt", "n_e", "Te_new", "gmin", "gmax", "p_nth", "amxwl", "f_pair")] + \
         [("fp_steps", ip)] + \
-        [(n, C.c_double) for n in ("dT_max", "E_tot_old", "E_tot_new", "hr_total", "hr_st_total")]
+        [(n, dp) for n in ("zone_E_old", "zone_E_new", "zone_hr", "zone_hr_st", "zone_dT")] + \
+        [(n, C.c_double) for n in ("dT_max", "E_tot_old", "E_tot_new", "hr_total", "hr_st_total", "dr", "dz",
+                                   "f_t_implicit")]
 
 
 COUNTERS = ["ndxout", "cmcount1", "cmcount2", "lkcount", "nevents", "histories", "trials", "multiple", "killed",

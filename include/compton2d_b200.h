@@ -148,25 +148,35 @@ int c2d_census_export(c2d_ctx *ctx, double *dbuf, int32_t *ibuf, uint64_t *sid, 
 int c2d_census_import(c2d_ctx *ctx, const double *dbuf, const int32_t *ibuf, const uint64_t *sid, int64_t n);
 int c2d_events_drain(c2d_ctx *ctx, c2d_event *buf, int64_t cap, int64_t *n);
 
-/* ---- Fokker-Planck update (update2d.f:337-1741 FP_calc, batched over zones) ------------------- */
+/* ---- Fokker-Planck update (update2d.f:337-1741 FP_calc, batched over zones) -------------------
+ * Inputs are what the per-zone job message carries (fp_mpi.f:612-700) plus the broadcast scalars
+ * (fp_mpi.f:579-600); outputs what FP_send_result returns (fp_mpi.f:860-930) and FP_end_bcast
+ * re-broadcasts (fp_mpi.f:1017-1079).  Only the zones first_zone, first_zone+zone_stride, ... (n_zones of
+ * them; n_zones < 0 = all that remain) are updated -- the multi-GPU partition; the other zones' output
+ * entries are left untouched.  Pair terms (n_pos, dn_pp, dne_pa, dnp_pa) are taken as zero: they are inert
+ * in the reference's MPI build. */
 typedef struct {
-    int first_zone, n_zones, zone_stride;       /* this context's share of the zones (0-based zone ids) */
-    int inj_switch, inj_dis, g2var_switch, pick_sw;
-    double time, dt;
+    int first_zone, n_zones, zone_stride;       /* 0-based zone ids */
+    int inj_switch, inj_dis, g2var_switch, pick_sw, cf_sentinel, ncycle;
+    double time, dt, lnL;
     double inj_g1, inj_g2, inj_p, inj_t, inj_gg, inj_sigma, inj_L, inj_v, pick_rate;
     double r_esc, r_acc;
-    double r_flare, z_flare, t_flare, sigma_r, sigma_z, sigma_t, flare_amp; int cf_sentinel;
-    const double *f_nt;                         /* [zone][num_nt] */
-    const double *n_field;                      /* [zone][nphfield]; NULL = use this step's device tally */
-    const double *n_e, *B_field, *tea, *tna, *vol;   /* [zone] */
-    const double *F_IC;                         /* [num_nt][nphfield] (icloss2d.f); NULL = build on device */
+    double r_flare, z_flare, t_flare, sigma_r, sigma_z, sigma_t, flare_amp;
+    const double *f_nt, *Pnt;                   /* [zone][num_nt] */
+    const double *n_field;                      /* [zone][nphfield]; NULL = this step's (reduced) device tally */
+    const double *ecens;                        /* [zone]; NULL = device tally */
+    const double *n_e, *B_field, *tea, *tna, *vol, *f_pair;   /* [zone] */
+    const double *Eloss_sy, *ec_old, *turb_lev; /* [zone] */
+    const double *F_IC;                         /* [num_nt][nphfield] (icloss2d.f); NULL = table built on device by c2d_ic_loss */
 } c2d_fp_in;
 
 typedef struct {
     double *f_nt, *Pnt;                         /* [zone][num_nt] */
-    double *n_e, *Te_new, *gmin, *gmax, *p_nth, *amxwl;   /* [zone] */
+    double *n_e, *Te_new, *gmin, *gmax, *p_nth, *amxwl, *f_pair;   /* [zone] (p_nth, gmin, gmax: in/out) */
     int32_t *fp_steps;                          /* [zone] sub-steps taken */
-    double dT_max, E_tot_old, E_tot_new, hr_total, hr_st_total;
+    double *zone_E_old, *zone_E_new, *zone_hr, *zone_hr_st, *zone_dT;   /* [zone] per-zone terms of the sums below (may be NULL) */
+    double dT_max, E_tot_old, E_tot_new, hr_total, hr_st_total;   /* over this call's zones, summed in zone order */
+    double dr, dz, f_t_implicit;                /* COMMON /d_update/ leftovers of the last zone (update2d.f:233-243) */
 } c2d_fp_out;
 
 int c2d_ic_loss(c2d_ctx *ctx, double *F_IC_out);           /* == IC_loss (icloss2d.f:1-125); F_IC_out may be NULL */

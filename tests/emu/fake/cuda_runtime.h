@@ -13,6 +13,7 @@
 #define __device__
 #define __global__
 #define __host__
+#define __constant__
 #define __forceinline__ inline
 #define __noinline__
 #define __launch_bounds__(...)
