@@ -109,10 +109,23 @@ static int drain_queue(Ctx *c)
         if (n3 > (unsigned long long)c->q_cap)
             return fail(C2D_EINVAL, "split3 queue overflow: %llu tasks > collision_capacity %lld", n3, (long long)c->q_cap);
         if (n3) {
-            c->timer_begin(2);
-            launch_split3(p, c->d_q3, (long long)n3, c->stream);
-            c->timer_end();
-            CU(cudaGetLastError());
+            // chunks of split3 tasks: attempts (one warp per sub-child) -> flight buffer -> flights
+            if (!c->d_flights) {
+                c->flight_cap = std::max<int64_t>((int64_t)p.split3, (int64_t)1 << 20);
+                CU(cudaMalloc(&c->d_flights, (size_t)c->flight_cap * sizeof(FlightTask)));
+            }
+            const long long per = std::max<long long>(1, c->flight_cap / p.split3);
+            for (long long t0 = 0; t0 < (long long)n3; t0 += per) {
+                const long long nt = std::min<long long>(per, (long long)n3 - t0);
+                c->timer_begin(2);
+                launch_split3_attempts(p, c->d_q3 + t0, nt, c->d_flights, c->stream);
+                c->timer_end();
+                CU(cudaGetLastError());
+                c->timer_begin(6);
+                launch_split3_flights(p, c->d_flights, nt * p.split3, c->stream);
+                c->timer_end();
+                CU(cudaGetLastError());
+            }
         }
         CU(cudaMemsetAsync(c->d_qcount + c->q_cur, 0, 8, c->stream));
         c->q_cur = other;
@@ -168,7 +181,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_f64); cudaFree(c->d_i64);
-    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_qcount); cudaFree(c->d_sig);
+    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_qcount); cudaFree(c->d_sig);
     cudaFree(c->d_sigS);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
     c->fp_free();

@@ -25,6 +25,8 @@ struct Ctx {
     int64_t *d_prefix = nullptr;
     unsigned long long *d_i64 = nullptr, *d_qcount = nullptr;
     CollTask *d_q[2] = {nullptr, nullptr}, *d_q3 = nullptr;
+    FlightTask *d_flights = nullptr;       // accepted 3rd-split sub-children of one chunk of split3 tasks
+    int64_t flight_cap = 0;
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;
     // offsets (in doubles) into d_step / d_f64, (in int64) into d_i64
@@ -44,7 +46,8 @@ struct Ctx {
     // Fokker-Planck state (c2d_fp.cu)
     FpState *fp = nullptr;
     void fp_free();
-    // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3, 3 FP, 4 sigma table, 5 tally bench
+    // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3_attempts, 3 FP, 4 sigma table, 5 tally bench,
+    // 6 k_split3_flights
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_which;

@@ -49,6 +49,14 @@ struct CollTask {            // a Compton collision waiting for its split2 child
     uint64_t sid;            // stream of the flight that collided
 };
 
+struct FlightTask {          // a scattered photon (after compb2d) waiting for its scat_flag = 1 flight
+    Photon p;
+    int i_gam, zi;
+    uint32_t d, pad;         // draw cursor of the stream `sid`
+    uint64_t sid;
+    double ewold;
+};
+
 struct Bank {                // census bank, SoA (commonblock.f:8,72 dbuf/ibuf record, imctrk2d.f:566-580)
     double *rpre, *zpre, *wmu, *phi, *ew, *xnu;
     uint32_t *bins;          // jgpsp | jgplc << 16 | jgpmu << 24
@@ -91,6 +99,37 @@ struct Params {
     unsigned long long q_cap;
 };
 
+// ------------------------------------------------------------------------------------------ warp
+// The kernels are written against a warp of kWarp lanes.  On the GPU kWarp = 32; the g++ debug build of
+// tests/emu (TEST INFRASTRUCTURE) runs the same sources with one-lane warps.
+#ifdef C2D_EMU
+constexpr int kWarp = 1;
+__device__ __forceinline__ int lane_id() { return 0; }
+__device__ __forceinline__ unsigned warp_ballot(bool pr) { return pr ? 1u : 0u; }
+template <class T> __device__ __forceinline__ T warp_shfl(T v, int) { return v; }
+template <class T> __device__ __forceinline__ T warp_shfl_xor(T v, int) { return v; }
+__device__ __forceinline__ int first_lane(unsigned m) { return __builtin_ffs((int)m) - 1; }
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) { return v; }
+#else
+constexpr int kWarp = 32;
+__device__ __forceinline__ int lane_id() { return (int)(threadIdx.x & 31u); }
+__device__ __forceinline__ unsigned warp_ballot(bool pr) { return __ballot_sync(0xffffffffu, pr); }
+template <class T> __device__ __forceinline__ T warp_shfl(T v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+template <class T> __device__ __forceinline__ T warp_shfl_xor(T v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ int first_lane(unsigned m) { return __ffs((int)m) - 1; }
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+__device__ __forceinline__ double warp_sum(double v)
+{
+    for (int o = kWarp / 2; o > 0; o >>= 1) v += warp_shfl_xor(v, o);
+    return v;
+}
+
 // ------------------------------------------------------------------------------------------ RNG
 __device__ __forceinline__ uint64_t mix64(uint64_t a, uint64_t b)
 {
@@ -106,9 +145,8 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
-        const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
-        const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
-        c0 = h1 ^ c1 ^ k0; c1 = l1; c2 = h0 ^ c3 ^ k1; c3 = l0;
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        c0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0; c1 = (uint32_t)p1; c2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
@@ -128,14 +166,48 @@ __device__ __forceinline__ double rng_uniform(const Params &p, uint64_t sid, uin
     return (d & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
 }
 
+// A stream cursor.  One Philox call yields draws 2m and 2m+1; the odd one is kept for the next call.
 struct Rng {
     uint64_t sid;
     uint32_t d;
-    __device__ __forceinline__ void stream(uint64_t s) { sid = s; d = 0; }
-    __device__ __forceinline__ double next(const Params &p) { return rng_uniform(p, sid, d++); }
+    uint32_t have;          // index of the cached (odd) draw, 0 = none (draw 0 is never odd)
+    double cached;
+    __device__ __forceinline__ void stream(uint64_t s) { sid = s; d = 0; have = 0; cached = 0.0; }
+    __device__ __forceinline__ double next(const Params &p)
+    {
+        const uint32_t i = d++;
+        if (i == have && i != 0u) return cached;
+        uint32_t o[4];
+        philox4x32_10((uint32_t)sid, (uint32_t)(sid >> 32), i >> 1, 0u, p.key0, p.key1, o);
+        if (i & 1u) return u52(o[2], o[3]);
+        cached = u52(o[2], o[3]); have = i + 1u;
+        return u52(o[0], o[1]);
+    }
 };
 
+// The xi of trial flight t (0-based) of a history with trial stream S: K = coarse16 << 36 | fine36,
+// u = (K + 0.5) 2^-52.  coarse = halfword (t & 7) of philox(S, t >> 3, 0); fine = low 36 bits of words 0,1 of
+// philox(S, t, 1).  Eight trials share one Philox call for the coarse part, and a trial whose coarse halfword
+// is below the threshold's never needs the fine part (see history()).
+__device__ __forceinline__ uint64_t trial_fine36(const Params &p, uint64_t S, uint32_t t)
+{
+    uint32_t o[4];
+    philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t, 1u, p.key0, p.key1, o);
+    return (((uint64_t)(o[1] & 0xFu)) << 32) | o[0];
+}
+__device__ __forceinline__ double trial_uniform(const Params &p, uint64_t S, uint32_t t)
+{
+    uint32_t o[4];
+    philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t >> 3, 0u, p.key0, p.key1, o);
+    const uint32_t w = o[(t & 7u) >> 1];
+    const uint64_t coarse = (t & 1u) ? (w >> 16) : (w & 0xFFFFu);
+    const uint64_t K = (coarse << 36) | trial_fine36(p, S, t);
+    return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+}
+
 // ------------------------------------------------------------------------------------------ small helpers
+// does either 16-bit half of w reach c (c <= 0x10000)?
+__device__ __forceinline__ bool half_ge(uint32_t w, uint32_t c) { return ((w & 0xFFFFu) >= c) | ((w >> 16) >= c); }
 __device__ __forceinline__ void atomic_add_f64(double *a, double v) { atomicAdd(a, v); }
 __device__ __forceinline__ void count(const Params &p, int which, unsigned long long n = 1ull)
 {
@@ -251,38 +323,45 @@ static __device__ __noinline__ void comtot_zones(const Params &p, double xnu, co
     for (int m = 0; m < nzn; m++) comac[m] = (c[m] < 1.e-40) ? 1.e-40 : p.n_e[zi[m]] * c[m];
 }
 
-#ifndef C2D_EMU
 // The same sum with the warp cooperating on ONE photon energy: electron bins strided over the lanes
 // (coalesced f_nt rows, one K-N evaluation per lane and bin, no divergence on the photon energy), then a
-// butterfly reduction.  Every lane of the warp must call it; returns comac[0..3] for the zones zi[0..nzn).
+// butterfly reduction.  Every lane of the warp must call it; returns comac[0..3] for the zones z0..z3 (nzn used).
 __device__ __forceinline__ void comtot_zones_warp(const Params &p, double xnu, int z0, int z1, int z2, int z3, int nzn,
                                                   double (&comac)[4])
 {
-    const int lane = threadIdx.x & 31;
+    const int lane = lane_id();
     const double x = xnu / 5.11e2;
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
     const double *f0 = p.f_nt + (size_t)z0 * p.num_nt, *f1 = p.f_nt + (size_t)z1 * p.num_nt;
     const double *f2 = p.f_nt + (size_t)z2 * p.num_nt, *f3 = p.f_nt + (size_t)z3 * p.num_nt;
-    for (int i = lane; i < p.num_nt - 1; i += 32) {
+    for (int i = lane; i < p.num_nt - 1; i += kWarp) {
         const double sE = sigma_kn_bin(p, i, x), dg = p.dgam[i];
         c0 = c0 + sE * f0[i] * dg;
         if (nzn > 1) c1 = c1 + sE * f1[i] * dg;
         if (nzn > 2) c2 = c2 + sE * f2[i] * dg;
         if (nzn > 3) c3 = c3 + sE * f3[i] * dg;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        c0 += __shfl_xor_sync(0xffffffffu, c0, o);
-        c1 += __shfl_xor_sync(0xffffffffu, c1, o);
-        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
-        c3 += __shfl_xor_sync(0xffffffffu, c3, o);
-    }
+    c0 = warp_sum(c0);
+    if (nzn > 1) c1 = warp_sum(c1);
+    if (nzn > 2) c2 = warp_sum(c2);
+    if (nzn > 3) c3 = warp_sum(c3);
     comac[0] = (c0 < 1.e-40) ? 1.e-40 : p.n_e[z0] * c0;
     comac[1] = (c1 < 1.e-40) ? 1.e-40 : p.n_e[z1] * c1;
     comac[2] = (c2 < 1.e-40) ? 1.e-40 : p.n_e[z2] * c2;
     comac[3] = (c3 < 1.e-40) ? 1.e-40 : p.n_e[z3] * c3;
 }
-#endif
+
+// one zone, warp-cooperative (every lane must call; all lanes get the result)
+__device__ __forceinline__ double comtot_zone_warp(const Params &p, double xnu, int zi)
+{
+    const int lane = lane_id();
+    const double x = xnu / 5.11e2;
+    double c0 = 0;
+    const double *f0 = p.f_nt + (size_t)zi * p.num_nt;
+    for (int i = lane; i < p.num_nt - 1; i += kWarp) c0 = c0 + sigma_kn_bin(p, i, x) * f0[i] * p.dgam[i];
+    c0 = warp_sum(c0);
+    return (c0 < 1.e-40) ? 1.e-40 : p.n_e[zi] * c0;
+}
 
 // sigma_mode 1: per-step table ln sigma(zone, ln E), Catmull-Rom cubic in ln E
 __device__ __forceinline__ double comtot_table(const Params &p, int zi, double xnu)
@@ -309,8 +388,12 @@ __device__ __forceinline__ double comtot_one(const Params &p, int zi, double xnu
 }
 
 // ------------------------------------------------------------------------------------------ scattering
+// Electron-bin tally of nth2d (nontherm2d.f:180).  A speculative caller (the 3rd-split attempts of k_split3)
+// passes a record instead of tallying: up to four bins packed 16 bits each, `n` counts every draw.
+struct ElRec { uint64_t bins; int n; };
+
 // nontherm2d.f:159-183
-__device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double &gamm, double &betb, int &ibin)
+__device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double &gamm, double &betb, int &ibin, ElRec *rec)
 {
     const double *P = p.Pnt + (size_t)zi * p.num_nt;
     double rnum = rng.next(p);
@@ -324,40 +407,50 @@ __device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double 
     const int i = lo;
     gamm = sqrt(p.gnt[i - 1] * p.gnt[i - 2]) + 1.0;
     betb = sqrt(1.0 - 1.0 / (gamm * gamm));
-    atomicAdd(p.nelectron + i, 1ull);
+    if (rec) {
+        if (rec->n < 4) rec->bins |= (uint64_t)i << (16 * rec->n);
+        rec->n++;
+    } else atomicAdd(p.nelectron + i, 1ull);
     ibin = i;
 }
 
-// compb_2d.f:1-318; P.jph/kph give the zone
-static __device__ __noinline__ void compb2d(const Params &p, Rng &rng, Photon &P, int &i_gam)
+// compb_2d.f:55-95 (label 100): draw the electron and the collision cosine, K-N rejection
+struct ElDraw { double gamm, betb, omeg, znue; };
+__device__ __forceinline__ void compb2d_electron(const Params &p, Rng &rng, int zi, double znu, ElDraw &e, int &i_gam, ElRec *rec)
 {
-    const double fuzz = 1.e-10, emasskev = 5.11e2;
-    const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
-    const double znu = P.xnu / emasskev;
-    double gamm, betb, omeg, znue, xknot, betz, sz, games, znues;
     for (;;) {                                       // label 100
-        nth2d(p, rng, zi, gamm, betb, i_gam);
-        omeg = 2.0 * rng.next(p) - 1.0;
-        C2D_CLAMP8(omeg);
+        nth2d(p, rng, zi, e.gamm, e.betb, i_gam, rec);
+        e.omeg = 2.0 * rng.next(p) - 1.0;
+        C2D_CLAMP8(e.omeg);
         const double tl = rng.next(p);
-        const double tr = 0.5 * (1.0 - betb * omeg);
-        if (tl > tr) omeg = -omeg;
-        C2D_CLAMP8(omeg);
-        znue = (1. - betb * omeg) * znu * gamm;
-        if (znue < 1.e-10) continue;
-        if (znue <= 1.e-2) {
-            xknot = 1.0 - znue * (2.0 - znue * (5.2 - znue * (13.3 - 1.144e3 * znue / 3.5e1)));
+        const double tr = 0.5 * (1.0 - e.betb * e.omeg);
+        if (tl > tr) e.omeg = -e.omeg;
+        C2D_CLAMP8(e.omeg);
+        e.znue = (1. - e.betb * e.omeg) * znu * e.gamm;
+        if (e.znue < 1.e-10) continue;
+        double xknot;
+        if (e.znue <= 1.e-2) {
+            xknot = 1.0 - e.znue * (2.0 - e.znue * (5.2 - e.znue * (13.3 - 1.144e3 * e.znue / 3.5e1)));
         } else {
-            const double znue3 = znue * znue * znue;
-            betz = 1.0 + 2.0 * znue;
-            const double gamz = znue * (znue - 2.0) - 2.0;
-            const double xxx = 4.0 * znue + 2.0 * znue3 * (1.0 + znue) / (betz * betz) + gamz * log(betz);
+            const double znue3 = e.znue * e.znue * e.znue;
+            const double betz = 1.0 + 2.0 * e.znue;
+            const double gamz = e.znue * (e.znue - 2.0) - 2.0;
+            const double xxx = 4.0 * e.znue + 2.0 * znue3 * (1.0 + e.znue) / (betz * betz) + gamz * log(betz);
             xknot = 3.75e-1 * xxx / znue3;
         }
         if (rng.next(p) > xknot) continue;
         break;
     }
-    betz = 1.0 + 2.0 * znue;
+}
+
+// compb_2d.f:96-318: rest-frame energy ratio, azimuths, Lorentz back-transform, new direction and bins
+__device__ __forceinline__ void compb2d_finish(const Params &p, Rng &rng, Photon &P, const ElDraw &e)
+{
+    const double fuzz = 1.e-10, emasskev = 5.11e2;
+    const double znu = P.xnu / emasskev;
+    const double gamm = e.gamm, betb = e.betb, omeg = e.omeg, znue = e.znue;
+    double sz, games;
+    const double betz = 1.0 + 2.0 * znue;
     for (;;) {                                       // labels 200/202
         sz = (1.0 + 2.0 * znue * rng.next(p)) / betz;
         games = 1.0 + (1.0 - 1.0 / sz) / znue;
@@ -367,7 +460,7 @@ static __device__ __noinline__ void compb2d(const Params &p, Rng &rng, Photon &P
         if (rng.next(p) * phat > tr) continue;
         break;
     }
-    znues = znue * sz;
+    const double znues = znue * sz;
     double wa, wb, swa;
     do {                                             // label 210
         wa = rng.next(p);
@@ -403,6 +496,14 @@ static __device__ __noinline__ void compb2d(const Params &p, Rng &rng, Photon &P
     P.xnu = xnus;
     P.wmu = wmus;
     P.phi = phis;
+}
+
+// compb_2d.f:1-318; P.jph/kph give the zone
+static __device__ __noinline__ void compb2d(const Params &p, Rng &rng, Photon &P, int &i_gam)
+{
+    ElDraw e;
+    compb2d_electron(p, rng, (P.jph - 1) * p.nr + (P.kph - 1), P.xnu / 5.11e2, e, i_gam, nullptr);
+    compb2d_finish(p, rng, P, e);
 }
 
 // ------------------------------------------------------------------------------------------ imcleak
@@ -479,157 +580,184 @@ __device__ __forceinline__ bool census_write(const Params &p, const Photon &P, R
 }
 
 // ------------------------------------------------------------------------------------------ the flight
-// One imctrk2d flight from label 110 (imctrk2d.f:158) until it ends.
+// One imctrk2d flight from label 110 (imctrk2d.f:158) until it ends, as a sequence of zone segments.
 //   MODE_PRE    collision-free ray of a history: no tallies, no draws; records the zone crossings
 //   MODE_TRIAL  scat_flag = -1 trial with a given colmfp: deposits absorption, stops at collision
 //   MODE_F0     scat_flag =  0 recombined flight: census / leak tallies, no deposition
 //   MODE_CHILD  scat_flag =  1 scattered photon: everything
-template <int MODE>
-__device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtmin, double colmfp, Seg *segs,
-                                int &nseg)
+constexpr int STEP_CONT = -1;
+
+struct FlightCtx {           // energy bins are constant along a flight (xnu only changes in compb2d)
+    int i_e, i_gg;
+    double dcol_f0;
+};
+__device__ __forceinline__ void flight_begin(const Params &p, double xnu, FlightCtx &c)
 {
-    // energy bins are constant along a flight (xnu only changes in compb2d)
-    const int i_e = scan_lt(p.E_ph, p.n_vol, P.xnu);
-    int i_gg = 0;
+    c.i_e = scan_lt(p.E_ph, p.n_vol, xnu);
+    c.i_gg = 0;
     if (p.pair_switch == 1)
-        for (i_gg = 1; i_gg <= p.n_gg; i_gg++)
-            if (P.xnu < p.E_gg[i_gg - 1]) break;
-    const double dcol_f0 = 100 * fmax(p.r[p.nr - 1], p.z[p.nz - 1]);
+        for (c.i_gg = 1; c.i_gg <= p.n_gg; c.i_gg++)
+            if (xnu < p.E_gg[c.i_gg - 1]) break;
+    c.dcol_f0 = 100 * fmax(p.r[p.nr - 1], p.z[p.nz - 1]);
+}
+
+// One segment (imctrk2d.f:207-586) of a photon with ew >= 1e-40 and |wmu| <= 1 in zone zi; sigsc is the
+// scattering opacity of this segment (comac * pair_enhance; ignored for MODE_PRE / MODE_F0).
+// Returns STEP_CONT when the flight goes on in the next zone, or the END_* code.
+template <int MODE>
+__device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, double wtmin, double &colmfp, double sigsc,
+                                        const FlightCtx &c, Seg *segs, int &s, int &nseg)
+{
+    const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
+    const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
+    const int i_e = c.i_e, i_gg = c.i_gg;
+    if (MODE == MODE_PRE || MODE == MODE_F0) sigsc = 0.0;
+    const double xqsqleft = (P.kph == 1) ? p.rmin * p.rmin : p.r[P.kph - 2] * p.r[P.kph - 2];
+    double dcol;
+    if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) dcol = colmfp / sigsc;
+    else if (MODE == MODE_F0) dcol = c.dcol_f0;
+    else dcol = INFINITY;
+    double trld; int ikind;
+    if (P.dcen <= dcol) { trld = P.dcen; ikind = 2; } else { trld = dcol; ikind = 3; }
+    // geometry, imctrk2d.f:233-365
+    double Eta = cos(P.phi);
+    const int Eta_switch = (P.phi <= kPi && P.phi >= 1.e-10) ? 1 : -1;
+    const double disp = Eta * P.rpre;
+    const double psq = P.rpre * P.rpre * (1. - Eta * Eta);
+    int kbnd, inout; double rbnd;
+    if (Eta < 0.0 && psq < xqsqleft) {
+        kbnd = P.kph - 1; inout = -1;
+        rbnd = (P.kph > 1) ? p.r[P.kph - 2] : p.rmin;
+    } else {
+        kbnd = P.kph; inout = 1;
+        rbnd = p.r[P.kph - 1];
+    }
+    double dpbsq = rbnd * rbnd - psq;
+    if (dpbsq < 1.e-6) dpbsq = 1.e-6;
+    const double disbr = (double)inout * sqrt(dpbsq) - disp;
+    double trldb = disbr / sqrt(1.0 - (P.wmu * P.wmu));
+    double f = disbr;
+    const double Zr = P.zpre + P.wmu * trldb;
+    const double zhigh = p.z[P.jph - 1], zlow = (P.jph == 1) ? p.zmin : p.z[P.jph - 2];
+    int knew, jnew; double Zbnd;
+    if (Zr > zhigh || Zr < zlow) {
+        const bool up = (Zr > zhigh);
+        Zbnd = up ? zhigh : zlow; knew = P.kph; jnew = up ? P.jph + 1 : P.jph - 1;
+        f = (Zbnd - P.zpre) * sqrt(1.0 - P.wmu * P.wmu) / P.wmu;
+        rbnd = sqrt(P.rpre * P.rpre + f * f + 2.0 * P.rpre * f * Eta);
+        trldb = sqrt(f * f + (Zbnd - P.zpre) * (Zbnd - P.zpre));
+    } else {
+        knew = P.kph + inout; jnew = P.jph;
+        rbnd = (kbnd > 0) ? p.r[kbnd - 1] : p.rmin;
+        Zbnd = Zr;
+    }
+    const double trldb_rec = trldb;
+    double rnew, znew;
+    if (trldb < trld) {
+        ikind = 1; trld = trldb; rnew = rbnd; znew = Zbnd;
+    } else {
+        jnew = P.jph; knew = P.kph;
+        f = trld * sqrt(1.0 - P.wmu * P.wmu);
+        rnew = sqrt(f * f + P.rpre * P.rpre + 2.0 * f * P.rpre * Eta);
+        znew = P.zpre + trld * P.wmu;
+    }
+    // absorption, imctrk2d.f:397-460
+    double sigabs = 1.e-40;
+    sigabs = sigabs + pair_enhance * p.kappa_tot[(size_t)zi * p.n_vol + (i_e - 1)];
+    double kgg_i = 0.0;
+    if (p.pair_switch == 1) {
+        const double *kg = p.k_gg + (size_t)zi * p.n_gg;
+        double kgg;
+        if (i_gg <= p.n_gg) kgg_i = kg[i_gg - 1];
+        if (P.xnu < p.E_gg[0]) kgg = (P.xnu / p.E_gg[0]) * kg[0];
+        else if (i_gg == p.n_gg) kgg = kg[p.n_gg - 1];
+        else if (i_gg > p.n_gg) kgg = 0.0;
+        else {
+            const double kgg0 = kg[i_gg - 1], kgg1 = kg[i_gg];
+            kgg = kgg0 + (P.xnu - p.E_gg[i_gg - 1]) * (kgg1 - kgg0) / (p.E_gg[i_gg] - p.E_gg[i_gg - 1]);
+        }
+        sigabs = sigabs + kgg;
+    }
+    if (sigabs < 1.e-40) sigabs = 1.e-40;
+    const double xabs = sigabs * trld;
+    const double ewnew = (xabs < 100.) ? P.ew * exp(-xabs) : 0.;
+    double deleabs;
+    if (P.xnu > 47.0 && sigabs > 1.e-40 && p.pair_switch == 1) deleabs = (P.ew - ewnew) * (sigabs - kgg_i) / sigabs;
+    else deleabs = P.ew - ewnew;
+    if (deleabs < 1.e-50) deleabs = 1.e-50;
+    if (MODE == MODE_PRE) {
+        if (s >= kMaxSeg) return END_OVERFLOW;
+        Seg &g = segs[s];
+        g.zi = zi; g.sigabs = sigabs; g.L = trld; g.trldb = trldb_rec; g.dcen = P.dcen; g.ew = P.ew;
+        g.dele = deleabs; g.rpre = P.rpre; g.sigsc = pair_enhance;    // sigsc := comac * pair_enhance later
+        nseg = s + 1;
+    } else {
+        double wmustar = P.wmu;
+        if (!(xabs <= .00001)) {
+            if (MODE == MODE_F0) rng.d++;                               // draw consumed, value unused (no deposit)
+            else {
+                const double mb_ran = rng.next(p);                      // always < ew/deleabs (>= 1)
+                const double sstar = -log(1. - mb_ran * deleabs / P.ew) / sigabs;
+                const double denom = sqrt(P.rpre * P.rpre + 2. * P.wmu * P.rpre * sstar + sstar * sstar);
+                wmustar = (P.wmu * P.rpre + sstar) / denom;
+            }
+        }
+        if (MODE != MODE_F0) {
+            atomic_add_f64(p.edep + zi, deleabs);
+            atomic_add_f64(p.prdep + zi, deleabs * wmustar * kCLight);
+        }
+    }
+    s++;
+    if (ewnew <= wtmin) { if (MODE != MODE_PRE) count(p, CNT_KILLED); return END_KILLED; }
+    P.ew = ewnew;
+    P.dcen = P.dcen - trld;
+    Eta = (f + Eta * P.rpre) / rnew;
+    if (Eta > 1.0) Eta = 1.0;
+    if (Eta < -1.0) Eta = -1.0;
+    P.phi = acos(Eta);
+    if (Eta_switch == -1) P.phi = 2.0 * kPi - P.phi;
+    P.rpre = rnew;
+    P.zpre = znew;
+    if (ikind == 1) {
+        colmfp = colmfp - sigsc * trld;
+        if (jnew == p.nz + 1 || jnew == 0 || knew == p.nr + 1 || knew == 0) {
+            P.jph = jnew; P.kph = knew;
+            if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
+            const int idead = imcleak(p, P);
+            count(p, CNT_LKCOUNT);
+            if (idead == 1) return END_LEAK;
+            return STEP_CONT;
+        }
+        P.kph = knew; P.jph = jnew;
+        return STEP_CONT;
+    }
+    if (ikind == 2) {
+        if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
+        return census_write(p, P, rng) ? END_CENSUS : END_FATAL;
+    }
+    return END_COLLISION;                                       // ikind == 3
+}
+
+// a whole flight by one thread (MODE_CHILD flights use child_flight_warp instead)
+template <int MODE>
+__device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtmin, double colmfp, Seg *segs, int &nseg)
+{
+    FlightCtx c;
+    flight_begin(p, P.xnu, c);
     int s = 0;
     for (;;) {                                                    // label 110
         if (P.ew < 1.e-40) return END_LOWEW;
         if (P.wmu > 1.0) P.wmu = 1.0;
         if (P.wmu < -1.0) P.wmu = -1.0;
-        const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
-        const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
-        double sigsc;
+        double sigsc = 0.0;
         if (MODE == MODE_TRIAL) sigsc = segs[s].sigsc;
-        else if (MODE == MODE_CHILD || MODE == MODE_TRIAL_SLOW) sigsc = 1.0 * comtot_one(p, zi, P.xnu) * pair_enhance;
-        else sigsc = 0.0;
-        const double xqsqleft = (P.kph == 1) ? p.rmin * p.rmin : p.r[P.kph - 2] * p.r[P.kph - 2];
-        double dcol;
-        if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) dcol = colmfp / sigsc;
-        else if (MODE == MODE_F0) dcol = dcol_f0;
-        else dcol = INFINITY;
-        double trld; int ikind;
-        if (P.dcen <= dcol) { trld = P.dcen; ikind = 2; } else { trld = dcol; ikind = 3; }
-        // geometry, imctrk2d.f:233-365
-        double Eta = cos(P.phi);
-        const int Eta_switch = (P.phi <= kPi && P.phi >= 1.e-10) ? 1 : -1;
-        const double disp = Eta * P.rpre;
-        const double psq = P.rpre * P.rpre * (1. - Eta * Eta);
-        int kbnd, inout; double rbnd;
-        if (Eta < 0.0 && psq < xqsqleft) {
-            kbnd = P.kph - 1; inout = -1;
-            rbnd = (P.kph > 1) ? p.r[P.kph - 2] : p.rmin;
-        } else {
-            kbnd = P.kph; inout = 1;
-            rbnd = p.r[P.kph - 1];
+        else if (MODE == MODE_TRIAL_SLOW) {
+            const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
+            const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
+            sigsc = 1.0 * comtot_one(p, zi, P.xnu) * pair_enhance;
         }
-        double dpbsq = rbnd * rbnd - psq;
-        if (dpbsq < 1.e-6) dpbsq = 1.e-6;
-        const double disbr = (double)inout * sqrt(dpbsq) - disp;
-        double trldb = disbr / sqrt(1.0 - (P.wmu * P.wmu));
-        double f = disbr;
-        const double Zr = P.zpre + P.wmu * trldb;
-        const double zhigh = p.z[P.jph - 1], zlow = (P.jph == 1) ? p.zmin : p.z[P.jph - 2];
-        int knew, jnew; double Zbnd;
-        if (Zr > zhigh || Zr < zlow) {
-            const bool up = (Zr > zhigh);
-            Zbnd = up ? zhigh : zlow; knew = P.kph; jnew = up ? P.jph + 1 : P.jph - 1;
-            f = (Zbnd - P.zpre) * sqrt(1.0 - P.wmu * P.wmu) / P.wmu;
-            rbnd = sqrt(P.rpre * P.rpre + f * f + 2.0 * P.rpre * f * Eta);
-            trldb = sqrt(f * f + (Zbnd - P.zpre) * (Zbnd - P.zpre));
-        } else {
-            knew = P.kph + inout; jnew = P.jph;
-            rbnd = (kbnd > 0) ? p.r[kbnd - 1] : p.rmin;
-            Zbnd = Zr;
-        }
-        const double trldb_rec = trldb;
-        double rnew, znew;
-        if (trldb < trld) {
-            ikind = 1; trld = trldb; rnew = rbnd; znew = Zbnd;
-        } else {
-            jnew = P.jph; knew = P.kph;
-            f = trld * sqrt(1.0 - P.wmu * P.wmu);
-            rnew = sqrt(f * f + P.rpre * P.rpre + 2.0 * f * P.rpre * Eta);
-            znew = P.zpre + trld * P.wmu;
-        }
-        // absorption, imctrk2d.f:397-460
-        double sigabs = 1.e-40;
-        sigabs = sigabs + pair_enhance * p.kappa_tot[(size_t)zi * p.n_vol + (i_e - 1)];
-        double kgg_i = 0.0;
-        if (p.pair_switch == 1) {
-            const double *kg = p.k_gg + (size_t)zi * p.n_gg;
-            double kgg;
-            if (i_gg <= p.n_gg) kgg_i = kg[i_gg - 1];
-            if (P.xnu < p.E_gg[0]) kgg = (P.xnu / p.E_gg[0]) * kg[0];
-            else if (i_gg == p.n_gg) kgg = kg[p.n_gg - 1];
-            else if (i_gg > p.n_gg) kgg = 0.0;
-            else {
-                const double kgg0 = kg[i_gg - 1], kgg1 = kg[i_gg];
-                kgg = kgg0 + (P.xnu - p.E_gg[i_gg - 1]) * (kgg1 - kgg0) / (p.E_gg[i_gg] - p.E_gg[i_gg - 1]);
-            }
-            sigabs = sigabs + kgg;
-        }
-        if (sigabs < 1.e-40) sigabs = 1.e-40;
-        const double xabs = sigabs * trld;
-        const double ewnew = (xabs < 100.) ? P.ew * exp(-xabs) : 0.;
-        double deleabs;
-        if (P.xnu > 47.0 && sigabs > 1.e-40 && p.pair_switch == 1) deleabs = (P.ew - ewnew) * (sigabs - kgg_i) / sigabs;
-        else deleabs = P.ew - ewnew;
-        if (deleabs < 1.e-50) deleabs = 1.e-50;
-        if (MODE == MODE_PRE) {
-            if (s >= kMaxSeg) return END_OVERFLOW;
-            Seg &g = segs[s];
-            g.zi = zi; g.sigabs = sigabs; g.L = trld; g.trldb = trldb_rec; g.dcen = P.dcen; g.ew = P.ew;
-            g.dele = deleabs; g.rpre = P.rpre; g.sigsc = pair_enhance;    // sigsc := comac * pair_enhance later
-            nseg = s + 1;
-        } else {
-            double wmustar = P.wmu;
-            if (!(xabs <= .00001)) {
-                if (MODE == MODE_F0) rng.d++;                               // draw consumed, value unused (no deposit)
-                else {
-                    const double mb_ran = rng.next(p);                      // always < ew/deleabs (>= 1)
-                    const double sstar = -log(1. - mb_ran * deleabs / P.ew) / sigabs;
-                    const double denom = sqrt(P.rpre * P.rpre + 2. * P.wmu * P.rpre * sstar + sstar * sstar);
-                    wmustar = (P.wmu * P.rpre + sstar) / denom;
-                }
-            }
-            if (MODE != MODE_F0) {
-                atomic_add_f64(p.edep + zi, deleabs);
-                atomic_add_f64(p.prdep + zi, deleabs * wmustar * kCLight);
-            }
-        }
-        s++;
-        if (ewnew <= wtmin) { if (MODE != MODE_PRE) count(p, CNT_KILLED); return END_KILLED; }
-        P.ew = ewnew;
-        P.dcen = P.dcen - trld;
-        Eta = (f + Eta * P.rpre) / rnew;
-        if (Eta > 1.0) Eta = 1.0;
-        if (Eta < -1.0) Eta = -1.0;
-        P.phi = acos(Eta);
-        if (Eta_switch == -1) P.phi = 2.0 * kPi - P.phi;
-        P.rpre = rnew;
-        P.zpre = znew;
-        if (ikind == 1) {
-            colmfp = colmfp - sigsc * trld;
-            if (jnew == p.nz + 1 || jnew == 0 || knew == p.nr + 1 || knew == 0) {
-                P.jph = jnew; P.kph = knew;
-                if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
-                const int idead = imcleak(p, P);
-                count(p, CNT_LKCOUNT);
-                if (idead == 1) return END_LEAK;
-                continue;
-            }
-            P.kph = knew; P.jph = jnew;
-            continue;
-        }
-        if (ikind == 2) {
-            if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
-            return census_write(p, P, rng) ? END_CENSUS : END_FATAL;
-        }
-        return END_COLLISION;                                       // ikind == 3
+        const int r = fly_step<MODE>(p, P, rng, wtmin, colmfp, sigsc, c, segs, s, nseg);
+        if (r != STEP_CONT) return r;
     }
 }
 

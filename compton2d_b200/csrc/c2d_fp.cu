@@ -49,12 +49,6 @@ struct FpState {
 };
 
 #ifndef C2D_EMU      // warp-cooperative device code: not part of the g++ debugging build (tests/emu)
-__device__ __forceinline__ double warp_sum(double v)
-{
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // volume2d.f:649-668
 __device__ __forceinline__ double gammln_dev(double xx)

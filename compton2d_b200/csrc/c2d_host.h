@@ -7,7 +7,8 @@ namespace c2d {
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st);
-void launch_split3(const Params &p, const CollTask *q3_in, long long n_in, cudaStream_t st);
+void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t st);
+void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st);
 void launch_sigma_table(const Params &p, double *table, int n_sig, double lnE0, double dlnE, cudaStream_t st);
 
 // Fokker-Planck (c2d_fp.cu)

@@ -7,7 +7,8 @@
 //   k_children       one thread per (Compton collision, child): the split2 loop of imctrk2d.f:619-689 --
 //                    compb2d, then the scat_flag = 1 flight; collisions of those flights go to the next
 //                    generation's queue, children that trigger the 3rd split go to the split3 queue.
-//   k_split3         one thread per (3rd-split child, ii2): imctrk2d.f:641-669.
+//   k_split3_attempts one warp per (3rd-split child, ii2): the rejection loop of imctrk2d.f:641-656,
+//                    attempts spread over the lanes; k_split3_flights: one thread per accepted sub-child.
 #include "c2d_host.h"
 
 namespace c2d {
@@ -89,7 +90,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     if (active && overflow) {
         count(p, CNT_SEGOVF);
         for (int t = 0; t < p.split1; t++)
-            nscat += literal_trial_slow(p, T0, S_trials, t, rng_uniform(p, S_trials, (uint32_t)t), wtmin);
+            nscat += literal_trial_slow(p, T0, S_trials, t, trial_uniform(p, S_trials, (uint32_t)t), wtmin);
         count(p, CNT_TRIALS, (unsigned long long)p.split1);
     }
     const bool fast = active && !overflow;
@@ -147,21 +148,29 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     double wmu_c = T0.wmu;
     if (wmu_c > 1.0) wmu_c = 1.0;
     if (wmu_c < -1.0) wmu_c = -1.0;
+    // K = coarse16 << 36 | fine36 (trial_uniform): a trial whose coarse halfword is below the threshold's
+    // cannot collide, and eight trials share one Philox call for their coarse halfwords
+    const uint32_t Cthr = (uint32_t)(Kthr >> 36);
     const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
-    for (int t2 = 0; 2 * t2 < p.split1; t2++) {
+    for (int t8 = 0; 8 * t8 < p.split1; t8++) {
         uint32_t o[4];
-        philox4x32_10(s_lo, s_hi, (uint32_t)t2, 0u, p.key0, p.key1, o);
+        philox4x32_10(s_lo, s_hi, (uint32_t)t8, 0u, p.key0, p.key1, o);
+        if (!has_rand && !(half_ge(o[0], Cthr) | half_ge(o[1], Cthr) | half_ge(o[2], Cthr) | half_ge(o[3], Cthr))) continue;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int t = 2 * t2 + h;
+        for (int h = 0; h < 8; h++) {
+            const int t = 8 * t8 + h;
             if (t >= p.split1) break;
-            const uint64_t K = ((((uint64_t)(h ? o[3] : o[1])) << 32) | (h ? o[2] : o[0])) >> 12;
-            if (K >= Kthr) {
-                const double u = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
-                if (trial_collides(segs, nseg, -log(u))) {
-                    nlit++;
-                    nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
-                    continue;
+            const uint32_t w = o[h >> 1];
+            const uint32_t coarse = (h & 1) ? (w >> 16) : (w & 0xFFFFu);
+            if (coarse >= Cthr) {
+                const uint64_t K = ((uint64_t)coarse << 36) | trial_fine36(p, S_trials, (uint32_t)t);
+                if (K >= Kthr) {
+                    const double u = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+                    if (trial_collides(segs, nseg, -log(u))) {
+                        nlit++;
+                        nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
+                        continue;
+                    }
                 }
             }
             if (has_rand) {       // absorption-point draws of l.451-459 (they only move prdep)
@@ -283,25 +292,70 @@ __global__ void __launch_bounds__(128) k_children(const Params p, const CollTask
     child_flight(p, P, rng, zi, ewold, i_gam);
 }
 
-// one thread per (3rd-split child, ii2): imctrk2d.f:641-669
-__global__ void __launch_bounds__(128) k_split3(const Params p, const CollTask *q3_in, long long n_in)
+// 3rd split, imctrk2d.f:641-669: every sub-child ii2 repeats compb2d until the scattered photon again exceeds
+// the trigger.  In Philox replay mode each pass of that rejection loop owns the stream mix64(S_sub, attempt), so
+// the passes can be evaluated in any order: one WARP per (3rd-split child, ii2), lane l tries attempt base + l + 1,
+// the lowest accepted attempt wins.  A pass whose electron cannot reach the trigger (gain <= (1+beta)^2 gamma^2
+// < 4 gamma^2) is rejected right after the electron draw.  The nth2d tallies of the passes up to and including
+// the winner are committed (the sequential loop made exactly those draws); later lanes' are discarded.
+__global__ void __launch_bounds__(128) k_split3_attempts(const Params p, const CollTask *q3_in, long long n_sub, FlightTask *out)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_in * p.split3) return;
-    const CollTask &task = q3_in[idx / p.split3];
-    const int ii2 = (int)(idx % p.split3) + 1;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    if (w >= n_sub) return;                                       // whole warps leave together
+    const int lane = lane_id();
+    const CollTask &task = q3_in[w / p.split3];
+    const int ii2 = (int)(w % p.split3) + 1;
     const double ewcsv = task.p.ew / p.split2;
     const double ewold = ewcsv / p.split3;
+    const double trigger = ewold * p.split2 * p.split1 * p.spl3_trg;
+    const double gain_min = (double)p.split2 * p.split1 * p.spl3_trg;
     const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
-    Rng rng; rng.stream(mix64(task.sid, (uint64_t)ii2));
-    Photon P;
-    int i_gam = 0;
-    do {
-        P = task.p;
-        P.ew = ewcsv / p.split3;
-        compb2d(p, rng, P, i_gam);
-    } while (P.ew <= ewold * p.split2 * p.split1 * p.spl3_trg);
-    child_flight(p, P, rng, zi, ewold, i_gam);
+    const double znu = task.p.xnu / 5.11e2;
+    const uint64_t S_sub = mix64(task.sid, (uint64_t)ii2);
+    Rng rng; Photon P; int i_gam = 0;
+    for (uint64_t base = 0;; base += kWarp) {
+        const uint64_t attempt = base + (uint64_t)lane + 1;
+        rng.stream(mix64(S_sub, attempt));
+        ElRec rec = {0ull, 0};
+        ElDraw e;
+        compb2d_electron(p, rng, zi, znu, e, i_gam, &rec);
+        bool ok = false;
+        if (4.0 * e.gamm * e.gamm * (1.0 + 1.e-9) > gain_min) {
+            P = task.p;
+            P.ew = ewcsv / p.split3;
+            compb2d_finish(p, rng, P, e);
+            ok = P.ew > trigger;
+        }
+        const unsigned m = warp_ballot(ok);
+        const int first = m ? first_lane(m) : kWarp;
+        if (lane <= first) {
+            if (rec.n <= 4) {
+                for (int k = 0; k < rec.n; k++) atomicAdd(p.nelectron + ((rec.bins >> (16 * k)) & 0xFFFFull), 1ull);
+            } else {                                              // > 4 K-N rejections in one pass: replay it, tallying
+                Rng r2; r2.stream(mix64(S_sub, attempt));
+                ElDraw e2; int ig2;
+                compb2d_electron(p, r2, zi, znu, e2, ig2, nullptr);
+            }
+        }
+        if (m) {
+            if (lane == first) {
+                FlightTask &f = out[w];
+                f.p = P; f.i_gam = i_gam; f.sid = rng.sid; f.d = rng.d; f.zi = zi; f.ewold = ewold;
+            }
+            return;
+        }
+    }
+}
+
+// one thread per accepted 3rd-split sub-child: tallies of l.657-661, then the scat_flag = 1 flight
+__global__ void __launch_bounds__(128) k_split3_flights(const Params p, const FlightTask *fl, long long n)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const FlightTask &f = fl[idx];
+    Photon P = f.p;
+    Rng rng; rng.stream(f.sid); rng.d = f.d;
+    child_flight(p, P, rng, f.zi, f.ewold, f.i_gam);
 }
 
 // ------------------------------------------------------------------------------------------ launchers
@@ -326,11 +380,16 @@ void launch_children(const Params &p, const CollTask *q_in, long long n_in, cuda
     const long long n = n_in * p.split2;
     k_children<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q_in, n_in);
 }
-void launch_split3(const Params &p, const CollTask *q3_in, long long n_in, cudaStream_t st)
+void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t st)
 {
-    if (n_in <= 0) return;
-    const long long n = n_in * p.split3;
-    k_split3<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q3_in, n_in);
+    if (n_tasks <= 0) return;
+    const long long n = n_tasks * p.split3 * kWarp;               // one warp per sub-child
+    k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q3_in, n_tasks * p.split3, out);
+}
+void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st)
+{
+    if (n <= 0) return;
+    k_split3_flights<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, fl, n);
 }
 #endif  // C2D_EMU
 

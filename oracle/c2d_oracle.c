@@ -198,6 +198,24 @@ double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d)
     return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
 }
 
+/* Philox replay mode: the xi of trial flight t (0-based) of a history with trial stream S.  The 52-bit
+ * integer K of u = (K + 0.5) 2^-52 is composed of two independent Philox outputs:
+ *   coarse 16 bits = halfword (t & 7) of philox(ctr = (S_lo, S_hi, t >> 3, 0))   (8 trials per call)
+ *   fine   36 bits = low 36 bits of words 0,1 of philox(ctr = (S_lo, S_hi, t, 1))
+ * so a consumer that only needs to know whether u exceeds a threshold close to 1 (the CUDA trial
+ * filter) can decide almost every trial from the coarse halfword alone. */
+double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t)
+{
+    uint32_t c0[4] = {(uint32_t)S, (uint32_t)(S >> 32), t >> 3, 0u}, c1[4] = {(uint32_t)S, (uint32_t)(S >> 32), t, 1u}, o[4], f[4];
+    orc_philox4x32(c0, key, o);
+    orc_philox4x32(c1, key, f);
+    const uint32_t w = o[(t & 7u) >> 1];
+    const uint64_t coarse = (t & 1u) ? (w >> 16) : (w & 0xFFFFu);
+    const uint64_t fine = (((uint64_t)(f[1] & 0xFu)) << 32) | f[0];
+    const uint64_t K = (coarse << 36) | fine;
+    return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+}
+
 /* rand.f:195-223 fibran (rand_switch=2 branch) / Philox extension */
 double orc_fibran(orc_state *s)
 {
@@ -532,7 +550,7 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
             if (philox) {          /* trial stream: first draw comes from the history's trial-xi stream */
                 rng_stream(s, orc_mix64(S_trials, (uint64_t)iitrk));
                 s->rng.has_pending = 1;
-                s->rng.pending = orc_philox_uniform(s->rng.key, S_trials, (uint32_t)(iitrk - 1));
+                s->rng.pending = orc_trial_uniform(s->rng.key, S_trials, (uint32_t)(iitrk - 1));
             }
         }
     L100:
@@ -726,8 +744,12 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
                 if (s->ew > ewold * s->split2 * s->split1 * s->spl3_trg) {        /* 3rd split, l.639-669 */
                     ewold = csv.ew / s->split3;
                     for (ii2 = 1; ii2 <= s->split3; ii2++) {
-                        if (philox) rng_stream(s, orc_mix64(S_child, (uint64_t)ii2));
+                        /* Philox mode: every pass of the rejection loop owns the stream
+                         * mix64(mix64(S_child, ii2), attempt), so attempts can be evaluated in any order */
+                        const uint64_t S_sub = orc_mix64(S_child, (uint64_t)ii2);
+                        uint64_t attempt = 0;
                         do {
+                            if (philox) rng_stream(s, orc_mix64(S_sub, ++attempt));
                             ph_restore(s, &csv);
                             s->ew = csv.ew / s->split3;
                             orc_compb2d(s, &i_gam);

@@ -16,16 +16,26 @@ template <int SRC> static void run_hist(const Params &p, long long first, long l
 }
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<0>(p, first, n, stride); }
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<1>(p, first, n, stride); }
-template <class K> static void run_flat(K kern, const Params &p, const CollTask *q, long long n_in, long long per)
+template <class F> static void run_grid(long long n, F body)
 {
     blockDim.x = 128;
-    const long long n = n_in * per, blocks = (n + 127) / 128;
+    const long long blocks = (n + 127) / 128;
     for (long long b = 0; b < blocks; b++)
         for (unsigned t = 0; t < 128; t++) {
             blockIdx.x = (unsigned)b; threadIdx.x = t;
-            kern(p, q, n_in);
+            body();
         }
 }
-void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t) { if (n_in > 0) run_flat(k_children, p, q_in, n_in, p.split2); }
-void launch_split3(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t) { if (n_in > 0) run_flat(k_split3, p, q_in, n_in, p.split3); }
+void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t)
+{
+    if (n_in > 0) run_grid(n_in * p.split2, [&] { k_children(p, q_in, n_in); });
+}
+void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t)
+{   // kWarp == 1 in this build: one serial "warp" per sub-child
+    if (n_tasks > 0) run_grid(n_tasks * p.split3, [&] { k_split3_attempts(p, q3_in, n_tasks * p.split3, out); });
+}
+void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t)
+{
+    if (n > 0) run_grid(n, [&] { k_split3_flights(p, fl, n); });
+}
 }  // namespace c2d

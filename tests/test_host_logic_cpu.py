@@ -1,0 +1,142 @@
+"""Host-logic tests on the GPU-less box.  The kernel sources of compton2d_b200/csrc are compiled with g++
+against tests/emu/fake/cuda_runtime.h (serial "launches", TEST INFRASTRUCTURE ONLY -- the product never
+loads this build) so that the C-ABI driver, the queue draining, the bank ping-pong, the sharding arithmetic
+and the Python host mirror can be exercised against the CPU oracle without a device.  The real parity gate
+is tests/test_gpu_parity.py on the B200."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests" / "emu"))
+
+
+@pytest.fixture()
+def emu(monkeypatch):
+    import build_emu
+    from compton2d_b200 import lib as L
+    so = build_emu.build()
+    monkeypatch.setattr(L, "LIBPATH", so)
+    monkeypatch.setattr(L, "_lib", None)
+    yield
+    monkeypatch.setattr(L, "_lib", None)
+
+
+def test_step_sequence_matches_oracle(emu):
+    from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step
+    from synth import make_problem
+    P = make_problem(nz=4, nr=3, nst=1500, ngroups=64, split=(40, 20, 6, 10), n_e=3.0e5)
+    o, g = make_oracle(P), make_gpu(P)
+    for cyc in (1, 2, 3):
+        ro = oracle_step(o, P, cyc, field=cyc > 1)
+        rg = gpu_step(g, P, cyc, field=cyc > 1)
+        bad = compare(rg, ro, tol=1e-11, census_tol=1e-6)   # scattered photons: compb2d amplifies ulp-level differences
+        assert not bad, (cyc, bad)
+    assert rg["counters"]["cmcount2"] > 0
+    g.close()
+
+
+def test_census_export_import_roundtrip(emu):
+    """write_record / read_record contract (census2d.f): export -> import into a fresh context -> same step."""
+    from parity_util import gpu_step, make_gpu
+    from synth import make_problem
+    P = make_problem(nz=3, nr=3, nst=2000, ngroups=32, split=(10, 5, 2, 10))
+    a = make_gpu(P)
+    gpu_step(a, P, 1, field=False)
+    d, i, s = a.census()
+    ra = gpu_step(a, P, 2)
+    b = make_gpu(P)
+    b.census_import(d, i, s)
+    rb = gpu_step(b, P, 2)
+    assert np.array_equal(ra["npcen"], rb["npcen"]) and ra["counters"]["ndxout"] == rb["counters"]["ndxout"]
+    assert np.allclose(ra["edep"], rb["edep"], rtol=1e-13, atol=0)
+    a.close(); b.close()
+
+
+def test_error_paths(emu):
+    from compton2d_b200 import C2dError
+    from parity_util import gpu_step, make_gpu
+    from synth import make_problem
+    P = make_problem(nz=3, nr=3, nst=2000, ngroups=32, split=(10, 5, 2, 10))
+    g = make_gpu(P, census_capacity=50)                 # 'too many photons' (imctrk2d.f:581-585)
+    with pytest.raises(C2dError) as e:
+        gpu_step(g, P, 1, field=False)
+    assert e.value.code == 4
+    g.close()
+    g = make_gpu(P)
+    with pytest.raises(C2dError) as e:                  # step not begun
+        g.imcvol2d()
+    assert e.value.code == 6
+    g.close()
+    P2 = dict(P)
+    with pytest.raises(C2dError) as e:                  # Compton reflection is not built
+        from compton2d_b200.host import Compton2d
+        Compton2d(nz=P["nz"], nr=P["nr"], z=P["z"], r=P["r"], E_ph=P["E_ph"], E_field=P["E_field"], E_gg=P["E_gg"],
+                  gnt=P["gnt"], hu=P["hu"], cr_sent=1)
+    assert e.value.code == 2
+
+
+WORKER = r'''
+import os, sys
+sys.path[:0] = [r"{root}", r"{root}/tests", r"{root}/tests/emu", r"{root}/oracle"]
+import numpy as np, torch, torch.distributed as dist
+import build_emu
+from compton2d_b200 import lib as L
+L.LIBPATH = build_emu.build()
+from parity_util import make_gpu
+from synth import make_problem
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+P = make_problem(nz=4, nr=3, nst=3000, ngroups=32, split=(20, 10, 3, 10), n_e=3.0e5)
+g = make_gpu(P, rank=rank, world=world)
+tot = None
+for cyc in (1, 2):
+    g.imcgen2d(ncycle=cyc, time=0.0, dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"], eps_th=P["eps_th"],
+               f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"], f_pair=P["f_pair"], k_gg=P["k_gg"], nsv=P["nsv"],
+               ewsv=P["ewsv"], Eloss_th=P["Eloss_th"], Eloss_tot=P["Eloss_tot"], zsurf=P["zsurf"], tbbl=P["tbbl"])
+    if cyc > 1:
+        g.imcfield2d()
+    g.imcvol2d()
+    g.sync()
+    t = g.tallies()
+    # the reduction the CUDA path does in place on the device, here over gloo on the host copies
+    pack = np.concatenate([t["edep"], t["ecens"], t["n_field"].ravel(), t["fout"].ravel(), t["E_IC"]])
+    ints = np.concatenate([t["npcen"], t["nelectron"], [t["counters"][k] for k in ("ndxout", "cmcount1", "cmcount2", "nevents")]])
+    tp, ti = torch.from_numpy(pack), torch.from_numpy(ints)
+    dist.all_reduce(tp); dist.all_reduce(ti)
+    sid = g.census()[2]
+    gathered = [None] * world
+    dist.all_gather_object(gathered, sid)
+if rank == 0:
+    np.savez(r"{out}", pack=tp.numpy(), ints=ti.numpy(), sid=np.sort(np.concatenate(gathered)))
+dist.destroy_process_group()
+'''
+
+
+def test_two_ranks_equal_one(emu, tmp_path):
+    """world_size 2 over gloo: histories sharded h mod 2, census kept per rank, tallies all-reduced ==
+    the single-rank run (integers exact, FP64 to 1e-12) after two steps."""
+    from parity_util import gpu_step, make_gpu
+    from synth import make_problem
+    P = make_problem(nz=4, nr=3, nst=3000, ngroups=32, split=(20, 10, 3, 10), n_e=3.0e5)
+    g = make_gpu(P)
+    gpu_step(g, P, 1, field=False)
+    one = gpu_step(g, P, 2)
+    g.close()
+    out = tmp_path / "two.npz"
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=str(ROOT), out=str(out)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29541")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29541", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    two = np.load(out)
+    ints1 = np.concatenate([one["npcen"], one["nelectron"], [one["counters"][k] for k in ("ndxout", "cmcount1", "cmcount2", "nevents")]])
+    assert np.array_equal(two["ints"], ints1)
+    pack1 = np.concatenate([one["edep"], one["ecens"], one["n_field"].ravel(), one["fout"].ravel(), one["E_IC"]])
+    assert np.abs(two["pack"] - pack1).max() <= 1e-12 * np.abs(pack1).max()
+    assert np.array_equal(two["sid"], np.sort(one["census"][2]))
