@@ -218,8 +218,8 @@ def our_arm(args):
         g.imcfield2d()
         g.imcvol2d()
         g.graphics_collect()
-        ms = sum(g.kernel_time(w)[0] for w in (0, 1, 2))
-        nl = sum(g.kernel_time(w)[1] for w in (0, 1, 2))
+        ms = sum(g.kernel_time(w)[0] for w in (0, 1, 2, 4, 6))
+        nl = sum(g.kernel_time(w)[1] for w in (0, 1, 2, 4, 6))
         t = g.tallies() if e2e else None
         return ms, nl, time.perf_counter() - t0, t
 
@@ -233,11 +233,12 @@ def our_arm(args):
     barrier()
     dev_ms, launches, hist = 0.0, 0, 0
     wall0 = time.perf_counter()
-    hist_ms = coll_ms = s3_ms = 0.0
+    hist_ms = coll_ms = s3_ms = s3f_ms = sig_ms = 0.0
     for _ in range(args.steps):
         h0 = g.census_count()
         ms, nl, _, _ = step(cyc, False); cyc += 1
         hist_ms += g.kernel_time(0)[0]; coll_ms += g.kernel_time(1)[0]; s3_ms += g.kernel_time(2)[0]
+        s3f_ms += g.kernel_time(6)[0]; sig_ms += g.kernel_time(4)[0]
         dev_ms += ms; launches += nl
         hist += h0 + (int(P["nsv"].sum()) - rank + world - 1) // world
     barrier()
@@ -296,7 +297,8 @@ def our_arm(args):
            "e2e": {"value": e_hist_all / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches_all),
            "kernel_ms_per_step": {"k_history": hist_ms / args.steps, "k_children": coll_ms / args.steps,
-                                  "k_split3": s3_ms / args.steps},
+                                  "k_split3_attempts": s3_ms / args.steps, "k_split3_flights": s3f_ms / args.steps,
+                                  "k_sigma_table": sig_ms / args.steps},
            "roofline": {"bound": "hbm", "kernel": "k_history", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                         "frac": achieved / hbm, "traffic": None,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",

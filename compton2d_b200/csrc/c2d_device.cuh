@@ -738,7 +738,7 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
     return END_COLLISION;                                       // ikind == 3
 }
 
-// a whole flight by one thread (MODE_CHILD flights use child_flight_warp instead)
+// a whole flight by one thread
 template <int MODE>
 __device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtmin, double colmfp, Seg *segs, int &nseg)
 {
@@ -751,7 +751,7 @@ __device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtm
         if (P.wmu < -1.0) P.wmu = -1.0;
         double sigsc = 0.0;
         if (MODE == MODE_TRIAL) sigsc = segs[s].sigsc;
-        else if (MODE == MODE_TRIAL_SLOW) {
+        else if (MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) {
             const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
             const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
             sigsc = 1.0 * comtot_one(p, zi, P.xnu) * pair_enhance;

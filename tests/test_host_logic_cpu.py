@@ -40,6 +40,22 @@ def test_step_sequence_matches_oracle(emu):
     g.close()
 
 
+def test_multiple_scattering_and_third_split(emu):
+    """Dense plasma, small splits: scattered photons collide again ('multiple scattering', imctrk2d.f:614) and most
+    children trigger the 3rd split (l.639-669)."""
+    from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step
+    from synth import make_problem
+    P = make_problem(nz=3, nr=3, nst=600, ngroups=64, split=(20, 10, 4, 10), n_e=4.0e7)
+    o, g = make_oracle(P), make_gpu(P)
+    for cyc in (1, 2):
+        ro = oracle_step(o, P, cyc, field=cyc > 1)
+        rg = gpu_step(g, P, cyc, field=cyc > 1)
+        bad = compare(rg, ro, tol=1e-10, census_tol=1e-4)
+        assert not bad, (cyc, bad)
+    assert rg["counters"]["multiple"] > 0
+    g.close()
+
+
 def test_census_export_import_roundtrip(emu):
     """write_record / read_record contract (census2d.f): export -> import into a fresh context -> same step."""
     from parity_util import gpu_step, make_gpu
