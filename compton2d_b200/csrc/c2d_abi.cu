@@ -146,6 +146,64 @@ static int check_fatal(Ctx *c)
     return 0;
 }
 
+// ---- sigma_mode 1: see c2d_sigma.cu
+int Ctx::sigma_setup()
+{
+    const int N = dims.num_nt, nb = N - 1, D = 8;
+    std::vector<double> th(nb);
+    for (int i = 0; i < nb; i++) th[i] = std::log(1.e-2 / (h_gam0[i] * h_opb[i]));
+    for (int i = 1; i < nb; i++)
+        if (!(th[i] < th[i - 1])) return fail(C2D_EINVAL, "sigma table: the electron grid gnt must increase strictly (bin %d)", i);
+    const double t0 = th[0], h = 0.2, tmax = std::log(1.e14 / 5.11e2);
+    const int nsub = std::max(1, (int)std::ceil((tmax - t0) / h));
+    const int n_int = nb + nsub;
+    sig_nodes = n_int * D;
+    std::vector<double> lo(n_int, 0.0), iw(n_int, 0.0), xs(sig_nodes, 1.0), M(D * D);
+    std::vector<int> ms(sig_nodes, nb);
+    auto interval = [&](int j, double a, double b, int m) {
+        lo[j] = a; iw[j] = 2.0 / (b - a);
+        for (int n = 0; n < D; n++) {
+            const double sn = std::cos(kPi * (n + 0.5) / D);
+            xs[j * D + n] = std::exp(0.5 * (a + b) + 0.5 * (b - a) * sn);
+            ms[j * D + n] = m;
+        }
+    };
+    for (int m = 1; m < nb; m++) interval(m, th[m], th[m - 1], m);       // m(x) = m on [theta_m, theta_{m-1})
+    for (int q = 0; q < nsub; q++) interval(nb + q, t0 + q * h, t0 + (q + 1) * h, 0);
+    for (int k = 0; k < D; k++)
+        for (int n = 0; n < D; n++) M[k * D + n] = (k == 0 ? 1.0 : 2.0) / D * std::cos(kPi * k * (n + 0.5) / D);
+    const size_t n_static = (size_t)2 * n_int + sig_nodes + D * D + (size_t)nb * sig_nodes;
+    CU(cudaMalloc(&d_sig_static, n_static * 8));
+    double *S = d_sig_static;
+    double *d_lo = S, *d_iw = S + n_int, *d_xs = S + 2 * n_int;
+    d_sig_M = d_xs + sig_nodes; d_sig_Kn = d_sig_M + D * D;
+    CU(cudaMemcpy(d_lo, lo.data(), n_int * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_iw, iw.data(), n_int * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_xs, xs.data(), (size_t)sig_nodes * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(d_sig_M, M.data(), D * D * 8, cudaMemcpyHostToDevice));
+    CU(cudaMalloc(&d_sig_ms, (size_t)sig_nodes * 4));
+    CU(cudaMemcpy(d_sig_ms, ms.data(), (size_t)sig_nodes * 4, cudaMemcpyHostToDevice));
+    const size_t n_step = (size_t)nzone * N * 3 + (size_t)nzone * sig_nodes * 2;
+    CU(cudaMalloc(&d_sig_step, n_step * 8));
+    d_sig_W = d_sig_step; d_sig_AB = d_sig_W + (size_t)nzone * N; d_sig_T = d_sig_AB + (size_t)nzone * N * 2;
+    d_sig_coef = d_sig_T + (size_t)nzone * sig_nodes;
+    P.sig_coef = d_sig_coef; P.sig_AB = d_sig_AB; P.sig_W = d_sig_W; P.sig_lo = d_lo; P.sig_iw = d_iw;
+    P.sig_nint = n_int; P.sig_nsub = nsub; P.sig_t0 = t0; P.sig_inv_h = 1.0 / h;
+    launch_sigma_kn(P, d_xs, d_sig_ms, sig_nodes, d_sig_Kn, stream);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int Ctx::sigma_build()
+{
+    timer_begin(4);
+    launch_sigma_build(P, d_sig_W, d_sig_AB, d_sig_Kn, sig_nodes, d_sig_T, d_sig_M, d_sig_coef, stream);
+    timer_end();
+    CU(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace c2d
 
 using namespace c2d;
@@ -181,8 +239,8 @@ int c2d_destroy(c2d_ctx *h)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_f64); cudaFree(c->d_i64);
-    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_qcount); cudaFree(c->d_sig);
-    cudaFree(c->d_sigS);
+    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_qcount);
+    cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
     c->fp_free();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -244,6 +302,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     CU(cudaMalloc(&c->d_static, hs.size() * 8));
     CU(cudaMemcpy(c->d_static, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
     c->h_gnt.assign(d->gnt, d->gnt + d->num_nt);
+    c->h_gam0 = gam0; c->h_opb = opb;
     c->h_Efield.assign(d->E_field, d->E_field + d->nphfield);
     c->h_z.assign(d->z, d->z + d->nz); c->h_r.assign(d->r, d->r + d->nr);
 
@@ -553,6 +612,31 @@ int c2d_events_drain(c2d_ctx *h, c2d_event *buf, int64_t cap, int64_t *n_out)
     const int64_t n = std::min<int64_t>(stored, cap);
     if (n && buf) CU(cudaMemcpy(buf, c->d_events, (size_t)n * 7 * 8, cudaMemcpyDeviceToHost));
     if ((int64_t)v > c->event_cap) return fail(C2D_EEVENTS, "%llu escape records produced, event_capacity %lld", v, (long long)c->event_cap);
+    return 0;
+}
+
+int c2d_comtot(c2d_ctx *h, int64_t n, const int32_t *zone, const double *xnu, int mode, double *comac)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
+    if (n < 0 || (n && (!zone || !xnu || !comac))) return fail(C2D_EINVAL, "NULL argument");
+    if (mode != 0 && mode != 1) return fail(C2D_EINVAL, "mode %d", mode);
+    if (mode == 1 && c->dims.sigma_mode != 1) return fail(C2D_EINVAL, "the context was created with sigma_mode 0: no table");
+    for (int64_t i = 0; i < n; i++)
+        if (zone[i] < 0 || zone[i] >= c->nzone || !(xnu[i] > 0.0)) return fail(C2D_EINVAL, "query %lld: zone %d xnu %g", (long long)i, zone[i], xnu[i]);
+    if (n == 0) return 0;
+    CU(cudaSetDevice(c->device));
+    int *d_zone = nullptr; double *d_x = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_zone, n * 4)); CU(cudaMalloc(&d_x, n * 8)); CU(cudaMalloc(&d_out, n * 8));
+    CU(cudaMemcpyAsync(d_zone, zone, n * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_x, xnu, n * 8, cudaMemcpyHostToDevice, c->stream));
+    Params p = c->P;
+    p.sigma_mode = mode;
+    launch_comtot_query(p, n, d_zone, d_x, d_out, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(comac, d_out, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_zone); cudaFree(d_x); cudaFree(d_out);
     return 0;
 }
 

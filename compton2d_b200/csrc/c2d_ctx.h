@@ -21,7 +21,6 @@ struct Ctx {
     long long q_peak = 0;
     // device memory
     double *d_static = nullptr, *d_step = nullptr, *d_f64 = nullptr, *d_events = nullptr;
-    double *d_sig = nullptr, *d_sigS = nullptr;
     int64_t *d_prefix = nullptr;
     unsigned long long *d_i64 = nullptr, *d_qcount = nullptr;
     CollTask *d_q[2] = {nullptr, nullptr}, *d_q3 = nullptr;
@@ -39,8 +38,12 @@ struct Ctx {
     std::vector<int64_t> h_prefix;
     std::vector<double> h_f64, h_gnt, h_Efield, h_z, h_r;
     std::vector<unsigned long long> h_i64;
-    // sigma(zone, E) table (sigma_mode 1)
-    int n_sig = 0;
+    // sigma(zone, E) table (sigma_mode 1, c2d_sigma.cu)
+    int sig_nodes = 0;
+    double *d_sig_static = nullptr, *d_sig_step = nullptr;   // [lo | iw | xs | M | Kn] and [W | AB | T | coef]
+    int *d_sig_ms = nullptr;
+    double *d_sig_W = nullptr, *d_sig_AB = nullptr, *d_sig_T = nullptr, *d_sig_coef = nullptr, *d_sig_Kn = nullptr, *d_sig_M = nullptr;
+    std::vector<double> h_gam0, h_opb;
     int sigma_setup();
     int sigma_build();
     // Fokker-Planck state (c2d_fp.cu)

@@ -81,8 +81,12 @@ struct Params {
     const double *kappa_tot, *eps_tot, *eps_th, *f_nt, *Pnt, *n_e, *f_pair, *k_gg, *tbbl;
     const double *ewsv, *Eloss_th, *Eloss_tot, *zsurf;
     const int64_t *nsv_prefix;         // [nzone+1]
-    const double *sig_table;           // sigma_mode 1: [nzone][n_sig] ln(sigma) on the ln(E) grid
-    int n_sig; double sig_lnE0, sig_inv_dlnE;
+    // sigma_mode 1 (c2d_sigma.cu): per-step piecewise-Chebyshev representation of comtot(zone, E)
+    const double *sig_coef;            // [nzone][sig_nint][8] coefficients of the exact-branch sum on each interval
+    const double *sig_AB;              // [nzone][num_nt][2] prefix sums of the Thomson-branch bins
+    const double *sig_W;               // [nzone][num_nt] f_nt * dgamma
+    const double *sig_lo, *sig_iw;     // [sig_nint] interval lower bound in ln(x) and 2 / width
+    int sig_nint, sig_nsub; double sig_t0, sig_inv_h;
     // tallies
     double *edep, *prdep, *ecens, *n_field, *n_ph, *E_IC, *fout, *edout, *erlki, *erlko, *erlku, *erlkl,
         *Ed_in, *Ed_ref;
@@ -270,7 +274,8 @@ static __device__ __constant__ double kDilogC[20] = {0.42996693560813697e0, 0.40
 // only the branches T <= 1 and T > 1 are reachable) evaluated side by side: two independent Clenshaw
 // recurrences keep the FP64 pipe busy.  The recurrence uses explicit FMAs (the only place the tracker departs
 // from the reference's operation-by-operation arithmetic; it moves sigma by <= 1 ulp).
-__device__ __forceinline__ double intg_v_diff(double xa, double xb)
+template <bool SMOOTH>
+__device__ __forceinline__ double intg_v_diff_t(double xa, double xb)
 {
     const double PI2 = kPi * kPi, PI6 = PI2 / 6, PI12 = PI2 / 12;
     double Ya, Sa, Aa, Yb, Sb, Ab;
@@ -287,20 +292,50 @@ __device__ __forceinline__ double intg_v_diff(double xa, double xb)
     double da = -(Sa * (B0a - Ha * B2a) + Aa), db = -(Sb * (B0b - Hb * B2b) + Ab);
     if (xa == 1.0) da = -PI12;                  // dilog(-1), comtot2d.f:385-386
     if (xb == 1.0) db = -PI12;
-    const double va = (-xa / 2.0 + 0.5 / (1.0 + xa)) + 4.0 * da + (9.0 + xa + 8.0 / xa) * log(1.0 + xa);
-    const double vb = (-xb / 2.0 + 0.5 / (1.0 + xb)) + 4.0 * db + (9.0 + xb + 8.0 / xb) * log(1.0 + xb);
+    const double la = SMOOTH ? log1p(xa) : log(1.0 + xa), lb = SMOOTH ? log1p(xb) : log(1.0 + xb);
+    const double va = (-xa / 2.0 + 0.5 / (1.0 + xa)) + 4.0 * da + (9.0 + xa + 8.0 / xa) * la;
+    const double vb = (-xb / 2.0 + 0.5 / (1.0 + xb)) + 4.0 * db + (9.0 + xb + 8.0 / xb) * lb;
     return va - vb;
+}
+__device__ __forceinline__ double intg_v_diff(double xa, double xb) { return intg_v_diff_t<false>(xa, xb); }
+
+// The reference forms log(1.0 + y) (comtot2d.f:352-353 intg_v): the rounding of 1 + y costs a relative error of up to
+// 1.1e-16 / y in the logarithm, which the factor 8 / y turns into noise that exceeds the signal of the high-gamma
+// bins near the Thomson switch (y_b = 2 gamma (1 - beta) x ~ 1e-13) and reaches ~2e-4 of comtot for 1e-7 < x < 1e-3.
+// That noise is part of the reference's answer.  It is reproduced exactly and cheaply: with s = fl(1 + y) and
+// e = (s - 1) - y (exact), log(s) = log1p(y) + e / (1 + y) to first order, so
+//   intg_v(y) = intg_v_smooth(y) + kn_eta(y),  kn_eta(y) = (9 + y + 8 / y) e / s.
+// intg_v_smooth (log1p instead of log(1 + y)) is what the sigma_mode-1 table interpolates.
+__device__ __forceinline__ double kn_eta(double y)
+{
+    if (!(y < 1.0)) return 0.0;                  // |eta| < 2e-15 there
+    const double s = 1.0 + y, e = (s - 1.0) - y, d = y * s;
+#ifdef C2D_EMU
+    double r = (double)(1.0f / (float)d);
+#else
+    double r = (double)__frcp_rn((float)d);
+#endif
+    r = r * (2.0 - d * r);                        // one Newton step: ~1e-14 relative
+    return fma(y, 9.0 + y, 8.0) * e * r;
 }
 
 // sigma_E of comtot2d.f:234-239 for electron bin i (0-based) and x = xnu/511.  kn_pref = 9.375e-2 sigma_T /
 // gamma^2 / beta, kn_a1 = 2 gamma (1 + beta), kn_a2 = 2 gamma (1 - beta) are the reference's own
 // left-to-right products, formed once on the host.
+__device__ __forceinline__ double sigma_kn_exact(const Params &p, int i, double x)
+{
+    return p.kn_pref[i] / (x * x) * intg_v_diff(p.kn_a1[i] * x, p.kn_a2[i] * x);
+}
+__device__ __forceinline__ double sigma_kn_smooth(const Params &p, int i, double x)
+{
+    return p.kn_pref[i] / (x * x) * intg_v_diff_t<true>(p.kn_a1[i] * x, p.kn_a2[i] * x);
+}
+__device__ __forceinline__ bool kn_thomson(const Params &p, int i, double x) { return x * p.gam0[i] * p.opb[i] < 1.e-2; }
 __device__ __forceinline__ double sigma_kn_bin(const Params &p, int i, double x)
 {
     const double sigthom = 6.6516e-25;
-    const double gamma0 = p.gam0[i];
-    if (x * gamma0 * p.opb[i] < 1.e-2) return sigthom * (1.0 - 2.0 * x * gamma0);
-    return p.kn_pref[i] / (x * x) * intg_v_diff(p.kn_a1[i] * x, p.kn_a2[i] * x);
+    if (kn_thomson(p, i, x)) return sigthom * (1.0 - 2.0 * x * p.gam0[i]);
+    return sigma_kn_exact(p, i, x);
 }
 
 // comac for up to four zones, one thread walking all electron bins: comtot2d.f:219-247
@@ -363,28 +398,75 @@ __device__ __forceinline__ double comtot_zone_warp(const Params &p, double xnu, 
     return (c0 < 1.e-40) ? 1.e-40 : p.n_e[zi] * c0;
 }
 
-// sigma_mode 1: per-step table ln sigma(zone, ln E), Catmull-Rom cubic in ln E
-__device__ __forceinline__ double comtot_table(const Params &p, int zi, double xnu)
+// sigma_mode 1: comtot(zone, E) from the per-step table of c2d_sigma.cu.  The bins split at m(x) = number of
+// bins on the Thomson branch of comtot2d.f:228 (the same floating-point predicate, found by bisection -- it is
+// monotone in the bin index):  c = sigma_T (A_z[m] - 2 x B_z[m]) + S_z(m, x),  where A, B are prefix sums over the
+// Thomson bins and S_z(m, .) -- the sum of the exact branch over bins >= m, a smooth function of x on the interval
+// where m(x) = m -- is a degree-7 Chebyshev series in ln x on that interval (m = 0: sub-intervals of width 1/sig_inv_h).
+// The table reproduces the per-history evaluation to ~1e-11 (the cancellation noise of the exact branch itself).
+struct SigCtx { int m, j; double x, s; };      // j = -1: all bins on the Thomson branch; j = -2: outside the table
+
+__device__ __forceinline__ void sig_begin(const Params &p, double xnu, SigCtx &c)
 {
-    const double t = (log(xnu) - p.sig_lnE0) * p.sig_inv_dlnE;
-    int i = (int)floor(t);
-    if (i < 1) i = 1;
-    if (i > p.n_sig - 3) i = p.n_sig - 3;
-    const double u = t - i;
-    const double *y = p.sig_table + (size_t)zi * p.n_sig + i;
-    const double ym = y[-1], y0 = y[0], y1 = y[1], y2 = y[2];
-    const double a = -0.5 * ym + 1.5 * y0 - 1.5 * y1 + 0.5 * y2;
-    const double b = ym - 2.5 * y0 + 2.0 * y1 - 0.5 * y2;
-    const double c = -0.5 * ym + 0.5 * y1;
-    return exp(((a * u + b) * u + c) * u + y0);
+    c.x = xnu / 5.11e2;
+    int lo = 0, hi = p.num_nt - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (kn_thomson(p, mid, c.x)) lo = mid + 1; else hi = mid;
+    }
+    c.m = lo; c.s = 0.0;
+    if (c.m == p.num_nt - 1) { c.j = -1; return; }
+    const double t = log(c.x);
+    if (c.m > 0) c.j = c.m;
+    else {
+        const double u = (t - p.sig_t0) * p.sig_inv_h;
+        const int sub = (u > 0.0) ? (int)u : 0;
+        if (!(u < (double)p.sig_nsub)) { c.j = -2; return; }
+        c.j = p.num_nt - 1 + sub;
+    }
+    c.s = (t - p.sig_lo[c.j]) * p.sig_iw[c.j] - 1.0;
 }
 
-__device__ __forceinline__ double comtot_one(const Params &p, int zi, double xnu)
+// Table value for up to four zones of one photon energy: the bins of the exact branch are walked once for the
+// rounding-noise term (two kn_eta per bin instead of two dilogarithms and three logarithms).
+__device__ __forceinline__ void comtot_table_zones(const Params &p, const SigCtx &c, const int *zi, int nzn, double *comac)
 {
-    if (p.sigma_mode == 1) return comtot_table(p, zi, xnu);
-    double c;
-    comtot_zones(p, xnu, &zi, 1, &c);
-    return c;
+    const double sigthom = 6.6516e-25;
+    const int N = p.num_nt;
+    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    if (c.j >= 0) {
+        const double *w0 = p.sig_W + (size_t)zi[0] * N, *w1 = p.sig_W + (size_t)zi[nzn > 1 ? 1 : 0] * N;
+        const double *w2 = p.sig_W + (size_t)zi[nzn > 2 ? 2 : 0] * N, *w3 = p.sig_W + (size_t)zi[nzn > 3 ? 3 : 0] * N;
+        for (int i = c.m; i < N - 1; i++) {
+            const double q = p.kn_pref[i] * (kn_eta(p.kn_a1[i] * c.x) - kn_eta(p.kn_a2[i] * c.x));
+            e0 = fma(q, w0[i], e0); e1 = fma(q, w1[i], e1); e2 = fma(q, w2[i], e2); e3 = fma(q, w3[i], e3);
+        }
+    }
+    const double ee[4] = {e0, e1, e2, e3};
+    const double inv_x2 = 1.0 / (c.x * c.x);
+    for (int k = 0; k < nzn; k++) {
+        const int z = zi[k];
+        const double *ab = p.sig_AB + ((size_t)z * N + c.m) * 2;
+        double v = sigthom * (ab[0] - 2.0 * c.x * ab[1]);
+        if (c.j >= 0) {
+            const double *kk = p.sig_coef + ((size_t)z * p.sig_nint + c.j) * 8;
+            const double s2 = c.s + c.s;
+            double b1 = kk[7], b2 = 0.0, b0;
+#pragma unroll
+            for (int q = 6; q >= 1; q--) { b0 = fma(s2, b1, kk[q]) - b2; b2 = b1; b1 = b0; }
+            v = v + (fma(c.s, b1, kk[0]) - b2) + ee[k] * inv_x2;
+        }
+        comac[k] = (v < 1.e-40) ? 1.e-40 : p.n_e[z] * v;
+    }
+}
+
+// comtot for one zone by one thread (scat_flag = 1 flights; `c` was set up by flight_begin when sigma_mode = 1)
+__device__ __forceinline__ double comtot_one(const Params &p, int zi, double xnu, const SigCtx &c)
+{
+    double r;
+    if (p.sigma_mode == 1 && c.j != -2) comtot_table_zones(p, c, &zi, 1, &r);
+    else comtot_zones(p, xnu, &zi, 1, &r);
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------ scattering
@@ -590,6 +672,7 @@ constexpr int STEP_CONT = -1;
 struct FlightCtx {           // energy bins are constant along a flight (xnu only changes in compb2d)
     int i_e, i_gg;
     double dcol_f0;
+    SigCtx sig;
 };
 __device__ __forceinline__ void flight_begin(const Params &p, double xnu, FlightCtx &c)
 {
@@ -599,6 +682,7 @@ __device__ __forceinline__ void flight_begin(const Params &p, double xnu, Flight
         for (c.i_gg = 1; c.i_gg <= p.n_gg; c.i_gg++)
             if (xnu < p.E_gg[c.i_gg - 1]) break;
     c.dcol_f0 = 100 * fmax(p.r[p.nr - 1], p.z[p.nz - 1]);
+    c.sig.j = -2;
 }
 
 // One segment (imctrk2d.f:207-586) of a photon with ew >= 1e-40 and |wmu| <= 1 in zone zi; sigsc is the
@@ -744,6 +828,7 @@ __device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtm
 {
     FlightCtx c;
     flight_begin(p, P.xnu, c);
+    if ((MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) && p.sigma_mode == 1) sig_begin(p, P.xnu, c.sig);
     int s = 0;
     for (;;) {                                                    // label 110
         if (P.ew < 1.e-40) return END_LOWEW;
@@ -754,7 +839,7 @@ __device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtm
         else if (MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) {
             const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
             const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
-            sigsc = 1.0 * comtot_one(p, zi, P.xnu) * pair_enhance;
+            sigsc = 1.0 * comtot_one(p, zi, P.xnu, c.sig) * pair_enhance;
         }
         const int r = fly_step<MODE>(p, P, rng, wtmin, colmfp, sigsc, c, segs, s, nseg);
         if (r != STEP_CONT) return r;

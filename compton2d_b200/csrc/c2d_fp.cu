@@ -721,7 +721,3 @@ int c2d_tally_bench(c2d_ctx *, int64_t, int, float *, int64_t *) { return c2d::f
 
 }  // extern "C"
 
-namespace c2d {
-int Ctx::sigma_setup() { return fail(C2D_EINVAL, "sigma_mode 1 not built yet"); }
-int Ctx::sigma_build() { return fail(C2D_EINVAL, "sigma_mode 1 not built yet"); }
-}  // namespace c2d

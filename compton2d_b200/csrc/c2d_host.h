@@ -9,7 +9,10 @@ void launch_history_census(const Params &p, long long first, long long n, long l
 void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st);
 void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t st);
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st);
-void launch_sigma_table(const Params &p, double *table, int n_sig, double lnE0, double dlnE, cudaStream_t st);
+void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t st);
+void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
+                        double *coef, cudaStream_t st);
+void launch_comtot_query(const Params &p, long long n, const int *zone, const double *xnu, double *out, cudaStream_t st);
 
 // Fokker-Planck (c2d_fp.cu)
 struct FpParams;

@@ -75,7 +75,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     Photon T0 = P0;
     T0.ew = P0.ew / p.split1;                                     // l.110
     const uint64_t S_trials = mix64(S_entry, kTagTrials);
-    if (active) count(p, CNT_HISTORIES);
+    const bool hist_active = active;
 
     // A: the collision-free ray
     Seg segs[kMaxSeg];
@@ -91,12 +91,34 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
         count(p, CNT_SEGOVF);
         for (int t = 0; t < p.split1; t++)
             nscat += literal_trial_slow(p, T0, S_trials, t, trial_uniform(p, S_trials, (uint32_t)t), wtmin);
-        count(p, CNT_TRIALS, (unsigned long long)p.split1);
     }
+    const bool overflow_counted = active && overflow;
     const bool fast = active && !overflow;
     // B: sigma_sc per crossing (comac_ar cache of l.175-183: one comtot per zone and history)
     if (p.sigma_mode == 1) {
-        if (fast) for (int s = 0; s < nseg; s++) segs[s].sigsc = 1.0 * comtot_table(p, segs[s].zi, T0.xnu) * segs[s].sigsc;
+        if (fast) {
+            SigCtx sc;
+            sig_begin(p, T0.xnu, sc);
+            unsigned have = 0u;
+            for (;;) {
+                int zl[4] = {0, 0, 0, 0}, nzn = 0;
+                for (int s = 0; s < nseg && nzn < 4; s++) {
+                    if (have & (1u << s)) continue;
+                    bool seen = false;
+                    for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
+                    if (!seen) zl[nzn++] = segs[s].zi;
+                }
+                if (nzn == 0) break;
+                double cm[4];
+                if (sc.j != -2) comtot_table_zones(p, sc, zl, nzn, cm);
+                else comtot_zones(p, T0.xnu, zl, nzn, cm);
+                for (int s = 0; s < nseg; s++) {
+                    if (have & (1u << s)) continue;
+                    for (int m = 0; m < nzn; m++)
+                        if (zl[m] == segs[s].zi) { segs[s].sigsc = 1.0 * cm[m] * segs[s].sigsc; have |= (1u << s); break; }
+                }
+            }
+        }
     } else {
         unsigned have = fast ? 0u : 0xffffffffu;
         for (;;) {
@@ -134,46 +156,57 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             }
         }
     }
-    if (fast) {
     // C: the split1 trial draws (l.126-156).  A trial collides only if -ln(u) is within the ray's
     // scattering depth, i.e. u >= thr; everything below thr provably does not (margins >> rounding).
-    double tau = 0.0; bool has_rand = false;
-    for (int s = 0; s < nseg; s++) { tau += segs[s].sigsc * segs[s].L; has_rand |= !(segs[s].sigabs * segs[s].L <= .00001); }
-    const double thr = exp(-tau * (1.0 + 1.e-12)) * (1.0 - 1.e-12);
-    // u = (K + 0.5) 2^-52 >= thr  <=>  K >= ceil(thr 2^52 - 0.5): the filter runs on integers
-    const double tk = thr * 4503599627370496.0 - 0.5;
-    const uint64_t Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
-    double pr_acc[kMaxSeg];
-    if (has_rand) for (int s = 0; s < nseg; s++) pr_acc[s] = 0.0;
+    bool has_rand = false;
+    uint64_t Kthr = 0;
+    int lit_t[4] = {-1, -1, -1, -1};
     double wmu_c = T0.wmu;
     if (wmu_c > 1.0) wmu_c = 1.0;
     if (wmu_c < -1.0) wmu_c = -1.0;
-    // K = coarse16 << 36 | fine36 (trial_uniform): a trial whose coarse halfword is below the threshold's
-    // cannot collide, and eight trials share one Philox call for their coarse halfwords
-    const uint32_t Cthr = (uint32_t)(Kthr >> 36);
-    const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
-    for (int t8 = 0; 8 * t8 < p.split1; t8++) {
-        uint32_t o[4];
-        philox4x32_10(s_lo, s_hi, (uint32_t)t8, 0u, p.key0, p.key1, o);
-        if (!has_rand && !(half_ge(o[0], Cthr) | half_ge(o[1], Cthr) | half_ge(o[2], Cthr) | half_ge(o[3], Cthr))) continue;
+    if (fast) {
+        double tau = 0.0;
+        for (int s = 0; s < nseg; s++) { tau += segs[s].sigsc * segs[s].L; has_rand |= !(segs[s].sigabs * segs[s].L <= .00001); }
+        const double thr = exp(-tau * (1.0 + 1.e-12)) * (1.0 - 1.e-12);
+        // u = (K + 0.5) 2^-52 >= thr  <=>  K >= ceil(thr 2^52 - 0.5): the filter runs on integers
+        const double tk = thr * 4503599627370496.0 - 0.5;
+        Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
+        // K = coarse16 << 36 | fine36 (trial_uniform): a trial whose coarse halfword is below the threshold's
+        // cannot collide, and eight trials share one Philox call for their coarse halfwords
+        const uint32_t Cthr = (uint32_t)(Kthr >> 36);
+        const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
+        for (int t8 = 0; 8 * t8 < p.split1; t8++) {
+            uint32_t o[4];
+            philox4x32_10(s_lo, s_hi, (uint32_t)t8, 0u, p.key0, p.key1, o);
+            if (!(half_ge(o[0], Cthr) | half_ge(o[1], Cthr) | half_ge(o[2], Cthr) | half_ge(o[3], Cthr))) continue;
 #pragma unroll
-        for (int h = 0; h < 8; h++) {
-            const int t = 8 * t8 + h;
-            if (t >= p.split1) break;
-            const uint32_t w = o[h >> 1];
-            const uint32_t coarse = (h & 1) ? (w >> 16) : (w & 0xFFFFu);
-            if (coarse >= Cthr) {
+            for (int h = 0; h < 8; h++) {
+                const int t = 8 * t8 + h;
+                if (t >= p.split1) break;
+                const uint32_t w = o[h >> 1];
+                const uint32_t coarse = (h & 1) ? (w >> 16) : (w & 0xFFFFu);
+                if (coarse < Cthr) continue;
                 const uint64_t K = ((uint64_t)coarse << 36) | trial_fine36(p, S_trials, (uint32_t)t);
-                if (K >= Kthr) {
-                    const double u = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
-                    if (trial_collides(segs, nseg, -log(u))) {
-                        nlit++;
-                        nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
-                        continue;
-                    }
-                }
+                if (K < Kthr) continue;
+                const double u = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+                if (!trial_collides(segs, nseg, -log(u))) continue;
+                if (nlit < 4) lit_t[nlit] = t;
+                nlit++;
+                nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
             }
-            if (has_rand) {       // absorption-point draws of l.451-459 (they only move prdep)
+        }
+    }
+    // C': absorption-point draws of l.451-459 for the non-colliding trials of a ray with sigabs L > 1e-5 in some
+    // crossing (they only move prdep): one uniform per (trial, absorbing crossing) from the trial's stream.  The
+    // warp serves one such lane at a time with its split1 trials spread over the lanes.
+    double pr_acc[kMaxSeg];
+    {
+        const bool coop = fast && has_rand && nlit <= 4;
+        if (fast && has_rand && !coop) {                          // many collisions: the owner lane walks its trials
+            for (int s = 0; s < nseg; s++) pr_acc[s] = 0.0;
+            for (int t = 0; t < p.split1; t++) {
+                const double u = trial_uniform(p, S_trials, (uint32_t)t);
+                if (trial_collides(segs, nseg, -log(u))) continue;
                 const uint64_t S_t = mix64(S_trials, (uint64_t)(t + 1));
                 uint32_t k = 0;
                 for (int s = 0; s < nseg; s++) {
@@ -186,11 +219,37 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                 }
             }
         }
+        unsigned todo = warp_ballot(coop);
+        const int lane = lane_id();
+        while (todo) {
+            const int src = first_lane(todo);
+            todo &= todo - 1;
+            const uint64_t S_src = warp_shfl(S_trials, src);
+            const int n_s = warp_shfl(nseg, src);
+            const double wm = warp_shfl(wmu_c, src);
+            const int l0 = warp_shfl(lit_t[0], src), l1 = warp_shfl(lit_t[1], src), l2 = warp_shfl(lit_t[2], src), l3 = warp_shfl(lit_t[3], src);
+            uint32_t k = 0;
+            for (int s = 0; s < n_s; s++) {
+                const int sc = (s < kMaxSeg) ? s : 0;
+                const double sa = warp_shfl(segs[sc].sigabs, src), L = warp_shfl(segs[sc].L, src);
+                if (sa * L <= .00001) continue;
+                const double dele = warp_shfl(segs[sc].dele, src), ew = warp_shfl(segs[sc].ew, src), rp = warp_shfl(segs[sc].rpre, src);
+                double acc = 0.0;
+                for (int t = lane; t < p.split1; t += kWarp) {
+                    if (t == l0 || t == l1 || t == l2 || t == l3) continue;
+                    const double mb_ran = rng_uniform(p, mix64(S_src, (uint64_t)(t + 1)), k);
+                    const double sstar = -log(1. - mb_ran * dele / ew) / sa;
+                    const double denom = sqrt(rp * rp + 2. * wm * rp * sstar + sstar * sstar);
+                    acc += dele * ((wm * rp + sstar) / denom) * kCLight;
+                }
+                acc = warp_sum(acc);
+                if (lane == src) pr_acc[sc] = acc;
+                k++;
+            }
+        }
     }
-    count(p, CNT_TRIALS, (unsigned long long)p.split1);
-    count(p, CNT_SEGMENTS, (unsigned long long)nseg);
     // D: absorption deposition of the non-colliding trials (l.465-466), identical per trial
-    {
+    if (fast) {
         const double n_nc = (double)(p.split1 - nlit);
         if (n_nc > 0)
             for (int s = 0; s < nseg; s++) {
@@ -200,7 +259,16 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                 else atomic_add_f64(p.prdep + g.zi, pr_acc[s]);
             }
     }
-    }   // fast
+    {   // counters, aggregated over the warp
+        const unsigned long long nh = warp_sum((unsigned long long)(hist_active ? 1 : 0));
+        const unsigned long long nt = warp_sum((unsigned long long)((fast || overflow_counted) ? p.split1 : 0));
+        const unsigned long long ns = warp_sum((unsigned long long)(fast ? nseg : 0));
+        if (lane_id() == 0) {
+            if (nh) count(p, CNT_HISTORIES, nh);
+            if (nt) count(p, CNT_TRIALS, nt);
+            if (ns) count(p, CNT_SEGMENTS, ns);
+        }
+    }
     // E: recombined flight of the unscattered weight (l.698-712)
     if (active && p.split1 - nscat > 0) {
         Photon F = P0;

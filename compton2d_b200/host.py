@@ -154,6 +154,15 @@ class Compton2d:
         _l.check(self.L.c2d_tally_device(self.h, C.byref(pf), C.byref(nf), C.byref(pi), C.byref(ni)))
         return _CudaView(pf.value, nf.value, "<f8"), _CudaView(pi.value, ni.value, "<i8")
 
+    def comtot(self, zone, xnu, mode=0):
+        """== comtot(j,k,xnuc,1,comac,enexc) (comtot2d.f:1-334) with the current step's tables: macroscopic Compton
+        opacity [1/cm] for arrays of 0-based zone ids and photon energies [keV]."""
+        z = np.ascontiguousarray(zone, dtype=np.int32).ravel()
+        x = np.ascontiguousarray(xnu, dtype=_F).ravel()
+        out = np.zeros(x.size)
+        _l.check(self.L.c2d_comtot(self.h, x.size, z.ctypes.data, x.ctypes.data, int(mode), out.ctypes.data))
+        return out
+
     # ------------------------------------------------------------------ Fokker-Planck
     def IC_loss(self):
         """== IC_loss (icloss2d.f:1-125): build F_IC[num_nt][nphfield] on the device and return it."""

@@ -64,7 +64,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
-           "c2d_kernel_time_ms", "c2d_tally_bench"]
+           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot"]
 
 _lib = None
 
@@ -101,6 +101,7 @@ def load():
     L.c2d_events_drain.argtypes = [vp, vp, C.c_int64, lp]
     L.c2d_ic_loss.argtypes = [vp, vp]
     L.c2d_update_fp.argtypes = [vp, C.POINTER(FpIn), C.POINTER(FpOut)]
+    L.c2d_comtot.argtypes = [vp, C.c_int64, vp, vp, C.c_int, vp]
     L.c2d_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), lp]
     L.c2d_tally_bench.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(C.c_float), lp]
     for fn in ("c2d_pack_bin_first", "c2d_unpack_bin_first"):

@@ -53,8 +53,10 @@ typedef struct {
     int64_t event_capacity;           /* escape records kept per step */
     int64_t collision_capacity;       /* pending Compton-collision tasks (scattering work queue) */
     uint32_t rseed;                   /* reader.f:466; Philox key word 0 (key word 1 = ncycle) */
-    int sigma_mode;                   /* 0: comtot evaluated exactly per history (comtot2d.f:219-247)
-                                         1: per-step sigma(zone,E) table, log-log cubic interpolation */
+    int sigma_mode;                   /* 0: comtot evaluated bin by bin for every history and zone (comtot2d.f:219-247)
+                                         1: per-step table of comtot(zone, E): Thomson-branch bins as prefix sums,
+                                            exact-branch bins as piecewise degree-7 Chebyshev series in ln E between
+                                            the branch switch points (same values to ~1e-11, see c2d_comtot) */
     double rmin, zmin;
     const double *z;                  /* [nz]  upper faces */
     const double *r;                  /* [nr]  outer faces */
@@ -139,6 +141,10 @@ int c2d_tally_read(c2d_ctx *ctx, c2d_tallies *out);        /* D2H copy of this c
 int c2d_tally_device(c2d_ctx *ctx, double **fp64_buf, int64_t *n_fp64, int64_t **i64_buf, int64_t *n_i64);
         /* device pointers of the packed tally buffers, for the per-step all-reduce
            (cens_add_up + E_add_up + xec_add + graphics_collect: update2d.f:1931-2083, xec2d.f:325-394) */
+
+int c2d_comtot(c2d_ctx *ctx, int64_t n, const int32_t *zone, const double *xnu, int mode, double *comac);
+        /* == comtot(j,k,xnuc,1,comac,enexc) (comtot2d.f:1-334) for n (0-based zone, xnu [keV]) pairs with the tables
+           of the current step; mode 0 = bin by bin, 1 = the sigma_mode-1 table (context must have sigma_mode 1) */
 
 /* ---- census bank: write_record / read_record contract (census2d.f:1-76) ---------------------- */
 int c2d_census_count(c2d_ctx *ctx, int64_t *n);

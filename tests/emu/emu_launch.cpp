@@ -2,6 +2,7 @@
 #include "cuda_runtime.h"
 EmuDim blockIdx, threadIdx, blockDim, gridDim;
 #include "../../compton2d_b200/csrc/c2d_track.cu"
+#include "../../compton2d_b200/csrc/c2d_sigma.cu"
 
 namespace c2d {
 template <int SRC> static void run_hist(const Params &p, long long first, long long n, long long stride)
@@ -37,5 +38,21 @@ void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t)
 {
     if (n > 0) run_grid(n, [&] { k_split3_flights(p, fl, n); });
+}
+void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t)
+{
+    run_grid((long long)n_nodes * (p.num_nt - 1), [&] { k_sigma_kn(p, xs, ms, n_nodes, Kn); });
+}
+void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
+                        double *coef, cudaStream_t)
+{
+    run_grid(p.nzone, [&] { k_sigma_prefix(p, W, AB); });
+    run_grid((long long)n_nodes * ((p.nzone + kSigZG - 1) / kSigZG), [&] { k_sigma_nodes(p, W, Kn, n_nodes, T); });
+    const long long ni = (long long)p.nzone * (n_nodes / kSigDeg);
+    run_grid(ni, [&] { k_sigma_coef(T, M, ni, coef); });
+}
+void launch_comtot_query(const Params &p, long long n, const int *zone, const double *xnu, double *out, cudaStream_t)
+{
+    if (n > 0) run_grid(n, [&] { k_comtot_query(p, n, zone, xnu, out); });
 }
 }  // namespace c2d

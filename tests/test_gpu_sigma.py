@@ -1,0 +1,78 @@
+"""sigma_mode 1 (per-step comtot table, c2d_sigma.cu) against the bin-by-bin evaluation of comtot2d.f:219-247
+(sigma_mode 0 / c2d_comtot mode 0) and, through the replay tests, against the CPU oracle.
+
+Tolerance: 2e-10 relative on comtot itself.  The table interpolates the smooth part of the exact-branch sum and adds
+the rounding noise of the reference's log(1 + y) bin by bin (kn_eta); what is left is the ~1e-11 cancellation noise
+of va - vb in intg_v, which no interpolant can follow."""
+import numpy as np
+import pytest
+
+from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step
+from synth import make_problem
+
+pytestmark = pytest.mark.gpu
+
+
+def _begin(g, P, cyc=1):
+    g.imcgen2d(ncycle=cyc, time=0.0, dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"], eps_th=P["eps_th"],
+               f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"], f_pair=P["f_pair"], k_gg=P["k_gg"], nsv=P["nsv"],
+               ewsv=P["ewsv"], Eloss_th=P["Eloss_th"], Eloss_tot=P["Eloss_tot"], zsurf=P["zsurf"], tbbl=P["tbbl"])
+
+
+def test_table_matches_bin_by_bin():
+    P = make_problem(nz=8, nr=8, nst=1000, ngroups=100, jitter=0.4)
+    rng = np.random.default_rng(5)
+    P["f_nt"] = P["f_nt"] * (1.0 + 0.8 * rng.random(P["f_nt"].shape))     # every zone its own electron spectrum
+    g = make_gpu(P, sigma_mode=1)
+    try:
+        _begin(g, P)
+        n = 400_000
+        x = 10.0 ** rng.uniform(-12.0, 13.9, n)
+        z = rng.integers(0, P["nzone"], n)
+        a, b = g.comtot(z, x, 0), g.comtot(z, x, 1)
+        assert np.all(a > 0) and np.all(np.isfinite(b))
+        r = np.abs(b / a - 1.0)
+        assert r.max() < 2e-10, (r.max(), x[r.argmax()])
+        assert np.median(r) < 1e-11
+        # beyond the table (x > 1e14 keV) the table mode falls back to the bin-by-bin sum: identical bits
+        xb = np.array([2e14, 1e15, 1e17]); zb = np.zeros(3, int)
+        assert np.array_equal(g.comtot(zb, xb, 0), g.comtot(zb, xb, 1))
+        # low-energy limit: every bin on the Thomson branch, comac -> n_e sigma_T sum(f dgamma)
+        lo = g.comtot(np.zeros(1, int), np.array([1e-12]), 1)[0]
+        w = (P["f_nt"][0, :-1] * np.diff(P["gnt"])).sum()
+        assert abs(lo / (P["n_e"][0] * 6.6516e-25 * w) - 1.0) < 1e-9
+    finally:
+        g.close()
+
+
+def test_table_follows_the_step_tables():
+    """The table is rebuilt by every c2d_step_begin from that step's f_nt (the FP update changes it every step)."""
+    P = make_problem(nz=3, nr=3, nst=100, ngroups=32)
+    g = make_gpu(P, sigma_mode=1)
+    try:
+        rng = np.random.default_rng(1)
+        x = 10.0 ** rng.uniform(-8, 8, 5000); z = rng.integers(0, 9, 5000)
+        for cyc in (1, 2):
+            P["f_nt"] = P["f_nt"] * (1.0 + 0.5 * rng.random(P["f_nt"].shape))
+            _begin(g, P, cyc)
+            a, b = g.comtot(z, x, 0), g.comtot(z, x, 1)
+            assert np.abs(b / a - 1.0).max() < 2e-10
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("cfg", [dict(nz=16, nr=16, nst=6000, ngroups=100),
+                                 dict(nz=3, nr=3, nst=600, ngroups=64, split=(20, 10, 4, 10), n_e=4.0e7),
+                                 dict(nz=5, nr=4, nst=8000, ngroups=100, split=(1, 1, 1, 10), n_e=2.0e6)])
+def test_replay_parity_with_table(cfg):
+    """Philox replay against the CPU oracle with sigma_mode 1: same bar as tests/test_gpu_parity.py."""
+    P = make_problem(**cfg)
+    o, g = make_oracle(P), make_gpu(P, sigma_mode=1)
+    try:
+        for cyc in (1, 2):
+            ro = oracle_step(o, P, cyc, field=cyc > 1)
+            rg = gpu_step(g, P, cyc, field=cyc > 1)
+            bad = compare(rg, ro, tol=1e-10, census_tol=1e-4)
+            assert not bad, (cyc, bad)
+    finally:
+        g.close()
