@@ -9,7 +9,8 @@ Workload (config.workload): BASELINE.json configs[1] -- Mrk 421-style SSC blob, 
 energy groups, 1e7 volume sources per step and GPU (nst = 2e7), split1/2/3 = 1000/1000/300, plus the census
 photons the previous steps left (weak scaling: every GPU sources 1e7 histories per step).
 A step = one IMC time step of the hot path: imcfield2d (census re-track) + imcvol2d (volume sources) +
-scattering queue + the packed tally all-reduce.  value = histories of all ranks / max-over-ranks device time.
+scattering queue + the packed tally all-reduce.  value = histories of all ranks / max-over-ranks device time of that
+region, bracketed by CUDA events on the library's stream (host gaps between the launches of the queue included).
 """
 from __future__ import annotations
 
@@ -215,10 +216,12 @@ def our_arm(args):
                    zsurf=P["zsurf"], tbbl=P["tbbl"])
         if not e2e:
             g.timing_reset()
+        g.mark()                                   # CUDA events on the library's stream bracket the tracked region
         g.imcfield2d()
         g.imcvol2d()
         g.graphics_collect()
-        ms = sum(g.kernel_time(w)[0] for w in (0, 1, 2, 4, 6))
+        g.mark(stop=True)
+        ms = g.kernel_time(7)[0]
         nl = sum(g.kernel_time(w)[1] for w in (0, 1, 2, 4, 6))
         t = g.tallies() if e2e else None
         return ms, nl, time.perf_counter() - t0, t
@@ -324,7 +327,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nst", type=int, default=20_000_000, help="particles per photon cycle per GPU (nst; sources = nst/2)")
-    ap.add_argument("--sigma-mode", type=int, default=0)
+    ap.add_argument("--sigma-mode", type=int, default=1, help="0: comtot bin by bin per history; 1: per-step table (same values to 5e-11)")
     ap.add_argument("--ref-nst", type=int, default=6_000, help="--impl reference: nst per instance (census grows every cycle)")
     ap.add_argument("--cpu-nst", type=int, default=30_000, help="nst of the bounded cpu_baseline sample (cycles 1-2, one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

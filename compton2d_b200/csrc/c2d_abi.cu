@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace c2d {
@@ -113,14 +114,28 @@ static int drain_queue(Ctx *c)
             if (!c->d_flights) {
                 c->flight_cap = std::max<int64_t>((int64_t)p.split3, (int64_t)1 << 20);
                 CU(cudaMalloc(&c->d_flights, (size_t)c->flight_cap * sizeof(FlightTask)));
+                CU(cudaMalloc(&c->d_hard, (size_t)c->flight_cap * sizeof(unsigned)));
             }
             const long long per = std::max<long long>(1, c->flight_cap / p.split3);
             for (long long t0 = 0; t0 < (long long)n3; t0 += per) {
                 const long long nt = std::min<long long>(per, (long long)n3 - t0);
+                CU(cudaMemsetAsync(c->d_qcount + 3, 0, 8, c->stream));
                 c->timer_begin(2);
-                launch_split3_attempts(p, c->d_q3 + t0, nt, c->d_flights, c->stream);
+                launch_split3_attempts(p, c->d_q3 + t0, nt, c->d_flights, c->split3_rounds, c->d_hard, c->d_qcount + 3, c->stream);
                 c->timer_end();
                 CU(cudaGetLastError());
+                if (c->split3_rounds > 0) {
+                    unsigned long long nh = 0;
+                    CU(cudaMemcpyAsync(&nh, c->d_qcount + 3, 8, cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));
+                    if (nh) {
+                        c->timer_begin(2);
+                        launch_split3_hard(p, c->d_q3 + t0, c->d_hard, (long long)nh, c->d_flights,
+                                           (unsigned long long)c->split3_rounds * kWarp, c->stream);
+                        c->timer_end();
+                        CU(cudaGetLastError());
+                    }
+                }
                 c->timer_begin(6);
                 launch_split3_flights(p, c->d_flights, nt * p.split3, c->stream);
                 c->timer_end();
@@ -195,6 +210,13 @@ int Ctx::sigma_setup()
     return 0;
 }
 
+int Ctx::sigma_ensure()
+{
+    if (dims.sigma_mode != 1 || sigma_ready) return 0;
+    sigma_ready = true;
+    return sigma_build();
+}
+
 int Ctx::sigma_build()
 {
     timer_begin(4);
@@ -228,6 +250,11 @@ int c2d_create(c2d_ctx **out, int device)
     c->device = device;
     c->n_sm = prop.multiProcessorCount;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+#ifdef C2D_EMU
+    c->split3_rounds = 0;                                         // the serial debug build has no block-team kernel
+#else
+    if (const char *e = getenv("C2D_SPLIT3_ROUNDS")) c->split3_rounds = std::max(1, atoi(e));
+#endif
     *out = reinterpret_cast<c2d_ctx *>(c);
     return 0;
 }
@@ -239,7 +266,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_f64); cudaFree(c->d_i64);
-    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_qcount);
+    cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
     c->fp_free();
@@ -428,7 +455,7 @@ int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
     c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
     c->P.ncycle = in->ncycle; c->P.key1 = (uint32_t)in->ncycle; c->P.dt = in->dt; c->P.time = in->time;
     c->field_done = false; c->vol_next = 0;
-    if (d.sigma_mode == 1) { rc = c->sigma_build(); if (rc) return rc; }
+    c->sigma_ready = false;
     CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its host arrays
     c->step_open = true;
     return 0;
@@ -441,6 +468,7 @@ int c2d_imcfield(c2d_ctx *h)
     if (c->field_done) return fail(C2D_ESTATE, "c2d_imcfield called twice in one step");
     CU(cudaSetDevice(c->device));
     c->field_done = true;
+    if (int rc = c->sigma_ensure()) return rc;
     c->timer_begin(0);
     launch_history_census(c->P, 0, c->n_census, 1, c->stream);
     c->timer_end();
@@ -459,6 +487,7 @@ int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     if (stride < 1 || first < 0) return fail(C2D_EINVAL, "bad shard first=%lld stride=%lld", (long long)first, (long long)stride);
     int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
     if (count < 0 || count > avail) count = avail;
+    if (int rc = c->sigma_ensure()) return rc;
     const int64_t chunk = (int64_t)1 << 30;
     for (int64_t done = 0; done < count; done += chunk) {
         const int64_t n = std::min(chunk, count - done);
@@ -626,6 +655,7 @@ int c2d_comtot(c2d_ctx *h, int64_t n, const int32_t *zone, const double *xnu, in
         if (zone[i] < 0 || zone[i] >= c->nzone || !(xnu[i] > 0.0)) return fail(C2D_EINVAL, "query %lld: zone %d xnu %g", (long long)i, zone[i], xnu[i]);
     if (n == 0) return 0;
     CU(cudaSetDevice(c->device));
+    if (int rc = c->sigma_ensure()) return rc;
     int *d_zone = nullptr; double *d_x = nullptr, *d_out = nullptr;
     CU(cudaMalloc(&d_zone, n * 4)); CU(cudaMalloc(&d_x, n * 8)); CU(cudaMalloc(&d_out, n * 8));
     CU(cudaMemcpyAsync(d_zone, zone, n * 4, cudaMemcpyHostToDevice, c->stream));
@@ -645,6 +675,18 @@ int c2d_kernel_time_ms(c2d_ctx *h, int which, float *ms, int64_t *launches)
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c) return fail(C2D_EINVAL, "NULL ctx");
     if (which == -1) { c->timing = true; return 0; }          // enable
+    if (which == -3 || which == -4) {                         // bracket a region on the library's stream -> family 7
+        CU(cudaSetDevice(c->device));
+        if (!c->ev_mark[0]) { CU(cudaEventCreate(&c->ev_mark[0])); CU(cudaEventCreate(&c->ev_mark[1])); }
+        CU(cudaEventRecord(c->ev_mark[which == -3 ? 0 : 1], c->stream));
+        if (which == -4) {
+            float t = 0;
+            CU(cudaEventSynchronize(c->ev_mark[1]));
+            CU(cudaEventElapsedTime(&t, c->ev_mark[0], c->ev_mark[1]));
+            c->k_ms[7] += t; c->k_launches[7]++;
+        }
+        return 0;
+    }
     if (which == -2) { c->timer_collect(); for (int k = 0; k < 8; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return 0; }   // reset
     if (which < 0 || which >= 8) return fail(C2D_EINVAL, "kernel family %d", which);
     c->timer_collect();

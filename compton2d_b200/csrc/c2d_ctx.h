@@ -26,6 +26,8 @@ struct Ctx {
     CollTask *d_q[2] = {nullptr, nullptr}, *d_q3 = nullptr;
     FlightTask *d_flights = nullptr;       // accepted 3rd-split sub-children of one chunk of split3 tasks
     int64_t flight_cap = 0;
+    unsigned *d_hard = nullptr;            // sub-children the warp phase of the 3rd split left unresolved
+    int split3_rounds = 32;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS)
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;
     // offsets (in doubles) into d_step / d_f64, (in int64) into d_i64
@@ -44,8 +46,10 @@ struct Ctx {
     int *d_sig_ms = nullptr;
     double *d_sig_W = nullptr, *d_sig_AB = nullptr, *d_sig_T = nullptr, *d_sig_coef = nullptr, *d_sig_Kn = nullptr, *d_sig_M = nullptr;
     std::vector<double> h_gam0, h_opb;
+    bool sigma_ready = false;
     int sigma_setup();
     int sigma_build();
+    int sigma_ensure();                    // builds the table on the step's first use
     // Fokker-Planck state (c2d_fp.cu)
     FpState *fp = nullptr;
     void fp_free();
@@ -55,6 +59,7 @@ struct Ctx {
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_which;
     size_t ev_used = 0;
+    cudaEvent_t ev_mark[2] = {nullptr, nullptr};
     double k_ms[8] = {0};
     int64_t k_launches[8] = {0};
     void timer_begin(int which);

@@ -36,7 +36,7 @@ enum { MODE_PRE = 2, MODE_TRIAL = -1, MODE_TRIAL_SLOW = -2, MODE_F0 = 0, MODE_CH
 enum { END_KILLED = 0, END_CENSUS = 1, END_LEAK = 2, END_DROPPED = 3, END_COLLISION = 4, END_LOWEW = 5,
        END_OVERFLOW = 6, END_FATAL = 7 };
 enum { CNT_NDXOUT = 0, CNT_CMCOUNT1, CNT_CMCOUNT2, CNT_LKCOUNT, CNT_NEVENTS, CNT_HISTORIES, CNT_TRIALS,
-       CNT_MULTIPLE, CNT_KILLED, CNT_SEGOVF, CNT_LITERAL, CNT_QPEAK, CNT_FATAL, CNT_SEGMENTS, CNT_PAD1, CNT_PAD2, CNT_N };   // CNT_N == 16
+       CNT_MULTIPLE, CNT_KILLED, CNT_SEGOVF, CNT_LITERAL, CNT_QPEAK, CNT_FATAL, CNT_SEGMENTS, CNT_S3PASSES, CNT_S3HARD, CNT_N };   // CNT_N == 16
 
 struct Photon {
     double xnu, wmu, phi, rpre, zpre, dcen, ew;

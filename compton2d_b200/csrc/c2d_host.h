@@ -7,7 +7,10 @@ namespace c2d {
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st);
-void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t st);
+void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
+                            unsigned *hard, unsigned long long *hard_count, cudaStream_t st);
+void launch_split3_hard(const Params &p, const CollTask *q3_in, const unsigned *hard, long long n_hard, FlightTask *out,
+                        unsigned long long first_attempt, cudaStream_t st);
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st);
 void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t st);
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,

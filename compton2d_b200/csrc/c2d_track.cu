@@ -362,58 +362,137 @@ __global__ void __launch_bounds__(128) k_children(const Params p, const CollTask
 
 // 3rd split, imctrk2d.f:641-669: every sub-child ii2 repeats compb2d until the scattered photon again exceeds
 // the trigger.  In Philox replay mode each pass of that rejection loop owns the stream mix64(S_sub, attempt), so
-// the passes can be evaluated in any order: one WARP per (3rd-split child, ii2), lane l tries attempt base + l + 1,
+// the passes can be evaluated in any order by a TEAM of threads: thread l of the team tries attempt base + l + 1,
 // the lowest accepted attempt wins.  A pass whose electron cannot reach the trigger (gain <= (1+beta)^2 gamma^2
 // < 4 gamma^2) is rejected right after the electron draw.  The nth2d tallies of the passes up to and including
-// the winner are committed (the sequential loop made exactly those draws); later lanes' are discarded.
-__global__ void __launch_bounds__(128) k_split3_attempts(const Params p, const CollTask *q3_in, long long n_sub, FlightTask *out)
+// the winner are committed (the sequential loop made exactly those draws); later threads' are discarded.
+//   k_split3_attempts  team = one warp per (3rd-split child, ii2), at most max_rounds rounds (0 = no limit); what is
+//                      still unresolved (acceptance can be as low as 1e-6 per pass) is listed in `hard`
+//   k_split3_hard      team = one block of 512 threads per listed sub-child, continuing at attempt `first_attempt`
+struct Split3Sub {
+    const CollTask *task;
+    int zi;
+    double ewcsv, ewold, trigger, gain_min, znu;
+    uint64_t S_sub;
+};
+__device__ __forceinline__ void split3_sub(const Params &p, const CollTask *q3_in, long long w, Split3Sub &u)
 {
-    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
-    if (w >= n_sub) return;                                       // whole warps leave together
-    const int lane = lane_id();
-    const CollTask &task = q3_in[w / p.split3];
+    u.task = q3_in + w / p.split3;
     const int ii2 = (int)(w % p.split3) + 1;
-    const double ewcsv = task.p.ew / p.split2;
-    const double ewold = ewcsv / p.split3;
-    const double trigger = ewold * p.split2 * p.split1 * p.spl3_trg;
-    const double gain_min = (double)p.split2 * p.split1 * p.spl3_trg;
-    const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
-    const double znu = task.p.xnu / 5.11e2;
-    const uint64_t S_sub = mix64(task.sid, (uint64_t)ii2);
-    Rng rng; Photon P; int i_gam = 0;
-    for (uint64_t base = 0;; base += kWarp) {
-        const uint64_t attempt = base + (uint64_t)lane + 1;
-        rng.stream(mix64(S_sub, attempt));
-        ElRec rec = {0ull, 0};
-        ElDraw e;
-        compb2d_electron(p, rng, zi, znu, e, i_gam, &rec);
-        bool ok = false;
-        if (4.0 * e.gamm * e.gamm * (1.0 + 1.e-9) > gain_min) {
-            P = task.p;
-            P.ew = ewcsv / p.split3;
-            compb2d_finish(p, rng, P, e);
-            ok = P.ew > trigger;
+    u.ewcsv = u.task->p.ew / p.split2;
+    u.ewold = u.ewcsv / p.split3;
+    u.trigger = u.ewold * p.split2 * p.split1 * p.spl3_trg;
+    u.gain_min = (double)p.split2 * p.split1 * p.spl3_trg;
+    u.zi = (u.task->p.jph - 1) * p.nr + (u.task->p.kph - 1);
+    u.znu = u.task->p.xnu / 5.11e2;
+    u.S_sub = mix64(u.task->sid, (uint64_t)ii2);
+}
+// one pass of the rejection loop (imctrk2d.f:642-656)
+__device__ __forceinline__ bool split3_pass(const Params &p, const Split3Sub &u, uint64_t attempt, Rng &rng, Photon &P,
+                                            int &i_gam, ElRec &rec)
+{
+    rng.stream(mix64(u.S_sub, attempt));
+    rec.bins = 0ull; rec.n = 0;
+    ElDraw e;
+    compb2d_electron(p, rng, u.zi, u.znu, e, i_gam, &rec);
+    if (!(4.0 * e.gamm * e.gamm * (1.0 + 1.e-9) > u.gain_min)) return false;
+    P = u.task->p;
+    P.ew = u.ewcsv / p.split3;
+    compb2d_finish(p, rng, P, e);
+    return P.ew > u.trigger;
+}
+// nth2d tallies of a committed pass.  `hist` is the block's shared-memory copy of nelectron (flushed once per block:
+// the passes hammer a handful of low-gamma bins, which global atomics would serialise), or null.
+__device__ __forceinline__ void split3_commit(const Params &p, const Split3Sub &u, uint64_t attempt, const ElRec &rec, unsigned *hist)
+{
+    if (rec.n <= 4) {
+        for (int k = 0; k < rec.n; k++) {
+            const unsigned bin = (unsigned)((rec.bins >> (16 * k)) & 0xFFFFull);
+            if (hist) atomicAdd(hist + bin, 1u); else atomicAdd(p.nelectron + bin, 1ull);
         }
-        const unsigned m = warp_ballot(ok);
-        const int first = m ? first_lane(m) : kWarp;
-        if (lane <= first) {
-            if (rec.n <= 4) {
-                for (int k = 0; k < rec.n; k++) atomicAdd(p.nelectron + ((rec.bins >> (16 * k)) & 0xFFFFull), 1ull);
-            } else {                                              // > 4 K-N rejections in one pass: replay it, tallying
-                Rng r2; r2.stream(mix64(S_sub, attempt));
-                ElDraw e2; int ig2;
-                compb2d_electron(p, r2, zi, znu, e2, ig2, nullptr);
-            }
-        }
-        if (m) {
-            if (lane == first) {
-                FlightTask &f = out[w];
-                f.p = P; f.i_gam = i_gam; f.sid = rng.sid; f.d = rng.d; f.zi = zi; f.ewold = ewold;
-            }
-            return;
-        }
+    } else {                                                      // > 4 K-N rejections in one pass: replay it, tallying
+        Rng r2; r2.stream(mix64(u.S_sub, attempt));
+        ElDraw e2; int ig2;
+        compb2d_electron(p, r2, u.zi, u.znu, e2, ig2, nullptr);
     }
 }
+__device__ __forceinline__ void split3_store(FlightTask &f, const Photon &P, int i_gam, const Rng &rng, const Split3Sub &u)
+{
+    f.p = P; f.i_gam = i_gam; f.sid = rng.sid; f.d = rng.d; f.zi = u.zi; f.ewold = u.ewold;
+}
+constexpr int kHistMax = 1024;
+#ifdef C2D_EMU
+#define C2D_HIST_BEGIN(p) unsigned *hist = nullptr;
+#define C2D_HIST_END(p)
+#else
+#define C2D_HIST_BEGIN(p)                                                                             \
+    __shared__ unsigned s_hist[kHistMax];                                                             \
+    unsigned *hist = ((p).num_nt + 2 <= kHistMax) ? s_hist : nullptr;                                 \
+    if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x) s_hist[i_] = 0u;      \
+    __syncthreads();
+#define C2D_HIST_END(p)                                                                               \
+    __syncthreads();                                                                                  \
+    if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x)                       \
+        if (s_hist[i_]) atomicAdd((p).nelectron + i_, (unsigned long long)s_hist[i_]);
+#endif
+
+__global__ void __launch_bounds__(128) k_split3_attempts(const Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
+                                                         int max_rounds, unsigned *hard, unsigned long long *hard_count)
+{
+    C2D_HIST_BEGIN(p)
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    if (w < n_sub) {                                              // whole warps together
+        const int lane = lane_id();
+        Split3Sub u;
+        split3_sub(p, q3_in, w, u);
+        Rng rng; Photon P; int i_gam = 0; ElRec rec;
+        uint64_t base = 0;
+        bool done = false;
+        for (int round = 0; max_rounds == 0 || round < max_rounds; round++, base += kWarp) {
+            const uint64_t attempt = base + (uint64_t)lane + 1;
+            const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
+            const unsigned m = warp_ballot(ok);
+            const int first = m ? first_lane(m) : kWarp;
+            if (lane <= first) split3_commit(p, u, attempt, rec, hist);
+            if (m) {
+                if (lane == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, base + (uint64_t)first + 1); }
+                done = true;
+                break;
+            }
+        }
+        if (!done && lane == 0) { hard[atomicAdd(hard_count, 1ull)] = (unsigned)w; count(p, CNT_S3HARD); }
+    }
+    C2D_HIST_END(p)
+}
+
+#ifndef C2D_EMU
+__global__ void __launch_bounds__(512) k_split3_hard(const Params p, const CollTask *q3_in, const unsigned *hard, FlightTask *out,
+                                                     unsigned long long first_attempt)
+{
+    __shared__ int win;
+    C2D_HIST_BEGIN(p)
+    const long long w = hard[blockIdx.x];
+    Split3Sub u;
+    split3_sub(p, q3_in, w, u);
+    Rng rng; Photon P; int i_gam = 0; ElRec rec;
+    for (uint64_t base = first_attempt;; base += blockDim.x) {
+        if (threadIdx.x == 0) win = 0x7fffffff;
+        __syncthreads();
+        const uint64_t attempt = base + threadIdx.x + 1;
+        const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
+        if (ok) atomicMin(&win, (int)threadIdx.x);
+        __syncthreads();
+        const int first = win;
+        if ((int)threadIdx.x <= first) split3_commit(p, u, attempt, rec, hist);
+        if (first != 0x7fffffff) {
+            if ((int)threadIdx.x == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, attempt); }
+            break;
+        }
+        __syncthreads();                                          // everyone has read `win` before it is reset
+    }
+    C2D_HIST_END(p)
+}
+#endif
 
 // one thread per accepted 3rd-split sub-child: tallies of l.657-661, then the scat_flag = 1 flight
 __global__ void __launch_bounds__(128) k_split3_flights(const Params p, const FlightTask *fl, long long n)
@@ -448,11 +527,17 @@ void launch_children(const Params &p, const CollTask *q_in, long long n_in, cuda
     const long long n = n_in * p.split2;
     k_children<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q_in, n_in);
 }
-void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t st)
+void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
+                            unsigned *hard, unsigned long long *hard_count, cudaStream_t st)
 {
     if (n_tasks <= 0) return;
     const long long n = n_tasks * p.split3 * kWarp;               // one warp per sub-child
-    k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q3_in, n_tasks * p.split3, out);
+    k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q3_in, n_tasks * p.split3, out, max_rounds, hard, hard_count);
+}
+void launch_split3_hard(const Params &p, const CollTask *q3_in, const unsigned *hard, long long n_hard, FlightTask *out,
+                        unsigned long long first_attempt, cudaStream_t st)
+{
+    if (n_hard > 0) k_split3_hard<<<(unsigned)n_hard, 512, 0, st>>>(p, q3_in, hard, out, first_attempt);
 }
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st)
 {

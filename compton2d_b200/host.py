@@ -294,6 +294,10 @@ class Compton2d:
     def timing(self, enable=True):
         _l.check(self.L.c2d_kernel_time_ms(self.h, -1 if enable else -2, None, None))
 
+    def mark(self, stop=False):
+        """Record the start / stop CUDA event of a timed bracket on the library's stream (kernel_time(7))."""
+        _l.check(self.L.c2d_kernel_time_ms(self.h, -4 if stop else -3, None, None))
+
     def timing_reset(self):
         _l.check(self.L.c2d_kernel_time_ms(self.h, -2, None, None))
 

@@ -116,7 +116,9 @@ enum {
     C2D_CNT_LITERAL = 10,    /* trial flights executed literally (collision candidates) */
     C2D_CNT_QPEAK = 11,      /* peak number of queued collision tasks */
     C2D_CNT_FATAL = 12,      /* device-side fatal conditions (0 on success) */
-    C2D_CNT_SEGMENTS = 13    /* zone crossings of the collision-free rays */
+    C2D_CNT_SEGMENTS = 13,   /* zone crossings of the collision-free rays */
+    C2D_CNT_S3PASSES = 14,   /* passes of the 3rd-split rejection loop (imctrk2d.f:642-656) up to each accepted one */
+    C2D_CNT_S3HARD = 15      /* 3rd-split sub-children finished by the block-team kernel */
 };
 
 /* Escape record: the 7 doubles of imcleak2d.f:171,181 (t_bound,xnu,ew,rpre,zpre,wmu,phi). */
@@ -195,7 +197,10 @@ void c2d_unpack_bin_first(const double *dense, int nbin_pad, int jmax, int kmax,
 void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int nz, int nr, double *common);
 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
-int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);   /* CUDA-event time per kernel family */
+int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);
+        /* CUDA-event time per kernel family on the library's stream.  which >= 0: read family (0 k_history, 1 k_children,
+           2 k_split3_attempts/_hard, 3 FP, 4 sigma table, 5 tally bench, 6 k_split3_flights, 7 bracket);
+           -1 enable, -2 reset, -3 / -4 record the start / stop event of a bracket (accumulated in family 7) */
 int c2d_tally_bench(c2d_ctx *ctx, int64_t n_events, int kind, float *ms, int64_t *bytes);
 
 #ifdef __cplusplus

@@ -31,10 +31,12 @@ void launch_children(const Params &p, const CollTask *q_in, long long n_in, cuda
 {
     if (n_in > 0) run_grid(n_in * p.split2, [&] { k_children(p, q_in, n_in); });
 }
-void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, cudaStream_t)
-{   // kWarp == 1 in this build: one serial "warp" per sub-child
-    if (n_tasks > 0) run_grid(n_tasks * p.split3, [&] { k_split3_attempts(p, q3_in, n_tasks * p.split3, out); });
+void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
+                            unsigned *hard, unsigned long long *hard_count, cudaStream_t)
+{   // kWarp == 1 in this build: one serial "warp" per sub-child, no round limit
+    if (n_tasks > 0) run_grid(n_tasks * p.split3, [&] { k_split3_attempts(p, q3_in, n_tasks * p.split3, out, 0, hard, hard_count); });
 }
+void launch_split3_hard(const Params &, const CollTask *, const unsigned *, long long, FlightTask *, unsigned long long, cudaStream_t) {}
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t)
 {
     if (n > 0) run_grid(n, [&] { k_split3_flights(p, fl, n); });

@@ -49,6 +49,7 @@ inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return 0; }
 inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return 0; }
 inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t, cudaEvent_t) { *ms = 0; return 0; }
 inline cudaError_t cudaEventDestroy(cudaEvent_t) { return 0; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return 0; }
 inline cudaError_t cudaFuncSetAttribute(const void *, int, int) { return 0; }
 enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 

@@ -76,3 +76,21 @@ def test_replay_parity_with_table(cfg):
             assert not bad, (cyc, bad)
     finally:
         g.close()
+
+
+def test_third_split_block_teams(monkeypatch):
+    """C2D_SPLIT3_ROUNDS=1: the warp phase of the 3rd split gives up after 32 passes, so most sub-children are
+    finished by the 512-thread teams of k_split3_hard; replay parity (incl. the nelectron tally of every pass the
+    sequential rejection loop makes) must not change."""
+    monkeypatch.setenv("C2D_SPLIT3_ROUNDS", "1")
+    P = make_problem(nz=3, nr=3, nst=600, ngroups=64, split=(20, 10, 4, 1000), n_e=4.0e7)
+    o, g = make_oracle(P), make_gpu(P)
+    try:
+        for cyc in (1, 2):
+            ro = oracle_step(o, P, cyc, field=cyc > 1)
+            rg = gpu_step(g, P, cyc, field=cyc > 1)
+            bad = compare(rg, ro, tol=1e-10, census_tol=1e-4)
+            assert not bad, (cyc, bad)
+        assert rg["counters"]["cmcount2"] > rg["counters"]["cmcount1"] * P["split"][1]      # 3rd split happened
+    finally:
+        g.close()
