@@ -1,6 +1,7 @@
 """Build libcompton2d_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
 from __future__ import annotations
 
+import os
 import subprocess
 import sys
 from pathlib import Path
@@ -21,7 +22,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         [HERE.parent / "include" / "compton2d_b200.h"]
     if not force and LIB.exists() and LIB.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
         return LIB
-    cmd = ["nvcc", *FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
+    extra = os.environ.get("C2D_NVCC_EXTRA", "").split()       # experiments, e.g. -DC2D_HIST_MINB=5
+    cmd = ["nvcc", *FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
     subprocess.check_call(cmd)
     return LIB
 

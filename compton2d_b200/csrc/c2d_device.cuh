@@ -156,6 +156,26 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
+// four blocks with counters (c0, c1, c2 + j, 0), j = 0..3, advanced round by round together
+__device__ __forceinline__ void philox4x32_10x4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1,
+                                                uint32_t (&o0)[4], uint32_t (&o1)[4], uint32_t (&o2)[4], uint32_t (&o3)[4])
+{
+    uint32_t a[4] = {c0, c0, c0, c0}, b[4] = {c1, c1, c1, c1}, c[4] = {c2, c2 + 1u, c2 + 2u, c2 + 3u}, d[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint64_t p0 = (uint64_t)0xD2511F53u * a[j], p1 = (uint64_t)0xCD9E8D57u * c[j];
+            a[j] = (uint32_t)(p1 >> 32) ^ b[j] ^ k0; b[j] = (uint32_t)p1; c[j] = (uint32_t)(p0 >> 32) ^ d[j] ^ k1; d[j] = (uint32_t)p0;
+        }
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    o0[0] = a[0]; o0[1] = b[0]; o0[2] = c[0]; o0[3] = d[0];
+    o1[0] = a[1]; o1[1] = b[1]; o1[2] = c[1]; o1[3] = d[1];
+    o2[0] = a[2]; o2[1] = b[2]; o2[2] = c[2]; o2[3] = d[2];
+    o3[0] = a[3]; o3[1] = b[3]; o3[2] = c[3]; o3[3] = d[3];
+}
+
 __device__ __forceinline__ double u52(uint32_t lo, uint32_t hi)
 {   // 52-bit uniform in (0,1): ((w >> 12) + 0.5) * 2^-52, exactly representable
     const uint64_t w = ((uint64_t)hi << 32) | lo;
@@ -189,29 +209,37 @@ struct Rng {
     }
 };
 
-// The xi of trial flight t (0-based) of a history with trial stream S: K = coarse16 << 36 | fine36,
-// u = (K + 0.5) 2^-52.  coarse = halfword (t & 7) of philox(S, t >> 3, 0); fine = low 36 bits of words 0,1 of
-// philox(S, t, 1).  Eight trials share one Philox call for the coarse part, and a trial whose coarse halfword
+// The xi of trial flight t (0-based) of a history with trial stream S: K = coarse8 << 44 | fine44,
+// u = (K + 0.5) 2^-52.  coarse = byte (t & 15) of philox(S, t >> 4, 0); fine = word 0 and the low 12 bits of word 1
+// of philox(S, t, 1).  Sixteen trials share one Philox call for the coarse part, and a trial whose coarse byte
 // is below the threshold's never needs the fine part (see history()).
-__device__ __forceinline__ uint64_t trial_fine36(const Params &p, uint64_t S, uint32_t t)
+__device__ __forceinline__ uint64_t trial_fine44(const Params &p, uint64_t S, uint32_t t)
 {
     uint32_t o[4];
     philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t, 1u, p.key0, p.key1, o);
-    return (((uint64_t)(o[1] & 0xFu)) << 32) | o[0];
+    return (((uint64_t)(o[1] & 0xFFFu)) << 32) | o[0];
 }
 __device__ __forceinline__ double trial_uniform(const Params &p, uint64_t S, uint32_t t)
 {
     uint32_t o[4];
-    philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t >> 3, 0u, p.key0, p.key1, o);
-    const uint32_t w = o[(t & 7u) >> 1];
-    const uint64_t coarse = (t & 1u) ? (w >> 16) : (w & 0xFFFFu);
-    const uint64_t K = (coarse << 36) | trial_fine36(p, S, t);
+    philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t >> 4, 0u, p.key0, p.key1, o);
+    const uint64_t coarse = (o[(t & 15u) >> 2] >> (8u * (t & 3u))) & 0xFFu;
+    const uint64_t K = (coarse << 44) | trial_fine44(p, S, t);
     return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
 }
 
 // ------------------------------------------------------------------------------------------ small helpers
-// does either 16-bit half of w reach c (c <= 0x10000)?
-__device__ __forceinline__ bool half_ge(uint32_t w, uint32_t c) { return ((w & 0xFFFFu) >= c) | ((w >> 16) >= c); }
+// 0xFF in every byte of w that is >= c (c <= 0x100; c = 0x100: none)
+__device__ __forceinline__ uint32_t bytes_ge(uint32_t w, uint32_t c)
+{
+#ifdef C2D_EMU
+    uint32_t m = 0;
+    for (int b = 0; b < 4; b++) if (((w >> (8 * b)) & 0xFFu) >= c) m |= 0xFFu << (8 * b);
+    return m;
+#else
+    return (c <= 0xFFu) ? __vcmpgeu4(w, c * 0x01010101u) : 0u;
+#endif
+}
 __device__ __forceinline__ void atomic_add_f64(double *a, double v) { atomicAdd(a, v); }
 __device__ __forceinline__ void count(const Params &p, int which, unsigned long long n = 1ull)
 {
@@ -427,22 +455,55 @@ __device__ __forceinline__ void sig_begin(const Params &p, double xnu, SigCtx &c
     c.s = (t - p.sig_lo[c.j]) * p.sig_iw[c.j] - 1.0;
 }
 
-// Table value for up to four zones of one photon energy: the bins of the exact branch are walked once for the
-// rounding-noise term (two kn_eta per bin instead of two dilogarithms and three logarithms).
-__device__ __forceinline__ void comtot_table_zones(const Params &p, const SigCtx &c, const int *zi, int nzn, double *comac)
+// Rounding-noise term of one electron bin (see kn_eta): pref_i (eta(a1_i x) - eta(a2_i x)).  The a-side noise is
+// < 1e-12 of the bin once y_a > 0.1 (it falls like 1 / y^3 from 1.6e-10 at the branch switch).
+__device__ __forceinline__ double kn_noise_bin(const Params &p, int i, double x)
+{
+    const double ya = p.kn_a1[i] * x;
+    return p.kn_pref[i] * (((ya < 0.1) ? kn_eta(ya) : 0.0) - kn_eta(p.kn_a2[i] * x));
+}
+
+// Noise sums  sum_{i >= m} noise_i(x) W[z][i]  for up to four zones, bins walked by ONE thread ...
+__device__ __forceinline__ void sig_noise_zones(const Params &p, double x, int m, const int *zi, int nzn, double (&ee)[4])
+{
+    const int N = p.num_nt;
+    const double *w0 = p.sig_W + (size_t)zi[0] * N, *w1 = p.sig_W + (size_t)zi[nzn > 1 ? 1 : 0] * N;
+    const double *w2 = p.sig_W + (size_t)zi[nzn > 2 ? 2 : 0] * N, *w3 = p.sig_W + (size_t)zi[nzn > 3 ? 3 : 0] * N;
+    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    for (int i = m; i < N - 1; i++) {
+        const double q = kn_noise_bin(p, i, x);
+        e0 = fma(q, w0[i], e0); e1 = fma(q, w1[i], e1); e2 = fma(q, w2[i], e2); e3 = fma(q, w3[i], e3);
+    }
+    ee[0] = e0; ee[1] = e1; ee[2] = e2; ee[3] = e3;
+}
+// ... or by the whole warp for one photon energy: bins strided over the lanes, so the W rows are read coalesced
+// (a thread-per-photon walk touches 32 different rows per load).  Every lane must call; all lanes get the sums.
+__device__ __forceinline__ void sig_noise_zones_warp(const Params &p, double x, int m, int z0, int z1, int z2, int z3, int nzn,
+                                                     double (&ee)[4])
+{
+    const int N = p.num_nt;
+    const double *w0 = p.sig_W + (size_t)z0 * N, *w1 = p.sig_W + (size_t)z1 * N;
+    const double *w2 = p.sig_W + (size_t)z2 * N, *w3 = p.sig_W + (size_t)z3 * N;
+    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+    for (int i = m + lane_id(); i < N - 1; i += kWarp) {
+        const double q = kn_noise_bin(p, i, x);
+        e0 = fma(q, w0[i], e0);
+        if (nzn > 1) e1 = fma(q, w1[i], e1);
+        if (nzn > 2) e2 = fma(q, w2[i], e2);
+        if (nzn > 3) e3 = fma(q, w3[i], e3);
+    }
+    ee[0] = warp_sum(e0);
+    ee[1] = (nzn > 1) ? warp_sum(e1) : 0.0;
+    ee[2] = (nzn > 2) ? warp_sum(e2) : 0.0;
+    ee[3] = (nzn > 3) ? warp_sum(e3) : 0.0;
+}
+
+// Table value for up to four zones of one photon energy, given the noise sums `ee` (zero when c.j < 0)
+__device__ __forceinline__ void comtot_table_finish(const Params &p, const SigCtx &c, const int *zi, int nzn, const double (&ee)[4],
+                                                    double *comac)
 {
     const double sigthom = 6.6516e-25;
     const int N = p.num_nt;
-    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-    if (c.j >= 0) {
-        const double *w0 = p.sig_W + (size_t)zi[0] * N, *w1 = p.sig_W + (size_t)zi[nzn > 1 ? 1 : 0] * N;
-        const double *w2 = p.sig_W + (size_t)zi[nzn > 2 ? 2 : 0] * N, *w3 = p.sig_W + (size_t)zi[nzn > 3 ? 3 : 0] * N;
-        for (int i = c.m; i < N - 1; i++) {
-            const double q = p.kn_pref[i] * (kn_eta(p.kn_a1[i] * c.x) - kn_eta(p.kn_a2[i] * c.x));
-            e0 = fma(q, w0[i], e0); e1 = fma(q, w1[i], e1); e2 = fma(q, w2[i], e2); e3 = fma(q, w3[i], e3);
-        }
-    }
-    const double ee[4] = {e0, e1, e2, e3};
     const double inv_x2 = 1.0 / (c.x * c.x);
     for (int k = 0; k < nzn; k++) {
         const int z = zi[k];
@@ -458,6 +519,12 @@ __device__ __forceinline__ void comtot_table_zones(const Params &p, const SigCtx
         }
         comac[k] = (v < 1.e-40) ? 1.e-40 : p.n_e[z] * v;
     }
+}
+__device__ __forceinline__ void comtot_table_zones(const Params &p, const SigCtx &c, const int *zi, int nzn, double *comac)
+{
+    double ee[4] = {0.0, 0.0, 0.0, 0.0};
+    if (c.j >= 0) sig_noise_zones(p, c.x, c.m, zi, nzn, ee);
+    comtot_table_finish(p, c, zi, nzn, ee, comac);
 }
 
 // comtot for one zone by one thread (scat_flag = 1 flights; `c` was set up by flight_begin when sigma_mode = 1)
@@ -525,8 +592,10 @@ __device__ __forceinline__ void compb2d_electron(const Params &p, Rng &rng, int 
     }
 }
 
-// compb_2d.f:96-318: rest-frame energy ratio, azimuths, Lorentz back-transform, new direction and bins
-__device__ __forceinline__ void compb2d_finish(const Params &p, Rng &rng, Photon &P, const ElDraw &e)
+// compb_2d.f:96-318: rest-frame energy ratio, azimuths, Lorentz back-transform, new direction and bins.
+// `ew_min` >= 0: a speculative caller (3rd-split passes) only wants the photon if its new weight exceeds ew_min; the
+// function returns false as soon as the scattered energy is known to miss it (the rest of the pass's stream is unused).
+__device__ __forceinline__ bool compb2d_finish(const Params &p, Rng &rng, Photon &P, const ElDraw &e, double ew_min = -1.0)
 {
     const double fuzz = 1.e-10, emasskev = 5.11e2;
     const double znu = P.xnu / emasskev;
@@ -555,6 +624,7 @@ __device__ __forceinline__ void compb2d_finish(const Params &p, Rng &rng, Photon
     double omeges = games * omege + cazes * sqrt((1. - omege * omege + fuzz) * (1. - games * games));
     C2D_CLAMP8(omeges);
     const double znus = (1.0 + betb * omeges) * gamm * znues;
+    if (ew_min >= 0.0 && !(P.ew * (znus * emasskev) / P.xnu > ew_min)) return false;
     double gams = 1.0 - (znue - znues) / (znu * znus);
     C2D_CLAMP8(gams);
     do {                                             // label 220
@@ -578,6 +648,7 @@ __device__ __forceinline__ void compb2d_finish(const Params &p, Rng &rng, Photon
     P.xnu = xnus;
     P.wmu = wmus;
     P.phi = phis;
+    return true;
 }
 
 // compb_2d.f:1-318; P.jph/kph give the zone

@@ -96,22 +96,35 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     const bool fast = active && !overflow;
     // B: sigma_sc per crossing (comac_ar cache of l.175-183: one comtot per zone and history)
     if (p.sigma_mode == 1) {
-        if (fast) {
-            SigCtx sc;
-            sig_begin(p, T0.xnu, sc);
-            unsigned have = 0u;
-            for (;;) {
-                int zl[4] = {0, 0, 0, 0}, nzn = 0;
-                for (int s = 0; s < nseg && nzn < 4; s++) {
-                    if (have & (1u << s)) continue;
-                    bool seen = false;
-                    for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
-                    if (!seen) zl[nzn++] = segs[s].zi;
-                }
-                if (nzn == 0) break;
+        SigCtx sc; sc.j = -2; sc.m = 0; sc.x = 1.0; sc.s = 0.0;
+        if (fast) sig_begin(p, T0.xnu, sc);
+        unsigned have = fast ? 0u : 0xffffffffu;
+        for (;;) {
+            int zl[4] = {0, 0, 0, 0}, nzn = 0;
+            for (int s = 0; s < nseg && nzn < 4; s++) {
+                if (have & (1u << s)) continue;
+                bool seen = false;
+                for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
+                if (!seen) zl[nzn++] = segs[s].zi;
+            }
+            if (!warp_ballot(nzn > 0)) break;
+            // the noise sums of the exact-branch bins, the warp serving one lane's photon at a time
+            double ee[4] = {0.0, 0.0, 0.0, 0.0};
+            unsigned todo = warp_ballot(nzn > 0 && sc.j >= 0);
+            while (todo) {
+                const int src = first_lane(todo);
+                todo &= todo - 1;
+                const double xs = warp_shfl(sc.x, src);
+                const int ms = warp_shfl(sc.m, src), an = warp_shfl(nzn, src);
+                const int a0 = warp_shfl(zl[0], src), a1 = warp_shfl(zl[1], src), a2 = warp_shfl(zl[2], src), a3 = warp_shfl(zl[3], src);
+                double r[4];
+                sig_noise_zones_warp(p, xs, ms, a0, a1, a2, a3, an, r);
+                if (lane_id() == src) { ee[0] = r[0]; ee[1] = r[1]; ee[2] = r[2]; ee[3] = r[3]; }
+            }
+            if (nzn > 0) {
                 double cm[4];
-                if (sc.j != -2) comtot_table_zones(p, sc, zl, nzn, cm);
-                else comtot_zones(p, T0.xnu, zl, nzn, cm);
+                if (sc.j != -2) comtot_table_finish(p, sc, zl, nzn, ee, cm);
+                else comtot_zones(p, T0.xnu, zl, nzn, cm);             // beyond the table: bin by bin
                 for (int s = 0; s < nseg; s++) {
                     if (have & (1u << s)) continue;
                     for (int m = 0; m < nzn; m++)
@@ -171,30 +184,59 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
         // u = (K + 0.5) 2^-52 >= thr  <=>  K >= ceil(thr 2^52 - 0.5): the filter runs on integers
         const double tk = thr * 4503599627370496.0 - 0.5;
         Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
-        // K = coarse16 << 36 | fine36 (trial_uniform): a trial whose coarse halfword is below the threshold's
-        // cannot collide, and eight trials share one Philox call for their coarse halfwords
-        const uint32_t Cthr = (uint32_t)(Kthr >> 36);
+        // K = coarse8 << 44 | fine44 (trial_uniform): a trial whose coarse byte is below the threshold's cannot
+        // collide, and sixteen trials share one Philox call for their coarse bytes
+        const uint32_t Cthr = (uint32_t)(Kthr >> 44);
         const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
-        for (int t8 = 0; 8 * t8 < p.split1; t8++) {
-            uint32_t o[4];
-            philox4x32_10(s_lo, s_hi, (uint32_t)t8, 0u, p.key0, p.key1, o);
-            if (!(half_ge(o[0], Cthr) | half_ge(o[1], Cthr) | half_ge(o[2], Cthr) | half_ge(o[3], Cthr))) continue;
+        // pass 1 (convergent): the coarse bytes of all trials; candidates (coarse >= Cthr, 1 trial in 256 for an
+        // optically thin ray) are only noted.  pass 2: the fine word and the exact collision test of the candidates,
+        // so that the lanes of a warp do their rare second Philox calls together instead of one lane at a time.
+        constexpr int kMaxCand = 12;
+        int cand[kMaxCand], ncand = 0;
+        auto examine = [&](int t, uint32_t coarse) {
+            const uint64_t K = ((uint64_t)coarse << 44) | trial_fine44(p, S_trials, (uint32_t)t);
+            if (K < Kthr) return;
+            const double u = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+            if (!trial_collides(segs, nseg, -log(u))) return;
+            if (nlit < 4) lit_t[nlit] = t;
+            nlit++;
+            nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
+        };
+        // four Philox blocks (64 trials) per iteration: four independent dependency chains hide the latency of the
+        // ten multiply-xor rounds
+        auto scan = [&](int t16, const uint32_t (&o)[4]) {
 #pragma unroll
-            for (int h = 0; h < 8; h++) {
-                const int t = 8 * t8 + h;
-                if (t >= p.split1) break;
-                const uint32_t w = o[h >> 1];
-                const uint32_t coarse = (h & 1) ? (w >> 16) : (w & 0xFFFFu);
-                if (coarse < Cthr) continue;
-                const uint64_t K = ((uint64_t)coarse << 36) | trial_fine36(p, S_trials, (uint32_t)t);
-                if (K < Kthr) continue;
-                const double u = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
-                if (!trial_collides(segs, nseg, -log(u))) continue;
-                if (nlit < 4) lit_t[nlit] = t;
-                nlit++;
-                nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
+            for (int w = 0; w < 4; w++) {
+                uint32_t m = bytes_ge(o[w], Cthr);                // 0xFF in every byte that reaches Cthr
+                while (m) {
+                    const int b = (first_lane(m)) >> 3;
+                    m &= ~(0xFFu << (8 * b));
+                    const int t = 16 * t16 + 4 * w + b;
+                    if (t >= p.split1) continue;
+                    const uint32_t coarse = (o[w] >> (8 * b)) & 0xFFu;
+                    if (ncand < kMaxCand) cand[ncand++] = t | (int)(coarse << 24);
+                    else examine(t, coarse);                      // optically thick ray: no point in deferring
+                }
             }
+        };
+        const int n16 = (p.split1 + 15) >> 4;
+        int t16 = 0;
+        for (; t16 + 4 <= n16; t16 += 4) {
+            uint32_t o0[4], o1[4], o2[4], o3[4];
+            philox4x32_10x4(s_lo, s_hi, (uint32_t)t16, p.key0, p.key1, o0, o1, o2, o3);
+            const uint32_t any = bytes_ge(o0[0], Cthr) | bytes_ge(o0[1], Cthr) | bytes_ge(o0[2], Cthr) | bytes_ge(o0[3], Cthr) |
+                                 bytes_ge(o1[0], Cthr) | bytes_ge(o1[1], Cthr) | bytes_ge(o1[2], Cthr) | bytes_ge(o1[3], Cthr) |
+                                 bytes_ge(o2[0], Cthr) | bytes_ge(o2[1], Cthr) | bytes_ge(o2[2], Cthr) | bytes_ge(o2[3], Cthr) |
+                                 bytes_ge(o3[0], Cthr) | bytes_ge(o3[1], Cthr) | bytes_ge(o3[2], Cthr) | bytes_ge(o3[3], Cthr);
+            if (!any) continue;
+            scan(t16, o0); scan(t16 + 1, o1); scan(t16 + 2, o2); scan(t16 + 3, o3);
         }
+        for (; t16 < n16; t16++) {
+            uint32_t o[4];
+            philox4x32_10(s_lo, s_hi, (uint32_t)t16, 0u, p.key0, p.key1, o);
+            scan(t16, o);
+        }
+        for (int c = 0; c < ncand; c++) examine(cand[c] & 0xFFFFFF, (uint32_t)cand[c] >> 24);
     }
     // C': absorption-point draws of l.451-459 for the non-colliding trials of a ray with sigabs L > 1e-5 in some
     // crossing (they only move prdep): one uniform per (trial, absorbing crossing) from the trial's stream.  The
@@ -280,8 +322,11 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     }
 }
 
+#ifndef C2D_HIST_MINB
+#define C2D_HIST_MINB 1
+#endif
 template <int SRC>
-__global__ void __launch_bounds__(128) k_history(const Params p, long long first, long long n, long long stride)
+__global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const Params p, long long first, long long n, long long stride)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < n;
@@ -398,7 +443,7 @@ __device__ __forceinline__ bool split3_pass(const Params &p, const Split3Sub &u,
     if (!(4.0 * e.gamm * e.gamm * (1.0 + 1.e-9) > u.gain_min)) return false;
     P = u.task->p;
     P.ew = u.ewcsv / p.split3;
-    compb2d_finish(p, rng, P, e);
+    if (!compb2d_finish(p, rng, P, e, u.trigger)) return false;
     return P.ew > u.trigger;
 }
 // nth2d tallies of a committed pass.  `hist` is the block's shared-memory copy of nelectron (flushed once per block:
@@ -436,33 +481,46 @@ constexpr int kHistMax = 1024;
         if (s_hist[i_]) atomicAdd((p).nelectron + i_, (unsigned long long)s_hist[i_]);
 #endif
 
+constexpr int kHistWarp = 256;      // bins of the per-warp nelectron copy of k_split3_attempts
 __global__ void __launch_bounds__(128) k_split3_attempts(const Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
                                                          int max_rounds, unsigned *hard, unsigned long long *hard_count)
 {
-    C2D_HIST_BEGIN(p)
+    // every warp keeps its own shared-memory copy of nelectron and flushes it by itself: no block barrier, so a warp
+    // whose sub-child is accepted early retires without waiting for its neighbours
+#ifdef C2D_EMU
+    unsigned *hist = nullptr;
+#else
+    __shared__ unsigned s_hist[4][kHistWarp];
+    unsigned *hist = (p.num_nt + 2 <= kHistWarp) ? s_hist[threadIdx.x >> 5] : nullptr;
+    if (hist) for (int i = lane_id(); i < p.num_nt + 2; i += kWarp) hist[i] = 0u;
+    __syncwarp();
+#endif
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
-    if (w < n_sub) {                                              // whole warps together
-        const int lane = lane_id();
-        Split3Sub u;
-        split3_sub(p, q3_in, w, u);
-        Rng rng; Photon P; int i_gam = 0; ElRec rec;
-        uint64_t base = 0;
-        bool done = false;
-        for (int round = 0; max_rounds == 0 || round < max_rounds; round++, base += kWarp) {
-            const uint64_t attempt = base + (uint64_t)lane + 1;
-            const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
-            const unsigned m = warp_ballot(ok);
-            const int first = m ? first_lane(m) : kWarp;
-            if (lane <= first) split3_commit(p, u, attempt, rec, hist);
-            if (m) {
-                if (lane == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, base + (uint64_t)first + 1); }
-                done = true;
-                break;
-            }
+    if (w >= n_sub) return;                                       // whole warps together
+    const int lane = lane_id();
+    Split3Sub u;
+    split3_sub(p, q3_in, w, u);
+    Rng rng; Photon P; int i_gam = 0; ElRec rec;
+    uint64_t base = 0;
+    bool done = false;
+    for (int round = 0; max_rounds == 0 || round < max_rounds; round++, base += kWarp) {
+        const uint64_t attempt = base + (uint64_t)lane + 1;
+        const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
+        const unsigned m = warp_ballot(ok);
+        const int first = m ? first_lane(m) : kWarp;
+        if (lane <= first) split3_commit(p, u, attempt, rec, hist);
+        if (m) {
+            if (lane == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, base + (uint64_t)first + 1); }
+            done = true;
+            break;
         }
-        if (!done && lane == 0) { hard[atomicAdd(hard_count, 1ull)] = (unsigned)w; count(p, CNT_S3HARD); }
     }
-    C2D_HIST_END(p)
+    if (!done && lane == 0) { hard[atomicAdd(hard_count, 1ull)] = (unsigned)w; count(p, CNT_S3HARD); }
+#ifndef C2D_EMU
+    __syncwarp();
+    if (hist) for (int i = lane; i < p.num_nt + 2; i += kWarp)
+        if (hist[i]) atomicAdd(p.nelectron + i, (unsigned long long)hist[i]);
+#endif
 }
 
 #ifndef C2D_EMU

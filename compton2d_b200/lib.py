@@ -6,10 +6,11 @@ shared object is missing -- there is no Python/CPU fallback of any kernel.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 HERE = Path(__file__).resolve().parent
-LIBPATH = HERE / "libcompton2d_b200.so"
+LIBPATH = Path(os.environ.get("C2D_LIBPATH", HERE / "libcompton2d_b200.so"))   # override: kernel-tuning experiments
 
 NMUMAX = 32
 NLCMAX = 16

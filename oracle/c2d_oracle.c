@@ -200,19 +200,18 @@ double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d)
 
 /* Philox replay mode: the xi of trial flight t (0-based) of a history with trial stream S.  The 52-bit
  * integer K of u = (K + 0.5) 2^-52 is composed of two independent Philox outputs:
- *   coarse 16 bits = halfword (t & 7) of philox(ctr = (S_lo, S_hi, t >> 3, 0))   (8 trials per call)
- *   fine   36 bits = low 36 bits of words 0,1 of philox(ctr = (S_lo, S_hi, t, 1))
+ *   coarse  8 bits = byte (t & 15) of philox(ctr = (S_lo, S_hi, t >> 4, 0))          (16 trials per call)
+ *   fine   44 bits = word 0 and the low 12 bits of word 1 of philox(ctr = (S_lo, S_hi, t, 1))
  * so a consumer that only needs to know whether u exceeds a threshold close to 1 (the CUDA trial
- * filter) can decide almost every trial from the coarse halfword alone. */
+ * filter) can decide 255 of 256 trials from the coarse byte alone. */
 double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t)
 {
-    uint32_t c0[4] = {(uint32_t)S, (uint32_t)(S >> 32), t >> 3, 0u}, c1[4] = {(uint32_t)S, (uint32_t)(S >> 32), t, 1u}, o[4], f[4];
+    uint32_t c0[4] = {(uint32_t)S, (uint32_t)(S >> 32), t >> 4, 0u}, c1[4] = {(uint32_t)S, (uint32_t)(S >> 32), t, 1u}, o[4], f[4];
     orc_philox4x32(c0, key, o);
     orc_philox4x32(c1, key, f);
-    const uint32_t w = o[(t & 7u) >> 1];
-    const uint64_t coarse = (t & 1u) ? (w >> 16) : (w & 0xFFFFu);
-    const uint64_t fine = (((uint64_t)(f[1] & 0xFu)) << 32) | f[0];
-    const uint64_t K = (coarse << 36) | fine;
+    const uint64_t coarse = (o[(t & 15u) >> 2] >> (8u * (t & 3u))) & 0xFFu;
+    const uint64_t fine = (((uint64_t)(f[1] & 0xFFFu)) << 32) | f[0];
+    const uint64_t K = (coarse << 44) | fine;
     return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
 }
 
