@@ -265,7 +265,7 @@ int c2d_destroy(c2d_ctx *h)
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_f64); cudaFree(c->d_i64);
+    cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
@@ -454,7 +454,7 @@ int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
     c->cur_out ^= 1;
     c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
     c->P.ncycle = in->ncycle; c->P.key1 = (uint32_t)in->ncycle; c->P.dt = in->dt; c->P.time = in->time;
-    c->field_done = false; c->vol_next = 0;
+    c->field_done = false; c->vol_next = 0; c->surf_open = false; c->surf_total = 0;
     c->sigma_ready = false;
     CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its host arrays
     c->step_open = true;
@@ -493,6 +493,95 @@ int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
         const int64_t n = std::min(chunk, count - done);
         c->timer_begin(0);
         launch_history_volume(c->P, first + done * stride, n, stride, c->stream);
+        c->timer_end();
+        CU(cudaGetLastError());
+    }
+    c->histories += count;
+    return drain_queue(c);
+}
+
+int c2d_surf_begin(c2d_ctx *h, const c2d_surf_in *in)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !in) return fail(C2D_EINVAL, "NULL argument");
+    if (!c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
+    CU(cudaSetDevice(c->device));
+    const int nz = c->dims.nz, nr = c->dims.nr, nslot = 2 * nz + 2 * nr;
+    if (in->n_spec < 0 || in->nfmax < 0) return fail(C2D_EINVAL, "bad spectrum table sizes");
+    std::vector<int64_t> prefix(nslot + 1, 0);
+    std::vector<double> ew(nslot, 0.0), tbb(nslot, 0.0);
+    std::vector<int> spec(nslot, 0);
+    auto slot = [&](int q, const int32_t *n, const double *w, const double *t, const int32_t *sp, int ring) -> int {
+        const int cnt = n ? n[ring] : 0;
+        if (cnt < 0) return fail(C2D_EINVAL, "negative surface photon count (slot %d)", q);
+        prefix[q + 1] = cnt;
+        ew[q] = w ? w[ring] : 0.0; tbb[q] = t ? t[ring] : 0.0; spec[q] = sp ? sp[ring] : 0;
+        if (cnt > 0 && !(tbb[q] > 0.0)) {
+            if (spec[q] < 0 || spec[q] >= in->n_spec || !in->nfile || in->nfile[spec[q]] < 2 || in->nfile[spec[q]] > in->nfmax)
+                return fail(C2D_EINVAL, "surface slot %d samples spectrum table %d, which is missing or has < 2 rows "
+                            "(imcsurf2d_para.f:652-657 'Less than 2 lines of input read')", q, spec[q]);
+        }
+        return 0;
+    };
+    for (int j = 0; j < nz; j++) {
+        if (int rc = slot(2 * j, in->nsurfi, in->ewsurfi, in->tbbi, in->spec_i, j)) return rc;
+        if (int rc = slot(2 * j + 1, in->nsurfo, in->ewsurfo, in->tbbo, in->spec_o, j)) return rc;
+    }
+    for (int k = 0; k < nr; k++) {
+        if (int rc = slot(2 * nz + 2 * k, in->nsurfu, in->ewsurfu, in->tbbu, in->spec_u, k)) return rc;
+        if (int rc = slot(2 * nz + 2 * k + 1, in->nsurfl, in->ewsurfl, in->tbbl, in->spec_l, k)) return rc;
+    }
+    for (int q = 0; q < nslot; q++) prefix[q + 1] += prefix[q];
+    c->surf_total = prefix[nslot];
+    // tbbl(k,ti) is one COMMON array in the reference: the lower-face leak test of imcleak (imcleak2d.f:95) reads the
+    // same values the source uses, so a tbbl given here replaces the one of c2d_step_begin
+    if (in->tbbl) { if (int rc = upload(c, c->d_step + c->o_tbbl, in->tbbl, nr)) return rc; }
+    // one blob: prefix | ew | tbb | E F P a1 I | spec | nfile
+    const size_t nt = (size_t)in->n_spec * in->nfmax;
+    const size_t bytes = (size_t)(nslot + 1) * 8 + (size_t)nslot * 16 + nt * 40 + (size_t)nslot * 4 + (size_t)std::max(in->n_spec, 1) * 4 + 64;
+    if (bytes > c->surf_bytes) {
+        cudaFree(c->d_surf);
+        CU(cudaMalloc(&c->d_surf, bytes));
+        c->surf_bytes = bytes;
+    }
+    std::vector<char> hb(bytes, 0);
+    char *base = hb.data();
+    size_t off = 0;
+    auto put = [&](const void *src, size_t n) { size_t o = off; if (src && n) memcpy(base + off, src, n); off += (n + 7) & ~size_t(7); return o; };
+    const size_t o_pre = put(prefix.data(), (size_t)(nslot + 1) * 8), o_ew = put(ew.data(), (size_t)nslot * 8), o_tbb = put(tbb.data(), (size_t)nslot * 8);
+    const size_t o_E = put(in->E_file, nt * 8), o_F = put(in->F_file, nt * 8), o_P = put(in->P_file, nt * 8), o_a = put(in->a1, nt * 8), o_I = put(in->I_file, nt * 8);
+    const size_t o_sp = put(spec.data(), (size_t)nslot * 4), o_nf = put(in->nfile, (size_t)in->n_spec * 4);
+    CU(cudaMemcpyAsync(c->d_surf, base, off, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    char *D = static_cast<char *>(c->d_surf);
+    Params &P = c->P;
+    P.surf_prefix = reinterpret_cast<const int64_t *>(D + o_pre);
+    P.ewsurf = reinterpret_cast<const double *>(D + o_ew); P.tbb_surf = reinterpret_cast<const double *>(D + o_tbb);
+    P.sp_E = reinterpret_cast<const double *>(D + o_E); P.sp_F = reinterpret_cast<const double *>(D + o_F);
+    P.sp_P = reinterpret_cast<const double *>(D + o_P); P.sp_a1 = reinterpret_cast<const double *>(D + o_a);
+    P.sp_I = reinterpret_cast<const double *>(D + o_I);
+    P.spec_surf = reinterpret_cast<const int *>(D + o_sp); P.sp_n = reinterpret_cast<const int *>(D + o_nf);
+    P.sp_nfmax = in->nfmax; P.star_switch = in->star_switch;
+    c->surf_open = true;
+    return 0;
+}
+
+int c2d_imcsurf(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
+    if (!c->surf_open) return fail(C2D_ESTATE, "c2d_surf_begin has not been called in this step");
+    CU(cudaSetDevice(c->device));
+    if (stride < 1 || first < 0) return fail(C2D_EINVAL, "bad shard first=%lld stride=%lld", (long long)first, (long long)stride);
+    const int64_t total = c->surf_total;
+    int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
+    if (count < 0 || count > avail) count = avail;
+    if (int rc = c->sigma_ensure()) return rc;
+    const int64_t chunk = (int64_t)1 << 30;
+    for (int64_t done = 0; done < count; done += chunk) {
+        const int64_t n = std::min(chunk, count - done);
+        c->timer_begin(0);
+        launch_history_surface(c->P, first + done * stride, n, stride, c->stream);
         c->timer_end();
         CU(cudaGetLastError());
     }

@@ -22,6 +22,10 @@ struct Ctx {
     // device memory
     double *d_static = nullptr, *d_step = nullptr, *d_f64 = nullptr, *d_events = nullptr;
     int64_t *d_prefix = nullptr;
+    void *d_surf = nullptr;                // surface-source blob of the current step
+    size_t surf_bytes = 0;
+    int64_t surf_total = 0;
+    bool surf_open = false;
     unsigned long long *d_i64 = nullptr, *d_qcount = nullptr;
     CollTask *d_q[2] = {nullptr, nullptr}, *d_q3 = nullptr;
     FlightTask *d_flights = nullptr;       // accepted 3rd-split sub-children of one chunk of split3 tasks

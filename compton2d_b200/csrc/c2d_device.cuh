@@ -31,6 +31,7 @@ constexpr int kNlcMax = 16;
 constexpr uint64_t kTagTrials = 0xA1ull;
 constexpr uint64_t kTagF0 = 0xF0ull;
 constexpr uint64_t kTagVol = 0x766F6Cull;
+constexpr uint64_t kTagSurf = 0x73726600ull;     // + boundary kind (0 inner, 1 outer, 2 upper, 3 lower)
 
 enum { MODE_PRE = 2, MODE_TRIAL = -1, MODE_TRIAL_SLOW = -2, MODE_F0 = 0, MODE_CHILD = 1 };
 enum { END_KILLED = 0, END_CENSUS = 1, END_LEAK = 2, END_DROPPED = 3, END_COLLISION = 4, END_LOWEW = 5,
@@ -81,6 +82,13 @@ struct Params {
     const double *kappa_tot, *eps_tot, *eps_th, *f_nt, *Pnt, *n_e, *f_pair, *k_gg, *tbbl;
     const double *ewsv, *Eloss_th, *Eloss_tot, *zsurf;
     const int64_t *nsv_prefix;         // [nzone+1]
+    // surface sources (c2d_surf_begin): slots in the order (inner, outer) of z ring 1..nz, then (upper, lower) of r ring 1..nr
+    const int64_t *surf_prefix;        // [2 nz + 2 nr + 1]
+    const double *ewsurf, *tbb_surf;   // [2 nz + 2 nr]
+    const int *spec_surf;              // [2 nz + 2 nr] external-spectrum table of the slot (used when tbb <= 0)
+    const double *sp_E, *sp_F, *sp_P, *sp_a1, *sp_I;   // [n_spec][sp_nfmax] file_sp tables (imcsurf2d_para.f:544-685)
+    const int *sp_n;                   // [n_spec] nfile
+    int sp_nfmax, star_switch;
     // sigma_mode 1 (c2d_sigma.cu): per-step piecewise-Chebyshev representation of comtot(zone, E)
     const double *sig_coef;            // [nzone][sig_nint][8] coefficients of the exact-branch sum on each interval
     const double *sig_AB;              // [nzone][num_nt][2] prefix sums of the Thomson-branch bins
@@ -463,41 +471,20 @@ __device__ __forceinline__ double kn_noise_bin(const Params &p, int i, double x)
     return p.kn_pref[i] * (((ya < 0.1) ? kn_eta(ya) : 0.0) - kn_eta(p.kn_a2[i] * x));
 }
 
-// Noise sums  sum_{i >= m} noise_i(x) W[z][i]  for up to four zones, bins walked by ONE thread ...
+// Noise sums  sum_{i >= m} noise_i(x) W[z][i]  for up to four zones
 __device__ __forceinline__ void sig_noise_zones(const Params &p, double x, int m, const int *zi, int nzn, double (&ee)[4])
 {
     const int N = p.num_nt;
     const double *w0 = p.sig_W + (size_t)zi[0] * N, *w1 = p.sig_W + (size_t)zi[nzn > 1 ? 1 : 0] * N;
     const double *w2 = p.sig_W + (size_t)zi[nzn > 2 ? 2 : 0] * N, *w3 = p.sig_W + (size_t)zi[nzn > 3 ? 3 : 0] * N;
     double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+#pragma unroll 4
     for (int i = m; i < N - 1; i++) {
         const double q = kn_noise_bin(p, i, x);
         e0 = fma(q, w0[i], e0); e1 = fma(q, w1[i], e1); e2 = fma(q, w2[i], e2); e3 = fma(q, w3[i], e3);
     }
     ee[0] = e0; ee[1] = e1; ee[2] = e2; ee[3] = e3;
 }
-// ... or by the whole warp for one photon energy: bins strided over the lanes, so the W rows are read coalesced
-// (a thread-per-photon walk touches 32 different rows per load).  Every lane must call; all lanes get the sums.
-__device__ __forceinline__ void sig_noise_zones_warp(const Params &p, double x, int m, int z0, int z1, int z2, int z3, int nzn,
-                                                     double (&ee)[4])
-{
-    const int N = p.num_nt;
-    const double *w0 = p.sig_W + (size_t)z0 * N, *w1 = p.sig_W + (size_t)z1 * N;
-    const double *w2 = p.sig_W + (size_t)z2 * N, *w3 = p.sig_W + (size_t)z3 * N;
-    double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-    for (int i = m + lane_id(); i < N - 1; i += kWarp) {
-        const double q = kn_noise_bin(p, i, x);
-        e0 = fma(q, w0[i], e0);
-        if (nzn > 1) e1 = fma(q, w1[i], e1);
-        if (nzn > 2) e2 = fma(q, w2[i], e2);
-        if (nzn > 3) e3 = fma(q, w3[i], e3);
-    }
-    ee[0] = warp_sum(e0);
-    ee[1] = (nzn > 1) ? warp_sum(e1) : 0.0;
-    ee[2] = (nzn > 2) ? warp_sum(e2) : 0.0;
-    ee[3] = (nzn > 3) ? warp_sum(e3) : 0.0;
-}
-
 // Table value for up to four zones of one photon energy, given the noise sums `ee` (zero when c.j < 0)
 __device__ __forceinline__ void comtot_table_finish(const Params &p, const SigCtx &c, const int *zi, int nzn, const double (&ee)[4],
                                                     double *comac)
@@ -1010,6 +997,116 @@ __device__ __forceinline__ void source_volume(const Params &p, Rng &rng, int zon
     P.jgpsp = sp_group(p, P.xnu, C2D_F4(1.000001), C2D_F4(.999999), p.nphtotal);
     P.jgplc = lc_group(p, P.xnu);
     P.jgpmu = mu_group(p, P.wmu);
+}
+
+#define C2D_CLAMP10(v) do { if ((v) > 0.9999999999e0) (v) = 0.9999999999e0; if ((v) < -0.9999999999e0) (v) = -0.9999999999e0; } while (0)
+
+// planck2d.f:1-141 (REAL*4 literals at l.72-73); P.wmu must be set
+__device__ __forceinline__ void planck(const Params &p, Rng &rng, double tpl, Photon &P)
+{
+    double u4;
+    do {
+        u4 = rng.next(p);
+        u4 = u4 * rng.next(p);
+        u4 = u4 * rng.next(p);
+        u4 = u4 * rng.next(p);
+    } while (u4 <= 1.e-200);
+    const double ap0 = -log(u4);
+    double ap1 = 1.0, ap2 = 1.0, ap3 = 1.0;
+    const double rn1 = 1.08232e0 * rng.next(p);
+    while (!(rn1 <= ap1)) {
+        ap2 = ap2 + 1.0;
+        ap3 = 1.0 / ap2;
+        ap1 = ap1 + (ap3 * ap3) * (ap3 * ap3);
+    }
+    P.xnu = ap0 * ap3 * tpl;
+    P.jgpsp = sp_group(p, P.xnu, C2D_F4(1.000001), C2D_F4(.999999), 0);
+    P.jgplc = lc_group(p, P.xnu);
+    P.jgpmu = mu_group(p, P.wmu);
+}
+
+// imcsurf2d_para.f:694-788; P.wmu must be set.  The CDF scan is a bisection (P_file is non-decreasing): first
+// i in [1, nfile-1] with P_file(i) > x1, else nfile.
+__device__ __forceinline__ void file_sample(const Params &p, Rng &rng, int spec, Photon &P)
+{
+    const size_t o = (size_t)spec * p.sp_nfmax;
+    const int nfile = p.sp_n[spec];
+    const double x1 = rng.next(p);
+    int lo = 1, hi = nfile;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (p.sp_P[o + mid - 1] > x1) hi = mid; else lo = mid + 1;
+    }
+    const int i = lo;
+    const double x2 = rng.next(p);
+    const double E = p.sp_E[o + i - 1], A = p.sp_a1[o + i - 1];
+    P.xnu = E * pow(A * p.sp_I[o + i - 1] * x2 / (p.sp_F[o + i - 1] * E) + 1.0, 1. / A);
+    P.jgpsp = sp_group(p, P.xnu, 1.000001e0, .999999e0, 0);
+    P.jgplc = lc_group(p, P.xnu);
+    P.jgpmu = mu_group(p, P.wmu);
+}
+
+// imcsurf2d_para.f:228-534: photon of surface slot `slot` (see Params::surf_prefix)
+__device__ __forceinline__ void source_surface(const Params &p, Rng &rng, int slot, Photon &P)
+{
+    const double tbb = p.tbb_surf[slot];
+    const int spec = p.spec_surf[slot];
+    P.ew = p.ewsurf[slot];
+    if (slot < 2 * p.nz) {                          // z_surf_calc(js)
+        const int js = (slot >> 1) + 1;
+        const double zlo = (js == 1) ? 0.0 : p.z[js - 2], zhi = p.z[js - 1];
+        P.jph = js;
+        P.wmu = 2.0 * rng.next(p) - 1.0;
+        C2D_CLAMP10(P.wmu);
+        if ((slot & 1) == 0) {                      // inner cylinder, l.255-289
+            P.phi = -1.1e1 / 7.0 + 2.2e1 / 7.0 * rng.next(p);
+            if (P.phi < -1.5707963e0) P.phi = -1.57079063e0;
+            if (P.phi > 1.5707963e0) P.phi = 1.5707963e0;
+            P.rpre = p.rmin;
+            if (js == 1) P.zpre = p.z[0] * rng.next(p);
+            else P.zpre = zlo + rng.next(p) * (zhi - zlo);
+            P.kph = 1;
+        } else {                                    // outer cylinder, l.296-337
+            P.rpre = p.r[p.nr - 1];
+            if (js == 1) P.zpre = p.z[0] * rng.next(p);
+            else P.zpre = zlo + rng.next(p) * (zhi - zlo);
+            const double x1 = rng.next(p), x2 = rng.next(p);
+            if (x1 < 0.5) {
+                P.phi = 1.1e1 / 7.0 + (1.1e1 / 7.0) * x2;
+                if (P.phi < 1.57079638e0) P.phi = 1.57079638e0;
+            } else {
+                P.phi = -1.1e1 / 7.0 - (1.1e1 / 7.0) * x2;
+                if (P.phi > -1.57079638e0) P.phi = -1.57079638e0;
+            }
+            P.kph = p.nr;
+        }
+        P.dcen = rng.next(p) * kCLight * p.dt;
+        if (tbb > 0.0) planck(p, rng, tbb, P); else file_sample(p, rng, spec, P);
+        return;
+    }
+    const int q = slot - 2 * p.nz, ks = (q >> 1) + 1;   // r_surf_calc(ks)
+    const double rlo = (ks == 1) ? p.rmin : p.r[ks - 2], rhi = p.r[ks - 1];
+    P.kph = ks;
+    if ((q & 1) == 0) {                             // upper disk, l.376-404
+        P.wmu = -rng.next(p);
+        C2D_CLAMP10(P.wmu);
+        P.phi = 2.0 * kPi * rng.next(p);
+        const double psi = rng.next(p);
+        P.zpre = p.z[p.nz - 1];
+        P.rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+        P.dcen = rng.next(p) * kCLight * p.dt;
+        if (tbb > 0.0) planck(p, rng, tbb, P); else file_sample(p, rng, spec, P);
+        P.jph = p.nz;
+    } else {                                        // lower disk, beamed upwards, l.444-490
+        P.wmu = 9.9999999e-1;
+        P.phi = 2.0 * kPi * rng.next(p);
+        const double psi = rng.next(p);
+        P.zpre = p.zmin;
+        P.rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+        if (tbb > 0.e-20) planck(p, rng, tbb, P); else file_sample(p, rng, spec, P);
+        P.dcen = rng.next(p) * kCLight * p.dt;      // drawn after the energy on this face (l.484)
+        P.jph = 1;
+    }
 }
 
 }  // namespace c2d

@@ -96,34 +96,24 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     const bool fast = active && !overflow;
     // B: sigma_sc per crossing (comac_ar cache of l.175-183: one comtot per zone and history)
     if (p.sigma_mode == 1) {
-        SigCtx sc; sc.j = -2; sc.m = 0; sc.x = 1.0; sc.s = 0.0;
-        if (fast) sig_begin(p, T0.xnu, sc);
-        unsigned have = fast ? 0u : 0xffffffffu;
-        for (;;) {
-            int zl[4] = {0, 0, 0, 0}, nzn = 0;
-            for (int s = 0; s < nseg && nzn < 4; s++) {
-                if (have & (1u << s)) continue;
-                bool seen = false;
-                for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
-                if (!seen) zl[nzn++] = segs[s].zi;
-            }
-            if (!warp_ballot(nzn > 0)) break;
-            // the noise sums of the exact-branch bins, the warp serving one lane's photon at a time
-            double ee[4] = {0.0, 0.0, 0.0, 0.0};
-            unsigned todo = warp_ballot(nzn > 0 && sc.j >= 0);
-            while (todo) {
-                const int src = first_lane(todo);
-                todo &= todo - 1;
-                const double xs = warp_shfl(sc.x, src);
-                const int ms = warp_shfl(sc.m, src), an = warp_shfl(nzn, src);
-                const int a0 = warp_shfl(zl[0], src), a1 = warp_shfl(zl[1], src), a2 = warp_shfl(zl[2], src), a3 = warp_shfl(zl[3], src);
-                double r[4];
-                sig_noise_zones_warp(p, xs, ms, a0, a1, a2, a3, an, r);
-                if (lane_id() == src) { ee[0] = r[0]; ee[1] = r[1]; ee[2] = r[2]; ee[3] = r[3]; }
-            }
-            if (nzn > 0) {
+        // table look-up per thread.  (Serving one lane's photon at a time with the bins spread over the warp, as the
+        // bin-by-bin mode below does, was measured 1.7x slower here: the noise term is too cheap to pay for the
+        // broadcasts and butterfly sums.)
+        if (fast) {
+            SigCtx sc;
+            sig_begin(p, T0.xnu, sc);
+            unsigned have = 0u;
+            for (;;) {
+                int zl[4] = {0, 0, 0, 0}, nzn = 0;
+                for (int s = 0; s < nseg && nzn < 4; s++) {
+                    if (have & (1u << s)) continue;
+                    bool seen = false;
+                    for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
+                    if (!seen) zl[nzn++] = segs[s].zi;
+                }
+                if (nzn == 0) break;
                 double cm[4];
-                if (sc.j != -2) comtot_table_finish(p, sc, zl, nzn, ee, cm);
+                if (sc.j != -2) comtot_table_zones(p, sc, zl, nzn, cm);
                 else comtot_zones(p, T0.xnu, zl, nzn, cm);             // beyond the table: bin by bin
                 for (int s = 0; s < nseg; s++) {
                     if (have & (1u << s)) continue;
@@ -346,6 +336,20 @@ __global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const Params p, 
         S_entry = mix64(mix64(kTagVol, (uint64_t)zone), (uint64_t)ivol);
         Rng rng; rng.stream(S_entry);
         source_volume(p, rng, zone, P0);
+    } else if (SRC == 2) {
+        const long long h = first + idx * stride;
+        const int nslot = 2 * p.nz + 2 * p.nr;
+        int lo = 0, hi = nslot;              // invariant: prefix[lo] <= h < prefix[hi]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (p.surf_prefix[mid] <= h) lo = mid; else hi = mid;
+        }
+        const long long nxs = h - p.surf_prefix[lo] + 1;
+        const int kind = (lo < 2 * p.nz) ? (lo & 1) : 2 + ((lo - 2 * p.nz) & 1);
+        const int ring = (lo < 2 * p.nz) ? (lo >> 1) + 1 : ((lo - 2 * p.nz) >> 1) + 1;
+        S_entry = mix64(mix64(kTagSurf + (uint64_t)kind, (uint64_t)ring), (uint64_t)nxs);
+        Rng rng; rng.stream(S_entry);
+        source_surface(p, rng, lo, P0);
     } else {
         const long long h = first + idx * stride;
         P0.rpre = p.in.rpre[h]; P0.zpre = p.in.zpre[h]; P0.wmu = p.in.wmu[h]; P0.phi = p.in.phi[h];
@@ -571,6 +575,13 @@ void launch_history_volume(const Params &p, long long first, long long n, long l
     const int threads = 128;
     const long long blocks = (n + threads - 1) / threads;
     k_history<0><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
+}
+void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
+{
+    if (n <= 0) return;
+    const int threads = 128;
+    const long long blocks = (n + threads - 1) / threads;
+    k_history<2><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
 }
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
 {

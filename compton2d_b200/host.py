@@ -116,9 +116,45 @@ class Compton2d:
         """== sum over zones of vol_calc (imcvol2d_para.f:90-414); this rank's share of the histories."""
         _l.check(self.L.c2d_imcvol(self.h, self.rank, -1, self.world))
 
-    def imcsurf2d(self):
-        """Surface sources (imcsurf2d_para.f); the shipped inputs have none (tbb = -0.d0)."""
-        return None
+    def imcsurf2d(self, *, nsurfu=None, nsurfl=None, nsurfi=None, nsurfo=None, ewsurfu=None, ewsurfl=None, ewsurfi=None,
+                  ewsurfo=None, tbbu=None, tbbl=None, tbbi=None, tbbo=None, spectra=(), spec_u=None, spec_l=None,
+                  spec_i=None, spec_o=None, star_switch=0):
+        """== imcsurf2d: sum over boundary rings of z_surf_calc + r_surf_calc (imcsurf2d_para.f:228-534); this rank's share
+        of the histories.  Arguments are the COMMON members the reference's master sends with the ring jobs
+        (surf_mpi.f:18-98,136,337): photon counts and weights per ring, the boundary temperatures of the current time
+        interval (tbb > 0: Planck spectrum; otherwise the ring samples spectrum table spec_*[ring] of `spectra`, a list of
+        dicts from compton2d_b200.spectrum.file_sp).  Without sources (the shipped input: tbb = -0.d0) it does nothing."""
+        def iv(a, n):
+            return np.zeros(n, np.int32) if a is None else np.ascontiguousarray(a, dtype=np.int32).ravel()
+
+        def dv(a, n):
+            return np.zeros(n) if a is None else _d(a, n)
+        nz, nr = self.nz, self.nr
+        cnt = dict(nsurfi=iv(nsurfi, nz), nsurfo=iv(nsurfo, nz), nsurfu=iv(nsurfu, nr), nsurfl=iv(nsurfl, nr))
+        self.n_surface = int(sum(int(v.sum()) for v in cnt.values()))
+        if self.n_surface == 0:
+            return None
+        dbl = dict(ewsurfi=dv(ewsurfi, nz), ewsurfo=dv(ewsurfo, nz), ewsurfu=dv(ewsurfu, nr), ewsurfl=dv(ewsurfl, nr),
+                   tbbi=dv(tbbi, nz), tbbo=dv(tbbo, nz), tbbu=dv(tbbu, nr), tbbl=dv(tbbl, nr))
+        sp = dict(spec_i=iv(spec_i, nz), spec_o=iv(spec_o, nz), spec_u=iv(spec_u, nr), spec_l=iv(spec_l, nr))
+        nfmax = max([len(t["E_file"]) for t in spectra], default=0)
+        tab = {k: np.zeros((max(len(spectra), 1), max(nfmax, 1))) for k in ("E_file", "F_file", "P_file", "a1", "I_file")}
+        nfile = np.zeros(max(len(spectra), 1), np.int32)
+        for q, t in enumerate(spectra):
+            for k in tab:
+                tab[k][q, : len(t[k])] = t[k]
+            nfile[q] = t["nfile"]
+        si = _l.SurfIn(star_switch=int(star_switch), n_spec=len(spectra), nfmax=nfmax)
+        for k, v in {**cnt, **sp}.items():
+            setattr(si, k, v.ctypes.data_as(_l.ip))
+        for k, v in {**dbl, **tab}.items():
+            setattr(si, k, _p(np.ascontiguousarray(v).ravel()))
+        keep = [np.ascontiguousarray(v).ravel() for v in tab.values()]          # pointers above must outlive the call
+        for k, v in zip(tab, keep):
+            setattr(si, k, _p(v))
+        si.nfile = nfile.ctypes.data_as(_l.ip)
+        _l.check(self.L.c2d_surf_begin(self.h, C.byref(si)))
+        _l.check(self.L.c2d_imcsurf(self.h, self.rank, -1, self.world))
 
     def imcredist(self):
         """Census rebalancing through the master (imcredist.f) is not needed: histories are sharded

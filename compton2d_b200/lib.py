@@ -34,6 +34,13 @@ class StepIn(C.Structure):
         [("nsv", ip)] + [(n, dp) for n in ("ewsv", "Eloss_th", "Eloss_tot", "zsurf", "tbbl")]
 
 
+class SurfIn(C.Structure):
+    _fields_ = [("star_switch", C.c_int)] + [(n, ip) for n in ("nsurfi", "nsurfo", "nsurfu", "nsurfl")] + \
+        [(n, dp) for n in ("ewsurfi", "ewsurfo", "ewsurfu", "ewsurfl", "tbbi", "tbbo", "tbbu", "tbbl")] + \
+        [(n, ip) for n in ("spec_i", "spec_o", "spec_u", "spec_l")] + [("n_spec", C.c_int), ("nfmax", C.c_int), ("nfile", ip)] + \
+        [(n, dp) for n in ("E_file", "F_file", "P_file", "a1", "I_file")]
+
+
 class Tallies(C.Structure):
     _fields_ = [("edep", dp), ("prdep", dp), ("ecens", dp), ("npcen", lp), ("n_field", dp), ("n_ph", dp),
                 ("E_IC", dp), ("nelectron", lp), ("fout", dp), ("edout", dp), ("erlki", dp), ("erlko", dp),
@@ -65,7 +72,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
-           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot"]
+           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf"]
 
 _lib = None
 
@@ -94,6 +101,8 @@ def load():
     L.c2d_imcfield.argtypes = [vp]
     L.c2d_imcvol.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.c2d_sync.argtypes = [vp]
+    L.c2d_surf_begin.argtypes = [vp, C.POINTER(SurfIn)]
+    L.c2d_imcsurf.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.c2d_tally_read.argtypes = [vp, C.POINTER(Tallies)]
     L.c2d_tally_device.argtypes = [vp, C.POINTER(vp), lp, C.POINTER(vp), lp]
     L.c2d_census_count.argtypes = [vp, lp]

@@ -86,6 +86,24 @@ typedef struct {
     const double *tbbl;               /* [nr] lower-boundary temperature of the current time interval tbbl(k,ti) */
 } c2d_step_in;
 
+/* Surface sources of one step (optional; BASELINE configs[2]): what r_surf_bcast / z_surf_bcast and the ring job
+ * messages carry (surf_mpi.f:18-98,136,337) plus the tables file_sp builds from an external spectrum file
+ * (imcsurf2d_para.f:544-685; parsing and normalisation stay on the host, compton2d_b200.spectrum.file_sp).
+ * A boundary ring emits nsurf* photons of weight ewsurf*; its energies are Planckian at tbb* when tbb* > 0
+ * (planck2d.f) and drawn from spectrum table spec_* otherwise (file_sample, imcsurf2d_para.f:694-788). */
+typedef struct {
+    int star_switch;                  /* reader.f; both settings beam the lower source (imcsurf2d_para.f:452-460) */
+    const int32_t *nsurfi, *nsurfo;   /* [nz] inner / outer cylinder */
+    const int32_t *nsurfu, *nsurfl;   /* [nr] upper / lower disk */
+    const double *ewsurfi, *ewsurfo, *ewsurfu, *ewsurfl;
+    const double *tbbi, *tbbo;        /* [nz] tbbi(j,ti), tbbo(j,ti) */
+    const double *tbbu, *tbbl;        /* [nr] tbbu(k,ti), tbbl(k,ti); tbbl also replaces c2d_step_in.tbbl (same COMMON array) */
+    const int32_t *spec_i, *spec_o, *spec_u, *spec_l;   /* spectrum-table index per ring (may be NULL = table 0) */
+    int n_spec, nfmax;                /* tables, entries per table (general.pa:17 nfmax = 500) */
+    const int32_t *nfile;             /* [n_spec] */
+    const double *E_file, *F_file, *P_file, *a1, *I_file;   /* [n_spec][nfmax] COMMON /insp/ */
+} c2d_surf_in;
+
 /* All tallies of one step, dense.  Filled by c2d_tally_read. */
 typedef struct {
     double *edep, *prdep, *ecens;     /* [zone] */
@@ -138,6 +156,9 @@ int c2d_imcvol(c2d_ctx *ctx, int64_t first, int64_t count, int64_t stride);
         /* == sum over zones of vol_calc (imcvol2d_para.f:90-414); this context tracks the volume
            histories with global index first, first+stride, ... (count of them; count<0 = all that remain),
            which is how histories shard over GPUs */
+int c2d_surf_begin(c2d_ctx *ctx, const c2d_surf_in *in);   /* after c2d_step_begin, when the step has surface sources */
+int c2d_imcsurf(c2d_ctx *ctx, int64_t first, int64_t count, int64_t stride);
+        /* == imcsurf2d: sum over rings of z_surf_calc + r_surf_calc (imcsurf2d_para.f:228-534); sharded like c2d_imcvol */
 int c2d_sync(c2d_ctx *ctx);                                /* drains the scattering queue, waits for the device */
 int c2d_tally_read(c2d_ctx *ctx, c2d_tallies *out);        /* D2H copy of this context's (or the reduced) tallies */
 int c2d_tally_device(c2d_ctx *ctx, double **fp64_buf, int64_t *n_fp64, int64_t **i64_buf, int64_t *n_i64);

@@ -83,7 +83,7 @@ void *orc_array(orc_state *s, const char *name, int64_t *count, int *elem_size)
 #define ORC_SCALARS_I(X) \
     X(pair_switch) X(cr_sent) X(spec_switch) X(rand_switch) X(ncycle) X(split1) X(split2) X(split3) \
     X(spl3_trg) X(inj_switch) X(inj_dis) X(g2var_switch) X(pick_sw) X(cf_sentinel) X(fp_dead_terms) \
-    X(nph_lc) X(nmu) X(nphtotal) X(fatal) X(idead)
+    X(nph_lc) X(nmu) X(nphtotal) X(fatal) X(idead) X(star_switch)
 #define ORC_SCALARS_L(X) \
     X(incounter) X(outcounter) X(cmcount1) X(cmcount2) X(lkcount) X(n_multiple) X(n_killed) \
     X(n_segments) X(n_trials) X(n_comtot) X(ndxout) X(ndxin) X(nev)
@@ -890,6 +890,197 @@ void orc_vol_calc(orc_state *s, int zone)
         s->jgpmu = mu_group(s, s->wmu);
         orc_imctrk2d(s, -1);
     }
+}
+
+/* ------------------------------------------------------------------ surface sources */
+/* planck2d.f:1-141: Planck-spectrum sampler + binning (REAL*4 literals 1.000001, .999999 at l.72-73) */
+void orc_planck(orc_state *s, double tpl)
+{
+    double u4, ap0, ap1, ap2, ap3, rn1;
+    do {
+        u4 = orc_fibran(s);
+        u4 = u4 * orc_fibran(s);
+        u4 = u4 * orc_fibran(s);
+        u4 = u4 * orc_fibran(s);
+    } while (u4 <= 1.e-200);
+    ap0 = -log(u4);
+    ap1 = 1.0; ap2 = 1.0; ap3 = 1.0;
+    rn1 = 1.08232e0 * orc_fibran(s);
+    while (!(rn1 <= ap1)) {
+        ap2 = ap2 + 1.0;
+        ap3 = 1.0 / ap2;
+        ap1 = ap1 + (ap3 * ap3) * (ap3 * ap3);       /* ap3**4: ifort expands to two squarings */
+    }
+    s->xnu = ap0 * ap3 * tpl;
+    s->jgpsp = sp_group(s, s->xnu, F4(1.000001), F4(.999999), 0);
+    s->jgplc = lc_group(s, s->xnu);
+    s->jgpmu = mu_group(s, s->wmu);
+}
+
+/* imcsurf2d_para.f:694-788: energy from the piecewise power-law CDF of an external spectrum */
+void orc_file_sample(orc_state *s, int spec)
+{
+    const double *E = s->E_file + (size_t)spec * ORC_NFMAX, *F = s->F_file + (size_t)spec * ORC_NFMAX;
+    const double *P = s->P_file + (size_t)spec * ORC_NFMAX, *A = s->a1_file + (size_t)spec * ORC_NFMAX;
+    const double *I = s->I_file + (size_t)spec * ORC_NFMAX;
+    const int nfile = s->nfile[spec];
+    int i;
+    double x1 = orc_fibran(s), x2;
+    for (i = 1; i <= nfile - 1; i++)
+        if (P[i - 1] > x1) break;                    /* DO variable is nfile after a completed loop */
+    x2 = orc_fibran(s);
+    s->xnu = E[i - 1] * pow(A[i - 1] * I[i - 1] * x2 / (F[i - 1] * E[i - 1]) + 1.0, 1. / A[i - 1]);
+    s->jgpsp = sp_group(s, s->xnu, 1.000001e0, .999999e0, 0);
+    s->jgplc = lc_group(s, s->xnu);
+    s->jgpmu = mu_group(s, s->wmu);
+}
+
+#define CLAMP10(v) do { if ((v) > 0.9999999999e0) (v) = 0.9999999999e0; if ((v) < -0.9999999999e0) (v) = -0.9999999999e0; } while (0)
+
+/* imcsurf2d_para.f:228-343: inner (r = rmin) and outer (r = r(nr)) cylinder sources of z-ring js.
+ * Philox mode: photon nxs of boundary kind b (0 inner, 1 outer, 2 upper, 3 lower) of ring q owns the stream
+ * mix64(mix64('srf' + b, q), nxs). */
+void orc_z_surf_calc(orc_state *s, int js)
+{
+    int nxs;
+    double x1, x2;
+    for (nxs = 1; nxs <= s->nsurfi[js - 1] && !s->fatal; nxs++) {
+        if (s->rng.mode == 3) rng_stream(s, orc_mix64(orc_mix64(0x73726600ull, (uint64_t)js), (uint64_t)nxs));
+        s->jph = js;
+        s->wmu = 2.0 * orc_fibran(s) - 1.0;
+        CLAMP10(s->wmu);
+        s->phi = -1.1e1 / 7.0 + 2.2e1 / 7.0 * orc_fibran(s);
+        if (s->phi < -1.5707963e0) s->phi = -1.57079063e0;
+        if (s->phi > 1.5707963e0) s->phi = 1.5707963e0;
+        s->rpre = s->rmin;
+        if (js == 1) s->zpre = ZZ(1) * orc_fibran(s);
+        else s->zpre = ZZ(js - 1) + orc_fibran(s) * (ZZ(js) - ZZ(js - 1));
+        s->ew = s->ewsurfi[js - 1];
+        s->dcen = orc_fibran(s) * C_LIGHT * s->dt;
+        if (s->tbbi[js - 1] > 0.0) orc_planck(s, s->tbbi[js - 1]);
+        else orc_file_sample(s, s->spec_i[js - 1]);
+        s->kph = 1;
+        orc_imctrk2d(s, -1);
+    }
+    for (nxs = 1; nxs <= s->nsurfo[js - 1] && !s->fatal; nxs++) {
+        if (s->rng.mode == 3) rng_stream(s, orc_mix64(orc_mix64(0x73726601ull, (uint64_t)js), (uint64_t)nxs));
+        s->jph = js;
+        s->wmu = 2.0 * orc_fibran(s) - 1.0;
+        CLAMP10(s->wmu);
+        s->rpre = RR(s->nr);
+        if (js == 1) s->zpre = ZZ(1) * orc_fibran(s);
+        else s->zpre = ZZ(js - 1) + orc_fibran(s) * (ZZ(js) - ZZ(js - 1));
+        x1 = orc_fibran(s);
+        x2 = orc_fibran(s);
+        if (x1 < 0.5) {
+            s->phi = 1.1e1 / 7.0 + (1.1e1 / 7.0) * x2;
+            if (s->phi < 1.57079638e0) s->phi = 1.57079638e0;
+        } else {
+            s->phi = -1.1e1 / 7.0 - (1.1e1 / 7.0) * x2;
+            if (s->phi > -1.57079638e0) s->phi = -1.57079638e0;
+        }
+        s->ew = s->ewsurfo[js - 1];
+        s->dcen = orc_fibran(s) * C_LIGHT * s->dt;
+        if (s->tbbo[js - 1] > 0.0) orc_planck(s, s->tbbo[js - 1]);
+        else orc_file_sample(s, s->spec_o[js - 1]);
+        s->kph = s->nr;
+        orc_imctrk2d(s, -1);
+    }
+}
+
+/* imcsurf2d_para.f:353-534: upper (z = z(nz)) and lower (z = zmin, beamed: wmu = 0.99999999) disk sources of r-ring ks */
+void orc_r_surf_calc(orc_state *s, int ks)
+{
+    int nxs;
+    double psi;
+    const double rlo = (ks == 1) ? s->rmin : RR(ks - 1), rhi = RR(ks);
+    for (nxs = 1; nxs <= s->nsurfu[ks - 1] && !s->fatal; nxs++) {
+        if (s->rng.mode == 3) rng_stream(s, orc_mix64(orc_mix64(0x73726602ull, (uint64_t)ks), (uint64_t)nxs));
+        s->kph = ks;
+        s->wmu = -orc_fibran(s);
+        CLAMP10(s->wmu);
+        s->phi = 2.0 * PI * orc_fibran(s);
+        psi = orc_fibran(s);
+        s->zpre = ZZ(s->nz);
+        s->rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+        s->ew = s->ewsurfu[ks - 1];
+        s->dcen = orc_fibran(s) * C_LIGHT * s->dt;
+        if (s->tbbu[ks - 1] > 0.0) orc_planck(s, s->tbbu[ks - 1]);
+        else orc_file_sample(s, s->spec_u[ks - 1]);
+        s->jph = s->nz;
+        orc_imctrk2d(s, -1);
+    }
+    for (nxs = 1; nxs <= s->nsurfl[ks - 1] && !s->fatal; nxs++) {
+        if (s->rng.mode == 3) rng_stream(s, orc_mix64(orc_mix64(0x73726603ull, (uint64_t)ks), (uint64_t)nxs));
+        s->kph = ks;
+        s->wmu = 9.9999999e-1;                        /* l.452-460: star or not, the lower source is beamed upwards */
+        s->phi = 2.0 * PI * orc_fibran(s);
+        psi = orc_fibran(s);
+        s->zpre = s->zmin;
+        s->rpre = sqrt((rlo * rlo) + psi * (rhi * rhi - rlo * rlo));
+        s->ew = s->ewsurfl[ks - 1];
+        if (s->tbbl[ks - 1] > 0.e-20) orc_planck(s, s->tbbl[ks - 1]);
+        else orc_file_sample(s, s->spec_l[ks - 1]);
+        s->dcen = orc_fibran(s) * C_LIGHT * s->dt;      /* drawn after the energy here (l.484) */
+        s->jph = 1;
+        orc_imctrk2d(s, -1);
+    }
+}
+
+/* imcsurf2d_para.f:544-685 file_sp: external spectrum (rows E, L_disk, F_blr, F_ir) -> normalised BLR + torus flux
+ * (Ghisellini & Madau 1996) and its piecewise power-law CDF.  Returns nfile (< 0: error).  The disk part
+ * (Id_file, F_como) is computed by the reference but not used (l.648-649: F_file = F_blr + F_ir). */
+int orc_file_sp(int n_rows, const double *E_in, const double *L_disk, const double *F_blr_in, const double *F_ir_in,
+                double g_bulk, double R_blr, double fr_blr, double R_ir, double fr_ir, double R_disk, double d_jet,
+                double *E_file, double *F_file, double *P_file, double *a1, double *I_file, double *int_file)
+{
+    double Ld[ORC_NFMAX], Fb[ORC_NFMAX], Fi[ORC_NFMAX];
+    int i, nfile;
+    double Ltot_disk = 0., Ftot_blr = 0., Ftot_ir = 0., Isum = 0.;
+    (void)R_disk; (void)d_jet;
+    for (i = 0; i < ORC_NFMAX; i++) { E_file[i] = 0; Ld[i] = 0; Fb[i] = 0; Fi[i] = 0; F_file[i] = 0; P_file[i] = 0; a1[i] = 0; I_file[i] = 0; }
+    /* the read loop stops after row nfmax-1 or at the first E <= 0 (l.567-594); end of file is an err= exit */
+    i = 0;
+    for (;;) {
+        i = i + 1;
+        if (i > n_rows) break;                         /* err=120 */
+        E_file[i - 1] = E_in[i - 1]; Ld[i - 1] = L_disk[i - 1]; Fb[i - 1] = F_blr_in[i - 1]; Fi[i - 1] = F_ir_in[i - 1];
+        if (!(E_file[i - 1] > 0. && i <= ORC_NFMAX - 1)) break;
+    }
+    nfile = i - 1;
+    for (i = 1; i <= ORC_NFMAX - 1; i++) {
+        Ltot_disk = Ltot_disk + Ld[i - 1] * (E_file[i] - E_file[i - 1]);
+        Ftot_blr = Ftot_blr + Fb[i - 1] * (E_file[i] - E_file[i - 1]);
+        Ftot_ir = Ftot_ir + Fi[i - 1] * (E_file[i] - E_file[i - 1]);
+    }
+    Ltot_disk = Ltot_disk / sqrt(E_file[1] / E_file[0]);
+    Ftot_blr = Ftot_blr / sqrt(E_file[1] / E_file[0]);
+    Ftot_ir = Ftot_ir / sqrt(E_file[1] / E_file[0]);
+    {
+        const double Ftot_blr_norm = 17. / 48. / PI * (g_bulk * g_bulk) * fr_blr * Ltot_disk / (R_blr * R_blr);
+        const double Ftot_ir_norm = 1. / 4. / PI * (g_bulk * g_bulk) * fr_ir * Ltot_disk / (R_ir * R_ir);
+        for (i = 0; i < ORC_NFMAX; i++) {
+            Fb[i] = Fb[i] / Ftot_blr * Ftot_blr_norm;
+            Fi[i] = Fi[i] / Ftot_ir * Ftot_ir_norm;
+            F_file[i] = Fb[i] + Fi[i];
+        }
+    }
+    if (nfile < 2) return -1;
+    for (i = 1; i <= nfile - 1; i++) {
+        const double alpha = log(F_file[i] / F_file[i - 1]) / log(E_file[i] / E_file[i - 1]);
+        a1[i - 1] = alpha + 1.;
+        if (a1[i - 1] > 2.e1) a1[i - 1] = 2.e1;
+        if (a1[i - 1] < -2.e1) a1[i - 1] = -2.e1;
+        if (fabs(a1[i - 1]) < 1.e-3)
+            I_file[i - 1] = F_file[i - 1] * E_file[i - 1] * log(E_file[i] / E_file[i - 1]);
+        else
+            I_file[i - 1] = F_file[i - 1] * E_file[i - 1] * (pow(E_file[i] / E_file[i - 1], a1[i - 1]) - 1.) / a1[i - 1];
+        Isum = Isum + I_file[i - 1];
+        P_file[i - 1] = Isum;
+    }
+    for (i = 1; i <= nfile - 1; i++) P_file[i - 1] = P_file[i - 1] / Isum;
+    *int_file = Isum;
+    return nfile;
 }
 
 /* imcfield2d.f:57-148.  Philox mode: a census photon's history stream is the id of

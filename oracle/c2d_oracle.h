@@ -44,6 +44,8 @@ typedef struct {
     uint64_t ndraw;           /* statistics */
 } orc_rng;
 
+#define ORC_NSPEC 4        /* external-spectrum tables held at once (file_sp results, imcsurf2d_para.f:544-685) */
+#define ORC_NFMAX 500      /* general.pa:17 nfmax */
 #define ORC_NMUMAX 32
 #define ORC_NLCMAX 16
 
@@ -57,7 +59,13 @@ typedef struct {
     X(Pnt, double, nzone * num_nt) X(n_e, double, nzone) X(tea, double, nzone) \
     X(hu, double, nphtotal + 1) X(Elcmin, double, ORC_NLCMAX) X(Elcmax, double, ORC_NLCMAX) \
     X(mu, double, ORC_NMUMAX) \
-    X(tbbl, double, nr) X(tbbu, double, nr) \
+    X(tbbl, double, nr) X(tbbu, double, nr) X(tbbi, double, nz) X(tbbo, double, nz) \
+    X(nsurfi, int, nz) X(nsurfo, int, nz) X(nsurfu, int, nr) X(nsurfl, int, nr) \
+    X(ewsurfi, double, nz) X(ewsurfo, double, nz) X(ewsurfu, double, nr) X(ewsurfl, double, nr) \
+    X(spec_i, int, nz) X(spec_o, int, nz) X(spec_u, int, nr) X(spec_l, int, nr) \
+    X(nfile, int, ORC_NSPEC) X(E_file, double, ORC_NSPEC * ORC_NFMAX) X(F_file, double, ORC_NSPEC * ORC_NFMAX) \
+    X(P_file, double, ORC_NSPEC * ORC_NFMAX) X(a1_file, double, ORC_NSPEC * ORC_NFMAX) \
+    X(I_file, double, ORC_NSPEC * ORC_NFMAX) \
     X(nsv, int, nzone) X(ewsv, double, nzone) X(Eloss_th, double, nzone) X(Eloss_tot, double, nzone) \
     X(zsurf, double, nzone) \
     X(edep, double, nzone) X(prdep, double, nzone) X(ecens, double, nzone) X(npcen, int64_t, nzone) \
@@ -79,7 +87,7 @@ typedef struct orc_state {
     /* dims */
     int nz, nr, nzone, n_vol, num_nt, nphfield, n_gg, nphtotal, nph_lc, nmu;
     /* switches / scalars (commonblock.f) */
-    int pair_switch, cr_sent, spec_switch, rand_switch, ncycle;
+    int pair_switch, cr_sent, spec_switch, rand_switch, ncycle, star_switch;
     int split1, split2, split3, spl3_trg;
     int inj_switch, inj_dis, g2var_switch, pick_sw, cf_sentinel;
     int fp_dead_terms;        /* 1 = also evaluate the numerically dead rate terms (log parity only) */
@@ -130,6 +138,16 @@ uint64_t orc_mix64(uint64_t a, uint64_t b);
 double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d);
 double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t);
 double orc_fibran(orc_state *s);
+
+/* surface sources (imcsurf2d_para.f) */
+void orc_planck(orc_state *s, double tpl);                             /* planck2d.f:1-141 */
+void orc_file_sample(orc_state *s, int spec);                          /* imcsurf2d_para.f:694-788 */
+void orc_z_surf_calc(orc_state *s, int js);                            /* imcsurf2d_para.f:228-343 */
+void orc_r_surf_calc(orc_state *s, int ks);                            /* imcsurf2d_para.f:353-534 */
+int orc_file_sp(int n_rows, const double *E_in, const double *L_disk, const double *F_blr_in, const double *F_ir_in,
+                double g_bulk, double R_blr, double fr_blr, double R_ir, double fr_ir, double R_disk, double d_jet,
+                double *E_file, double *F_file, double *P_file, double *a1, double *I_file, double *int_file);
+                                                                       /* imcsurf2d_para.f:544-685 */
 
 /* leaves */
 double orc_dilog(double x);                                            /* comtot2d.f:356-433 */

@@ -55,6 +55,10 @@ def lib():
         L.orc_comtot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_vol_calc.argtypes = [C.c_void_p, C.c_int]
         L.orc_field_calc.argtypes = [C.c_void_p]
+        L.orc_z_surf_calc.argtypes = [C.c_void_p, C.c_int]
+        L.orc_r_surf_calc.argtypes = [C.c_void_p, C.c_int]
+        L.orc_file_sp.restype = C.c_int
+        L.orc_file_sp.argtypes = [C.c_int] + [C.c_void_p] * 4 + [C.c_double] * 7 + [C.c_void_p] * 6
         L.orc_step_zero_worker.argtypes = [C.c_void_p]
         L.orc_imctrk2d.argtypes = [C.c_void_p, C.c_int]
         L.orc_IC_loss.argtypes = [C.c_void_p]
@@ -131,6 +135,21 @@ class Oracle:
         for zone in range(1, self.dims["nzone"] + 1):
             self.vol_calc(zone)
 
+    def surf_all(self):
+        """imcsurf2d (imcsurf2d_para.f:1-225): all z rings, then all r rings."""
+        for js in range(1, self.dims["nz"] + 1):
+            self.L.orc_z_surf_calc(self.p, js)
+        for ks in range(1, self.dims["nr"] + 1):
+            self.L.orc_r_surf_calc(self.p, ks)
+
+    def set_spectrum(self, slot, E_file, F_file, P_file, a1, I_file, nfile):
+        a = self.a
+        for name, v in (("E_file", E_file), ("F_file", F_file), ("P_file", P_file), ("a1_file", a1), ("I_file", I_file)):
+            arr = getattr(a, name)
+            arr[slot * 500: slot * 500 + 500] = 0.0
+            arr[slot * 500: slot * 500 + len(v)] = v
+        a.nfile[slot] = int(nfile)
+
     def fp_calc(self, zone):
         self.L.orc_fp_calc(self.p, int(zone))
 
@@ -165,3 +184,13 @@ class _Arrays:
         a = getattr(self, name)
         v = np.asarray(val).ravel()
         a[: v.size] = v
+
+
+def file_sp(rows, g_bulk, R_blr, fr_blr, R_ir, fr_ir, R_disk, d_jet):
+    """orc_file_sp on an [n,>=4] table (E, L_disk, F_blr, F_ir) -> dict(E_file, F_file, P_file, a1, I_file, int_file, nfile)."""
+    rows = np.ascontiguousarray(np.asarray(rows, float)[:, :4].T)
+    out = [np.zeros(500) for _ in range(5)]
+    integ = C.c_double()
+    n = lib().orc_file_sp(rows.shape[1], rows[0].ctypes.data, rows[1].ctypes.data, rows[2].ctypes.data, rows[3].ctypes.data,
+                          g_bulk, R_blr, fr_blr, R_ir, fr_ir, R_disk, d_jet, *[o.ctypes.data for o in out], C.byref(integ))
+    return dict(E_file=out[0], F_file=out[1], P_file=out[2], a1=out[3], I_file=out[4], int_file=integ.value, nfile=n)

@@ -43,6 +43,12 @@ CONFIGS = {
     # rmin > 0 (inner boundary absorbs), nmu = 1, different seed
     "annulus": dict(over=dict(nz=3, nr=4, nst=5000, tstop="1.e+3", rmin="0.2d16", rseed=4242),
                     zone={}),
+    # external-Compton seed photons (BASELINE configs[2]): upper and lower disk sources sampled from a spectrum
+    # file (the only live surface-source path of the reference: nsurf* > 0 requires tbb* < 0, imcgen2d.f:441-442)
+    "surface": dict(over=dict(nz=3, nr=4, nst=1200, tstop="1.e+3", **{"t0(1)": "0.d0", "t1(1)": "1.d20"}), zone={},
+                    wi=dict(tbbl="-1.d0", l_fname="blackbody_G15_4spectra.in", tbbu="-1.d0",
+                            u_fname="blackbody_G15_4spectra.in"),
+                    files=["/root/reference/disk/blackbody_G15_4spectra.in"]),
 }
 
 # (name, dims-to-keep as function of (nz, nr, nmu)) -- None = scalar / full
@@ -74,7 +80,12 @@ def varlist(nz, nr):
         ("n_ph", (100, nz, nr)), ("k_gg", (100, nz, nr)), ("e_gg", (100,)),
         ("mu", (32,)), ("ed_abs", (nr,)), ("ed_ref", (nr,)), ("ed_in", (nr,)),
         ("hu", (129,)), ("elcmin", (10,)), ("elcmax", (10,)),
-        ("tbbu", (nr, 1)), ("tbbl", (nr, 1)),
+        ("tbbu", (nr, 1)), ("tbbl", (nr, 1)), ("tbbi", (nz, 1)), ("tbbo", (nz, 1)),
+        ("nsurfu", (nr,)), ("nsurfl", (nr,)), ("nsurfi", (nz,)), ("nsurfo", (nz,)),
+        ("ewsurfu", (nr,)), ("ewsurfl", (nr,)), ("ewsurfi", (nz,)), ("ewsurfo", (nz,)), ("star_switch", None),
+        ("nfile", None), ("e_file", (500,)), ("p_file", (500,)), ("a1", (500,)), ("i_file", (500,)), ("f_file", (500,)),
+        ("int_file", None), ("r_blr", None), ("fr_blr", None), ("r_ir", None), ("fr_ir", None), ("r_disk", None),
+        ("d_jet", None),
         ("inj_g1", None), ("inj_g2", None), ("inj_p", None), ("inj_t", None), ("inj_gg", None),
         ("inj_sigma", None), ("inj_l", None), ("inj_v", None), ("g_bulk", None), ("pick_rate", None),
         ("r_esc", None), ("r_acc", None), ("f_ic", (200, 400)),
@@ -133,7 +144,9 @@ def main(name):
     rd = Path("/tmp") / f"c2d_gold_{name}"
     shutil.rmtree(rd, ignore_errors=True)
     rd.mkdir()
-    vals = refrun.write_inputs(rd, cfg["over"], cfg["zone"])
+    vals = refrun.write_inputs(rd, cfg["over"], cfg["zone"], **cfg.get("wi", {}))
+    for f in cfg.get("files", []):
+        shutil.copy(f, rd / Path(f).name)
     nz, nr = int(vals["nz"]), int(vals["nr"])
     r = refrun.run(rd)
     assert r.returncode == 0, (rd / "stdout.txt").read_text()[-2000:]

@@ -83,7 +83,7 @@ def _key(label: str) -> str:
 
 def write_inputs(rundir: Path, overrides: dict | None = None, zone: dict | None = None,
                  zone_fn=None, staged: Path | None = None,
-                 tbbl=None, l_fname: str | None = None) -> dict:
+                 tbbl=None, l_fname: str | None = None, tbbu=None, u_fname: str | None = None) -> dict:
     """Lay out `rundir` (input/ output/ temp/ rates/) from the shipped templates.
 
     overrides: {key: value-string} for input.dat, key = the token left of '=' in the
@@ -92,6 +92,7 @@ def write_inputs(rundir: Path, overrides: dict | None = None, zone: dict | None 
                ep_switch B_field amxwl gmin gmax p_nth q_turb(j,k) turb_lev(j,k)).
     zone_fn:   optional callable (j, k) -> dict of per-zone overrides.
     tbbl/l_fname: lower-boundary temperature (string) + spectrum file for every k.
+    tbbu/u_fname: the same for the upper boundary.
     Returns the effective scalar settings as strings.
     """
     staged = staged or stage_reference() or REFDIR
@@ -120,6 +121,10 @@ def write_inputs(rundir: Path, overrides: dict | None = None, zone: dict | None 
     nr = int(vals["nr"]); nz = int(vals["nz"])
     for k in range(1, nr + 1):
         (l0, v0), (l1, v1), (l2, v2), (l3, v3) = grp
+        if tbbu is not None:
+            v0 = str(tbbu)
+        if u_fname is not None:
+            v1 = u_fname
         if tbbl is not None:
             v2 = str(tbbl)
         if l_fname is not None:

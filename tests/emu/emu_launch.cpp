@@ -16,6 +16,7 @@ template <int SRC> static void run_hist(const Params &p, long long first, long l
         }
 }
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<0>(p, first, n, stride); }
+void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<2>(p, first, n, stride); }
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<1>(p, first, n, stride); }
 template <class F> static void run_grid(long long n, F body)
 {

@@ -55,7 +55,24 @@ def make_oracle(P, rseed=9857, cens_cap=400000, ev_cap=400000):
     return o
 
 
-def oracle_step(o, P, ncycle, time=None, field=True, vol=True):
+SURF_KEYS = ("nsurfu", "nsurfl", "nsurfi", "nsurfo", "ewsurfu", "ewsurfl", "ewsurfi", "ewsurfo", "tbbu", "tbbl", "tbbi", "tbbo")
+
+
+def oracle_surface(o, S):
+    """Load the surface-source description S (dict, see make_surface) into the oracle and run imcsurf2d."""
+    a = o.a
+    for k in SURF_KEYS:
+        if S.get(k) is not None:
+            setattr(a, k, S[k])
+    o["star_switch"] = int(S.get("star_switch", 0))
+    for q, t in enumerate(S.get("spectra", ())):
+        o.set_spectrum(q, t["E_file"], t["F_file"], t["P_file"], t["a1"], t["I_file"], t["nfile"])
+    for k in ("spec_u", "spec_l", "spec_i", "spec_o"):
+        getattr(a, k)[:] = 0 if S.get(k) is None else S[k]
+    o.surf_all()
+
+
+def oracle_step(o, P, ncycle, time=None, field=True, vol=True, surf=None):
     a = o.a
     for k in ("kappa_tot", "eps_tot", "eps_th", "k_gg", "f_nt", "Pnt", "n_e", "tea", "f_pair", "nsv", "ewsv",
               "Eloss_th", "Eloss_tot", "zsurf", "tbbl"):
@@ -71,6 +88,8 @@ def oracle_step(o, P, ncycle, time=None, field=True, vol=True):
         o["ndxout"] = 0
     if vol:
         o.vol_all()
+    if surf is not None:
+        oracle_surface(o, surf)
     assert int(o["fatal"]) == 0, f"oracle fatal {int(o['fatal'])}"
     nz, nr, nzone = P["nz"], P["nr"], P["nzone"]
     npt = P["hu"].size - 1
@@ -97,7 +116,7 @@ def make_gpu(P, rseed=9857, sigma_mode=0, census_capacity=400000, event_capacity
                      collision_capacity=collision_capacity, sigma_mode=sigma_mode, device=device, rank=rank, world=world)
 
 
-def gpu_step(g, P, ncycle, time=None, field=True, vol=True):
+def gpu_step(g, P, ncycle, time=None, field=True, vol=True, surf=None):
     g.imcgen2d(ncycle=ncycle, time=P["time"] if time is None else time, dt=P["dt"], kappa_tot=P["kappa_tot"],
                eps_tot=P["eps_tot"], eps_th=P["eps_th"], f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"],
                f_pair=P["f_pair"], k_gg=P["k_gg"], nsv=P["nsv"], ewsv=P["ewsv"], Eloss_th=P["Eloss_th"],
@@ -106,6 +125,8 @@ def gpu_step(g, P, ncycle, time=None, field=True, vol=True):
         g.imcfield2d()
     if vol:
         g.imcvol2d()
+    if surf is not None:
+        g.imcsurf2d(**surf)
     g.sync()
     t = g.tallies()
     t["census"] = g.census()

@@ -116,3 +116,25 @@ def test_sharded_equals_whole():
         assert np.abs(s - whole[k]).max() <= 1e-11 * np.abs(whole[k]).max()
     sid = np.sort(np.concatenate([parts[0]["census"][2], parts[1]["census"][2]]))
     assert np.array_equal(sid, np.sort(whole["census"][2]))
+
+
+@pytest.mark.parametrize("kind,sigma_mode", [("file", 0), ("file", 1), ("planck", 1)])
+def test_replay_parity_surface_sources(kind, sigma_mode):
+    """imcsurf2d (imcsurf2d_para.f:228-534): BASELINE configs[2] -- upper and lower disk rings sampling the reference's
+    disk/blackbody_G15_4spectra.in through file_sp / file_sample (lower disk beamed at wmu = 0.99999999) -- and Planckian
+    boundaries on all four faces (planck2d.f).  The oracle's restatement of this phase is pinned to the reference binary
+    in tests/test_oracle_vs_refbin.py::test_surface_sources_match_reference_binary."""
+    from synth import make_surface
+    P = make_problem(nz=16, nr=16, nst=3000, ngroups=100, split=(100, 50, 10, 10), n_e=3.0e5,
+                     rmin=0.1e16 if kind == "planck" else 0.0)
+    S = make_surface(P, 6000, kind)
+    o, g = make_oracle(P), make_gpu(P, sigma_mode=sigma_mode)
+    try:
+        for cyc in (1, 2):
+            ro = oracle_step(o, P, cyc, field=cyc > 1, surf=S)
+            rg = gpu_step(g, P, cyc, field=cyc > 1, surf=S)
+            bad = compare(rg, ro, tol=1e-10, census_tol=1e-5)
+            assert not bad, (cyc, bad)
+        assert rg["counters"]["histories"] > 5000
+    finally:
+        g.close()

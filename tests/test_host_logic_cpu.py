@@ -56,6 +56,23 @@ def test_multiple_scattering_and_third_split(emu):
     g.close()
 
 
+@pytest.mark.parametrize("kind", ["file", "planck"])
+def test_surface_sources(emu, kind):
+    """imcsurf2d: disk sources sampled from an external spectrum (BASELINE configs[2]) and Planckian boundaries."""
+    from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step
+    from synth import make_problem, make_surface
+    P = make_problem(nz=4, nr=3, nst=800, ngroups=64, split=(20, 10, 4, 10), n_e=3.0e6, rmin=0.1e16 if kind == "planck" else 0.0)
+    S = make_surface(P, 1500, kind)
+    o, g = make_oracle(P), make_gpu(P)
+    for cyc in (1, 2):
+        ro = oracle_step(o, P, cyc, field=cyc > 1, surf=S)
+        rg = gpu_step(g, P, cyc, field=cyc > 1, surf=S)
+        bad = compare(rg, ro, tol=1e-10, census_tol=1e-6)
+        assert not bad, (cyc, bad)
+    assert rg["counters"]["histories"] > int(P["nsv"].sum()) + 1400
+    g.close()
+
+
 def test_census_export_import_roundtrip(emu):
     """write_record / read_record contract (census2d.f): export -> import into a fresh context -> same step."""
     from parity_util import gpu_step, make_gpu

@@ -135,3 +135,67 @@ def test_ic_loss_matches_reference_binary():
     o.L.orc_IC_loss(o.p)
     fic = o.a.F_IC[: 200 * 400].reshape(200, 400)
     assert np.abs(fic / F.f_ic - 1).max() < 1e-8      # f_Li series stops at |term/sum| < 1e-10
+
+
+# ------------------------------------------------------------------------------------------ surface sources
+def _load_surface_inputs(o, s1):
+    """What z_surf_bcast / r_surf_send_job deliver after snapshot C was taken (surf_mpi.f:18-98,337) plus the
+    file_sp tables the worker builds per ring (imcsurf2d_para.f:441-442)."""
+    a = o.a
+    for v in ("nsurfu", "nsurfl", "nsurfi", "nsurfo", "ewsurfu", "ewsurfl", "ewsurfi", "ewsurfo"):
+        setattr(a, v, s1[v])
+    a.tbbu = s1.tbbu[:, 0]; a.tbbl = s1.tbbl[:, 0]; a.tbbi = s1.tbbi[:, 0]; a.tbbo = s1.tbbo[:, 0]
+    o["star_switch"] = int(s1.star_switch)
+    o.set_spectrum(0, s1.e_file, s1.f_file, s1.p_file, s1.a1, s1.i_file, int(s1.nfile))
+    a.spec_u[:] = 0; a.spec_l[:] = 0; a.spec_i[:] = 0; a.spec_o[:] = 0
+    # tables that reach the worker with z_surf_bcast (SURVEY.md 3.6): the current kappa_tot, dt, hu ...
+    a.kappa_tot = np.transpose(s1.kappa_tot, (1, 2, 0))
+    o["dt"] = float(s1.dt[0])
+
+
+@pytest.mark.parametrize("cyc", [1, 2])
+def test_surface_sources_match_reference_binary(cyc):
+    """imcsurf2d (upper + lower disk, file_sample spectrum; BASELINE configs[2]) between snapshots C and D."""
+    g = Golden("surface")
+    s0, s1 = g.snap(f"c{cyc}_C"), g.snap(f"c{cyc}_D")
+    assert int(s1.ndxout) - int(s0.ndxout) > 1000
+    o = new_oracle(s0)
+    load_snapshot(o, s0)
+    _load_surface_inputs(o, s1)
+    o.surf_all()
+    bad = compare_tracking(o, s1)
+    assert not bad, bad
+
+
+def test_file_sp_matches_reference_binary():
+    """file_sp (imcsurf2d_para.f:544-685): the spectrum tables the binary built from disk/blackbody_G15_4spectra.in.
+    The input rows are stored in the golden (tests/golden/spectrum_G15.npy) so the test does not need /root/reference."""
+    from pathlib import Path
+    g = Golden("surface")
+    s1 = g.snap("c1_D")
+    rows = np.load(Path(__file__).resolve().parent / "golden" / "spectrum_G15.npy")
+    import orc
+    t = orc.file_sp(rows, float(s1.g_bulk), float(s1.r_blr), float(s1.fr_blr), float(s1.r_ir), float(s1.fr_ir),
+                    float(s1.r_disk), float(s1.d_jet))
+    assert t["nfile"] == int(s1.nfile)
+    n = t["nfile"]
+    assert np.array_equal(t["E_file"][:n], s1.e_file[:n])
+    for k, ref in (("F_file", s1.f_file), ("P_file", s1.p_file), ("a1", s1.a1), ("I_file", s1.i_file)):
+        r = np.abs(t[k][: n - 1] - ref[: n - 1]) / np.maximum(np.abs(ref[: n - 1]), 1e-300)
+        assert r.max() < 1e-11, (k, r.max())
+    assert abs(t["int_file"] / float(s1.int_file) - 1.0) < 1e-12
+
+
+def test_host_file_sp_matches_reference_binary():
+    """compton2d_b200.spectrum.file_sp (the product's host-side parser) against the binary's tables."""
+    from pathlib import Path
+    from compton2d_b200.spectrum import file_sp
+    s1 = Golden("surface").snap("c1_D")
+    rows = np.load(Path(__file__).resolve().parent / "golden" / "spectrum_G15.npy")
+    t = file_sp(rows, g_bulk=float(s1.g_bulk), R_blr=float(s1.r_blr), fr_blr=float(s1.fr_blr), R_ir=float(s1.r_ir),
+                fr_ir=float(s1.fr_ir))
+    n = t["nfile"]
+    assert n == int(s1.nfile) and np.array_equal(t["E_file"][:n], s1.e_file[:n])
+    for k, ref in (("F_file", s1.f_file), ("P_file", s1.p_file), ("a1", s1.a1), ("I_file", s1.i_file)):
+        r = np.abs(t[k][: n - 1] - ref[: n - 1]) / np.maximum(np.abs(ref[: n - 1]), 1e-300)
+        assert r.max() < 1e-11, (k, r.max())
