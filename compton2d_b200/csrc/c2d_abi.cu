@@ -306,7 +306,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     };
     const size_t o_z = put(d->z, d->nz), o_r = put(d->r, d->nr), o_Eph = put(d->E_ph, d->n_vol);
     const size_t o_Ef = put(d->E_field, d->nphfield), o_Egg = put(d->E_gg, d->n_gg), o_gnt = put(d->gnt, d->num_nt);
-    std::vector<double> gam0(d->num_nt), opb(d->num_nt), dgam(d->num_nt, 0.0), pref(d->num_nt), a1(d->num_nt), a2(d->num_nt);
+    std::vector<double> gam0(d->num_nt), opb(d->num_nt), dgam(d->num_nt, 0.0), pref(d->num_nt), a1(d->num_nt), a2(d->num_nt), cb(d->num_nt);
     for (int i = 0; i < d->num_nt; i++) {
         // comtot2d.f:223-238, the bin-only factors in the reference's own left-to-right order
         const double sigthom = 6.6516e-25;
@@ -320,10 +320,11 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
         volatile double u = 2 * gam0[i];
         a1[i] = u * (1 + betta);
         a2[i] = u * (1 - betta);
+        cb[i] = 8.0 * pref[i] / a2[i];                         // sigma_mode 1 noise term, see kn_noise_bin
         if (i + 1 < d->num_nt) dgam[i] = d->gnt[i + 1] - d->gnt[i];
     }
     const size_t o_g0 = put(gam0.data(), d->num_nt), o_be = put(opb.data(), d->num_nt), o_dg = put(dgam.data(), d->num_nt);
-    const size_t o_pref = put(pref.data(), d->num_nt), o_a1 = put(a1.data(), d->num_nt), o_a2 = put(a2.data(), d->num_nt);
+    const size_t o_pref = put(pref.data(), d->num_nt), o_a1 = put(a1.data(), d->num_nt), o_a2 = put(a2.data(), d->num_nt), o_cb = put(cb.data(), d->num_nt);
     const size_t o_hu = put(d->hu, d->nphtotal + 1);
     const size_t o_lmin = put(d->Elcmin, d->nph_lc), o_lmax = put(d->Elcmax, d->nph_lc), o_mu = put(d->mu, d->nmu);
     CU(cudaMalloc(&c->d_static, hs.size() * 8));
@@ -380,7 +381,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     P.key0 = d->rseed; P.rmin = d->rmin; P.zmin = d->zmin;
     const double *S = c->d_static;
     P.z = S + o_z; P.r = S + o_r; P.E_ph = S + o_Eph; P.E_field = S + o_Ef; P.E_gg = S + o_Egg; P.gnt = S + o_gnt;
-    P.gam0 = S + o_g0; P.opb = S + o_be; P.dgam = S + o_dg; P.kn_pref = S + o_pref; P.kn_a1 = S + o_a1; P.kn_a2 = S + o_a2; P.hu = S + o_hu; P.Elcmin = S + o_lmin; P.Elcmax = S + o_lmax;
+    P.gam0 = S + o_g0; P.opb = S + o_be; P.dgam = S + o_dg; P.kn_pref = S + o_pref; P.kn_a1 = S + o_a1; P.kn_a2 = S + o_a2; P.kn_cb = S + o_cb; P.hu = S + o_hu; P.Elcmin = S + o_lmin; P.Elcmax = S + o_lmax;
     P.mu = S + o_mu;
     const double *T = c->d_step;
     P.kappa_tot = T + c->o_kappa; P.eps_tot = T + c->o_epstot; P.eps_th = T + c->o_epsth; P.f_nt = T + c->o_fnt;

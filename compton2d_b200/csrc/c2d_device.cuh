@@ -77,7 +77,7 @@ struct Params {
     uint32_t key0, key1;
     double rmin, zmin, dt, time;
     // static tables
-    const double *z, *r, *E_ph, *E_field, *E_gg, *gnt, *gam0, *opb, *dgam, *kn_pref, *kn_a1, *kn_a2, *hu, *Elcmin, *Elcmax, *mu;
+    const double *z, *r, *E_ph, *E_field, *E_gg, *gnt, *gam0, *opb, *dgam, *kn_pref, *kn_a1, *kn_a2, *kn_cb, *hu, *Elcmin, *Elcmax, *mu;
     // per-step tables
     const double *kappa_tot, *eps_tot, *eps_th, *f_nt, *Pnt, *n_e, *f_pair, *k_gg, *tbbl;
     const double *ewsv, *Eloss_th, *Eloss_tot, *zsurf;
@@ -164,26 +164,6 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
 
-// four blocks with counters (c0, c1, c2 + j, 0), j = 0..3, advanced round by round together
-__device__ __forceinline__ void philox4x32_10x4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t k0, uint32_t k1,
-                                                uint32_t (&o0)[4], uint32_t (&o1)[4], uint32_t (&o2)[4], uint32_t (&o3)[4])
-{
-    uint32_t a[4] = {c0, c0, c0, c0}, b[4] = {c1, c1, c1, c1}, c[4] = {c2, c2 + 1u, c2 + 2u, c2 + 3u}, d[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint64_t p0 = (uint64_t)0xD2511F53u * a[j], p1 = (uint64_t)0xCD9E8D57u * c[j];
-            a[j] = (uint32_t)(p1 >> 32) ^ b[j] ^ k0; b[j] = (uint32_t)p1; c[j] = (uint32_t)(p0 >> 32) ^ d[j] ^ k1; d[j] = (uint32_t)p0;
-        }
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    o0[0] = a[0]; o0[1] = b[0]; o0[2] = c[0]; o0[3] = d[0];
-    o1[0] = a[1]; o1[1] = b[1]; o1[2] = c[1]; o1[3] = d[1];
-    o2[0] = a[2]; o2[1] = b[2]; o2[2] = c[2]; o2[3] = d[2];
-    o3[0] = a[3]; o3[1] = b[3]; o3[2] = c[3]; o3[3] = d[3];
-}
-
 __device__ __forceinline__ double u52(uint32_t lo, uint32_t hi)
 {   // 52-bit uniform in (0,1): ((w >> 12) + 0.5) * 2^-52, exactly representable
     const uint64_t w = ((uint64_t)hi << 32) | lo;
@@ -234,6 +214,15 @@ __device__ __forceinline__ double trial_uniform(const Params &p, uint64_t S, uin
     const uint64_t coarse = (o[(t & 15u) >> 2] >> (8u * (t & 3u))) & 0xFFu;
     const uint64_t K = (coarse << 44) | trial_fine44(p, S, t);
     return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+}
+
+// The uniform of the k-th absorption-point draw (imctrk2d.f:451-459) of trial flight t: word pair (t & 1) of
+// philox(S, t >> 1, 2 + k) -- two trials share a call.
+__device__ __forceinline__ double abs_uniform(const Params &p, uint64_t S, uint32_t t, uint32_t k)
+{
+    uint32_t o[4];
+    philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t >> 1, 2u + k, p.key0, p.key1, o);
+    return (t & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
 }
 
 // ------------------------------------------------------------------------------------------ small helpers
@@ -464,11 +453,19 @@ __device__ __forceinline__ void sig_begin(const Params &p, double xnu, SigCtx &c
 }
 
 // Rounding-noise term of one electron bin (see kn_eta): pref_i (eta(a1_i x) - eta(a2_i x)).  The a-side noise is
-// < 1e-12 of the bin once y_a > 0.1 (it falls like 1 / y^3 from 1.6e-10 at the branch switch).
-__device__ __forceinline__ double kn_noise_bin(const Params &p, int i, double x)
+// < 1e-12 of the bin once y_a > 0.1 (it falls like 1 / y^3 from 1.6e-10 at the branch switch).  On the b side
+// y_b = a2_i x is tiny for all but the lowest-gamma bins, where (9 + y + 8 / y) / (1 + y) = (8 / y) (1 + y / 8 + O(y^3)):
+// with kn_cb = 8 pref_i / a2_i formed once on the host the bin costs no division.
+__device__ __forceinline__ double kn_noise_bin(const Params &p, int i, double x, double inv_x)
 {
-    const double ya = p.kn_a1[i] * x;
-    return p.kn_pref[i] * (((ya < 0.1) ? kn_eta(ya) : 0.0) - kn_eta(p.kn_a2[i] * x));
+    const double ya = p.kn_a1[i] * x, yb = p.kn_a2[i] * x;
+    double q;
+    if (yb < 1.e-3) {
+        const double s = 1.0 + yb, e = (s - 1.0) - yb;
+        q = -(p.kn_cb[i] * inv_x) * (e * fma(0.125, yb, 1.0));
+    } else q = -(p.kn_pref[i] * kn_eta(yb));
+    if (ya < 0.1) q = q + p.kn_pref[i] * kn_eta(ya);
+    return q;
 }
 
 // Noise sums  sum_{i >= m} noise_i(x) W[z][i]  for up to four zones
@@ -478,9 +475,9 @@ __device__ __forceinline__ void sig_noise_zones(const Params &p, double x, int m
     const double *w0 = p.sig_W + (size_t)zi[0] * N, *w1 = p.sig_W + (size_t)zi[nzn > 1 ? 1 : 0] * N;
     const double *w2 = p.sig_W + (size_t)zi[nzn > 2 ? 2 : 0] * N, *w3 = p.sig_W + (size_t)zi[nzn > 3 ? 3 : 0] * N;
     double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
-#pragma unroll 4
+    const double inv_x = 1.0 / x;
     for (int i = m; i < N - 1; i++) {
-        const double q = kn_noise_bin(p, i, x);
+        const double q = kn_noise_bin(p, i, x, inv_x);
         e0 = fma(q, w0[i], e0); e1 = fma(q, w1[i], e1); e2 = fma(q, w2[i], e2); e3 = fma(q, w3[i], e3);
     }
     ee[0] = e0; ee[1] = e1; ee[2] = e2; ee[3] = e3;
@@ -731,6 +728,8 @@ struct FlightCtx {           // energy bins are constant along a flight (xnu onl
     int i_e, i_gg;
     double dcol_f0;
     SigCtx sig;
+    uint64_t abs_S;          // trial flights: absorption-point draws come from abs_uniform(abs_S, abs_t, abs_k++)
+    uint32_t abs_t, abs_k;
 };
 __device__ __forceinline__ void flight_begin(const Params &p, double xnu, FlightCtx &c)
 {
@@ -748,7 +747,7 @@ __device__ __forceinline__ void flight_begin(const Params &p, double xnu, Flight
 // Returns STEP_CONT when the flight goes on in the next zone, or the END_* code.
 template <int MODE>
 __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, double wtmin, double &colmfp, double sigsc,
-                                        const FlightCtx &c, Seg *segs, int &s, int &nseg)
+                                        FlightCtx &c, Seg *segs, int &s, int &nseg)
 {
     const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
     const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
@@ -838,7 +837,8 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
         if (!(xabs <= .00001)) {
             if (MODE == MODE_F0) rng.d++;                               // draw consumed, value unused (no deposit)
             else {
-                const double mb_ran = rng.next(p);                      // always < ew/deleabs (>= 1)
+                const double mb_ran = (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW) ? abs_uniform(p, c.abs_S, c.abs_t, c.abs_k++)
+                                                                                      : rng.next(p);   // always < ew/deleabs (>= 1)
                 const double sstar = -log(1. - mb_ran * deleabs / P.ew) / sigabs;
                 const double denom = sqrt(P.rpre * P.rpre + 2. * P.wmu * P.rpre * sstar + sstar * sstar);
                 wmustar = (P.wmu * P.rpre + sstar) / denom;
@@ -882,10 +882,12 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
 
 // a whole flight by one thread
 template <int MODE>
-__device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtmin, double colmfp, Seg *segs, int &nseg)
+__device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtmin, double colmfp, Seg *segs, int &nseg,
+                                uint64_t abs_S = 0, uint32_t abs_t = 0)
 {
     FlightCtx c;
     flight_begin(p, P.xnu, c);
+    c.abs_S = abs_S; c.abs_t = abs_t; c.abs_k = 0;
     if ((MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) && p.sigma_mode == 1) sig_begin(p, P.xnu, c.sig);
     int s = 0;
     for (;;) {                                                    // label 110

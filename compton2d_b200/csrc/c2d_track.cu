@@ -40,7 +40,7 @@ static __device__ __noinline__ int literal_trial(const Params &p, const Photon &
     Photon P = T0;
     int ns = nseg;
     count(p, CNT_LITERAL);
-    const int end = fly<MODE_TRIAL>(p, P, rng, wtmin, -log(u), segs, ns);
+    const int end = fly<MODE_TRIAL>(p, P, rng, wtmin, -log(u), segs, ns, S_trials, (uint32_t)t);
     if (end == END_COLLISION) {
         count(p, CNT_CMCOUNT1);
         push_collision(p, P, rng.sid);
@@ -58,7 +58,7 @@ static __device__ __noinline__ int literal_trial_slow(const Params &p, const Pho
     Photon P = T0;
     int ns = 0;
     count(p, CNT_LITERAL);
-    const int end = fly<MODE_TRIAL_SLOW>(p, P, rng, wtmin, -log(u), nullptr, ns);
+    const int end = fly<MODE_TRIAL_SLOW>(p, P, rng, wtmin, -log(u), nullptr, ns, S_trials, (uint32_t)t);
     if (end == END_COLLISION) {
         count(p, CNT_CMCOUNT1);
         push_collision(p, P, rng.sid);
@@ -192,8 +192,8 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             nlit++;
             nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
         };
-        // four Philox blocks (64 trials) per iteration: four independent dependency chains hide the latency of the
-        // ten multiply-xor rounds
+        // (Interleaving four Philox blocks per iteration for more instruction-level parallelism was measured 30 % slower:
+        // the kernel is sensitive to code size and register pressure.)
         auto scan = [&](int t16, const uint32_t (&o)[4]) {
 #pragma unroll
             for (int w = 0; w < 4; w++) {
@@ -211,16 +211,6 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
         };
         const int n16 = (p.split1 + 15) >> 4;
         int t16 = 0;
-        for (; t16 + 4 <= n16; t16 += 4) {
-            uint32_t o0[4], o1[4], o2[4], o3[4];
-            philox4x32_10x4(s_lo, s_hi, (uint32_t)t16, p.key0, p.key1, o0, o1, o2, o3);
-            const uint32_t any = bytes_ge(o0[0], Cthr) | bytes_ge(o0[1], Cthr) | bytes_ge(o0[2], Cthr) | bytes_ge(o0[3], Cthr) |
-                                 bytes_ge(o1[0], Cthr) | bytes_ge(o1[1], Cthr) | bytes_ge(o1[2], Cthr) | bytes_ge(o1[3], Cthr) |
-                                 bytes_ge(o2[0], Cthr) | bytes_ge(o2[1], Cthr) | bytes_ge(o2[2], Cthr) | bytes_ge(o2[3], Cthr) |
-                                 bytes_ge(o3[0], Cthr) | bytes_ge(o3[1], Cthr) | bytes_ge(o3[2], Cthr) | bytes_ge(o3[3], Cthr);
-            if (!any) continue;
-            scan(t16, o0); scan(t16 + 1, o1); scan(t16 + 2, o2); scan(t16 + 3, o3);
-        }
         for (; t16 < n16; t16++) {
             uint32_t o[4];
             philox4x32_10(s_lo, s_hi, (uint32_t)t16, 0u, p.key0, p.key1, o);
@@ -239,12 +229,11 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             for (int t = 0; t < p.split1; t++) {
                 const double u = trial_uniform(p, S_trials, (uint32_t)t);
                 if (trial_collides(segs, nseg, -log(u))) continue;
-                const uint64_t S_t = mix64(S_trials, (uint64_t)(t + 1));
                 uint32_t k = 0;
                 for (int s = 0; s < nseg; s++) {
                     const Seg &g = segs[s];
                     if (g.sigabs * g.L <= .00001) continue;
-                    const double mb_ran = rng_uniform(p, S_t, k++);
+                    const double mb_ran = abs_uniform(p, S_trials, (uint32_t)t, k++);
                     const double sstar = -log(1. - mb_ran * g.dele / g.ew) / g.sigabs;
                     const double denom = sqrt(g.rpre * g.rpre + 2. * wmu_c * g.rpre * sstar + sstar * sstar);
                     pr_acc[s] += g.dele * ((wmu_c * g.rpre + sstar) / denom) * kCLight;
@@ -267,12 +256,18 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                 if (sa * L <= .00001) continue;
                 const double dele = warp_shfl(segs[sc].dele, src), ew = warp_shfl(segs[sc].ew, src), rp = warp_shfl(segs[sc].rpre, src);
                 double acc = 0.0;
-                for (int t = lane; t < p.split1; t += kWarp) {
-                    if (t == l0 || t == l1 || t == l2 || t == l3) continue;
-                    const double mb_ran = rng_uniform(p, mix64(S_src, (uint64_t)(t + 1)), k);
-                    const double sstar = -log(1. - mb_ran * dele / ew) / sa;
-                    const double denom = sqrt(rp * rp + 2. * wm * rp * sstar + sstar * sstar);
-                    acc += dele * ((wm * rp + sstar) / denom) * kCLight;
+                for (int t2 = 2 * lane; t2 < p.split1; t2 += 2 * kWarp) {       // trials t2, t2 + 1: one Philox call
+                    uint32_t o[4];
+                    philox4x32_10((uint32_t)S_src, (uint32_t)(S_src >> 32), (uint32_t)t2 >> 1, 2u + k, p.key0, p.key1, o);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const int t = t2 + h;
+                        if (t >= p.split1 || t == l0 || t == l1 || t == l2 || t == l3) continue;
+                        const double mb_ran = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
+                        const double sstar = -log(1. - mb_ran * dele / ew) / sa;
+                        const double denom = sqrt(rp * rp + 2. * wm * rp * sstar + sstar * sstar);
+                        acc += dele * ((wm * rp + sstar) / denom) * kCLight;
+                    }
                 }
                 acc = warp_sum(acc);
                 if (lane == src) pr_acc[sc] = acc;
@@ -313,7 +308,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
 }
 
 #ifndef C2D_HIST_MINB
-#define C2D_HIST_MINB 1
+#define C2D_HIST_MINB 4
 #endif
 template <int SRC>
 __global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const Params p, long long first, long long n, long long stride)

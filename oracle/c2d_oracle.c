@@ -215,6 +215,16 @@ double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t)
     return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
 }
 
+/* Philox replay mode: the uniform of the k-th absorption-point draw (imctrk2d.f:451-459) of trial flight t:
+ * word pair (t & 1) of philox(ctr = (S_lo, S_hi, t >> 1, 2 + k)) -- two trials share a call. */
+double orc_abs_uniform(const uint32_t key[2], uint64_t S, uint32_t t, uint32_t k)
+{
+    uint32_t c[4] = {(uint32_t)S, (uint32_t)(S >> 32), t >> 1, 2u + k}, o[4];
+    orc_philox4x32(c, key, o);
+    const uint64_t w = (t & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+    return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+}
+
 /* rand.f:195-223 fibran (rand_switch=2 branch) / Philox extension */
 double orc_fibran(orc_state *s)
 {
@@ -530,6 +540,7 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
     double ewold, disp, psq, disbr, dpbsq, Zbnd, rbnd, xqsqleft, trld, trldb, dcol;
     double wtmin, Zr, Rr, kgg, pair_enhance, Eta, comac, sigabs, colmfp, mb_ran, denom, f;
     double sigsc, deleabs, ewnew, xabs, sstar, delpr, wmustar, rnew, znew;
+    uint32_t kabs = 0;
     photon_sv tsv, csv;
     /* comac_ar(jmax,kmax) cache of l.103,175-183 (zero = not yet computed) */
     double *comac_ar = NULL;
@@ -550,6 +561,7 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
                 rng_stream(s, orc_mix64(S_trials, (uint64_t)iitrk));
                 s->rng.has_pending = 1;
                 s->rng.pending = orc_trial_uniform(s->rng.key, S_trials, (uint32_t)(iitrk - 1));
+                kabs = 0;
             }
         }
     L100:
@@ -660,7 +672,10 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
         if (xabs <= .00001) {
             wmustar = s->wmu;
         } else {
-            do { mb_ran = orc_fibran(s); } while (!(mb_ran < (s->ew / deleabs)));   /* l.451-456 */
+            do {
+                if (philox && scat_flag == -1) mb_ran = orc_abs_uniform(s->rng.key, S_trials, (uint32_t)(iitrk - 1), kabs++);
+                else mb_ran = orc_fibran(s);
+            } while (!(mb_ran < (s->ew / deleabs)));                                /* l.451-456 */
             sstar = -log(1. - mb_ran * deleabs / s->ew) / sigabs;
             denom = sqrt(s->rpre * s->rpre + 2. * s->wmu * s->rpre * sstar + sstar * sstar);
             wmustar = (s->wmu * s->rpre + sstar) / denom;

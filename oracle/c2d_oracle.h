@@ -137,6 +137,7 @@ void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 uint64_t orc_mix64(uint64_t a, uint64_t b);
 double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d);
 double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t);
+double orc_abs_uniform(const uint32_t key[2], uint64_t S, uint32_t t, uint32_t k);
 double orc_fibran(orc_state *s);
 
 /* surface sources (imcsurf2d_para.f) */
