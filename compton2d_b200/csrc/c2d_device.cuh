@@ -864,7 +864,8 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
         colmfp = colmfp - sigsc * trld;
         if (jnew == p.nz + 1 || jnew == 0 || knew == p.nr + 1 || knew == 0) {
             P.jph = jnew; P.kph = knew;
-            if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
+            if (MODE == MODE_PRE) return END_LEAK;                 // the ray leaves the grid here (nothing tallied)
+            if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW) return END_DROPPED;
             const int idead = imcleak(p, P);
             count(p, CNT_LKCOUNT);
             if (idead == 1) return END_LEAK;
@@ -874,7 +875,8 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
         return STEP_CONT;
     }
     if (ikind == 2) {
-        if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW || MODE == MODE_PRE) return END_DROPPED;
+        if (MODE == MODE_PRE) return END_CENSUS;                   // the ray ends at census (nothing tallied)
+        if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW) return END_DROPPED;
         return census_write(p, P, rng) ? END_CENSUS : END_FATAL;
     }
     return END_COLLISION;                                       // ikind == 3

@@ -81,9 +81,11 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     Seg segs[kMaxSeg];
     int nseg = 0, nscat = 0, nlit = 0;
     bool overflow = false;
+    Photon Q = T0;                                                // end point of the collision-free ray
+    int endA = END_LOWEW;
     if (active) {
-        Photon Q = T0; Rng dummy; dummy.stream(0);
-        const int endA = fly<MODE_PRE>(p, Q, dummy, wtmin, 0.0, segs, nseg);
+        Rng dummy; dummy.stream(0);
+        endA = fly<MODE_PRE>(p, Q, dummy, wtmin, 0.0, segs, nseg);
         overflow = (endA == END_OVERFLOW);
         if (endA == END_LOWEW && nseg == 0) active = false;   // ew < 1e-40 at entry: nothing is tallied (l.161)
     }
@@ -192,12 +194,17 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             nlit++;
             nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
         };
-        // (Interleaving four Philox blocks per iteration for more instruction-level parallelism was measured 30 % slower:
-        // the kernel is sensitive to code size and register pressure.)
-        auto scan = [&](int t16, const uint32_t (&o)[4]) {
+        const int n16 = (p.split1 + 15) >> 4;
+        for (int t16 = 0; t16 < n16; t16++) {
+            uint32_t o[4];
+            philox4x32_10(s_lo, s_hi, (uint32_t)t16, 0u, p.key0, p.key1, o);
+            uint32_t mk[4];                                       // 0xFF in every byte that reaches Cthr
+#pragma unroll
+            for (int w = 0; w < 4; w++) mk[w] = bytes_ge(o[w], Cthr);
+            if (!(mk[0] | mk[1] | mk[2] | mk[3])) continue;       // 94 % of the groups of an optically thin ray
 #pragma unroll
             for (int w = 0; w < 4; w++) {
-                uint32_t m = bytes_ge(o[w], Cthr);                // 0xFF in every byte that reaches Cthr
+                uint32_t m = mk[w];
                 while (m) {
                     const int b = (first_lane(m)) >> 3;
                     m &= ~(0xFFu << (8 * b));
@@ -208,13 +215,6 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                     else examine(t, coarse);                      // optically thick ray: no point in deferring
                 }
             }
-        };
-        const int n16 = (p.split1 + 15) >> 4;
-        int t16 = 0;
-        for (; t16 < n16; t16++) {
-            uint32_t o[4];
-            philox4x32_10(s_lo, s_hi, (uint32_t)t16, 0u, p.key0, p.key1, o);
-            scan(t16, o);
         }
         for (int c = 0; c < ncand; c++) examine(cand[c] & 0xFFFFFF, (uint32_t)cand[c] >> 24);
     }
@@ -296,13 +296,40 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             if (ns) count(p, CNT_SEGMENTS, ns);
         }
     }
-    // E: recombined flight of the unscattered weight (l.698-712)
+    // E: recombined flight of the unscattered weight (l.698-712): scat_flag = 0, no collisions, no deposition.  It
+    // follows the ray of step A, so its geometry is not traced again: the weight is attenuated crossing by crossing
+    // (with this flight's own kill threshold and its own draw count) and the census / leak tallies are made at the
+    // ray's end point.  Rays that step A did not finish the same way (killed earlier because a trial carries 1/split1
+    // of the weight, more crossings than the fast path holds) and photons that pass through the axis are flown literally.
     if (active && p.split1 - nscat > 0) {
         Photon F = P0;
         F.ew = (p.split1 - nscat) * T0.ew;
+        const double wt0 = 1.e-10 * F.ew;
         Rng rng; rng.stream(mix64(S_entry, kTagF0));
-        int dummy = 0;
-        const int end = fly<MODE_F0>(p, F, rng, 1.e-10 * F.ew, 0.0, nullptr, dummy);
+        int dummy = 0, end = END_DROPPED;
+        bool literal = !(fast && (endA == END_CENSUS || endA == END_LEAK));
+        if (!literal) {
+            bool alive = true;
+            for (int s = 0; s < nseg; s++) {
+                if (F.ew < 1.e-40) { alive = false; break; }      // l.161
+                const double xabs = segs[s].sigabs * segs[s].L;
+                const double ewnew = (xabs < 100.) ? F.ew * exp(-xabs) : 0.;
+                if (!(xabs <= .00001)) rng.d++;                   // the absorption-point draw is consumed, its value unused
+                if (ewnew <= wt0) { count(p, CNT_KILLED); alive = false; break; }
+                F.ew = ewnew;
+            }
+            if (alive) {
+                F.rpre = Q.rpre; F.zpre = Q.zpre; F.phi = Q.phi; F.wmu = Q.wmu; F.dcen = Q.dcen; F.jph = Q.jph; F.kph = Q.kph;
+                if (endA == END_CENSUS) {
+                    if (!census_write(p, F, rng)) end = END_FATAL;
+                } else {
+                    const int idead = imcleak(p, F);
+                    count(p, CNT_LKCOUNT);
+                    literal = (idead != 1);                       // through the axis: the flight goes on
+                }
+            }
+        }
+        if (literal) end = fly<MODE_F0>(p, F, rng, wt0, 0.0, nullptr, dummy);
         if (end == END_COLLISION) count(p, CNT_FATAL);
     }
 }
