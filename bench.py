@@ -172,6 +172,62 @@ def workload_config(args, ref=False):
             "step": "imcfield2d + imcvol2d + scattering queue + tally all-reduce"}
 
 
+# ------------------------------------------------------------------------------------------ Fokker-Planck leg
+def fp_bench(local, hbm, reps=3, nz=64, nr=64):
+    """FP zone-steps/s (second half of BASELINE.json's metric) on the BASELINE configs[4] grid: 64 x 64 zones, the
+    reference's 200 momentum bins (its compile-time num_nt; 512 bins exceed what the reference can run),
+    every zone carrying the reference binary's own pre-FP state of the shipped plasma (tests/golden/refbin_small.npz,
+    snapshot c2_E, zone (1,1): electron spectrum, tallied photon field, shipped injection block with the pick-up
+    Gaussian on), photon field jittered +-10 % per zone.  One call = FP_calc for all zones (c2d_update_fp); a zone-step =
+    one implicit Chang-Cooper sub-step of one zone."""
+    import numpy as np
+    from golden_util import Golden
+    from parity_util import make_gpu
+    from synth import make_problem
+    E = Golden("small").snap("c2_E")
+    P = make_problem(nz=nz, nr=nr, nst=1000, ngroups=100)
+    nzone = nz * nr
+    g = make_gpu(P, census_capacity=1000, event_capacity=1000, device=local)
+    try:
+        g.timing(True)
+        F_IC = g.IC_loss()
+        rng = np.random.default_rng(7)
+        vr = P["vol"] / float(E.vol[0, 0])
+        tr = P["dt"] / float(E.dt[0])
+        til = lambda a: np.ascontiguousarray(np.tile(np.asarray(a, float), (nzone, 1)))
+        n_field = til(E.n_field[:, 0, 0]) * vr[:, None] * (1.0 + 0.2 * (rng.random((nzone, 1)) - 0.5))
+        inj = {k: float(E[k.lower()]) for k in ("inj_g1", "inj_g2", "inj_p", "inj_t", "inj_gg", "inj_sigma", "inj_L", "inj_v", "pick_rate")}
+        inj.update({k: int(E[k]) for k in ("inj_switch", "inj_dis", "g2var_switch", "pick_sw")})
+        kw = dict(time=2.0 * P["dt"], dt=P["dt"], f_nt=til(E.f_nt[0, 0]), Pnt=til(E.pnt[0, 0]), n_e=np.full(nzone, float(E.n_e[0, 0])),
+                  B_field=np.full(nzone, float(E.b_field[0, 0])), tea=np.full(nzone, float(E.tea[0, 0])),
+                  tna=np.full(nzone, float(E.tna[0, 0])), vol=P["vol"], Eloss_sy=float(E.eloss_sy[0, 0]) * vr * tr,
+                  ec_old=float(E.ec_old[0, 0]) * vr, turb_lev=np.full(nzone, float(E.turb_lev[0, 0])),
+                  gmin=np.full(nzone, float(E.gmin[0, 0])), gmax=np.full(nzone, float(E.gmax[0, 0])),
+                  p_nth=np.full(nzone, float(E.p_nth[0, 0])), amxwl=np.full(nzone, float(E.amxwl[0, 0])),
+                  n_field=n_field, ecens=float(E.ecens[0, 0]) * vr, F_IC=F_IC, lnL=float(E.lnl), r_esc=float(E.r_esc),
+                  r_acc=float(E.r_acc), inj=inj)
+        out = g.update(**kw)                       # warm-up
+        g.timing_reset()
+        t0 = time.perf_counter()
+        steps = 0
+        for _ in range(reps):
+            out = g.update(**kw)
+            steps += int(out["fp_steps"].sum())
+        wall = time.perf_counter() - t0
+        ms, nl = g.kernel_time(3)
+        N, nf = P["gnt"].size, P["E_field"].size
+        bytes_alg = steps * 5.0 * 8.0 * N + reps * nzone * (8.0 * nf + 200.0)      # SURVEY.md 8d: 5*8*N B per zone-step
+        ach = bytes_alg / (ms * 1e-3) / 1e9
+        return {"metric": "fp_zone_steps_per_s", "value": steps / (ms * 1e-3), "unit": "zone-steps/s",
+                "e2e_value": steps / wall, "zones": nzone, "bins": N, "sub_steps_per_zone": steps / (reps * nzone),
+                "kernel_ms_per_call": ms / reps, "launches": int(nl),
+                "roofline": {"bound": "hbm", "kernel": "k_fp_zones", "achieved": ach, "peak": hbm, "unit": "GB/s",
+                             "frac": ach / hbm, "traffic": None},
+                "workload": "BASELINE configs[4] grid 64x64 zones x 200 bins (reference's num_nt), shipped plasma + injection block"}
+    finally:
+        g.close()
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def our_arm(args):
     import numpy as np
@@ -307,6 +363,11 @@ def our_arm(args):
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                         "bytes_per_step": bytes_step},
            "counters": c, "clocks": clocks}
+    if not args.no_fp and world == 1:
+        try:
+            out["fp"] = fp_bench(local, hbm)
+        except Exception as e:                     # the FP leg must never take the headline down with it
+            out["fp"] = {"error": repr(e)[:300]}
     if not args.no_cpu_baseline and world == 1:
         r = run_reference_sample(args.cpu_nst, ncores=1, warm=0, timed=2)
         if r and "error" not in r:
@@ -331,6 +392,7 @@ def main():
     ap.add_argument("--ref-nst", type=int, default=6_000, help="--impl reference: nst per instance (census grows every cycle)")
     ap.add_argument("--cpu-nst", type=int, default=30_000, help="nst of the bounded cpu_baseline sample (cycles 1-2, one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp", action="store_true", help="skip the Fokker-Planck zone-steps/s leg")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
