@@ -228,6 +228,21 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64):
         g.close()
 
 
+def tally_bench(g, hbm, n_events=100_000_000):
+    """Stand-alone tally-commit kernel (csrc/c2d_tally.cu) on a generated list of deposition events, zones hashed:
+    achieved algorithmic GB/s (56 B/event) against the measured HBM peak."""
+    g.tally_bench(n_events // 10, 0)               # warm-up
+    best = None
+    for _ in range(3):
+        ms, nb = g.tally_bench(n_events, 0)
+        best = ms if best is None else min(best, ms)
+    ach = 56.0 * n_events / (best * 1e-3) / 1e9
+    ms_s, _ = g.tally_bench(n_events, 0x20)
+    return {"kernel": "k_tally_deposit", "events": n_events, "ms": best, "events_per_s": n_events / (best * 1e-3),
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None},
+            "sorted_by_zone_ms": ms_s}
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def our_arm(args):
     import numpy as np
@@ -363,6 +378,11 @@ def our_arm(args):
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                         "bytes_per_step": bytes_step},
            "counters": c, "clocks": clocks}
+    if not args.no_fp and world == 1:
+        try:
+            out["tally"] = tally_bench(g, hbm)
+        except Exception as e:
+            out["tally"] = {"error": repr(e)[:300]}
     if not args.no_fp and world == 1:
         try:
             out["fp"] = fp_bench(local, hbm)

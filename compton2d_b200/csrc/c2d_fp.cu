@@ -717,7 +717,6 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
     return 0;
 }
 
-int c2d_tally_bench(c2d_ctx *, int64_t, int, float *, int64_t *) { return c2d::fail(C2D_EINVAL, "not built yet"); }
 
 }  // extern "C"
 

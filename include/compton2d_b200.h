@@ -223,6 +223,10 @@ int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);
            2 k_split3_attempts/_hard, 3 FP, 4 sigma table, 5 tally bench, 6 k_split3_flights, 7 bracket);
            -1 enable, -2 reset, -3 / -4 record the start / stop event of a bracket (accumulated in family 7) */
 int c2d_tally_bench(c2d_ctx *ctx, int64_t n_events, int kind, float *ms, int64_t *bytes);
+        /* stand-alone tally-commit kernel on a generated event list (csrc/c2d_tally.cu): kind 0 deposition (edep, prdep;
+           56 algorithmic B/event), kind 1 census (bank record + npcen, ecens, n_field; 112 B/event); | 0x10 without the
+           warp-level pre-reduction, | 0x20 events sorted by zone.  Adds into the context's tallies; returns the kernel's
+           CUDA-event time and the algorithmic bytes */
 
 #ifdef __cplusplus
 }
