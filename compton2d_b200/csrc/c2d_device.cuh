@@ -197,24 +197,51 @@ struct Rng {
     }
 };
 
-// The xi of trial flight t (0-based) of a history with trial stream S: K = coarse8 << 44 | fine44,
-// u = (K + 0.5) 2^-52.  coarse = byte (t & 15) of philox(S, t >> 4, 0); fine = word 0 and the low 12 bits of word 1
-// of philox(S, t, 1).  Sixteen trials share one Philox call for the coarse part, and a trial whose coarse byte
-// is below the threshold's never needs the fine part (see history()).
+// The xi of the trial flights of a history with trial stream S: u_t = (K_t + 0.5) 2^-52, K_t = coarse8 << 44 | fine44.
+//   Which trials have coarse = 0xFF ("candidates", 1 trial in 256, independently) is decided by the GAPS between them:
+//       gap_j = floor(ln U_j / ln(255/256)),  U_j = word pair (j & 1) of philox(S, j >> 1, 3),
+//       candidate_j = candidate_{j-1} + 1 + gap_j  -- a Bernoulli(1/256) process has geometric gaps;
+//   every other trial has coarse = (w * 255) >> 32 in [0, 254], w = word (t & 3) of philox(S, t >> 2, 0);
+//   fine = word 0 and the low 12 bits of word 1 of philox(S, t, 1).
+// A trial collides only if u exceeds a threshold close to 1, so an optically thin ray (tau < 1/256) only has to look at
+// its ~split1/256 candidates: history() jumps from candidate to candidate instead of drawing split1 numbers.
+constexpr double kLnQ = -3.9138993211363287e-3;      // ln(255/256)
 __device__ __forceinline__ uint64_t trial_fine44(const Params &p, uint64_t S, uint32_t t)
 {
     uint32_t o[4];
     philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t, 1u, p.key0, p.key1, o);
     return (((uint64_t)(o[1] & 0xFFFu)) << 32) | o[0];
 }
-__device__ __forceinline__ double trial_uniform(const Params &p, uint64_t S, uint32_t t)
-{
-    uint32_t o[4];
-    philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t >> 4, 0u, p.key0, p.key1, o);
-    const uint64_t coarse = (o[(t & 15u) >> 2] >> (8u * (t & 3u))) & 0xFFu;
-    const uint64_t K = (coarse << 44) | trial_fine44(p, S, t);
-    return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
-}
+struct TrialGen {
+    uint64_t S;
+    long long next_c;        // position of the next candidate (>= split1: none left)
+    uint32_t j;
+    __device__ __forceinline__ void advance(const Params &p)
+    {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), j >> 1, 3u, p.key0, p.key1, o);
+        const double U = (j & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
+        const double gap = floor(log(U) / kLnQ);
+        j++;
+        next_c = (gap > 1.e9) ? (1ll << 40) : next_c + 1 + (long long)gap;
+    }
+    __device__ __forceinline__ void init(const Params &p, uint64_t S_) { S = S_; j = 0; next_c = -1; advance(p); }
+    // coarse byte of trial t; t must not decrease between calls
+    __device__ __forceinline__ uint32_t coarse(const Params &p, uint32_t t)
+    {
+        while (next_c < (long long)t) advance(p);
+        if (next_c == (long long)t) return 0xFFu;
+        uint32_t o[4];
+        philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), t >> 2, 0u, p.key0, p.key1, o);
+        const uint32_t w = (t & 2u) ? ((t & 1u) ? o[3] : o[2]) : ((t & 1u) ? o[1] : o[0]);
+        return (uint32_t)(((uint64_t)w * 255u) >> 32);
+    }
+    __device__ __forceinline__ double uniform(const Params &p, uint32_t t)
+    {
+        const uint64_t K = ((uint64_t)coarse(p, t) << 44) | trial_fine44(p, S, t);
+        return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+    }
+};
 
 // The uniform of the k-th absorption-point draw (imctrk2d.f:451-459) of trial flight t: word pair (t & 1) of
 // philox(S, t >> 1, 2 + k) -- two trials share a call.
@@ -226,17 +253,6 @@ __device__ __forceinline__ double abs_uniform(const Params &p, uint64_t S, uint3
 }
 
 // ------------------------------------------------------------------------------------------ small helpers
-// 0xFF in every byte of w that is >= c (c <= 0x100; c = 0x100: none)
-__device__ __forceinline__ uint32_t bytes_ge(uint32_t w, uint32_t c)
-{
-#ifdef C2D_EMU
-    uint32_t m = 0;
-    for (int b = 0; b < 4; b++) if (((w >> (8 * b)) & 0xFFu) >= c) m |= 0xFFu << (8 * b);
-    return m;
-#else
-    return (c <= 0xFFu) ? __vcmpgeu4(w, c * 0x01010101u) : 0u;
-#endif
-}
 __device__ __forceinline__ void atomic_add_f64(double *a, double v) { atomicAdd(a, v); }
 __device__ __forceinline__ void count(const Params &p, int which, unsigned long long n = 1ull)
 {

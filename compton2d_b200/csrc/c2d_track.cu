@@ -91,8 +91,9 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     }
     if (active && overflow) {
         count(p, CNT_SEGOVF);
+        TrialGen tg; tg.init(p, S_trials);
         for (int t = 0; t < p.split1; t++)
-            nscat += literal_trial_slow(p, T0, S_trials, t, trial_uniform(p, S_trials, (uint32_t)t), wtmin);
+            nscat += literal_trial_slow(p, T0, S_trials, t, tg.uniform(p, (uint32_t)t), wtmin);
     }
     const bool overflow_counted = active && overflow;
     const bool fast = active && !overflow;
@@ -176,15 +177,9 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
         // u = (K + 0.5) 2^-52 >= thr  <=>  K >= ceil(thr 2^52 - 0.5): the filter runs on integers
         const double tk = thr * 4503599627370496.0 - 0.5;
         Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
-        // K = coarse8 << 44 | fine44 (trial_uniform): a trial whose coarse byte is below the threshold's cannot
-        // collide, and sixteen trials share one Philox call for their coarse bytes
+        // K = coarse8 << 44 | fine44 (TrialGen): a trial whose coarse byte is below the threshold's cannot collide.
+        // Thin ray (threshold byte 0xFF): only the candidates are visited, ~split1/256 of them; otherwise every trial.
         const uint32_t Cthr = (uint32_t)(Kthr >> 44);
-        const uint32_t s_lo = (uint32_t)S_trials, s_hi = (uint32_t)(S_trials >> 32);
-        // pass 1 (convergent): the coarse bytes of all trials; candidates (coarse >= Cthr, 1 trial in 256 for an
-        // optically thin ray) are only noted.  pass 2: the fine word and the exact collision test of the candidates,
-        // so that the lanes of a warp do their rare second Philox calls together instead of one lane at a time.
-        constexpr int kMaxCand = 12;
-        int cand[kMaxCand], ncand = 0;
         auto examine = [&](int t, uint32_t coarse) {
             const uint64_t K = ((uint64_t)coarse << 44) | trial_fine44(p, S_trials, (uint32_t)t);
             if (K < Kthr) return;
@@ -194,29 +189,17 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             nlit++;
             nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
         };
-        const int n16 = (p.split1 + 15) >> 4;
-        for (int t16 = 0; t16 < n16; t16++) {
-            uint32_t o[4];
-            philox4x32_10(s_lo, s_hi, (uint32_t)t16, 0u, p.key0, p.key1, o);
-            uint32_t mk[4];                                       // 0xFF in every byte that reaches Cthr
-#pragma unroll
-            for (int w = 0; w < 4; w++) mk[w] = bytes_ge(o[w], Cthr);
-            if (!(mk[0] | mk[1] | mk[2] | mk[3])) continue;       // 94 % of the groups of an optically thin ray
-#pragma unroll
-            for (int w = 0; w < 4; w++) {
-                uint32_t m = mk[w];
-                while (m) {
-                    const int b = (first_lane(m)) >> 3;
-                    m &= ~(0xFFu << (8 * b));
-                    const int t = 16 * t16 + 4 * w + b;
-                    if (t >= p.split1) continue;
-                    const uint32_t coarse = (o[w] >> (8 * b)) & 0xFFu;
-                    if (ncand < kMaxCand) cand[ncand++] = t | (int)(coarse << 24);
-                    else examine(t, coarse);                      // optically thick ray: no point in deferring
+        if (Cthr <= 0xFFu) {                                      // 0x100: tau = 0, nothing can collide
+            TrialGen tg; tg.init(p, S_trials);
+            if (Cthr == 0xFFu) {
+                while (tg.next_c < (long long)p.split1) { examine((int)tg.next_c, 0xFFu); tg.advance(p); }
+            } else {
+                for (int t = 0; t < p.split1; t++) {
+                    const uint32_t coarse = tg.coarse(p, (uint32_t)t);
+                    if (coarse >= Cthr) examine(t, coarse);
                 }
             }
         }
-        for (int c = 0; c < ncand; c++) examine(cand[c] & 0xFFFFFF, (uint32_t)cand[c] >> 24);
     }
     // C': absorption-point draws of l.451-459 for the non-colliding trials of a ray with sigabs L > 1e-5 in some
     // crossing (they only move prdep): one uniform per (trial, absorbing crossing) from the trial's stream.  The
@@ -226,8 +209,9 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
         const bool coop = fast && has_rand && nlit <= 4;
         if (fast && has_rand && !coop) {                          // many collisions: the owner lane walks its trials
             for (int s = 0; s < nseg; s++) pr_acc[s] = 0.0;
+            TrialGen tg; tg.init(p, S_trials);
             for (int t = 0; t < p.split1; t++) {
-                const double u = trial_uniform(p, S_trials, (uint32_t)t);
+                const double u = tg.uniform(p, (uint32_t)t);
                 if (trial_collides(segs, nseg, -log(u))) continue;
                 uint32_t k = 0;
                 for (int s = 0; s < nseg; s++) {

@@ -198,21 +198,54 @@ double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d)
     return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
 }
 
-/* Philox replay mode: the xi of trial flight t (0-based) of a history with trial stream S.  The 52-bit
- * integer K of u = (K + 0.5) 2^-52 is composed of two independent Philox outputs:
- *   coarse  8 bits = byte (t & 15) of philox(ctr = (S_lo, S_hi, t >> 4, 0))          (16 trials per call)
- *   fine   44 bits = word 0 and the low 12 bits of word 1 of philox(ctr = (S_lo, S_hi, t, 1))
- * so a consumer that only needs to know whether u exceeds a threshold close to 1 (the CUDA trial
- * filter) can decide 255 of 256 trials from the coarse byte alone. */
-double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t)
+/* Philox replay mode: the xi of the trial flights of a history with trial stream S.  u_t = (K_t + 0.5) 2^-52 with
+ * K_t = coarse8 << 44 | fine44, three independent Philox outputs:
+ *   which trials have coarse = 0xFF ("candidates": 1 trial in 256, independently) is decided by the GAPS between them,
+ *       gap_j = floor(ln U_j / ln(255/256)),  U_j = word pair (j & 1) of philox(ctr = (S_lo, S_hi, j >> 1, 3)),
+ *       candidate_j = candidate_{j-1} + 1 + gap_j  (candidate_{-1} = -1): a Bernoulli(1/256) process has geometric gaps;
+ *   every other trial has coarse = (w * 255) >> 32 in [0, 254], w = word (t & 3) of philox(ctr = (S_lo, S_hi, t >> 2, 0));
+ *   fine = word 0 and the low 12 bits of word 1 of philox(ctr = (S_lo, S_hi, t, 1)).
+ * A trial collides only if u exceeds a threshold close to 1, so for an optically thin ray (tau < 1/256) only the
+ * candidates need to be looked at: the CUDA path jumps from candidate to candidate instead of drawing split1 numbers.
+ * The generator must be asked for non-decreasing t. */
+typedef struct { uint64_t S; int64_t next_c; uint32_t j; } orc_trialgen;
+#define ORC_LN_Q (-3.9138993211363287e-3)      /* ln(255/256) */
+static void trialgen_advance(const uint32_t key[2], orc_trialgen *g)
 {
-    uint32_t c0[4] = {(uint32_t)S, (uint32_t)(S >> 32), t >> 4, 0u}, c1[4] = {(uint32_t)S, (uint32_t)(S >> 32), t, 1u}, o[4], f[4];
-    orc_philox4x32(c0, key, o);
+    uint32_t c[4] = {(uint32_t)g->S, (uint32_t)(g->S >> 32), g->j >> 1, 3u}, o[4];
+    orc_philox4x32(c, key, o);
+    const uint64_t w = (g->j & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
+    const double U = ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
+    const double gap = floor(log(U) / ORC_LN_Q);
+    g->j++;
+    g->next_c = (gap > 1.e9) ? (int64_t)1 << 40 : g->next_c + 1 + (int64_t)gap;
+}
+static void trialgen_init(const uint32_t key[2], orc_trialgen *g, uint64_t S)
+{
+    g->S = S; g->j = 0; g->next_c = -1;
+    trialgen_advance(key, g);
+}
+static double trialgen_uniform(const uint32_t key[2], orc_trialgen *g, uint32_t t)
+{
+    uint32_t c1[4] = {(uint32_t)g->S, (uint32_t)(g->S >> 32), t, 1u}, f[4];
+    uint64_t coarse;
+    while (g->next_c < (int64_t)t) trialgen_advance(key, g);
+    if (g->next_c == (int64_t)t) coarse = 0xFFu;
+    else {
+        uint32_t c0[4] = {(uint32_t)g->S, (uint32_t)(g->S >> 32), t >> 2, 0u}, o[4];
+        orc_philox4x32(c0, key, o);
+        coarse = ((uint64_t)o[t & 3u] * 255u) >> 32;
+    }
     orc_philox4x32(c1, key, f);
-    const uint64_t coarse = (o[(t & 15u) >> 2] >> (8u * (t & 3u))) & 0xFFu;
     const uint64_t fine = (((uint64_t)(f[1] & 0xFFFu)) << 32) | f[0];
-    const uint64_t K = (coarse << 44) | fine;
-    return ((double)K + 0.5) * (1.0 / 4503599627370496.0);
+    return ((double)((coarse << 44) | fine) + 0.5) * (1.0 / 4503599627370496.0);
+}
+/* stand-alone form (tests): u_t for t = 0 .. n-1 */
+void orc_trial_uniforms(const uint32_t key[2], uint64_t S, int n, double *u)
+{
+    orc_trialgen g;
+    trialgen_init(key, &g, S);
+    for (int t = 0; t < n; t++) u[t] = trialgen_uniform(key, &g, (uint32_t)t);
 }
 
 /* Philox replay mode: the uniform of the k-th absorption-point draw (imctrk2d.f:451-459) of trial flight t:
@@ -541,6 +574,7 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
     double wtmin, Zr, Rr, kgg, pair_enhance, Eta, comac, sigabs, colmfp, mb_ran, denom, f;
     double sigsc, deleabs, ewnew, xabs, sstar, delpr, wmustar, rnew, znew;
     uint32_t kabs = 0;
+    orc_trialgen tgen;
     photon_sv tsv, csv;
     /* comac_ar(jmax,kmax) cache of l.103,175-183 (zero = not yet computed) */
     double *comac_ar = NULL;
@@ -552,6 +586,7 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
     nscat = 0;
     ph_save(s, &tsv);
     if (scat_flag == -1) tsv.ew = s->ew / s->split1;         /* l.109-113 */
+    if (scat_flag == -1 && philox) trialgen_init(s->rng.key, &tgen, S_trials);
 
     for (iitrk = 1; iitrk <= s->split1; iitrk++) {           /* do 910 */
         ph_restore(s, &tsv);
@@ -560,7 +595,7 @@ void orc_imctrk2d(orc_state *s, int scat_flag)
             if (philox) {          /* trial stream: first draw comes from the history's trial-xi stream */
                 rng_stream(s, orc_mix64(S_trials, (uint64_t)iitrk));
                 s->rng.has_pending = 1;
-                s->rng.pending = orc_trial_uniform(s->rng.key, S_trials, (uint32_t)(iitrk - 1));
+                s->rng.pending = trialgen_uniform(s->rng.key, &tgen, (uint32_t)(iitrk - 1));
                 kabs = 0;
             }
         }

@@ -136,7 +136,7 @@ void orc_philox_key(orc_state *s, uint32_t seed, uint32_t cycle);
 void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 uint64_t orc_mix64(uint64_t a, uint64_t b);
 double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d);
-double orc_trial_uniform(const uint32_t key[2], uint64_t S, uint32_t t);
+void orc_trial_uniforms(const uint32_t key[2], uint64_t S, int n, double *u);
 double orc_abs_uniform(const uint32_t key[2], uint64_t S, uint32_t t, uint32_t k);
 double orc_fibran(orc_state *s);
 

@@ -138,3 +138,13 @@ def test_replay_parity_surface_sources(kind, sigma_mode):
         assert rg["counters"]["histories"] > 5000
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("sigma_mode", [0, 1])
+def test_replay_parity_thin_rays_with_collisions(sigma_mode):
+    """tau ~ 1e-3 < 1/256 with split1 = 1000: trial draws visited candidate by candidate (TrialGen), ~0.8 collisions per
+    history so the candidate positions, the fine words and the literal trial flights are all exercised."""
+    P = make_problem(nz=6, nr=6, nst=6000, ngroups=64, split=(1000, 4, 2, 10), n_e=2.0e6)
+    rg = _run(P, cycles=(1, 2), census_tol=1e-4, sigma_mode=sigma_mode)
+    c = rg["counters"]
+    assert 0.1 < c["cmcount1"] / c["histories"] < 1000 / 256

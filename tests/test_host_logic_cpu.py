@@ -56,6 +56,23 @@ def test_multiple_scattering_and_third_split(emu):
     g.close()
 
 
+def test_thin_rays_with_collisions(emu):
+    """tau ~ 1e-3 < 1/256 with split1 = 1000: the trial draws go candidate by candidate (TrialGen gaps), and there are
+    enough collisions (~0.8 per history) for the candidate positions to matter."""
+    from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step
+    from synth import make_problem
+    P = make_problem(nz=6, nr=6, nst=1200, ngroups=64, split=(1000, 4, 2, 10), n_e=2.0e6)
+    o, g = make_oracle(P), make_gpu(P, sigma_mode=1)
+    for cyc in (1, 2):
+        ro = oracle_step(o, P, cyc, field=cyc > 1)
+        rg = gpu_step(g, P, cyc, field=cyc > 1)
+        bad = compare(rg, ro, tol=1e-10, census_tol=1e-4)
+        assert not bad, (cyc, bad)
+    c = rg["counters"]
+    assert 0.1 < c["cmcount1"] / c["histories"] < 1000 / 256
+    g.close()
+
+
 @pytest.mark.parametrize("kind", ["file", "planck"])
 def test_surface_sources(emu, kind):
     """imcsurf2d: disk sources sampled from an external spectrum (BASELINE configs[2]) and Planckian boundaries."""
