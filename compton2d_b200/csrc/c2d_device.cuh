@@ -252,6 +252,13 @@ __device__ __forceinline__ double abs_uniform(const Params &p, uint64_t S, uint3
     return (t & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
 }
 
+// read-only global load (tables that no kernel of the same launch writes)
+#ifdef C2D_EMU
+__device__ __forceinline__ double c2d_ldg(const double *a) { return *a; }
+#else
+__device__ __forceinline__ double c2d_ldg(const double *a) { return __ldg(a); }
+#endif
+
 // ------------------------------------------------------------------------------------------ small helpers
 __device__ __forceinline__ void atomic_add_f64(double *a, double v) { atomicAdd(a, v); }
 __device__ __forceinline__ void count(const Params &p, int which, unsigned long long n = 1ull)
@@ -469,22 +476,12 @@ __device__ __forceinline__ void sig_begin(const Params &p, double xnu, SigCtx &c
 }
 
 // Rounding-noise term of one electron bin (see kn_eta): pref_i (eta(a1_i x) - eta(a2_i x)).  The a-side noise is
-// < 1e-12 of the bin once y_a > 0.1 (it falls like 1 / y^3 from 1.6e-10 at the branch switch).  On the b side
+// < 1e-12 of the bin once y_a = a1_i x > 0.1 (it falls like 1 / y^3 from 1.6e-10 at the branch switch).  On the b side
 // y_b = a2_i x is tiny for all but the lowest-gamma bins, where (9 + y + 8 / y) / (1 + y) = (8 / y) (1 + y / 8 + O(y^3)):
-// with kn_cb = 8 pref_i / a2_i formed once on the host the bin costs no division.
-__device__ __forceinline__ double kn_noise_bin(const Params &p, int i, double x, double inv_x)
-{
-    const double ya = p.kn_a1[i] * x, yb = p.kn_a2[i] * x;
-    double q;
-    if (yb < 1.e-3) {
-        const double s = 1.0 + yb, e = (s - 1.0) - yb;
-        q = -(p.kn_cb[i] * inv_x) * (e * fma(0.125, yb, 1.0));
-    } else q = -(p.kn_pref[i] * kn_eta(yb));
-    if (ya < 0.1) q = q + p.kn_pref[i] * kn_eta(ya);
-    return q;
-}
-
-// Noise sums  sum_{i >= m} noise_i(x) W[z][i]  for up to four zones
+// with kn_cb = 8 pref_i / a2_i formed once on the host the bin costs no division.  a1 grows and a2 falls with the bin
+// index, so "y_a < 0.1" and "y_b >= 1e-3" are index ranges [.., ia) and [.., ib), found once per photon energy.
+//
+// Noise sums  sum_{i >= m} noise_i(x) W[z][i]  for up to four zones (rows beyond nzn are not read).
 __device__ __forceinline__ void sig_noise_zones(const Params &p, double x, int m, const int *zi, int nzn, double (&ee)[4])
 {
     const int N = p.num_nt;
@@ -492,12 +489,45 @@ __device__ __forceinline__ void sig_noise_zones(const Params &p, double x, int m
     const double *w2 = p.sig_W + (size_t)zi[nzn > 2 ? 2 : 0] * N, *w3 = p.sig_W + (size_t)zi[nzn > 3 ? 3 : 0] * N;
     double e0 = 0, e1 = 0, e2 = 0, e3 = 0;
     const double inv_x = 1.0 / x;
-    for (int i = m; i < N - 1; i++) {
-        const double q = kn_noise_bin(p, i, x, inv_x);
-        e0 = fma(q, w0[i], e0); e1 = fma(q, w1[i], e1); e2 = fma(q, w2[i], e2); e3 = fma(q, w3[i], e3);
+    int ia, ib;
+    {   // ia = first bin with a1_i x >= 0.1 ; ib = first bin with a2_i x < 1e-3
+        int lo = m, hi = N - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a1[mid] * x < 0.1) lo = mid + 1; else hi = mid; }
+        ia = lo;
+        lo = m; hi = N - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a2[mid] * x < 1.e-3) hi = mid; else lo = mid + 1; }
+        ib = lo;
+    }
+    // bins [m, i_fast): the full expressions (few bins: the lowest-gamma ones and those just above the branch switch)
+    const int i_fast = (ia > ib) ? ia : ib;
+    int i = m;
+    for (; i < i_fast && i < N - 1; i++) {
+        const double yb = p.kn_a2[i] * x;
+        double q;
+        if (i >= ib) {
+            const double s = 1.0 + yb, e = (s - 1.0) - yb;
+            q = -(p.kn_cb[i] * inv_x) * (e * fma(0.125, yb, 1.0));
+        } else q = -(p.kn_pref[i] * kn_eta(yb));
+        if (i < ia) q = q + p.kn_pref[i] * kn_eta(p.kn_a1[i] * x);
+        e0 = fma(q, w0[i], e0);
+        if (nzn > 1) e1 = fma(q, w1[i], e1);
+        if (nzn > 2) e2 = fma(q, w2[i], e2);
+        if (nzn > 3) e3 = fma(q, w3[i], e3);
+    }
+    // bins [i_fast, N-1): b side only, division-free, branch-free
+    const double *a2 = p.kn_a2, *cb = p.kn_cb;
+    for (; i < N - 1; i++) {
+        const double yb = c2d_ldg(a2 + i) * x;
+        const double s = 1.0 + yb, e = (s - 1.0) - yb;
+        const double q = -(c2d_ldg(cb + i) * inv_x) * (e * fma(0.125, yb, 1.0));
+        e0 = fma(q, c2d_ldg(w0 + i), e0);
+        if (nzn > 1) e1 = fma(q, c2d_ldg(w1 + i), e1);
+        if (nzn > 2) e2 = fma(q, c2d_ldg(w2 + i), e2);
+        if (nzn > 3) e3 = fma(q, c2d_ldg(w3 + i), e3);
     }
     ee[0] = e0; ee[1] = e1; ee[2] = e2; ee[3] = e3;
 }
+
 // Table value for up to four zones of one photon energy, given the noise sums `ee` (zero when c.j < 0)
 __device__ __forceinline__ void comtot_table_finish(const Params &p, const SigCtx &c, const int *zi, int nzn, const double (&ee)[4],
                                                     double *comac)

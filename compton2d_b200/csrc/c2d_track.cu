@@ -240,6 +240,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                 if (sa * L <= .00001) continue;
                 const double dele = warp_shfl(segs[sc].dele, src), ew = warp_shfl(segs[sc].ew, src), rp = warp_shfl(segs[sc].rpre, src);
                 double acc = 0.0;
+                const double frac = dele / ew, inv_sa = 1.0 / sa;            // hoisted out of the trial loop (<= 1 ulp on prdep)
                 for (int t2 = 2 * lane; t2 < p.split1; t2 += 2 * kWarp) {       // trials t2, t2 + 1: one Philox call
                     uint32_t o[4];
                     philox4x32_10((uint32_t)S_src, (uint32_t)(S_src >> 32), (uint32_t)t2 >> 1, 2u + k, p.key0, p.key1, o);
@@ -248,7 +249,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                         const int t = t2 + h;
                         if (t >= p.split1 || t == l0 || t == l1 || t == l2 || t == l3) continue;
                         const double mb_ran = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
-                        const double sstar = -log(1. - mb_ran * dele / ew) / sa;
+                        const double sstar = -log(1. - mb_ran * frac) * inv_sa;
                         const double denom = sqrt(rp * rp + 2. * wm * rp * sstar + sstar * sstar);
                         acc += dele * ((wm * rp + sstar) / denom) * kCLight;
                     }
