@@ -24,7 +24,10 @@ namespace c2d {
 constexpr double kPi = 3.1415926536e0;        // general.pa:25
 constexpr double kRadCp = 3.333564097e-11;    // general.pa:24
 constexpr double kCLight = 2.9979245620e10;   // general.pa:26
-constexpr int kMaxSeg = 12;                   // zone crossings held by the fast path of one history
+#ifndef C2D_MAXSEG
+#define C2D_MAXSEG 12
+#endif
+constexpr int kMaxSeg = C2D_MAXSEG;           // zone crossings held by the fast path of one history
 constexpr int kNmuMax = 32;
 constexpr int kNlcMax = 16;
 

@@ -21,7 +21,7 @@ namespace c2d {
 
 constexpr int kSigDeg = 8;          // nodes (= coefficients) per interval
 
-__global__ void k_sigma_kn(const Params p, const double *xs, const int *ms, int n_nodes, double *Kn)
+__global__ void k_sigma_kn(const __grid_constant__ Params p, const double *xs, const int *ms, int n_nodes, double *Kn)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n_nodes * (p.num_nt - 1)) return;
@@ -29,7 +29,7 @@ __global__ void k_sigma_kn(const Params p, const double *xs, const int *ms, int 
     Kn[idx] = (i >= ms[node]) ? sigma_kn_smooth(p, i, xs[node]) : 0.0;
 }
 
-__global__ void k_sigma_prefix(const Params p, double *W, double *AB)
+__global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, double *AB)
 {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nzone) return;
@@ -50,7 +50,7 @@ __global__ void k_sigma_prefix(const Params p, double *W, double *AB)
 }
 
 constexpr int kSigZG = 4;           // zones per thread of k_sigma_nodes
-__global__ void k_sigma_nodes(const Params p, const double *W, const double *Kn, int n_nodes, double *T)
+__global__ void k_sigma_nodes(const __grid_constant__ Params p, const double *W, const double *Kn, int n_nodes, double *T)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int ngrp = (p.nzone + kSigZG - 1) / kSigZG;
@@ -89,7 +89,7 @@ __global__ void k_sigma_coef(const double *T, const double *M, long long n_inter
 }
 
 // c2d_comtot: comac for n (zone, xnu) pairs; mode 0 = bin by bin, 1 = table
-__global__ void k_comtot_query(Params p, long long n, const int *zone, const double *xnu, double *out)
+__global__ void k_comtot_query(const __grid_constant__ Params p, long long n, const int *zone, const double *xnu, double *out)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;

@@ -323,7 +323,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
 #define C2D_HIST_MINB 4
 #endif
 template <int SRC>
-__global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const Params p, long long first, long long n, long long stride)
+__global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const __grid_constant__ Params p, long long first, long long n, long long stride)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < n;
@@ -391,7 +391,7 @@ __device__ __forceinline__ void child_flight(const Params &p, Photon &P, Rng &rn
 
 // one thread per (collision, child ii): the split2 loop of imctrk2d.f:619-689.  Children that trigger
 // the 3rd split (l.639) are queued for k_split3 instead of looping split3 times in one thread.
-__global__ void __launch_bounds__(128) k_children(const Params p, const CollTask *q_in, long long n_in)
+__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const CollTask *q_in, long long n_in)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n_in * p.split2) return;
@@ -493,7 +493,7 @@ constexpr int kHistMax = 1024;
 #endif
 
 constexpr int kHistWarp = 256;      // bins of the per-warp nelectron copy of k_split3_attempts
-__global__ void __launch_bounds__(128) k_split3_attempts(const Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
+__global__ void __launch_bounds__(128) k_split3_attempts(const __grid_constant__ Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
                                                          int max_rounds, unsigned *hard, unsigned long long *hard_count)
 {
     // every warp keeps its own shared-memory copy of nelectron and flushes it by itself: no block barrier, so a warp
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(128) k_split3_attempts(const Params p, const C
 }
 
 #ifndef C2D_EMU
-__global__ void __launch_bounds__(512) k_split3_hard(const Params p, const CollTask *q3_in, const unsigned *hard, FlightTask *out,
+__global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Params p, const CollTask *q3_in, const unsigned *hard, FlightTask *out,
                                                      unsigned long long first_attempt)
 {
     __shared__ int win;
@@ -564,7 +564,7 @@ __global__ void __launch_bounds__(512) k_split3_hard(const Params p, const CollT
 #endif
 
 // one thread per accepted 3rd-split sub-child: tallies of l.657-661, then the scat_flag = 1 flight
-__global__ void __launch_bounds__(128) k_split3_flights(const Params p, const FlightTask *fl, long long n)
+__global__ void __launch_bounds__(128) k_split3_flights(const __grid_constant__ Params p, const FlightTask *fl, long long n)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;

@@ -12,6 +12,7 @@
 #define C2D_EMU 1
 #define __device__
 #define __global__
+#define __grid_constant__
 #define __host__
 #define __constant__
 #define __forceinline__ inline
