@@ -493,7 +493,10 @@ constexpr int kHistMax = 1024;
 #endif
 
 constexpr int kHistWarp = 256;      // bins of the per-warp nelectron copy of k_split3_attempts
-__global__ void __launch_bounds__(128) k_split3_attempts(const __grid_constant__ Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
+#ifndef C2D_S3_MINB
+#define C2D_S3_MINB 8
+#endif
+__global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __grid_constant__ Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
                                                          int max_rounds, unsigned *hard, unsigned long long *hard_count)
 {
     // every warp keeps its own shared-memory copy of nelectron and flushes it by itself: no block barrier, so a warp
