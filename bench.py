@@ -358,6 +358,13 @@ def our_arm(args):
     bytes_step = 68.0 * n_in + 68.0 * c["ndxout"] + 32.0 * seg + 48.0 * c["ndxout"] + (48.0 + 56.0) * c["nevents"]
     k_ms = hist_ms / max(1, args.steps)
     achieved = bytes_step / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    # DRAM traffic of the same launches: per-history figures measured with ncu (profiles/r01_traffic.json)
+    traffic = None
+    try:
+        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        traffic = tj["k_history_census_dram_bytes_per_history"] * n_in + tj["k_history_volume_dram_bytes_per_history"] * per_step
+    except Exception:
+        pass
     value = hist_all / (dev_ms * 1e-3)
     h2d = 8 * sum(int(np.asarray(P[k]).size) for k in ("kappa_tot", "eps_tot", "eps_th", "f_nt", "Pnt", "n_e", "tea",
                                                        "f_pair", "k_gg", "ewsv", "Eloss_th", "Eloss_tot", "zsurf",
@@ -374,7 +381,8 @@ def our_arm(args):
                                   "k_split3_attempts": s3_ms / args.steps, "k_split3_flights": s3f_ms / args.steps,
                                   "k_sigma_table": sig_ms / args.steps},
            "roofline": {"bound": "hbm", "kernel": "k_history", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                        "frac": achieved / hbm, "traffic": None,
+                        "frac": achieved / hbm, "traffic": traffic,
+                        "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per history x histories of the step)",
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                         "bytes_per_step": bytes_step},
            "counters": c, "clocks": clocks}
