@@ -265,7 +265,7 @@ int c2d_destroy(c2d_ctx *h)
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_f64); cudaFree(c->d_i64);
+    cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
@@ -330,6 +330,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     CU(cudaMalloc(&c->d_static, hs.size() * 8));
     CU(cudaMemcpy(c->d_static, hs.data(), hs.size() * 8, cudaMemcpyHostToDevice));
     c->h_gnt.assign(d->gnt, d->gnt + d->num_nt);
+    c->h_Eph.assign(d->E_ph, d->E_ph + d->n_vol);
     c->h_gam0 = gam0; c->h_opb = opb;
     c->h_Efield.assign(d->E_field, d->E_field + d->nphfield);
     c->h_z.assign(d->z, d->z + d->nz); c->h_r.assign(d->r, d->r + d->nr);
@@ -459,6 +460,124 @@ int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
     c->sigma_ready = false;
     CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its host arrays
     c->step_open = true;
+    return 0;
+}
+
+// == imcgen2d for the volume sources, on the device: volume_em for every zone from the live electron
+// spectrum (csrc/c2d_gen.cu), the per-zone energy budget (imcgen2d.f:280-283,291,330) and the photon budget
+// (imcgen2d.f:405-459), then everything c2d_step_begin does.  The opacity / emissivity tables never visit the host.
+int c2d_step_begin_gen(c2d_ctx *h, const c2d_gen_in *in, c2d_gen_out *out)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !in) return fail(C2D_EINVAL, "NULL argument");
+    if (!c->inited) return fail(C2D_ESTATE, "c2d_init has not been called");
+    CU(cudaSetDevice(c->device));
+    const c2d_dims &d = c->dims;
+    const int nzone = c->nzone, nv = d.n_vol;
+    if (!in->f_nt || !in->Pnt || !in->n_e || !in->tea || !in->B_field || !in->vol || !in->zsurf)
+        return fail(C2D_EINVAL, "c2d_step_begin_gen: missing per-zone input");
+    if (!(in->dt >= 0.0) || in->nst < 0) return fail(C2D_EINVAL, "dt = %g, nst = %lld", in->dt, (long long)in->nst);
+    // volume_em regenerates E_ph on every call (volume2d.f:53,96,112-113); the grid given to c2d_init must be that one
+    {
+        const double dE = std::exp(std::log(1.e20) / (double)nv);
+        double E = 1.e-10 / dE;
+        for (int i = 0; i < nv; i++) {
+            E = E * dE;
+            if (std::fabs(c->h_Eph[i] - E) > 1.e-13 * E)
+                return fail(C2D_EINVAL, "E_ph(%d) = %.17g differs from the grid volume_em generates (%.17g, volume2d.f:53,96)", i + 1, c->h_Eph[i], E);
+        }
+    }
+    {
+        unsigned long long n = 0;
+        CU(cudaMemcpyAsync(&n, c->P.counters + CNT_NDXOUT, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->n_census = (int64_t)std::min<unsigned long long>(n, (unsigned long long)c->census_cap);
+    }
+    double *T = c->d_step;
+    int rc = 0;
+    rc |= upload(c, T + c->o_fnt, in->f_nt, (size_t)nzone * d.num_nt);
+    rc |= upload(c, T + c->o_pnt, in->Pnt, (size_t)nzone * d.num_nt);
+    rc |= upload(c, T + c->o_ne, in->n_e, nzone);
+    rc |= upload(c, T + c->o_fpair, in->f_pair, nzone);
+    rc |= upload(c, T + c->o_kgg, in->k_gg, (size_t)nzone * d.n_gg);
+    rc |= upload(c, T + c->o_tbbl, in->tbbl, d.nr);
+    rc |= upload(c, T + c->o_zsurf, in->zsurf, nzone, 1.0);
+    rc |= upload(c, T + c->o_tea, in->tea, nzone);
+    if (rc) return rc;
+    // scratch: B_field | j_sy | sum_th | sum_g1
+    const size_t n_scr = (size_t)nzone * (nv + 3);
+    if (n_scr > c->gen_cap) {
+        cudaFree(c->d_gen);
+        CU(cudaMalloc(&c->d_gen, n_scr * 8));
+        c->gen_cap = n_scr;
+    }
+    double *G = c->d_gen;
+    CU(cudaMemcpyAsync(G, in->B_field, (size_t)nzone * 8, cudaMemcpyHostToDevice, c->stream));
+    GenParams q;
+    q.nzone = nzone; q.nz = d.nz; q.nr = d.nr; q.N = d.num_nt; q.nv = nv; q.rmin = d.rmin;
+    q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.E_ph = c->P.E_ph;
+    q.f_nt = T + c->o_fnt; q.n_e = T + c->o_ne; q.tea = T + c->o_tea; q.B_field = G;
+    q.j_sy = G + nzone; q.sum_th = G + nzone + (size_t)nzone * nv; q.sum_g1 = q.sum_th + nzone;
+    q.kappa_tot = T + c->o_kappa; q.eps_tot = T + c->o_epstot; q.eps_th = T + c->o_epsth;
+    c->timer_begin(4);
+    launch_volume_em(q, c->stream);
+    c->timer_end();
+    CU(cudaGetLastError());
+    std::vector<double> hs((size_t)2 * nzone);
+    CU(cudaMemcpyAsync(hs.data(), q.sum_th, (size_t)2 * nzone * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // energy and photon budget in the reference's zone order (imcgen2d.f:280-283,291,330,405-459)
+    std::vector<double> e_sy(nzone), e_th(nzone), ew(nzone);
+    std::vector<int32_t> nsv(nzone);
+    double Emiss_tot = 0.0;
+    for (int zi = 0; zi < nzone; zi++) {
+        e_sy[zi] = 1.058e-15 * in->n_e[zi] * in->dt * std::pow(in->B_field[zi], 2.0) * hs[nzone + zi] * in->vol[zi];
+        e_th[zi] = in->dt * in->zsurf[zi] * hs[zi];
+        Emiss_tot = Emiss_tot + e_sy[zi];
+    }
+    c->h_prefix.assign(nzone + 1, 0);
+    for (int zi = 0; zi < nzone; zi++) {
+        nsv[zi] = (Emiss_tot > 0.0) ? (int32_t)(0.5 * (double)in->nst * e_sy[zi] / Emiss_tot) : 0;
+        ew[zi] = (nsv[zi] > 0) ? e_sy[zi] / (double)nsv[zi] : 0.0;
+        c->h_prefix[zi + 1] = c->h_prefix[zi] + nsv[zi];
+    }
+    rc |= upload(c, T + c->o_ewsv, ew.data(), nzone);
+    rc |= upload(c, T + c->o_elth, e_th.data(), nzone);
+    rc |= upload(c, T + c->o_eltot, e_sy.data(), nzone);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_prefix, c->h_prefix.data(), (size_t)(nzone + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_f64, 0, c->n_f64 * 8, c->stream));
+    CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
+    c->cur_out ^= 1;
+    c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
+    c->P.ncycle = in->ncycle; c->P.key1 = (uint32_t)in->ncycle; c->P.dt = in->dt; c->P.time = in->time;
+    c->field_done = false; c->vol_next = 0; c->surf_open = false; c->surf_total = 0;
+    c->sigma_ready = false;
+    CU(cudaStreamSynchronize(c->stream));
+    c->step_open = true;
+    if (out) {
+        if (out->nsv) memcpy(out->nsv, nsv.data(), (size_t)nzone * 4);
+        if (out->ewsv) memcpy(out->ewsv, ew.data(), (size_t)nzone * 8);
+        if (out->Eloss_sy) memcpy(out->Eloss_sy, e_sy.data(), (size_t)nzone * 8);
+        if (out->Eloss_th) memcpy(out->Eloss_th, e_th.data(), (size_t)nzone * 8);
+        if (out->Eloss_tot) memcpy(out->Eloss_tot, e_sy.data(), (size_t)nzone * 8);
+        out->Emiss_tot = Emiss_tot;
+        out->n_volume = c->h_prefix.back();
+    }
+    return 0;
+}
+
+// D2H copy of the step tables the device holds (kappa_tot, eps_tot, eps_th: [zone][n_vol]); any pointer may be NULL
+int c2d_step_tables_read(c2d_ctx *h, double *kappa_tot, double *eps_tot, double *eps_th)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->nzone * c->dims.n_vol * 8;
+    if (kappa_tot) CU(cudaMemcpyAsync(kappa_tot, c->d_step + c->o_kappa, n, cudaMemcpyDeviceToHost, c->stream));
+    if (eps_tot) CU(cudaMemcpyAsync(eps_tot, c->d_step + c->o_epstot, n, cudaMemcpyDeviceToHost, c->stream));
+    if (eps_th) CU(cudaMemcpyAsync(eps_th, c->d_step + c->o_epsth, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

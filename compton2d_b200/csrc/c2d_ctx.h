@@ -42,7 +42,9 @@ struct Ctx {
     size_t i_npcen = 0, i_nel = 0, i_cnt = 0, n_i64 = 0;
     Params P{};
     std::vector<int64_t> h_prefix;
-    std::vector<double> h_f64, h_gnt, h_Efield, h_z, h_r;
+    std::vector<double> h_f64, h_gnt, h_Efield, h_z, h_r, h_Eph;
+    double *d_gen = nullptr;               // scratch of c2d_step_begin_gen
+    size_t gen_cap = 0;
     std::vector<unsigned long long> h_i64;
     // sigma(zone, E) table (sigma_mode 1, c2d_sigma.cu)
     int sig_nodes = 0;

@@ -18,6 +18,18 @@ void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn
                         double *coef, cudaStream_t st);
 void launch_comtot_query(const Params &p, long long n, const int *zone, const double *xnu, double *out, cudaStream_t st);
 
+// step prologue (c2d_gen.cu)
+struct GenParams {
+    int nzone, nz, nr, N, nv;
+    double rmin;
+    const double *z, *r, *gnt, *E_ph;
+    const double *f_nt, *n_e, *tea, *B_field;      // [zone][N], [zone] ...
+    double *j_sy;                                   // scratch [zone][nv]
+    double *kappa_tot, *eps_tot, *eps_th;           // step tables [zone][nv]
+    double *sum_th, *sum_g1;                        // [zone] raw thermalised emissivity sum, sum_g_1
+};
+void launch_volume_em(const GenParams &q, cudaStream_t st);
+
 // Fokker-Planck (c2d_fp.cu)
 struct FpParams;
 }  // namespace c2d

@@ -108,6 +108,36 @@ class Compton2d:
         self.ncycle = int(ncycle)
         self.n_volume = int(nsv_a.sum()) if nsv_a is not None else 0
 
+    def imcgen2d_device(self, *, ncycle, time, dt, nst, f_nt, Pnt, n_e, tea, B_field, vol, zsurf, f_pair=None, k_gg=None,
+                        tbbl=None):
+        """== imcgen2d for the volume sources with volume_em on the device (volume2d.f:10-394, imcgen2d.f:203-459): the
+        opacity / emissivity tables are built from the live electron spectrum in HBM and never visit the host.  Returns
+        dict(nsv, ewsv, Eloss_sy, Eloss_th, Eloss_tot, Emiss_tot) -- what the reference leaves in COMMON."""
+        nzn = self.nzone
+        a = dict(f_nt=_d(f_nt, nzn * self.num_nt, "f_nt"), Pnt=_d(Pnt, nzn * self.num_nt, "Pnt"), n_e=_d(n_e, nzn, "n_e"),
+                 tea=_d(tea, nzn, "tea"), B_field=_d(B_field, nzn, "B_field"), vol=_d(vol, nzn, "vol"), zsurf=_d(zsurf, nzn, "zsurf"),
+                 f_pair=_d(f_pair, nzn, "f_pair"), k_gg=_d(k_gg, nzn * self.n_gg, "k_gg"), tbbl=_d(tbbl, self.nr, "tbbl"))
+        gi = _l.GenIn(ncycle=int(ncycle), time=float(time), dt=float(dt), nst=int(nst))
+        for k, v in a.items():
+            setattr(gi, k, _p(v))
+        out = dict(nsv=np.zeros(nzn, np.int32), ewsv=np.zeros(nzn), Eloss_sy=np.zeros(nzn), Eloss_th=np.zeros(nzn),
+                   Eloss_tot=np.zeros(nzn))
+        go = _l.GenOut()
+        go.nsv = out["nsv"].ctypes.data_as(_l.ip)
+        for k in ("ewsv", "Eloss_sy", "Eloss_th", "Eloss_tot"):
+            setattr(go, k, _p(out[k]))
+        _l.check(self.L.c2d_step_begin_gen(self.h, C.byref(gi), C.byref(go)))
+        self.ncycle = int(ncycle)
+        self.n_volume = int(go.n_volume)
+        out["Emiss_tot"] = go.Emiss_tot
+        return out
+
+    def step_tables(self):
+        """-> dict(kappa_tot, eps_tot, eps_th) [zone][n_vol]: the step tables as the device holds them."""
+        t = {k: np.zeros((self.nzone, self.n_vol)) for k in ("kappa_tot", "eps_tot", "eps_th")}
+        _l.check(self.L.c2d_step_tables_read(self.h, t["kappa_tot"].ctypes.data, t["eps_tot"].ctypes.data, t["eps_th"].ctypes.data))
+        return t
+
     def imcfield2d(self):
         """== field_calc (imcfield2d.f:57-148): re-track this GPU's census bank."""
         _l.check(self.L.c2d_imcfield(self.h))

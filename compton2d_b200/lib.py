@@ -34,6 +34,16 @@ class StepIn(C.Structure):
         [("nsv", ip)] + [(n, dp) for n in ("ewsv", "Eloss_th", "Eloss_tot", "zsurf", "tbbl")]
 
 
+class GenIn(C.Structure):
+    _fields_ = [("ncycle", C.c_int), ("time", C.c_double), ("dt", C.c_double), ("nst", C.c_int64)] + \
+        [(n, dp) for n in ("f_nt", "Pnt", "n_e", "tea", "B_field", "vol", "zsurf", "f_pair", "k_gg", "tbbl")]
+
+
+class GenOut(C.Structure):
+    _fields_ = [("nsv", ip)] + [(n, dp) for n in ("ewsv", "Eloss_sy", "Eloss_th", "Eloss_tot")] + \
+        [("Emiss_tot", C.c_double), ("n_volume", C.c_int64)]
+
+
 class SurfIn(C.Structure):
     _fields_ = [("star_switch", C.c_int)] + [(n, ip) for n in ("nsurfi", "nsurfo", "nsurfu", "nsurfl")] + \
         [(n, dp) for n in ("ewsurfi", "ewsurfo", "ewsurfu", "ewsurfl", "tbbi", "tbbo", "tbbu", "tbbl")] + \
@@ -72,7 +82,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
-           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf"]
+           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read"]
 
 _lib = None
 
@@ -99,6 +109,8 @@ def load():
     L.c2d_destroy.argtypes = [vp]
     L.c2d_step_begin.argtypes = [vp, C.POINTER(StepIn)]
     L.c2d_imcfield.argtypes = [vp]
+    L.c2d_step_begin_gen.argtypes = [vp, C.POINTER(GenIn), C.POINTER(GenOut)]
+    L.c2d_step_tables_read.argtypes = [vp, vp, vp, vp]
     L.c2d_imcvol.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.c2d_sync.argtypes = [vp]
     L.c2d_surf_begin.argtypes = [vp, C.POINTER(SurfIn)]

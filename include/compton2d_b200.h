@@ -86,6 +86,27 @@ typedef struct {
     const double *tbbl;               /* [nr] lower-boundary temperature of the current time interval tbbl(k,ti) */
 } c2d_step_in;
 
+/* The step prologue on the device: instead of the finished tables of c2d_step_in, hand over the plasma
+ * state and let the device run volume_em (volume2d.f:10-394, the terms that reach an output: synchrotron emissivity and
+ * self-absorption from the live electron spectrum) plus the volume-source budget of imcgen2d (imcgen2d.f:280-283,291,
+ * 330,405-459).  ep_switch = 0 (B_field as given); the > 10 nst bias cap (imcgen2d.f:491-517) cannot trigger for volume
+ * sources alone.  c2d_dims.E_ph must be the grid volume_em generates (1e-10 (1e20)^(i/n_vol) keV). */
+typedef struct {
+    int ncycle;
+    double time, dt;
+    int64_t nst;                      /* reader.f nst: particles per photon cycle; nsv = 0.5 nst Eloss_tot / sum(Eloss_tot) */
+    const double *f_nt, *Pnt;         /* [zone][num_nt] */
+    const double *n_e, *tea, *B_field, *vol, *zsurf;   /* [zone] */
+    const double *f_pair, *k_gg, *tbbl;               /* as in c2d_step_in (may be NULL) */
+} c2d_gen_in;
+
+typedef struct {
+    int32_t *nsv;                     /* [zone] (any pointer may be NULL) */
+    double *ewsv, *Eloss_sy, *Eloss_th, *Eloss_tot;   /* [zone] */
+    double Emiss_tot;
+    int64_t n_volume;                 /* sum(nsv) */
+} c2d_gen_out;
+
 /* Surface sources of one step (optional; BASELINE configs[2]): what r_surf_bcast / z_surf_bcast and the ring job
  * messages carry (surf_mpi.f:18-98,136,337) plus the tables file_sp builds from an external spectrum file
  * (imcsurf2d_para.f:544-685; parsing and normalisation stay on the host, compton2d_b200.spectrum.file_sp).
@@ -151,6 +172,10 @@ int c2d_version(void);
 
 /* ---- one IMC time step: same order as xec (xec2d.f:141-193) --------------------------------- */
 int c2d_step_begin(c2d_ctx *ctx, const c2d_step_in *in);   /* replaces imcgen2d's worker branch + the broadcasts */
+int c2d_step_begin_gen(c2d_ctx *ctx, const c2d_gen_in *in, c2d_gen_out *out);
+        /* == imcgen2d for the volume sources, computed on the device; replaces c2d_step_begin for the step */
+int c2d_step_tables_read(c2d_ctx *ctx, double *kappa_tot, double *eps_tot, double *eps_th);
+        /* D2H copy of the step's [zone][n_vol] tables (for COMMON copy-back / checks); pointers may be NULL */
 int c2d_imcfield(c2d_ctx *ctx);                            /* == field_calc (imcfield2d.f:57-148) on the resident bank */
 int c2d_imcvol(c2d_ctx *ctx, int64_t first, int64_t count, int64_t stride);
         /* == sum over zones of vol_calc (imcvol2d_para.f:90-414); this context tracks the volume

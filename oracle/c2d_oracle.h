@@ -140,6 +140,10 @@ void orc_trial_uniforms(const uint32_t key[2], uint64_t S, int n, double *u);
 double orc_abs_uniform(const uint32_t key[2], uint64_t S, uint32_t t, uint32_t k);
 double orc_fibran(orc_state *s);
 
+/* step prologue: emissivity / opacity tables from the live electron spectrum and the photon budget */
+void orc_volume_em(orc_state *s, int zone, double l_min);            /* volume2d.f:10-394, live (synchrotron) terms */
+void orc_imcgen_volume(orc_state *s, int nst);                         /* imcgen2d.f:203-336,405-459: Eloss_*, nsv, ewsv */
+
 /* surface sources (imcsurf2d_para.f) */
 void orc_planck(orc_state *s, double tpl);                             /* planck2d.f:1-141 */
 void orc_file_sample(orc_state *s, int spec);                          /* imcsurf2d_para.f:694-788 */

@@ -19,6 +19,8 @@
 #define PI 3.1415926536e0
 #define C_LIGHT 2.9979245620e10
 #define ZI(j, k) (((j) - 1) * s->nr + ((k) - 1))
+#define ZZ(j) (s->z[(j) - 1])
+#define RR(k) (s->r[(k) - 1])
 
 /* volume2d.f:649-668 (Numerical Recipes gammln) */
 double orc_gammln(double xx)
@@ -454,4 +456,130 @@ void orc_fp_calc(orc_state *s, int zone)
     }
 done:
     free(gamma); free(bigW); free(npos_new); free(inject_ne);
+}
+
+
+/* ------------------------------------------------------------------ step prologue */
+/* volume2d.f:676-713: exp(t) K_{1/3}(t) */
+static double expk13(double t)
+{
+    const double c1 = (double)0.35502805f, c2 = (double)0.25881940f;   /* DATA with REAL*4 literals (l.686) */
+    if (t <= 1.0) {
+        double z3 = 1.5 * t;
+        const double zs = pow(z3, 0.3333333333333333e0);
+        const double z = zs * zs;
+        z3 = z3 * z3;
+        const double f1 = 1.0 + z3 / 6.0 * (1.0 + z3 / 30.0 * (1.0 + z3 / 56.0));
+        const double f2 = z * (1.0 + z3 / 12.0 * (1.0 + z3 / 42.0 * (1.0 + z3 / 90.0)));
+        return exp(t) * PI * 1.7320508e0 / zs * (c1 * f1 - c2 * f2);
+    }
+    const double z = 1.0 / (72.0 * t);
+    const double poly = 1.0 - 5.0 * z * (1.0 - 38.5 * z);
+    return sqrt(0.5 * PI / t) * poly / (1.0 + 1.0 / (1.0 + 58.0 * t * t));
+}
+/* volume2d.f:717-746: exp(t) K_{4/3}(t) */
+static double expk43(double t)
+{
+    if (t <= 1.0) {
+        const double poly = 1.0 + t * (0.9757317e0 - 7.6790616e-2 * t);
+        return 0.44648975e0 * pow(2.0 / t, 1.333333333e0) * poly;
+    }
+    const double z = 1.0 / (72.0 * t);
+    const double poly = 1.0 + 55.0 * z * (1.0 - 8.5 * z);
+    return sqrt(0.5 * PI / t) * poly * (1.0 + 1.0 / (1.0 + 50.0 * t * t));
+}
+
+/* volume2d.f:10-394 volume_em(j,k,T_keV,ne_local,B,l_min): only the terms that reach an output.  Since the 2009-2011
+ * edits (l.330-341) kappa_tot = kappa_sy and the emission CDF holds synchrotron only; bremsstrahlung, cyclotron and
+ * pair annihilation are computed by the reference and discarded (Eloss_cy only goes to the log).  Outputs: E_ph,
+ * kappa_tot, eps_tot, eps_th of the zone and the raw thermalised emissivity sum in Eloss_th (imcgen2d scales it). */
+void orc_volume_em(orc_state *s, int zone, double l_min)
+{
+    const int N = s->num_nt, nv = s->n_vol;
+    const int j = (zone - 1) / s->nr + 1, k = zone - s->nr * (j - 1), zi = ZI(j, k);
+    const double T_keV = s->tea[zi], ne_local = s->n_e[zi], B = s->B_field[zi];
+    const double *f = s->f_nt + (size_t)zi * N, *gnt = s->gnt;
+    const double ee = 4.803e-10, em = 9.109e-28, sigmaT = 6.6524616e-25;
+    const double nu_b = ee * B / (2 * PI * em * C_LIGHT);
+    const double Ub = pow(B, 2.0) / (8.0 * PI);
+    const double face = pow(3.0, 1.5) * sigmaT * C_LIGHT * Ub / (PI * nu_b);
+    const double dE = exp(log(1.e20) / (double)nv);
+    const double kappa_C = 6.65e-25 * ne_local;
+    const double nu_p = 9.e3 * sqrt(ne_local);
+    double *gamma0 = (double *)malloc(sizeof(double) * 2 * (size_t)N), *gamp = gamma0 + N;
+    double *P = (double *)malloc(sizeof(double) * 2 * (size_t)nv), *P_th = P + nv;
+    double P_sum = 0., sum_th = 0., E = 1.e-10 / dE;
+    int i, i2;
+    for (i = 0; i < N; i++) { gamma0[i] = gnt[i] + 1.0; gamp[i] = gamma0[i] * sqrt(pow(gamma0[i], 2.0) - 1.0); }
+    s->Eloss_th[zi] = 0.;
+    for (i = 1; i <= nv; i++) {
+        double j_sy, kappa_sy, nu;
+        E = E * dE;
+        s->E_ph[i - 1] = E;
+        nu = 2.41487e17 * E;
+        if (nu <= nu_p) { j_sy = 0.; kappa_sy = 0.; }
+        else {
+            double sum = 0., sum_k = 0.;
+            for (i2 = 1; i2 <= N - 1; i2++) {
+                const double facg = 3.0 * pow(gamma0[i2 - 1], 2.0) * nu_b;
+                const double tt = nu / facg;
+                double es;
+                if (tt < 1.0e4) {
+                    const double eq43 = expk43(tt), eq13 = expk13(tt);
+                    const double ff = tt * tt * (eq43 * eq13 - (double)0.6f * tt * (eq43 - eq13) * (eq43 + eq13));
+                    es = face * ff * exp(-2.0 * tt);
+                } else es = 0.0;
+                const double sd = f[i2 - 1] * es, sd_k = gamp[i2 - 1] * es;
+                sum = sum + (gnt[i2] - gnt[i2 - 1]) * sd;
+                sum_k = sum_k + (f[i2 - 1] / gamp[i2 - 1] - f[i2] / gamp[i2]) * sd_k;
+            }
+            j_sy = sum * ne_local / (4.0 * PI);
+            kappa_sy = sum_k * ne_local / (8.0 * PI * em * (nu * nu));
+        }
+        if (kappa_sy < 0.) kappa_sy = -1.0 * kappa_sy;
+        s->kappa_tot[(size_t)zi * nv + (i - 1)] = kappa_sy;
+        if (kappa_sy < fmax(1.0 / l_min, 1e1 * kappa_C)) {
+            P_sum = P_sum + j_sy * E * (dE - 1.0);
+        } else {
+            const double x = E / T_keV, tau_tot = kappa_sy * l_min;
+            double j_th = (x < 1.e2) ? 1.47e-47 * (nu * nu * nu) / (exp(x) - 1.0) : 1.e-50;
+            if (tau_tot < 5.e1) j_th = j_th * (1.0 - exp(-tau_tot));
+            sum_th = sum_th + j_th * E * (dE - 1.0);
+            s->Eloss_th[zi] = s->Eloss_th[zi] + j_th * E * (dE - 1.0);
+        }
+        P[i - 1] = P_sum;
+        P_th[i - 1] = sum_th;
+    }
+    for (i = 0; i < nv; i++) {
+        s->eps_tot[(size_t)zi * nv + i] = (P_sum > 1.e-50) ? P[i] / P_sum : 0.;
+        s->eps_th[(size_t)zi * nv + i] = (sum_th > 1.e-50) ? P_th[i] / sum_th : 0.;
+    }
+    free(gamma0); free(P);
+}
+
+/* imcgen2d.f:203-336 (per-zone energy budget; the emission is synchrotron only, l.330) and l.405-459 (photon budget).
+ * ep_switch = 0 (B_field as given).  Fills kappa_tot, eps_*, E_ph, Eloss_sy, Eloss_th, Eloss_tot, nsv, ewsv. */
+void orc_imcgen_volume(orc_state *s, int nst)
+{
+    const int N = s->num_nt;
+    double Emiss_tot = 0.;
+    for (int j = 1; j <= s->nz; j++)
+        for (int k = 1; k <= s->nr; k++) {
+            const int zi = ZI(j, k), zone = k + s->nr * (j - 1);
+            const double dzz = (j == 1) ? ZZ(1) : ZZ(j) - ZZ(j - 1), drr = (k == 1) ? RR(1) - s->rmin : RR(k) - RR(k - 1);
+            const double l_min = fmin(dzz, drr);
+            const double *f = s->f_nt + (size_t)zi * N;
+            orc_volume_em(s, zone, l_min);
+            double sum_g_1 = 0.;
+            for (int i = 1; i <= N - 1; i++)
+                sum_g_1 = sum_g_1 + (pow(s->gnt[i - 1] + 1.0, 2.0) - 1.0) * f[i - 1] * (s->gnt[i] - s->gnt[i - 1]);
+            s->Eloss_sy[zi] = 1.058e-15 * s->n_e[zi] * s->dt * pow(s->B_field[zi], 2.0) * sum_g_1 * s->vol[zi];
+            s->Eloss_th[zi] = s->dt * s->zsurf[zi] * s->Eloss_th[zi];
+            s->Eloss_tot[zi] = s->Eloss_sy[zi];
+            Emiss_tot = Emiss_tot + s->Eloss_tot[zi];
+        }
+    for (int zi = 0; zi < s->nzone; zi++) {
+        s->nsv[zi] = (int)(0.5 * nst * s->Eloss_tot[zi] / Emiss_tot);
+        s->ewsv[zi] = (s->nsv[zi] > 0) ? s->Eloss_tot[zi] / (double)s->nsv[zi] : 0.;
+    }
 }

@@ -55,6 +55,8 @@ def lib():
         L.orc_comtot.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double]
         L.orc_vol_calc.argtypes = [C.c_void_p, C.c_int]
         L.orc_field_calc.argtypes = [C.c_void_p]
+        L.orc_volume_em.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.orc_imcgen_volume.argtypes = [C.c_void_p, C.c_int]
         L.orc_z_surf_calc.argtypes = [C.c_void_p, C.c_int]
         L.orc_r_surf_calc.argtypes = [C.c_void_p, C.c_int]
         L.orc_file_sp.restype = C.c_int
@@ -134,6 +136,9 @@ class Oracle:
     def vol_all(self):
         for zone in range(1, self.dims["nzone"] + 1):
             self.vol_calc(zone)
+
+    def imcgen_volume(self, nst):
+        self.L.orc_imcgen_volume(self.p, int(nst))
 
     def surf_all(self):
         """imcsurf2d (imcsurf2d_para.f:1-225): all z rings, then all r rings."""

@@ -3,6 +3,7 @@
 EmuDim blockIdx, threadIdx, blockDim, gridDim;
 #include "../../compton2d_b200/csrc/c2d_track.cu"
 #include "../../compton2d_b200/csrc/c2d_sigma.cu"
+#include "../../compton2d_b200/csrc/c2d_gen.cu"
 
 namespace c2d {
 template <int SRC> static void run_hist(const Params &p, long long first, long long n, long long stride)
@@ -53,6 +54,13 @@ void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn
     run_grid((long long)n_nodes * ((p.nzone + kSigZG - 1) / kSigZG), [&] { k_sigma_nodes(p, W, Kn, n_nodes, T); });
     const long long ni = (long long)p.nzone * (n_nodes / kSigDeg);
     run_grid(ni, [&] { k_sigma_coef(T, M, ni, coef); });
+}
+void launch_volume_em(const GenParams &q, cudaStream_t)
+{
+    run_grid((long long)q.nzone * q.nv, [&] { k_volume_sy(q); });
+    blockDim.x = 64;
+    for (int b = 0; b < (q.nzone + 63) / 64; b++)
+        for (unsigned t = 0; t < 64; t++) { blockIdx.x = (unsigned)b; threadIdx.x = t; k_volume_cdf(q); }
 }
 void launch_comtot_query(const Params &p, long long n, const int *zone, const double *xnu, double *out, cudaStream_t)
 {

@@ -90,6 +90,31 @@ def test_surface_sources(emu, kind):
     g.close()
 
 
+@pytest.mark.parametrize("name,cyc", [("small", 1), ("dense", 2)])
+def test_step_prologue_on_device_matches_reference_binary(emu, name, cyc):
+    """c2d_step_begin_gen (volume_em + volume-source budget, csrc/c2d_gen.cu) against the binary's own tables, then a
+    tracked step from those device-built tables equals the step from the host-supplied ones."""
+    from gen_util import NST, check_against_binary, plasma_from_snapshot
+    from golden_util import Golden
+    from parity_util import gpu_step, make_gpu
+    g = Golden(name)
+    P, inp, ref = plasma_from_snapshot(g, cyc)
+    gpu = make_gpu(P)
+    out = gpu.imcgen2d_device(ncycle=cyc, nst=NST[name], f_pair=P["f_pair"], k_gg=P["k_gg"], tbbl=P["tbbl"], **inp)
+    check_against_binary(out, gpu.step_tables(), ref)
+    gpu.imcvol2d(); gpu.sync()
+    t_dev = gpu.tallies()
+    gpu.close()
+    # the same step from host tables (the binary's): identical integer tallies
+    P2 = dict(P, kappa_tot=ref["kappa_tot"], eps_tot=ref["eps_tot"], eps_th=ref["eps_th"], nsv=ref["nsv"], ewsv=ref["ewsv"],
+              Eloss_th=ref["Eloss_th"], Eloss_tot=ref["Eloss_tot"], f_nt=inp["f_nt"], Pnt=inp["Pnt"], n_e=inp["n_e"], tea=inp["tea"],
+              dt=inp["dt"], time=inp["time"])
+    gpu = make_gpu(P2)
+    t_host = gpu_step(gpu, P2, cyc, field=False)
+    gpu.close()
+    assert np.array_equal(t_dev["npcen"], t_host["npcen"]) and t_dev["counters"]["ndxout"] == t_host["counters"]["ndxout"]
+
+
 def test_census_export_import_roundtrip(emu):
     """write_record / read_record contract (census2d.f): export -> import into a fresh context -> same step."""
     from parity_util import gpu_step, make_gpu

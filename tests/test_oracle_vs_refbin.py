@@ -199,3 +199,27 @@ def test_host_file_sp_matches_reference_binary():
     for k, ref in (("F_file", s1.f_file), ("P_file", s1.p_file), ("a1", s1.a1), ("I_file", s1.i_file)):
         r = np.abs(t[k][: n - 1] - ref[: n - 1]) / np.maximum(np.abs(ref[: n - 1]), 1e-300)
         assert r.max() < 1e-11, (k, r.max())
+
+
+# ------------------------------------------------------------------------------------------ step prologue
+@pytest.mark.parametrize("name,cyc", [(n, c) for n in ("small", "annulus", "dense") for c in (1, 2)])
+def test_volume_em_and_budget_match_reference_binary(name, cyc):
+    """volume_em (volume2d.f:10-394) + the volume-source budget of imcgen2d (imcgen2d.f:203-459) from the plasma state the
+    master held at the top of the cycle: emission CDFs, opacity, energy loss and photon counts as the binary computed them."""
+    from gen_util import NST, plasma_from_snapshot, rel
+    g = Golden(name)
+    P, inp, ref = plasma_from_snapshot(g, cyc)
+    A = g.snap(f"c{cyc}_A")
+    o = new_oracle(A)
+    load_snapshot(o, A)
+    o.a.zsurf = inp["zsurf"]; o.a.vol = inp["vol"]
+    o["dt"] = inp["dt"]
+    o.imcgen_volume(NST[name])
+    nzone = P["nzone"]
+    a = o.a
+    assert np.array_equal(a.E_ph[:400], P["E_ph"])
+    assert np.array_equal(a.nsv[:nzone], ref["nsv"])
+    for k in ("ewsv", "Eloss_tot", "Eloss_th"):
+        assert rel(getattr(a, k)[:nzone], ref[k]) < 1e-13, k
+    for k in ("kappa_tot", "eps_tot", "eps_th"):
+        assert rel(getattr(a, k)[: nzone * 400], ref[k]) < 1e-13, k
