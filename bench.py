@@ -165,9 +165,14 @@ def reference_arm(args):
 
 
 def workload_config(args, ref=False):
-    return {"workload": "BASELINE configs[1]: Mrk 421-style SSC blob, 16x16 zones, 100 photon energy groups, "
-                        "1e7 volume sources/step/GPU (nst=2e7) + census, split1/2/3=1000/1000/300, pair_switch=0",
-            "nz": 16, "nr": 16, "groups": 100, "nst_per_gpu": args.nst, "split": [1000, 1000, 300, 10],
+    if getattr(args, "workload", "c1") == "c3":
+        name = ("BASELINE configs[3]: synthetic grid 64x64 zones, 200 photon energy groups, 1.25e8 volume sources/step/GPU "
+                "(nst=2.5e8; 1e9 histories/step on 8 GPUs) + census, split1/2/3=1000/1000/300, pair_switch=0")
+    else:
+        name = ("BASELINE configs[1]: Mrk 421-style SSC blob, 16x16 zones, 100 photon energy groups, "
+                "1e7 volume sources/step/GPU (nst=2e7) + census, split1/2/3=1000/1000/300, pair_switch=0")
+    return {"workload": name,
+            "nz": args.nz, "nr": args.nr, "groups": args.groups, "nst_per_gpu": args.nst, "split": [1000, 1000, 300, 10],
             "sigma_mode": args.sigma_mode, "l2": "inputs larger than L2 (census bank >= 0.6 GB/step after warm-up)",
             "step": "imcfield2d + imcvol2d + scattering queue + tally all-reduce"}
 
@@ -264,7 +269,7 @@ def our_arm(args):
         dist = None
 
     # weak scaling: nst grows with the GPU count, every rank tracks h = rank (mod world)
-    P = make_problem(nz=16, nr=16, nst=args.nst * world, ngroups=100)
+    P = make_problem(nz=args.nz, nr=args.nr, nst=args.nst * world, ngroups=args.groups)
     per_step = int(P["nsv"].sum()) // world + 1
     cap = int(per_step * (args.steps + args.warmup + 2) * 1.1) + 1000
     g = make_gpu(P, sigma_mode=args.sigma_mode, census_capacity=cap, event_capacity=max(per_step // 2, 1000),
@@ -421,7 +426,12 @@ def main():
     ap.add_argument("--cpu-nst", type=int, default=30_000, help="nst of the bounded cpu_baseline sample (cycles 1-2, one core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp", action="store_true", help="skip the Fokker-Planck zone-steps/s leg")
+    ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
+                    help="c1 = BASELINE configs[1] (the bench line); c3 = configs[3] shape, 64x64 zones x 200 groups, 1.25e8 sources/GPU")
     args = ap.parse_args()
+    args.nz, args.nr, args.groups = (64, 64, 200) if args.workload == "c3" else (16, 16, 100)
+    if args.workload == "c3" and args.nst == 20_000_000:
+        args.nst = 250_000_000
     if args.impl == "reference":
         reference_arm(args)
     else:
