@@ -1179,3 +1179,51 @@ void orc_step_zero_worker(orc_state *s)
     memset(s->Ed_ref, 0, sizeof(double) * s->nr);
     s->incounter = s->outcounter = s->cmcount1 = s->cmcount2 = s->lkcount = 0;
 }
+
+
+/* ------------------------------------------------------------------ event-list reduction */
+/* postprocessing/plcm.c:384-450: Doppler boost into the observer frame (bulk Lorentz factor gam_bulk along +z),
+ * light-travel-time correction to the plane through r = rmax, then binning in arrival time (st_max bins of width dt
+ * from t_offset), observer-frame direction cosine and -- possibly overlapping -- energy bands.
+ * events: 7 doubles per record (t_bound, xnu, ew, rpre, zpre, wmu, phi), imcleak2d.f:171,181.
+ * Accumulators [k][n][l] (time, mu, band), added to (not zeroed). */
+void orc_lightcurve(int64_t n_ev, const double *ev, double gam_bulk, double rmax, double dt, double t_offset, int st_max,
+                    int n_mu, const double *mu0, const double *mu1, int n_bins, const double *E0, const double *E1,
+                    double *sum_ew, double *sum_ew2, int64_t *count)
+{
+    for (int64_t q = 0; q < n_ev; q++) {
+        double t_bound = ev[7 * q], E = ev[7 * q + 1], ew = ev[7 * q + 2], r = ev[7 * q + 3], z = ev[7 * q + 4];
+        double mu = ev[7 * q + 5], phi = ev[7 * q + 6], betta, doppler, cdt, time;
+        int k, n, l;
+        mu = -mu;
+        betta = sqrt(1. - 1. / (gam_bulk * gam_bulk));
+        doppler = gam_bulk * (1. + mu * betta);
+        t_bound = (t_bound - betta * z * 3.33333333e-11) / doppler;
+        E = E * doppler;
+        ew = ew * doppler;
+        mu = (mu + betta) / (1. + mu * betta);
+        cdt = z * mu / gam_bulk + sqrt(1. - mu * mu) * (rmax - r * cos(phi));
+        time = t_bound + 3.33333333e-11 * cdt;
+        time -= t_offset;
+        if (time < 0.) continue;
+        /* t0[k] = k dt accumulated by repeated addition in plcm.c:243-247 */
+        {
+            double t0 = 0.;
+            for (k = 0; k < st_max; k++) {
+                const double t1 = t0 + dt;
+                if (time >= t0 && time < t1) break;
+                t0 = t1;
+            }
+        }
+        for (n = 0; n < n_mu; n++)
+            if (mu >= mu0[n] && mu < mu1[n]) break;
+        if (!(k < st_max && n < n_mu)) continue;
+        for (l = 0; l < n_bins; l++)
+            if (E >= E0[l] && E < E1[l]) {
+                const size_t at = ((size_t)k * n_mu + n) * n_bins + l;
+                sum_ew[at] += ew;
+                sum_ew2[at] += (ew * ew);
+                count[at]++;
+            }
+    }
+}

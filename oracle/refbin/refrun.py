@@ -67,6 +67,38 @@ def stage_reference(ref: Path = REF_DEFAULT) -> Path | None:
 
 
 # --------------------------------------------------------------------------- inputs
+def build_plcm(ref: Path = REF_DEFAULT) -> Path | None:
+    """Compile the reference's own light-curve post-processor (postprocessing/plcm.c, K&R C) from the source where it lies
+    into oracle/_ref/plcm.  Only where the reference tree exists; the binary travels to the GPU box."""
+    src = ref / "postprocessing" / "plcm.c"
+    out = REFDIR / "plcm"
+    if out.exists() and (not src.exists() or out.stat().st_mtime >= src.stat().st_mtime):
+        return out
+    if not src.exists():
+        return None
+    REFDIR.mkdir(parents=True, exist_ok=True)
+    subprocess.check_call(["gcc", "-std=gnu89", "-w", "-O1", "-include", str(HERE / "gets_shim.h"), "-o", str(out), str(src), "-lm"])
+    return out
+
+
+def run_plcm(events, answers: str, workdir: Path, infile: str = "p001_evb.dat") -> dict:
+    """Run oracle/_ref/plcm on an event list ([n,7] array, written in the reference's format 105 of imcleak2d.f:181) with
+    the given stdin answers (the content of a postprocessing/*_lc.input file).  -> {file name: text} of what it wrote."""
+    import numpy as np
+    exe = REFDIR / "plcm"
+    workdir.mkdir(parents=True, exist_ok=True)
+    with open(workdir / infile, "w") as f:
+        for r in np.asarray(events, float).reshape(-1, 7):
+            f.write(" ".join("%14.7E" % v for v in r) + "\n")
+    before = set(os.listdir(workdir))
+    # (bytes, not text: plcm echoes file-name buffers it filled with strncpy and never terminated)
+    r = subprocess.run(f"ulimit -s unlimited; exec {exe}", shell=True, cwd=workdir, input=answers.encode(), capture_output=True,
+                       timeout=600, executable="/bin/bash")
+    if r.returncode != 0:
+        raise RuntimeError(f"plcm failed ({r.returncode}): {r.stdout[-500:]!r} {r.stderr[-500:]!r}")
+    return {n: (workdir / n).read_text() for n in sorted(set(os.listdir(workdir)) - before)}
+
+
 def _records(path: Path):
     out = []
     for line in path.read_text().splitlines():
