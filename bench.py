@@ -248,6 +248,26 @@ def tally_bench(g, hbm, n_events=100_000_000):
             "sorted_by_zone_ms": ms_s}
 
 
+MRK421_LC = "p001_evb.dat\n33\n1e16\nlc07_ev0.dat\n1\nlc07_ev0.dat\n0.99944\n0.99964\n7e2\n0\n7e4\n7\n" + \
+    "".join(f"{a}\n{b}\n1\n0\n" for a, b in ((1e-3, 3e-3), (2, 4), (9, 15), (15, 20), (20, 60), (5e5, 5e7), (1e9, 1e10)))
+
+
+def lc_bench(g, hbm, n_events=100_000_000):
+    """Event-list reduction (csrc/c2d_lc.cu) on a generated list of escape records with the bin tables of
+    the reference's own postprocessing/mrk421_lc.input (content reproduced above): 56 algorithmic B/record."""
+    from compton2d_b200.lightcurve import lc_reduction, parse_lc_input
+    cfg = parse_lc_input(MRK421_LC)
+    out = {"kernel": "k_lc_reduce", "events": n_events, "bins": "postprocessing/mrk421_lc.input (1 mu window, 7 bands)"}
+    for label, st_max in (("shared_acc_128_time_bins", 128), ("hbm_acc_1024_time_bins", 1024)):
+        g.lc_begin(lc_reduction(cfg, st_max=st_max))
+        g.lc_bench(n_events // 10)                  # warm-up
+        best = min(g.lc_bench(n_events)[0] for _ in range(3))
+        ach = 56.0 * n_events / (best * 1e-3) / 1e9
+        out[label] = {"ms": best, "events_per_s": n_events / (best * 1e-3),
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None}}
+    return out
+
+
 # ------------------------------------------------------------------------------------------ our arm
 def our_arm(args):
     import numpy as np
@@ -396,6 +416,11 @@ def our_arm(args):
             out["tally"] = tally_bench(g, hbm)
         except Exception as e:
             out["tally"] = {"error": repr(e)[:300]}
+    if not args.no_fp and world == 1:
+        try:
+            out["lc"] = lc_bench(g, hbm)
+        except Exception as e:
+            out["lc"] = {"error": repr(e)[:300]}
     if not args.no_fp and world == 1:
         try:
             out["fp"] = fp_bench(local, hbm)

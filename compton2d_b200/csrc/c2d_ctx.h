@@ -10,6 +10,7 @@ namespace c2d {
 int fail(int code, const char *fmt, ...);
 
 struct FpState;
+struct LcState;
 
 struct Ctx {
     int device = 0, n_sm = 0;
@@ -59,6 +60,9 @@ struct Ctx {
     // Fokker-Planck state (c2d_fp.cu)
     FpState *fp = nullptr;
     void fp_free();
+    // event-list reduction (c2d_lc.cu)
+    LcState *lc = nullptr;
+    void lc_free();
     // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3_attempts, 3 FP, 4 sigma table, 5 tally bench,
     // 6 k_split3_flights
     bool timing = false;

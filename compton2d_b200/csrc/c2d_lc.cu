@@ -1,0 +1,395 @@
+// c2d_lc.cu -- event-list reduction on the device.
+//
+// The reference writes every escaping photon as a 105-byte text line (imcleak2d.f:171,181) and turns the files into
+// science products afterwards with two C programs that share one per-photon transform and differ in their bin rules:
+//   postprocessing/plcm.c:384-450  light curves:  L(t_obs, mu_obs, band), <ew>, <ew^2> per bin
+//   postprocessing/pspt.c:249-289  SEDs:          L(E_obs, t_obs) in one viewing-angle window
+// Here the escape records never leave HBM: k_lc_reduce streams the step's records (7 doubles each, the layout
+// imcleak writes), applies the transform -- Doppler boost with the bulk Lorentz factor, light-travel-time correction to the
+// plane through r = rmax -- and bins in arrival time, observer-frame direction cosine and photon energy with the bin
+// tables of c2d_lc_config (either program's rules).  The accumulators persist across steps, as the files do.
+//
+// k_lc_reduce: one warp = 32 consecutive records (1792 contiguous bytes, fetched as 112 16-byte loads, transposed through
+// shared memory so every lane gets its own record); the next tile is in flight while the current one is processed.
+// Commits are reduced warp-level (__match_any_sync on the cell index, lane-ordered sums) and go to a per-block copy of the
+// accumulators in shared memory when the bin table fits (flushed once per block), else straight to HBM.
+// Algorithmic bytes: 56 per record (the read; the accumulators are a few kB).
+#include "c2d_ctx.h"
+
+#include <algorithm>
+#include <vector>
+
+namespace c2d {
+
+struct LcParams {
+    double gam_bulk, betta, rmax, t_offset;
+    int n_t, n_mu, n_bands, mu_closed, first_band_only;
+    const double *t_lo, *t_hi, *mu0, *mu1, *E0, *E1;     // device copies of the bin tables
+    double *sum_ew, *sum_ew2;                            // [n_t][n_mu][n_bands]
+    unsigned long long *count;
+};
+
+struct LcState {
+    LcParams q{};
+    double *d_tab = nullptr;       // [t_lo | t_hi | mu0 | mu1 | E0 | E1]
+    double *d_acc = nullptr;       // [sum_ew | sum_ew2 | count (u64)]
+    size_t cells = 0;
+    double *d_stage = nullptr;     // host-provided records
+    size_t stage_cap = 0;
+};
+
+// plcm.c:393-401 == pspt.c:257-264, then `time -= t_offset` (plcm.c:412).  Returns the observer-frame arrival time;
+// E, ew, mu are replaced by their observer-frame values.
+__host__ __device__ __forceinline__ double lc_transform(const LcParams &q, double t_bound, double &E, double &ew, double r, double z,
+                                                        double &mu, double phi)
+{
+    mu = -mu;
+    const double doppler = q.gam_bulk * (1. + mu * q.betta);
+    t_bound = (t_bound - q.betta * z * 3.33333333e-11) / doppler;
+    E = E * doppler;
+    ew = ew * doppler;
+    mu = (mu + q.betta) / (1. + mu * q.betta);
+    const double cdt = z * mu / q.gam_bulk + sqrt(1. - mu * mu) * (q.rmax - r * cos(phi));
+    double time = t_bound + 3.33333333e-11 * cdt;
+    time -= q.t_offset;
+    return time;
+}
+
+// first k with t_lo[k] <= time < t_hi[k] (plcm.c:416-420, pspt.c:282-284); both tables are nondecreasing (checked by
+// c2d_lc_begin), so the first k with t_hi[k] > time is the only candidate
+__host__ __device__ __forceinline__ int lc_time_bin(const double *t_lo, const double *t_hi, int n_t, double time)
+{
+    int lo = 0, hi = n_t;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (t_hi[mid] > time) hi = mid; else lo = mid + 1;
+    }
+    return (lo < n_t && time >= t_lo[lo]) ? lo : -1;
+}
+
+__host__ __device__ __forceinline__ int lc_mu_bin(const double *mu0, const double *mu1, int n_mu, int closed, double mu)
+{
+    for (int n = 0; n < n_mu; n++)
+        if (mu >= mu0[n] && (closed ? mu <= mu1[n] : mu < mu1[n])) return n;      // plcm.c:422-426 / pspt.c:274
+    return -1;
+}
+
+#ifndef C2D_EMU
+constexpr int kLcWarps = 8;                     // warps per block
+constexpr int kLcTileDoubles = 32 * 7;          // one warp tile: 32 records
+
+// 16-byte chunk c of the record array (n7 = 7 n doubles in total); the odd tail double is fetched alone
+__device__ __forceinline__ double2 lc_load_chunk(const double *ev, long long c, long long n7)
+{
+    const long long d = 2 * c;
+    if (d + 1 < n7) return __ldcs(reinterpret_cast<const double2 *>(ev) + c);
+    double2 v = make_double2(0., 0.);
+    if (d < n7) v.x = __ldcs(ev + d);
+    return v;
+}
+
+// warp-level pre-reduction: lanes that hit the same cell are summed in lane order (deterministic within the warp) and the
+// lowest of them commits.  cell < 0: nothing to commit
+template <bool SHARED>
+__device__ __forceinline__ void lc_commit(double *s1, double *s2, unsigned long long *cnt, int cell, double ew)
+{
+    const unsigned peers = __match_any_sync(0xffffffffu, cell);
+    const int lane = threadIdx.x & 31;
+    const bool alone = peers == (1u << lane);
+    double a = ew, b = ew * ew;
+    const unsigned crowded = __ballot_sync(0xffffffffu, !alone && cell >= 0);
+    if (crowded) {
+        double sa = 0., sb = 0.;
+        for (unsigned m = crowded; m; m &= m - 1) {                               // only lanes that share a cell are broadcast
+            const int src = __ffs(m) - 1;
+            const double v = __shfl_sync(0xffffffffu, ew, src);
+            if ((peers >> src) & 1u) { sa = sa + v; sb = sb + v * v; }
+        }
+        if (!alone) { a = sa; b = sb; }
+    }
+    if (cell >= 0 && lane == __ffs(peers) - 1) {
+        atomicAdd(s1 + cell, a);
+        atomicAdd(s2 + cell, b);
+        if (SHARED) atomicAdd(reinterpret_cast<unsigned *>(cnt) + cell, (unsigned)__popc(peers));   // 32-bit per-block counts
+        else atomicAdd(cnt + cell, (unsigned long long)__popc(peers));
+    }
+}
+
+template <bool SHARED>
+__global__ void __launch_bounds__(kLcWarps * 32) k_lc_reduce(const __grid_constant__ LcParams q, const double *__restrict__ ev,
+                                                            const unsigned long long *n_ptr, long long n_cap)
+{
+    extern __shared__ double sh[];
+    // shared layout: [tile per warp | t_lo | t_hi | mu0 | mu1 | E0 | E1 | (sum_ew | sum_ew2 | count32)]
+    double *tile = sh + (threadIdx.x >> 5) * kLcTileDoubles;
+    double *s_tlo = sh + kLcWarps * kLcTileDoubles, *s_thi = s_tlo + q.n_t;
+    double *s_mu0 = s_thi + q.n_t, *s_mu1 = s_mu0 + q.n_mu, *s_E0 = s_mu1 + q.n_mu, *s_E1 = s_E0 + q.n_bands;
+    const int cells = q.n_t * q.n_mu * q.n_bands;
+    double *a1 = SHARED ? s_E1 + q.n_bands : q.sum_ew, *a2 = SHARED ? a1 + cells : q.sum_ew2;
+    unsigned long long *ac = SHARED ? reinterpret_cast<unsigned long long *>(a2 + cells) : q.count;
+    for (int i = threadIdx.x; i < q.n_t; i += blockDim.x) { s_tlo[i] = q.t_lo[i]; s_thi[i] = q.t_hi[i]; }
+    for (int i = threadIdx.x; i < q.n_mu; i += blockDim.x) { s_mu0[i] = q.mu0[i]; s_mu1[i] = q.mu1[i]; }
+    for (int i = threadIdx.x; i < q.n_bands; i += blockDim.x) { s_E0[i] = q.E0[i]; s_E1[i] = q.E1[i]; }
+    if (SHARED) {
+        for (int i = threadIdx.x; i < 2 * cells; i += blockDim.x) a1[i] = 0.;
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) reinterpret_cast<unsigned *>(ac)[i] = 0u;
+    }
+    __syncthreads();
+
+    long long n = (long long)*n_ptr;
+    if (n > n_cap) n = n_cap;
+    const long long n7 = 7 * n, n_tiles = (n + 31) / 32;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * kLcWarps + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * kLcWarps;
+    double2 r0, r1, r2, r3;
+    r3 = make_double2(0., 0.);
+    auto fetch = [&](long long t) {                                              // 112 chunks of 16 bytes per tile
+        const long long c = t * 112 + lane;
+        r0 = lc_load_chunk(ev, c, n7); r1 = lc_load_chunk(ev, c + 32, n7); r2 = lc_load_chunk(ev, c + 64, n7);
+        if (lane < 16) r3 = lc_load_chunk(ev, c + 96, n7);
+    };
+    if (warp0 < n_tiles) fetch(warp0);
+    for (long long t = warp0; t < n_tiles; t += n_warps) {
+        double2 *t2 = reinterpret_cast<double2 *>(tile);
+        t2[lane] = r0; t2[lane + 32] = r1; t2[lane + 64] = r2;
+        if (lane < 16) t2[lane + 96] = r3;
+        __syncwarp();
+        if (t + n_warps < n_tiles) fetch(t + n_warps);                           // next tile in flight during the arithmetic
+        const double *rec = tile + 7 * lane;
+        const double t_bound = rec[0], r = rec[3], z = rec[4], phi = rec[6];
+        double E = rec[1], ew = rec[2], mu = rec[5];
+        __syncwarp();
+        bool live = t * 32 + lane < n;
+        int base = -1;
+        if (live) {
+            const double time = lc_transform(q, t_bound, E, ew, r, z, mu, phi);
+            const int k = lc_time_bin(s_tlo, s_thi, q.n_t, time);
+            const int m = lc_mu_bin(s_mu0, s_mu1, q.n_mu, q.mu_closed, mu);
+            live = k >= 0 && m >= 0;
+            base = (k * q.n_mu + m) * q.n_bands;
+        }
+        // plcm.c:441-449: every band that holds E; pspt.c:278-280: the first one only
+        if (!__any_sync(0xffffffffu, live)) continue;
+        for (int l = 0; l < q.n_bands; l++) {
+            const bool hit = live && E >= s_E0[l] && E < s_E1[l];
+            if (!__any_sync(0xffffffffu, hit)) continue;
+            lc_commit<SHARED>(a1, a2, ac, hit ? base + l : -1, ew);
+            if (hit && q.first_band_only) live = false;
+            if (!__any_sync(0xffffffffu, live)) break;
+        }
+    }
+    if (SHARED) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < cells; i += blockDim.x) {
+            const unsigned c = reinterpret_cast<unsigned *>(ac)[i];
+            if (c) { atomicAdd(q.sum_ew + i, a1[i]); atomicAdd(q.sum_ew2 + i, a2[i]); atomicAdd(q.count + i, (unsigned long long)c); }
+        }
+    }
+}
+
+// synthetic records for c2d_lc_bench: escape records of a 1e16 cm blob over ~30 light-crossing times, from a fixed hash
+__global__ void k_lc_gen(long long n, double *ev)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint64_t h = (uint64_t)i * 0x9E3779B97F4A7C15ull;
+        auto u = [&]() { h ^= h >> 29; h *= 0xBF58476D1CE4E5B9ull; h ^= h >> 32; return (double)(h >> 11) * (1.0 / 9007199254740992.0); };
+        double *e = ev + 7 * i;
+        e[0] = 1.0e7 * u();                         // t_bound [s]
+        e[1] = exp(log(1e-7) + log(1e15) * u());    // xnu [keV]
+        e[2] = 1.0e38 * (0.5 + u());                // ew [erg]
+        e[3] = 0.75e16 * sqrt(u());                 // rpre
+        e[4] = 1.0e16 * u();                        // zpre
+        e[5] = -1.0 + 2.0 * u();                    // wmu
+        e[6] = 3.1415926536 * u();                  // phi
+    }
+}
+#endif  // !C2D_EMU
+
+static int lc_launch(Ctx *c, const double *d_ev, const unsigned long long *d_n, long long n_cap, float *ms)
+{
+    LcState *s = c->lc;
+#ifdef C2D_EMU
+    (void)ms;
+    const LcParams &q = s->q;
+    long long n = std::min<long long>((long long)*d_n, n_cap);
+    for (long long i = 0; i < n; i++) {
+        const double *rec = d_ev + 7 * i;
+        double E = rec[1], ew = rec[2], mu = rec[5];
+        const double time = lc_transform(q, rec[0], E, ew, rec[3], rec[4], mu, rec[6]);
+        const int k = lc_time_bin(q.t_lo, q.t_hi, q.n_t, time), m = lc_mu_bin(q.mu0, q.mu1, q.n_mu, q.mu_closed, mu);
+        if (k < 0 || m < 0) continue;
+        for (int l = 0; l < q.n_bands; l++)
+            if (E >= q.E0[l] && E < q.E1[l]) {
+                const size_t at = ((size_t)k * q.n_mu + m) * q.n_bands + l;
+                q.sum_ew[at] += ew; q.sum_ew2[at] += ew * ew; q.count[at]++;
+                if (q.first_band_only) break;
+            }
+    }
+    return 0;
+#else
+    const LcParams &q = s->q;
+    const size_t tab = (size_t)kLcWarps * kLcTileDoubles + 2 * (size_t)q.n_t + 2 * (size_t)q.n_mu + 2 * (size_t)q.n_bands;
+    const size_t priv = 2 * s->cells + (s->cells + 1) / 2;
+    const bool shared = (tab + priv) * 8 <= 72 * 1024;                           // 3 blocks / SM with the private copy
+    const size_t smem = (tab + (shared ? priv : 0)) * 8;
+    if (smem > 200 * 1024) return fail(C2D_EINVAL, "light-curve bin tables need %zu bytes of shared memory", smem);
+    auto kern = shared ? k_lc_reduce<true> : k_lc_reduce<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(C2D_ECUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kLcWarps * 32, smem);
+    const int grid = c->n_sm * std::max(1, per_sm);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (ms) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, c->stream); }
+    kern<<<grid, kLcWarps * 32, smem, c->stream>>>(q, d_ev, d_n, n_cap);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(C2D_ECUDA, "k_lc_reduce launch: %s", cudaGetErrorString(e));
+    if (ms) {
+        cudaEventRecord(e1, c->stream);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(ms, e0, e1);
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+    return 0;
+#endif
+}
+
+void Ctx::lc_free()
+{
+    if (!lc) return;
+    cudaFree(lc->d_tab); cudaFree(lc->d_acc); cudaFree(lc->d_stage);
+    delete lc;
+    lc = nullptr;
+}
+
+}  // namespace c2d
+
+using namespace c2d;
+
+#define CUL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) \
+    return fail(C2D_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); } while (0)
+
+extern "C" int c2d_lc_begin(c2d_ctx *h, const c2d_lc_config *cfg)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (!cfg) return fail(C2D_EINVAL, "NULL config");
+    if (cfg->n_t < 1 || cfg->n_mu < 1 || cfg->n_bands < 1 || !cfg->t_lo || !cfg->t_hi || !cfg->mu0 || !cfg->mu1 || !cfg->E0 || !cfg->E1)
+        return fail(C2D_EINVAL, "light-curve bin tables: n_t %d n_mu %d n_bands %d or a NULL table", cfg->n_t, cfg->n_mu, cfg->n_bands);
+    if (!(cfg->gam_bulk >= 1.0)) return fail(C2D_EINVAL, "gam_bulk = %g", cfg->gam_bulk);
+    for (int k = 1; k < cfg->n_t; k++)
+        if (!(cfg->t_lo[k] >= cfg->t_lo[k - 1]) || !(cfg->t_hi[k] >= cfg->t_hi[k - 1]))
+            return fail(C2D_EINVAL, "time-bin edges must be nondecreasing (bin %d)", k);
+    const size_t cells = (size_t)cfg->n_t * cfg->n_mu * cfg->n_bands;
+    if (cells > ((size_t)1 << 28)) return fail(C2D_EINVAL, "%zu accumulator cells", cells);
+    CUL(cudaSetDevice(c->device));
+    c->lc_free();
+    LcState *s = c->lc = new LcState();
+    s->cells = cells;
+    const size_t nt = cfg->n_t, nm = cfg->n_mu, nb = cfg->n_bands, ntab = 2 * (nt + nm + nb);
+    std::vector<double> tab(ntab);
+    double *p = tab.data();
+    std::copy(cfg->t_lo, cfg->t_lo + nt, p); p += nt; std::copy(cfg->t_hi, cfg->t_hi + nt, p); p += nt;
+    std::copy(cfg->mu0, cfg->mu0 + nm, p); p += nm; std::copy(cfg->mu1, cfg->mu1 + nm, p); p += nm;
+    std::copy(cfg->E0, cfg->E0 + nb, p); p += nb; std::copy(cfg->E1, cfg->E1 + nb, p);
+    CUL(cudaMalloc(&s->d_tab, ntab * 8));
+    CUL(cudaMalloc(&s->d_acc, 3 * cells * 8));
+    CUL(cudaMemcpyAsync(s->d_tab, tab.data(), ntab * 8, cudaMemcpyHostToDevice, c->stream));
+    CUL(cudaMemsetAsync(s->d_acc, 0, 3 * cells * 8, c->stream));
+    CUL(cudaStreamSynchronize(c->stream));
+    LcParams &q = s->q;
+    q.gam_bulk = cfg->gam_bulk;
+    q.betta = sqrt(1. - 1. / (cfg->gam_bulk * cfg->gam_bulk));                  // plcm.c:394 (the same for every photon)
+    q.rmax = cfg->rmax; q.t_offset = cfg->t_offset;
+    q.n_t = cfg->n_t; q.n_mu = cfg->n_mu; q.n_bands = cfg->n_bands;
+    q.mu_closed = cfg->mu_closed ? 1 : 0; q.first_band_only = cfg->first_band_only ? 1 : 0;
+    q.t_lo = s->d_tab; q.t_hi = q.t_lo + nt; q.mu0 = q.t_hi + nt; q.mu1 = q.mu0 + nm; q.E0 = q.mu1 + nm; q.E1 = q.E0 + nb;
+    q.sum_ew = s->d_acc; q.sum_ew2 = s->d_acc + cells;
+    q.count = reinterpret_cast<unsigned long long *>(s->d_acc + 2 * cells);
+    return 0;
+}
+
+extern "C" int c2d_lc_accumulate(c2d_ctx *h)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (!c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (int rc = c2d_sync(h)) return rc;                                        // the scattering queue must have drained
+    // the record count lives on the device (counters[C2D_CNT_NEVENTS]); records beyond event_capacity were not stored
+    return lc_launch(c, c->d_events, c->P.counters + CNT_NEVENTS, c->event_cap, nullptr);
+}
+
+extern "C" int c2d_lc_accumulate_events(c2d_ctx *h, const c2d_event *ev, int64_t n)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (!c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (n < 0 || (n && !ev)) return fail(C2D_EINVAL, "n = %lld", (long long)n);
+    if (n == 0) return 0;
+    CUL(cudaSetDevice(c->device));
+    LcState *s = c->lc;
+    const size_t need = (size_t)n * 7 + 1;                                      // + the count
+    if (need > s->stage_cap) {
+        cudaFree(s->d_stage); s->d_stage = nullptr; s->stage_cap = 0;
+        CUL(cudaMalloc(&s->d_stage, (need + 1) * 8));
+        s->stage_cap = need;
+    }
+    const unsigned long long cnt = (unsigned long long)n;
+    double *d_cnt = s->d_stage + (((size_t)n * 7 + 1) & ~(size_t)1);           // the 8-byte slot after the records
+    CUL(cudaMemcpyAsync(s->d_stage, ev, (size_t)n * 56, cudaMemcpyHostToDevice, c->stream));
+    CUL(cudaMemcpyAsync(d_cnt, &cnt, 8, cudaMemcpyHostToDevice, c->stream));
+    if (int rc = lc_launch(c, s->d_stage, reinterpret_cast<unsigned long long *>(d_cnt), n, nullptr)) return rc;
+    CUL(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+extern "C" int c2d_lc_read(c2d_ctx *h, double *sum_ew, double *sum_ew2, int64_t *count)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    CUL(cudaSetDevice(c->device));
+    LcState *s = c->lc;
+    CUL(cudaStreamSynchronize(c->stream));
+    if (sum_ew) CUL(cudaMemcpy(sum_ew, s->q.sum_ew, s->cells * 8, cudaMemcpyDeviceToHost));
+    if (sum_ew2) CUL(cudaMemcpy(sum_ew2, s->q.sum_ew2, s->cells * 8, cudaMemcpyDeviceToHost));
+    if (count) CUL(cudaMemcpy(count, s->q.count, s->cells * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int c2d_lc_device(c2d_ctx *h, double **sums, int64_t **count, int64_t *cells)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (sums) *sums = c->lc->d_acc;
+    if (count) *count = reinterpret_cast<int64_t *>(c->lc->q.count);
+    if (cells) *cells = (int64_t)c->lc->cells;
+    return 0;
+}
+
+extern "C" int c2d_lc_bench(c2d_ctx *h, int64_t n_events, float *ms, int64_t *bytes)
+{
+#ifdef C2D_EMU
+    (void)h; (void)n_events; (void)ms; (void)bytes;
+    return fail(C2D_EINVAL, "c2d_lc_bench needs the device build");
+#else
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (n_events < 1) return fail(C2D_EINVAL, "n_events = %lld", (long long)n_events);
+    CUL(cudaSetDevice(c->device));
+    double *d_ev = nullptr;
+    CUL(cudaMalloc(&d_ev, ((size_t)n_events * 7 + 2) * 8));
+    k_lc_gen<<<c->n_sm * 8, 256, 0, c->stream>>>(n_events, d_ev);
+    CUL(cudaGetLastError());
+    const unsigned long long cnt = (unsigned long long)n_events;
+    double *d_cnt = d_ev + (((size_t)n_events * 7 + 1) & ~(size_t)1);
+    CUL(cudaMemcpyAsync(d_cnt, &cnt, 8, cudaMemcpyHostToDevice, c->stream));
+    float t = 0;
+    int rc = lc_launch(c, d_ev, reinterpret_cast<unsigned long long *>(d_cnt), n_events, &t);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_ev);
+    if (rc) return rc;
+    if (ms) *ms = t;
+    if (bytes) *bytes = n_events * 56;
+    return 0;
+#endif
+}

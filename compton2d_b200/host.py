@@ -356,6 +356,57 @@ class Compton2d:
         _l.check(self.L.c2d_events_drain(self.h, buf.ctypes.data, self.event_capacity, C.byref(n)))
         return buf[: min(n.value, self.event_capacity)].copy()
 
+    # ------------------------------------------------------------------ event-list reduction
+    def lc_begin(self, red):
+        """Set the bin tables of the light-curve / SED reduction (`lightcurve.lc_reduction` = postprocessing/plcm.c's
+        rules, `lightcurve.sed_reduction` = pspt.c's) and zero the accumulators."""
+        a = {k: _d(red[k]) for k in ("t_lo", "t_hi", "mu0", "mu1", "E0", "E1")}
+        if a["t_lo"].size != a["t_hi"].size or a["mu0"].size != a["mu1"].size or a["E0"].size != a["E1"].size:
+            raise ValueError("bin tables: lower and upper edges differ in length")
+        cfg = _l.LcConfig(gam_bulk=float(red["gam_bulk"]), rmax=float(red["rmax"]), t_offset=float(red["t_offset"]),
+                          n_t=a["t_lo"].size, n_mu=a["mu0"].size, n_bands=a["E0"].size, mu_closed=int(red["mu_closed"]),
+                          first_band_only=int(red["first_band_only"]))
+        for k, v in a.items():
+            setattr(cfg, k, _p(v))
+        _l.check(self.L.c2d_lc_begin(self.h, C.byref(cfg)))
+        self._lc_shape = (a["t_lo"].size, a["mu0"].size, a["E0"].size)
+
+    def lc_accumulate(self):
+        """Bin this step's escape records where they lie in HBM (instead of `write(1000+myid, 105)`, imcleak2d.f:181,
+        followed by plcm / pspt on the files).  Once per step, after imcfield2d / imcvol2d / imcsurf2d."""
+        _l.check(self.L.c2d_lc_accumulate(self.h))
+
+    def lc_accumulate_events(self, events):
+        """The same for an [n,7] array of records in host memory (an event file read back)."""
+        ev = np.ascontiguousarray(events, dtype=_F).reshape(-1, 7)
+        _l.check(self.L.c2d_lc_accumulate_events(self.h, ev.ctypes.data, ev.shape[0]))
+
+    def lc_read(self, group=None):
+        """-> (sum_ew, sum_ew2, count) [time][mu][band], summed over ranks (every rank wrote its own p###_evb.dat in the
+        reference and plcm read them all, plcm.c:370-383,452-466); feed to lightcurve.finalize / finalize_sed."""
+        shp = self._lc_shape
+        s1, s2, cnt = np.zeros(shp), np.zeros(shp), np.zeros(shp, np.int64)
+        if self.world == 1:
+            _l.check(self.L.c2d_lc_read(self.h, s1.ctypes.data, s2.ctypes.data, cnt.ctypes.data))
+            return s1, s2, cnt
+        import torch
+        import torch.distributed as dist
+        ps, pc, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        _l.check(self.L.c2d_lc_device(self.h, C.byref(ps), C.byref(pc), C.byref(n)))
+        self.sync()
+        tf = torch.as_tensor(_CudaView(ps.value, 2 * n.value, "<f8"), device="cuda").clone()
+        ti = torch.as_tensor(_CudaView(pc.value, n.value, "<i8"), device="cuda").clone()
+        dist.all_reduce(tf, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(ti, op=dist.ReduceOp.SUM, group=group)
+        f = tf.cpu().numpy()
+        return f[: n.value].reshape(shp), f[n.value:].reshape(shp), ti.cpu().numpy().reshape(shp)
+
+    def lc_bench(self, n_events):
+        """-> (ms, algorithmic bytes) of k_lc_reduce on n generated records with the current tables."""
+        ms, nb = C.c_float(), C.c_int64()
+        _l.check(self.L.c2d_lc_bench(self.h, int(n_events), C.byref(ms), C.byref(nb)))
+        return ms.value, nb.value
+
     # ------------------------------------------------------------------ measurement
     def timing(self, enable=True):
         _l.check(self.L.c2d_kernel_time_ms(self.h, -1 if enable else -2, None, None))

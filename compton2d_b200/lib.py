@@ -75,6 +75,12 @@ class FpOut(C.Structure):
                                    "f_t_implicit")]
 
 
+class LcConfig(C.Structure):
+    _fields_ = [(n, C.c_double) for n in ("gam_bulk", "rmax", "t_offset")] + \
+        [(n, C.c_int) for n in ("n_t", "n_mu", "n_bands", "mu_closed", "first_band_only")] + \
+        [(n, dp) for n in ("t_lo", "t_hi", "mu0", "mu1", "E0", "E1")]
+
+
 COUNTERS = ["ndxout", "cmcount1", "cmcount2", "lkcount", "nevents", "histories", "trials", "multiple", "killed",
             "segovf", "literal", "qpeak", "fatal", "segments", "s3passes", "s3hard"]
 
@@ -82,7 +88,8 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
-           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read"]
+           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
+           "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench"]
 
 _lib = None
 
@@ -126,6 +133,12 @@ def load():
     L.c2d_comtot.argtypes = [vp, C.c_int64, vp, vp, C.c_int, vp]
     L.c2d_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), lp]
     L.c2d_tally_bench.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(C.c_float), lp]
+    L.c2d_lc_begin.argtypes = [vp, C.POINTER(LcConfig)]
+    L.c2d_lc_accumulate.argtypes = [vp]
+    L.c2d_lc_accumulate_events.argtypes = [vp, vp, C.c_int64]
+    L.c2d_lc_read.argtypes = [vp, vp, vp, vp]
+    L.c2d_lc_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), lp]
+    L.c2d_lc_bench.argtypes = [vp, C.c_int64, C.POINTER(C.c_float), lp]
     for fn in ("c2d_pack_bin_first", "c2d_unpack_bin_first"):
         getattr(L, fn).argtypes = [vp] + [C.c_int] * 6 + [vp]
         getattr(L, fn).restype = None

@@ -97,7 +97,7 @@ typedef struct {
     int64_t nst;                      /* reader.f nst: particles per photon cycle; nsv = 0.5 nst Eloss_tot / sum(Eloss_tot) */
     const double *f_nt, *Pnt;         /* [zone][num_nt] */
     const double *n_e, *tea, *B_field, *vol, *zsurf;   /* [zone] */
-    const double *f_pair, *k_gg, *tbbl;               /* as in c2d_step_in (may be NULL) */
+    const double *f_pair, *k_gg, *tbbl;               /* as in c2d_step_in; may be NULL */
 } c2d_gen_in;
 
 typedef struct {
@@ -201,6 +201,39 @@ int c2d_census_export(c2d_ctx *ctx, double *dbuf, int32_t *ibuf, uint64_t *sid, 
            sid[n] = replay stream id (may be NULL) */
 int c2d_census_import(c2d_ctx *ctx, const double *dbuf, const int32_t *ibuf, const uint64_t *sid, int64_t n);
 int c2d_events_drain(c2d_ctx *ctx, c2d_event *buf, int64_t cap, int64_t *n);
+
+/* ---- event-list reduction -------------------------------------------------------
+ * The reference turns its p###_evb.dat event files (one 105-byte text line per escaping photon, imcleak2d.f:181) into
+ * light curves and SEDs with two stand-alone C programs that share one per-photon transform (Doppler boost with the bulk
+ * Lorentz factor, light-travel-time correction to the plane through r = rmax) and differ in their bin rules:
+ *   postprocessing/plcm.c:384-450   L(t_obs, mu_obs, band) with <ew>, <ew^2>;  mu bins [mu0, mu1), EVERY band holding E
+ *   postprocessing/pspt.c:249-289   L(E_obs, t_obs);  one CLOSED mu window [mu0, mu1], only the FIRST band holding E
+ * These entry points do the same reduction on the escape records while they are still in HBM.  The accumulators
+ * [time bin][mu bin][band] persist across steps (as the event files do) until the next c2d_lc_begin.
+ * compton2d_b200/lightcurve.py builds the tables from the programs' own answer files (mrk421_lc.input, ...). */
+typedef struct {
+    double gam_bulk, rmax, t_offset;  /* plcm.c:104-130 prompts; t_offset is subtracted from the arrival time (plcm.c:412) */
+    int n_t, n_mu, n_bands;
+    int mu_closed;                    /* 0: mu0 <= mu < mu1 (plcm.c:423), 1: mu0 <= mu <= mu1 (pspt.c:274) */
+    int first_band_only;              /* 0: plcm.c:441-449, 1: pspt.c:278-280 */
+    const double *t_lo, *t_hi;        /* [n_t]   t_lo <= t < t_hi, first match; both nondecreasing (plcm.c:236-240, pspt.c:145-148) */
+    const double *mu0, *mu1;          /* [n_mu]  first match */
+    const double *E0, *E1;            /* [n_bands]  E0 <= E < E1 */
+} c2d_lc_config;
+
+int c2d_lc_begin(c2d_ctx *ctx, const c2d_lc_config *cfg);  /* sets the bin tables, zeroes the accumulators */
+int c2d_lc_accumulate(c2d_ctx *ctx);
+        /* bins the escape records of the current step (those c2d_events_drain would return); call once per step after
+           the tracking calls -- it drains the scattering queue like c2d_sync */
+int c2d_lc_accumulate_events(c2d_ctx *ctx, const c2d_event *ev, int64_t n);
+        /* the same for n records in host memory (event files of an earlier run / of the reference) */
+int c2d_lc_read(c2d_ctx *ctx, double *sum_ew, double *sum_ew2, int64_t *count);
+        /* [n_t][n_mu][n_bands] each (any pointer may be NULL): sum of ew, of ew^2, photon count -- plcm's F, F2,
+           particle_sum before its normalisation (plcm.c:470-496); pspt's F, particle_sum (pspt.c:286-287) */
+int c2d_lc_device(c2d_ctx *ctx, double **sums, int64_t **count, int64_t *cells);
+        /* device pointers of the accumulators ([2][cells] FP64, [cells] int64) for the reduction over GPUs */
+int c2d_lc_bench(c2d_ctx *ctx, int64_t n_events, float *ms, int64_t *bytes);
+        /* k_lc_reduce on n generated records with the current tables; CUDA-event time and algorithmic bytes (56 / record) */
 
 /* ---- Fokker-Planck update (update2d.f:337-1741 FP_calc, batched over zones) -------------------
  * Inputs are what the per-zone job message carries (fp_mpi.f:612-700) plus the broadcast scalars

@@ -1182,14 +1182,20 @@ void orc_step_zero_worker(orc_state *s)
 
 
 /* ------------------------------------------------------------------ event-list reduction */
-/* postprocessing/plcm.c:384-450: Doppler boost into the observer frame (bulk Lorentz factor gam_bulk along +z),
- * light-travel-time correction to the plane through r = rmax, then binning in arrival time (st_max bins of width dt
- * from t_offset), observer-frame direction cosine and -- possibly overlapping -- energy bands.
+/* The per-photon transform and binning shared by the reference's two post-processors, postprocessing/plcm.c:384-450
+ * (light curves) and postprocessing/pspt.c:249-289 (time-resolved SEDs): Doppler boost into the observer frame (bulk
+ * Lorentz factor gam_bulk along +z), light-travel-time correction to the plane through r = rmax, then binning in arrival
+ * time, observer-frame direction cosine and photon energy.  The two programs differ only in the bin rules:
+ *   plcm: time bins t_lo[k] = k dt by repeated addition (plcm.c:236-240), `time -= t_offset` first; mu bins half open
+ *         [mu0, mu1), first match; EVERY band [E0, E1) that holds E is incremented (bands may overlap, l.441-449);
+ *   pspt: time bins t_lo[n] = t0 + n dt, t_hi[n] = t0 + n dt + dt (pspt.c:145-148); ONE closed mu window (l.274:
+ *         `mu < mu0 || mu > mu1` skips); only the FIRST band that holds E (l.278-280).
  * events: 7 doubles per record (t_bound, xnu, ew, rpre, zpre, wmu, phi), imcleak2d.f:171,181.
  * Accumulators [k][n][l] (time, mu, band), added to (not zeroed). */
-void orc_lightcurve(int64_t n_ev, const double *ev, double gam_bulk, double rmax, double dt, double t_offset, int st_max,
-                    int n_mu, const double *mu0, const double *mu1, int n_bins, const double *E0, const double *E1,
-                    double *sum_ew, double *sum_ew2, int64_t *count)
+void orc_events_reduce(int64_t n_ev, const double *ev, double gam_bulk, double rmax, double t_offset, int n_t,
+                       const double *t_lo, const double *t_hi, int n_mu, const double *mu0, const double *mu1, int mu_closed,
+                       int n_bins, const double *E0, const double *E1, int first_band_only,
+                       double *sum_ew, double *sum_ew2, int64_t *count)
 {
     for (int64_t q = 0; q < n_ev; q++) {
         double t_bound = ev[7 * q], E = ev[7 * q + 1], ew = ev[7 * q + 2], r = ev[7 * q + 3], z = ev[7 * q + 4];
@@ -1205,25 +1211,18 @@ void orc_lightcurve(int64_t n_ev, const double *ev, double gam_bulk, double rmax
         cdt = z * mu / gam_bulk + sqrt(1. - mu * mu) * (rmax - r * cos(phi));
         time = t_bound + 3.33333333e-11 * cdt;
         time -= t_offset;
-        if (time < 0.) continue;
-        /* t0[k] = k dt accumulated by repeated addition in plcm.c:243-247 */
-        {
-            double t0 = 0.;
-            for (k = 0; k < st_max; k++) {
-                const double t1 = t0 + dt;
-                if (time >= t0 && time < t1) break;
-                t0 = t1;
-            }
-        }
+        for (k = 0; k < n_t; k++)
+            if (time >= t_lo[k] && time < t_hi[k]) break;
         for (n = 0; n < n_mu; n++)
-            if (mu >= mu0[n] && mu < mu1[n]) break;
-        if (!(k < st_max && n < n_mu)) continue;
+            if (mu >= mu0[n] && (mu_closed ? mu <= mu1[n] : mu < mu1[n])) break;
+        if (!(k < n_t && n < n_mu)) continue;
         for (l = 0; l < n_bins; l++)
             if (E >= E0[l] && E < E1[l]) {
                 const size_t at = ((size_t)k * n_mu + n) * n_bins + l;
                 sum_ew[at] += ew;
                 sum_ew2[at] += (ew * ew);
                 count[at]++;
+                if (first_band_only) break;
             }
     }
 }

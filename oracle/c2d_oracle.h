@@ -144,10 +144,12 @@ double orc_fibran(orc_state *s);
 void orc_volume_em(orc_state *s, int zone, double l_min);            /* volume2d.f:10-394, live (synchrotron) terms */
 void orc_imcgen_volume(orc_state *s, int nst);                         /* imcgen2d.f:203-336,405-459: Eloss_*, nsv, ewsv */
 
-/* event-list reduction: the per-photon transform and binning of postprocessing/plcm.c:384-450 */
-void orc_lightcurve(int64_t n, const double *events, double gam_bulk, double rmax, double dt, double t_offset, int st_max,
-                    int n_mu, const double *mu0, const double *mu1, int n_bins, const double *E0, const double *E1,
-                    double *sum_ew, double *sum_ew2, int64_t *count);
+/* event-list reduction: the per-photon transform and binning of postprocessing/plcm.c:384-450 and
+ * postprocessing/pspt.c:249-289 */
+void orc_events_reduce(int64_t n, const double *events, double gam_bulk, double rmax, double t_offset, int n_t,
+                       const double *t_lo, const double *t_hi, int n_mu, const double *mu0, const double *mu1, int mu_closed,
+                       int n_bins, const double *E0, const double *E1, int first_band_only,
+                       double *sum_ew, double *sum_ew2, int64_t *count);
 
 /* surface sources (imcsurf2d_para.f) */
 void orc_planck(orc_state *s, double tpl);                             /* planck2d.f:1-141 */

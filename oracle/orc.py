@@ -201,16 +201,18 @@ def file_sp(rows, g_bulk, R_blr, fr_blr, R_ir, fr_ir, R_disk, d_jet):
     return dict(E_file=out[0], F_file=out[1], P_file=out[2], a1=out[3], I_file=out[4], int_file=integ.value, nfile=n)
 
 
-def lightcurve(events, cfg, st_max=1024):
-    """orc_lightcurve on an [n,7] event list with a parsed plcm input (compton2d_b200.lightcurve.parse_lc_input).
-    -> (sum_ew, sum_ew2, count) [st_max][n_mu][n_bins]."""
+def events_reduce(events, red):
+    """orc_events_reduce on an [n,7] event list with the bin tables of compton2d_b200.lightcurve.lc_reduction /
+    sed_reduction.  -> (sum_ew, sum_ew2, count) [n_t][n_mu][n_bands]."""
     ev = np.ascontiguousarray(events, dtype=np.float64).reshape(-1, 7)
-    n_mu, nb = int(cfg["n_mu"]), len(cfg["E0"])
-    s1 = np.zeros((st_max, n_mu, nb)); s2 = np.zeros((st_max, n_mu, nb)); cnt = np.zeros((st_max, n_mu, nb), np.int64)
-    mu0 = np.ascontiguousarray(cfg["mu0"], float); mu1 = np.ascontiguousarray(cfg["mu1"], float)
-    E0 = np.ascontiguousarray(cfg["E0"], float); E1 = np.ascontiguousarray(cfg["E1"], float)
+    arr = {k: np.ascontiguousarray(red[k], float) for k in ("t_lo", "t_hi", "mu0", "mu1", "E0", "E1")}
+    n_t, n_mu, nb = len(arr["t_lo"]), len(arr["mu0"]), len(arr["E0"])
+    s1 = np.zeros((n_t, n_mu, nb)); s2 = np.zeros((n_t, n_mu, nb)); cnt = np.zeros((n_t, n_mu, nb), np.int64)
     L = lib()
-    L.orc_lightcurve.argtypes = [C.c_int64, C.c_void_p] + [C.c_double] * 4 + [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
-    L.orc_lightcurve(len(ev), ev.ctypes.data, cfg["gam_bulk"], cfg["rmax"], cfg["dt"], cfg["t_offset"], st_max, n_mu,
-                     mu0.ctypes.data, mu1.ctypes.data, nb, E0.ctypes.data, E1.ctypes.data, s1.ctypes.data, s2.ctypes.data, cnt.ctypes.data)
+    L.orc_events_reduce.argtypes = [C.c_int64, C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                    C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 3
+    L.orc_events_reduce(len(ev), ev.ctypes.data, red["gam_bulk"], red["rmax"], red["t_offset"], n_t, arr["t_lo"].ctypes.data,
+                        arr["t_hi"].ctypes.data, n_mu, arr["mu0"].ctypes.data, arr["mu1"].ctypes.data, int(red["mu_closed"]), nb,
+                        arr["E0"].ctypes.data, arr["E1"].ctypes.data, int(red["first_band_only"]),
+                        s1.ctypes.data, s2.ctypes.data, cnt.ctypes.data)
     return s1, s2, cnt

@@ -67,11 +67,12 @@ def stage_reference(ref: Path = REF_DEFAULT) -> Path | None:
 
 
 # --------------------------------------------------------------------------- inputs
-def build_plcm(ref: Path = REF_DEFAULT) -> Path | None:
-    """Compile the reference's own light-curve post-processor (postprocessing/plcm.c, K&R C) from the source where it lies
-    into oracle/_ref/plcm.  Only where the reference tree exists; the binary travels to the GPU box."""
-    src = ref / "postprocessing" / "plcm.c"
-    out = REFDIR / "plcm"
+def build_plcm(ref: Path = REF_DEFAULT, prog: str = "plcm") -> Path | None:
+    """Compile one of the reference's own post-processors (postprocessing/plcm.c: light curves, pspt.c: SEDs; K&R C) from
+    the source where it lies into oracle/_ref/<prog>.  Only where the reference tree exists; the binary travels to the
+    GPU box."""
+    src = ref / "postprocessing" / f"{prog}.c"
+    out = REFDIR / prog
     if out.exists() and (not src.exists() or out.stat().st_mtime >= src.stat().st_mtime):
         return out
     if not src.exists():
@@ -81,11 +82,11 @@ def build_plcm(ref: Path = REF_DEFAULT) -> Path | None:
     return out
 
 
-def run_plcm(events, answers: str, workdir: Path, infile: str = "p001_evb.dat") -> dict:
+def run_plcm(events, answers: str, workdir: Path, infile: str = "p001_evb.dat", prog: str = "plcm") -> dict:
     """Run oracle/_ref/plcm on an event list ([n,7] array, written in the reference's format 105 of imcleak2d.f:181) with
     the given stdin answers (the content of a postprocessing/*_lc.input file).  -> {file name: text} of what it wrote."""
     import numpy as np
-    exe = REFDIR / "plcm"
+    exe = REFDIR / prog
     workdir.mkdir(parents=True, exist_ok=True)
     with open(workdir / infile, "w") as f:
         for r in np.asarray(events, float).reshape(-1, 7):
@@ -95,7 +96,7 @@ def run_plcm(events, answers: str, workdir: Path, infile: str = "p001_evb.dat") 
     r = subprocess.run(f"ulimit -s unlimited; exec {exe}", shell=True, cwd=workdir, input=answers.encode(), capture_output=True,
                        timeout=600, executable="/bin/bash")
     if r.returncode != 0:
-        raise RuntimeError(f"plcm failed ({r.returncode}): {r.stdout[-500:]!r} {r.stderr[-500:]!r}")
+        raise RuntimeError(f"{prog} failed ({r.returncode}): {r.stdout[-500:]!r} {r.stderr[-500:]!r}")
     return {n: (workdir / n).read_text() for n in sorted(set(os.listdir(workdir)) - before)}
 
 

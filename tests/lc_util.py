@@ -4,7 +4,7 @@ from pathlib import Path
 
 import numpy as np
 
-from compton2d_b200.lightcurve import finalize, parse_lc_input
+from compton2d_b200.lightcurve import finalize, finalize_sed, parse_lc_input, parse_sed_input
 
 GOLD = Path(__file__).resolve().parent / "golden"
 
@@ -31,3 +31,19 @@ def check_against_plcm(g, cfg, s1, s2, cnt, tol=2e-6):
         scale = np.sqrt(res["F2"][:rows, n, :])
         assert np.all(np.abs(sf - ref) <= 2e-3 * scale + 1e-26), n
     assert int(cnt.sum()) > 1000
+
+
+def load_sed_case(name):
+    g = np.load(GOLD / f"pspt_{name}.npz")
+    cfg = parse_sed_input(str(g["answers"]))
+    events = np.load(GOLD / f"refbin_{name}.npz")["events"]
+    return g, cfg, events
+
+
+def check_against_pspt(g, cfg, s1, cnt, tol=2e-6):
+    """pspt prints sqrt(E0 E1), F per time bin (%e) and the photon count of the last time bin only."""
+    res = finalize_sed(s1, cnt, cfg)
+    assert np.allclose(res["E"], g["E"], rtol=tol)
+    assert np.array_equal(res["particle_sum"], g["count_last"])
+    assert np.allclose(res["F"], g["F"], rtol=tol, atol=1e-26), np.abs(res["F"] / g["F"] - 1).max()
+    assert (g["F"] > 1e-20).sum() > 50

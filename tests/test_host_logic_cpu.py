@@ -215,3 +215,49 @@ def test_two_ranks_equal_one(emu, tmp_path):
     pack1 = np.concatenate([one["edep"], one["ecens"], one["n_field"].ravel(), one["fout"].ravel(), one["E_IC"]])
     assert np.abs(two["pack"] - pack1).max() <= 1e-12 * np.abs(pack1).max()
     assert np.array_equal(two["sid"], np.sort(one["census"][2]))
+
+
+def test_event_list_reduction_host_logic(emu):
+    """SURVEY 8f N2 through the C ABI (emu build: the transform + bin functions of csrc/c2d_lc.cu run serially): records from
+    host memory against the reference's own plcm / pspt outputs, then the records of a tracked step binned where they lie
+    against the oracle's reduction of the drained list, accumulating over two steps."""
+    import orc
+    from compton2d_b200 import C2dError
+    from compton2d_b200.lightcurve import lc_reduction, sed_reduction
+    from lc_util import check_against_plcm, check_against_pspt, load_case, load_sed_case
+    from parity_util import gpu_step, make_gpu
+    from synth import make_problem
+    P = make_problem(nz=4, nr=3, nst=1500, ngroups=64, split=(40, 20, 6, 10), n_e=3.0e5)
+    g = make_gpu(P)
+    with pytest.raises(C2dError):
+        g.lc_accumulate()                                  # c2d_lc_begin first
+    gold, cfg, events = load_case("small")
+    g.lc_begin(lc_reduction(cfg))
+    g.lc_accumulate_events(events[:1000]); g.lc_accumulate_events(events[1000:])
+    check_against_plcm(gold, cfg, *g.lc_read())
+    gold, cfg, events = load_sed_case("dense")
+    g.lc_begin(sed_reduction(cfg))
+    g.lc_accumulate_events(events)
+    s1, s2, cnt = g.lc_read()
+    check_against_pspt(gold, cfg, s1, cnt)
+    # a tracked step: the blob of make_problem, wide angle bins, arrival times of a few light-crossing times
+    red = dict(gam_bulk=10.0, rmax=float(P["r"][-1]), t_offset=0.0, t_lo=np.arange(64) * 0.2 * P["dt"],
+               t_hi=(np.arange(64) + 1) * 0.2 * P["dt"], mu0=np.array([-1.0, 0.9]), mu1=np.array([0.9, 1.0]), mu_closed=0,
+               E0=np.array([1e-9, 1e-3, 1e-5]), E1=np.array([1e-3, 1e3, 1e1]), first_band_only=0)
+    g.lc_begin(red)
+    ev_all = []
+    for cyc in (1, 2):
+        t = gpu_step(g, P, cyc, field=cyc > 1)
+        g.lc_accumulate()
+        ev_all.append(t["events"])
+    ev_all = np.concatenate(ev_all)
+    assert len(ev_all) > 50
+    o1, o2, oc = orc.events_reduce(ev_all, red)
+    s1, s2, cnt = g.lc_read()
+    assert np.array_equal(cnt, oc) and cnt.sum() > 50
+    assert np.allclose(s1, o1, rtol=1e-13, atol=0) and np.allclose(s2, o2, rtol=1e-13, atol=0)
+    bad = dict(red, t_hi=red["t_hi"][::-1].copy())
+    with pytest.raises(C2dError) as e:
+        g.lc_begin(bad)
+    assert e.value.code == 2
+    g.close()

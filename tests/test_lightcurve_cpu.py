@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 import orc
-from lc_util import check_against_plcm, load_case
+from compton2d_b200.lightcurve import lc_reduction, sed_reduction
+from lc_util import check_against_plcm, check_against_pspt, load_case, load_sed_case
 
 
 @pytest.mark.parametrize("name", ["small", "dense"])
@@ -12,8 +13,18 @@ def test_oracle_lightcurve_matches_reference_plcm(name):
     g, cfg, events = load_case(name)
     assert cfg["n_mu"] == 2 and len(cfg["E0"]) == 9 and cfg["gam_bulk"] == 33.0
     # plcm reads the event file the binary wrote with e14.7: feed the oracle the same 8-digit values
-    s1, s2, cnt = orc.lightcurve(events, cfg)
+    s1, s2, cnt = orc.events_reduce(events, lc_reduction(cfg))
     check_against_plcm(g, cfg, s1, s2, cnt)
+
+
+@pytest.mark.parametrize("name", ["small", "dense"])
+def test_oracle_sed_matches_reference_pspt(name):
+    g, cfg, events = load_sed_case(name)
+    assert cfg["n_t"] == 7 and len(cfg["E0"]) == 25
+    s1, s2, cnt = orc.events_reduce(events, sed_reduction(cfg))
+    check_against_pspt(g, cfg, s1, cnt)
+    # the regions overlap (1e-3 .. 1e-2 keV is in both): pspt counts a photon once, in the first band that holds it
+    assert int(cnt.sum()) <= len(events)
 
 
 def test_parse_reference_input_files():
@@ -27,3 +38,7 @@ def test_parse_reference_input_files():
     # README-style file with comments after '!'
     c = parse_lc_input("p001_evb.dat\n15  ! Gamma\n1e17 ! r_max\nx.dat\n1\nx.dat\n0.9974 ! mu_min\n0.9982\n2e4\n0\n1.5e6\n1\n1e-6\n3e-6\n2\n1\n")
     assert c["gam_bulk"] == 15 and np.allclose(c["E0"], [1e-6, 2e-6]) and np.allclose(c["E1"], [2e-6, 3e-6])
+    # pspt's answer file (postprocessing/mrk421_sed.input)
+    from compton2d_b200.lightcurve import parse_sed_input
+    c = parse_sed_input("p001_evb.dat\n33\n1e16\nsed30.dat\n30\n1.6e4\n6e4\n0.99944\n0.99964\n1\n1e-7\n1e10\n100\n0\nn\n")
+    assert c["n_t"] == 30 and c["t_end"] == 6e4 and len(c["E0"]) == 100 and c["E0"][0] == 1e-7 and abs(c["E1"][-1] / 1e10 - 1) < 1e-12
