@@ -439,6 +439,34 @@ def our_arm(args):
         dist.destroy_process_group()
 
 
+def legs_only(args):
+    """--only fp,lc,tally: the stand-alone kernel legs without the tracking headline (profiling runs)."""
+    import torch
+    from parity_util import make_gpu
+    from synth import make_problem
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    out = {}
+    legs = args.only.split(",")
+    if "lc" in legs or "tally" in legs:
+        P = make_problem(nz=16, nr=16, nst=1000, ngroups=100)
+        g = make_gpu(P, census_capacity=1000, event_capacity=1000)
+        if "lc" in legs:
+            out["lc"] = lc_bench(g, hbm)
+        if "tally" in legs:
+            out["tally"] = tally_bench(g, hbm)
+        g.close()
+    if "fp" in legs:
+        out["fp"] = fp_bench(0, hbm)
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -453,11 +481,14 @@ def main():
     ap.add_argument("--no-fp", action="store_true", help="skip the Fokker-Planck zone-steps/s leg")
     ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
                     help="c1 = BASELINE configs[1] (the bench line); c3 = configs[3] shape, 64x64 zones x 200 groups, 1.25e8 sources/GPU")
+    ap.add_argument("--only", default="", help="comma list of stand-alone legs (fp, lc, tally) to run instead of the bench line")
     args = ap.parse_args()
     args.nz, args.nr, args.groups = (64, 64, 200) if args.workload == "c3" else (16, 16, 100)
     if args.workload == "c3" and args.nst == 20_000_000:
         args.nst = 250_000_000
-    if args.impl == "reference":
+    if args.only:
+        legs_only(args)
+    elif args.impl == "reference":
         reference_arm(args)
     else:
         our_arm(args)

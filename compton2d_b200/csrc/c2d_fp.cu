@@ -32,6 +32,11 @@ struct FpParams {
     double inj_g1, inj_g2, inj_p, inj_t, inj_gg, inj_sigma, inj_L, inj_v, pick_rate, r_esc, r_acc;
     double r_flare, z_flare, t_flare, sigma_r, sigma_z, sigma_t, flare_amp;
     const double *z, *r, *gnt, *F_IC;
+    const double *F_ICt;           // F_IC transposed, [nf][N]: lanes (= electron bins) read consecutive addresses
+    const double *qt_t, *qt_x15, *qt_x25;   // McDonald quadrature lattice (Theta-independent factors), [kQuadRounds * 32]
+    const double *gtab;            // gamma_bar on a uniform grid in ln(Theta): the predictor of the temperature search
+    int gtab_n;
+    double gtab_x0, gtab_ih;       // first node, 1 / spacing
     // per zone, in
     const double *f_nt_in, *Pnt_in, *n_field, *ecens, *n_e_in, *B_field, *tea, *tna, *vol, *f_pair_in, *Eloss_sy,
         *ec_old, *turb_lev;
@@ -46,7 +51,13 @@ struct FpState {
     bool have_FIC = false;
     double *d_io = nullptr;       // staging blob for per-zone inputs/outputs
     size_t io_cap = 0;
+    double *d_gtab = nullptr;     // [kGtabN] gamma_bar(exp(x0 + i h)), built once by k_gbar_table
+    double *d_FICt = nullptr;     // [nf][N]
+    double *d_quad = nullptr;     // [3][kQuadRounds * 32]: t, (ts^2-1)^(3/2), (ts^2-1)^(5/2)
 };
+constexpr int kQuadRounds = 1024;                                 // 32768 lattice points t = 1.001^n: covers z >= 1e-12
+constexpr int kGtabN = 640;
+constexpr double kGtabX0 = -1.7, kGtabH = 0.02;                   // Theta = 0.183 ... 6.5e4
 
 #ifndef C2D_EMU      // warp-cooperative device code: not part of the g++ debugging build (tests/emu)
 
@@ -66,7 +77,19 @@ __device__ __forceinline__ double gammln_dev(double xx)
 // volume2d.f:572-626: gamma_bar(Theta), both McDonald quadratures (nu = 2, 3) in one lane-parallel pass.
 // Term n of the reference's loop is t_n = 1.001^n; lane l takes n = l, l+32, ...; each quadrature stops
 // after the first term (in n order) with t >= 2 and sd <= 1e-8, exactly like the scalar loop.
-__device__ double warp_gamma_bar(double Theta, int lane)
+// The Theta-independent factors of a term -- t_n, (ts^2-1)^(3/2), (ts^2-1)^(5/2) with ts = t_n (1 + 1.001)/2 -- come from
+// a table built once by k_quad_table with the same products (the first kQuadRounds rounds; later ones are computed),
+// so a term costs one exp: sd = x^(k/2) exp(-z ts)  [the reference divides by exp(z ts): same value to 1 ulp].
+struct QuadTab { const double *t, *x15, *x25; };
+
+__device__ __forceinline__ void quad_term(double t, double s, double &x15, double &x25)
+{
+    const double ts = t * s, x = ts * ts - 1.0, sx = sqrt(x);
+    x15 = x * sx;
+    x25 = x * x * sx;
+}
+
+__device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab)
 {
     double g;
     if (Theta < (double)0.2f) {
@@ -74,17 +97,30 @@ __device__ double warp_gamma_bar(double Theta, int lane)
                 (1. + (double)1.875f * Theta + (double).8203f * (Theta * Theta)) - Theta;
     } else {
         const double z = 1.0 / Theta, dt = 1.001, d = dt - 1.0, s = 5.e-1 * (1.0 + dt);
-        double t = 1.0, dt32 = 1.0;
-        for (int i = 0; i < 32; i++) { if (i < lane) t = t * dt; dt32 = dt32 * dt; }
         double sum2 = 0.0, sum3 = 0.0;
         bool done2 = false, done3 = false;
+        double t = 1.0, dt32 = 1.0;                               // dt32 only needed beyond the table
+        double tn = tab.t[lane], a15 = tab.x15[lane], a25 = tab.x25[lane];
         for (int round = 0; round < 4096 && !(done2 && done3); round++) {
-            const double ts = t * s, y = z * ts, x = ts * ts - 1.0;
+            double x15, x25;
+            if (round < kQuadRounds) {
+                t = tn; x15 = a15; x25 = a25;
+                if (round + 1 < kQuadRounds) {                    // next round's factors in flight
+                    const int nx = (round + 1) * 32 + lane;
+                    tn = tab.t[nx]; a15 = tab.x15[nx]; a25 = tab.x25[nx];
+                } else {
+                    for (int i = 0; i < 32; i++) dt32 = dt32 * dt;
+                }
+            } else {
+                t = t * dt32;
+                quad_term(t, s, x15, x25);
+            }
+            const double y = z * (t * s);
             double sd2 = 0.0, sd3 = 0.0;
             if (y < 2.25e2) {
-                const double ex = exp(y), sx = sqrt(x);
-                sd2 = (x * sx) / ex;              // (ts^2 - 1)^(3/2)
-                sd3 = (x * x * sx) / ex;          // (ts^2 - 1)^(5/2)
+                const double e = exp(-y);
+                sd2 = x15 * e;
+                sd3 = x25 * e;
             }
             const unsigned stop2 = __ballot_sync(0xffffffffu, !(t < 2.0 || sd2 > 1.e-8));
             const unsigned stop3 = __ballot_sync(0xffffffffu, !(t < 2.0 || sd3 > 1.e-8));
@@ -98,7 +134,6 @@ __device__ double warp_gamma_bar(double Theta, int lane)
                 if (lane <= last) sum3 += d * t * sd3;
                 done3 = (stop3 != 0u);
             }
-            t = t * dt32;
         }
         sum2 = warp_sum(sum2); sum3 = warp_sum(sum3);
         const double sp = sqrt(3.14159265e0);
@@ -108,6 +143,30 @@ __device__ double warp_gamma_bar(double Theta, int lane)
     }
     if (g < 1.0) g = 1.0;
     return g;
+}
+
+// the quadrature lattice: lane l of round r holds t = 1.001^l (l sequential products) times (1.001^32)^r (r products)
+__global__ void k_quad_table(double *t_out, double *x15_out, double *x25_out, int rounds)
+{
+    const int lane = threadIdx.x;
+    const double dt = 1.001, s = 5.e-1 * (1.0 + dt);
+    double t = 1.0, dt32 = 1.0;
+    for (int i = 0; i < 32; i++) { if (i < lane) t = t * dt; dt32 = dt32 * dt; }
+    for (int r = 0; r < rounds; r++) {
+        double x15, x25;
+        quad_term(t, s, x15, x25);
+        t_out[r * 32 + lane] = t; x15_out[r * 32 + lane] = x15; x25_out[r * 32 + lane] = x25;
+        t = t * dt32;
+    }
+}
+
+// F_IC [N][nf] -> [nf][N]
+__global__ void k_transpose(const double *in, int rows, int cols, double *out)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= rows * cols) return;
+    const int r = idx / cols, c = idx - r * cols;
+    out[(size_t)c * rows + r] = in[idx];
 }
 
 // Theta_0 * c^n (n >= 0) or Theta_0 / c^|n| (n < 0) by the reference's sequential products (update2d.f:1449,1456)
@@ -125,11 +184,11 @@ __device__ __forceinline__ double theta_lattice(double Theta0, int n)
 //   dir = -1: Theta_n = Theta_0 / 1.005^n, stop when !(gbar < gamma_bar(Theta_n)) or Theta_n < 1e-2
 // gamma_bar is monotone on the lattice, so "stops at n" is monotone in n and a bracketing search started
 // at `guess` returns the same n as the step-by-step walk.
-__device__ int lattice_search(int dir, double Th_e, double gbar, int guess, int lane, double &g_out)
+__device__ int lattice_search(int dir, double Th_e, double gbar, int guess, int lane, const QuadTab tab, double &g_out)
 {
     auto stops = [&](int n, double &g) {
         const double th = theta_lattice(Th_e, dir * n);
-        g = warp_gamma_bar(th, lane);
+        g = warp_gamma_bar(th, lane, tab);
         return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
     };
     int lo = 0, hi = -1, n = max(1, guess), s = 1;
@@ -156,24 +215,96 @@ __device__ int lattice_search(int dir, double Th_e, double gbar, int guess, int 
     return hi;
 }
 
+// gamma_bar from the table (4-point Lagrange in ln Theta, ~1e-9 relative): a PREDICTOR only -- every decision of the
+// temperature search is confirmed with the exact quadrature.  Below 0.2 the reference's own rational fit (exact).
+__device__ double gamma_bar_approx(const FpParams &q, double Theta)
+{
+    double g;
+    if (Theta < (double)0.2f) {
+        g = (1. + (double)4.375f * Theta + (double)7.383f * (Theta * Theta) + (double)3.384f * (Theta * Theta * Theta)) /
+                (1. + (double)1.875f * Theta + (double).8203f * (Theta * Theta)) - Theta;
+    } else {
+        const double u = (log(Theta) - q.gtab_x0) * q.gtab_ih;
+        int i = (int)u;
+        if (i < 1) i = 1;
+        if (i > q.gtab_n - 3) {
+            if (u > (double)(q.gtab_n - 2)) return 3.0 * Theta;    // beyond the table: K3/K2 - Theta -> 3 Theta
+            i = q.gtab_n - 3;
+        }
+        const double t = u - (double)i;                           // nodes i-1, i, i+1, i+2 at t = -1, 0, 1, 2
+        const double *y = q.gtab + i;
+        g = -t * (t - 1.0) * (t - 2.0) / 6.0 * y[-1] + (t + 1.0) * (t - 1.0) * (t - 2.0) / 2.0 * y[0]
+            - (t + 1.0) * t * (t - 2.0) / 2.0 * y[1] + (t + 1.0) * t * (t - 1.0) / 6.0 * y[2];
+    }
+    if (g < 1.0) g = 1.0;
+    return g;
+}
+
+// lattice_search with the predictor in place of the quadrature: the n the exact search will most likely return
+__device__ int lattice_predict(const FpParams &q, int dir, double Th_e, double gbar, int guess)
+{
+    auto stops = [&](int n) {
+        const double th = theta_lattice(Th_e, dir * n);
+        const double g = gamma_bar_approx(q, th);
+        return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
+    };
+    int lo = 0, hi, n = max(1, guess), s = 1;
+    if (stops(n)) {
+        hi = n;
+        while (hi - lo > 1) {
+            n = max(lo + 1, hi - s); s *= 2;
+            if (stops(n)) hi = n; else { lo = n; break; }
+        }
+    } else {
+        lo = n;
+        for (;;) {
+            n = lo + s; s *= 2;
+            if (stops(n) || n > (1 << 20)) { hi = n; break; }
+            lo = n;
+        }
+    }
+    while (hi - lo > 1) {
+        n = lo + (hi - lo) / 2;
+        if (stops(n)) hi = n; else lo = n;
+    }
+    return hi;
+}
+
 // update2d.f:1441-1469: the new electron temperature.  Returns The_new; g_av_out = gamma_bar(The_new).
-__device__ double temperature_search(double Th_e, double g_av, double gbar, int lane, double &g_av_out)
+// The predicted lattice point n is confirmed by two exact quadratures (the walk stops at n and does not stop at n - 1);
+// if the confirmation fails the exact bracketing search takes over from n.
+__device__ double temperature_search(const FpParams &q, double Th_e, double g_av, double gbar, int lane, double &g_av_out)
 {
     g_av_out = g_av;
-    if (gbar > g_av) {
-        int guess = 1;
-        if (gbar > 4.0) {
-            const double tstar = gbar / 2.985;                      // K3/K2 - Theta -> 3 Theta for Theta >> 1
-            if (tstar > Th_e) guess = max(1, (int)(log(tstar / Th_e) / log((double)1.005f)));
-        }
-        const int n = lattice_search(+1, Th_e, gbar, guess, lane, g_av_out);
-        return theta_lattice(Th_e, n);
+    if (!(gbar > g_av) && !(gbar < g_av)) return Th_e;
+    const int dir = (gbar > g_av) ? +1 : -1;
+    int guess = 1;
+    if (dir > 0 && gbar > 4.0) {
+        const double tstar = gbar / 2.985;                          // K3/K2 - Theta -> 3 Theta for Theta >> 1
+        if (tstar > Th_e) guess = max(1, (int)(log(tstar / Th_e) / log((double)1.005f)));
     }
-    if (gbar < g_av) {
-        const int n = lattice_search(-1, Th_e, gbar, 1, lane, g_av_out);
-        return theta_lattice(Th_e, -n);
-    }
-    return Th_e;
+    int n = lattice_predict(q, dir, Th_e, gbar, guess);
+    const QuadTab tab{q.qt_t, q.qt_x15, q.qt_x25};
+    auto stops = [&](int m, double &g) {
+        const double th = theta_lattice(Th_e, dir * m);
+        g = warp_gamma_bar(th, lane, tab);
+        return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
+    };
+    double g_n, g_m;
+    bool ok = stops(n, g_n);
+    if (ok && n > 1) ok = !stops(n - 1, g_m);
+    if (ok) g_av_out = g_n;
+    else n = lattice_search(dir, Th_e, gbar, n, lane, tab, g_av_out);
+    return theta_lattice(Th_e, dir * n);
+}
+
+// one warp per node of the predictor table
+__global__ void __launch_bounds__(128) k_gbar_table(double *tab, int n, double x0, double h, const QuadTab qt)
+{
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const double g = warp_gamma_bar(exp(x0 + (double)i * h), threadIdx.x & 31, qt);
+    if ((threadIdx.x & 31) == 0) tab[i] = g;
 }
 
 // shared-memory layout per warp: 9 arrays of N doubles
@@ -233,16 +364,27 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
     const double Th_p = Tp_flare / 9.382e5;
     double Th_e = q.tea[zi] / 5.11e2;
     const double f_th = 1.5 * volume * n_lept;
-    // dg_ic(i) = -sum_ph n_field(ph) F_IC(i,ph) / volume (l.568-574): one bin per lane, F_IC row streamed from L2
+    // dg_ic(i) = -sum_ph n_field(ph) F_IC(i,ph) / volume (l.568-574): one bin per lane, the transposed F_IC streamed from L2.
+    // volume ~ 1e45 cm^3 is outside the exponent range of the inline FP64 division (every quotient would take the ~100-
+    // instruction slow path), so numerator and denominator are scaled by the same power of two first -- exact, the
+    // quotient is bit-identical -- and the empty bins of the photon field (a - 0 = a) are skipped.
     {
         const double *nfld = q.n_field + (size_t)zi * nf;
-        for (int i = lane; i < N; i += 32) {
+        const double sc = scalbn(1.0, -ilogb(volume)), vs = volume * sc;
+        double *nf_s = a_i;                                       // a_i | b_i | c_i: 3 N doubles of scratch
+        const bool staged = nf <= 3 * N;
+        if (staged) { for (int ip = lane; ip < nf; ip += 32) nf_s[ip] = nfld[ip] * sc; __syncwarp(); }
+        for (int i0 = 0; i0 < N; i0 += 32) {
+            const int i = i0 + lane;
+            const bool live = i < N - 1;
+            const double *F = q.F_ICt + (live ? i : 0);
             double v = 0.0;
-            if (i < N - 1) {
-                const double *F = q.F_IC + (size_t)i * nf;
-                for (int ip = 0; ip < nf; ip++) v = v - nfld[ip] * F[ip] / volume;
+            for (int ip = 0; ip < nf; ip++) {
+                const double a = staged ? nf_s[ip] : nfld[ip] * sc;
+                if (a == 0.0) continue;                           // warp-uniform
+                v = v - a * F[(size_t)ip * N] / vs;
             }
-            dg_ic[i] = v;
+            if (i < N) dg_ic[i] = live ? v : 0.0;
         }
     }
     __syncwarp();
@@ -250,8 +392,8 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
     const double dr = (k == 1) ? q.r[k - 1] - q.rmin : q.r[k - 1] - q.r[k - 2];
     const double dz = (j == 1) ? q.z[j - 1] - q.zmin : q.z[j - 1] - q.z[j - 2];
     double sum_E = 0.0, sum_last = 1.0;
-    for (;;) {                                                    // label 200
-        double g_av = warp_gamma_bar(Th_e, lane);
+    double g_av = warp_gamma_bar(Th_e, lane, QuadTab{q.qt_t, q.qt_x15, q.qt_x25});
+    for (;;) {                                                    // label 200 (g_av = gamma_bar(Th_e), l.600)
         double hr_th_c = 0.0;
         for (int i = lane; i < N - 1; i += 32)
             hr_th_c = hr_th_c - 8.176e-7 * dg_ic[i] * f_old[i] * (gnt[i + 1] - gnt[i]) * volume * n_lept;
@@ -417,9 +559,10 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
         gbar = warp_sum(gbar);
         __syncwarp();
         double g_new;
-        const double The_new = temperature_search(Th_e, g_av, gbar, lane, g_new);
+        const double The_new = temperature_search(q, Th_e, g_av, gbar, lane, g_new);
         Te_new = 5.11e2 * The_new;
         Th_e = The_new;
+        g_av = g_new;                                             // == gamma_bar(Th_e) of the next sub-step
         if (!(t_fp < dt1) || fp_steps > 1000000) break;
     }
     // epilogue (l.1480-1500)
@@ -545,9 +688,19 @@ __global__ void k_ic_loss(const double *gnt, const double *E_field, int N, int n
     F_IC[idx] = v;
 }
 
+void launch_gbar_table(double *tab, double *quad, cudaStream_t st)
+{
+    const size_t n = (size_t)kQuadRounds * 32;
+    k_quad_table<<<1, 32, 0, st>>>(quad, quad + n, quad + 2 * n, kQuadRounds);
+    k_gbar_table<<<(kGtabN + 3) / 4, 128, 0, st>>>(tab, kGtabN, kGtabX0, kGtabH, QuadTab{quad, quad + n, quad + 2 * n});
+}
+void launch_transpose(const double *in, int rows, int cols, double *out, cudaStream_t st)
+{
+    k_transpose<<<(rows * cols + 255) / 256, 256, 0, st>>>(in, rows, cols, out);
+}
 void launch_fp(const FpParams &q, cudaStream_t st)
 {
-    const int warps = 4;
+    const int warps = 2;                                          // 14.4 kB of shared memory per warp (N = 200): 7 blocks / SM
     const size_t smem = (size_t)warps * 9 * q.N * sizeof(double);
     cudaFuncSetAttribute(k_fp_zones, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int blocks = (q.n_zones + warps - 1) / warps;
@@ -559,13 +712,15 @@ void launch_ic_loss(const double *gnt, const double *E_field, int N, int nf, dou
 }
 #else
 void launch_fp(const FpParams &, cudaStream_t) {}
+void launch_gbar_table(double *, double *, cudaStream_t) {}
+void launch_transpose(const double *, int, int, double *, cudaStream_t) {}
 void launch_ic_loss(const double *, const double *, int, int, double *, cudaStream_t) {}
 #endif
 
 void Ctx::fp_free()
 {
     if (!fp) return;
-    cudaFree(fp->d_FIC); cudaFree(fp->d_io);
+    cudaFree(fp->d_FIC); cudaFree(fp->d_io); cudaFree(fp->d_gtab); cudaFree(fp->d_FICt); cudaFree(fp->d_quad);
     delete fp;
     fp = nullptr;
 }
@@ -578,6 +733,11 @@ static int fp_state(Ctx *c)
     if (c->fp) return 0;
     c->fp = new FpState();
     CUF(cudaMalloc(&c->fp->d_FIC, (size_t)c->dims.num_nt * c->dims.nphfield * 8));
+    CUF(cudaMalloc(&c->fp->d_FICt, (size_t)c->dims.num_nt * c->dims.nphfield * 8));
+    CUF(cudaMalloc(&c->fp->d_gtab, (size_t)kGtabN * 8));
+    CUF(cudaMalloc(&c->fp->d_quad, (size_t)3 * kQuadRounds * 32 * 8));
+    launch_gbar_table(c->fp->d_gtab, c->fp->d_quad, c->stream);
+    CUF(cudaGetLastError());
     return 0;
 }
 
@@ -597,6 +757,7 @@ int c2d_ic_loss(c2d_ctx *h, double *F_IC_out)
     const int N = c->dims.num_nt, nf = c->dims.nphfield;
     c->timer_begin(3);
     launch_ic_loss(c->P.gnt, c->P.E_field, N, nf, c->fp->d_FIC, c->stream);
+    launch_transpose(c->fp->d_FIC, N, nf, c->fp->d_FICt, c->stream);
     c->timer_end();
     CUF(cudaGetLastError());
     c->fp->have_FIC = true;
@@ -625,9 +786,11 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
     if (in->n_zones >= 0 && in->n_zones < n_zones) n_zones = in->n_zones;
     if (in->F_IC) {
         CUF(cudaMemcpyAsync(c->fp->d_FIC, in->F_IC, (size_t)N * nf * 8, cudaMemcpyHostToDevice, c->stream));
+        launch_transpose(c->fp->d_FIC, N, nf, c->fp->d_FICt, c->stream);
         c->fp->have_FIC = true;
     } else if (!c->fp->have_FIC) {
         launch_ic_loss(c->P.gnt, c->P.E_field, N, nf, c->fp->d_FIC, c->stream);
+        launch_transpose(c->fp->d_FIC, N, nf, c->fp->d_FICt, c->stream);
         c->fp->have_FIC = true;
     }
     // staging blob: inputs then outputs
@@ -674,6 +837,9 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
     q.r_flare = in->r_flare; q.z_flare = in->z_flare; q.t_flare = in->t_flare; q.sigma_r = in->sigma_r;
     q.sigma_z = in->sigma_z; q.sigma_t = in->sigma_t; q.flare_amp = in->flare_amp;
     q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.F_IC = c->fp->d_FIC;
+    q.F_ICt = c->fp->d_FICt;
+    { const size_t nq = (size_t)kQuadRounds * 32; q.qt_t = c->fp->d_quad; q.qt_x15 = q.qt_t + nq; q.qt_x25 = q.qt_t + 2 * nq; }
+    q.gtab = c->fp->d_gtab; q.gtab_n = kGtabN; q.gtab_x0 = kGtabX0; q.gtab_ih = 1.0 / kGtabH;
     q.f_nt_in = D + o_f; q.Pnt_in = D + o_P;
     q.n_field = in->n_field ? D + o_nf : c->P.n_field;
     q.ecens = in->ecens ? D + o_ec : c->P.ecens;
