@@ -33,7 +33,7 @@ struct FpParams {
     double r_flare, z_flare, t_flare, sigma_r, sigma_z, sigma_t, flare_amp;
     const double *z, *r, *gnt, *F_IC;
     const double *F_ICt;           // F_IC transposed, [nf][N]: lanes (= electron bins) read consecutive addresses
-    const double *qt_t, *qt_x15, *qt_x25;   // McDonald quadrature lattice (Theta-independent factors), [kQuadRounds * 32]
+    const double *qt_x15;          // McDonald quadrature lattice: (ts_n^2 - 1)^(3/2), [kQuadRounds * 32]
     const double *gtab;            // gamma_bar on a uniform grid in ln(Theta): the predictor of the temperature search
     int gtab_n;
     double gtab_x0, gtab_ih;       // first node, 1 / spacing
@@ -53,7 +53,7 @@ struct FpState {
     size_t io_cap = 0;
     double *d_gtab = nullptr;     // [kGtabN] gamma_bar(exp(x0 + i h)), built once by k_gbar_table
     double *d_FICt = nullptr;     // [nf][N]
-    double *d_quad = nullptr;     // [3][kQuadRounds * 32]: t, (ts^2-1)^(3/2), (ts^2-1)^(5/2)
+    double *d_quad = nullptr;     // [kQuadRounds * 32]: (ts^2-1)^(3/2)
 };
 constexpr int kQuadRounds = 1024;                                 // 32768 lattice points t = 1.001^n: covers z >= 1e-12
 constexpr int kGtabN = 640;
@@ -77,50 +77,45 @@ __device__ __forceinline__ double gammln_dev(double xx)
 // volume2d.f:572-626: gamma_bar(Theta), both McDonald quadratures (nu = 2, 3) in one lane-parallel pass.
 // Term n of the reference's loop is t_n = 1.001^n; lane l takes n = l, l+32, ...; each quadrature stops
 // after the first term (in n order) with t >= 2 and sd <= 1e-8, exactly like the scalar loop.
-// The Theta-independent factors of a term -- t_n, (ts^2-1)^(3/2), (ts^2-1)^(5/2) with ts = t_n (1 + 1.001)/2 -- come from
-// a table built once by k_quad_table with the same products (the first kQuadRounds rounds; later ones are computed),
-// so a term costs one exp: sd = x^(k/2) exp(-z ts)  [the reference divides by exp(z ts): same value to 1 ulp].
-struct QuadTab { const double *t, *x15, *x25; };
+// The Theta-independent factor (ts^2-1)^(3/2), ts = t_n (1 + 1.001)/2, comes from a table built once by k_quad_table
+// (the first kQuadRounds rounds; later ones are computed), so a term costs one exp: sd = x^(k/2) exp(-z ts)  [the
+// reference divides by exp(z ts): same value to 1 ulp].
+struct QuadTab { const double *x15; };
 
-__device__ __forceinline__ void quad_term(double t, double s, double &x15, double &x25)
+__device__ __forceinline__ double quad_x15(double t, double s)
 {
-    const double ts = t * s, x = ts * ts - 1.0, sx = sqrt(x);
-    x15 = x * sx;
-    x25 = x * x * sx;
+    const double ts = t * s, x = ts * ts - 1.0;
+    return x * sqrt(x);
 }
 
-__device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab)
+// force_quad: use the quadrature below Theta = 0.2 too (the predictor table must be smooth across the switch)
+__device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab, bool force_quad = false)
 {
     double g;
-    if (Theta < (double)0.2f) {
+    if (Theta < (double)0.2f && !force_quad) {
         g = (1. + (double)4.375f * Theta + (double)7.383f * (Theta * Theta) + (double)3.384f * (Theta * Theta * Theta)) /
                 (1. + (double)1.875f * Theta + (double).8203f * (Theta * Theta)) - Theta;
     } else {
         const double z = 1.0 / Theta, dt = 1.001, d = dt - 1.0, s = 5.e-1 * (1.0 + dt);
         double sum2 = 0.0, sum3 = 0.0;
         bool done2 = false, done3 = false;
-        double t = 1.0, dt32 = 1.0;                               // dt32 only needed beyond the table
-        double tn = tab.t[lane], a15 = tab.x15[lane], a25 = tab.x25[lane];
+        double t = 1.0, dt32 = 1.0;
+        for (int i = 0; i < 32; i++) { if (i < lane) t = t * dt; dt32 = dt32 * dt; }
+        double p0 = tab.x15[lane], p1 = tab.x15[32 + lane];       // two rounds of table loads in flight
         for (int round = 0; round < 4096 && !(done2 && done3); round++) {
-            double x15, x25;
+            double x15;
             if (round < kQuadRounds) {
-                t = tn; x15 = a15; x25 = a25;
-                if (round + 1 < kQuadRounds) {                    // next round's factors in flight
-                    const int nx = (round + 1) * 32 + lane;
-                    tn = tab.t[nx]; a15 = tab.x15[nx]; a25 = tab.x25[nx];
-                } else {
-                    for (int i = 0; i < 32; i++) dt32 = dt32 * dt;
-                }
+                x15 = p0; p0 = p1;
+                if (round + 2 < kQuadRounds) p1 = tab.x15[(round + 2) * 32 + lane];
             } else {
-                t = t * dt32;
-                quad_term(t, s, x15, x25);
+                x15 = quad_x15(t, s);
             }
-            const double y = z * (t * s);
+            const double ts = t * s, y = z * ts;
             double sd2 = 0.0, sd3 = 0.0;
             if (y < 2.25e2) {
                 const double e = exp(-y);
-                sd2 = x15 * e;
-                sd3 = x25 * e;
+                sd2 = x15 * e;                                    // (ts^2 - 1)^(3/2) / exp(y)
+                sd3 = sd2 * (ts * ts - 1.0);                      // (ts^2 - 1)^(5/2) / exp(y)
             }
             const unsigned stop2 = __ballot_sync(0xffffffffu, !(t < 2.0 || sd2 > 1.e-8));
             const unsigned stop3 = __ballot_sync(0xffffffffu, !(t < 2.0 || sd3 > 1.e-8));
@@ -134,6 +129,7 @@ __device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab)
                 if (lane <= last) sum3 += d * t * sd3;
                 done3 = (stop3 != 0u);
             }
+            t = t * dt32;
         }
         sum2 = warp_sum(sum2); sum3 = warp_sum(sum3);
         const double sp = sqrt(3.14159265e0);
@@ -146,16 +142,14 @@ __device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab)
 }
 
 // the quadrature lattice: lane l of round r holds t = 1.001^l (l sequential products) times (1.001^32)^r (r products)
-__global__ void k_quad_table(double *t_out, double *x15_out, double *x25_out, int rounds)
+__global__ void k_quad_table(double *x15_out, int rounds)
 {
     const int lane = threadIdx.x;
     const double dt = 1.001, s = 5.e-1 * (1.0 + dt);
     double t = 1.0, dt32 = 1.0;
     for (int i = 0; i < 32; i++) { if (i < lane) t = t * dt; dt32 = dt32 * dt; }
     for (int r = 0; r < rounds; r++) {
-        double x15, x25;
-        quad_term(t, s, x15, x25);
-        t_out[r * 32 + lane] = t; x15_out[r * 32 + lane] = x15; x25_out[r * 32 + lane] = x25;
+        x15_out[r * 32 + lane] = quad_x15(t, s);
         t = t * dt32;
     }
 }
@@ -215,11 +209,15 @@ __device__ int lattice_search(int dir, double Th_e, double gbar, int guess, int 
     return hi;
 }
 
-// gamma_bar from the table (4-point Lagrange in ln Theta, ~1e-9 relative): a PREDICTOR only -- every decision of the
-// temperature search is confirmed with the exact quadrature.  Below 0.2 the reference's own rational fit (exact).
-__device__ double gamma_bar_approx(const FpParams &q, double Theta)
+// gamma_bar from the table (4-point Lagrange in ln Theta; measured against the quadrature: 3e-9 typical, 5e-8 worst,
+// tests/test_gpu_fp.py): a PREDICTOR -- the temperature search confirms its decisions with the exact quadrature unless the
+// predicted value clears gbar by kGtabMargin.  Below 0.2 the reference's own rational fit (exact).
+// in_table = false beyond the last node (K3/K2 - Theta -> 3 Theta): never trusted without confirmation.
+constexpr double kGtabMargin = 1.e-5;
+__device__ double gamma_bar_approx(const FpParams &q, double Theta, bool &in_table)
 {
     double g;
+    in_table = true;
     if (Theta < (double)0.2f) {
         g = (1. + (double)4.375f * Theta + (double)7.383f * (Theta * Theta) + (double)3.384f * (Theta * Theta * Theta)) /
                 (1. + (double)1.875f * Theta + (double).8203f * (Theta * Theta)) - Theta;
@@ -227,10 +225,7 @@ __device__ double gamma_bar_approx(const FpParams &q, double Theta)
         const double u = (log(Theta) - q.gtab_x0) * q.gtab_ih;
         int i = (int)u;
         if (i < 1) i = 1;
-        if (i > q.gtab_n - 3) {
-            if (u > (double)(q.gtab_n - 2)) return 3.0 * Theta;    // beyond the table: K3/K2 - Theta -> 3 Theta
-            i = q.gtab_n - 3;
-        }
+        if (i > q.gtab_n - 3) { in_table = false; return 3.0 * Theta; }
         const double t = u - (double)i;                           // nodes i-1, i, i+1, i+2 at t = -1, 0, 1, 2
         const double *y = q.gtab + i;
         g = -t * (t - 1.0) * (t - 2.0) / 6.0 * y[-1] + (t + 1.0) * (t - 1.0) * (t - 2.0) / 2.0 * y[0]
@@ -245,7 +240,8 @@ __device__ int lattice_predict(const FpParams &q, int dir, double Th_e, double g
 {
     auto stops = [&](int n) {
         const double th = theta_lattice(Th_e, dir * n);
-        const double g = gamma_bar_approx(q, th);
+        bool in_table;
+        const double g = gamma_bar_approx(q, th, in_table);
         return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
     };
     int lo = 0, hi, n = max(1, guess), s = 1;
@@ -271,8 +267,9 @@ __device__ int lattice_predict(const FpParams &q, int dir, double Th_e, double g
 }
 
 // update2d.f:1441-1469: the new electron temperature.  Returns The_new; g_av_out = gamma_bar(The_new).
-// The predicted lattice point n is confirmed by two exact quadratures (the walk stops at n and does not stop at n - 1);
-// if the confirmation fails the exact bracketing search takes over from n.
+// The predicted lattice point n is confirmed by the exact quadrature: the walk stops at n and does not stop at n - 1 (the
+// latter taken from the predictor when it is not a close call); if the confirmation fails the exact bracketing search takes
+// over from n.
 __device__ double temperature_search(const FpParams &q, double Th_e, double g_av, double gbar, int lane, double &g_av_out)
 {
     g_av_out = g_av;
@@ -284,15 +281,22 @@ __device__ double temperature_search(const FpParams &q, double Th_e, double g_av
         if (tstar > Th_e) guess = max(1, (int)(log(tstar / Th_e) / log((double)1.005f)));
     }
     int n = lattice_predict(q, dir, Th_e, gbar, guess);
-    const QuadTab tab{q.qt_t, q.qt_x15, q.qt_x25};
+    const QuadTab tab{q.qt_x15};
     auto stops = [&](int m, double &g) {
         const double th = theta_lattice(Th_e, dir * m);
         g = warp_gamma_bar(th, lane, tab);
         return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
     };
+    // the walk must not stop at n - 1: confirmed by the quadrature unless the predictor clears gbar by kGtabMargin there
+    bool sure_m = false;
+    if (n > 1) {
+        bool in_table;
+        const double g_pred = gamma_bar_approx(q, theta_lattice(Th_e, dir * (n - 1)), in_table);
+        sure_m = in_table && fabs(g_pred - gbar) > kGtabMargin * gbar;
+    }
     double g_n, g_m;
-    bool ok = stops(n, g_n);
-    if (ok && n > 1) ok = !stops(n - 1, g_m);
+    bool ok = stops(n, g_n);                                      // the exact value at n is the next sub-step's g_av
+    if (ok && n > 1 && !sure_m) ok = !stops(n - 1, g_m);
     if (ok) g_av_out = g_n;
     else n = lattice_search(dir, Th_e, gbar, n, lane, tab, g_av_out);
     return theta_lattice(Th_e, dir * n);
@@ -303,7 +307,7 @@ __global__ void __launch_bounds__(128) k_gbar_table(double *tab, int n, double x
 {
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (i >= n) return;
-    const double g = warp_gamma_bar(exp(x0 + (double)i * h), threadIdx.x & 31, qt);
+    const double g = warp_gamma_bar(exp(x0 + (double)i * h), threadIdx.x & 31, qt, true);
     if ((threadIdx.x & 31) == 0) tab[i] = g;
 }
 
@@ -392,7 +396,7 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
     const double dr = (k == 1) ? q.r[k - 1] - q.rmin : q.r[k - 1] - q.r[k - 2];
     const double dz = (j == 1) ? q.z[j - 1] - q.zmin : q.z[j - 1] - q.z[j - 2];
     double sum_E = 0.0, sum_last = 1.0;
-    double g_av = warp_gamma_bar(Th_e, lane, QuadTab{q.qt_t, q.qt_x15, q.qt_x25});
+    double g_av = warp_gamma_bar(Th_e, lane, QuadTab{q.qt_x15});
     for (;;) {                                                    // label 200 (g_av = gamma_bar(Th_e), l.600)
         double hr_th_c = 0.0;
         for (int i = lane; i < N - 1; i += 32)
@@ -607,6 +611,20 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
     if (amxwl > 9.999e-1) {
         amxwl = 1.0;
     } else {
+        // update2d.f:1700-1738: scan p_nth = 0.1, 0.15, ... for the power law whose mean energy matches <gamma>.
+        // gamma^-p is carried from step to step by one multiplication with gamma^-0.05 and exp(-gamma/gmax) is hoisted
+        // (the reference calls gam**p_nth and exp(y) for every bin and step: same values to ~1e-14)
+        double *ipw = a_i, *ipstep = b_i, *wq = bigC;
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) {
+            const int i1 = i + 1;
+            const double gam = gnt[i] + 1.0, y = gam / gmax;
+            const bool use = !(i1 < i_lo || i1 > N - 2) && y < 100.0;
+            ipw[i] = use ? pow(gam, -(double)0.1f) : 0.0;
+            ipstep[i] = use ? pow(gam, -0.5e-1) : 0.0;
+            wq[i] = use ? (gnt[i + 1] - gnt[i]) * exp(-y) : 0.0;
+        }
+        __syncwarp();
         double sum_g = 1.e50, sumg_old;
         p_nth = (double)0.1f;
         for (;;) {
@@ -617,14 +635,11 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
             else N_nt = (1.0 - amxwl) / log(gmax / gmin);
             double sg = 0.0, sgg = 0.0;
             for (int i = lane; i < N; i += 32) {
-                const int i1 = i + 1;
-                if (i1 < i_lo || i1 > N - 2) continue;
-                const double gam = gnt[i] + 1.0, y = gam / gmax;
-                if (y < 100.0) {
-                    const double f_pl = N_nt / (pow(gam, p_nth) * exp(y));
-                    sg += f_pl * gam * (gnt[i + 1] - gnt[i]);
-                    sgg += f_pl * (gnt[i + 1] - gnt[i]);
-                }
+                const double pw = ipw[i];
+                const double f_pl = N_nt * pw * wq[i];            // f_pl (gnt(i+1) - gnt(i))
+                sg += f_pl * (gnt[i] + 1.0);
+                sgg += f_pl;
+                ipw[i] = pw * ipstep[i];
             }
             sg = warp_sum(sg); sgg = warp_sum(sgg);
             sum_g = fabs(sg / sgg - sum_E);
@@ -690,9 +705,22 @@ __global__ void k_ic_loss(const double *gnt, const double *E_field, int N, int n
 
 void launch_gbar_table(double *tab, double *quad, cudaStream_t st)
 {
-    const size_t n = (size_t)kQuadRounds * 32;
-    k_quad_table<<<1, 32, 0, st>>>(quad, quad + n, quad + 2 * n, kQuadRounds);
-    k_gbar_table<<<(kGtabN + 3) / 4, 128, 0, st>>>(tab, kGtabN, kGtabX0, kGtabH, QuadTab{quad, quad + n, quad + 2 * n});
+    k_quad_table<<<1, 32, 0, st>>>(quad, kQuadRounds);
+    k_gbar_table<<<(kGtabN + 3) / 4, 128, 0, st>>>(tab, kGtabN, kGtabX0, kGtabH, QuadTab{quad});
+}
+// one warp per query: the quadrature and the predictor table side by side (c2d_gamma_bar)
+__global__ void __launch_bounds__(128) k_gbar_query(const FpParams q, int n, const double *theta, double *exact, double *table)
+{
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (i >= n) return;
+    const double g = warp_gamma_bar(theta[i], threadIdx.x & 31, QuadTab{q.qt_x15});
+    bool in_table;
+    const double ga = gamma_bar_approx(q, theta[i], in_table);
+    if ((threadIdx.x & 31) == 0) { exact[i] = g; table[i] = in_table ? ga : -ga; }
+}
+void launch_gbar_query(const FpParams &q, int n, const double *theta, double *exact, double *table, cudaStream_t st)
+{
+    k_gbar_query<<<(n + 3) / 4, 128, 0, st>>>(q, n, theta, exact, table);
 }
 void launch_transpose(const double *in, int rows, int cols, double *out, cudaStream_t st)
 {
@@ -714,6 +742,7 @@ void launch_ic_loss(const double *gnt, const double *E_field, int N, int nf, dou
 void launch_fp(const FpParams &, cudaStream_t) {}
 void launch_gbar_table(double *, double *, cudaStream_t) {}
 void launch_transpose(const double *, int, int, double *, cudaStream_t) {}
+void launch_gbar_query(const FpParams &, int, const double *, double *, double *, cudaStream_t) {}
 void launch_ic_loss(const double *, const double *, int, int, double *, cudaStream_t) {}
 #endif
 
@@ -735,7 +764,7 @@ static int fp_state(Ctx *c)
     CUF(cudaMalloc(&c->fp->d_FIC, (size_t)c->dims.num_nt * c->dims.nphfield * 8));
     CUF(cudaMalloc(&c->fp->d_FICt, (size_t)c->dims.num_nt * c->dims.nphfield * 8));
     CUF(cudaMalloc(&c->fp->d_gtab, (size_t)kGtabN * 8));
-    CUF(cudaMalloc(&c->fp->d_quad, (size_t)3 * kQuadRounds * 32 * 8));
+    CUF(cudaMalloc(&c->fp->d_quad, (size_t)kQuadRounds * 32 * 8));
     launch_gbar_table(c->fp->d_gtab, c->fp->d_quad, c->stream);
     CUF(cudaGetLastError());
     return 0;
@@ -763,6 +792,31 @@ int c2d_ic_loss(c2d_ctx *h, double *F_IC_out)
     c->fp->have_FIC = true;
     if (F_IC_out) CUF(cudaMemcpyAsync(F_IC_out, c->fp->d_FIC, (size_t)N * nf * 8, cudaMemcpyDeviceToHost, c->stream));
     CUF(cudaStreamSynchronize(c->stream));
+    return 0;
+}
+
+int c2d_gamma_bar(c2d_ctx *h, int64_t n, const double *Theta, double *gbar, double *gbar_table)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (n < 0 || (n && (!Theta || !gbar))) return fail(C2D_EINVAL, "NULL argument");
+    for (int64_t i = 0; i < n; i++) if (!(Theta[i] > 0.0)) return fail(C2D_EINVAL, "Theta[%lld] = %g", (long long)i, Theta[i]);
+    if (n == 0) return 0;
+    CUF(cudaSetDevice(c->device));
+    int rc = fp_state(c);
+    if (rc) return rc;
+    double *d = nullptr;
+    CUF(cudaMalloc(&d, (size_t)3 * n * 8));
+    CUF(cudaMemcpyAsync(d, Theta, (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    FpParams q;
+    memset(&q, 0, sizeof q);
+    q.qt_x15 = c->fp->d_quad; q.gtab = c->fp->d_gtab; q.gtab_n = kGtabN; q.gtab_x0 = kGtabX0; q.gtab_ih = 1.0 / kGtabH;
+    launch_gbar_query(q, (int)n, d, d + n, d + 2 * n, c->stream);
+    CUF(cudaGetLastError());
+    CUF(cudaMemcpyAsync(gbar, d + n, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (gbar_table) CUF(cudaMemcpyAsync(gbar_table, d + 2 * n, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUF(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
     return 0;
 }
 
@@ -838,7 +892,7 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
     q.sigma_z = in->sigma_z; q.sigma_t = in->sigma_t; q.flare_amp = in->flare_amp;
     q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.F_IC = c->fp->d_FIC;
     q.F_ICt = c->fp->d_FICt;
-    { const size_t nq = (size_t)kQuadRounds * 32; q.qt_t = c->fp->d_quad; q.qt_x15 = q.qt_t + nq; q.qt_x25 = q.qt_t + 2 * nq; }
+    q.qt_x15 = c->fp->d_quad;
     q.gtab = c->fp->d_gtab; q.gtab_n = kGtabN; q.gtab_x0 = kGtabX0; q.gtab_ih = 1.0 / kGtabH;
     q.f_nt_in = D + o_f; q.Pnt_in = D + o_P;
     q.n_field = in->n_field ? D + o_nf : c->P.n_field;

@@ -236,6 +236,13 @@ class Compton2d:
         _l.check(self.L.c2d_ic_loss(self.h, F.ctypes.data))
         return F
 
+    def gamma_bar(self, Theta):
+        """== gamma_bar(Theta) (volume2d.f:572-594) -> (quadrature values, predictor-table values; negative beyond the table)."""
+        th = np.ascontiguousarray(Theta, dtype=_F).ravel()
+        g, gt = np.zeros(th.size), np.zeros(th.size)
+        _l.check(self.L.c2d_gamma_bar(self.h, th.size, th.ctypes.data, g.ctypes.data, gt.ctypes.data))
+        return g, gt
+
     def update(self, *, time, dt, f_nt, Pnt, n_e, B_field, tea, tna, vol, Eloss_sy, ec_old, turb_lev, gmin, gmax,
                p_nth, amxwl, f_pair=None, n_field=None, ecens=None, F_IC=None, lnL=20.0, r_esc=0.3, r_acc=1.0,
                inj=None, flare=None, group=None):

@@ -268,6 +268,10 @@ typedef struct {
 
 int c2d_ic_loss(c2d_ctx *ctx, double *F_IC_out);           /* == IC_loss (icloss2d.f:1-125); F_IC_out may be NULL */
 int c2d_update_fp(c2d_ctx *ctx, const c2d_fp_in *in, c2d_fp_out *out);
+int c2d_gamma_bar(c2d_ctx *ctx, int64_t n, const double *Theta, double *gbar, double *gbar_table);
+        /* == gamma_bar(Theta) (volume2d.f:572-594: <gamma> of a Maxwellian, McDonald quadratures above Theta = 0.2) for n
+           temperatures; gbar_table (may be NULL) = the interpolation table that predicts the lattice point of FP_calc's
+           temperature walk (update2d.f:1446-1463), negated where Theta lies beyond the table */
 
 /* ---- COMMON <-> dense packing helpers (host code) ------------------------------------------- */
 void c2d_pack_bin_first(const double *common, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *dense);

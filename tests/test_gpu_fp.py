@@ -109,3 +109,26 @@ def test_ic_loss_device_table():
     finally:
         gpu.close()
     assert np.abs(fic / F.f_ic - 1).max() < 1e-8
+
+
+def test_gamma_bar_and_predictor_table():
+    """gamma_bar on the device (lane-parallel McDonald quadratures) against the oracle's scalar loop, and the interpolation
+    table that predicts the temperature walk against the quadrature: the walk trusts the table only where it clears gbar by
+    1e-5 (kGtabMargin, csrc/c2d_fp.cu), so its error must stay well below that (measured: 3e-9 typical, 5e-8 worst) -- across the fit/quadrature switch at
+    Theta = 0.2 too."""
+    import orc
+    from synth import make_problem
+    P = make_problem(nz=2, nr=2, nst=100, ngroups=16)
+    g = make_gpu(P, census_capacity=1000, event_capacity=1000)
+    rng = np.random.default_rng(3)
+    th = np.concatenate([np.exp(rng.uniform(np.log(0.01), np.log(3.0e4), 400)), 0.2 * 1.005 ** np.arange(-6, 30),
+                         [0.19999, 0.2, 0.20001, 1.0, 1.957, 100.0]])
+    ge, gt = g.gamma_bar(th)
+    ref = np.array([orc.lib().orc_gamma_bar(float(t)) for t in th])
+    assert np.abs(ge / ref - 1).max() < 1e-11
+    inside = gt > 0
+    err = np.abs(gt[inside] / ge[inside] - 1)
+    assert inside.sum() > 400 and err.max() < 2e-7, (err.max(), th[inside][err.argmax()])
+    print("predictor table: max rel err %.2e at Theta = %.4g, median %.2e" % (err.max(), th[inside][err.argmax()], np.median(err)))
+    assert np.all(th[~inside] > 1.0e4)
+    g.close()
