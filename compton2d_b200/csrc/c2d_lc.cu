@@ -27,13 +27,15 @@ struct LcParams {
     double gam_bulk, betta, rmax, t_offset;
     int n_t, n_mu, n_bands, mu_closed, first_band_only;
     const double *t_lo, *t_hi, *mu0, *mu1, *E0, *E1;     // device copies of the bin tables
+    int n_edge;                                          // sorted distinct band edges; interval i = [edge[i], edge[i+1])
+    const double *edge, *covered;                        // covered[i] != 0: some band holds interval i
     double *sum_ew, *sum_ew2;                            // [n_t][n_mu][n_bands]
     unsigned long long *count;
 };
 
 struct LcState {
     LcParams q{};
-    double *d_tab = nullptr;       // [t_lo | t_hi | mu0 | mu1 | E0 | E1]
+    double *d_tab = nullptr;       // [t_lo | t_hi | mu0 | mu1 | E0 | E1 | edge | covered]
     double *d_acc = nullptr;       // [sum_ew | sum_ew2 | count (u64)]
     size_t cells = 0;
     double *d_stage = nullptr;     // host-provided records
@@ -123,12 +125,17 @@ __device__ __forceinline__ void lc_commit(double *s1, double *s2, unsigned long 
     }
 }
 
-// does any band hold E?  (the filter stage only needs yes / no; the commit stage walks the bands)
-__device__ __forceinline__ bool lc_any_band(const double *E0, const double *E1, int n_bands, double E)
+// does any band hold E?  (the filter stage only needs yes / no; the commit stage walks the bands.)  The band edges cut the
+// energy axis into intervals that are either inside some band or inside none: one branch-free bisection over the sorted
+// distinct edges (built by c2d_lc_begin) instead of a divergent scan of the bands.  Same answer as the scan for every E.
+__device__ __forceinline__ bool lc_any_band(const double *edge, const double *covered, int n_edge, double E)
 {
-    for (int l = 0; l < n_bands; l++)
-        if (E >= E0[l] && E < E1[l]) return true;
-    return false;
+    int lo = 0, hi = n_edge;                                  // first index with edge > E
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (edge[mid] > E) hi = mid; else lo = mid + 1;
+    }
+    return lo > 0 && lo < n_edge && covered[lo - 1] != 0.0;   // E in [edge[lo-1], edge[lo])
 }
 
 // The full path for one (compacted) tile of up to 32 records in shared memory: transform, bins, commits.
@@ -176,16 +183,18 @@ __global__ void __launch_bounds__(kLcWarps * 32) k_lc_reduce(const __grid_consta
                                                             const unsigned long long *n_ptr, long long n_cap)
 {
     extern __shared__ double sh[];
-    // shared layout: [tile + 2-tile queue per warp | t_lo | t_hi | mu0 | mu1 | E0 | E1 | (sum_ew | sum_ew2 | count32)]
+    // shared layout: [tile + 2-tile queue per warp | t_lo | t_hi | mu0 | mu1 | E0 | E1 | edge | covered | (sum_ew | sum_ew2 | count32)]
     double *tile = sh + (threadIdx.x >> 5) * (3 * kLcTileDoubles), *queue = tile + kLcTileDoubles;
     double *s_tlo = sh + kLcWarps * 3 * kLcTileDoubles, *s_thi = s_tlo + q.n_t;
     double *s_mu0 = s_thi + q.n_t, *s_mu1 = s_mu0 + q.n_mu, *s_E0 = s_mu1 + q.n_mu, *s_E1 = s_E0 + q.n_bands;
+    double *s_edge = s_E1 + q.n_bands, *s_cov = s_edge + q.n_edge;
     const int cells = q.n_t * q.n_mu * q.n_bands;
-    double *a1 = SHARED ? s_E1 + q.n_bands : q.sum_ew, *a2 = SHARED ? a1 + cells : q.sum_ew2;
+    double *a1 = SHARED ? s_cov + q.n_edge : q.sum_ew, *a2 = SHARED ? a1 + cells : q.sum_ew2;
     unsigned long long *ac = SHARED ? reinterpret_cast<unsigned long long *>(a2 + cells) : q.count;
     for (int i = threadIdx.x; i < q.n_t; i += blockDim.x) { s_tlo[i] = q.t_lo[i]; s_thi[i] = q.t_hi[i]; }
     for (int i = threadIdx.x; i < q.n_mu; i += blockDim.x) { s_mu0[i] = q.mu0[i]; s_mu1[i] = q.mu1[i]; }
     for (int i = threadIdx.x; i < q.n_bands; i += blockDim.x) { s_E0[i] = q.E0[i]; s_E1[i] = q.E1[i]; }
+    for (int i = threadIdx.x; i < q.n_edge; i += blockDim.x) { s_edge[i] = q.edge[i]; s_cov[i] = q.covered[i]; }
     if (SHARED) {
         for (int i = threadIdx.x; i < 2 * cells; i += blockDim.x) a1[i] = 0.;
         for (int i = threadIdx.x; i < cells; i += blockDim.x) reinterpret_cast<unsigned *>(ac)[i] = 0u;
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(kLcWarps * 32) k_lc_reduce(const __grid_consta
         if (live) {
             double E = rec[1], ew = 0., mu = rec[5];
             lc_boost(q, E, ew, mu);
-            live = lc_mu_bin(s_mu0, s_mu1, q.n_mu, q.mu_closed, mu) >= 0 && lc_any_band(s_E0, s_E1, q.n_bands, E);
+            live = lc_mu_bin(s_mu0, s_mu1, q.n_mu, q.mu_closed, mu) >= 0 && lc_any_band(s_edge, s_cov, q.n_edge, E);
         }
         const unsigned pass = __ballot_sync(0xffffffffu, live);
         if (pass) {
@@ -306,7 +315,8 @@ static int lc_launch(Ctx *c, const double *d_ev, const unsigned long long *d_n, 
     return 0;
 #else
     const LcParams &q = s->q;
-    const size_t tab = (size_t)kLcWarps * 3 * kLcTileDoubles + 2 * (size_t)q.n_t + 2 * (size_t)q.n_mu + 2 * (size_t)q.n_bands;
+    const size_t tab = (size_t)kLcWarps * 3 * kLcTileDoubles + 2 * (size_t)q.n_t + 2 * (size_t)q.n_mu + 2 * (size_t)q.n_bands +
+                       2 * (size_t)q.n_edge;
     const size_t priv = 2 * s->cells + (s->cells + 1) / 2;
     const bool shared = (tab + priv) * 8 <= 100 * 1024;                          // 2 blocks / SM with the private copy
     const size_t smem = (tab + (shared ? priv : 0)) * 8;
@@ -364,12 +374,25 @@ extern "C" int c2d_lc_begin(c2d_ctx *h, const c2d_lc_config *cfg)
     c->lc_free();
     LcState *s = c->lc = new LcState();
     s->cells = cells;
-    const size_t nt = cfg->n_t, nm = cfg->n_mu, nb = cfg->n_bands, ntab = 2 * (nt + nm + nb);
+    // the band edges in ascending order and, per interval between neighbours, whether a band holds it (NaN edges: the
+    // band can hold nothing and is left out)
+    std::vector<double> edge;
+    for (int l = 0; l < cfg->n_bands; l++)
+        if (cfg->E0[l] < cfg->E1[l]) { edge.push_back(cfg->E0[l]); edge.push_back(cfg->E1[l]); }
+    std::sort(edge.begin(), edge.end());
+    edge.erase(std::unique(edge.begin(), edge.end()), edge.end());
+    if (edge.empty()) edge.push_back(0.0);
+    std::vector<double> covered(edge.size(), 0.0);
+    for (size_t i = 0; i + 1 < edge.size(); i++)
+        for (int l = 0; l < cfg->n_bands; l++)
+            if (cfg->E0[l] <= edge[i] && edge[i] < cfg->E1[l]) { covered[i] = 1.0; break; }
+    const size_t nt = cfg->n_t, nm = cfg->n_mu, nb = cfg->n_bands, ne = edge.size(), ntab = 2 * (nt + nm + nb + ne);
     std::vector<double> tab(ntab);
     double *p = tab.data();
     std::copy(cfg->t_lo, cfg->t_lo + nt, p); p += nt; std::copy(cfg->t_hi, cfg->t_hi + nt, p); p += nt;
     std::copy(cfg->mu0, cfg->mu0 + nm, p); p += nm; std::copy(cfg->mu1, cfg->mu1 + nm, p); p += nm;
-    std::copy(cfg->E0, cfg->E0 + nb, p); p += nb; std::copy(cfg->E1, cfg->E1 + nb, p);
+    std::copy(cfg->E0, cfg->E0 + nb, p); p += nb; std::copy(cfg->E1, cfg->E1 + nb, p); p += nb;
+    std::copy(edge.begin(), edge.end(), p); p += ne; std::copy(covered.begin(), covered.end(), p);
     CUL(cudaMalloc(&s->d_tab, ntab * 8));
     CUL(cudaMalloc(&s->d_acc, 3 * cells * 8));
     CUL(cudaMemcpyAsync(s->d_tab, tab.data(), ntab * 8, cudaMemcpyHostToDevice, c->stream));
@@ -382,6 +405,7 @@ extern "C" int c2d_lc_begin(c2d_ctx *h, const c2d_lc_config *cfg)
     q.n_t = cfg->n_t; q.n_mu = cfg->n_mu; q.n_bands = cfg->n_bands;
     q.mu_closed = cfg->mu_closed ? 1 : 0; q.first_band_only = cfg->first_band_only ? 1 : 0;
     q.t_lo = s->d_tab; q.t_hi = q.t_lo + nt; q.mu0 = q.t_hi + nt; q.mu1 = q.mu0 + nm; q.E0 = q.mu1 + nm; q.E1 = q.E0 + nb;
+    q.n_edge = (int)ne; q.edge = q.E1 + nb; q.covered = q.edge + ne;
     q.sum_ew = s->d_acc; q.sum_ew2 = s->d_acc + cells;
     q.count = reinterpret_cast<unsigned long long *>(s->d_acc + 2 * cells);
     return 0;
