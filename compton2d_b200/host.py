@@ -363,6 +363,25 @@ class Compton2d:
         _l.check(self.L.c2d_events_drain(self.h, buf.ctypes.data, self.event_capacity, C.byref(n)))
         return buf[: min(n.value, self.event_capacity)].copy()
 
+    # ------------------------------------------------------------------ reference file formats
+    def write_cens(self, path):
+        """== write_cens (census2d.f:1-36) for this rank's census: p###_census.dat as write_record leaves it
+        (write_record.f:432-437).  Returns the number of photons written (ndxout of p###_misc.dat)."""
+        n = C.c_int64()
+        _l.check(self.L.c2d_census_write(self.h, str(path).encode(), C.byref(n)))
+        return n.value
+
+    def read_cens(self, path, entries):
+        """== read_cens (census2d.f:41-73): load `entries` photons of a p###_census.dat into the resident bank."""
+        _l.check(self.L.c2d_census_read(self.h, str(path).encode(), int(entries)))
+
+    def write_events(self, path, append=True):
+        """This step's escape records in the reference's event-file format (format 105, imcleak2d.f:181); the reference
+        appends to unit 1000+myid for the whole run.  Returns the number of records written."""
+        n = C.c_int64()
+        _l.check(self.L.c2d_events_write(self.h, str(path).encode(), 1 if append else 0, C.byref(n)))
+        return n.value
+
     # ------------------------------------------------------------------ event-list reduction
     def lc_begin(self, red):
         """Set the bin tables of the light-curve / SED reduction (`lightcurve.lc_reduction` = postprocessing/plcm.c's

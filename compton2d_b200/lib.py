@@ -89,7 +89,8 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
            "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
-           "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar"]
+           "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar",
+           "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7"]
 
 _lib = None
 
@@ -133,6 +134,11 @@ def load():
     L.c2d_comtot.argtypes = [vp, C.c_int64, vp, vp, C.c_int, vp]
     L.c2d_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), lp]
     L.c2d_tally_bench.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(C.c_float), lp]
+    L.c2d_census_write.argtypes = [vp, C.c_char_p, lp]
+    L.c2d_census_read.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.c2d_events_write.argtypes = [vp, C.c_char_p, C.c_int, lp]
+    L.c2d_format_e14_7.argtypes = [C.c_double, C.c_char_p]
+    L.c2d_format_e14_7.restype = None
     L.c2d_gamma_bar.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.c2d_lc_begin.argtypes = [vp, C.POINTER(LcConfig)]
     L.c2d_lc_accumulate.argtypes = [vp]

@@ -202,6 +202,20 @@ int c2d_census_export(c2d_ctx *ctx, double *dbuf, int32_t *ibuf, uint64_t *sid, 
 int c2d_census_import(c2d_ctx *ctx, const double *dbuf, const int32_t *ibuf, const uint64_t *sid, int64_t n);
 int c2d_events_drain(c2d_ctx *ctx, c2d_event *buf, int64_t cap, int64_t *n);
 
+/* ---- the device-owned state in the reference's own file formats ---------------------
+ * What write_record / read_record keep of a worker between runs is its census (write_record.f:432-437 ->
+ * p###_census.dat); what a worker writes while it runs is its event file (unit 1000+myid, imcleak2d.f:171,181).
+ * Both are text with Fortran E14.7 / I5 fields; these entry points produce and read exactly those files, so a run can be
+ * handed over between the reference and this library in either direction, and plcm / pspt keep working on the events. */
+int c2d_census_write(c2d_ctx *ctx, const char *path, int64_t *n_written);
+        /* == write_cens(ndxout, unit) (census2d.f:1-36): per photon `6e14.7` then `6i5` */
+int c2d_census_read(c2d_ctx *ctx, const char *path, int64_t entries);
+        /* == read_cens(entries, unit) (census2d.f:41-73) into the resident bank; entries = ndxout of p###_misc.dat */
+int c2d_events_write(c2d_ctx *ctx, const char *path, int append, int64_t *n_written);
+        /* the step's escape records as imcleak writes them: format 105 = 6(e14.7,1x),e14.7 (imcleak2d.f:181) */
+void c2d_format_e14_7(double v, char *out14);
+        /* the E14.7 edit descriptor as ifort prints it (14 characters, no terminator) */
+
 /* ---- event-list reduction -------------------------------------------------------
  * The reference turns its p###_evb.dat event files (one 105-byte text line per escaping photon, imcleak2d.f:181) into
  * light curves and SEDs with two stand-alone C programs that share one per-photon transform (Doppler boost with the bulk

@@ -229,6 +229,9 @@ def main(name):
     # event file of the worker (text, 7 doubles per record; imcleak2d.f:181)
     ev = np.loadtxt(rd / "p001_evb.dat", ndmin=2) if evt1.strip() else np.zeros((0, 7))
     out["events"] = ev
+    # the worker's event file as the binary formatted it (format 105 of imcleak2d.f:181), first 600 records: pins the
+    # e14.7 formatter of the library's reference-format writers (c2d_events_write / c2d_census_write)
+    (GOLD / f"evb_{name}.txt").write_text("".join(evt1.splitlines(keepends=True)[:600]))
     out["labels"] = np.array([lab for _, lab in pts])
     # scalars the log prints (FP energy check etc.) stay in the log; keep stdout tail for provenance
     GOLD.mkdir(parents=True, exist_ok=True)
