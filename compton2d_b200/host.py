@@ -412,20 +412,18 @@ class Compton2d:
         reference and plcm read them all, plcm.c:370-383,452-466); feed to lightcurve.finalize / finalize_sed."""
         shp = self._lc_shape
         s1, s2, cnt = np.zeros(shp), np.zeros(shp), np.zeros(shp, np.int64)
+        _l.check(self.L.c2d_lc_read(self.h, s1.ctypes.data, s2.ctypes.data, cnt.ctypes.data))
         if self.world == 1:
-            _l.check(self.L.c2d_lc_read(self.h, s1.ctypes.data, s2.ctypes.data, cnt.ctypes.data))
             return s1, s2, cnt
         import torch
         import torch.distributed as dist
-        ps, pc, n = C.c_void_p(), C.c_void_p(), C.c_int64()
-        _l.check(self.L.c2d_lc_device(self.h, C.byref(ps), C.byref(pc), C.byref(n)))
-        self.sync()
-        tf = torch.as_tensor(_CudaView(ps.value, 2 * n.value, "<f8"), device="cuda").clone()
-        ti = torch.as_tensor(_CudaView(pc.value, n.value, "<i8"), device="cuda").clone()
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"     # a few kB: reduced from the host copies
+        tf = torch.from_numpy(np.stack([s1, s2])).to(dev)
+        ti = torch.from_numpy(cnt).to(dev)
         dist.all_reduce(tf, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(ti, op=dist.ReduceOp.SUM, group=group)
         f = tf.cpu().numpy()
-        return f[: n.value].reshape(shp), f[n.value:].reshape(shp), ti.cpu().numpy().reshape(shp)
+        return f[0], f[1], ti.cpu().numpy()
 
     def lc_bench(self, n_events):
         """-> (ms, algorithmic bytes) of k_lc_reduce on n generated records with the current tables."""

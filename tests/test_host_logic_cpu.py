@@ -168,6 +168,10 @@ dist.init_process_group("gloo")
 rank, world = dist.get_rank(), dist.get_world_size()
 P = make_problem(nz=4, nr=3, nst=3000, ngroups=32, split=(20, 10, 3, 10), n_e=3.0e5)
 g = make_gpu(P, rank=rank, world=world)
+red = dict(gam_bulk=10.0, rmax=float(P["r"][-1]), t_offset=0.0, t_lo=np.arange(32) * 0.4 * P["dt"], t_hi=(np.arange(32) + 1) * 0.4 * P["dt"],
+           mu0=np.array([-1.0, 0.9]), mu1=np.array([0.9, 1.0]), mu_closed=0, E0=np.array([1e-9, 1e-3]), E1=np.array([1e-3, 1e3]),
+           first_band_only=0)
+g.lc_begin(red)
 tot = None
 for cyc in (1, 2):
     g.imcgen2d(ncycle=cyc, time=0.0, dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"], eps_th=P["eps_th"],
@@ -177,6 +181,7 @@ for cyc in (1, 2):
         g.imcfield2d()
     g.imcvol2d()
     g.sync()
+    g.lc_accumulate()
     t = g.tallies()
     # the reduction the CUDA path does in place on the device, here over gloo on the host copies
     pack = np.concatenate([t["edep"], t["ecens"], t["n_field"].ravel(), t["fout"].ravel(), t["E_IC"]])
@@ -186,8 +191,9 @@ for cyc in (1, 2):
     sid = g.census()[2]
     gathered = [None] * world
     dist.all_gather_object(gathered, sid)
+lc1, lc2, lcn = g.lc_read()
 if rank == 0:
-    np.savez(r"{out}", pack=tp.numpy(), ints=ti.numpy(), sid=np.sort(np.concatenate(gathered)))
+    np.savez(r"{out}", pack=tp.numpy(), ints=ti.numpy(), sid=np.sort(np.concatenate(gathered)), lc1=lc1, lc2=lc2, lcn=lcn)
 dist.destroy_process_group()
 '''
 
@@ -199,8 +205,13 @@ def test_two_ranks_equal_one(emu, tmp_path):
     from synth import make_problem
     P = make_problem(nz=4, nr=3, nst=3000, ngroups=32, split=(20, 10, 3, 10), n_e=3.0e5)
     g = make_gpu(P)
-    gpu_step(g, P, 1, field=False)
-    one = gpu_step(g, P, 2)
+    red = dict(gam_bulk=10.0, rmax=float(P["r"][-1]), t_offset=0.0, t_lo=np.arange(32) * 0.4 * P["dt"],
+               t_hi=(np.arange(32) + 1) * 0.4 * P["dt"], mu0=np.array([-1.0, 0.9]), mu1=np.array([0.9, 1.0]), mu_closed=0,
+               E0=np.array([1e-9, 1e-3]), E1=np.array([1e-3, 1e3]), first_band_only=0)
+    g.lc_begin(red)
+    gpu_step(g, P, 1, field=False); g.lc_accumulate()
+    one = gpu_step(g, P, 2); g.lc_accumulate()
+    lc_one = g.lc_read()
     g.close()
     out = tmp_path / "two.npz"
     script = tmp_path / "worker.py"
@@ -215,6 +226,9 @@ def test_two_ranks_equal_one(emu, tmp_path):
     pack1 = np.concatenate([one["edep"], one["ecens"], one["n_field"].ravel(), one["fout"].ravel(), one["E_IC"]])
     assert np.abs(two["pack"] - pack1).max() <= 1e-12 * np.abs(pack1).max()
     assert np.array_equal(two["sid"], np.sort(one["census"][2]))
+    # light-curve accumulators of the two ranks, summed, == the single-rank ones (every rank bins its own escape records)
+    assert np.array_equal(two["lcn"], lc_one[2]) and lc_one[2].sum() > 20
+    assert np.allclose(two["lc1"], lc_one[0], rtol=1e-12, atol=0) and np.allclose(two["lc2"], lc_one[1], rtol=1e-12, atol=0)
 
 
 def test_event_list_reduction_host_logic(emu):
