@@ -101,35 +101,61 @@ __device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab, bool
         bool done2 = false, done3 = false;
         double t = 1.0, dt32 = 1.0;
         for (int i = 0; i < 32; i++) { if (i < lane) t = t * dt; dt32 = dt32 * dt; }
-        double p0 = tab.x15[lane], p1 = tab.x15[32 + lane];       // two rounds of table loads in flight
-        for (int round = 0; round < 4096 && !(done2 && done3); round++) {
-            double x15;
-            if (round < kQuadRounds) {
-                x15 = p0; p0 = p1;
-                if (round + 2 < kQuadRounds) p1 = tab.x15[(round + 2) * 32 + lane];
-            } else {
-                x15 = quad_x15(t, s);
+        // Four rounds (128 terms) per trip: the stop tests are gathered per lane and the warp votes once; only the trip
+        // in which a quadrature ends is resolved round by round.  Per-lane summation order is unchanged.
+        double pf[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) pf[k] = tab.x15[k * 32 + lane];
+        for (int round = 0; round < 4096 && !(done2 && done3); round += 4) {
+            double tr[4], s2r[4], s3r[4];
+            unsigned st2 = 0u, st3 = 0u;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const double x15 = (round + k < kQuadRounds) ? pf[k] : quad_x15(t, s);
+                if (round + 4 + k < kQuadRounds) pf[k] = tab.x15[(round + 4 + k) * 32 + lane];   // next trip's loads in flight
+                const double ts = t * s, y = z * ts;
+                double sd2 = 0.0, sd3 = 0.0;
+                if (y < 2.25e2) {
+                    const double e = exp(-y);
+                    sd2 = x15 * e;                                // (ts^2 - 1)^(3/2) / exp(y)
+                    sd3 = sd2 * (ts * ts - 1.0);                  // (ts^2 - 1)^(5/2) / exp(y)
+                }
+                tr[k] = t; s2r[k] = sd2; s3r[k] = sd3;
+                if (!(t < 2.0 || sd2 > 1.e-8)) st2 |= 1u << k;
+                if (!(t < 2.0 || sd3 > 1.e-8)) st3 |= 1u << k;
+                t = t * dt32;
             }
-            const double ts = t * s, y = z * ts;
-            double sd2 = 0.0, sd3 = 0.0;
-            if (y < 2.25e2) {
-                const double e = exp(-y);
-                sd2 = x15 * e;                                    // (ts^2 - 1)^(3/2) / exp(y)
-                sd3 = sd2 * (ts * ts - 1.0);                      // (ts^2 - 1)^(5/2) / exp(y)
-            }
-            const unsigned stop2 = __ballot_sync(0xffffffffu, !(t < 2.0 || sd2 > 1.e-8));
-            const unsigned stop3 = __ballot_sync(0xffffffffu, !(t < 2.0 || sd3 > 1.e-8));
+            const bool any2 = __any_sync(0xffffffffu, st2 != 0u), any3 = __any_sync(0xffffffffu, st3 != 0u);
             if (!done2) {
-                const int last = stop2 ? (__ffs(stop2) - 1) : 31;
-                if (lane <= last) sum2 += d * t * sd2;
-                done2 = (stop2 != 0u);
+                if (!any2) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) sum2 += d * tr[k] * s2r[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (done2) break;
+                        const unsigned stop2 = __ballot_sync(0xffffffffu, (st2 >> k) & 1u);
+                        const int last = stop2 ? (__ffs(stop2) - 1) : 31;
+                        if (lane <= last) sum2 += d * tr[k] * s2r[k];
+                        done2 = (stop2 != 0u);
+                    }
+                }
             }
             if (!done3) {
-                const int last = stop3 ? (__ffs(stop3) - 1) : 31;
-                if (lane <= last) sum3 += d * t * sd3;
-                done3 = (stop3 != 0u);
+                if (!any3) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) sum3 += d * tr[k] * s3r[k];
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        if (done3) break;
+                        const unsigned stop3 = __ballot_sync(0xffffffffu, (st3 >> k) & 1u);
+                        const int last = stop3 ? (__ffs(stop3) - 1) : 31;
+                        if (lane <= last) sum3 += d * tr[k] * s3r[k];
+                        done3 = (stop3 != 0u);
+                    }
+                }
             }
-            t = t * dt32;
         }
         sum2 = warp_sum(sum2); sum3 = warp_sum(sum3);
         const double sp = sqrt(3.14159265e0);
@@ -312,7 +338,7 @@ __global__ void __launch_bounds__(128) k_gbar_table(double *tab, int n, double x
 }
 
 // shared-memory layout per warp: 9 arrays of N doubles
-__global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
+__global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -375,18 +401,36 @@ __global__ void __launch_bounds__(128) k_fp_zones(const FpParams q)
     {
         const double *nfld = q.n_field + (size_t)zi * nf;
         const double sc = scalbn(1.0, -ilogb(volume)), vs = volume * sc;
-        double *nf_s = a_i;                                       // a_i | b_i | c_i: 3 N doubles of scratch
-        const bool staged = nf <= 3 * N;
-        if (staged) { for (int ip = lane; ip < nf; ip += 32) nf_s[ip] = nfld[ip] * sc; __syncwarp(); }
+        // scratch a_i | b_i | c_i (3 N doubles): the non-empty bins compacted -- scaled value and bin index
+        double *nf_s = a_i;
+        int *nf_i = reinterpret_cast<int *>(a_i + nf);
+        const bool staged = 2 * nf + nf <= 2 * 3 * N;             // nf doubles + nf ints
+        int n_live = 0;
+        if (staged) {
+            for (int base = 0; base < nf; base += 32) {
+                const int ip = base + lane;
+                const double a = (ip < nf) ? nfld[ip] * sc : 0.0;
+                const unsigned m = __ballot_sync(0xffffffffu, a != 0.0);
+                __syncwarp();
+                if (a != 0.0) { const int pos = n_live + __popc(m & ((1u << lane) - 1u)); nf_s[pos] = a; nf_i[pos] = ip; }
+                n_live += __popc(m);
+            }
+            __syncwarp();
+        }
         for (int i0 = 0; i0 < N; i0 += 32) {
             const int i = i0 + lane;
             const bool live = i < N - 1;
             const double *F = q.F_ICt + (live ? i : 0);
             double v = 0.0;
-            for (int ip = 0; ip < nf; ip++) {
-                const double a = staged ? nf_s[ip] : nfld[ip] * sc;
-                if (a == 0.0) continue;                           // warp-uniform
-                v = v - a * F[(size_t)ip * N] / vs;
+            if (staged) {
+#pragma unroll 4
+                for (int jj = 0; jj < n_live; jj++) v = v - nf_s[jj] * F[(size_t)nf_i[jj] * N] / vs;
+            } else {
+                for (int ip = 0; ip < nf; ip++) {
+                    const double a = nfld[ip] * sc;
+                    if (a == 0.0) continue;                       // warp-uniform
+                    v = v - a * F[(size_t)ip * N] / vs;
+                }
             }
             if (i < N) dg_ic[i] = live ? v : 0.0;
         }
