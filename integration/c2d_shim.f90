@@ -54,6 +54,19 @@ module c2d_abi
      integer(c_int) function c2d_events_drain(ctx, buf, cap, n) bind(C, name='c2d_events_drain')
        import; type(c_ptr), value :: ctx, buf; integer(c_int64_t), value :: cap; integer(c_int64_t) :: n
      end function
+     integer(c_int) function c2d_events_write(ctx, path, append, n) bind(C, name='c2d_events_write')
+       import; type(c_ptr), value :: ctx; character(kind=c_char) :: path(*); integer(c_int), value :: append
+       integer(c_int64_t) :: n
+     end function
+     integer(c_int) function c2d_census_write(ctx, path, n) bind(C, name='c2d_census_write')
+       import; type(c_ptr), value :: ctx; character(kind=c_char) :: path(*); integer(c_int64_t) :: n
+     end function
+     integer(c_int) function c2d_census_read(ctx, path, entries) bind(C, name='c2d_census_read')
+       import; type(c_ptr), value :: ctx; character(kind=c_char) :: path(*); integer(c_int64_t), value :: entries
+     end function
+     integer(c_int) function c2d_lc_accumulate(ctx) bind(C, name='c2d_lc_accumulate')
+       import; type(c_ptr), value :: ctx
+     end function
      type(c_ptr) function c2d_last_error() bind(C, name='c2d_last_error')
        import
      end function
@@ -107,6 +120,35 @@ subroutine graphics_collect                        ! xec2d.f:371; also does xec_
   ! dense host copies, then scatter into COMMON: edep(j,k) = dense_edep(k + nr*(j-1)), n_field(:,j,k) via
   ! c2d_unpack_bin_first(dense, nphfield, jmax, kmax, nphfield, nz, nr, n_field), fout(1:nmu,1:nphtotal) ...
   call c2d_check(c2d_sync(ctx))
+  ! escaping photons: either the reference's event file, byte for byte (imcleak2d.f:181) ...
+  !   call c2d_check(c2d_events_write(ctx, 'p001_evb.dat'//c_null_char, 1_c_int, nev))
+  ! ... or binned on the device with plcm's / pspt's rules (c2d_lc_begin was called after setup)
+  call c2d_check(c2d_lc_accumulate(ctx))
   ! with more than one rank: MPI_Allreduce on the two device buffers of c2d_tally_device (CUDA-aware MPI / NCCL)
   call c2d_check(c2d_tally_read(ctx, t))
+end subroutine
+
+subroutine write_cens(entries, nunit_c)            ! census2d.f:1 -- called by write_record.f:435 for the worker's census
+  use c2d_abi
+  implicit none
+  integer entries, nunit_c
+  integer(c_int64_t) :: n
+  character*35 localrecord, recordfilename
+  include 'general.pa'
+  include 'commonblock.f'
+  close(nunit_c)                                   ! the library writes the same text (6e14.7 / 6i5 per photon)
+  localrecord = recordfilename('census.dat', myid)
+  call c2d_check(c2d_census_write(ctx, trim(localrecord)//c_null_char, n))
+  open(unit=nunit_c, file=localrecord, position='append')
+end subroutine
+
+subroutine read_cens(entries, nunit_c)             ! census2d.f:41 -- called by read_record.f
+  use c2d_abi
+  implicit none
+  integer entries, nunit_c
+  character*35 localrecord, recordfilename
+  include 'general.pa'
+  include 'commonblock.f'
+  localrecord = recordfilename('census.dat', myid)
+  call c2d_check(c2d_census_read(ctx, trim(localrecord)//c_null_char, int(entries, c_int64_t)))
 end subroutine
