@@ -178,13 +178,14 @@ def workload_config(args, ref=False):
 
 
 # ------------------------------------------------------------------------------------------ Fokker-Planck leg
-def fp_bench(local, hbm, reps=3, nz=64, nr=64):
+def fp_bench(local, hbm, reps=3, nz=64, nr=64, bins=200):
     """FP zone-steps/s (second half of BASELINE.json's metric) on the BASELINE configs[4] grid: 64 x 64 zones, the
     reference's 200 momentum bins (its compile-time num_nt; 512 bins exceed what the reference can run),
     every zone carrying the reference binary's own pre-FP state of the shipped plasma (tests/golden/refbin_small.npz,
     snapshot c2_E, zone (1,1): electron spectrum, tallied photon field, shipped injection block with the pick-up
     Gaussian on), photon field jittered +-10 % per zone.  One call = FP_calc for all zones (c2d_update_fp); a zone-step =
-    one implicit Chang-Cooper sub-step of one zone."""
+    one implicit Chang-Cooper sub-step of one zone.  bins = 512: the configs[4] momentum grid gamma - 1 = 0.2 q^(i-2),
+    q = (1.1^198)^(1/510), the binary's spectrum resampled onto it (as tests/test_gpu_configs.py does)."""
     import numpy as np
     from golden_util import Golden
     from parity_util import make_gpu
@@ -192,6 +193,14 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64):
     E = Golden("small").snap("c2_E")
     P = make_problem(nz=nz, nr=nr, nst=1000, ngroups=100)
     nzone = nz * nr
+    f_nt, pnt = np.asarray(E.f_nt[0, 0], float), np.asarray(E.pnt[0, 0], float)
+    if bins != 200:
+        gnt = 0.2 * ((1.1 ** 198) ** (1.0 / (bins - 2))) ** (np.arange(1, bins + 1) - 2.0)
+        f = np.exp(np.interp(np.log(gnt), np.log(np.asarray(E.gnt)), np.log(np.maximum(f_nt, 1e-300))))
+        f[f < 1e-250] = 0.0; f[-1] = 0.0
+        f_nt = f / (f[:-1] * np.diff(gnt)).sum()
+        pnt = np.concatenate(([0.0], np.cumsum(f_nt[:-1] * np.diff(gnt))))
+        P["gnt"] = gnt
     g = make_gpu(P, census_capacity=1000, event_capacity=1000, device=local)
     try:
         g.timing(True)
@@ -203,7 +212,7 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64):
         n_field = til(E.n_field[:, 0, 0]) * vr[:, None] * (1.0 + 0.2 * (rng.random((nzone, 1)) - 0.5))
         inj = {k: float(E[k.lower()]) for k in ("inj_g1", "inj_g2", "inj_p", "inj_t", "inj_gg", "inj_sigma", "inj_L", "inj_v", "pick_rate")}
         inj.update({k: int(E[k]) for k in ("inj_switch", "inj_dis", "g2var_switch", "pick_sw")})
-        kw = dict(time=2.0 * P["dt"], dt=P["dt"], f_nt=til(E.f_nt[0, 0]), Pnt=til(E.pnt[0, 0]), n_e=np.full(nzone, float(E.n_e[0, 0])),
+        kw = dict(time=2.0 * P["dt"], dt=P["dt"], f_nt=til(f_nt), Pnt=til(pnt), n_e=np.full(nzone, float(E.n_e[0, 0])),
                   B_field=np.full(nzone, float(E.b_field[0, 0])), tea=np.full(nzone, float(E.tea[0, 0])),
                   tna=np.full(nzone, float(E.tna[0, 0])), vol=P["vol"], Eloss_sy=float(E.eloss_sy[0, 0]) * vr * tr,
                   ec_old=float(E.ec_old[0, 0]) * vr, turb_lev=np.full(nzone, float(E.turb_lev[0, 0])),
@@ -228,7 +237,8 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64):
                 "kernel_ms_per_call": ms / reps, "launches": int(nl),
                 "roofline": {"bound": "hbm", "kernel": "k_fp_zones", "achieved": ach, "peak": hbm, "unit": "GB/s",
                              "frac": ach / hbm, "traffic": None},
-                "workload": "BASELINE configs[4] grid 64x64 zones x 200 bins (reference's num_nt), shipped plasma + injection block"}
+                "workload": f"BASELINE configs[4] grid 64x64 zones x {bins} bins" + (" (reference's num_nt)" if bins == 200 else
+                            " (configs[4] momentum grid)") + ", shipped plasma + injection block"}
     finally:
         g.close()
 
@@ -424,6 +434,7 @@ def our_arm(args):
     if not args.no_fp and world == 1:
         try:
             out["fp"] = fp_bench(local, hbm)
+            out["fp512"] = fp_bench(local, hbm, bins=512)
         except Exception as e:                     # the FP leg must never take the headline down with it
             out["fp"] = {"error": repr(e)[:300]}
     if not args.no_cpu_baseline and world == 1:
@@ -464,6 +475,8 @@ def legs_only(args):
         g.close()
     if "fp" in legs:
         out["fp"] = fp_bench(0, hbm)
+    if "fp512" in legs:
+        out["fp512"] = fp_bench(0, hbm, bins=512)
     print(json.dumps(out))
 
 

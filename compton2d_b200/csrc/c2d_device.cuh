@@ -21,6 +21,10 @@
 
 namespace c2d {
 
+// x**2 as the Fortran compiler evaluates it: one multiplication (exactly rounded, unlike the device pow)
+__host__ __device__ __forceinline__ double sq(double x) { return x * x; }
+
+
 constexpr double kPi = 3.1415926536e0;        // general.pa:25
 constexpr double kRadCp = 3.333564097e-11;    // general.pa:24
 constexpr double kCLight = 2.9979245620e10;   // general.pa:26

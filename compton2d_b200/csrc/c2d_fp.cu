@@ -159,7 +159,7 @@ __device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab, bool
         }
         sum2 = warp_sum(sum2); sum3 = warp_sum(sum3);
         const double sp = sqrt(3.14159265e0);
-        const double K2 = sp * pow(5.e-1 * z, 2.0) * sum2 / exp(gammln_dev(2.5));
+        const double K2 = sp * sq(5.e-1 * z) * sum2 / exp(gammln_dev(2.5));
         const double K3 = sp * pow(5.e-1 * z, 3.0) * sum3 / exp(gammln_dev(3.5));
         g = K3 / K2 - Theta;
     }
@@ -385,8 +385,8 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
     const double zmid = (j > 1) ? 5.e-1 * (q.z[j - 1] + q.z[j - 2]) : 5.e-1 * (q.z[j - 1] + q.zmin);
     double tl_flare = 0.0;
     if (q.cf_sentinel == 1) {
-        const double y = 5.e-1 * (pow((rmid - q.r_flare) / q.sigma_r, 2.0) + pow((zmid - q.z_flare) / q.sigma_z, 2.0) +
-                                  pow((q.time - q.t_flare) / q.sigma_t, 2.0));
+        const double y = 5.e-1 * (sq((rmid - q.r_flare) / q.sigma_r) + sq((zmid - q.z_flare) / q.sigma_z) +
+                                  sq((q.time - q.t_flare) / q.sigma_t));
         tl_flare = (y < 1.e2) ? q.flare_amp / exp(y) : 0.0;
     }
     const double tlev = q.turb_lev[zi] + tl_flare;
@@ -447,8 +447,8 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
             hr_th_c = hr_th_c - 8.176e-7 * dg_ic[i] * f_old[i] * (gnt[i + 1] - gnt[i]) * volume * n_lept;
         hr_th_c = warp_sum(hr_th_c);
         const double gamma_R = 2.1e-3 * sqrt(n_lept) / (B * sqrt(g_av));
-        const double h_T = (double).79788f * (2. * pow(Th_e + Th_p, 2.0) + 2.0 * (Th_e + Th_p) + 1.0) /
-                           (pow(Th_e + Th_p, 1.5) * (1.0 + 1.875 * Th_e + .8203 * pow(Th_e, 2.0)));
+        const double h_T = (double).79788f * (2. * sq(Th_e + Th_p) + 2.0 * (Th_e + Th_p) + 1.0) /
+                           (pow(Th_e + Th_p, 1.5) * (1.0 + 1.875 * Th_e + .8203 * sq(Th_e)));
         const double hr_th_Coul = f_th * 1.7386e-26 * n_p * q.lnL * h_T * (Tp_flare - Te_new);
         double y = gamma_R / g_av;
         const double hr_th_sy = (y < 100.0) ? -q.Eloss_sy[zi] / (dt1 * exp(y)) : 0.0;
@@ -458,13 +458,13 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
         const double dT_total = 6.25e8 * dt1 * hr_th_total / f_th;
         f_t_implicit = 1.e-2 * Te_new / fabs(dT_total);               // df_implicit, general.pa:27
         if (f_t_implicit > 2.5e-1) f_t_implicit = 2.5e-1;              // df_T, general.pa:28
-        const double f_sy = 1.058e-15 * pow(B, 2.0) / 8.176e-7;
+        const double f_sy = 1.058e-15 * sq(B) / 8.176e-7;
         const double g_thr = 1.0 + 4.0 * Th_e;
         double hr_st_A = 0.0, hr_nt_A = 0.0;
         for (int i = lane; i < N; i += 32) {                          // loops 300 + 350, live terms
             const double gam = gnt[i] + 1.0;
             y = gamma_R / gam;
-            const double dg_sy = (y < 100.0) ? -f_sy * (pow(gam, 2.0) - 1.0) / exp(y) : -1.e-50;
+            const double dg_sy = (y < 100.0) ? -f_sy * (sq(gam) - 1.0) / exp(y) : -1.e-50;
             const double dg_A = gam / t_acc;
             dgdt[i] = dg_sy + dg_ic[i] + dg_A;
             if (i < N - 1) {
@@ -493,7 +493,7 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
             double inj_sum = 0.0;
             for (int i = lane; i < N - 1; i += 32) {
                 const double gam = gnt[i] + 1.0;
-                const double v = 1.e2 * exp(-pow(gam - q.inj_gg, 2.0) / 2 / pow(q.inj_sigma, 2.0)) / (q.inj_sigma * sqrt(2 * pi));
+                const double v = 1.e2 * exp(-sq(gam - q.inj_gg) / 2 / sq(q.inj_sigma)) / (q.inj_sigma * sqrt(2 * pi));
                 a_i[i] = v;
                 inj_sum += v * (gnt[i + 1] - gnt[i]);
             }
@@ -516,7 +516,7 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
                     const double gam = gnt[i] + 1.0;
                     double v = 0.0;
                     if (q.inj_dis == 1) {
-                        v = 1.e2 * exp(-pow(gam - q.inj_gg, 2.0) / 2 / pow(q.inj_sigma, 2.0)) / (q.inj_sigma * sqrt(2 * pi));
+                        v = 1.e2 * exp(-sq(gam - q.inj_gg) / 2 / sq(q.inj_sigma)) / (q.inj_sigma * sqrt(2 * pi));
                     } else if (q.inj_dis == 2) {
                         if (gam > q.inj_g1) {
                             const double inj_y = (q.g2var_switch == 1) ? gam / inj_g2var : gam / q.inj_g2;
@@ -671,11 +671,14 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
         __syncwarp();
         double sum_g = 1.e50, sumg_old;
         p_nth = (double)0.1f;
+        // gmax^(1-p), gmin^(1-p) of the normalisation N_nt (which cancels in sg / sgg up to rounding) are carried the same way
+        double pgx = pow(gmax, 1.0 - p_nth), pgn = pow(gmin, 1.0 - p_nth);
+        const double pgx_step = pow(gmax, -0.5e-1), pgn_step = pow(gmin, -0.5e-1);
         for (;;) {
             sumg_old = sum_g;
             const double p_1 = 1.0 - p_nth;
             double N_nt;
-            if (fabs(p_1) > 1.e-4) N_nt = (1. - amxwl) * p_1 / (pow(gmax, p_1) - pow(gmin, p_1));
+            if (fabs(p_1) > 1.e-4) N_nt = (1. - amxwl) * p_1 / (pgx - pgn);
             else N_nt = (1.0 - amxwl) / log(gmax / gmin);
             double sg = 0.0, sgg = 0.0;
             for (int i = lane; i < N; i += 32) {
@@ -688,7 +691,7 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
             sg = warp_sum(sg); sgg = warp_sum(sgg);
             sum_g = fabs(sg / sgg - sum_E);
             if (sum_g < sumg_old) {
-                if (p_nth < 10.) { p_nth = p_nth + 0.5e-1; continue; }
+                if (p_nth < 10.) { p_nth = p_nth + 0.5e-1; pgx = pgx * pgx_step; pgn = pgn * pgn_step; continue; }
             }
             break;
         }

@@ -51,7 +51,7 @@ __global__ void __launch_bounds__(128) k_volume_sy(const __grid_constant__ GenPa
     const double ee = 4.803e-10, em = 9.109e-28, sigmaT = 6.6524616e-25;
     const double B = q.B_field[zi], ne_local = q.n_e[zi];
     const double nu_b = ee * B / (2 * kPi * em * kCLight);
-    const double Ub = pow(B, 2.0) / (8.0 * kPi);
+    const double Ub = sq(B) / (8.0 * kPi);
     const double face = pow(3.0, 1.5) * sigmaT * kCLight * Ub / (kPi * nu_b);
     const double nu_p = 9.e3 * sqrt(ne_local);
     const double nu = 2.41487e17 * q.E_ph[i];
@@ -60,11 +60,11 @@ __global__ void __launch_bounds__(128) k_volume_sy(const __grid_constant__ GenPa
         const double *f = q.f_nt + (size_t)zi * q.N;
         double sum = 0., sum_k = 0.;
         double g_cur = q.gnt[0] + 1.0;
-        double gamp_cur = g_cur * sqrt(pow(g_cur, 2.0) - 1.0);
+        double gamp_cur = g_cur * sqrt(sq(g_cur) - 1.0);
         for (int i2 = 0; i2 < q.N - 1; i2++) {
             const double g_next = q.gnt[i2 + 1] + 1.0;
-            const double gamp_next = g_next * sqrt(pow(g_next, 2.0) - 1.0);
-            const double facg = 3.0 * pow(g_cur, 2.0) * nu_b;
+            const double gamp_next = g_next * sqrt(sq(g_next) - 1.0);
+            const double facg = 3.0 * sq(g_cur) * nu_b;
             const double tt = nu / facg;
             double es = 0.0;
             if (tt < 1.0e4) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(64) k_volume_cdf(const __grid_constant__ GenPa
     }
     const double *f = q.f_nt + (size_t)zi * q.N;
     double sum_g_1 = 0.;
-    for (int i = 0; i < q.N - 1; i++) sum_g_1 = sum_g_1 + (pow(q.gnt[i] + 1.0, 2.0) - 1.0) * f[i] * (q.gnt[i + 1] - q.gnt[i]);
+    for (int i = 0; i < q.N - 1; i++) sum_g_1 = sum_g_1 + (sq(q.gnt[i] + 1.0) - 1.0) * f[i] * (q.gnt[i + 1] - q.gnt[i]);
     q.sum_th[zi] = sum_th;
     q.sum_g1[zi] = sum_g_1;
 }
