@@ -236,7 +236,8 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64, bins=200):
                 "e2e_value": steps / wall, "zones": nzone, "bins": N, "sub_steps_per_zone": steps / (reps * nzone),
                 "kernel_ms_per_call": ms / reps, "launches": int(nl),
                 "roofline": {"bound": "hbm", "kernel": "k_fp_zones", "achieved": ach, "peak": hbm, "unit": "GB/s",
-                             "frac": ach / hbm, "traffic": None},
+                             "frac": ach / hbm, "traffic": 21.0e6 if bins == 200 else None,
+                             "note": "latency-bound (McDonald quadratures, Thomas recurrence): HBM is not the limiter, see DESIGN.md 4"},
                 "workload": f"BASELINE configs[4] grid 64x64 zones x {bins} bins" + (" (reference's num_nt)" if bins == 200 else
                             " (configs[4] momentum grid)") + ", shipped plasma + injection block"}
     finally:
@@ -267,6 +268,11 @@ def lc_bench(g, hbm, n_events=100_000_000):
     the reference's own postprocessing/mrk421_lc.input (content reproduced above): 56 algorithmic B/record."""
     from compton2d_b200.lightcurve import lc_reduction, parse_lc_input
     cfg = parse_lc_input(MRK421_LC)
+    per_rec = None
+    try:
+        per_rec = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())["k_lc_reduce_dram_bytes_per_record"]
+    except Exception:
+        pass
     out = {"kernel": "k_lc_reduce", "events": n_events, "bins": "postprocessing/mrk421_lc.input (1 mu window, 7 bands)"}
     for label, st_max in (("shared_acc_128_time_bins", 128), ("hbm_acc_1024_time_bins", 1024)):
         g.lc_begin(lc_reduction(cfg, st_max=st_max))
@@ -274,7 +280,8 @@ def lc_bench(g, hbm, n_events=100_000_000):
         best = min(g.lc_bench(n_events)[0] for _ in range(3))
         ach = 56.0 * n_events / (best * 1e-3) / 1e9
         out[label] = {"ms": best, "events_per_s": n_events / (best * 1e-3),
-                      "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None}}
+                      "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                                   "traffic": per_rec * n_events if per_rec else None}}
     return out
 
 
