@@ -42,8 +42,9 @@ def _fine_grid(n=512):
     return g
 
 
-def test_c4_shape_fp_parity():
-    N, nz, nr = 512, 8, 8                      # 64 of the 4096 zones: the oracle needs ~0.2 s per zone at 512 bins
+@pytest.mark.parametrize("N", [512, 128])       # 128 bins: nphfield > 2 N, the dg_ic loop without its shared-memory staging
+def test_c4_shape_fp_parity(N):
+    nz, nr = 8, 8                              # 64 of the 4096 zones: the oracle needs ~0.2 s per zone at 512 bins
     E = Golden("small").snap("c2_E")
     gnt = _fine_grid(N)
     P = make_problem(nz=nz, nr=nr, nst=100, ngroups=32)
