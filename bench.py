@@ -128,14 +128,17 @@ def run_reference_sample(nst, ncores=1, warm=0, timed=2, workdir=None, fp=False,
             hist += nct[cyc - 1] + nct[0]
             cyc_secs[k] = max(cyc_secs[k], tt[pts[f"c{cyc}_D"]] - tt[pts[f"c{cyc}_A"]])
         if fp and "c1_F" in pts:
+            # the FP farm of cycle 1 (fp_mpi.f:596 FP_bcast .. first E_add_up reduce); sub-steps as the worker prints them
             fp_secs.append(tt[pts["c1_F"]] - tt[pts["c1_E"]])
-            fp_steps += 5 * nz * nr
+            steps = [int(l.split("=")[-1]) for l in out.splitlines() if "fp_steps=" in l]
+            fp_steps += sum(steps[: nz * nr]) if len(steps) >= nz * nr else 5 * nz * nr
     shutil.rmtree(base, ignore_errors=True)
     secs = sum(cyc_secs)
     r = {"histories": hist, "seconds": secs, "value": hist / secs, "wall_s": wall, "cores": ncores,
          "ms_per_step": 1e3 * secs / timed}
     if fp_secs:
         r["fp_zone_steps_per_s"] = fp_steps / max(fp_secs)
+        r["fp_zone_steps"], r["fp_seconds"] = fp_steps, max(fp_secs)
     return r
 
 
@@ -444,6 +447,12 @@ def our_arm(args):
             out["fp512"] = fp_bench(local, hbm, bins=512)
         except Exception as e:                     # the FP leg must never take the headline down with it
             out["fp"] = {"error": repr(e)[:300]}
+    if not args.no_cpu_baseline and not args.no_fp and world == 1 and isinstance(out.get("fp"), dict) and "value" in out["fp"]:
+        r = run_reference_sample(1000, ncores=1, warm=0, timed=2, fp=True, nz=4, nr=4)
+        if r and "fp_zone_steps_per_s" in r:
+            out["fp"]["cpu_baseline"] = {"value": r["fp_zone_steps_per_s"], "unit": "zone-steps/s", "cores": 1, "kind": "reference",
+                                         "sample": f"FP farm of cycle 1 of the prebuilt reference binary, 4x4 zones x 200 bins: "
+                                                   f"{r['fp_zone_steps']} zone-steps in {r['fp_seconds']:.1f} s on 1 worker core"}
     if not args.no_cpu_baseline and world == 1:
         r = run_reference_sample(args.cpu_nst, ncores=1, warm=0, timed=2)
         if r and "error" not in r:
