@@ -149,6 +149,18 @@ static int drain_queue(Ctx *c)
     return fail(C2D_EINVAL, "scattering cascade did not terminate after 1000 generations");
 }
 
+// cr_sent = 1 reflects specularly only where the lower boundary has no temperature (imcleak2d.f:113); a hot boundary
+// reflects through the P_ref / W_abs matrices of ref_matrix.f (l.124-158), which are not built
+static int check_mirror(Ctx *c, const double *tbbl)
+{
+    if (c->dims.cr_sent != 1 || !tbbl) return 0;
+    for (int k = 0; k < c->dims.nr; k++)
+        if (tbbl[k] > 0.0)
+            return fail(C2D_EINVAL, "cr_sent = 1 with tbbl(%d) = %g > 0: Compton reflection off a hot lower boundary (imcleak2d.f:124-158) "
+                        "is not built", k + 1, tbbl[k]);
+    return 0;
+}
+
 static int check_fatal(Ctx *c)
 {
     unsigned long long cnt[CNT_N];
@@ -282,7 +294,9 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c || !d) return fail(C2D_EINVAL, "NULL argument");
     if (c->inited) return fail(C2D_ESTATE, "context already initialised");
-    if (d->cr_sent != 0) return fail(C2D_EINVAL, "cr_sent = %d: Compton reflection (imcleak2d.f:107-165,216-273) is not built", d->cr_sent);
+    if (d->cr_sent != 0 && d->cr_sent != 1 && d->cr_sent != 4)
+        return fail(C2D_EINVAL, "cr_sent = %d: Compton reflection off the outer cylinder (imcleak2d.f:216-273, P_ref / W_abs of ref_matrix.f) "
+                    "is not built; cr_sent = 1 (cold lower boundary) and 4 mirror at the lower surface", d->cr_sent);
     if (d->nz < 1 || d->nr < 1 || d->nz > 65535 || d->nr > 65535) return fail(C2D_EINVAL, "bad grid %d x %d", d->nz, d->nr);
     if (d->nmu < 1 || d->nmu > C2D_NMUMAX || d->nph_lc < 0 || d->nph_lc > C2D_NLCMAX || d->nphtotal < 1 || d->nphtotal > 65535)
         return fail(C2D_EINVAL, "bad bin counts nmu=%d nph_lc=%d nphtotal=%d", d->nmu, d->nph_lc, d->nphtotal);
@@ -377,7 +391,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     memset(&P, 0, sizeof P);
     P.nz = d->nz; P.nr = d->nr; P.nzone = nzone; P.n_vol = d->n_vol; P.num_nt = d->num_nt; P.nphfield = d->nphfield;
     P.n_gg = d->n_gg; P.nphtotal = d->nphtotal; P.nph_lc = d->nph_lc; P.nmu = d->nmu;
-    P.pair_switch = d->pair_switch; P.spec_switch = d->spec_switch;
+    P.pair_switch = d->pair_switch; P.spec_switch = d->spec_switch; P.cr_sent = d->cr_sent;
     P.split1 = d->split1; P.split2 = d->split2; P.split3 = d->split3; P.spl3_trg = d->spl3_trg;
     P.sigma_mode = d->sigma_mode;
     P.key0 = d->rseed; P.rmin = d->rmin; P.zmin = d->zmin;
@@ -437,6 +451,7 @@ int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
     rc |= upload(c, T + c->o_fpair, in->f_pair, nzone);
     rc |= upload(c, T + c->o_kgg, in->k_gg, (size_t)nzone * d.n_gg);
     rc |= upload(c, T + c->o_tbbl, in->tbbl, d.nr);
+    if (int rc_m = check_mirror(c, in->tbbl)) return rc_m;
     rc |= upload(c, T + c->o_ewsv, in->ewsv, nzone);
     rc |= upload(c, T + c->o_elth, in->Eloss_th, nzone);
     rc |= upload(c, T + c->o_eltot, in->Eloss_tot, nzone, 1.0);
@@ -502,6 +517,7 @@ int c2d_step_begin_gen(c2d_ctx *h, const c2d_gen_in *in, c2d_gen_out *out)
     rc |= upload(c, T + c->o_fpair, in->f_pair, nzone);
     rc |= upload(c, T + c->o_kgg, in->k_gg, (size_t)nzone * d.n_gg);
     rc |= upload(c, T + c->o_tbbl, in->tbbl, d.nr);
+    if (int rc_m = check_mirror(c, in->tbbl)) return rc_m;
     rc |= upload(c, T + c->o_zsurf, in->zsurf, nzone, 1.0);
     rc |= upload(c, T + c->o_tea, in->tea, nzone);
     if (rc) return rc;
@@ -657,6 +673,7 @@ int c2d_surf_begin(c2d_ctx *h, const c2d_surf_in *in)
     // tbbl(k,ti) is one COMMON array in the reference: the lower-face leak test of imcleak (imcleak2d.f:95) reads the
     // same values the source uses, so a tbbl given here replaces the one of c2d_step_begin
     if (in->tbbl) { if (int rc = upload(c, c->d_step + c->o_tbbl, in->tbbl, nr)) return rc; }
+    if (int rc_m = check_mirror(c, in->tbbl)) return rc_m;
     // one blob: prefix | ew | tbb | E F P a1 I | spec | nfile
     const size_t nt = (size_t)in->n_spec * in->nfmax;
     const size_t bytes = (size_t)(nslot + 1) * 8 + (size_t)nslot * 16 + nt * 40 + (size_t)nslot * 4 + (size_t)std::max(in->n_spec, 1) * 4 + 64;

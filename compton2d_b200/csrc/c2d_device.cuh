@@ -11,7 +11,7 @@
 //   dilog_neg()      comtot2d.f:356-433   CERNLIB C332 dilogarithm (argument -x, x > 0)
 //   compb2d()        compb_2d.f:1-318     one Compton scattering
 //   nth2d()          nontherm2d.f:159-183 electron draw from Pnt
-//   imcleak()        imcleak2d.f:2-320    boundary tallies + escape record (cr_sent = 0)
+//   imcleak()        imcleak2d.f:2-320    boundary tallies + escape record; specular mirror at the lower surface (cr_sent = 1 / 4)
 //   source_volume()  imcvol2d_para.f:157-389
 // The arithmetic follows the reference expression by expression (REAL*4 literals included) so that
 // integer outcomes replay exactly against the CPU oracle; compile with -fmad=false.
@@ -80,7 +80,7 @@ struct Seg {                 // one zone crossing of the collision-free ray of a
 
 struct Params {
     int nz, nr, nzone, n_vol, num_nt, nphfield, n_gg, nphtotal, nph_lc, nmu;
-    int pair_switch, spec_switch, split1, split2, split3, spl3_trg, ncycle, sigma_mode;
+    int pair_switch, spec_switch, cr_sent, split1, split2, split3, spl3_trg, ncycle, sigma_mode;
     uint32_t key0, key1;
     double rmin, zmin, dt, time;
     // static tables
@@ -708,7 +708,16 @@ __device__ __forceinline__ void escape_tally(const Params &p, const Photon &P, d
     if (P.jgpsp > 0 && p.spec_switch == 0) atomic_add_f64(p.fout + (P.jgpmu - 1) * p.nphtotal + (P.jgpsp - 1), P.ew);
 }
 
-// imcleak2d.f:2-320 with cr_sent = 0.  Returns idead.
+// imcleak2d.f:329-405
+__device__ __forceinline__ void get_bin(const Params &p, Photon &P)
+{
+    P.jgpsp = sp_group(p, P.xnu, (double)1.000001f, (double).999999f, 0);
+    P.jgplc = lc_group(p, P.xnu);
+    P.jgpmu = mu_group(p, P.wmu);
+}
+
+// imcleak2d.f:2-320.  cr_sent = 0, or the specular mirror at the lower surface (l.107-122: cr_sent = 4, or cr_sent = 1 where
+// the boundary has no temperature -- c2d_step_begin refuses the other combinations).  Returns idead.
 __device__ __forceinline__ int imcleak(const Params &p, Photon &P)
 {
     const double t_bound = p.time + p.dt - kRadCp * P.dcen;     // l.203,302 (lower face: see DESIGN.md)
@@ -721,6 +730,13 @@ __device__ __forceinline__ int imcleak(const Params &p, Photon &P)
         if (p.tbbl[P.kph - 1] > 0.0) {
             atomic_add_f64(p.Ed_in + (P.kph - 1), P.ew);
             atomic_add_f64(p.erlkl + (P.kph - 1), P.ew);
+        }
+        if (p.cr_sent != 0) {                                     // l.113-122, 160-165: wmu -> -wmu, the flight goes on in row 1
+            P.wmu = -P.wmu;
+            if (P.jgpsp > 0 && p.spec_switch == 1) atomic_add_f64(p.fout + (P.jgpmu - 1) * p.nphtotal + (P.jgpsp - 1), P.ew);
+            get_bin(p, P);
+            P.jph = 1;
+            return 0;
         }
         if (p.ncycle > 0) escape_tally(p, P, t_bound);
         return 1;

@@ -32,7 +32,7 @@ extern "C" {
 enum {
     C2D_OK = 0,
     C2D_ENODEV = 1,        /* no CUDA device / wrong architecture */
-    C2D_EINVAL = 2,        /* bad argument or unsupported switch (cr_sent != 0, ...) */
+    C2D_EINVAL = 2,        /* bad argument or unsupported switch (cr_sent = 2 / 3, ...) */
     C2D_ECUDA = 3,         /* CUDA runtime error (message in c2d_last_error) */
     C2D_ECENSUS = 4,       /* census bank full: the reference's 'too many photons' STOP (imctrk2d.f:581-585) */
     C2D_EEVENTS = 5,       /* event buffer full (records beyond capacity were counted, not stored) */
@@ -47,7 +47,8 @@ typedef struct {
     int nz, nr;                       /* commonblock.f /zones/ */
     int n_vol, num_nt, nphfield, n_gg; /* general.pa:13-18 (400, 200, 400, 100 in the reference build) */
     int nphtotal, nph_lc, nmu;        /* spectrum groups, light-curve bands, angle bins (setup2d.f:148-173) */
-    int pair_switch, cr_sent, spec_switch;   /* reader.f sentinels; cr_sent must be 0 */
+    int pair_switch, cr_sent, spec_switch;   /* reader.f sentinels; cr_sent: 0, or 1 / 4 = specular reflection at the lower surface
+                                                (imcleak2d.f:107-122; 1 needs tbbl <= 0 everywhere); 2, 3 are refused */
     int split1, split2, split3, spl3_trg;    /* reader.f:587-590 */
     int64_t census_capacity;          /* ucens (general.pa:7), photons */
     int64_t event_capacity;           /* escape records kept per step */

@@ -502,10 +502,12 @@ static void escape_tally(orc_state *s)
         s->fout[(s->jgpmu - 1) * s->nphtotal + (s->jgpsp - 1)] += s->ew;
 }
 
-/* imcleak2d.f:2-320, cr_sent = 0 paths (Compton reflection is SURVEY 8f N4: no oracle, not built) */
+/* imcleak2d.f:2-320.  Of the reflection options (cr_sent != 0) the specular mirror at the lower surface is
+ * restated (l.107-122: cr_sent = 4, or cr_sent = 1 / 3 where the boundary has no temperature, tbbl <= 0 -- every shipped
+ * input); the Green's-function reflection off a hot lower boundary (l.124-158) and off the outer cylinder (cr_sent = 2 / 3,
+ * l.216-273) needs P_ref / W_abs of ref_matrix.f and raises fatal = 3. */
 void orc_imcleak(orc_state *s)
 {
-    if (s->cr_sent != 0) { s->fatal = 3; s->idead = 1; return; }
     if (s->kph == 0) {                       /* inner r boundary, l.71-88 */
         if (s->rmin > 1.e-10) {
             s->idead = 1;
@@ -522,6 +524,19 @@ void orc_imcleak(orc_state *s)
             s->Ed_in[s->kph - 1] += s->ew;
             s->erlkl[s->kph - 1] += s->ew;
         }
+        if (s->cr_sent == 1 || s->cr_sent == 3 || s->cr_sent == 4) {       /* l.107-165 */
+            if (s->tbbl[s->kph - 1] <= 0.0 || s->cr_sent == 4) {           /* specular reflection, l.113-122 */
+                s->wmu = -s->wmu;
+                if (s->jgpsp > 0 && s->spec_switch == 1)
+                    s->fout[(s->jgpmu - 1) * s->nphtotal + (s->jgpsp - 1)] += s->ew;
+                orc_get_bin(s);                                            /* label 60, l.160-165 */
+                s->idead = 0;
+                s->jph = 1;
+                return;
+            }
+            s->fatal = 3; s->idead = 1;                                    /* P_ref / W_abs reflection: not restated */
+            return;
+        }
         /* no reflection: photon exits.  The FORTRAN does not update t_bound here
          * (stale COMMON value of the previous escape); order-free Philox mode uses the
          * formula of the other faces. */
@@ -530,8 +545,12 @@ void orc_imcleak(orc_state *s)
         s->idead = 1;
         return;
     }
-    if (s->jph != s->nz + 1) {               /* outer r boundary, l.194-212 (cr_sent = 0) */
+    if (s->jph != s->nz + 1) {               /* outer r boundary, l.194-212 */
         s->erlko[s->jph - 1] += s->ew;
+        if (!(s->wmu > 0. || s->cr_sent == 0 || s->cr_sent == 1 || s->cr_sent == 4)) {    /* l.197-198: else l.216-273 */
+            s->fatal = 3; s->idead = 1;
+            return;
+        }
         s->t_bound = s->time + s->dt - RAD_CP * s->dcen;
         if (s->ncycle > 0) escape_tally(s);
         s->idead = 1;

@@ -43,6 +43,10 @@ CONFIGS = {
     # rmin > 0 (inner boundary absorbs), nmu = 1, different seed
     "annulus": dict(over=dict(nz=3, nr=4, nst=5000, tstop="1.e+3", rmin="0.2d16", rseed=4242),
                     zone={}),
+    # specular reflection at the lower surface: cr_sent = 1 with the shipped cold boundary (tbbl = -0.d0),
+    # imcleak2d.f:107-122; denser plasma and small splits so that scattered photons bounce too
+    "mirror": dict(over=dict(nz=3, nr=3, nst=1500, tstop="1.e+3", cr_sent=1, split1=60, split2=40, split3=12, rseed=777),
+                   zone=dict(n_e="0.300e06")),
     # external-Compton seed photons (BASELINE configs[2]): upper and lower disk sources sampled from a spectrum
     # file (the only live surface-source path of the reference: nsurf* > 0 requires tbb* < 0, imcgen2d.f:441-442)
     "surface": dict(over=dict(nz=3, nr=4, nst=1200, tstop="1.e+3", **{"t0(1)": "0.d0", "t1(1)": "1.d20"}), zone={},
@@ -231,7 +235,8 @@ def main(name):
     out["events"] = ev
     # the worker's event file as the binary formatted it (format 105 of imcleak2d.f:181), first 600 records: pins the
     # e14.7 formatter of the library's reference-format writers (c2d_events_write / c2d_census_write)
-    (GOLD / f"evb_{name}.txt").write_text("".join(evt1.splitlines(keepends=True)[:600]))
+    if name == "dense":
+        (GOLD / f"evb_{name}.txt").write_text("".join(evt1.splitlines(keepends=True)[:600]))
     out["labels"] = np.array([lab for _, lab in pts])
     # scalars the log prints (FP energy check etc.) stay in the log; keep stdout tail for provenance
     GOLD.mkdir(parents=True, exist_ok=True)

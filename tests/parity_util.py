@@ -47,7 +47,7 @@ def make_oracle(P, rseed=9857, cens_cap=400000, ev_cap=400000):
     for k in ("z", "r", "E_ph", "E_field", "E_gg", "gnt", "hu", "Elcmin", "Elcmax", "mu"):
         setattr(a, k, P[k])
     o["rmin"] = P["rmin"]; o["zmin"] = P["zmin"]
-    o["pair_switch"] = P["pair_switch"]; o["spec_switch"] = P["spec_switch"]; o["cr_sent"] = 0
+    o["pair_switch"] = P["pair_switch"]; o["spec_switch"] = P["spec_switch"]; o["cr_sent"] = P.get("cr_sent", 0)
     for k, v in zip(("split1", "split2", "split3", "spl3_trg"), P["split"]):
         o[k] = v
     o["rand_switch"] = 3
@@ -111,7 +111,7 @@ def make_gpu(P, rseed=9857, sigma_mode=0, census_capacity=400000, event_capacity
     from compton2d_b200.host import Compton2d
     return Compton2d(nz=P["nz"], nr=P["nr"], z=P["z"], r=P["r"], rmin=P["rmin"], zmin=P["zmin"], E_ph=P["E_ph"],
                      E_field=P["E_field"], E_gg=P["E_gg"], gnt=P["gnt"], hu=P["hu"], Elcmin=P["Elcmin"],
-                     Elcmax=P["Elcmax"], mu=P["mu"], pair_switch=P["pair_switch"], spec_switch=P["spec_switch"],
+                     Elcmax=P["Elcmax"], mu=P["mu"], pair_switch=P["pair_switch"], spec_switch=P["spec_switch"], cr_sent=P.get("cr_sent", 0),
                      split=P["split"], rseed=rseed, census_capacity=census_capacity, event_capacity=event_capacity,
                      collision_capacity=collision_capacity, sigma_mode=sigma_mode, device=device, rank=rank, world=world)
 

@@ -66,9 +66,9 @@ def test_cpp_mirror_equals_python_mirror(exe, tmp_path, monkeypatch):
 
 
 def test_cpp_mirror_error_behaviour(exe, tmp_path):
-    """cr_sent != 0 (Compton reflection, not built): the library returns C2D_EINVAL, the mirror throws, the host prints and stops."""
+    """cr_sent = 2 (Compton reflection off the outer cylinder, not built): the library returns C2D_EINVAL, the mirror throws, the host prints and stops."""
     from synth import make_problem
     P = make_problem(nz=2, nr=2, nst=100, ngroups=16)
     _dump(P, tmp_path)
-    r = subprocess.run([str(exe), str(tmp_path), "1"], capture_output=True, text=True, timeout=600)
+    r = subprocess.run([str(exe), str(tmp_path), "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 12 and "cr_sent" in r.stderr

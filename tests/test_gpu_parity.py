@@ -148,3 +148,16 @@ def test_replay_parity_thin_rays_with_collisions(sigma_mode):
     rg = _run(P, cycles=(1, 2), census_tol=1e-4, sigma_mode=sigma_mode)
     c = rg["counters"]
     assert 0.1 < c["cmcount1"] / c["histories"] < 1000 / 256
+
+
+@pytest.mark.parametrize("cr_sent,spec_switch,sigma_mode", [(1, 0, 0), (4, 1, 1)])
+def test_replay_parity_mirror_at_the_lower_surface(cr_sent, spec_switch, sigma_mode):
+    """SURVEY 8f N4, the live part: specular reflection at z = zmin (imcleak2d.f:107-122; the oracle's restatement is pinned to the
+    reference binary run with cr_sent = 1, tests/golden/refbin_mirror.npz).  Tables of that run; recombined flights and scattered
+    children bounce and go on in row 1, so nothing leaves downwards."""
+    g = Golden("mirror")
+    P = problem_from_snapshot(g.snap("c1_B"), g.snap("c1_C"))
+    P["cr_sent"] = cr_sent; P["spec_switch"] = spec_switch
+    rg = _run(P, sigma_mode=sigma_mode)
+    ev = rg["events"]
+    assert len(ev) > 100 and not np.any((ev[:, 4] <= P["zmin"]) & (ev[:, 5] < 0)) and rg["counters"]["cmcount2"] > 0

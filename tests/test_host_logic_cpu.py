@@ -148,10 +148,10 @@ def test_error_paths(emu):
     assert e.value.code == 6
     g.close()
     P2 = dict(P)
-    with pytest.raises(C2dError) as e:                  # Compton reflection is not built
+    with pytest.raises(C2dError) as e:                  # Compton reflection off the outer cylinder is not built
         from compton2d_b200.host import Compton2d
         Compton2d(nz=P["nz"], nr=P["nr"], z=P["z"], r=P["r"], E_ph=P["E_ph"], E_field=P["E_field"], E_gg=P["E_gg"],
-                  gnt=P["gnt"], hu=P["hu"], cr_sent=1)
+                  gnt=P["gnt"], hu=P["hu"], cr_sent=2)
     assert e.value.code == 2
 
 
@@ -274,4 +274,31 @@ def test_event_list_reduction_host_logic(emu):
     with pytest.raises(C2dError) as e:
         g.lc_begin(bad)
     assert e.value.code == 2
+    g.close()
+
+
+@pytest.mark.parametrize("cr_sent,spec_switch", [(1, 0), (4, 1)])
+def test_mirror_at_the_lower_surface(emu, cr_sent, spec_switch):
+    """SURVEY 8f N4, the live part: specular reflection at the lower surface (imcleak2d.f:107-122, cr_sent = 1 with a cold
+    boundary / cr_sent = 4).  Recombined flights and scattered children bounce (wmu -> -wmu, bins re-derived, the flight goes
+    on in row 1); nothing escapes through z = zmin."""
+    from compton2d_b200 import C2dError
+    from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step
+    from synth import make_problem
+    P = make_problem(nz=3, nr=3, nst=1500, ngroups=64, split=(40, 20, 6, 10), n_e=3.0e5)
+    P["cr_sent"] = cr_sent; P["spec_switch"] = spec_switch
+    o, g = make_oracle(P), make_gpu(P)
+    for cyc in (1, 2):
+        ro = oracle_step(o, P, cyc, field=cyc > 1)
+        rg = gpu_step(g, P, cyc, field=cyc > 1)
+        bad = compare(rg, ro, tol=1e-11, census_tol=1e-6)
+        assert not bad, (cyc, bad)
+    assert rg["counters"]["cmcount2"] > 0 and rg["counters"]["lkcount"] > 0
+    ev = rg["events"]
+    assert len(ev) > 10 and not np.any((ev[:, 4] <= P["zmin"]) & (ev[:, 5] < 0))       # no record leaves downwards through z = zmin
+    if cr_sent == 1:                                       # a hot lower boundary would need the reflection matrices
+        with pytest.raises(C2dError) as e:
+            g.imcgen2d(ncycle=3, time=0.0, dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"], eps_th=P["eps_th"],
+                       f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], nsv=P["nsv"], ewsv=P["ewsv"], tbbl=np.full(P["nr"], 0.5))
+        assert e.value.code == 2
     g.close()
