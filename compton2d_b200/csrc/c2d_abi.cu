@@ -149,15 +149,15 @@ static int drain_queue(Ctx *c)
     return fail(C2D_EINVAL, "scattering cascade did not terminate after 1000 generations");
 }
 
-// cr_sent = 1 reflects specularly only where the lower boundary has no temperature (imcleak2d.f:113); a hot boundary
-// reflects through the P_ref / W_abs matrices of ref_matrix.f (l.124-158), which are not built
+// cr_sent = 1 / 3 reflect specularly only where the lower boundary has no temperature (imcleak2d.f:113); a hot boundary
+// reflects through the P_ref / W_abs tables of ref_matrix.f (l.124-158), which the caller must have supplied
 static int check_mirror(Ctx *c, const double *tbbl)
 {
-    if (c->dims.cr_sent != 1 || !tbbl) return 0;
+    if ((c->dims.cr_sent != 1 && c->dims.cr_sent != 3) || !tbbl || c->P.n_ref > 0) return 0;
     for (int k = 0; k < c->dims.nr; k++)
         if (tbbl[k] > 0.0)
-            return fail(C2D_EINVAL, "cr_sent = 1 with tbbl(%d) = %g > 0: Compton reflection off a hot lower boundary (imcleak2d.f:124-158) "
-                        "is not built", k + 1, tbbl[k]);
+            return fail(C2D_EINVAL, "cr_sent = %d with tbbl(%d) = %g > 0: Compton reflection off a hot lower boundary (imcleak2d.f:124-158) "
+                        "needs the tables E_ref, P_ref, W_abs in c2d_dims", c->dims.cr_sent, k + 1, tbbl[k]);
     return 0;
 }
 
@@ -277,7 +277,7 @@ int c2d_destroy(c2d_ctx *h)
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
+    cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
@@ -294,9 +294,11 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c || !d) return fail(C2D_EINVAL, "NULL argument");
     if (c->inited) return fail(C2D_ESTATE, "context already initialised");
-    if (d->cr_sent != 0 && d->cr_sent != 1 && d->cr_sent != 4)
-        return fail(C2D_EINVAL, "cr_sent = %d: Compton reflection off the outer cylinder (imcleak2d.f:216-273, P_ref / W_abs of ref_matrix.f) "
-                    "is not built; cr_sent = 1 (cold lower boundary) and 4 mirror at the lower surface", d->cr_sent);
+    if (d->cr_sent < 0 || d->cr_sent > 4) return fail(C2D_EINVAL, "cr_sent = %d", d->cr_sent);
+    const bool have_ref = d->n_ref > 1 && d->E_ref && d->P_ref && d->W_abs;
+    if ((d->cr_sent == 2 || d->cr_sent == 3) && !have_ref)
+        return fail(C2D_EINVAL, "cr_sent = %d: Compton reflection (imcleak2d.f:124-165,216-273) needs the tables E_ref, P_ref, W_abs of "
+                    "ref_matrix.f in c2d_dims", d->cr_sent);
     if (d->nz < 1 || d->nr < 1 || d->nz > 65535 || d->nr > 65535) return fail(C2D_EINVAL, "bad grid %d x %d", d->nz, d->nr);
     if (d->nmu < 1 || d->nmu > C2D_NMUMAX || d->nph_lc < 0 || d->nph_lc > C2D_NLCMAX || d->nphtotal < 1 || d->nphtotal > 65535)
         return fail(C2D_EINVAL, "bad bin counts nmu=%d nph_lc=%d nphtotal=%d", d->nmu, d->nph_lc, d->nphtotal);
@@ -392,6 +394,15 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     P.nz = d->nz; P.nr = d->nr; P.nzone = nzone; P.n_vol = d->n_vol; P.num_nt = d->num_nt; P.nphfield = d->nphfield;
     P.n_gg = d->n_gg; P.nphtotal = d->nphtotal; P.nph_lc = d->nph_lc; P.nmu = d->nmu;
     P.pair_switch = d->pair_switch; P.spec_switch = d->spec_switch; P.cr_sent = d->cr_sent;
+    P.n_ref = 0; P.E_ref = P.P_ref = P.W_abs = nullptr;
+    if (have_ref) {
+        const size_t nr_ = (size_t)d->n_ref;
+        CU(cudaMalloc(&c->d_ref, (nr_ + 2 * nr_ * nr_) * 8));
+        CU(cudaMemcpy(c->d_ref, d->E_ref, nr_ * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_ref + nr_, d->P_ref, nr_ * nr_ * 8, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(c->d_ref + nr_ + nr_ * nr_, d->W_abs, nr_ * nr_ * 8, cudaMemcpyHostToDevice));
+        P.n_ref = d->n_ref; P.E_ref = c->d_ref; P.P_ref = c->d_ref + nr_; P.W_abs = c->d_ref + nr_ + nr_ * nr_;
+    }
     P.split1 = d->split1; P.split2 = d->split2; P.split3 = d->split3; P.spl3_trg = d->spl3_trg;
     P.sigma_mode = d->sigma_mode;
     P.key0 = d->rseed; P.rmin = d->rmin; P.zmin = d->zmin;

@@ -21,6 +21,7 @@ struct Ctx {
     int64_t census_cap = 0, event_cap = 0, q_cap = 0, n_census = 0, vol_next = 0, histories = 0;
     long long q_peak = 0;
     // device memory
+    double *d_ref = nullptr;               // [E_ref | P_ref | W_abs] Compton-reflection tables (static)
     double *d_static = nullptr, *d_step = nullptr, *d_f64 = nullptr, *d_events = nullptr;
     int64_t *d_prefix = nullptr;
     void *d_surf = nullptr;                // surface-source blob of the current step

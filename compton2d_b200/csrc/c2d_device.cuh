@@ -81,6 +81,8 @@ struct Seg {                 // one zone crossing of the collision-free ray of a
 struct Params {
     int nz, nr, nzone, n_vol, num_nt, nphfield, n_gg, nphtotal, nph_lc, nmu;
     int pair_switch, spec_switch, cr_sent, split1, split2, split3, spl3_trg, ncycle, sigma_mode;
+    int n_ref;                                        // Compton-reflection tables of ref_matrix.f (static inputs), 0 = none
+    const double *E_ref, *P_ref, *W_abs;              // P_ref / W_abs in COMMON order: (n_out, n_in) at (n_in-1) n_ref + (n_out-1)
     uint32_t key0, key1;
     double rmin, zmin, dt, time;
     // static tables
@@ -716,9 +718,65 @@ __device__ __forceinline__ void get_bin(const Params &p, Photon &P)
     P.jgpmu = mu_group(p, P.wmu);
 }
 
-// imcleak2d.f:2-320.  cr_sent = 0, or the specular mirror at the lower surface (l.107-122: cr_sent = 4, or cr_sent = 1 where
-// the boundary has no temperature -- c2d_step_begin refuses the other combinations).  Returns idead.
-__device__ __forceinline__ int imcleak(const Params &p, Photon &P)
+// imcleak2d.f:126-146 == 224-241: energy of the Compton-reflected photon from the Green's-function tables of ref_matrix.f
+// (linear scans as in the reference: a rare event).  Two uniforms.  Returns W_abs(n_out, n_in); P.xnu is replaced.
+__device__ __forceinline__ double reflect_energy(const Params &p, Rng &rng, Photon &P)
+{
+    const int n_ref = p.n_ref;
+    int n_in = 1, n_out = 1;
+    while (p.E_ref[n_in - 1] < P.xnu && n_in < n_ref) n_in++;
+    const double rnum = rng.next(p);
+    const double *col = p.P_ref + (size_t)(n_in - 1) * n_ref;
+    while (col[n_out - 1] < rnum && n_out < n_ref) n_out++;
+    if (n_out > 1) P.xnu = p.E_ref[n_out - 2] + rng.next(p) * (p.E_ref[n_out - 1] - p.E_ref[n_out - 2]);
+    else P.xnu = p.E_ref[n_out - 1];
+    return p.W_abs[(size_t)(n_in - 1) * n_ref + (n_out - 1)];
+}
+
+// The reflection options of imcleak (cr_sent != 0), out of line so that the common cr_sent = 0 path keeps its registers:
+//   lower surface, cr_sent = 1 / 3 / 4 (imcleak2d.f:107-165): specular mirror where the boundary has no temperature (or
+//     cr_sent = 4), Compton reflection through the tables where it is hot; the flight goes on in row 1 -> returns 0
+//   outer cylinder, cr_sent = 2 / 3 and wmu <= 0 (l.216-273): Compton reflection at the outer disk, recorded as escaped -> 1
+//   anything else -> -1 (the caller takes the cr_sent = 0 path)
+static __device__ __noinline__ int imcleak_reflect(const Params &p, Photon &P, Rng &rng)
+{
+    const double xnu_sv = P.xnu;
+    if (!(P.jph > 0)) {
+        if (!(p.cr_sent == 1 || p.cr_sent == 3 || p.cr_sent == 4)) return -1;
+        if (p.tbbl[P.kph - 1] <= 0.0 || p.cr_sent == 4) {         // l.113-122: wmu -> -wmu
+            P.wmu = -P.wmu;
+            if (P.jgpsp > 0 && p.spec_switch == 1) atomic_add_f64(p.fout + (P.jgpmu - 1) * p.nphtotal + (P.jgpsp - 1), P.ew);
+        } else {                                                  // l.124-158
+            const double w = reflect_energy(p, rng, P);
+            const double ewnew = P.ew * w * P.xnu / xnu_sv;
+            atomic_add_f64(p.Ed_ref + (P.kph - 1), ewnew);
+            P.wmu = fabs(P.wmu);
+            P.ew = ewnew;
+        }
+        get_bin(p, P);                                            // label 60, l.160-165
+        P.jph = 1;
+        return 0;
+    }
+    if (P.jph != p.nz + 1 && !(P.wmu > 0. || p.cr_sent == 1 || p.cr_sent == 4)) {
+        const double w = reflect_energy(p, rng, P);
+        P.ew = P.ew * w * P.xnu / xnu_sv;
+        double tb = 1.e20;
+        if (fabs(P.wmu) > 1.e-6) {
+            tb = p.time + p.dt - kRadCp * (P.dcen + P.zpre / P.wmu);
+            P.zpre = 0.;
+            const double f = P.zpre * sqrt(1. - P.wmu * P.wmu) / fabs(P.wmu);          // zpre already zeroed (l.249-250): f = 0
+            P.rpre = sqrt(P.rpre * P.rpre + f * f + 2. * P.rpre * f * cos(P.phi));
+        }
+        P.wmu = rng.next(p);
+        get_bin(p, P);
+        if (p.ncycle > 0) escape_tally(p, P, tb);
+        return 1;
+    }
+    return -1;
+}
+
+// imcleak2d.f:2-320.  Returns idead; 0 = the flight goes on (through the axis, or reflected: P.xnu may have changed).
+__device__ __forceinline__ int imcleak(const Params &p, Photon &P, Rng &rng)
 {
     const double t_bound = p.time + p.dt - kRadCp * P.dcen;     // l.203,302 (lower face: see DESIGN.md)
     if (P.kph == 0) {
@@ -731,18 +789,13 @@ __device__ __forceinline__ int imcleak(const Params &p, Photon &P)
             atomic_add_f64(p.Ed_in + (P.kph - 1), P.ew);
             atomic_add_f64(p.erlkl + (P.kph - 1), P.ew);
         }
-        if (p.cr_sent != 0) {                                     // l.113-122, 160-165: wmu -> -wmu, the flight goes on in row 1
-            P.wmu = -P.wmu;
-            if (P.jgpsp > 0 && p.spec_switch == 1) atomic_add_f64(p.fout + (P.jgpmu - 1) * p.nphtotal + (P.jgpsp - 1), P.ew);
-            get_bin(p, P);
-            P.jph = 1;
-            return 0;
-        }
+        if (p.cr_sent != 0) { const int r = imcleak_reflect(p, P, rng); if (r >= 0) return r; }
         if (p.ncycle > 0) escape_tally(p, P, t_bound);
         return 1;
     }
     if (P.jph != p.nz + 1) {
         atomic_add_f64(p.erlko + (P.jph - 1), P.ew);
+        if (p.cr_sent != 0) { const int r = imcleak_reflect(p, P, rng); if (r >= 0) return r; }
         if (p.ncycle > 0) escape_tally(p, P, t_bound);
         return 1;
     }
@@ -935,7 +988,7 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
             P.jph = jnew; P.kph = knew;
             if (MODE == MODE_PRE) return END_LEAK;                 // the ray leaves the grid here (nothing tallied)
             if (MODE == MODE_TRIAL || MODE == MODE_TRIAL_SLOW) return END_DROPPED;
-            const int idead = imcleak(p, P);
+            const int idead = imcleak(p, P, rng);
             count(p, CNT_LKCOUNT);
             if (idead == 1) return END_LEAK;
             return STEP_CONT;
@@ -972,8 +1025,13 @@ __device__ __noinline__ int fly(const Params &p, Photon &P, Rng &rng, double wtm
             const double pair_enhance = (p.pair_switch == 1) ? 1.0 + 2.0 * p.f_pair[zi] : 1.0;
             sigsc = 1.0 * comtot_one(p, zi, P.xnu, c.sig) * pair_enhance;
         }
+        const double xnu_was = P.xnu;
         const int r = fly_step<MODE>(p, P, rng, wtmin, colmfp, sigsc, c, segs, s, nseg);
         if (r != STEP_CONT) return r;
+        if (P.xnu != xnu_was) {                                   // Compton reflection at the lower surface changed the energy
+            flight_begin(p, P.xnu, c);
+            if ((MODE == MODE_TRIAL_SLOW || MODE == MODE_CHILD) && p.sigma_mode == 1) sig_begin(p, P.xnu, c.sig);
+        }
     }
 }
 

@@ -308,7 +308,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                 if (endA == END_CENSUS) {
                     if (!census_write(p, F, rng)) end = END_FATAL;
                 } else {
-                    const int idead = imcleak(p, F);
+                    const int idead = imcleak(p, F, rng);
                     count(p, CNT_LKCOUNT);
                     literal = (idead != 1);                       // through the axis: the flight goes on
                 }

@@ -46,7 +46,7 @@ class _CudaView:
 
 class Compton2d:
     def __init__(self, *, nz, nr, z, r, rmin=0.0, zmin=0.0, E_ph, E_field, E_gg, gnt, hu, Elcmin=(), Elcmax=(),
-                 mu=(1.0,), pair_switch=0, cr_sent=0, spec_switch=0, split=(1000, 1000, 300, 10), rseed=9857,
+                 mu=(1.0,), pair_switch=0, cr_sent=0, spec_switch=0, E_ref=None, P_ref=None, W_abs=None, split=(1000, 1000, 300, 10), rseed=9857,
                  census_capacity=5_000_000, event_capacity=1_000_000, collision_capacity=65536, sigma_mode=0,
                  device=0, rank=0, world=1):
         self.L = _l.load()
@@ -64,6 +64,10 @@ class Compton2d:
                     collision_capacity=collision_capacity, rseed=rseed, sigma_mode=sigma_mode, rmin=rmin, zmin=zmin)
         for name in ("z", "r", "E_ph", "E_field", "E_gg", "gnt", "hu", "Elcmin", "Elcmax", "mu"):
             setattr(d, name, _p(k[name]) if k[name].size else None)
+        if E_ref is not None:            # Compton-reflection tables of ref_matrix.f, P_ref / W_abs in COMMON (Fortran) order
+            k["E_ref"] = _d(E_ref); k["P_ref"] = _d(P_ref, k["E_ref"].size ** 2, "P_ref"); k["W_abs"] = _d(W_abs, k["E_ref"].size ** 2, "W_abs")
+            d.n_ref = k["E_ref"].size
+            d.E_ref, d.P_ref, d.W_abs = _p(k["E_ref"]), _p(k["P_ref"]), _p(k["W_abs"])
         self.census_capacity, self.event_capacity = int(census_capacity), int(event_capacity)
         self.h = C.c_void_p()
         _l.check(self.L.c2d_create(C.byref(self.h), int(device)))

@@ -25,7 +25,8 @@ class Dims(C.Structure):
                                        "split3", "spl3_trg")] + \
         [("census_capacity", C.c_int64), ("event_capacity", C.c_int64), ("collision_capacity", C.c_int64),
          ("rseed", C.c_uint32), ("sigma_mode", C.c_int), ("rmin", C.c_double), ("zmin", C.c_double)] + \
-        [(n, dp) for n in ("z", "r", "E_ph", "E_field", "E_gg", "gnt", "hu", "Elcmin", "Elcmax", "mu")]
+        [(n, dp) for n in ("z", "r", "E_ph", "E_field", "E_gg", "gnt", "hu", "Elcmin", "Elcmax", "mu")] + \
+        [("n_ref", C.c_int), ("E_ref", dp), ("P_ref", dp), ("W_abs", dp)]
 
 
 class StepIn(C.Structure):

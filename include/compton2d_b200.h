@@ -32,7 +32,7 @@ extern "C" {
 enum {
     C2D_OK = 0,
     C2D_ENODEV = 1,        /* no CUDA device / wrong architecture */
-    C2D_EINVAL = 2,        /* bad argument or unsupported switch (cr_sent = 2 / 3, ...) */
+    C2D_EINVAL = 2,        /* bad argument or unsupported combination (Compton reflection without its tables, ...) */
     C2D_ECUDA = 3,         /* CUDA runtime error (message in c2d_last_error) */
     C2D_ECENSUS = 4,       /* census bank full: the reference's 'too many photons' STOP (imctrk2d.f:581-585) */
     C2D_EEVENTS = 5,       /* event buffer full (records beyond capacity were counted, not stored) */
@@ -47,8 +47,9 @@ typedef struct {
     int nz, nr;                       /* commonblock.f /zones/ */
     int n_vol, num_nt, nphfield, n_gg; /* general.pa:13-18 (400, 200, 400, 100 in the reference build) */
     int nphtotal, nph_lc, nmu;        /* spectrum groups, light-curve bands, angle bins (setup2d.f:148-173) */
-    int pair_switch, cr_sent, spec_switch;   /* reader.f sentinels; cr_sent: 0, or 1 / 4 = specular reflection at the lower surface
-                                                (imcleak2d.f:107-122; 1 needs tbbl <= 0 everywhere); 2, 3 are refused */
+    int pair_switch, cr_sent, spec_switch;   /* reader.f sentinels.  cr_sent (imcleak2d.f:107-165,216-273): 0 none, 1 lower surface
+                                                (mirror where tbbl <= 0, Compton reflection where hot), 2 outer cylinder, 3 both,
+                                                4 mirror at the lower surface; Compton reflection needs the tables below */
     int split1, split2, split3, spl3_trg;    /* reader.f:587-590 */
     int64_t census_capacity;          /* ucens (general.pa:7), photons */
     int64_t event_capacity;           /* escape records kept per step */
@@ -68,6 +69,12 @@ typedef struct {
     const double *hu;                 /* [nphtotal+1] */
     const double *Elcmin, *Elcmax;    /* [nph_lc] */
     const double *mu;                 /* [nmu] */
+    /* Compton-reflection tables (COMMON /reflection/, commonblock.f:76-77,185; computed once by Pref_calc / Wref_calc,
+       ref_matrix.f, setup2d.f:40-41; shipped every step by xec_bcast, xec2d.f:313-318).  Needed for cr_sent = 2, 3 and for
+       cr_sent = 1 with a hot lower boundary; n_ref = 0 / NULL otherwise. */
+    int n_ref;                        /* general.pa:19 (500) */
+    const double *E_ref;              /* [n_ref] keV */
+    const double *P_ref, *W_abs;      /* [n_ref][n_ref] as they lie in COMMON: element (n_out, n_in) at (n_in-1) n_ref + (n_out-1) */
 } c2d_dims;
 
 /* Per-step inputs: what imcgen2d (imcgen2d.f) leaves in COMMON for the workers, i.e. the union of

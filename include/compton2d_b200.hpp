@@ -32,6 +32,7 @@ struct Grid {
     int nz = 0, nr = 0;
     double rmin = 0.0, zmin = 0.0;
     std::vector<double> z, r, E_ph, E_field, E_gg, gnt, hu, Elcmin, Elcmax, mu;
+    std::vector<double> E_ref, P_ref, W_abs;      // Compton-reflection tables of ref_matrix.f (COMMON order), empty = none
 };
 struct Options {
     int pair_switch = 0, cr_sent = 0, spec_switch = 0;
@@ -67,6 +68,7 @@ class Compton2d {
         d.rseed = o.rseed; d.sigma_mode = o.sigma_mode; d.rmin = g.rmin; d.zmin = g.zmin;
         d.z = ptr(grid_.z); d.r = ptr(grid_.r); d.E_ph = ptr(grid_.E_ph); d.E_field = ptr(grid_.E_field); d.E_gg = ptr(grid_.E_gg);
         d.gnt = ptr(grid_.gnt); d.hu = ptr(grid_.hu); d.Elcmin = ptr(grid_.Elcmin); d.Elcmax = ptr(grid_.Elcmax); d.mu = ptr(grid_.mu);
+        if (!grid_.E_ref.empty()) { d.n_ref = (int)grid_.E_ref.size(); d.E_ref = ptr(grid_.E_ref); d.P_ref = ptr(grid_.P_ref); d.W_abs = ptr(grid_.W_abs); }
         check(c2d_create(&h_, o.device));
         const int rc = c2d_init(h_, &d);
         if (rc != 0) { const std::string msg = c2d_last_error(); c2d_destroy(h_); h_ = nullptr; throw Error(rc, msg); }

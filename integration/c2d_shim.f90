@@ -11,6 +11,8 @@ module c2d_abi
      integer(c_int) :: sigma_mode
      real(c_double) :: rmin, zmin
      type(c_ptr) :: z, r, E_ph, E_field, E_gg, gnt, hu, Elcmin, Elcmax, mu
+     integer(c_int) :: n_ref                          ! COMMON /reflection/: c_loc(E_ref), c_loc(P_ref), c_loc(W_abs) as they lie
+     type(c_ptr) :: E_ref, P_ref, W_abs
   end type
   type, bind(C) :: c2d_step_in
      integer(c_int) :: ncycle

@@ -502,12 +502,29 @@ static void escape_tally(orc_state *s)
         s->fout[(s->jgpmu - 1) * s->nphtotal + (s->jgpsp - 1)] += s->ew;
 }
 
-/* imcleak2d.f:2-320.  Of the reflection options (cr_sent != 0) the specular mirror at the lower surface is
- * restated (l.107-122: cr_sent = 4, or cr_sent = 1 / 3 where the boundary has no temperature, tbbl <= 0 -- every shipped
- * input); the Green's-function reflection off a hot lower boundary (l.124-158) and off the outer cylinder (cr_sent = 2 / 3,
- * l.216-273) needs P_ref / W_abs of ref_matrix.f and raises fatal = 3. */
+/* imcleak2d.f:126-146 == 224-241: energy of the Compton-reflected photon from the Green's-function tables of ref_matrix.f
+ * (P_ref = cumulative distribution of the outgoing bin per incoming bin, W_abs = surviving weight fraction; inputs here, the
+ * host computes them once in setup, setup2d.f:40-41).  Two uniforms.  Returns W_abs(n_out, n_in); s->xnu is replaced. */
+static double reflect_energy(orc_state *s)
+{
+    const int n_ref = ORC_NREF;
+    int n_in = 1, n_out = 1;
+    while (s->E_ref[n_in - 1] < s->xnu && n_in < n_ref) n_in++;
+    {
+        const double rnum = orc_fibran(s);
+        while (s->P_ref[(size_t)(n_in - 1) * n_ref + (n_out - 1)] < rnum && n_out < n_ref) n_out++;
+    }
+    if (n_out > 1) s->xnu = s->E_ref[n_out - 2] + orc_fibran(s) * (s->E_ref[n_out - 1] - s->E_ref[n_out - 2]);
+    else s->xnu = s->E_ref[n_out - 1];
+    return s->W_abs[(size_t)(n_in - 1) * n_ref + (n_out - 1)];
+}
+
+/* imcleak2d.f:2-320 with its reflection options (cr_sent): specular mirror at the lower surface (l.107-122:
+ * cr_sent = 4, or cr_sent = 1 / 3 where the boundary has no temperature -- every shipped input), Compton reflection off a hot
+ * lower boundary (l.124-165) and off the outer cylinder for photons heading down (cr_sent = 2 / 3, l.216-273). */
 void orc_imcleak(orc_state *s)
 {
+    const double xnu_sv = s->xnu;
     if (s->kph == 0) {                       /* inner r boundary, l.71-88 */
         if (s->rmin > 1.e-10) {
             s->idead = 1;
@@ -534,7 +551,16 @@ void orc_imcleak(orc_state *s)
                 s->jph = 1;
                 return;
             }
-            s->fatal = 3; s->idead = 1;                                    /* P_ref / W_abs reflection: not restated */
+            {                                                               /* l.124-165 */
+                const double w = reflect_energy(s);
+                const double ewnew = s->ew * w * s->xnu / xnu_sv;
+                s->Ed_ref[s->kph - 1] += ewnew;
+                s->wmu = fabs(s->wmu);
+                s->ew = ewnew;
+            }
+            orc_get_bin(s);
+            s->idead = 0;
+            s->jph = 1;
             return;
         }
         /* no reflection: photon exits.  The FORTRAN does not update t_bound here
@@ -548,7 +574,23 @@ void orc_imcleak(orc_state *s)
     if (s->jph != s->nz + 1) {               /* outer r boundary, l.194-212 */
         s->erlko[s->jph - 1] += s->ew;
         if (!(s->wmu > 0. || s->cr_sent == 0 || s->cr_sent == 1 || s->cr_sent == 4)) {    /* l.197-198: else l.216-273 */
-            s->fatal = 3; s->idead = 1;
+            /* Compton reflection at the outer disk: the photon is taken down to z = 0 along its direction, re-emitted with
+             * the reflected energy and weight in a random upward direction, and recorded as escaped */
+            const double w = reflect_energy(s);
+            s->ew = s->ew * w * s->xnu / xnu_sv;
+            if (fabs(s->wmu) > 1.e-6) {
+                double f;
+                s->t_bound = s->time + s->dt - RAD_CP * (s->dcen + s->zpre / s->wmu);
+                s->zpre = 0.;
+                f = s->zpre * sqrt(1. - s->wmu * s->wmu) / fabs(s->wmu);     /* zpre already zeroed (l.249-250): f = 0 */
+                s->rpre = sqrt(s->rpre * s->rpre + f * f + 2. * s->rpre * f * cos(s->phi));
+            } else {
+                s->t_bound = 1.e20;
+            }
+            s->wmu = orc_fibran(s);
+            orc_get_bin(s);
+            if (s->ncycle > 0) escape_tally(s);
+            s->idead = 1;
             return;
         }
         s->t_bound = s->time + s->dt - RAD_CP * s->dcen;

@@ -50,6 +50,7 @@ typedef struct {
 #define ORC_NLCMAX 16
 
 /* X-macro: name, C type, element-count expression (in terms of dims) */
+#define ORC_NREF 500        /* general.pa:19 n_ref */
 #define ORC_FIELDS(X) \
     X(z, double, nz) X(r, double, nr) \
     X(E_ph, double, n_vol) X(kappa_tot, double, nzone * n_vol) \
@@ -74,6 +75,9 @@ typedef struct {
     X(edout, double, ORC_NMUMAX * ORC_NLCMAX) \
     X(erlki, double, nz) X(erlko, double, nz) X(erlku, double, nr) X(erlkl, double, nr) \
     X(Ed_in, double, nr) X(Ed_ref, double, nr) \
+    /* Compton-reflection tables of ref_matrix.f (inputs: general.pa n_ref = 500); P_ref / W_abs in COMMON order, \
+       element (n_out, n_in) at (n_in - 1) n_ref + (n_out - 1) */ \
+    X(E_ref, double, ORC_NREF) X(P_ref, double, ORC_NREF * ORC_NREF) X(W_abs, double, ORC_NREF * ORC_NREF) \
     /* FP inputs / outputs */ \
     X(tna, double, nzone) X(B_field, double, nzone) X(vol, double, nzone) \
     X(Eloss_sy, double, nzone) X(Eloss_br, double, nzone) X(ec_old, double, nzone) \

@@ -47,6 +47,14 @@ CONFIGS = {
     # imcleak2d.f:107-122; denser plasma and small splits so that scattered photons bounce too
     "mirror": dict(over=dict(nz=3, nr=3, nst=1500, tstop="1.e+3", cr_sent=1, split1=60, split2=40, split3=12, rseed=777),
                    zone=dict(n_e="0.300e06")),
+    # Compton reflection off a hot lower boundary and off the outer cylinder (cr_sent = 3, tbbl = 0.5 keV: imcleak2d.f:124-165,
+    # 216-273) with the Green's-function tables of ref_matrix.f, which are dumped too (extra=)
+    # (t1(1) = 1e20 keeps the time-interval index ti at 1: with the shipped t1(1) = 1 s the workers read tbbl(k, 2) = 0 from
+    # cycle 2 on and fall back to the mirror, imcsurf2d_para.f:55-63)
+    "reflect": dict(over=dict(nz=3, nr=3, nst=1500, tstop="1.e+3", cr_sent=3, split1=60, split2=40, split3=12, rseed=4711,
+                              **{"t0(1)": "0.d0", "t1(1)": "1.d20"}),
+                    zone=dict(n_e="0.300e06"), wi=dict(tbbl="0.5d0"),
+                    extra=[("p_ref", (500, 500)), ("w_abs", (500, 500)), ("e_ref", (500,))]),
     # external-Compton seed photons (BASELINE configs[2]): upper and lower disk sources sampled from a spectrum
     # file (the only live surface-source path of the reference: nsurf* > 0 requires tbb* < 0, imcgen2d.f:441-442)
     "surface": dict(over=dict(nz=3, nr=4, nst=1200, tstop="1.e+3", **{"t0(1)": "0.d0", "t1(1)": "1.d20"}), zone={},
@@ -158,7 +166,7 @@ def main(name):
     pts = snapshot_points(trace)
     print("snapshot points:", pts)
 
-    vl = varlist(nz, nr)
+    vl = varlist(nz, nr) + list(cfg.get("extra", []))
     spec = []
     layout = []
     for vname, keep in vl:

@@ -36,6 +36,13 @@ class _Snap:
     def __init__(self, g, label):
         self.g, self.label = g, label
 
+    def __contains__(self, var):
+        try:
+            self.g.get(self.label, var)
+            return True
+        except KeyError:
+            return False
+
     def __getattr__(self, var):
         return self.g.get(self.label, var)
 

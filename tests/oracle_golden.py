@@ -63,6 +63,10 @@ def load_snapshot(o, snap):
         setattr(a, cname(v), snap[v])
     for v in ZONE_BIN_FIRST:
         setattr(a, cname(v), np.transpose(snap[v], (1, 2, 0)))
+    if "p_ref" in snap:                               # Compton-reflection tables (golden [n_out, n_in] -> COMMON order)
+        a.E_ref = snap.e_ref
+        a.P_ref = np.ascontiguousarray(np.asarray(snap.p_ref).T).ravel()
+        a.W_abs = np.ascontiguousarray(np.asarray(snap.w_abs).T).ravel()
     a.nsv = snap.nsv
     a.npcen = snap.npcen.astype(np.int64)
     a.nelectron[:] = 0
@@ -126,7 +130,7 @@ def compare_tracking(o, snap, tol=1e-11):
         e = rel(getattr(a, v)[: g.size].reshape(g.shape), g)
         if e > tol:
             bad[v] = e
-    for v in ("erlki", "erlko", "erlku", "erlkl", "ed_in", "e_ic"):
+    for v in ("erlki", "erlko", "erlku", "erlkl", "ed_in", "ed_ref", "e_ic"):
         e = rel(getattr(a, cname(v))[: snap[v].size], snap[v])
         # E_IC is a sum over a few dozen scattering events whose energy transfers differ from the ifort binary's at the
         # 1e-9 level (compb2d's cancellations amplify libm ulp differences)

@@ -48,6 +48,8 @@ def make_oracle(P, rseed=9857, cens_cap=400000, ev_cap=400000):
         setattr(a, k, P[k])
     o["rmin"] = P["rmin"]; o["zmin"] = P["zmin"]
     o["pair_switch"] = P["pair_switch"]; o["spec_switch"] = P["spec_switch"]; o["cr_sent"] = P.get("cr_sent", 0)
+    if "E_ref" in P:                                   # Compton-reflection tables, P_ref / W_abs flat in COMMON order
+        a.E_ref = P["E_ref"]; a.P_ref = P["P_ref"]; a.W_abs = P["W_abs"]
     for k, v in zip(("split1", "split2", "split3", "spl3_trg"), P["split"]):
         o[k] = v
     o["rand_switch"] = 3
@@ -112,6 +114,7 @@ def make_gpu(P, rseed=9857, sigma_mode=0, census_capacity=400000, event_capacity
     return Compton2d(nz=P["nz"], nr=P["nr"], z=P["z"], r=P["r"], rmin=P["rmin"], zmin=P["zmin"], E_ph=P["E_ph"],
                      E_field=P["E_field"], E_gg=P["E_gg"], gnt=P["gnt"], hu=P["hu"], Elcmin=P["Elcmin"],
                      Elcmax=P["Elcmax"], mu=P["mu"], pair_switch=P["pair_switch"], spec_switch=P["spec_switch"], cr_sent=P.get("cr_sent", 0),
+                     E_ref=P.get("E_ref"), P_ref=P.get("P_ref"), W_abs=P.get("W_abs"),
                      split=P["split"], rseed=rseed, census_capacity=census_capacity, event_capacity=event_capacity,
                      collision_capacity=collision_capacity, sigma_mode=sigma_mode, device=device, rank=rank, world=world)
 
@@ -180,3 +183,14 @@ def compare(gpu, ref, tol=1e-11, census_tol=1e-9):
         if r.max() > census_tol:
             bad["events"] = float(r.max())
     return bad
+
+
+def reflection_tables(P):
+    """E_ref, P_ref, W_abs of the reference binary's setup (Pref_calc / Wref_calc, ref_matrix.f) from the `reflect` golden, flat in
+    COMMON order, into problem P."""
+    from golden_util import Golden
+    s = Golden("reflect").snap("c1_B")
+    P["E_ref"] = np.array(s.e_ref)
+    P["P_ref"] = np.ascontiguousarray(np.asarray(s.p_ref).T).ravel()
+    P["W_abs"] = np.ascontiguousarray(np.asarray(s.w_abs).T).ravel()
+    return P

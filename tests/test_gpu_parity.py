@@ -161,3 +161,22 @@ def test_replay_parity_mirror_at_the_lower_surface(cr_sent, spec_switch, sigma_m
     rg = _run(P, sigma_mode=sigma_mode)
     ev = rg["events"]
     assert len(ev) > 100 and not np.any((ev[:, 4] <= P["zmin"]) & (ev[:, 5] < 0)) and rg["counters"]["cmcount2"] > 0
+
+
+@pytest.mark.parametrize("cr_sent,sigma_mode", [(3, 0), (2, 1), (1, 1)])
+def test_replay_parity_compton_reflection(cr_sent, sigma_mode):
+    """Compton reflection through the tables of ref_matrix.f (static inputs; here the reference binary's own, from the `reflect`
+    golden, whose run pins the oracle's restatement): hot lower boundary (imcleak2d.f:124-165; the flight goes on in row 1 with a
+    new energy, so the opacity look-ups of the flight are redone) and outer cylinder (l.216-273)."""
+    from parity_util import reflection_tables
+    g = Golden("reflect")
+    P = problem_from_snapshot(g.snap("c1_B"), g.snap("c1_C"))
+    P["cr_sent"] = cr_sent
+    reflection_tables(P)
+    assert P["tbbl"].min() > 0
+    rg = _run(P, sigma_mode=sigma_mode)
+    if cr_sent != 2:
+        assert rg["Ed_ref"].sum() > 0 and (rg["census"][0][:, 5] >= 1.0).sum() > 50
+    if cr_sent != 1:
+        ev = rg["events"]
+        assert ((ev[:, 4] == 0) & (ev[:, 5] > 0) & (ev[:, 1] >= 1.0)).sum() > 10      # reflected at the outer disk

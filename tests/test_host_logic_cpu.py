@@ -302,3 +302,28 @@ def test_mirror_at_the_lower_surface(emu, cr_sent, spec_switch):
                        f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], nsv=P["nsv"], ewsv=P["ewsv"], tbbl=np.full(P["nr"], 0.5))
         assert e.value.code == 2
     g.close()
+
+
+@pytest.mark.parametrize("cr_sent", [3, 2])
+def test_compton_reflection_tables(emu, cr_sent):
+    """Compton reflection through the Green's-function tables of ref_matrix.f (inputs; here the binary's own): off a hot lower
+    boundary (imcleak2d.f:124-165, the flight goes on with a new energy) and off the outer cylinder (l.216-273)."""
+    from compton2d_b200 import C2dError
+    from parity_util import compare, gpu_step, make_gpu, make_oracle, oracle_step, reflection_tables
+    from synth import make_problem
+    P = make_problem(nz=3, nr=3, nst=1500, ngroups=64, split=(40, 20, 6, 10), n_e=3.0e5)
+    P["cr_sent"] = cr_sent; P["tbbl"] = np.full(P["nr"], 0.5)
+    with pytest.raises(C2dError) as e:                  # without the tables
+        make_gpu(P)
+    assert e.value.code == 2
+    reflection_tables(P)
+    o, g = make_oracle(P), make_gpu(P)
+    for cyc in (1, 2):
+        ro = oracle_step(o, P, cyc, field=cyc > 1)
+        rg = gpu_step(g, P, cyc, field=cyc > 1)
+        bad = compare(rg, ro, tol=1e-11, census_tol=1e-6)
+        assert not bad, (cyc, bad)
+    assert rg["counters"]["lkcount"] > 0 and rg["counters"]["cmcount2"] > 0
+    if cr_sent == 3:
+        assert rg["Ed_ref"].sum() > 0 and (rg["census"][0][:, 5] >= 1.0).sum() > 50      # reflected photons (>= 1 keV) in the census
+    g.close()

@@ -17,7 +17,7 @@ import pytest
 
 from oracle_golden import Golden, cname, compare_tracking, load_snapshot, new_oracle
 
-CASES = [(n, c, ph) for n in ("small", "annulus", "dense", "mirror") for c in (1, 2) for ph in ("field", "vol")]
+CASES = [(n, c, ph) for n in ("small", "annulus", "dense", "mirror", "reflect") for c in (1, 2) for ph in ("field", "vol")]
 
 
 def _run_phase(g, cyc, phase):
@@ -58,7 +58,7 @@ def test_phase_matches_reference_binary(name, cyc, phase):
         assert (r.max(axis=1) > 1e-7).mean() < 0.01
 
 
-@pytest.mark.parametrize("name", ["small", "annulus", "dense", "mirror"])
+@pytest.mark.parametrize("name", ["small", "annulus", "dense", "mirror", "reflect"])
 def test_event_file_matches_reference_binary(name):
     """The worker's event file (imcleak2d.f:171-181) over cycles 1-2, in order."""
     g = Golden(name)
