@@ -282,7 +282,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
     c->fp_free();
-    c->lc_free();
+    c->lc_free_all();
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;

@@ -62,8 +62,14 @@ struct Ctx {
     FpState *fp = nullptr;
     void fp_free();
     // event-list reduction (c2d_lc.cu)
-    LcState *lc = nullptr;
-    void lc_free();
+    static constexpr int kLcSlots = 4;     // independent reducers (light curves and SEDs of one run at once)
+    LcState *lc_slot[kLcSlots] = {nullptr, nullptr, nullptr, nullptr};
+    int lc_active = 0;
+    LcState *&lc_cur() { return lc_slot[lc_active]; }
+    double *d_lc_stage = nullptr;          // host-provided records, shared by the slots
+    size_t lc_stage_cap = 0;
+    void lc_free(int slot);
+    void lc_free_all();
     // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3_attempts, 3 FP, 4 sigma table, 5 tally bench,
     // 6 k_split3_flights
     bool timing = false;

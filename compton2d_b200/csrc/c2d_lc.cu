@@ -38,8 +38,6 @@ struct LcState {
     double *d_tab = nullptr;       // [t_lo | t_hi | mu0 | mu1 | E0 | E1 | edge | covered]
     double *d_acc = nullptr;       // [sum_ew | sum_ew2 | count (u64)]
     size_t cells = 0;
-    double *d_stage = nullptr;     // host-provided records
-    size_t stage_cap = 0;
 };
 
 // plcm.c:393-401 == pspt.c:257-264, split in two so that a record outside every mu bin or every band (most records, for
@@ -289,9 +287,8 @@ __global__ void k_lc_gen(long long n, double *ev)
 }
 #endif  // !C2D_EMU
 
-static int lc_launch(Ctx *c, const double *d_ev, const unsigned long long *d_n, long long n_cap, float *ms)
+static int lc_launch(Ctx *c, LcState *s, const double *d_ev, const unsigned long long *d_n, long long n_cap, float *ms)
 {
-    LcState *s = c->lc;
 #ifdef C2D_EMU
     (void)ms;
     const LcParams &q = s->q;
@@ -342,12 +339,23 @@ static int lc_launch(Ctx *c, const double *d_ev, const unsigned long long *d_n, 
 #endif
 }
 
-void Ctx::lc_free()
+void Ctx::lc_free(int slot)
 {
-    if (!lc) return;
-    cudaFree(lc->d_tab); cudaFree(lc->d_acc); cudaFree(lc->d_stage);
-    delete lc;
-    lc = nullptr;
+    LcState *&s = lc_slot[slot];
+    if (!s) return;
+    cudaFree(s->d_tab); cudaFree(s->d_acc);
+    delete s;
+    s = nullptr;
+}
+void Ctx::lc_free_all()
+{
+    for (int k = 0; k < kLcSlots; k++) lc_free(k);
+    cudaFree(d_lc_stage); d_lc_stage = nullptr; lc_stage_cap = 0;
+}
+static bool lc_any(const Ctx *c)
+{
+    for (int k = 0; k < Ctx::kLcSlots; k++) if (c->lc_slot[k]) return true;
+    return false;
 }
 
 }  // namespace c2d
@@ -371,8 +379,8 @@ extern "C" int c2d_lc_begin(c2d_ctx *h, const c2d_lc_config *cfg)
     const size_t cells = (size_t)cfg->n_t * cfg->n_mu * cfg->n_bands;
     if (cells > ((size_t)1 << 28)) return fail(C2D_EINVAL, "%zu accumulator cells", cells);
     CUL(cudaSetDevice(c->device));
-    c->lc_free();
-    LcState *s = c->lc = new LcState();
+    c->lc_free(c->lc_active);
+    LcState *s = c->lc_cur() = new LcState();
     s->cells = cells;
     // the band edges in ascending order and, per interval between neighbours, whether a band holds it (NaN edges: the
     // band can hold nothing and is left out)
@@ -411,36 +419,49 @@ extern "C" int c2d_lc_begin(c2d_ctx *h, const c2d_lc_config *cfg)
     return 0;
 }
 
+extern "C" int c2d_lc_select(c2d_ctx *h, int slot)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c) return fail(C2D_EINVAL, "NULL ctx");
+    if (slot < 0 || slot >= Ctx::kLcSlots) return fail(C2D_EINVAL, "reducer %d (0 .. %d)", slot, Ctx::kLcSlots - 1);
+    c->lc_active = slot;
+    return 0;
+}
+
 extern "C" int c2d_lc_accumulate(c2d_ctx *h)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
-    if (!c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (!lc_any(c)) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
     if (int rc = c2d_sync(h)) return rc;                                        // the scattering queue must have drained
     // the record count lives on the device (counters[C2D_CNT_NEVENTS]); records beyond event_capacity were not stored
-    return lc_launch(c, c->d_events, c->P.counters + CNT_NEVENTS, c->event_cap, nullptr);
+    for (int k = 0; k < Ctx::kLcSlots; k++)
+        if (c->lc_slot[k])
+            if (int rc = lc_launch(c, c->lc_slot[k], c->d_events, c->P.counters + CNT_NEVENTS, c->event_cap, nullptr)) return rc;
+    return 0;
 }
 
 extern "C" int c2d_lc_accumulate_events(c2d_ctx *h, const c2d_event *ev, int64_t n)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
-    if (!c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (!lc_any(c)) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
     if (n < 0 || (n && !ev)) return fail(C2D_EINVAL, "n = %lld", (long long)n);
     if (n == 0) return 0;
     CUL(cudaSetDevice(c->device));
-    LcState *s = c->lc;
     const size_t need = (size_t)n * 7 + 1;                                      // + the count
-    if (need > s->stage_cap) {
-        cudaFree(s->d_stage); s->d_stage = nullptr; s->stage_cap = 0;
-        CUL(cudaMalloc(&s->d_stage, (need + 1) * 8));
-        s->stage_cap = need;
+    if (need > c->lc_stage_cap) {
+        cudaFree(c->d_lc_stage); c->d_lc_stage = nullptr; c->lc_stage_cap = 0;
+        CUL(cudaMalloc(&c->d_lc_stage, (need + 1) * 8));
+        c->lc_stage_cap = need;
     }
     const unsigned long long cnt = (unsigned long long)n;
-    double *d_cnt = s->d_stage + (((size_t)n * 7 + 1) & ~(size_t)1);           // the 8-byte slot after the records
-    CUL(cudaMemcpyAsync(s->d_stage, ev, (size_t)n * 56, cudaMemcpyHostToDevice, c->stream));
+    double *d_cnt = c->d_lc_stage + (((size_t)n * 7 + 1) & ~(size_t)1);        // the 8-byte slot after the records
+    CUL(cudaMemcpyAsync(c->d_lc_stage, ev, (size_t)n * 56, cudaMemcpyHostToDevice, c->stream));
     CUL(cudaMemcpyAsync(d_cnt, &cnt, 8, cudaMemcpyHostToDevice, c->stream));
-    if (int rc = lc_launch(c, s->d_stage, reinterpret_cast<unsigned long long *>(d_cnt), n, nullptr)) return rc;
+    for (int k = 0; k < Ctx::kLcSlots; k++)
+        if (c->lc_slot[k])
+            if (int rc = lc_launch(c, c->lc_slot[k], c->d_lc_stage, reinterpret_cast<unsigned long long *>(d_cnt), n, nullptr)) return rc;
     CUL(cudaStreamSynchronize(c->stream));
     return 0;
 }
@@ -448,9 +469,9 @@ extern "C" int c2d_lc_accumulate_events(c2d_ctx *h, const c2d_event *ev, int64_t
 extern "C" int c2d_lc_read(c2d_ctx *h, double *sum_ew, double *sum_ew2, int64_t *count)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);
-    if (!c || !c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (!c || !c->lc_cur()) return fail(C2D_ESTATE, "c2d_lc_begin has not been called for reducer %d", c ? c->lc_active : 0);
     CUL(cudaSetDevice(c->device));
-    LcState *s = c->lc;
+    LcState *s = c->lc_cur();
     CUL(cudaStreamSynchronize(c->stream));
     if (sum_ew) CUL(cudaMemcpy(sum_ew, s->q.sum_ew, s->cells * 8, cudaMemcpyDeviceToHost));
     if (sum_ew2) CUL(cudaMemcpy(sum_ew2, s->q.sum_ew2, s->cells * 8, cudaMemcpyDeviceToHost));
@@ -461,10 +482,10 @@ extern "C" int c2d_lc_read(c2d_ctx *h, double *sum_ew, double *sum_ew2, int64_t 
 extern "C" int c2d_lc_device(c2d_ctx *h, double **sums, int64_t **count, int64_t *cells)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);
-    if (!c || !c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
-    if (sums) *sums = c->lc->d_acc;
-    if (count) *count = reinterpret_cast<int64_t *>(c->lc->q.count);
-    if (cells) *cells = (int64_t)c->lc->cells;
+    if (!c || !c->lc_cur()) return fail(C2D_ESTATE, "c2d_lc_begin has not been called for reducer %d", c ? c->lc_active : 0);
+    if (sums) *sums = c->lc_cur()->d_acc;
+    if (count) *count = reinterpret_cast<int64_t *>(c->lc_cur()->q.count);
+    if (cells) *cells = (int64_t)c->lc_cur()->cells;
     return 0;
 }
 
@@ -475,7 +496,7 @@ extern "C" int c2d_lc_bench(c2d_ctx *h, int64_t n_events, float *ms, int64_t *by
     return fail(C2D_EINVAL, "c2d_lc_bench needs the device build");
 #else
     Ctx *c = reinterpret_cast<Ctx *>(h);
-    if (!c || !c->lc) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
+    if (!c || !c->lc_cur()) return fail(C2D_ESTATE, "c2d_lc_begin has not been called for reducer %d", c ? c->lc_active : 0);
     if (n_events < 1) return fail(C2D_EINVAL, "n_events = %lld", (long long)n_events);
     CUL(cudaSetDevice(c->device));
     double *d_ev = nullptr;
@@ -486,7 +507,7 @@ extern "C" int c2d_lc_bench(c2d_ctx *h, int64_t n_events, float *ms, int64_t *by
     double *d_cnt = d_ev + (((size_t)n_events * 7 + 1) & ~(size_t)1);
     CUL(cudaMemcpyAsync(d_cnt, &cnt, 8, cudaMemcpyHostToDevice, c->stream));
     float t = 0;
-    int rc = lc_launch(c, d_ev, reinterpret_cast<unsigned long long *>(d_cnt), n_events, &t);
+    int rc = lc_launch(c, c->lc_cur(), d_ev, reinterpret_cast<unsigned long long *>(d_cnt), n_events, &t);
     cudaStreamSynchronize(c->stream);
     cudaFree(d_ev);
     if (rc) return rc;

@@ -387,9 +387,11 @@ class Compton2d:
         return n.value
 
     # ------------------------------------------------------------------ event-list reduction
-    def lc_begin(self, red):
+    def lc_begin(self, red, slot=0):
         """Set the bin tables of the light-curve / SED reduction (`lightcurve.lc_reduction` = postprocessing/plcm.c's
-        rules, `lightcurve.sed_reduction` = pspt.c's) and zero the accumulators."""
+        rules, `lightcurve.sed_reduction` = pspt.c's) and zero the accumulators.  `slot` 0..3: independent reducers fed by
+        the same lc_accumulate (the reference runs plcm and pspt on the same event files)."""
+        _l.check(self.L.c2d_lc_select(self.h, int(slot)))
         a = {k: _d(red[k]) for k in ("t_lo", "t_hi", "mu0", "mu1", "E0", "E1")}
         if a["t_lo"].size != a["t_hi"].size or a["mu0"].size != a["mu1"].size or a["E0"].size != a["E1"].size:
             raise ValueError("bin tables: lower and upper edges differ in length")
@@ -399,7 +401,9 @@ class Compton2d:
         for k, v in a.items():
             setattr(cfg, k, _p(v))
         _l.check(self.L.c2d_lc_begin(self.h, C.byref(cfg)))
-        self._lc_shape = (a["t_lo"].size, a["mu0"].size, a["E0"].size)
+        if not hasattr(self, "_lc_shapes"):
+            self._lc_shapes = {}
+        self._lc_shapes[int(slot)] = (a["t_lo"].size, a["mu0"].size, a["E0"].size)
 
     def lc_accumulate(self):
         """Bin this step's escape records where they lie in HBM (instead of `write(1000+myid, 105)`, imcleak2d.f:181,
@@ -411,10 +415,11 @@ class Compton2d:
         ev = np.ascontiguousarray(events, dtype=_F).reshape(-1, 7)
         _l.check(self.L.c2d_lc_accumulate_events(self.h, ev.ctypes.data, ev.shape[0]))
 
-    def lc_read(self, group=None):
+    def lc_read(self, group=None, slot=0):
         """-> (sum_ew, sum_ew2, count) [time][mu][band], summed over ranks (every rank wrote its own p###_evb.dat in the
         reference and plcm read them all, plcm.c:370-383,452-466); feed to lightcurve.finalize / finalize_sed."""
-        shp = self._lc_shape
+        shp = self._lc_shapes[int(slot)]
+        _l.check(self.L.c2d_lc_select(self.h, int(slot)))
         s1, s2, cnt = np.zeros(shp), np.zeros(shp), np.zeros(shp, np.int64)
         _l.check(self.L.c2d_lc_read(self.h, s1.ctypes.data, s2.ctypes.data, cnt.ctypes.data))
         if self.world == 1:

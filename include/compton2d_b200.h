@@ -243,6 +243,9 @@ typedef struct {
     const double *E0, *E1;            /* [n_bands]  E0 <= E < E1 */
 } c2d_lc_config;
 
+int c2d_lc_select(c2d_ctx *ctx, int slot);
+        /* a context holds up to 4 independent reducers (e.g. plcm's light curves and pspt's SEDs of the same run); c2d_lc_begin,
+           _read, _device and _bench act on the selected one (default 0), the _accumulate calls feed every reducer that was begun */
 int c2d_lc_begin(c2d_ctx *ctx, const c2d_lc_config *cfg);  /* sets the bin tables, zeroes the accumulators */
 int c2d_lc_accumulate(c2d_ctx *ctx);
         /* bins the escape records of the current step (those c2d_events_drain would return); call once per step after

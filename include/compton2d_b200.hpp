@@ -182,6 +182,7 @@ class Compton2d {
         return n;
     }
     // event-list reduction with plcm's / pspt's bin rules (postprocessing/plcm.c:384-450, pspt.c:249-289)
+    void lc_select(int slot) { check(c2d_lc_select(h_, slot)); }           // up to 4 reducers per context, all fed by lc_accumulate
     void lc_begin(const c2d_lc_config &cfg) { check(c2d_lc_begin(h_, &cfg)); lc_cells_ = (size_t)cfg.n_t * cfg.n_mu * cfg.n_bands; }
     void lc_accumulate() { check(c2d_lc_accumulate(h_)); }
     void lc_read(std::vector<double> &sum_ew, std::vector<double> &sum_ew2, std::vector<int64_t> &count)

@@ -103,3 +103,16 @@ def test_bench_hook(ctx):
     ms, nbytes = g.lc_bench(1 << 22)
     assert ms > 0 and nbytes == 56 << 22
     assert g.lc_read()[2].sum() > 0
+
+
+def test_two_reducers_fed_by_the_same_records(ctx):
+    """plcm's light curve (slot 0) and pspt's SED (slot 1) from one pass over the records, as the reference runs both programs on
+    the same event files."""
+    g, _ = ctx
+    gold_lc, cfg_lc, events = load_case("dense")
+    gold_sed, cfg_sed, _ = load_sed_case("dense")
+    g.lc_begin(lc_reduction(cfg_lc), slot=0); g.lc_begin(sed_reduction(cfg_sed), slot=1)
+    g.lc_accumulate_events(events)
+    check_against_plcm(gold_lc, cfg_lc, *g.lc_read(slot=0))
+    s1, s2, cnt = g.lc_read(slot=1)
+    check_against_pspt(gold_sed, cfg_sed, s1, cnt)

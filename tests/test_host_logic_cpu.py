@@ -254,6 +254,16 @@ def test_event_list_reduction_host_logic(emu):
     g.lc_accumulate_events(events)
     s1, s2, cnt = g.lc_read()
     check_against_pspt(gold, cfg, s1, cnt)
+    # two reducers fed by the same records: plcm's light curve in slot 0, pspt's SED in slot 1
+    gold_lc, cfg_lc, ev_small = load_case("small")
+    gold_sed, cfg_sed, _ = load_sed_case("small")
+    g.lc_begin(lc_reduction(cfg_lc), slot=0); g.lc_begin(sed_reduction(cfg_sed), slot=1)
+    g.lc_accumulate_events(ev_small)
+    check_against_plcm(gold_lc, cfg_lc, *g.lc_read(slot=0))
+    s1, s2, cnt = g.lc_read(slot=1)
+    check_against_pspt(gold_sed, cfg_sed, s1, cnt)
+    g.lc_begin(sed_reduction(cfg), slot=1)               # re-beginning one slot leaves the other alone
+    check_against_plcm(gold_lc, cfg_lc, *g.lc_read(slot=0))
     # a tracked step: the blob of make_problem, wide angle bins, arrival times of a few light-crossing times
     red = dict(gam_bulk=10.0, rmax=float(P["r"][-1]), t_offset=0.0, t_lo=np.arange(64) * 0.2 * P["dt"],
                t_hi=(np.arange(64) + 1) * 0.2 * P["dt"], mu0=np.array([-1.0, 0.9]), mu1=np.array([0.9, 1.0]), mu_closed=0,
