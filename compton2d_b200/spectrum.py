@@ -65,3 +65,53 @@ def file_sp(rows, *, g_bulk, R_blr, fr_blr, R_ir, fr_ir, R_disk=None, d_jet=None
             P[k] = Isum
     P[: nfile - 1] /= Isum
     return dict(E_file=E, F_file=F, P_file=P, a1=a1, I_file=I, int_file=float(Isum), nfile=int(nfile))
+
+
+SIGMA_SB = 1.0267e24        # imcgen2d.f:14 (erg cm^-2 s^-1 keV^-4)
+
+
+def surface_budget(*, nst, time, dt, z, r, rmin=0.0, tbbi=None, tbbo=None, tbbu=None, tbbl=None, t0=0.0, int_file=None,
+                   star_switch=0, Rstar=1.0, dist_star=1.0, n_volume=0):
+    """The surface-source half of imcgen2d (imcgen2d.f:120-190 energies entering through each boundary ring, 424-443 photon
+    numbers, 457-476 weights, 491-517 the > 10 nst cap) -- host arithmetic over nz + nr rings, the remaining piece of
+    SURVEY.md 8f N1 next to `Compton2d.imcgen2d_device` (volume sources).
+
+    tbb*: boundary temperatures of the current time interval [keV]; a ring with tbb < 0 (and time + dt/2 >= t0) is fed by a
+    spectrum file whose integral `int_file` (file_sp) may be a scalar or a dict(i=, o=, u=, l=) of per-ring arrays.
+    Returns dict(nsurf{i,o,u,l}, ewsurf{i,o,u,l}, erin{i,o,u,l}, fbias) ready for `Compton2d.imcsurf2d`; `n_volume` (sum of
+    nsv) only enters the cap, whose factor the caller applies to nsv / ewsv too when fbias != 1."""
+    z = np.asarray(z, float); r = np.asarray(r, float)
+    nz, nr = z.size, r.size
+    zlo = np.concatenate(([0.0], z[:-1])); rlo = np.concatenate(([rmin], r[:-1]))
+    A = dict(i=2.0 * PI * rmin * (z - zlo), o=2.0 * PI * r[-1] * (z - zlo), u=PI * (r ** 2 - rlo ** 2), l=PI * (r ** 2 - rlo ** 2))
+    tb = dict(i=tbbi, o=tbbo, u=tbbu, l=tbbl)
+    n_ring = dict(i=nz, o=nz, u=nr, l=nr)
+    out, n_new = {}, int(n_volume)
+    for f in "ioul":
+        t = np.zeros(n_ring[f]) if tb[f] is None else np.asarray(tb[f], float)
+        intf = int_file.get(f, 0.0) if isinstance(int_file, dict) else (0.0 if int_file is None else int_file)
+        intf = np.broadcast_to(np.asarray(intf, float), t.shape)
+        from_file = (t < 0.0) & (time + 0.5 * dt >= t0)
+        erin = np.where(from_file, dt * A[f] * intf, dt * A[f] * SIGMA_SB * t ** 4.0)
+        if f == "u" and star_switch == 1:
+            erin = np.where(from_file, erin, erin * (Rstar / dist_star) ** 2.0)
+        if f in "io":
+            n = np.where(t < 0.0, nst // nz, 0).astype(np.int64)                       # integer division, l.427-428
+        else:
+            n = np.where(t < 0.0, (nst * (r ** 2 - rlo ** 2) / r[-1] ** 2).astype(np.int64), 0)     # truncation, l.435-436
+        out["erin" + f] = erin
+        out["nsurf" + f] = n
+        n_new += int(n.sum())
+    for f in "ioul":
+        n = out["nsurf" + f]
+        out["ewsurf" + f] = np.where(n > 0, out["erin" + f] / np.maximum(n, 1), 0.0)
+    out["fbias"] = 1.0
+    if n_new > 10 * nst:                                                             # l.491-517
+        fb = float(10 * nst) / float(n_new)
+        for f in "ioul":
+            out["nsurf" + f] = (out["nsurf" + f].astype(float) * fb).astype(np.int64)
+            out["ewsurf" + f] = out["ewsurf" + f] / fb
+        out["fbias"] = fb
+    for f in "ioul":
+        out["nsurf" + f] = out["nsurf" + f].astype(np.int32)
+    return out

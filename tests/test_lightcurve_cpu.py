@@ -42,3 +42,21 @@ def test_parse_reference_input_files():
     from compton2d_b200.lightcurve import parse_sed_input
     c = parse_sed_input("p001_evb.dat\n33\n1e16\nsed30.dat\n30\n1.6e4\n6e4\n0.99944\n0.99964\n1\n1e-7\n1e10\n100\n0\nn\n")
     assert c["n_t"] == 30 and c["t_end"] == 6e4 and len(c["E0"]) == 100 and c["E0"][0] == 1e-7 and abs(c["E1"][-1] / 1e10 - 1) < 1e-12
+
+
+def test_surface_budget_matches_reference_binary():
+    """compton2d_b200.spectrum.surface_budget (imcgen2d.f:120-190,424-476) against what the binary's master shipped to its
+    worker in the `surface` golden run (upper and lower disk fed by a spectrum file, nst = 1200)."""
+    from compton2d_b200.spectrum import surface_budget
+    from golden_util import Golden
+    s = Golden("surface").snap("c1_D")
+    b = surface_budget(nst=1200, time=float(s.time), dt=float(s.dt[0]), z=s.z, r=s.r, rmin=float(s.rmin), tbbi=s.tbbi[:, 0],
+                       tbbo=s.tbbo[:, 0], tbbu=s.tbbu[:, 0], tbbl=s.tbbl[:, 0], t0=0.0, int_file=float(s.int_file))
+    for f in "ioul":
+        assert np.array_equal(b["nsurf" + f], np.asarray(s["nsurf" + f])), f
+        assert np.allclose(b["ewsurf" + f], np.asarray(s["ewsurf" + f]), rtol=1e-14, atol=0), f
+    assert b["nsurfu"].sum() == 1200 and b["fbias"] == 1.0
+    # the > 10 nst cap
+    c = surface_budget(nst=100, time=0.0, dt=1.0, z=s.z, r=s.r, tbbu=-np.ones(4), tbbl=-np.ones(4), int_file=1.0, n_volume=2000)
+    n_new = 2000 + 2 * int((100 * np.diff(np.concatenate(([0.0], np.asarray(s.r) ** 2))) / s.r[-1] ** 2).astype(int).sum())
+    assert c["fbias"] == 1000.0 / n_new and c["nsurfu"].sum() <= 50
