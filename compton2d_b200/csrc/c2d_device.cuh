@@ -161,8 +161,8 @@ __device__ __forceinline__ uint64_t mix64(uint64_t a, uint64_t b)
     return x;
 }
 
-__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                              uint32_t k0, uint32_t k1, uint32_t (&o)[4])
+__device__ __forceinline__ void philox4x32_10_inl(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                  uint32_t k0, uint32_t k1, uint32_t (&o)[4])
 {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -172,6 +172,28 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
     }
     o[0] = c0; o[1] = c1; o[2] = c2; o[3] = c3;
 }
+// The history kernels call Philox from ~100 places; inlined, those copies are 11 % of a 91 000-instruction kernel whose
+// warps stall on instruction fetch (no_instructions 23 % of the stall samples).  One out-of-line copy, result in registers.
+#if defined(C2D_EMU) || defined(C2D_PHILOX_INLINE)
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&o)[4])
+{
+    philox4x32_10_inl(c0, c1, c2, c3, k0, k1, o);
+}
+#else
+static __device__ __noinline__ uint4 philox4x32_10_call(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1)
+{
+    uint32_t o[4];
+    philox4x32_10_inl(c0, c1, c2, c3, k0, k1, o);
+    return make_uint4(o[0], o[1], o[2], o[3]);
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t (&o)[4])
+{
+    const uint4 v = philox4x32_10_call(c0, c1, c2, c3, k0, k1);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+}
+#endif
 
 __device__ __forceinline__ double u52(uint32_t lo, uint32_t hi)
 {   // 52-bit uniform in (0,1): ((w >> 12) + 0.5) * 2^-52, exactly representable

@@ -320,7 +320,7 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
 }
 
 #ifndef C2D_HIST_MINB
-#define C2D_HIST_MINB 4
+#define C2D_HIST_MINB 8
 #endif
 template <int SRC>
 __global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const __grid_constant__ Params p, long long first, long long n, long long stride)
@@ -494,7 +494,7 @@ constexpr int kHistMax = 1024;
 
 constexpr int kHistWarp = 256;      // bins of the per-warp nelectron copy of k_split3_attempts
 #ifndef C2D_S3_MINB
-#define C2D_S3_MINB 8
+#define C2D_S3_MINB 16
 #endif
 __global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __grid_constant__ Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
                                                          int max_rounds, unsigned *hard, unsigned long long *hard_count)
