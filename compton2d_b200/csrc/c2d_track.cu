@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Par
 #endif
 
 // one thread per accepted 3rd-split sub-child: tallies of l.657-661, then the scat_flag = 1 flight
-__global__ void __launch_bounds__(128) k_split3_flights(const __grid_constant__ Params p, const FlightTask *fl, long long n)
+__global__ void __launch_bounds__(128, 8) k_split3_flights(const __grid_constant__ Params p, const FlightTask *fl, long long n)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= n) return;
