@@ -337,3 +337,36 @@ def test_compton_reflection_tables(emu, cr_sent):
     if cr_sent == 3:
         assert rg["Ed_ref"].sum() > 0 and (rg["census"][0][:, 5] >= 1.0).sum() > 50      # reflected photons (>= 1 keV) in the census
     g.close()
+
+
+def test_degenerate_inputs(emu, tmp_path):
+    """Empty and ragged inputs: a step without sources, an empty census through the file formats, the event-list reduction of
+    no records, an event buffer that overflows (records beyond event_capacity are counted, not stored: C2D_EEVENTS)."""
+    from compton2d_b200 import C2dError
+    from parity_util import gpu_step, make_gpu
+    from synth import make_problem
+    P = make_problem(nz=3, nr=2, nst=400, ngroups=16, split=(10, 5, 2, 10))
+    P0 = dict(P, nsv=np.zeros_like(P["nsv"]))
+    g = make_gpu(P0)
+    t = gpu_step(g, P0, 1, field=True)                       # empty census re-tracked, no volume sources
+    assert t["counters"]["histories"] == 0 and t["counters"]["ndxout"] == 0 and not t["edep"].any() and len(t["events"]) == 0
+    assert g.write_cens(tmp_path / "empty.dat") == 0 and (tmp_path / "empty.dat").read_text() == ""
+    g.read_cens(tmp_path / "empty.dat", 0)
+    assert g.census_count() == 0
+    assert g.write_events(tmp_path / "ev.dat", append=False) == 0
+    red = dict(gam_bulk=10.0, rmax=1e16, t_offset=0.0, t_lo=np.arange(4.0), t_hi=np.arange(4.0) + 1, mu0=[-1.0], mu1=[1.0], mu_closed=1,
+               E0=[1e-9], E1=[1e9], first_band_only=1)
+    g.lc_begin(red)
+    g.lc_accumulate()
+    g.lc_accumulate_events(np.zeros((0, 7)))
+    assert g.lc_read()[2].sum() == 0
+    g.close()
+    # event buffer overflow
+    g = make_gpu(P, event_capacity=5)
+    with pytest.raises(C2dError) as e:                       # gpu_step drains the events
+        gpu_step(g, P, 1, field=False)
+    assert e.value.code == 5 and g.tallies()["counters"]["nevents"] > 5
+    g.lc_begin(red)
+    g.lc_accumulate()                                        # bins the 5 records that were stored
+    assert g.lc_read()[2].sum() <= 5
+    g.close()
