@@ -915,7 +915,21 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
         else CUF(cudaMemsetAsync(D + off, 0, cnt * 8, c->stream));
         return 0;
     };
-    rc = up(o_f, in->f_nt, (size_t)nzone * N) | up(o_P, in->Pnt, (size_t)nzone * N) | up(o_ne, in->n_e, nzone) |
+    // Pnt: FP_calc rebuilds the running CDF and keeps only its last entry (update2d.f:1485) -- unless a zone is empty
+    // (n_lept < 1e-11, l.472), whose Pnt is handed back untouched.  Upload the full table only then.
+    bool need_pnt = false;
+    for (int z = 0; z < nzone && !need_pnt; z++) {
+        const double fpz = in->f_pair ? in->f_pair[z] : 0.0;
+        need_pnt = !(in->n_e[z] * (1. + fpz) + in->n_e[z] * fpz >= 1.e-11);        // n_lept as k_fp_zones forms it
+    }
+    if (need_pnt) rc = up(o_P, in->Pnt, (size_t)nzone * N);
+    else {
+        CUF(cudaMemcpy2DAsync(D + o_P + (N - 1), (size_t)N * 8, in->Pnt + (N - 1), (size_t)N * 8, 8, (size_t)nzone,
+                              cudaMemcpyHostToDevice, c->stream));
+        rc = 0;
+    }
+    if (rc) return rc;
+    rc = up(o_f, in->f_nt, (size_t)nzone * N) | up(o_ne, in->n_e, nzone) |
          up(o_B, in->B_field, nzone) | up(o_tea, in->tea, nzone) | up(o_tna, in->tna, nzone) | up(o_vol, in->vol, nzone) |
          up(o_fp, in->f_pair, nzone) | up(o_sy, in->Eloss_sy, nzone) | up(o_eco, in->ec_old, nzone) | up(o_tl, in->turb_lev, nzone);
     if (rc) return rc;

@@ -44,6 +44,11 @@ template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = (T *)ca
 inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return 0; }
 inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return 0; }
+inline cudaError_t cudaMemcpy2DAsync(void *d, size_t dp, const void *s, size_t sp, size_t w, size_t h, cudaMemcpyKind, cudaStream_t)
+{
+    for (size_t i = 0; i < h; i++) memcpy((char *)d + i * dp, (const char *)s + i * sp, w);
+    return 0;
+}
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { memset(d, v, n); return 0; }
 inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = nullptr; return 0; }
