@@ -785,6 +785,14 @@ int c2d_tally_read(c2d_ctx *h, c2d_tallies *t)
     return 0;
 }
 
+int c2d_tally_reduce(c2d_ctx *h, c2d_tallies *t)
+{
+    if (int rc = c2d_sync(h)) return rc;
+    return c2d_tally_read(h, t);
+}
+
+int c2d_finalize(c2d_ctx *h) { return c2d_destroy(h); }
+
 int c2d_census_count(c2d_ctx *h, int64_t *n)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);

@@ -91,7 +91,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
            "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
            "c2d_lc_select", "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar",
-           "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7"]
+           "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7", "c2d_tally_reduce", "c2d_finalize"]
 
 _lib = None
 
@@ -125,6 +125,8 @@ def load():
     L.c2d_surf_begin.argtypes = [vp, C.POINTER(SurfIn)]
     L.c2d_imcsurf.argtypes = [vp, C.c_int64, C.c_int64, C.c_int64]
     L.c2d_tally_read.argtypes = [vp, C.POINTER(Tallies)]
+    L.c2d_tally_reduce.argtypes = [vp, C.POINTER(Tallies)]
+    L.c2d_finalize.argtypes = [vp]
     L.c2d_tally_device.argtypes = [vp, C.POINTER(vp), lp, C.POINTER(vp), lp]
     L.c2d_census_count.argtypes = [vp, lp]
     L.c2d_census_export.argtypes = [vp, vp, vp, vp, C.c_int64, lp]

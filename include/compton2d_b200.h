@@ -194,6 +194,10 @@ int c2d_imcsurf(c2d_ctx *ctx, int64_t first, int64_t count, int64_t stride);
         /* == imcsurf2d: sum over rings of z_surf_calc + r_surf_calc (imcsurf2d_para.f:228-534); sharded like c2d_imcvol */
 int c2d_sync(c2d_ctx *ctx);                                /* drains the scattering queue, waits for the device */
 int c2d_tally_read(c2d_ctx *ctx, c2d_tallies *out);        /* D2H copy of this context's (or the reduced) tallies */
+int c2d_tally_reduce(c2d_ctx *ctx, c2d_tallies *out);
+        /* c2d_sync + c2d_tally_read: the name SURVEY.md 8b gives the end-of-step hand-over.  With more than one rank the host
+           all-reduces the two buffers of c2d_tally_device (NCCL / CUDA-aware MPI) between c2d_sync and this call */
+int c2d_finalize(c2d_ctx *ctx);                             /* == c2d_destroy */
 int c2d_tally_device(c2d_ctx *ctx, double **fp64_buf, int64_t *n_fp64, int64_t **i64_buf, int64_t *n_i64);
         /* device pointers of the packed tally buffers, for the per-step all-reduce
            (cens_add_up + E_add_up + xec_add + graphics_collect: update2d.f:1931-2083, xec2d.f:325-394) */
