@@ -319,11 +319,16 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
     }
 }
 
+// 64 registers, 32 warps / SM (profiles/r01_ncu_v31_k_history.md); measured block sizes at that occupancy:
+// 64 x 16: 65.5, 128 x 8: 63.4, 256 x 4: 61.1, 512 x 2: 63.6, 1024 x 1: 70.6 ms / step
+#ifndef C2D_HIST_THREADS
+#define C2D_HIST_THREADS 256
+#endif
 #ifndef C2D_HIST_MINB
-#define C2D_HIST_MINB 8
+#define C2D_HIST_MINB 4
 #endif
 template <int SRC>
-__global__ void __launch_bounds__(128, C2D_HIST_MINB) k_history(const __grid_constant__ Params p, long long first, long long n, long long stride)
+__global__ void __launch_bounds__(C2D_HIST_THREADS, C2D_HIST_MINB) k_history(const __grid_constant__ Params p, long long first, long long n, long long stride)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < n;
@@ -582,21 +587,21 @@ __global__ void __launch_bounds__(128, 8) k_split3_flights(const __grid_constant
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
 {
     if (n <= 0) return;
-    const int threads = 128;
+    const int threads = C2D_HIST_THREADS;
     const long long blocks = (n + threads - 1) / threads;
     k_history<0><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
 }
 void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
 {
     if (n <= 0) return;
-    const int threads = 128;
+    const int threads = C2D_HIST_THREADS;
     const long long blocks = (n + threads - 1) / threads;
     k_history<2><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
 }
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st)
 {
     if (n <= 0) return;
-    const int threads = 128;
+    const int threads = C2D_HIST_THREADS;
     const long long blocks = (n + threads - 1) / threads;
     k_history<1><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
 }
