@@ -33,7 +33,7 @@ struct Ctx {
     FlightTask *d_flights = nullptr;       // accepted 3rd-split sub-children of one chunk of split3 tasks
     int64_t flight_cap = 0;
     unsigned *d_hard = nullptr;            // sub-children the warp phase of the 3rd split left unresolved
-    int split3_rounds = 32;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS)
+    int split3_rounds = 64;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS; measured 8..128)
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;
     // offsets (in doubles) into d_step / d_f64, (in int64) into d_i64
