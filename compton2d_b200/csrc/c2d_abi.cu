@@ -173,6 +173,17 @@ static int check_fatal(Ctx *c)
     return 0;
 }
 
+// records beyond event_capacity are counted, not stored -- whoever consumes the stored list must fail loudly
+int check_events(Ctx *c)
+{
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(&v, c->P.counters + CNT_NEVENTS, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (v > (unsigned long long)c->event_cap)
+        return fail(C2D_EEVENTS, "%llu escape records produced, event_capacity %lld: the list is incomplete", v, (long long)c->event_cap);
+    return 0;
+}
+
 // ---- sigma_mode 1: see c2d_sigma.cu
 int Ctx::sigma_setup()
 {
@@ -240,6 +251,104 @@ int Ctx::sigma_build()
 
 }  // namespace c2d
 
+// ---- pieces of the step prologue shared by c2d_step_begin_gen (host arrays) and c2d_step (resident plasma state)
+namespace c2d {
+
+int latch_census(Ctx *c)
+{   // the photon count in flight: take over what the previous step wrote
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, c->P.counters + CNT_NDXOUT, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->n_census = (int64_t)std::min<unsigned long long>(n, (unsigned long long)c->census_cap);
+    return 0;
+}
+
+// volume_em for every zone from the f_nt / n_e / tea already in the step blob and the B_field at d_B (device), then the
+// per-zone energy budget in the reference's zone order (imcgen2d.f:280-283,291,330) and the volume photon budget (l.405-459)
+int gen_core(Ctx *c, double dt, int64_t nst, const double *d_B, const double *h_ne, const double *h_B, const double *h_vol,
+             const double *h_zsurf, GenBudget &g)
+{
+    const c2d_dims &d = c->dims;
+    const int nzone = c->nzone, nv = d.n_vol;
+    // volume_em regenerates E_ph on every call (volume2d.f:53,96,112-113); the grid given to c2d_init must be that one
+    {
+        const double dE = std::exp(std::log(1.e20) / (double)nv);
+        double E = 1.e-10 / dE;
+        for (int i = 0; i < nv; i++) {
+            E = E * dE;
+            if (std::fabs(c->h_Eph[i] - E) > 1.e-13 * E)
+                return fail(C2D_EINVAL, "E_ph(%d) = %.17g differs from the grid volume_em generates (%.17g, volume2d.f:53,96)", i + 1, c->h_Eph[i], E);
+        }
+    }
+    double *T = c->d_step;
+    // scratch: j_sy | sum_th | sum_g1
+    const size_t n_scr = (size_t)nzone * (nv + 3);
+    if (n_scr > c->gen_cap) {
+        cudaFree(c->d_gen); c->d_gen = nullptr; c->gen_cap = 0;
+        CU(cudaMalloc(&c->d_gen, n_scr * 8));
+        c->gen_cap = n_scr;
+    }
+    double *G = c->d_gen;
+    GenParams q;
+    q.nzone = nzone; q.nz = d.nz; q.nr = d.nr; q.N = d.num_nt; q.nv = nv; q.rmin = d.rmin;
+    q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.E_ph = c->P.E_ph;
+    q.f_nt = T + c->o_fnt; q.n_e = T + c->o_ne; q.tea = T + c->o_tea; q.B_field = d_B;
+    q.j_sy = G + nzone; q.sum_th = G + nzone + (size_t)nzone * nv; q.sum_g1 = q.sum_th + nzone;
+    q.kappa_tot = T + c->o_kappa; q.eps_tot = T + c->o_epstot; q.eps_th = T + c->o_epsth;
+    c->timer_begin(4);
+    launch_volume_em(q, c->stream);
+    c->timer_end();
+    CU(cudaGetLastError());
+    std::vector<double> hs((size_t)2 * nzone);
+    CU(cudaMemcpyAsync(hs.data(), q.sum_th, (size_t)2 * nzone * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    g.e_sy.assign(nzone, 0.0); g.e_th.assign(nzone, 0.0); g.ew.assign(nzone, 0.0); g.nsv.assign(nzone, 0);
+    g.Emiss_tot = 0.0;
+    for (int zi = 0; zi < nzone; zi++) {
+        g.e_sy[zi] = 1.058e-15 * h_ne[zi] * dt * std::pow(h_B[zi], 2.0) * hs[nzone + zi] * h_vol[zi];
+        g.e_th[zi] = dt * h_zsurf[zi] * hs[zi];
+        g.Emiss_tot = g.Emiss_tot + g.e_sy[zi];
+    }
+    for (int zi = 0; zi < nzone; zi++) {
+        g.nsv[zi] = (g.Emiss_tot > 0.0) ? (int32_t)(0.5 * (double)nst * g.e_sy[zi] / g.Emiss_tot) : 0;
+        g.ew[zi] = (g.nsv[zi] > 0) ? g.e_sy[zi] / (double)g.nsv[zi] : 0.0;
+    }
+    return 0;
+}
+
+int budget_upload(Ctx *c, const GenBudget &g)
+{
+    const int nzone = c->nzone;
+    double *T = c->d_step;
+    c->h_prefix.assign(nzone + 1, 0);
+    for (int zi = 0; zi < nzone; zi++) c->h_prefix[zi + 1] = c->h_prefix[zi] + g.nsv[zi];
+    int rc = 0;
+    rc |= upload(c, T + c->o_ewsv, g.ew.data(), nzone);
+    rc |= upload(c, T + c->o_elth, g.e_th.data(), nzone);
+    rc |= upload(c, T + c->o_eltot, g.e_sy.data(), nzone);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_prefix, c->h_prefix.data(), (size_t)(nzone + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    return 0;
+}
+
+// zero the per-step tallies (imcgen2d.f:87-104,534-551,559-601), swap the census banks, open the step
+int begin_common(Ctx *c, int ncycle, double time, double dt)
+{
+    CU(cudaMemsetAsync(c->d_f64, 0, c->n_f64 * 8, c->stream));
+    CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
+    // census: last step's output bank becomes this step's input (no 360 MB copy as in imcfield2d.f:96-97)
+    c->cur_out ^= 1;
+    c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
+    c->P.ncycle = ncycle; c->P.key1 = (uint32_t)ncycle; c->P.dt = dt; c->P.time = time;
+    c->field_done = false; c->vol_next = 0; c->surf_open = false; c->surf_total = 0;
+    c->sigma_ready = false; c->step_reduced = false; c->step_tracked = false;
+    CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its host arrays
+    c->step_open = true;
+    return 0;
+}
+
+}  // namespace c2d
+
 using namespace c2d;
 
 extern "C" {
@@ -280,6 +389,8 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
+    cudaFree(c->d_fout_total); cudaFree(c->d_cnt_global); cudaFree(c->d_plasma); cudaFree(c->d_fpx);
+    comm_free(c);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
     c->fp_free();
     c->lc_free_all();
@@ -380,6 +491,10 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     c->n_i64 = c->i_cnt + CNT_N;
     CU(cudaMalloc(&c->d_i64, c->n_i64 * 8));
     CU(cudaMemset(c->d_i64, 0, c->n_i64 * 8));
+    CU(cudaMalloc(&c->d_fout_total, (size_t)C2D_NMUMAX * d->nphtotal * 8));
+    CU(cudaMemset(c->d_fout_total, 0, (size_t)C2D_NMUMAX * d->nphtotal * 8));
+    CU(cudaMalloc(&c->d_cnt_global, CNT_N * 8));
+    CU(cudaMemset(c->d_cnt_global, 0, CNT_N * 8));
 
     // ---- banks, events, collision queues
     for (int b = 0; b < 2; b++) { int rc = alloc_bank(c->bank[b], c->census_cap); if (rc) return rc; }
@@ -444,13 +559,7 @@ int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
     const int nzone = c->nzone;
     if (!in->kappa_tot || !in->f_nt || !in->Pnt || !in->n_e) return fail(C2D_EINVAL, "missing per-step table");
     if (!(in->dt >= 0.0)) return fail(C2D_EINVAL, "dt = %g", in->dt);
-    // the photon count in flight: take over what the previous step wrote
-    {
-        unsigned long long n = 0;
-        CU(cudaMemcpyAsync(&n, c->P.counters + CNT_NDXOUT, 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        c->n_census = (int64_t)std::min<unsigned long long>(n, (unsigned long long)c->census_cap);
-    }
+    if (int rc_l = latch_census(c)) return rc_l;
     double *T = c->d_step;
     int rc = 0;
     rc |= upload(c, T + c->o_kappa, in->kappa_tot, (size_t)nzone * d.n_vol);
@@ -476,18 +585,7 @@ int c2d_step_begin(c2d_ctx *h, const c2d_step_in *in)
         c->h_prefix[zi + 1] = c->h_prefix[zi] + nsv;
     }
     CU(cudaMemcpyAsync(c->d_prefix, c->h_prefix.data(), (size_t)(nzone + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    // zero the per-step tallies (imcgen2d.f:87-104,534-551,559-601)
-    CU(cudaMemsetAsync(c->d_f64, 0, c->n_f64 * 8, c->stream));
-    CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
-    // census: last step's output bank becomes this step's input (no 360 MB copy as in imcfield2d.f:96-97)
-    c->cur_out ^= 1;
-    c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
-    c->P.ncycle = in->ncycle; c->P.key1 = (uint32_t)in->ncycle; c->P.dt = in->dt; c->P.time = in->time;
-    c->field_done = false; c->vol_next = 0; c->surf_open = false; c->surf_total = 0;
-    c->sigma_ready = false;
-    CU(cudaStreamSynchronize(c->stream));      // the caller may reuse its host arrays
-    c->step_open = true;
-    return 0;
+    return begin_common(c, in->ncycle, in->time, in->dt);
 }
 
 // == imcgen2d for the volume sources, on the device: volume_em for every zone from the live electron
@@ -500,26 +598,11 @@ int c2d_step_begin_gen(c2d_ctx *h, const c2d_gen_in *in, c2d_gen_out *out)
     if (!c->inited) return fail(C2D_ESTATE, "c2d_init has not been called");
     CU(cudaSetDevice(c->device));
     const c2d_dims &d = c->dims;
-    const int nzone = c->nzone, nv = d.n_vol;
+    const int nzone = c->nzone;
     if (!in->f_nt || !in->Pnt || !in->n_e || !in->tea || !in->B_field || !in->vol || !in->zsurf)
         return fail(C2D_EINVAL, "c2d_step_begin_gen: missing per-zone input");
     if (!(in->dt >= 0.0) || in->nst < 0) return fail(C2D_EINVAL, "dt = %g, nst = %lld", in->dt, (long long)in->nst);
-    // volume_em regenerates E_ph on every call (volume2d.f:53,96,112-113); the grid given to c2d_init must be that one
-    {
-        const double dE = std::exp(std::log(1.e20) / (double)nv);
-        double E = 1.e-10 / dE;
-        for (int i = 0; i < nv; i++) {
-            E = E * dE;
-            if (std::fabs(c->h_Eph[i] - E) > 1.e-13 * E)
-                return fail(C2D_EINVAL, "E_ph(%d) = %.17g differs from the grid volume_em generates (%.17g, volume2d.f:53,96)", i + 1, c->h_Eph[i], E);
-        }
-    }
-    {
-        unsigned long long n = 0;
-        CU(cudaMemcpyAsync(&n, c->P.counters + CNT_NDXOUT, 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        c->n_census = (int64_t)std::min<unsigned long long>(n, (unsigned long long)c->census_cap);
-    }
+    if (int rc = latch_census(c)) return rc;
     double *T = c->d_step;
     int rc = 0;
     rc |= upload(c, T + c->o_fnt, in->f_nt, (size_t)nzone * d.num_nt);
@@ -532,64 +615,25 @@ int c2d_step_begin_gen(c2d_ctx *h, const c2d_gen_in *in, c2d_gen_out *out)
     rc |= upload(c, T + c->o_zsurf, in->zsurf, nzone, 1.0);
     rc |= upload(c, T + c->o_tea, in->tea, nzone);
     if (rc) return rc;
-    // scratch: B_field | j_sy | sum_th | sum_g1
-    const size_t n_scr = (size_t)nzone * (nv + 3);
+    // B_field rides in the first nzone doubles of the generator's scratch
+    const size_t n_scr = (size_t)nzone * (d.n_vol + 3);
     if (n_scr > c->gen_cap) {
-        cudaFree(c->d_gen);
+        cudaFree(c->d_gen); c->d_gen = nullptr; c->gen_cap = 0;
         CU(cudaMalloc(&c->d_gen, n_scr * 8));
         c->gen_cap = n_scr;
     }
-    double *G = c->d_gen;
-    CU(cudaMemcpyAsync(G, in->B_field, (size_t)nzone * 8, cudaMemcpyHostToDevice, c->stream));
-    GenParams q;
-    q.nzone = nzone; q.nz = d.nz; q.nr = d.nr; q.N = d.num_nt; q.nv = nv; q.rmin = d.rmin;
-    q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.E_ph = c->P.E_ph;
-    q.f_nt = T + c->o_fnt; q.n_e = T + c->o_ne; q.tea = T + c->o_tea; q.B_field = G;
-    q.j_sy = G + nzone; q.sum_th = G + nzone + (size_t)nzone * nv; q.sum_g1 = q.sum_th + nzone;
-    q.kappa_tot = T + c->o_kappa; q.eps_tot = T + c->o_epstot; q.eps_th = T + c->o_epsth;
-    c->timer_begin(4);
-    launch_volume_em(q, c->stream);
-    c->timer_end();
-    CU(cudaGetLastError());
-    std::vector<double> hs((size_t)2 * nzone);
-    CU(cudaMemcpyAsync(hs.data(), q.sum_th, (size_t)2 * nzone * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    // energy and photon budget in the reference's zone order (imcgen2d.f:280-283,291,330,405-459)
-    std::vector<double> e_sy(nzone), e_th(nzone), ew(nzone);
-    std::vector<int32_t> nsv(nzone);
-    double Emiss_tot = 0.0;
-    for (int zi = 0; zi < nzone; zi++) {
-        e_sy[zi] = 1.058e-15 * in->n_e[zi] * in->dt * std::pow(in->B_field[zi], 2.0) * hs[nzone + zi] * in->vol[zi];
-        e_th[zi] = in->dt * in->zsurf[zi] * hs[zi];
-        Emiss_tot = Emiss_tot + e_sy[zi];
-    }
-    c->h_prefix.assign(nzone + 1, 0);
-    for (int zi = 0; zi < nzone; zi++) {
-        nsv[zi] = (Emiss_tot > 0.0) ? (int32_t)(0.5 * (double)in->nst * e_sy[zi] / Emiss_tot) : 0;
-        ew[zi] = (nsv[zi] > 0) ? e_sy[zi] / (double)nsv[zi] : 0.0;
-        c->h_prefix[zi + 1] = c->h_prefix[zi] + nsv[zi];
-    }
-    rc |= upload(c, T + c->o_ewsv, ew.data(), nzone);
-    rc |= upload(c, T + c->o_elth, e_th.data(), nzone);
-    rc |= upload(c, T + c->o_eltot, e_sy.data(), nzone);
-    if (rc) return rc;
-    CU(cudaMemcpyAsync(c->d_prefix, c->h_prefix.data(), (size_t)(nzone + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemsetAsync(c->d_f64, 0, c->n_f64 * 8, c->stream));
-    CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
-    c->cur_out ^= 1;
-    c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
-    c->P.ncycle = in->ncycle; c->P.key1 = (uint32_t)in->ncycle; c->P.dt = in->dt; c->P.time = in->time;
-    c->field_done = false; c->vol_next = 0; c->surf_open = false; c->surf_total = 0;
-    c->sigma_ready = false;
-    CU(cudaStreamSynchronize(c->stream));
-    c->step_open = true;
+    CU(cudaMemcpyAsync(c->d_gen, in->B_field, (size_t)nzone * 8, cudaMemcpyHostToDevice, c->stream));
+    GenBudget g;
+    if (int rc2 = gen_core(c, in->dt, in->nst, c->d_gen, in->n_e, in->B_field, in->vol, in->zsurf, g)) return rc2;
+    if (int rc2 = budget_upload(c, g)) return rc2;
+    if (int rc2 = begin_common(c, in->ncycle, in->time, in->dt)) return rc2;
     if (out) {
-        if (out->nsv) memcpy(out->nsv, nsv.data(), (size_t)nzone * 4);
-        if (out->ewsv) memcpy(out->ewsv, ew.data(), (size_t)nzone * 8);
-        if (out->Eloss_sy) memcpy(out->Eloss_sy, e_sy.data(), (size_t)nzone * 8);
-        if (out->Eloss_th) memcpy(out->Eloss_th, e_th.data(), (size_t)nzone * 8);
-        if (out->Eloss_tot) memcpy(out->Eloss_tot, e_sy.data(), (size_t)nzone * 8);
-        out->Emiss_tot = Emiss_tot;
+        if (out->nsv) memcpy(out->nsv, g.nsv.data(), (size_t)nzone * 4);
+        if (out->ewsv) memcpy(out->ewsv, g.ew.data(), (size_t)nzone * 8);
+        if (out->Eloss_sy) memcpy(out->Eloss_sy, g.e_sy.data(), (size_t)nzone * 8);
+        if (out->Eloss_th) memcpy(out->Eloss_th, g.e_th.data(), (size_t)nzone * 8);
+        if (out->Eloss_tot) memcpy(out->Eloss_tot, g.e_sy.data(), (size_t)nzone * 8);
+        out->Emiss_tot = g.Emiss_tot;
         out->n_volume = c->h_prefix.back();
     }
     return 0;
@@ -615,7 +659,7 @@ int c2d_imcfield(c2d_ctx *h)
     if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
     if (c->field_done) return fail(C2D_ESTATE, "c2d_imcfield called twice in one step");
     CU(cudaSetDevice(c->device));
-    c->field_done = true;
+    c->field_done = true; c->step_tracked = true;
     if (int rc = c->sigma_ensure()) return rc;
     c->timer_begin(0);
     launch_history_census(c->P, 0, c->n_census, 1, c->stream);
@@ -635,6 +679,7 @@ int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     if (stride < 1 || first < 0) return fail(C2D_EINVAL, "bad shard first=%lld stride=%lld", (long long)first, (long long)stride);
     int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
     if (count < 0 || count > avail) count = avail;
+    c->step_tracked = true;
     if (int rc = c->sigma_ensure()) return rc;
     const int64_t chunk = (int64_t)1 << 30;
     for (int64_t done = 0; done < count; done += chunk) {
@@ -725,6 +770,7 @@ int c2d_imcsurf(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     const int64_t total = c->surf_total;
     int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
     if (count < 0 || count > avail) count = avail;
+    c->step_tracked = true;
     if (int rc = c->sigma_ensure()) return rc;
     const int64_t chunk = (int64_t)1 << 30;
     for (int64_t done = 0; done < count; done += chunk) {
@@ -766,10 +812,14 @@ int c2d_tally_read(c2d_ctx *h, c2d_tallies *t)
     if (!c || !c->inited || !t) return fail(C2D_ESTATE, "context not initialised");
     CU(cudaSetDevice(c->device));
     c->h_f64.resize(c->n_f64); c->h_i64.resize(c->n_i64);
+    unsigned long long cg[CNT_N];
     CU(cudaMemcpyAsync(c->h_f64.data(), c->d_f64, c->n_f64 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(c->h_i64.data(), c->d_i64, c->n_i64 * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpyAsync(cg, c->d_cnt_global, sizeof cg, cudaMemcpyDeviceToHost, c->stream));
     const c2d_dims &d = c->dims;
+    if (t->fout_total)
+        CU(cudaMemcpyAsync(t->fout_total, c->d_fout_total, (size_t)C2D_NMUMAX * d.nphtotal * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     const int nzone = c->nzone;
     auto cp = [&](double *dst, size_t off, size_t n) { if (dst) memcpy(dst, c->h_f64.data() + off, n * 8); };
     cp(t->edep, c->t_edep, nzone); cp(t->prdep, c->t_prdep, nzone); cp(t->ecens, c->t_ecens, nzone);
@@ -782,13 +832,55 @@ int c2d_tally_read(c2d_ctx *h, c2d_tallies *t)
     if (t->nelectron) memcpy(t->nelectron, c->h_i64.data() + c->i_nel, (size_t)(d.num_nt + 2) * 8);
     for (int k = 0; k < 16; k++) t->counters[k] = (k < CNT_N) ? (int64_t)c->h_i64[c->i_cnt + k] : 0;
     t->counters[C2D_CNT_QPEAK] = c->q_peak;
+    // before c2d_tally_reduce ran in this step the global counters are this rank's
+    for (int k = 0; k < 16; k++) t->counters_global[k] = c->step_reduced && k < CNT_N ? (int64_t)cg[k] : t->counters[k];
     return 0;
 }
 
+#ifndef C2D_EMU
+__global__ void k_add_into(double *dst, const double *src, size_t n)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = dst[i] + src[i];
+}
+#endif
+static int add_into(Ctx *c, double *dst, const double *src, size_t n)
+{
+#ifndef C2D_EMU
+    k_add_into<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(dst, src, n);
+    CU(cudaGetLastError());
+#else
+    (void)c;
+    for (size_t i = 0; i < n; i++) dst[i] = dst[i] + src[i];
+#endif
+    return 0;
+}
+
+// The end-of-step reduction: cens_add_up + E_add_up + xec_add + graphics_collect (update2d.f:1931-2083, xec2d.f:325-394).
+// In place on the device: every rank ends up with the sums (the reference reduces to the master and re-broadcasts what the
+// workers need with FP_bcast).  counters[NDXOUT] and [NEVENTS] index this rank's census bank / event list, so the counter
+// block is reduced out of place (c2d_tallies.counters_global).  The run-long escaping spectrum (the master's fout,
+// xec2d.f:389-394: sum of the workers' never-zeroed copies) is accumulated here from the reduced per-step one.
 int c2d_tally_reduce(c2d_ctx *h, c2d_tallies *t)
 {
+    Ctx *c = reinterpret_cast<Ctx *>(h);
     if (int rc = c2d_sync(h)) return rc;
-    return c2d_tally_read(h, t);
+    if (!c->step_reduced) {
+        if (comm_world(c) > 1) {
+            c->timer_begin(8);
+            int rc = comm_allreduce(c, c->d_f64, c->d_f64, c->n_f64, 0);
+            if (!rc) rc = comm_allreduce(c, c->d_i64, c->d_i64, c->i_cnt, 1);
+            if (!rc) rc = comm_allreduce(c, c->d_i64 + c->i_cnt, c->d_cnt_global, CNT_N, 1);
+            c->timer_end();
+            if (rc) return rc;
+        } else {
+            CU(cudaMemcpyAsync(c->d_cnt_global, c->d_i64 + c->i_cnt, CNT_N * 8, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (int rc = add_into(c, c->d_fout_total, c->d_f64 + c->t_fout, (size_t)C2D_NMUMAX * c->dims.nphtotal)) return rc;
+        c->step_reduced = true;
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return t ? c2d_tally_read(h, t) : 0;
 }
 
 int c2d_finalize(c2d_ctx *h) { return c2d_destroy(h); }
@@ -844,9 +936,21 @@ int c2d_census_import(c2d_ctx *h, const double *dbuf, const int32_t *ibuf, const
     if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
     if (n < 0 || n > c->census_cap) return fail(C2D_ECENSUS, "too many photons needed to read: %lld > %lld (imcfield2d.f:84-86)", (long long)n, (long long)c->census_cap);
     if (n && (!dbuf || !ibuf)) return fail(C2D_EINVAL, "NULL census buffers");
+    // a bad restart file must not become out-of-bounds device indices (zone in census_write, (jgpmu-1) nphtotal in escape_tally)
+    for (int64_t i = 0; i < n; i++) {
+        const int32_t *r = ibuf + 6 * i;
+        const bool ok = r[0] >= 0 && r[0] <= c->dims.nphtotal && r[1] >= 0 && r[1] <= c->dims.nph_lc && r[2] >= 0 && r[2] <= c->dims.nmu &&
+                        r[3] >= 1 && r[3] <= c->dims.nz && r[4] >= 1 && r[4] <= c->dims.nr && (r[2] >= 1 || (r[0] == 0 && r[1] == 0));
+        if (!ok)
+            return fail(C2D_EINVAL, "census record %lld out of range: jgpsp %d jgplc %d jgpmu %d jph %d kph %d (grid %d x %d, %d groups, %d bands, %d mu bins)",
+                        (long long)i + 1, r[0], r[1], r[2], r[3], r[4], c->dims.nz, c->dims.nr, c->dims.nphtotal, c->dims.nph_lc, c->dims.nmu);
+    }
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    Bank &b = c->bank[c->cur_out];
+    // between steps the photons go where the last step left its census; right after c2d_step_begin (banks swapped, count
+    // latched, nothing tracked yet) they are this step's census input
+    const bool into_input = c->step_open && !c->step_tracked;
+    Bank &b = into_input ? c->bank[c->cur_out ^ 1] : c->bank[c->cur_out];
     if (n) {
         std::vector<double> col(n);
         double *cols[6] = {b.rpre, b.zpre, b.wmu, b.phi, b.ew, b.xnu};
@@ -870,6 +974,7 @@ int c2d_census_import(c2d_ctx *h, const double *dbuf, const int32_t *ibuf, const
         CU(cudaMemcpy(b.sid, sd.data(), n * 8, cudaMemcpyHostToDevice));
     }
     unsigned long long v = (unsigned long long)n;
+    if (into_input) { c->n_census = n; return 0; }
     CU(cudaMemcpy(c->P.counters + CNT_NDXOUT, &v, 8, cudaMemcpyHostToDevice));
     return 0;
 }
@@ -921,6 +1026,7 @@ int c2d_kernel_time_ms(c2d_ctx *h, int which, float *ms, int64_t *launches)
     Ctx *c = reinterpret_cast<Ctx *>(h);
     if (!c) return fail(C2D_EINVAL, "NULL ctx");
     if (which == -1) { c->timing = true; return 0; }          // enable
+    if (which == -5) { c->timer_collect(); c->timing = false; return 0; }   // disable
     if (which == -3 || which == -4) {                         // bracket a region on the library's stream -> family 7
         CU(cudaSetDevice(c->device));
         if (!c->ev_mark[0]) { CU(cudaEventCreate(&c->ev_mark[0])); CU(cudaEventCreate(&c->ev_mark[1])); }
@@ -933,8 +1039,8 @@ int c2d_kernel_time_ms(c2d_ctx *h, int which, float *ms, int64_t *launches)
         }
         return 0;
     }
-    if (which == -2) { c->timer_collect(); for (int k = 0; k < 8; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return 0; }   // reset
-    if (which < 0 || which >= 8) return fail(C2D_EINVAL, "kernel family %d", which);
+    if (which == -2) { c->timer_collect(); for (int k = 0; k < Ctx::kFamilies; k++) { c->k_ms[k] = 0; c->k_launches[k] = 0; } return 0; }   // reset
+    if (which < 0 || which >= Ctx::kFamilies) return fail(C2D_EINVAL, "kernel family %d", which);
     c->timer_collect();
     if (ms) *ms = (float)c->k_ms[which];
     if (launches) *launches = c->k_launches[which];

@@ -8,16 +8,40 @@
 namespace c2d {
 
 int fail(int code, const char *fmt, ...);
+struct Ctx;
+int check_events(Ctx *c);      // C2D_EEVENTS when the step produced more escape records than event_capacity
 
 struct FpState;
 struct LcState;
+struct Comm;
+struct FpParams;
+
+// collectives (c2d_comm.cu).  kind: 0 = FP64 sum, 1 = int64 sum, 2 = FP64 max; device pointers, library stream
+struct Ctx;
+int comm_world(const Ctx *c);
+int comm_rank(const Ctx *c);
+void comm_free(Ctx *c);
+int comm_allreduce(Ctx *c, const void *send, void *recv, size_t n, int kind);
+int comm_allgather(Ctx *c, const void *send, void *recv, size_t bytes_per_rank);
+
+// rows of the resident plasma blob Ctx::d_plasma (each padded to an even number of zones)
+enum { PL_TNA = 0, PL_B, PL_GMIN, PL_GMAX, PL_PNTH, PL_AMXWL, PL_TURB, PL_VOL, PL_ELOSS_SY, PL_EC_OLD, PL_TE_NEW, PL_ROWS };
+constexpr int kFpRecExtra = 16;        // per-zone scalars of the FP exchange record (c2d_fp.cu)
+int fp_resident(Ctx *c, const c2d_fp_in *in, double *zinfo_host);   // FP on the resident state + all-gather; zinfo [zone][16]
+
+struct GenBudget { std::vector<int32_t> nsv; std::vector<double> ew, e_sy, e_th; double Emiss_tot = 0.0; };
+int latch_census(Ctx *c);
+int gen_core(Ctx *c, double dt, int64_t nst, const double *d_B, const double *h_ne, const double *h_B, const double *h_vol,
+             const double *h_zsurf, GenBudget &g);
+int budget_upload(Ctx *c, const GenBudget &g);
+int begin_common(Ctx *c, int ncycle, double time, double dt);
 
 struct Ctx {
     int device = 0, n_sm = 0;
     cudaStream_t stream = nullptr;
     c2d_dims dims{};
     int nzone = 0;
-    bool inited = false, step_open = false, field_done = false;
+    bool inited = false, step_open = false, field_done = false, step_tracked = false;
     int64_t census_cap = 0, event_cap = 0, q_cap = 0, n_census = 0, vol_next = 0, histories = 0;
     long long q_peak = 0;
     // device memory
@@ -43,6 +67,17 @@ struct Ctx {
            t_erlko = 0, t_erlku = 0, t_erlkl = 0, t_Edin = 0, t_Edref = 0, n_f64 = 0;
     size_t i_npcen = 0, i_nel = 0, i_cnt = 0, n_i64 = 0;
     Params P{};
+    // collectives + what only exists once per rank
+    Comm *comm = nullptr;
+    double *d_fout_total = nullptr;        // [C2D_NMUMAX][nphtotal] escaping spectrum summed over the run (xec2d.f:389-394)
+    unsigned long long *d_cnt_global = nullptr;   // [CNT_N] counters summed over the ranks by c2d_tally_reduce
+    bool step_reduced = false;             // c2d_tally_reduce already ran in this step
+    // resident plasma state (c2d_step.cu): f_nt, Pnt, n_e, f_pair, tea, zsurf live in d_step (the tracker reads them there)
+    double *d_plasma = nullptr;            // [tna | B_field | gmin | gmax | p_nth | amxwl | turb_lev | vol | Eloss_sy | ec_old | Te_new] x nzone
+    bool plasma_set = false;
+    std::vector<double> h_ne, h_B, h_vol, h_zsurf, h_tna;   // host mirrors of the per-zone scalars the budget arithmetic needs
+    double *d_fpx = nullptr;               // FP exchange buffers: [out arrays | send | recv]
+    size_t fpx_cap = 0;
     std::vector<int64_t> h_prefix;
     std::vector<double> h_f64, h_gnt, h_Efield, h_z, h_r, h_Eph;
     double *d_gen = nullptr;               // scratch of c2d_step_begin_gen
@@ -71,14 +106,16 @@ struct Ctx {
     void lc_free(int slot);
     void lc_free_all();
     // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3_attempts, 3 FP, 4 sigma table, 5 tally bench,
-    // 6 k_split3_flights
+    // 6 k_split3_flights, 7 bracket, 8 tally all-reduce (includes the wait for the slowest rank), 9 FP all-gather,
+    // 10 cascade exchange (all-gather of the 3rd-split tasks), 11 bank sort
     bool timing = false;
     std::vector<cudaEvent_t> ev_pool;
     std::vector<int> ev_which;
     size_t ev_used = 0;
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
-    double k_ms[8] = {0};
-    int64_t k_launches[8] = {0};
+    static constexpr int kFamilies = 12;
+    double k_ms[kFamilies] = {0};
+    int64_t k_launches[kFamilies] = {0};
     void timer_begin(int which);
     void timer_end();
     void timer_collect();

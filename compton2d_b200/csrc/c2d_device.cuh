@@ -81,6 +81,7 @@ struct Seg {                 // one zone crossing of the collision-free ray of a
 struct Params {
     int nz, nr, nzone, n_vol, num_nt, nphfield, n_gg, nphtotal, nph_lc, nmu;
     int pair_switch, spec_switch, cr_sent, split1, split2, split3, spl3_trg, ncycle, sigma_mode;
+    int bins_off;                                     // 1: sources are born with jgpsp = jgplc = jgpmu = 0 (c2d_run.quirk_cycle0)
     int n_ref;                                        // Compton-reflection tables of ref_matrix.f (static inputs), 0 = none
     const double *E_ref, *P_ref, *W_abs;              // P_ref / W_abs in COMMON order: (n_out, n_in) at (n_in-1) n_ref + (n_out-1)
     uint32_t key0, key1;

@@ -817,6 +817,143 @@ static int fp_state(Ctx *c)
     return 0;
 }
 
+
+// the broadcast scalars of FP_bcast (fp_mpi.f:579-600) + the static tables
+static void fp_fill_scalars(Ctx *c, const c2d_fp_in *in, FpParams &q)
+{
+    const c2d_dims &d = c->dims;
+    memset(&q, 0, sizeof q);
+    q.nz = d.nz; q.nr = d.nr; q.N = d.num_nt; q.nf = d.nphfield; q.pair_switch = d.pair_switch;
+    q.inj_switch = in->inj_switch; q.inj_dis = in->inj_dis; q.g2var_switch = in->g2var_switch; q.pick_sw = in->pick_sw;
+    q.cf_sentinel = in->cf_sentinel;
+    q.time = in->time; q.dt = in->dt; q.lnL = in->lnL; q.rmin = d.rmin; q.zmin = d.zmin;
+    q.z_nz = c->h_z[d.nz - 1]; q.r_nr = c->h_r[d.nr - 1];
+    q.inj_g1 = in->inj_g1; q.inj_g2 = in->inj_g2; q.inj_p = in->inj_p; q.inj_t = in->inj_t; q.inj_gg = in->inj_gg;
+    q.inj_sigma = in->inj_sigma; q.inj_L = in->inj_L; q.inj_v = in->inj_v; q.pick_rate = in->pick_rate;
+    q.r_esc = in->r_esc; q.r_acc = in->r_acc;
+    q.r_flare = in->r_flare; q.z_flare = in->z_flare; q.t_flare = in->t_flare; q.sigma_r = in->sigma_r;
+    q.sigma_z = in->sigma_z; q.sigma_t = in->sigma_t; q.flare_amp = in->flare_amp;
+    q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.F_IC = c->fp->d_FIC;
+    q.F_ICt = c->fp->d_FICt;
+    q.qt_x15 = c->fp->d_quad;
+    q.gtab = c->fp->d_gtab; q.gtab_n = kGtabN; q.gtab_x0 = kGtabX0; q.gtab_ih = 1.0 / kGtabH;
+}
+
+// ---- the Fokker-Planck update on the resident plasma state (c2d_step.cu), zones dealt out rank::world, and the exchange of
+// the results: FP_recv_result + FP_end_bcast (fp_mpi.f:926,1017-1079) as one all-gather of packed per-zone records
+// [f_nt N | Pnt N | n_e Te_new gmin gmax p_nth amxwl f_pair E_old E_new hr hr_st dT steps dr dz f_t_implicit].
+#ifndef C2D_EMU
+__global__ void k_fp_pack(const FpParams q, double *send, int rec)
+{
+    const int slot = blockIdx.x;
+    const int zi = q.first_zone + slot * q.zone_stride;
+    double *o = send + (size_t)slot * rec;
+    const int N = q.N;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { o[i] = q.f_nt[(size_t)zi * N + i]; o[N + i] = q.Pnt[(size_t)zi * N + i]; }
+    if (threadIdx.x == 0) {
+        double *e = o + 2 * N;
+        e[0] = q.n_e[zi]; e[1] = q.Te_new[zi]; e[2] = q.gmin[zi]; e[3] = q.gmax[zi]; e[4] = q.p_nth[zi]; e[5] = q.amxwl[zi];
+        e[6] = q.f_pair[zi]; e[7] = q.zE_old[zi]; e[8] = q.zE_new[zi]; e[9] = q.z_hr[zi]; e[10] = q.z_hrst[zi]; e[11] = q.z_dT[zi];
+        e[12] = (double)q.fp_steps[zi]; e[13] = q.z_misc[3 * zi]; e[14] = q.z_misc[3 * zi + 1]; e[15] = q.z_misc[3 * zi + 2];
+    }
+}
+// recv = [world][n_slot][rec]; slot s of rank w holds zone w + s world.  Writes the state every rank carries into the next
+// step (update2d.f:262-276: tea = Te_new clamped to [5, 1000] keV where tna > 1) and the per-zone scalars zinfo[zone][16].
+__global__ void k_fp_unpack(const double *recv, int world, int n_slot, int rec, int nzone, int N, double *f_nt, double *Pnt,
+                            double *n_e, double *f_pair, double *tea, const double *tna, double *gmin, double *gmax, double *p_nth,
+                            double *amxwl, double *Te_new, double *zinfo)
+{
+    const int zi = blockIdx.x;
+    if (zi >= nzone) return;
+    const int w = zi % world, s = zi / world;
+    const double *o = recv + ((size_t)w * n_slot + s) * rec;
+    for (int i = threadIdx.x; i < N; i += blockDim.x) { f_nt[(size_t)zi * N + i] = o[i]; Pnt[(size_t)zi * N + i] = o[N + i]; }
+    if (threadIdx.x < kFpRecExtra) zinfo[(size_t)zi * kFpRecExtra + threadIdx.x] = o[2 * N + threadIdx.x];
+    if (threadIdx.x == 0) {
+        const double *e = o + 2 * N;
+        n_e[zi] = e[0]; Te_new[zi] = e[1]; gmin[zi] = e[2]; gmax[zi] = e[3]; p_nth[zi] = e[4]; amxwl[zi] = e[5]; f_pair[zi] = e[6];
+        if (tna[zi] > 1.) {
+            double t = e[1];
+            t = fmin(1.e3, t);
+            t = fmax(5.0, t);
+            tea[zi] = t;
+        }
+    }
+}
+#endif
+
+int fp_resident(Ctx *c, const c2d_fp_in *in, double *zinfo_host)
+{
+#ifdef C2D_EMU
+    (void)c; (void)in; (void)zinfo_host;
+    return fail(C2D_EINVAL, "the Fokker-Planck kernel needs the device build");
+#else
+    int rc = fp_state(c);
+    if (rc) return rc;
+    const c2d_dims &d = c->dims;
+    const int N = d.num_nt, nf = d.nphfield, nzone = c->nzone;
+    const int world = comm_world(c), rank = comm_rank(c);
+    if (!c->fp->have_FIC) {
+        launch_ic_loss(c->P.gnt, c->P.E_field, N, nf, c->fp->d_FIC, c->stream);
+        launch_transpose(c->fp->d_FIC, N, nf, c->fp->d_FICt, c->stream);
+        c->fp->have_FIC = true;
+    }
+    const int n_slot = (nzone + world - 1) / world, rec = 2 * N + kFpRecExtra;
+    const int n_own = (rank < nzone) ? (nzone - rank + world - 1) / world : 0;
+    // scratch: out arrays | send | recv | zinfo
+    size_t n = 0;
+    auto take = [&](size_t cnt) { size_t o = n; n += (cnt + 1) & ~size_t(1); return o; };
+    const size_t p_f = take((size_t)nzone * N), p_P = take((size_t)nzone * N), p_ne = take(nzone), p_Te = take(nzone),
+                 p_gmin = take(nzone), p_gmax = take(nzone), p_pn = take(nzone), p_am = take(nzone), p_fp = take(nzone),
+                 p_Eo = take(nzone), p_En = take(nzone), p_hr = take(nzone), p_hs = take(nzone), p_dT = take(nzone),
+                 p_misc = take((size_t)3 * nzone), p_steps = take(nzone), p_send = take((size_t)n_slot * rec),
+                 p_recv = take((size_t)world * n_slot * rec), p_zi = take((size_t)nzone * kFpRecExtra);
+    if (n > c->fpx_cap) {
+        cudaFree(c->d_fpx); c->d_fpx = nullptr; c->fpx_cap = 0;
+        CUF(cudaMalloc(&c->d_fpx, n * 8));
+        c->fpx_cap = n;
+    }
+    double *D = c->d_fpx, *T = c->d_step, *S = c->d_plasma;
+    const size_t nzp = ((size_t)nzone + 1) & ~size_t(1);
+    double *s_tna = S + PL_TNA * nzp, *s_B = S + PL_B * nzp, *s_gmin = S + PL_GMIN * nzp, *s_gmax = S + PL_GMAX * nzp,
+           *s_pn = S + PL_PNTH * nzp, *s_am = S + PL_AMXWL * nzp, *s_tl = S + PL_TURB * nzp, *s_vol = S + PL_VOL * nzp,
+           *s_sy = S + PL_ELOSS_SY * nzp, *s_eco = S + PL_EC_OLD * nzp, *s_Te = S + PL_TE_NEW * nzp;
+    // gmin / gmax / p_nth / amxwl are in/out of FP_calc (a zone whose amxwl -> 1 keeps its p_nth)
+    CUF(cudaMemcpyAsync(D + p_gmin, s_gmin, (size_t)nzone * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUF(cudaMemcpyAsync(D + p_gmax, s_gmax, (size_t)nzone * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUF(cudaMemcpyAsync(D + p_pn, s_pn, (size_t)nzone * 8, cudaMemcpyDeviceToDevice, c->stream));
+    CUF(cudaMemcpyAsync(D + p_am, s_am, (size_t)nzone * 8, cudaMemcpyDeviceToDevice, c->stream));
+    FpParams q;
+    fp_fill_scalars(c, in, q);
+    q.first_zone = rank; q.n_zones = n_own; q.zone_stride = world;
+    q.f_nt_in = T + c->o_fnt; q.Pnt_in = T + c->o_pnt;
+    q.n_field = c->P.n_field; q.ecens = c->P.ecens;                 // this step's tallies, already reduced over the ranks
+    q.n_e_in = T + c->o_ne; q.B_field = s_B; q.tea = T + c->o_tea; q.tna = s_tna; q.vol = s_vol;
+    q.f_pair_in = T + c->o_fpair; q.Eloss_sy = s_sy; q.ec_old = s_eco; q.turb_lev = s_tl;
+    q.f_nt = D + p_f; q.Pnt = D + p_P; q.n_e = D + p_ne; q.Te_new = D + p_Te; q.gmin = D + p_gmin; q.gmax = D + p_gmax;
+    q.p_nth = D + p_pn; q.amxwl = D + p_am; q.f_pair = D + p_fp;
+    q.zE_old = D + p_Eo; q.zE_new = D + p_En; q.z_hr = D + p_hr; q.z_hrst = D + p_hs; q.z_dT = D + p_dT; q.z_misc = D + p_misc;
+    q.fp_steps = reinterpret_cast<int *>(D + p_steps);
+    if (n_own > 0) {
+        c->timer_begin(3);
+        launch_fp(q, c->stream);
+        k_fp_pack<<<n_own, 128, 0, c->stream>>>(q, D + p_send, rec);
+        c->timer_end();
+        CUF(cudaGetLastError());
+    }
+    c->timer_begin(9);
+    rc = comm_allgather(c, D + p_send, D + p_recv, (size_t)n_slot * rec * 8);
+    c->timer_end();
+    if (rc) return rc;
+    k_fp_unpack<<<nzone, 128, 0, c->stream>>>(D + p_recv, world, n_slot, rec, nzone, N, T + c->o_fnt, T + c->o_pnt, T + c->o_ne,
+                                              T + c->o_fpair, T + c->o_tea, s_tna, s_gmin, s_gmax, s_pn, s_am, s_Te, D + p_zi);
+    CUF(cudaGetLastError());
+    CUF(cudaMemcpyAsync(zinfo_host, D + p_zi, (size_t)nzone * kFpRecExtra * 8, cudaMemcpyDeviceToHost, c->stream));
+    CUF(cudaStreamSynchronize(c->stream));
+    return 0;
+#endif
+}
+
 }  // namespace c2d
 
 using namespace c2d;
@@ -939,22 +1076,8 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
     rc = up(p_gmin, out->gmin, nzone) | up(p_gmax, out->gmax, nzone) | up(p_pn, out->p_nth, nzone) | up(p_am, out->amxwl, nzone);
     if (rc) return rc;
     FpParams q;
-    memset(&q, 0, sizeof q);
-    q.nz = d.nz; q.nr = d.nr; q.N = N; q.nf = nf; q.pair_switch = d.pair_switch;
+    fp_fill_scalars(c, in, q);
     q.first_zone = in->first_zone; q.n_zones = n_zones; q.zone_stride = in->zone_stride;
-    q.inj_switch = in->inj_switch; q.inj_dis = in->inj_dis; q.g2var_switch = in->g2var_switch; q.pick_sw = in->pick_sw;
-    q.cf_sentinel = in->cf_sentinel;
-    q.time = in->time; q.dt = in->dt; q.lnL = in->lnL; q.rmin = d.rmin; q.zmin = d.zmin;
-    q.z_nz = c->h_z[d.nz - 1]; q.r_nr = c->h_r[d.nr - 1];
-    q.inj_g1 = in->inj_g1; q.inj_g2 = in->inj_g2; q.inj_p = in->inj_p; q.inj_t = in->inj_t; q.inj_gg = in->inj_gg;
-    q.inj_sigma = in->inj_sigma; q.inj_L = in->inj_L; q.inj_v = in->inj_v; q.pick_rate = in->pick_rate;
-    q.r_esc = in->r_esc; q.r_acc = in->r_acc;
-    q.r_flare = in->r_flare; q.z_flare = in->z_flare; q.t_flare = in->t_flare; q.sigma_r = in->sigma_r;
-    q.sigma_z = in->sigma_z; q.sigma_t = in->sigma_t; q.flare_amp = in->flare_amp;
-    q.z = c->P.z; q.r = c->P.r; q.gnt = c->P.gnt; q.F_IC = c->fp->d_FIC;
-    q.F_ICt = c->fp->d_FICt;
-    q.qt_x15 = c->fp->d_quad;
-    q.gtab = c->fp->d_gtab; q.gtab_n = kGtabN; q.gtab_x0 = kGtabX0; q.gtab_ih = 1.0 / kGtabH;
     q.f_nt_in = D + o_f; q.Pnt_in = D + o_P;
     q.n_field = in->n_field ? D + o_nf : c->P.n_field;
     q.ecens = in->ecens ? D + o_ec : c->P.ecens;

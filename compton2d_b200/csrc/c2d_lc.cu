@@ -434,6 +434,7 @@ extern "C" int c2d_lc_accumulate(c2d_ctx *h)
     if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
     if (!lc_any(c)) return fail(C2D_ESTATE, "c2d_lc_begin has not been called");
     if (int rc = c2d_sync(h)) return rc;                                        // the scattering queue must have drained
+    if (int rc = check_events(c)) return rc;                                    // an overflowed list would silently drop photons
     // the record count lives on the device (counters[C2D_CNT_NEVENTS]); records beyond event_capacity were not stored
     for (int k = 0; k < Ctx::kLcSlots; k++)
         if (c->lc_slot[k])

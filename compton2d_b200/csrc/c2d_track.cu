@@ -374,6 +374,7 @@ __global__ void __launch_bounds__(C2D_HIST_THREADS, C2D_HIST_MINB) k_history(con
         if (P0.wmu < -1.0) P0.wmu = -1.0;
         S_entry = p.in.sid[h];
     }
+    if (SRC != 1 && p.bins_off) { P0.jgpsp = 0; P0.jgplc = 0; P0.jgpmu = 0; }
     history(p, active, P0, S_entry);
 }
 

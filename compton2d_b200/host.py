@@ -77,8 +77,60 @@ class Compton2d:
             self.L.c2d_destroy(self.h)
             self.h = None
             raise
-        self.fout_total = np.zeros((_l.NMUMAX, self.nphtotal))      # cumulative over the run (xec2d.f:389-394)
         self.ncycle = 0
+        self.time = 0.0
+        self._comm_ready = self.world == 1
+        self._ext_keep = None
+
+    # ------------------------------------------------------------------ ranks
+    def comm_init(self, group=None):
+        """Join this context to the job's ranks.  With torch.distributed on NCCL the library opens its own NCCL
+        communicator (rank 0 makes the id, the 128 bytes travel through torch.distributed once) and every later collective --
+        the tally all-reduce, the FP all-gather, the 3rd-split exchange -- runs inside libcompton2d_b200.so on its stream.
+        On any other backend (gloo in the CPU tests of the host logic, where "device" memory is host memory) the library
+        is handed that transport through c2d_comm_init_ext."""
+        if self._comm_ready:
+            return
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend(group) == "nccl":
+            idb = (C.c_ubyte * _l.COMM_ID_BYTES)()
+            if self.rank == 0:
+                _l.check(self.L.c2d_comm_unique_id(idb))
+            t = torch.tensor(list(bytes(idb)), dtype=torch.uint8, device="cuda")
+            dist.broadcast(t, src=0, group=group)
+            idb = (C.c_ubyte * _l.COMM_ID_BYTES)(*t.cpu().tolist())
+            _l.check(self.L.c2d_comm_init(self.h, idb, self.rank, self.world))
+        else:
+            world = self.world
+
+            def view(ptr, n, dt):
+                return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(dt)), shape=(int(n),))
+
+            def allreduce(user, send, recv, n, kind, stream):
+                try:
+                    dt = C.c_int64 if kind == 1 else C.c_double
+                    t = torch.from_numpy(view(send, n, dt).copy())
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX if kind == 2 else dist.ReduceOp.SUM, group=group)
+                    view(recv, n, dt)[:] = t.numpy()
+                    return 0
+                except Exception:                      # never raise through the C frame
+                    return 1
+
+            def allgather(user, send, recv, nbytes, stream):
+                try:
+                    t = torch.from_numpy(view(send, nbytes, C.c_ubyte).copy())
+                    out = [torch.empty_like(t) for _ in range(world)]
+                    dist.all_gather(out, t, group=group)
+                    view(recv, nbytes * world, C.c_ubyte)[:] = torch.cat(out).numpy()
+                    return 0
+                except Exception:
+                    return 1
+
+            vt = _l.CommExt(None, _l.ALLREDUCE_FN(allreduce), _l.ALLGATHER_FN(allgather))
+            self._ext_keep = vt                        # the callbacks must outlive the context
+            _l.check(self.L.c2d_comm_init_ext(self.h, self.rank, self.world, C.byref(vt)))
+        self._comm_ready = True
 
     def close(self):
         if getattr(self, "h", None):
@@ -199,24 +251,11 @@ class Compton2d:
         _l.check(self.L.c2d_sync(self.h))
 
     def graphics_collect(self, group=None):
-        """cens_add_up + E_add_up + xec_add + graphics_collect (update2d.f:1931-2083, xec2d.f:325-394):
-        one all-reduce(sum) per packed tally buffer, in place on the device."""
-        self.sync()
-        if self.world == 1:
-            return
-        import torch
-        import torch.distributed as dist
-        f, i = self.tally_device_views()
-        tf = torch.as_tensor(f, device="cuda")
-        ti = torch.as_tensor(i, device="cuda")
-        # counters[0] = ndxout and counters[4] = nevents index this rank's census bank / event buffer:
-        # they are per-rank state and must survive the reduction
-        keep = ti[[-16, -12]].clone()
-        dist.all_reduce(tf, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(ti, op=dist.ReduceOp.SUM, group=group)
-        self.ndxout_global, self.nevents_global = (int(x) for x in ti[[-16, -12]].tolist())
-        ti[[-16, -12]] = keep
-        torch.cuda.synchronize()
+        """cens_add_up + E_add_up + xec_add + graphics_collect (update2d.f:1931-2083, xec2d.f:325-394): c2d_tally_reduce --
+        one all-reduce(sum) per packed tally buffer, in place on the device, inside the library (NCCL on its stream); the
+        run-long escaping spectrum fout_total advances by the reduced per-step one."""
+        self.comm_init(group)
+        _l.check(self.L.c2d_tally_reduce(self.h, None))
 
     def tally_device_views(self):
         pf, pi = C.c_void_p(), C.c_void_p()
@@ -333,11 +372,93 @@ class Compton2d:
                    nelectron=np.zeros(self.num_nt + 2, np.int64), fout=np.zeros((_l.NMUMAX, self.nphtotal)),
                    edout=np.zeros((_l.NMUMAX, _l.NLCMAX)), erlki=np.zeros(self.nz), erlko=np.zeros(self.nz),
                    erlku=np.zeros(self.nr), erlkl=np.zeros(self.nr), Ed_in=np.zeros(self.nr), Ed_ref=np.zeros(self.nr))
+        out["fout_total"] = np.zeros((_l.NMUMAX, self.nphtotal))
         t = _l.Tallies()
         for k, v in out.items():
             setattr(t, k, v.ctypes.data_as(_l.lp if v.dtype == np.int64 else _l.dp))
         _l.check(self.L.c2d_tally_read(self.h, C.byref(t)))
         out["counters"] = {n: int(t.counters[i]) for i, n in enumerate(_l.COUNTERS)}
+        out["counters_global"] = {n: int(t.counters_global[i]) for i, n in enumerate(_l.COUNTERS)}
+        return out
+
+    # ------------------------------------------------------------------ closed time step on the resident plasma
+    def plasma_set(self, **kw):
+        """Upload (parts of) the per-zone plasma state: f_nt, Pnt [zone][num_nt]; n_e, tea, tna, B_field, f_pair, gmin, gmax,
+        p_nth, amxwl, turb_lev, vol, zsurf [zone]; k_gg [zone][n_gg].  The first call needs all but f_pair, turb_lev, k_gg."""
+        nzn, N = self.nzone, self.num_nt
+        size = dict(f_nt=nzn * N, Pnt=nzn * N, k_gg=nzn * self.n_gg)
+        p = _l.Plasma()
+        keep = {}
+        for name, _ in _l.Plasma._fields_:
+            v = kw.pop(name, None)
+            keep[name] = _d(v, size.get(name, nzn), name)
+            setattr(p, name, _p(keep[name]))
+        if kw:
+            raise TypeError(f"unknown plasma members {sorted(kw)}")
+        _l.check(self.L.c2d_plasma_set(self.h, C.byref(p)))
+
+    def plasma_get(self):
+        nzn, N = self.nzone, self.num_nt
+        out = {n: np.zeros((nzn, N) if n in ("f_nt", "Pnt") else nzn) for n, _ in _l.PlasmaOut._fields_}
+        p = _l.PlasmaOut()
+        for k, v in out.items():
+            setattr(p, k, _p(v))
+        _l.check(self.L.c2d_plasma_get(self.h, C.byref(p)))
+        return out
+
+    def run_config(self, *, nst, T_const=0, quirk_cycle0=0, inj=None, flare=None, r_esc=0.3, r_acc=1.0, surface=None):
+        """The run constants of input.dat the step needs (reader.f:157-597); `surface` = dict(tbbi/tbbo [nz], tbbu/tbbl [nr],
+        spectra=[file_sp dicts], spec_* per ring, t0, star_switch, Rstar, dist_star) or None."""
+        inj, flare = dict(inj or {}), dict(flare or {})
+        r = _l.Run(nst=int(nst), T_const=int(T_const), quirk_cycle0=int(quirk_cycle0), inj_switch=int(inj.get("inj_switch", 0)),
+                   inj_dis=int(inj.get("inj_dis", 2)), g2var_switch=int(inj.get("g2var_switch", 0)), pick_sw=int(inj.get("pick_sw", 0)),
+                   cf_sentinel=int(flare.get("cf_sentinel", 0)), inj_g1=float(inj.get("inj_g1", 1e2)), inj_g2=float(inj.get("inj_g2", 3e4)),
+                   inj_p=float(inj.get("inj_p", 1.0)), inj_t=float(inj.get("inj_t", 1.2e6)), inj_gg=float(inj.get("inj_gg", 1e2)),
+                   inj_sigma=float(inj.get("inj_sigma", 1e1)), inj_L=float(inj.get("inj_L", 5e40)), inj_v=float(inj.get("inj_v", 2.9965e10)),
+                   pick_rate=float(inj.get("pick_rate", 0.8e-3)), r_esc=float(r_esc), r_acc=float(r_acc),
+                   r_flare=float(flare.get("r_flare", 0.0)), z_flare=float(flare.get("z_flare", 0.0)), t_flare=float(flare.get("t_flare", 1e6)),
+                   sigma_r=float(flare.get("sigma_r", 1e15)), sigma_z=float(flare.get("sigma_z", 1e15)), sigma_t=float(flare.get("sigma_t", 1e6)),
+                   flare_amp=float(flare.get("flare_amp", 10.0)))
+        keep = [r]
+        if surface:
+            nz, nr = self.nz, self.nr
+            spectra = list(surface.get("spectra", ()))
+            nfmax = max([len(t["E_file"]) for t in spectra], default=1)
+            sr = _l.SurfRun(star_switch=int(surface.get("star_switch", 0)), Rstar=float(surface.get("Rstar", 1.0)),
+                            dist_star=float(surface.get("dist_star", 1.0)), t0=float(surface.get("t0", 0.0)), n_spec=len(spectra), nfmax=nfmax)
+            for name, n in (("tbbi", nz), ("tbbo", nz), ("tbbu", nr), ("tbbl", nr)):
+                a = _d(surface.get(name), n, name); keep.append(a); setattr(sr, name, _p(a))
+            for name, n in (("spec_i", nz), ("spec_o", nz), ("spec_u", nr), ("spec_l", nr)):
+                v = surface.get(name)
+                a = None if v is None else np.ascontiguousarray(v, dtype=np.int32).ravel()
+                keep.append(a); setattr(sr, name, a.ctypes.data_as(_l.ip) if a is not None else None)
+            tab = {k: np.zeros((max(len(spectra), 1), nfmax)) for k in ("E_file", "F_file", "P_file", "a1", "I_file")}
+            nfile = np.zeros(max(len(spectra), 1), np.int32); intf = np.zeros(max(len(spectra), 1))
+            for q, t in enumerate(spectra):
+                for k in tab:
+                    tab[k][q, : len(t[k])] = t[k]
+                nfile[q] = t["nfile"]; intf[q] = t["int_file"]
+            for k, v in tab.items():
+                keep.append(v); setattr(sr, k, _p(v.ravel()))
+            keep += [nfile, intf]
+            sr.nfile = nfile.ctypes.data_as(_l.ip); sr.int_file = _p(intf)
+            keep.append(sr)
+            r.surf = C.pointer(sr)
+        self._run = (r, keep)
+        return r
+
+    def step(self, dt, group=None):
+        """== one iteration of xec's loop (xec2d.f:100-110 / 141-193) on the resident plasma: imcgen2d -> imcfield2d ->
+        imcvol2d -> imcsurf2d -> update -> graphics_collect, entirely inside the library (c2d_step).  Advances self.time and
+        self.ncycle as xec does (l.94-103).  -> dict of the scalars the reference logs for the cycle."""
+        self.comm_init(group)
+        rep = _l.StepReport()
+        _l.check(self.L.c2d_step(self.h, C.byref(self._run[0]), int(self.ncycle), float(self.time), float(dt), C.byref(rep)))
+        out = {n: getattr(rep, n) for n, _ in _l.StepReport._fields_ if n != "ms"}
+        out["ms"] = dict(zip(_l.FAMILIES, list(rep.ms)))
+        if self.ncycle > 0:
+            self.time += float(dt)
+        self.ncycle += 1
         return out
 
     def census_count(self):
@@ -442,7 +563,7 @@ class Compton2d:
 
     # ------------------------------------------------------------------ measurement
     def timing(self, enable=True):
-        _l.check(self.L.c2d_kernel_time_ms(self.h, -1 if enable else -2, None, None))
+        _l.check(self.L.c2d_kernel_time_ms(self.h, -1 if enable else -5, None, None))
 
     def mark(self, stop=False):
         """Record the start / stop CUDA event of a timed bracket on the library's stream (kernel_time(7))."""

@@ -55,7 +55,8 @@ class SurfIn(C.Structure):
 class Tallies(C.Structure):
     _fields_ = [("edep", dp), ("prdep", dp), ("ecens", dp), ("npcen", lp), ("n_field", dp), ("n_ph", dp),
                 ("E_IC", dp), ("nelectron", lp), ("fout", dp), ("edout", dp), ("erlki", dp), ("erlko", dp),
-                ("erlku", dp), ("erlkl", dp), ("Ed_in", dp), ("Ed_ref", dp), ("counters", C.c_int64 * 16)]
+                ("erlku", dp), ("erlkl", dp), ("Ed_in", dp), ("Ed_ref", dp), ("counters", C.c_int64 * 16),
+                ("fout_total", dp), ("counters_global", C.c_int64 * 16)]
 
 
 class FpIn(C.Structure):
@@ -76,6 +77,54 @@ class FpOut(C.Structure):
                                    "f_t_implicit")]
 
 
+class Plasma(C.Structure):
+    _fields_ = [(n, dp) for n in ("f_nt", "Pnt", "n_e", "tea", "tna", "B_field", "f_pair", "gmin", "gmax", "p_nth", "amxwl",
+                                  "turb_lev", "vol", "zsurf", "k_gg")]
+
+
+class PlasmaOut(C.Structure):
+    _fields_ = [(n, dp) for n in ("f_nt", "Pnt", "n_e", "tea", "f_pair", "B_field", "gmin", "gmax", "p_nth", "amxwl", "Te_new",
+                                  "Eloss_sy", "ec_old")]
+
+
+class SurfRun(C.Structure):
+    _fields_ = [("star_switch", C.c_int), ("Rstar", C.c_double), ("dist_star", C.c_double), ("t0", C.c_double)] + \
+        [(n, dp) for n in ("tbbi", "tbbo", "tbbu", "tbbl")] + [(n, ip) for n in ("spec_i", "spec_o", "spec_u", "spec_l")] + \
+        [("n_spec", C.c_int), ("nfmax", C.c_int), ("nfile", ip), ("int_file", dp)] + \
+        [(n, dp) for n in ("E_file", "F_file", "P_file", "a1", "I_file")]
+
+
+class Run(C.Structure):
+    _fields_ = [("nst", C.c_int64), ("T_const", C.c_int), ("quirk_cycle0", C.c_int)] + \
+        [(n, C.c_int) for n in ("inj_switch", "inj_dis", "g2var_switch", "pick_sw", "cf_sentinel")] + \
+        [(n, C.c_double) for n in ("inj_g1", "inj_g2", "inj_p", "inj_t", "inj_gg", "inj_sigma", "inj_L", "inj_v", "pick_rate",
+                                   "r_esc", "r_acc", "r_flare", "z_flare", "t_flare", "sigma_r", "sigma_z", "sigma_t",
+                                   "flare_amp")] + [("surf", C.POINTER(SurfRun))]
+
+
+class StepReport(C.Structure):
+    _fields_ = [("ncycle", C.c_int), ("time", C.c_double), ("dt", C.c_double), ("n_census_in", C.c_int64),
+                ("n_volume", C.c_int64), ("n_surface", C.c_int64)] + \
+        [(n, C.c_int64) for n in ("histories", "ndxout", "nevents", "cmcount1", "cmcount2")] + \
+        [(n, C.c_double) for n in ("bingo", "Emiss_tot", "fbias", "luminosity")] + \
+        [(n, C.c_int) for n in ("fp_ran", "fp_steps_min", "fp_steps_max")] + \
+        [(n, C.c_double) for n in ("E_tot_old", "E_tot_new", "dE_fraction", "dT_max", "dt_new", "hr_total", "hr_st_total")] + \
+        [("ms", C.c_double * 12)]
+
+
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
+
+
+class CommExt(C.Structure):
+    _fields_ = [("user", C.c_void_p), ("allreduce", ALLREDUCE_FN), ("allgather", ALLGATHER_FN)]
+
+
+COMM_ID_BYTES = 128
+FAMILIES = ["k_history", "k_children", "k_split3_attempts", "k_fp_zones", "k_sigma_table", "tally_bench", "k_split3_flights",
+            "bracket", "tally_allreduce", "fp_allgather", "cascade_exchange", "bank_sort"]
+
+
 class LcConfig(C.Structure):
     _fields_ = [(n, C.c_double) for n in ("gam_bulk", "rmax", "t_offset")] + \
         [(n, C.c_int) for n in ("n_t", "n_mu", "n_bands", "mu_closed", "first_band_only")] + \
@@ -91,7 +140,9 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
            "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
            "c2d_lc_select", "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar",
-           "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7", "c2d_tally_reduce", "c2d_finalize"]
+           "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7", "c2d_tally_reduce", "c2d_finalize",
+           "c2d_comm_unique_id", "c2d_comm_init", "c2d_comm_init_ext", "c2d_comm_info", "c2d_comm_destroy",
+           "c2d_plasma_set", "c2d_plasma_get", "c2d_step"]
 
 _lib = None
 
@@ -150,6 +201,14 @@ def load():
     L.c2d_lc_read.argtypes = [vp, vp, vp, vp]
     L.c2d_lc_device.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), lp]
     L.c2d_lc_bench.argtypes = [vp, C.c_int64, C.POINTER(C.c_float), lp]
+    L.c2d_comm_unique_id.argtypes = [vp]
+    L.c2d_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.c2d_comm_init_ext.argtypes = [vp, C.c_int, C.c_int, C.POINTER(CommExt)]
+    L.c2d_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.c2d_comm_destroy.argtypes = [vp]
+    L.c2d_plasma_set.argtypes = [vp, C.POINTER(Plasma)]
+    L.c2d_plasma_get.argtypes = [vp, C.POINTER(PlasmaOut)]
+    L.c2d_step.argtypes = [vp, C.POINTER(Run), C.c_int, C.c_double, C.c_double, C.POINTER(StepReport)]
     for fn in ("c2d_pack_bin_first", "c2d_unpack_bin_first"):
         getattr(L, fn).argtypes = [vp] + [C.c_int] * 6 + [vp]
         getattr(L, fn).restype = None

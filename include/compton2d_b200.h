@@ -36,7 +36,8 @@ enum {
     C2D_ECUDA = 3,         /* CUDA runtime error (message in c2d_last_error) */
     C2D_ECENSUS = 4,       /* census bank full: the reference's 'too many photons' STOP (imctrk2d.f:581-585) */
     C2D_EEVENTS = 5,       /* event buffer full (records beyond capacity were counted, not stored) */
-    C2D_ESTATE = 6         /* call order violated (step_begin before init, ...) */
+    C2D_ESTATE = 6,        /* call order violated (step_begin before init, ...) */
+    C2D_ECOMM = 7          /* collective failed / no transport (NCCL missing, rank mismatch) */
 };
 
 typedef struct c2d_ctx c2d_ctx;      /* opaque; one per GPU / per reference worker rank */
@@ -141,12 +142,16 @@ typedef struct {
     double *n_ph;                     /* [zone][n_gg] */
     double *E_IC;                     /* [num_nt] */
     int64_t *nelectron;               /* [num_nt+2], index = electron bin i (1-based as in nth2d) */
-    double *fout;                     /* [C2D_NMUMAX][nphtotal]  (cumulative over the run, as on the reference's workers) */
+    double *fout;                     /* [C2D_NMUMAX][nphtotal]  escaping spectrum of THIS step (zeroed by c2d_step_begin) */
     double *edout;                    /* [C2D_NMUMAX][C2D_NLCMAX] */
     double *erlki, *erlko;            /* [nz] */
     double *erlku, *erlkl;            /* [nr] */
     double *Ed_in, *Ed_ref;           /* [nr] */
-    int64_t counters[16];             /* see C2D_CNT_* */
+    int64_t counters[16];             /* see C2D_CNT_*; this rank's */
+    double *fout_total;               /* [C2D_NMUMAX][nphtotal]  escaping spectrum summed over the run and over the ranks: the
+                                         master's fout after graphics_collect (xec2d.f:389-394 sums the workers' never-zeroed
+                                         copies; graphics2d.f:147 divides it by time + dt).  Advanced by c2d_tally_reduce. */
+    int64_t counters_global[16];      /* counters summed over the ranks by c2d_tally_reduce (== counters on one rank) */
 } c2d_tallies;
 
 enum {
@@ -195,8 +200,10 @@ int c2d_imcsurf(c2d_ctx *ctx, int64_t first, int64_t count, int64_t stride);
 int c2d_sync(c2d_ctx *ctx);                                /* drains the scattering queue, waits for the device */
 int c2d_tally_read(c2d_ctx *ctx, c2d_tallies *out);        /* D2H copy of this context's (or the reduced) tallies */
 int c2d_tally_reduce(c2d_ctx *ctx, c2d_tallies *out);
-        /* c2d_sync + c2d_tally_read: the name SURVEY.md 8b gives the end-of-step hand-over.  With more than one rank the host
-           all-reduces the two buffers of c2d_tally_device (NCCL / CUDA-aware MPI) between c2d_sync and this call */
+        /* the end-of-step reduction: c2d_sync, then ONE all-reduce(sum) of the packed FP64 tally buffer and one of the packed
+           int64 buffer over the ranks of c2d_comm_init, in place in HBM -- cens_add_up + E_add_up + xec_add + graphics_collect
+           (update2d.f:1931-2083, xec2d.f:325-394) -- then fout_total += fout, then c2d_tally_read (out may be NULL).  Once per
+           step (a second call in the same step only reads).  Collective: every rank must call it. */
 int c2d_finalize(c2d_ctx *ctx);                             /* == c2d_destroy */
 int c2d_tally_device(c2d_ctx *ctx, double **fp64_buf, int64_t *n_fp64, int64_t **i64_buf, int64_t *n_i64);
         /* device pointers of the packed tally buffers, for the per-step all-reduce
@@ -205,6 +212,27 @@ int c2d_tally_device(c2d_ctx *ctx, double **fp64_buf, int64_t *n_fp64, int64_t *
 int c2d_comtot(c2d_ctx *ctx, int64_t n, const int32_t *zone, const double *xnu, int mode, double *comac);
         /* == comtot(j,k,xnuc,1,comac,enexc) (comtot2d.f:1-334) for n (0-based zone, xnu [keV]) pairs with the tables
            of the current step; mode 0 = bin by bin, 1 = the sigma_mode-1 table (context must have sigma_mode 1) */
+
+/* ---- ranks: one context per GPU, NCCL over NVLink inside the library -----------------------------------
+ * The reference's MPI calls on this path become: c2d_tally_reduce (all-reduce), the all-gather of the electron
+ * state after the Fokker-Planck update (c2d_step / c2d_update_fp_resident; FP_recv_result + FP_end_bcast, fp_mpi.f:926,
+ * 1017-1079) and the re-dealing of 3rd-split work between the ranks (c2d_sync).  NCCL is bound at run time (the libnccl.so.2
+ * the process already holds, else the system's).  Rank 0 makes an id, the host ships its 128 bytes to the other ranks with
+ * whatever it has (MPI_BCAST from the Fortran host, torch.distributed from Python), every rank calls c2d_comm_init. */
+#define C2D_COMM_ID_BYTES 128
+int c2d_comm_unique_id(void *id128);                              /* ncclGetUniqueId */
+int c2d_comm_init(c2d_ctx *ctx, const void *id128, int rank, int world);   /* collective; world = 1 needs no id */
+/* A host that brings its own transport (the reference's MPI on CUDA-aware buffers; gloo in the CPU tests of the host logic).
+ * Pointers are DEVICE pointers, the call must be ordered after the work already queued on `cuda_stream` and complete (or be
+ * stream-ordered) before it returns.  kind: 0 = FP64 sum, 1 = int64 sum, 2 = FP64 max; send may equal recv. */
+typedef struct {
+    void *user;
+    int (*allreduce)(void *user, const void *send, void *recv, int64_t n, int kind, void *cuda_stream);
+    int (*allgather)(void *user, const void *send, void *recv, int64_t bytes_per_rank, void *cuda_stream);
+} c2d_comm_ext;
+int c2d_comm_init_ext(c2d_ctx *ctx, int rank, int world, const c2d_comm_ext *transport);
+int c2d_comm_info(c2d_ctx *ctx, int *rank, int *world);
+int c2d_comm_destroy(c2d_ctx *ctx);
 
 /* ---- census bank: write_record / read_record contract (census2d.f:1-76) ---------------------- */
 int c2d_census_count(c2d_ctx *ctx, int64_t *n);
@@ -301,6 +329,71 @@ int c2d_gamma_bar(c2d_ctx *ctx, int64_t n, const double *Theta, double *gbar, do
         /* == gamma_bar(Theta) (volume2d.f:572-594: <gamma> of a Maxwellian, McDonald quadratures above Theta = 0.2) for n
            temperatures; gbar_table (may be NULL) = the interpolation table that predicts the lattice point of FP_calc's
            temperature walk (update2d.f:1446-1463), negated where Theta lies beyond the table */
+
+/* ---- the closed time step on a device-resident plasma state ---------------------------------------------
+ * One iteration of xec's loop (xec2d.f:100-110 / 141-193): imcgen2d -> imcfield2d -> imcvol2d -> imcsurf2d -> update ->
+ * graphics_collect, with the plasma the master keeps in COMMON (and re-broadcasts every step: vol_bcast, z_surf_bcast,
+ * FP_bcast, FP_end_bcast) resident in HBM on every rank instead.  See csrc/c2d_step.cu for the exact order. */
+typedef struct {                      /* per-zone plasma: inputm.dat (reader.f:608-657) + what FP_end_bcast carries (fp_mpi.f:1017-1079) */
+    const double *f_nt, *Pnt;         /* [zone][num_nt] (P_nontherm, nontherm2d.f:2-150) */
+    const double *n_e, *tea, *tna, *B_field;          /* [zone]; B_field as given (ep_switch = 0, imcgen2d.f:213-238) */
+    const double *f_pair;             /* [zone] or NULL */
+    const double *gmin, *gmax, *p_nth, *amxwl;        /* [zone] power-law fit carried between steps (update2d.f:1656-1738) */
+    const double *turb_lev;           /* [zone] or NULL */
+    const double *vol, *zsurf;        /* [zone] setup2d.f:80-114 */
+    const double *k_gg;               /* [zone][n_gg] or NULL */
+} c2d_plasma;                         /* c2d_plasma_set: NULL members keep their value (the first call needs all but f_pair, turb_lev, k_gg) */
+
+typedef struct {                      /* c2d_plasma_get: any pointer may be NULL */
+    double *f_nt, *Pnt;
+    double *n_e, *tea, *f_pair, *B_field, *gmin, *gmax, *p_nth, *amxwl;
+    double *Te_new;                   /* unclamped temperature of the last FP update (update2d.f:1441-1469) */
+    double *Eloss_sy, *ec_old;        /* this step's synchrotron loss (imcgen2d.f:280-283) and the census energy carried in (l.90-96) */
+} c2d_plasma_out;
+
+typedef struct {                      /* surface sources of a run: the boundary block of input.dat for the current time interval */
+    int star_switch;
+    double Rstar, dist_star;          /* imcgen2d.f:163-164 (star_switch = 1) */
+    double t0;                        /* t0(ti): file-fed rings switch on at time + dt/2 >= t0 (imcgen2d.f:127) */
+    const double *tbbi, *tbbo;        /* [nz] */
+    const double *tbbu, *tbbl;        /* [nr] */
+    const int32_t *spec_i, *spec_o, *spec_u, *spec_l;   /* spectrum table per ring (NULL = table 0) */
+    int n_spec, nfmax;
+    const int32_t *nfile;             /* [n_spec] */
+    const double *int_file;           /* [n_spec] integral of each table (file_sp, imcsurf2d_para.f:640-650) */
+    const double *E_file, *F_file, *P_file, *a1, *I_file;   /* [n_spec][nfmax] */
+} c2d_surf_run;
+
+typedef struct {                      /* run constants of input.dat the step needs (reader.f:157-597) */
+    int64_t nst;                      /* particles per photon cycle */
+    int T_const;                      /* 1: electron spectrum frozen, update is skipped (xec2d.f:87) */
+    int quirk_cycle0;                 /* 1: cycle 0 as the reference's MPI workers run it: dt = 0 and no energy groups,
+                                         every source photon is banked unflown at its birth point with bins 0 */
+    int inj_switch, inj_dis, g2var_switch, pick_sw, cf_sentinel;
+    double inj_g1, inj_g2, inj_p, inj_t, inj_gg, inj_sigma, inj_L, inj_v, pick_rate;
+    double r_esc, r_acc;
+    double r_flare, z_flare, t_flare, sigma_r, sigma_z, sigma_t, flare_amp;
+    const c2d_surf_run *surf;         /* NULL: no surface sources (the shipped input: every tbb = -0.d0) */
+} c2d_run;
+
+typedef struct {                      /* what the reference prints to log.txt / stdout for the cycle, summed over the ranks */
+    int ncycle;
+    double time, dt;
+    int64_t n_census_in;              /* census photons this RANK re-tracked */
+    int64_t n_volume, n_surface;      /* source photons of the cycle (all ranks) */
+    int64_t histories, ndxout, nevents, cmcount1, cmcount2;   /* all ranks */
+    double bingo, Emiss_tot, fbias;   /* imcgen2d.f:405-421 'Total ingoing energy', l.491-517 */
+    double luminosity;                /* E_add_up: sum(erlk*) / dt (update2d.f:2068) */
+    int fp_ran, fp_steps_min, fp_steps_max;
+    double E_tot_old, E_tot_new, dE_fraction, dT_max, dt_new, hr_total, hr_st_total;   /* update2d.f:206-243 */
+    double ms[12];                    /* CUDA-event ms per kernel family since timing was enabled (c2d_kernel_time_ms) */
+} c2d_step_report;
+
+int c2d_plasma_set(c2d_ctx *ctx, const c2d_plasma *p);
+int c2d_plasma_get(c2d_ctx *ctx, c2d_plasma_out *p);
+int c2d_step(c2d_ctx *ctx, const c2d_run *run, int ncycle, double time, double dt, c2d_step_report *report);
+        /* collective when c2d_comm_init was called with world > 1.  The host advances the clock as xec does
+           (xec2d.f:94-103): if ncycle > 0 then time += dt; ncycle += 1. */
 
 /* ---- COMMON <-> dense packing helpers (host code) ------------------------------------------- */
 void c2d_pack_bin_first(const double *common, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *dense);

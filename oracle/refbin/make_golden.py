@@ -55,6 +55,10 @@ CONFIGS = {
                               **{"t0(1)": "0.d0", "t1(1)": "1.d20"}),
                     zone=dict(n_e="0.300e06"), wi=dict(tbbl="0.5d0"),
                     extra=[("p_ref", (500, 500)), ("w_abs", (500, 500)), ("e_ref", (500,))]),
+    # BASELINE configs[0]: src_20121026/input.dat + inputm.dat AS SHIPPED (30 x 9 zones, nst = 8e5, split 1000/1000/300,
+    # pair_switch = 1, T_const = 0), cycles 0-2 (tstop = 1e3 as in SURVEY.md 8 "golden values").  ~20 min per pass on one
+    # core; only the first 2000 census records of each snapshot are kept, and the first 4000 event records.
+    "c0": dict(over=dict(tstop="1.e+3"), zone={}, ncens=2000, census_head=True, events_head=4000, keep_logs=True),
     # external-Compton seed photons (BASELINE configs[2]): upper and lower disk sources sampled from a spectrum
     # file (the only live surface-source path of the reference: nsurf* > 0 requires tbb* < 0, imcgen2d.f:441-442)
     "surface": dict(over=dict(nz=3, nr=4, nst=1200, tstop="1.e+3", **{"t0(1)": "0.d0", "t1(1)": "1.d20"}), zone={},
@@ -64,7 +68,7 @@ CONFIGS = {
 }
 
 # (name, dims-to-keep as function of (nz, nr, nmu)) -- None = scalar / full
-def varlist(nz, nr):
+def varlist(nz, nr, ncens=NCENS):
     Z = lambda *lead: (lambda: tuple(lead) + (nz, nr))
     v = [
         ("ndxout", None), ("nz", None), ("nr", None), ("ncycle", None), ("pair_switch", None),
@@ -75,7 +79,7 @@ def varlist(nz, nr):
         ("split1", None), ("split2", None), ("split3", None), ("spl3_trg", None),
         ("t_const", None), ("inj_switch", None), ("inj_dis", None), ("g2var_switch", None), ("pick_sw", None),
         ("cf_sentinel", None), ("nst", None),
-        ("ibufout", (6 * NCENS,)), ("dbufout", (6 * NCENS,)),
+        ("ibufout", (6 * ncens,)), ("dbufout", (6 * ncens,)),
         ("amxwl", (nz, nr)), ("gmin", (nz, nr)), ("gmax", (nz, nr)), ("p_nth", (nz, nr)),
         ("q_turb", (nz, nr)), ("turb_lev", (nz, nr)), ("ec_old", (nz, nr)),
         ("n_pos", (nz, nr, 200)), ("dn_pp", (nz, nr, 200)), ("dne_pa", (nz, nr, 200)), ("dnp_pa", (nz, nr, 200)),
@@ -166,7 +170,8 @@ def main(name):
     pts = snapshot_points(trace)
     print("snapshot points:", pts)
 
-    vl = varlist(nz, nr) + list(cfg.get("extra", []))
+    ncens = int(cfg.get("ncens", NCENS))
+    vl = varlist(nz, nr, ncens) + list(cfg.get("extra", []))
     spec = []
     layout = []
     for vname, keep in vl:
@@ -224,7 +229,9 @@ def main(name):
     # trim census dumps to the live count
     for idx, lab in pts:
         n = int(out[f"{lab}/ndxout"])
-        assert n <= NCENS, f"census {n} exceeds dump cap"
+        if cfg.get("census_head"):
+            n = min(n, ncens)                # big runs: only the head of the census is kept (the count is in ndxout)
+        assert n <= ncens, f"census {n} exceeds dump cap"
         out[f"{lab}/dbufout"] = out[f"{lab}/dbufout"][: 6 * n]
         out[f"{lab}/ibufout"] = out[f"{lab}/ibufout"][: 6 * n]
     # de-duplicate: a variable is stored under a label only if it differs from the value at
@@ -240,7 +247,20 @@ def main(name):
                 last[v] = out[k]
     # event file of the worker (text, 7 doubles per record; imcleak2d.f:181)
     ev = np.loadtxt(rd / "p001_evb.dat", ndmin=2) if evt1.strip() else np.zeros((0, 7))
+    if cfg.get("events_head"):
+        # big runs: head of the list + the sums the parity gates use (SURVEY.md 8 notes)
+        out["events_count"] = np.array(len(ev)); out["events_sum_ew"] = np.array(ev[:, 2].sum())
+        out["events_t_hist"] = np.histogram(ev[:, 0], bins=64)[0]; out["events_t_edges"] = np.histogram(ev[:, 0], bins=64)[1]
+        out["events_lnE_hist"], out["events_lnE_edges"] = np.histogram(np.log10(ev[:, 1]), bins=np.linspace(-10, 12, 89))
+        out["events_lnE_ew"] = np.histogram(np.log10(ev[:, 1]), bins=np.linspace(-10, 12, 89), weights=ev[:, 2])[0]
+        ev = ev[: cfg["events_head"]]
     out["events"] = ev
+    if cfg.get("keep_logs"):
+        # what the master wrote: log.txt (bingo, Luminosity, (Delta E)/E, dT_max), the light curve and temperature files
+        for fn in ("log.txt", "output/lcb_01.dat", "output/temp_b.dat", "output/spb.dat", "output/phb.dat", "stdout.txt"):
+            f = rd / fn
+            if f.exists():
+                out["file/" + fn] = np.array(f.read_text()[-200000:])
     # the worker's event file as the binary formatted it (format 105 of imcleak2d.f:181), first 600 records: pins the
     # e14.7 formatter of the library's reference-format writers (c2d_events_write / c2d_census_write)
     if name == "dense":

@@ -367,6 +367,101 @@ def test_degenerate_inputs(emu, tmp_path):
         gpu_step(g, P, 1, field=False)
     assert e.value.code == 5 and g.tallies()["counters"]["nevents"] > 5
     g.lc_begin(red)
-    g.lc_accumulate()                                        # bins the 5 records that were stored
-    assert g.lc_read()[2].sum() <= 5
+    with pytest.raises(C2dError) as e:                       # an incomplete list must not be binned silently
+        g.lc_accumulate()
+    assert e.value.code == 5 and g.lc_read()[2].sum() == 0
     g.close()
+    # a census record whose indices would become out-of-bounds device addresses is refused
+    g = make_gpu(P)
+    d = np.ones((2, 6)); i = np.array([[1, 1, 1, 1, 1, 7], [1, 1, 1, P["nz"] + 1, 1, 7]], np.int32)
+    with pytest.raises(C2dError) as e:
+        g.census_import(d, i)
+    assert e.value.code == 2 and "record 2" in str(e.value)
+    g.close()
+
+
+def test_closed_step_host_logic(emu):
+    """c2d_step on the resident plasma (emu build, T_const = 1: no FP kernel there) against the oracle running the same
+    phases in the reference's order for cycles 0-2, cycle 0 with the MPI build's quirk (dt = 0, no groups):
+    device-built tables (volume_em), budget, bank carry-over, ec_old / bingo bookkeeping, cumulative fout."""
+    from golden_util import Golden
+    from loop_util import compare_plasma, gpu_closed, gpu_cycle, initial_state, oracle_cycle
+    from parity_util import compare
+    o, st, P, scal = initial_state(Golden("small"))
+    scal = dict(scal, nst=1600)
+    g = gpu_closed(P, st, scal, T_const=1)
+    time, fout_total = 0.0, 0.0
+    for cyc in range(3):
+        ro = oracle_cycle(o, cyc, time, scal, T_const=1)
+        rg = gpu_cycle(g, scal["dt"])
+        assert rg["report"]["n_volume"] == int(ro["nsv"].sum()) and rg["report"]["n_census_in"] == ro["n_census_in"]
+        bad = compare(rg, ro, tol=1e-10, census_tol=1e-6)
+        assert not bad, (cyc, bad)
+        assert not compare_plasma(rg["plasma"], ro["plasma"], after_fp=False)
+        assert abs(rg["report"]["bingo"] / ro["report"]["bingo"] - 1) < 1e-12
+        assert abs(rg["report"]["luminosity"] - ro["report"]["luminosity"]) <= 1e-10 * max(ro["report"]["luminosity"], 1e-300)
+        fout_total = fout_total + ro["fout"]
+        assert np.allclose(rg["fout_total"], fout_total, rtol=1e-10, atol=0)
+        if cyc == 0:                                   # unflown, un-binned, one census photon per source photon
+            assert rg["counters"]["ndxout"] == int(ro["nsv"].sum()) and not rg["census"][1][:, :3].any()
+        if cyc > 0:
+            time += scal["dt"]
+    assert rg["counters"]["nevents"] > 10 and g.ncycle == 3 and abs(g.time - 2 * scal["dt"]) < 1e-9 * g.time
+    g.close()
+
+
+WORKER_STEP = r'''
+import os, sys
+sys.path[:0] = [r"{root}", r"{root}/tests", r"{root}/tests/emu", r"{root}/oracle"]
+import numpy as np, torch, torch.distributed as dist
+import build_emu
+from compton2d_b200 import lib as L
+L.LIBPATH = build_emu.build()
+from golden_util import Golden
+from loop_util import gpu_closed, initial_state
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+o, st, P, scal = initial_state(Golden("small"))
+scal = dict(scal, nst=1600)
+g = gpu_closed(P, st, scal, T_const=1, rank=rank, world=world)
+reps = []
+for cyc in range(3):
+    reps.append(g.step(scal["dt"]))
+t = g.tallies()
+sid = g.census()[2]
+gathered = [None] * world
+dist.all_gather_object(gathered, sid)
+if rank == 0:
+    np.savez(r"{out}", edep=t["edep"], ecens=t["ecens"], n_field=t["n_field"], fout_total=t["fout_total"], npcen=t["npcen"],
+             ndxout=reps[-1]["ndxout"], nevents=reps[-1]["nevents"], hist=reps[-1]["histories"], sid=np.sort(np.concatenate(gathered)),
+             local_ndxout=t["counters"]["ndxout"], global_ndxout=t["counters_global"]["ndxout"])
+dist.destroy_process_group()
+'''
+
+
+def test_closed_step_two_ranks_library_collectives(emu, tmp_path):
+    """world_size 2 over gloo with the collectives INSIDE the library (c2d_tally_reduce through the transport handed to
+    c2d_comm_init_ext; on the GPU the same calls go to NCCL): three closed steps on two ranks == on one rank."""
+    from golden_util import Golden
+    from loop_util import gpu_closed, initial_state
+    o, st, P, scal = initial_state(Golden("small"))
+    scal = dict(scal, nst=1600)
+    g = gpu_closed(P, st, scal, T_const=1)
+    for cyc in range(3):
+        rep = g.step(scal["dt"])
+    one = g.tallies()
+    sid1 = np.sort(g.census()[2])
+    g.close()
+    out = tmp_path / "two.npz"
+    script = tmp_path / "worker_step.py"
+    script.write_text(WORKER_STEP.format(root=str(ROOT), out=str(out)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29543")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29543", str(script)], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    two = np.load(out)
+    assert np.array_equal(two["npcen"], one["npcen"]) and int(two["ndxout"]) == rep["ndxout"] and int(two["nevents"]) == rep["nevents"]
+    assert int(two["hist"]) == rep["histories"] and np.array_equal(two["sid"], sid1)
+    assert int(two["global_ndxout"]) == rep["ndxout"] and 0 < int(two["local_ndxout"]) < rep["ndxout"]
+    for k in ("edep", "ecens", "n_field", "fout_total"):
+        assert np.abs(two[k] - one[k]).max() <= 1e-12 * np.abs(one[k]).max(), k
