@@ -221,10 +221,12 @@ int Ctx::sigma_setup()
     CU(cudaMemcpy(d_sig_M, M.data(), D * D * 8, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&d_sig_ms, (size_t)sig_nodes * 4));
     CU(cudaMemcpy(d_sig_ms, ms.data(), (size_t)sig_nodes * 4, cudaMemcpyHostToDevice));
-    const size_t n_step = (size_t)nzone * N * 3 + (size_t)nzone * sig_nodes * 2;
+    const size_t n_step = (size_t)nzone * N * 4 + (size_t)nzone * sig_nodes * 2 + (((size_t)nzone + 1) & ~size_t(1));
     CU(cudaMalloc(&d_sig_step, n_step * 8));
     d_sig_W = d_sig_step; d_sig_AB = d_sig_W + (size_t)nzone * N; d_sig_T = d_sig_AB + (size_t)nzone * N * 2;
     d_sig_coef = d_sig_T + (size_t)nzone * sig_nodes;
+    double *d_NB = d_sig_coef + (size_t)nzone * sig_nodes;
+    P.sig_NB = d_NB; P.sig_if = reinterpret_cast<const int *>(d_NB + (size_t)nzone * N);
     P.sig_coef = d_sig_coef; P.sig_AB = d_sig_AB; P.sig_W = d_sig_W; P.sig_lo = d_lo; P.sig_iw = d_iw;
     P.sig_nint = n_int; P.sig_nsub = nsub; P.sig_t0 = t0; P.sig_inv_h = 1.0 / h;
     launch_sigma_kn(P, d_xs, d_sig_ms, sig_nodes, d_sig_Kn, stream);
@@ -249,6 +251,27 @@ int Ctx::sigma_build()
     return 0;
 }
 
+}  // namespace c2d
+
+// k_history in chunks of at most qabs_cap histories (each queues at most one absorption-draw task), every chunk followed by
+// k_absdraw on the device-side count
+namespace c2d {
+int launch_history_chunks(Ctx *c, int src, int64_t first, int64_t count, int64_t stride)
+{
+    const int64_t chunk = std::min<int64_t>((int64_t)1 << 30, c->qabs_cap);
+    for (int64_t done = 0; done < count; done += chunk) {
+        const int64_t n = std::min(chunk, count - done);
+        c->timer_begin(0);
+        if (src == 0) launch_history_volume(c->P, first + done * stride, n, stride, c->stream);
+        else if (src == 1) launch_history_census(c->P, first + done * stride, n, stride, c->stream);
+        else launch_history_surface(c->P, first + done * stride, n, stride, c->stream);
+        launch_absdraw(c->P, c->d_qabs, c->d_qcount + 4, c->n_sm, c->stream);
+        c->timer_end();
+        CU(cudaGetLastError());
+        CU(cudaMemsetAsync(c->d_qcount + 4, 0, 16, c->stream));        // absorption-draw queue and literal pool
+    }
+    return 0;
+}
 }  // namespace c2d
 
 // ---- pieces of the step prologue shared by c2d_step_begin_gen (host arrays) and c2d_step (resident plasma state)
@@ -336,8 +359,11 @@ int begin_common(Ctx *c, int ncycle, double time, double dt)
 {
     CU(cudaMemsetAsync(c->d_f64, 0, c->n_f64 * 8, c->stream));
     CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
-    // census: last step's output bank becomes this step's input (no 360 MB copy as in imcfield2d.f:96-97)
-    c->cur_out ^= 1;
+    // census: last step's output bank becomes this step's input (no 360 MB copy as in imcfield2d.f:96-97) -- sorted by
+    // (zone, energy class) into the other bank on the way (c2d_bank.cu), in which case the roles stay as they are
+    const int sorted = bank_sort(c, c->n_census);
+    if (sorted < 0) return C2D_ECUDA;
+    if (!sorted) c->cur_out ^= 1;
     c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
     c->P.ncycle = ncycle; c->P.key1 = (uint32_t)ncycle; c->P.dt = dt; c->P.time = time;
     c->field_done = false; c->vol_next = 0; c->surf_open = false; c->surf_total = 0;
@@ -389,6 +415,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
+    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool);
     cudaFree(c->d_fout_total); cudaFree(c->d_cnt_global); cudaFree(c->d_plasma); cudaFree(c->d_fpx);
     comm_free(c);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
@@ -501,8 +528,15 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     CU(cudaMalloc(&c->d_events, (size_t)c->event_cap * 7 * 8));
     for (int b = 0; b < 2; b++) CU(cudaMalloc(&c->d_q[b], (size_t)c->q_cap * sizeof(CollTask)));
     CU(cudaMalloc(&c->d_q3, (size_t)c->q_cap * sizeof(CollTask)));
-    CU(cudaMalloc(&c->d_qcount, 32));
-    CU(cudaMemset(c->d_qcount, 0, 32));
+    CU(cudaMalloc(&c->d_qcount, 64));      // [0],[1] collision queues, [2] split3 queue, [3] hard list, [4] absorption-draw queue, [5] literal pool
+    CU(cudaMemset(c->d_qcount, 0, 64));
+    // absorption-draw queue: k_history is launched in chunks of at most qabs_cap histories, each of which queues at most one task
+    c->qabs_cap = std::min<int64_t>((int64_t)1 << 24, std::max<int64_t>((int64_t)1 << 16, c->census_cap));
+    if (const char *e = getenv("C2D_QABS_CAP")) c->qabs_cap = std::max<int64_t>(1024, atoll(e));
+    c->lit_cap = std::max<int64_t>((int64_t)1 << 22, (int64_t)64 * d->split1);
+    CU(cudaMalloc(&c->d_qabs, (size_t)c->qabs_cap * sizeof(AbsTask)));
+    CU(cudaMalloc(&c->d_litpool, (size_t)c->lit_cap * sizeof(int)));
+    if (const char *e = getenv("C2D_SORT_BANK")) c->sort_bank = atoi(e) != 0;
 
     Params &P = c->P;
     memset(&P, 0, sizeof P);
@@ -542,6 +576,8 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
     c->q_cur = 0;
     P.q_out = c->d_q[0]; P.q_out_count = c->d_qcount; P.q_cap = c->q_cap;
     P.q3 = c->d_q3; P.q3_count = c->d_qcount + 2;
+    P.qabs = c->d_qabs; P.qabs_count = c->d_qcount + 4; P.qabs_cap = (unsigned long long)c->qabs_cap;
+    P.lit_pool = c->d_litpool; P.lit_count = c->d_qcount + 5; P.lit_cap = (unsigned long long)c->lit_cap;
     c->n_census = 0;
 
     if (d->sigma_mode == 1) { int rc = c->sigma_setup(); if (rc) return rc; }
@@ -661,10 +697,7 @@ int c2d_imcfield(c2d_ctx *h)
     CU(cudaSetDevice(c->device));
     c->field_done = true; c->step_tracked = true;
     if (int rc = c->sigma_ensure()) return rc;
-    c->timer_begin(0);
-    launch_history_census(c->P, 0, c->n_census, 1, c->stream);
-    c->timer_end();
-    CU(cudaGetLastError());
+    if (int rc = launch_history_chunks(c, 1, 0, c->n_census, 1)) return rc;
     c->histories += c->n_census;
     c->n_census = 0;
     return drain_queue(c);
@@ -681,14 +714,7 @@ int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     if (count < 0 || count > avail) count = avail;
     c->step_tracked = true;
     if (int rc = c->sigma_ensure()) return rc;
-    const int64_t chunk = (int64_t)1 << 30;
-    for (int64_t done = 0; done < count; done += chunk) {
-        const int64_t n = std::min(chunk, count - done);
-        c->timer_begin(0);
-        launch_history_volume(c->P, first + done * stride, n, stride, c->stream);
-        c->timer_end();
-        CU(cudaGetLastError());
-    }
+    if (int rc = launch_history_chunks(c, 0, first, count, stride)) return rc;
     c->histories += count;
     return drain_queue(c);
 }
@@ -772,14 +798,7 @@ int c2d_imcsurf(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     if (count < 0 || count > avail) count = avail;
     c->step_tracked = true;
     if (int rc = c->sigma_ensure()) return rc;
-    const int64_t chunk = (int64_t)1 << 30;
-    for (int64_t done = 0; done < count; done += chunk) {
-        const int64_t n = std::min(chunk, count - done);
-        c->timer_begin(0);
-        launch_history_surface(c->P, first + done * stride, n, stride, c->stream);
-        c->timer_end();
-        CU(cudaGetLastError());
-    }
+    if (int rc = launch_history_chunks(c, 2, first, count, stride)) return rc;
     c->histories += count;
     return drain_queue(c);
 }

@@ -35,6 +35,8 @@ int gen_core(Ctx *c, double dt, int64_t nst, const double *d_B, const double *h_
              const double *h_zsurf, GenBudget &g);
 int budget_upload(Ctx *c, const GenBudget &g);
 int begin_common(Ctx *c, int ncycle, double time, double dt);
+int bank_sort(Ctx *c, long long n);    // -> 1 sorted into the other bank, 0 skipped, -1 error (c2d_bank.cu)
+int launch_history_chunks(Ctx *c, int src, int64_t first, int64_t count, int64_t stride);
 
 struct Ctx {
     int device = 0, n_sm = 0;
@@ -60,6 +62,12 @@ struct Ctx {
     int split3_rounds = 64;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS; measured 8..128)
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;
+    // census bank sort (c2d_bank.cu) and the absorption-draw queue of k_history (c2d_track.cu)
+    bool sort_bank = true;                 // C2D_SORT_BANK=0 keeps the bank in arrival order (A/B measurements)
+    unsigned long long *d_sortkeys = nullptr;
+    AbsTask *d_qabs = nullptr;
+    int *d_litpool = nullptr;
+    int64_t qabs_cap = 0, lit_cap = 0;
     // offsets (in doubles) into d_step / d_f64, (in int64) into d_i64
     size_t o_kappa = 0, o_epstot = 0, o_epsth = 0, o_fnt = 0, o_pnt = 0, o_ne = 0, o_fpair = 0, o_kgg = 0, o_tbbl = 0,
            o_ewsv = 0, o_elth = 0, o_eltot = 0, o_zsurf = 0, o_tea = 0, n_step = 0;

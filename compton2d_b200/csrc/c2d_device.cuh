@@ -76,6 +76,15 @@ struct Bank {                // census bank, SoA (commonblock.f:8,72 dbuf/ibuf r
 struct Seg {                 // one zone crossing of the collision-free ray of a history
     int zi;
     double sigsc, sigabs, L, trldb, dcen, ew, dele, rpre;
+    double att;              // exp(-sigabs L) (0 when sigabs L >= 100): the factor every weight on this ray is attenuated by
+};
+
+struct AbsTask {             // a history whose ray has sigabs L > 1e-5 in some crossing: its per-trial absorption-point draws
+    Photon p;                // (imctrk2d.f:451-459) are summed by k_absdraw, one warp per task
+    int nlit;                // literal trials (flown one by one, they make their own draws): indices at lit_pool[lit_off ...]
+    unsigned long long lit_off;
+    uint64_t S_trials;
+    double wtmin;
 };
 
 struct Params {
@@ -104,6 +113,8 @@ struct Params {
     const double *sig_AB;              // [nzone][num_nt][2] prefix sums of the Thomson-branch bins
     const double *sig_W;               // [nzone][num_nt] f_nt * dgamma
     const double *sig_lo, *sig_iw;     // [sig_nint] interval lower bound in ln(x) and 2 / width
+    const double *sig_NB;              // [nzone][num_nt] suffix sums bounding the rounding-noise terms of bins >= i (sig_noise_zone)
+    const int *sig_if;                 // [nzone] first bin with f_nt > 0
     int sig_nint, sig_nsub; double sig_t0, sig_inv_h;
     // tallies
     double *edep, *prdep, *ecens, *n_field, *n_ph, *E_IC, *fout, *edout, *erlki, *erlko, *erlku, *erlkl,
@@ -119,7 +130,24 @@ struct Params {
     CollTask *q3;                      // children that triggered the 3rd split (imctrk2d.f:639)
     unsigned long long *q3_count;
     unsigned long long q_cap;
+    AbsTask *qabs;                     // histories waiting for k_absdraw
+    unsigned long long *qabs_count, qabs_cap;
+    int *lit_pool;                     // trial indices of the literal trials of queued histories
+    unsigned long long *lit_count, lit_cap;
 };
+
+constexpr int kSortE = 8;              // energy classes of the bank's sort key
+// energy class of a census photon: roughly one per decade of photon energy below ~1 keV (three binary orders each) -- the
+// Thomson-branch count m(x) of comtot, and with it the length of the sigma table's noise loop, is a function of log x
+__device__ __forceinline__ int sort_class(double xnu)
+{
+    int e2;
+    (void)frexp(xnu, &e2);
+    int c = (1 - e2) / 3;
+    if (c < 0) c = 0;
+    if (c > kSortE - 1) c = kSortE - 1;
+    return c;
+}
 
 // ------------------------------------------------------------------------------------------ warp
 // The kernels are written against a warp of kWarp lanes.  On the GPU kWarp = 32; the g++ debug build of
@@ -589,11 +617,71 @@ __device__ __forceinline__ void comtot_table_zones(const Params &p, const SigCtx
     comtot_table_finish(p, c, zi, nzn, ee, comac);
 }
 
+// One zone, with the noise sum cut where it no longer matters.  The rounding-noise term of bin i is bounded by
+//   (1.2e-16 / x) (1.125 cb_i + 9 pref_i / a1_i) W[z][i]      (|e| <= 2^-53; b side (1 + y/8) <= 1.125; a side (9 + y + 8/y) <= 9/y, y < 0.1)
+// and NB[z][i] holds the suffix sum of those bounds over the bins >= i (k_sigma_prefix).  The electron spectra fall off
+// steeply, so the tail of the loop contributes < 1e-13 of the value long before the last bin: checked every 8 bins.
+__device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCtx &c, int z)
+{
+    const double sigthom = 6.6516e-25;
+    const int N = p.num_nt;
+    const double *ab = p.sig_AB + ((size_t)z * N + c.m) * 2;
+    double v = sigthom * (c2d_ldg(ab) - 2.0 * c.x * c2d_ldg(ab + 1));
+    if (c.j >= 0) {
+        const double *kk = p.sig_coef + ((size_t)z * p.sig_nint + c.j) * 8;
+        const double s2 = c.s + c.s;
+        double b1 = c2d_ldg(kk + 7), b2 = 0.0, b0;
+#pragma unroll
+        for (int q = 6; q >= 1; q--) { b0 = fma(s2, b1, c2d_ldg(kk + q)) - b2; b2 = b1; b1 = b0; }
+        v = v + (fma(c.s, b1, c2d_ldg(kk)) - b2);
+        // noise: sum_{i >= m} noise_i(x) W[z][i]
+        const double x = c.x, inv_x = 1.0 / x;
+        const double *w = p.sig_W + (size_t)z * N, *nb = p.sig_NB + (size_t)z * N;
+        const double thr = fabs(v) * (x * x * x) * 8.0e2;          // bound * 1.2e-16 / x^3 <= 1e-13 |v|
+        int i = c.m;
+        const int ifz = p.sig_if[z];
+        if (i < ifz) i = ifz;
+        double e0 = 0.0;
+        if (i < N - 1 && c2d_ldg(nb + i) > thr) {
+            int ia, ib;
+            {   // ia = first bin with a1_i x >= 0.1 ; ib = first bin with a2_i x < 1e-3
+                int lo = c.m, hi = N - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a1[mid] * x < 0.1) lo = mid + 1; else hi = mid; }
+                ia = lo;
+                lo = c.m; hi = N - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a2[mid] * x < 1.e-3) hi = mid; else lo = mid + 1; }
+                ib = lo;
+            }
+            const int i_fast = (ia > ib) ? ia : ib;
+            for (; i < i_fast && i < N - 1; i++) {               // the full expressions (few bins)
+                const double yb = p.kn_a2[i] * x;
+                double q;
+                if (i >= ib) {
+                    const double s = 1.0 + yb, e = (s - 1.0) - yb;
+                    q = -(p.kn_cb[i] * inv_x) * (e * fma(0.125, yb, 1.0));
+                } else q = -(p.kn_pref[i] * kn_eta(yb));
+                if (i < ia) q = q + p.kn_pref[i] * kn_eta(p.kn_a1[i] * x);
+                e0 = fma(q, w[i], e0);
+            }
+            const double *a2 = p.kn_a2, *cb = p.kn_cb;
+            for (; i < N - 1; i++) {                              // b side only, division-free, branch-free
+                if ((i & 7) == 0 && !(c2d_ldg(nb + i) > thr)) break;
+                const double yb = c2d_ldg(a2 + i) * x;
+                const double s = 1.0 + yb, e = (s - 1.0) - yb;
+                const double q = -(c2d_ldg(cb + i) * inv_x) * (e * fma(0.125, yb, 1.0));
+                e0 = fma(q, c2d_ldg(w + i), e0);
+            }
+        }
+        v = v + e0 * (inv_x * inv_x);
+    }
+    return (v < 1.e-40) ? 1.e-40 : p.n_e[z] * v;
+}
+
 // comtot for one zone by one thread (scat_flag = 1 flights; `c` was set up by flight_begin when sigma_mode = 1)
 __device__ __forceinline__ double comtot_one(const Params &p, int zi, double xnu, const SigCtx &c)
 {
     double r;
-    if (p.sigma_mode == 1 && c.j != -2) comtot_table_zones(p, c, &zi, 1, &r);
+    if (p.sigma_mode == 1 && c.j != -2) r = comtot_table_zone(p, c, zi);
     else comtot_zones(p, xnu, &zi, 1, &r);
     return r;
 }
@@ -827,12 +915,16 @@ __device__ __forceinline__ int imcleak(const Params &p, Photon &P, Rng &rng)
     return 1;
 }
 
-// census append: imctrk2d.f:541-586
-__device__ __forceinline__ bool census_write(const Params &p, const Photon &P, Rng &rng)
+// census append: imctrk2d.f:541-586, in two halves so that the history kernel can commit the per-zone half (npcen, ecens)
+// through its warp / block tally hierarchy
+__device__ __forceinline__ void census_zone_tally(const Params &p, int zi, double ew)
+{
+    atomicAdd(p.npcen + zi, 1ull);
+    atomic_add_f64(p.ecens + zi, ew);
+}
+__device__ __forceinline__ bool census_record(const Params &p, const Photon &P, Rng &rng)
 {
     const int zi = (P.jph - 1) * p.nr + (P.kph - 1);
-    atomicAdd(p.npcen + zi, 1ull);
-    atomic_add_f64(p.ecens + zi, P.ew);
     if (p.pair_switch == 1) {
         int i_gg;
         for (i_gg = 1; i_gg <= p.n_gg; i_gg++)
@@ -859,6 +951,11 @@ __device__ __forceinline__ bool census_write(const Params &p, const Photon &P, R
     p.out.sid[n] = rng.sid;
     p.out.seed[n] = (int)(rng.next(p) * 1.e5);
     return true;
+}
+__device__ __forceinline__ bool census_write(const Params &p, const Photon &P, Rng &rng)
+{
+    census_zone_tally(p, (P.jph - 1) * p.nr + (P.kph - 1), P.ew);
+    return census_record(p, P, rng);
 }
 
 // ------------------------------------------------------------------------------------------ the flight
@@ -966,7 +1063,8 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
     }
     if (sigabs < 1.e-40) sigabs = 1.e-40;
     const double xabs = sigabs * trld;
-    const double ewnew = (xabs < 100.) ? P.ew * exp(-xabs) : 0.;
+    const double att = (xabs < 100.) ? exp(-xabs) : 0.;
+    const double ewnew = (xabs < 100.) ? P.ew * att : 0.;
     double deleabs;
     if (P.xnu > 47.0 && sigabs > 1.e-40 && p.pair_switch == 1) deleabs = (P.ew - ewnew) * (sigabs - kgg_i) / sigabs;
     else deleabs = P.ew - ewnew;
@@ -976,6 +1074,7 @@ __device__ __forceinline__ int fly_step(const Params &p, Photon &P, Rng &rng, do
         Seg &g = segs[s];
         g.zi = zi; g.sigabs = sigabs; g.L = trld; g.trldb = trldb_rec; g.dcen = P.dcen; g.ew = P.ew;
         g.dele = deleabs; g.rpre = P.rpre; g.sigsc = pair_enhance;    // sigsc := comac * pair_enhance later
+        g.att = att;
         nseg = s + 1;
     } else {
         double wmustar = P.wmu;

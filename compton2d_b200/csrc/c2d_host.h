@@ -7,6 +7,7 @@ namespace c2d {
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
+void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
 void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st);
 void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st);

@@ -29,7 +29,7 @@ __global__ void k_sigma_kn(const __grid_constant__ Params p, const double *xs, c
     Kn[idx] = (i >= ms[node]) ? sigma_kn_smooth(p, i, xs[node]) : 0.0;
 }
 
-__global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, double *AB)
+__global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, double *AB, double *NB, int *IF)
 {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nzone) return;
@@ -47,6 +47,18 @@ __global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, doub
     double *ab = AB + ((size_t)z * N + (N - 1)) * 2;
     ab[0] = A; ab[1] = B;
     W[(size_t)z * N + (N - 1)] = 0.0;
+    // bounds of the rounding-noise terms (comtot_table_zone): suffix sums of (1.125 cb_i + 9 pref_i / a1_i) |W_i|, and the
+    // first bin that holds electrons
+    double nb = 0.0;
+    int first = N - 1;
+    NB[(size_t)z * N + (N - 1)] = 0.0;
+    for (int i = N - 2; i >= 0; i--) {
+        const double w = fabs(W[(size_t)z * N + i]);
+        nb = nb + (1.125 * p.kn_cb[i] + 9.0 * p.kn_pref[i] / p.kn_a1[i]) * w;
+        NB[(size_t)z * N + i] = nb;
+        if (w > 0.0) first = i;
+    }
+    IF[z] = first;
 }
 
 constexpr int kSigZG = 4;           // zones per thread of k_sigma_nodes
@@ -107,7 +119,7 @@ void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nod
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
                         double *coef, cudaStream_t st)
 {
-    k_sigma_prefix<<<(p.nzone + 63) / 64, 64, 0, st>>>(p, W, AB);
+    k_sigma_prefix<<<(p.nzone + 63) / 64, 64, 0, st>>>(p, W, AB, const_cast<double *>(p.sig_NB), const_cast<int *>(p.sig_if));
     const long long n = (long long)n_nodes * ((p.nzone + kSigZG - 1) / kSigZG);
     k_sigma_nodes<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, W, Kn, n_nodes, T);
     const long long ni = (long long)p.nzone * (n_nodes / kSigDeg);

@@ -21,39 +21,115 @@ __device__ __forceinline__ void push_collision(const Params &p, const Photon &P,
     t.p = P; t.pad = 0; t.sid = sid;
 }
 
-// exact replay of the collision decision of imctrk2d.f:214-227,370 along the recorded ray
-__device__ __forceinline__ bool trial_collides(const Seg *segs, int nseg, double colmfp)
+// ------------------------------------------------------------------------------------------ tally hierarchy
+// The per-zone tallies of a history (edep, prdep per crossing; npcen, ecens at census) go warp -> block -> HBM: when the lanes
+// of a warp agree on the zone (the census bank is kept sorted by zone, so they usually do) their contributions are summed
+// with shuffles and lane 0 adds the sum to the block's shared-memory slot of that zone; each slot is committed to HBM with one
+// atomic per tally at block end.  Lanes that disagree, and zones that find no free slot, fall back to global atomics.
+constexpr int kTallySlots = 16;
+struct BlockTally {
+    int key[kTallySlots];                                // zone, -1 = free
+    double dep_e[kTallySlots], dep_p[kTallySlots];       // edep, prdep
+    double cen_e[kTallySlots];                           // ecens
+    unsigned cen_n[kTallySlots];                         // npcen
+};
+#ifndef C2D_EMU
+__device__ __forceinline__ void bt_init(BlockTally &bt)
 {
-    for (int s = 0; s < nseg; s++) {
-        const double dcol = colmfp / segs[s].sigsc;
-        if (!(segs[s].dcen <= dcol) && !(segs[s].trldb < dcol)) return true;
-        colmfp = colmfp - segs[s].sigsc * segs[s].L;
+    if (threadIdx.x < kTallySlots) {
+        bt.key[threadIdx.x] = -1; bt.dep_e[threadIdx.x] = 0.0; bt.dep_p[threadIdx.x] = 0.0; bt.cen_e[threadIdx.x] = 0.0; bt.cen_n[threadIdx.x] = 0u;
     }
-    return false;
+    __syncthreads();
+}
+__device__ __forceinline__ int bt_slot(BlockTally &bt, int z)
+{
+    int s = z & (kTallySlots - 1);
+#pragma unroll 1
+    for (int k = 0; k < kTallySlots; k++) {
+        const int old = atomicCAS(&bt.key[s], -1, z);
+        if (old == -1 || old == z) return s;
+        s = (s + 1) & (kTallySlots - 1);
+    }
+    return -1;
+}
+__device__ __forceinline__ void bt_flush(const Params &p, BlockTally &bt)
+{
+    __syncthreads();
+    if (threadIdx.x < kTallySlots && bt.key[threadIdx.x] >= 0) {
+        const int z = bt.key[threadIdx.x], s = threadIdx.x;
+        if (bt.dep_e[s] != 0.0) atomic_add_f64(p.edep + z, bt.dep_e[s]);
+        if (bt.dep_p[s] != 0.0) atomic_add_f64(p.prdep + z, bt.dep_p[s]);
+        if (bt.cen_n[s]) { atomicAdd(p.npcen + z, (unsigned long long)bt.cen_n[s]); atomic_add_f64(p.ecens + z, bt.cen_e[s]); }
+    }
+}
+#endif
+// every lane of the warp calls; lanes with valid = false contribute nothing
+__device__ __forceinline__ void tally_dep(const Params &p, BlockTally *bt, bool valid, int z, double a, double b)
+{
+#ifndef C2D_EMU
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (!m) return;
+    const int z0 = __shfl_sync(0xffffffffu, z, __ffs(m) - 1);
+    if (bt && __all_sync(0xffffffffu, !valid || z == z0)) {
+        a = warp_sum(valid ? a : 0.0); b = warp_sum(valid ? b : 0.0);
+        if (lane_id() == 0) {
+            const int s = bt_slot(*bt, z0);
+            if (s >= 0) { atomicAdd(&bt->dep_e[s], a); atomicAdd(&bt->dep_p[s], b); }
+            else { atomic_add_f64(p.edep + z0, a); atomic_add_f64(p.prdep + z0, b); }
+        }
+        return;
+    }
+#else
+    (void)bt;
+#endif
+    if (valid) { atomic_add_f64(p.edep + z, a); atomic_add_f64(p.prdep + z, b); }
+}
+__device__ __forceinline__ void tally_census_zone(const Params &p, BlockTally *bt, bool valid, int z, double ew)
+{
+#ifndef C2D_EMU
+    const unsigned m = __ballot_sync(0xffffffffu, valid);
+    if (!m) return;
+    const int z0 = __shfl_sync(0xffffffffu, z, __ffs(m) - 1);
+    if (bt && __all_sync(0xffffffffu, !valid || z == z0)) {
+        ew = warp_sum(valid ? ew : 0.0);
+        if (lane_id() == 0) {
+            const int s = bt_slot(*bt, z0);
+            if (s >= 0) { atomicAdd(&bt->cen_e[s], ew); atomicAdd(&bt->cen_n[s], (unsigned)__popc(m)); }
+            else { atomicAdd(p.npcen + z0, (unsigned long long)__popc(m)); atomic_add_f64(p.ecens + z0, ew); }
+        }
+        return;
+    }
+#else
+    (void)bt;
+#endif
+    if (valid) census_zone_tally(p, z, ew);
 }
 
-// one trial flight executed literally (imctrk2d.f:126-695 body for scat_flag = -1)
-static __device__ __noinline__ int literal_trial(const Params &p, const Photon &T0, uint64_t S_trials, int t, double u,
-                                          double wtmin, Seg *segs, int nseg)
+// ------------------------------------------------------------------------------------------ rare paths of a history
+// A trial flight that may collide is flown literally (imctrk2d.f:126-695 body for scat_flag = -1) with comtot evaluated per
+// crossing (the same values as the per-history cache comac_ar of l.175-183).  It makes its own deposits, so the share the
+// history deposited for it as one of the `split1` identical collision-free trials is taken back first.
+static __device__ __noinline__ int literal_trial(const Params &p, const Photon &T0, uint64_t S_trials, int t, double u, double wtmin)
 {
-    Rng rng; rng.stream(mix64(S_trials, (uint64_t)(t + 1)));
-    Photon P = T0;
-    int ns = nseg;
-    count(p, CNT_LITERAL);
-    const int end = fly<MODE_TRIAL>(p, P, rng, wtmin, -log(u), segs, ns, S_trials, (uint32_t)t);
-    if (end == END_COLLISION) {
-        count(p, CNT_CMCOUNT1);
-        push_collision(p, P, rng.sid);
-        return 1;
+    {   // take back one trial's share of the collision-free ray's absorption (what step D below deposited for it)
+        Photon Q = T0;
+        Rng dummy; dummy.stream(0);
+        FlightCtx c;
+        flight_begin(p, Q.xnu, c);
+        double wmu_c = T0.wmu;
+        if (wmu_c > 1.0) wmu_c = 1.0;
+        if (wmu_c < -1.0) wmu_c = -1.0;
+        for (;;) {
+            if (Q.ew < 1.e-40) break;
+            if (Q.wmu > 1.0) Q.wmu = 1.0;
+            if (Q.wmu < -1.0) Q.wmu = -1.0;
+            Seg g; int s = 0, ns = 0; double colmfp = 0.0;
+            const int r = fly_step<MODE_PRE>(p, Q, dummy, wtmin, colmfp, 0.0, c, &g, s, ns);
+            atomic_add_f64(p.edep + g.zi, -g.dele);
+            if (g.sigabs * g.L <= .00001) atomic_add_f64(p.prdep + g.zi, -(g.dele * wmu_c * kCLight));
+            if (r != STEP_CONT) break;
+        }
     }
-    return 0;
-}
-
-// slow path for rays that cross more than kMaxSeg zones: the trial is flown with comtot evaluated
-// per crossing (same values as the per-history cache, imctrk2d.f:175-183)
-static __device__ __noinline__ int literal_trial_slow(const Params &p, const Photon &T0, uint64_t S_trials, int t, double u,
-                                               double wtmin)
-{
     Rng rng; rng.stream(mix64(S_trials, (uint64_t)(t + 1)));
     Photon P = T0;
     int ns = 0;
@@ -67,116 +143,113 @@ static __device__ __noinline__ int literal_trial_slow(const Params &p, const Pho
     return 0;
 }
 
-// One top-level history = one imctrk2d(-1) call.  Every lane of the warp runs this function (inactive lanes
-// carry `active = false`) because step B evaluates comtot warp-cooperatively.
-__device__ __forceinline__ void history(const Params &p, bool active, const Photon &P0, uint64_t S_entry)
+// One top-level history = one imctrk2d(-1) call.  Every lane of the warp runs this function (inactive lanes carry
+// `active = false`): the crossing loop is warp-uniform so that comtot (sigma_mode 0) and the tallies can cooperate.
+//
+// The ray of the split1 trial flights is traced ONCE and nothing of it is stored: per crossing the scattering opacity is
+// looked up, the ray's optical depth accumulated, the absorption of all split1 trials deposited, and the weight of the
+// recombined scat_flag = 0 flight attenuated alongside.  What needs the ray again is rare and re-traces it: a trial that may
+// collide (literal_trial), the absorption-point draws of rays with sigabs L > 1e-5 (k_absdraw, queued), a recombined flight
+// that outlives the trial ray or follows collisions.
+__device__ __forceinline__ void history(const Params &p, bool active, const Photon &P0, uint64_t S_entry, BlockTally *bt)
 {
     const double wtmin = 1.e-10 * P0.ew;                          // imctrk2d.f:82,92
     Photon T0 = P0;
     T0.ew = P0.ew / p.split1;                                     // l.110
     const uint64_t S_trials = mix64(S_entry, kTagTrials);
     const bool hist_active = active;
-
-    // A: the collision-free ray
-    Seg segs[kMaxSeg];
-    int nseg = 0, nscat = 0, nlit = 0;
-    bool overflow = false;
-    Photon Q = T0;                                                // end point of the collision-free ray
-    int endA = END_LOWEW;
-    if (active) {
-        Rng dummy; dummy.stream(0);
-        endA = fly<MODE_PRE>(p, Q, dummy, wtmin, 0.0, segs, nseg);
-        overflow = (endA == END_OVERFLOW);
-        if (endA == END_LOWEW && nseg == 0) active = false;   // ew < 1e-40 at entry: nothing is tallied (l.161)
-    }
-    if (active && overflow) {
-        count(p, CNT_SEGOVF);
-        TrialGen tg; tg.init(p, S_trials);
-        for (int t = 0; t < p.split1; t++)
-            nscat += literal_trial_slow(p, T0, S_trials, t, tg.uniform(p, (uint32_t)t), wtmin);
-    }
-    const bool overflow_counted = active && overflow;
-    const bool fast = active && !overflow;
-    // B: sigma_sc per crossing (comac_ar cache of l.175-183: one comtot per zone and history)
-    if (p.sigma_mode == 1) {
-        // table look-up per thread.  (Serving one lane's photon at a time with the bins spread over the warp, as the
-        // bin-by-bin mode below does, was measured 1.7x slower here: the noise term is too cheap to pay for the
-        // broadcasts and butterfly sums.)
-        if (fast) {
-            SigCtx sc;
-            sig_begin(p, T0.xnu, sc);
-            unsigned have = 0u;
-            for (;;) {
-                int zl[4] = {0, 0, 0, 0}, nzn = 0;
-                for (int s = 0; s < nseg && nzn < 4; s++) {
-                    if (have & (1u << s)) continue;
-                    bool seen = false;
-                    for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
-                    if (!seen) zl[nzn++] = segs[s].zi;
-                }
-                if (nzn == 0) break;
-                double cm[4];
-                if (sc.j != -2) comtot_table_zones(p, sc, zl, nzn, cm);
-                else comtot_zones(p, T0.xnu, zl, nzn, cm);             // beyond the table: bin by bin
-                for (int s = 0; s < nseg; s++) {
-                    if (have & (1u << s)) continue;
-                    for (int m = 0; m < nzn; m++)
-                        if (zl[m] == segs[s].zi) { segs[s].sigsc = 1.0 * cm[m] * segs[s].sigsc; have |= (1u << s); break; }
-                }
-            }
-        }
-    } else {
-        unsigned have = fast ? 0u : 0xffffffffu;
-        for (;;) {
-            // up to four not-yet-evaluated distinct zones of this lane's ray
-            int zl[4] = {0, 0, 0, 0}, nzn = 0;
-            for (int s = 0; s < nseg && nzn < 4; s++) {
-                if (have & (1u << s)) continue;
-                bool seen = false;
-                for (int m = 0; m < nzn; m++) seen |= (zl[m] == segs[s].zi);
-                if (!seen) zl[nzn++] = segs[s].zi;
-            }
-            double cm[4] = {0, 0, 0, 0};
-#ifndef C2D_EMU
-            unsigned todo = __ballot_sync(0xffffffffu, nzn > 0);
-            if (!todo) break;
-            while (todo) {                                         // the warp serves one lane's photon at a time
-                const int src = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const double xs = __shfl_sync(0xffffffffu, T0.xnu, src);
-                const int a0 = __shfl_sync(0xffffffffu, zl[0], src), a1 = __shfl_sync(0xffffffffu, zl[1], src);
-                const int a2 = __shfl_sync(0xffffffffu, zl[2], src), a3 = __shfl_sync(0xffffffffu, zl[3], src);
-                const int an = __shfl_sync(0xffffffffu, nzn, src);
-                double r[4];
-                comtot_zones_warp(p, xs, a0, a1, a2, a3, an, r);
-                if ((int)(threadIdx.x & 31) == src) { cm[0] = r[0]; cm[1] = r[1]; cm[2] = r[2]; cm[3] = r[3]; }
-            }
-#else
-            if (nzn == 0) break;
-            comtot_zones(p, T0.xnu, zl, nzn, cm);
-#endif
-            for (int s = 0; s < nseg; s++) {
-                if (have & (1u << s)) continue;
-                for (int m = 0; m < nzn; m++)
-                    if (zl[m] == segs[s].zi) { segs[s].sigsc = 1.0 * cm[m] * segs[s].sigsc; have |= (1u << s); break; }
-            }
-        }
-    }
-    // C: the split1 trial draws (l.126-156).  A trial collides only if -ln(u) is within the ray's
-    // scattering depth, i.e. u >= thr; everything below thr provably does not (margins >> rounding).
-    bool has_rand = false;
-    uint64_t Kthr = 0;
-    int lit_t[4] = {-1, -1, -1, -1};
     double wmu_c = T0.wmu;
     if (wmu_c > 1.0) wmu_c = 1.0;
     if (wmu_c < -1.0) wmu_c = -1.0;
-    if (fast) {
-        double tau = 0.0;
-        for (int s = 0; s < nseg; s++) { tau += segs[s].sigsc * segs[s].L; has_rand |= !(segs[s].sigabs * segs[s].L <= .00001); }
+    const double n_all = (double)p.split1;
+
+    // A + B + D + E in one pass over the crossings
+    Photon Q = T0;                                                // runs along the collision-free ray with a trial's weight
+    int endA = END_LOWEW, nseg = 0;
+    double tau = 0.0;
+    bool has_rand = false;
+    // the recombined flight (l.698-712) carries split1 trial weights unless trials collide (then it is flown literally below)
+    double F_ew = n_all * T0.ew;
+    const double wt0 = 1.e-10 * F_ew;
+    uint32_t F_d = 0;
+    int F_state = 0;                                              // 0 alive, 1 dropped silently (ew < 1e-40), 2 killed
+    SigCtx sc; sc.j = -2;
+    FlightCtx fc;
+    if (active) {
+        flight_begin(p, T0.xnu, fc);
+        if (p.sigma_mode == 1) sig_begin(p, T0.xnu, sc);
+    }
+    int last_z = -1;
+    double last_c = 0.0;
+    bool go = active;
+    while (warp_ballot(go)) {
+        Seg g;
+        g.zi = 0; g.dele = 0.0; g.sigabs = 0.0; g.L = 0.0; g.sigsc = 1.0; g.att = 1.0;
+        int r = STEP_CONT;
+        bool have = false;
+        if (go) {
+            if (Q.ew < 1.e-40) { endA = END_LOWEW; go = false; }   // l.161
+            else {
+                if (Q.wmu > 1.0) Q.wmu = 1.0;
+                if (Q.wmu < -1.0) Q.wmu = -1.0;
+                Rng dummy; dummy.stream(0);
+                int s = 0, ns = 0; double colmfp = 0.0;
+                r = fly_step<MODE_PRE>(p, Q, dummy, wtmin, colmfp, 0.0, fc, &g, s, ns);
+                have = true; nseg++;
+            }
+        }
+        // B: comtot of this crossing's zone (comac_ar of l.175-183: one value per zone and history)
+        double comac = last_c;
+        const bool need = have && g.zi != last_z;
+        if (p.sigma_mode == 1) {
+            if (need) comac = (sc.j != -2) ? comtot_table_zone(p, sc, g.zi) : comtot_one(p, g.zi, T0.xnu, sc);
+        } else {
+            unsigned todo = warp_ballot(need);
+            while (todo) {                                         // the warp serves one lane's photon at a time
+                const int src = first_lane(todo);
+                todo &= todo - 1;
+                const double xs = warp_shfl(T0.xnu, src);
+                const int zs = warp_shfl(g.zi, src);
+                const double v = comtot_zone_warp(p, xs, zs);
+                if (lane_id() == src) comac = v;
+            }
+        }
+        if (need) { last_z = g.zi; last_c = comac; }
+        double d_e = 0.0, d_p = 0.0;
+        if (have) {
+            const double sigsc = 1.0 * comac * g.sigsc;
+            tau += sigsc * g.L;
+            const double xabs = g.sigabs * g.L;
+            const bool rnd = !(xabs <= .00001);
+            has_rand |= rnd;
+            // D: absorption of the split1 trials in this crossing (l.465-466); the prdep of a crossing with absorption-point
+            // draws comes from k_absdraw
+            d_e = n_all * g.dele;
+            d_p = rnd ? 0.0 : n_all * (g.dele * wmu_c * kCLight);
+            // E: the recombined flight's weight through the same crossing
+            if (F_state == 0) {
+                if (F_ew < 1.e-40) F_state = 1;
+                else {
+                    const double ewnew = (xabs < 100.) ? F_ew * g.att : 0.;
+                    if (rnd) F_d++;                               // the absorption-point draw is consumed, its value unused
+                    if (ewnew <= wt0) F_state = 2; else F_ew = ewnew;
+                }
+            }
+            if (r != STEP_CONT) { endA = r; go = false; }
+        }
+        tally_dep(p, bt, have, g.zi, d_e, d_p);
+    }
+    if (active && endA == END_LOWEW && nseg == 0) active = false; // ew < 1e-40 at entry: nothing is tallied (l.161)
+
+    // C: the split1 trial draws (l.126-156).  A trial collides only if -ln(u) is within the ray's scattering depth, i.e.
+    // u >= thr; everything below thr provably does not (margins >> rounding).  Whatever reaches thr is flown literally.
+    int nscat = 0, nlit = 0;
+    unsigned long long lit_off = 0;
+    if (active) {
         const double thr = exp(-tau * (1.0 + 1.e-12)) * (1.0 - 1.e-12);
         // u = (K + 0.5) 2^-52 >= thr  <=>  K >= ceil(thr 2^52 - 0.5): the filter runs on integers
         const double tk = thr * 4503599627370496.0 - 0.5;
-        Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
+        const uint64_t Kthr = (tk <= 0.0) ? 0ull : (uint64_t)ceil(tk);
         // K = coarse8 << 44 | fine44 (TrialGen): a trial whose coarse byte is below the threshold's cannot collide.
         // Thin ray (threshold byte 0xFF): only the candidates are visited, ~split1/256 of them; otherwise every trial.
         const uint32_t Cthr = (uint32_t)(Kthr >> 44);
@@ -184,10 +257,12 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
             const uint64_t K = ((uint64_t)coarse << 44) | trial_fine44(p, S_trials, (uint32_t)t);
             if (K < Kthr) return;
             const double u = ((double)K + 0.5) * (1.0 / 4503599627370496.0);
-            if (!trial_collides(segs, nseg, -log(u))) return;
-            if (nlit < 4) lit_t[nlit] = t;
+            if (has_rand) {                                        // k_absdraw must leave this trial's draws to its literal flight
+                if (nlit == 0) lit_off = atomicAdd(p.lit_count, (unsigned long long)p.split1);
+                if (lit_off + (unsigned long long)nlit < p.lit_cap) p.lit_pool[lit_off + nlit] = t; else count(p, CNT_FATAL);
+            }
             nlit++;
-            nscat += literal_trial(p, T0, S_trials, t, u, wtmin, segs, nseg);
+            nscat += literal_trial(p, T0, S_trials, t, u, wtmin);
         };
         if (Cthr <= 0xFFu) {                                      // 0x100: tau = 0, nothing can collide
             TrialGen tg; tg.init(p, S_trials);
@@ -200,121 +275,57 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
                 }
             }
         }
-    }
-    // C': absorption-point draws of l.451-459 for the non-colliding trials of a ray with sigabs L > 1e-5 in some
-    // crossing (they only move prdep): one uniform per (trial, absorbing crossing) from the trial's stream.  The
-    // warp serves one such lane at a time with its split1 trials spread over the lanes.
-    double pr_acc[kMaxSeg];
-    {
-        const bool coop = fast && has_rand && nlit <= 4;
-        if (fast && has_rand && !coop) {                          // many collisions: the owner lane walks its trials
-            for (int s = 0; s < nseg; s++) pr_acc[s] = 0.0;
-            TrialGen tg; tg.init(p, S_trials);
-            for (int t = 0; t < p.split1; t++) {
-                const double u = tg.uniform(p, (uint32_t)t);
-                if (trial_collides(segs, nseg, -log(u))) continue;
-                uint32_t k = 0;
-                for (int s = 0; s < nseg; s++) {
-                    const Seg &g = segs[s];
-                    if (g.sigabs * g.L <= .00001) continue;
-                    const double mb_ran = abs_uniform(p, S_trials, (uint32_t)t, k++);
-                    const double sstar = -log(1. - mb_ran * g.dele / g.ew) / g.sigabs;
-                    const double denom = sqrt(g.rpre * g.rpre + 2. * wmu_c * g.rpre * sstar + sstar * sstar);
-                    pr_acc[s] += g.dele * ((wmu_c * g.rpre + sstar) / denom) * kCLight;
-                }
+        // C': absorption-point draws of l.451-459 for the other trials (they only move prdep): queued for k_absdraw
+        if (has_rand) {
+            const unsigned long long n = atomicAdd(p.qabs_count, 1ull);
+            if (n >= p.qabs_cap) count(p, CNT_FATAL);
+            else {
+                AbsTask &a = p.qabs[n];
+                a.p = T0; a.nlit = nlit; a.lit_off = lit_off; a.S_trials = S_trials; a.wtmin = wtmin;
             }
         }
-        unsigned todo = warp_ballot(coop);
-        const int lane = lane_id();
-        while (todo) {
-            const int src = first_lane(todo);
-            todo &= todo - 1;
-            const uint64_t S_src = warp_shfl(S_trials, src);
-            const int n_s = warp_shfl(nseg, src);
-            const double wm = warp_shfl(wmu_c, src);
-            const int l0 = warp_shfl(lit_t[0], src), l1 = warp_shfl(lit_t[1], src), l2 = warp_shfl(lit_t[2], src), l3 = warp_shfl(lit_t[3], src);
-            uint32_t k = 0;
-            for (int s = 0; s < n_s; s++) {
-                const int sc = (s < kMaxSeg) ? s : 0;
-                const double sa = warp_shfl(segs[sc].sigabs, src), L = warp_shfl(segs[sc].L, src);
-                if (sa * L <= .00001) continue;
-                const double dele = warp_shfl(segs[sc].dele, src), ew = warp_shfl(segs[sc].ew, src), rp = warp_shfl(segs[sc].rpre, src);
-                double acc = 0.0;
-                const double frac = dele / ew, inv_sa = 1.0 / sa;            // hoisted out of the trial loop (<= 1 ulp on prdep)
-                for (int t2 = 2 * lane; t2 < p.split1; t2 += 2 * kWarp) {       // trials t2, t2 + 1: one Philox call
-                    uint32_t o[4];
-                    philox4x32_10((uint32_t)S_src, (uint32_t)(S_src >> 32), (uint32_t)t2 >> 1, 2u + k, p.key0, p.key1, o);
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const int t = t2 + h;
-                        if (t >= p.split1 || t == l0 || t == l1 || t == l2 || t == l3) continue;
-                        const double mb_ran = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
-                        const double sstar = -log(1. - mb_ran * frac) * inv_sa;
-                        const double denom = sqrt(rp * rp + 2. * wm * rp * sstar + sstar * sstar);
-                        acc += dele * ((wm * rp + sstar) / denom) * kCLight;
-                    }
-                }
-                acc = warp_sum(acc);
-                if (lane == src) pr_acc[sc] = acc;
-                k++;
-            }
-        }
-    }
-    // D: absorption deposition of the non-colliding trials (l.465-466), identical per trial
-    if (fast) {
-        const double n_nc = (double)(p.split1 - nlit);
-        if (n_nc > 0)
-            for (int s = 0; s < nseg; s++) {
-                const Seg &g = segs[s];
-                atomic_add_f64(p.edep + g.zi, n_nc * g.dele);
-                if (g.sigabs * g.L <= .00001) atomic_add_f64(p.prdep + g.zi, n_nc * (g.dele * wmu_c * kCLight));
-                else atomic_add_f64(p.prdep + g.zi, pr_acc[s]);
-            }
     }
     {   // counters, aggregated over the warp
         const unsigned long long nh = warp_sum((unsigned long long)(hist_active ? 1 : 0));
-        const unsigned long long nt = warp_sum((unsigned long long)((fast || overflow_counted) ? p.split1 : 0));
-        const unsigned long long ns = warp_sum((unsigned long long)(fast ? nseg : 0));
+        const unsigned long long nt = warp_sum((unsigned long long)(active ? p.split1 : 0));
+        const unsigned long long ns = warp_sum((unsigned long long)(active ? nseg : 0));
         if (lane_id() == 0) {
             if (nh) count(p, CNT_HISTORIES, nh);
             if (nt) count(p, CNT_TRIALS, nt);
             if (ns) count(p, CNT_SEGMENTS, ns);
         }
     }
-    // E: recombined flight of the unscattered weight (l.698-712): scat_flag = 0, no collisions, no deposition.  It
-    // follows the ray of step A, so its geometry is not traced again: the weight is attenuated crossing by crossing
-    // (with this flight's own kill threshold and its own draw count) and the census / leak tallies are made at the
-    // ray's end point.  Rays that step A did not finish the same way (killed earlier because a trial carries 1/split1
-    // of the weight, more crossings than the fast path holds) and photons that pass through the axis are flown literally.
+    // E: the recombined flight of the unscattered weight (l.698-712): scat_flag = 0, no collisions, no deposition.  Without
+    // collisions it followed the ray above: its census / leak tallies are made at the ray's end point.  Otherwise (trials
+    // collided, the trial ray was killed first -- a trial carries 1/split1 of the weight --, the photon passes through the
+    // axis) it is flown literally.
+    Rng rng; rng.stream(mix64(S_entry, kTagF0));
+    Photon F = P0;
+    bool do_census = false, literal = false;
     if (active && p.split1 - nscat > 0) {
-        Photon F = P0;
-        F.ew = (p.split1 - nscat) * T0.ew;
-        const double wt0 = 1.e-10 * F.ew;
-        Rng rng; rng.stream(mix64(S_entry, kTagF0));
-        int dummy = 0, end = END_DROPPED;
-        bool literal = !(fast && (endA == END_CENSUS || endA == END_LEAK));
-        if (!literal) {
-            bool alive = true;
-            for (int s = 0; s < nseg; s++) {
-                if (F.ew < 1.e-40) { alive = false; break; }      // l.161
-                const double xabs = segs[s].sigabs * segs[s].L;
-                const double ewnew = (xabs < 100.) ? F.ew * exp(-xabs) : 0.;
-                if (!(xabs <= .00001)) rng.d++;                   // the absorption-point draw is consumed, its value unused
-                if (ewnew <= wt0) { count(p, CNT_KILLED); alive = false; break; }
-                F.ew = ewnew;
-            }
-            if (alive) {
-                F.rpre = Q.rpre; F.zpre = Q.zpre; F.phi = Q.phi; F.wmu = Q.wmu; F.dcen = Q.dcen; F.jph = Q.jph; F.kph = Q.kph;
-                if (endA == END_CENSUS) {
-                    if (!census_write(p, F, rng)) end = END_FATAL;
-                } else {
+        if (nscat == 0 && (endA == END_CENSUS || endA == END_LEAK)) {
+            if (F_state == 2) count(p, CNT_KILLED);
+            if (F_state == 0) {
+                F.ew = F_ew; F.rpre = Q.rpre; F.zpre = Q.zpre; F.phi = Q.phi; F.wmu = Q.wmu; F.dcen = Q.dcen; F.jph = Q.jph; F.kph = Q.kph;
+                rng.d = F_d;
+                if (endA == END_CENSUS) do_census = true;
+                else {
                     const int idead = imcleak(p, F, rng);
                     count(p, CNT_LKCOUNT);
                     literal = (idead != 1);                       // through the axis: the flight goes on
                 }
             }
+        } else {
+            F.ew = (p.split1 - nscat) * T0.ew;
+            literal = true;
         }
-        if (literal) end = fly<MODE_F0>(p, F, rng, wt0, 0.0, nullptr, dummy);
+    }
+    tally_census_zone(p, bt, do_census, (F.jph - 1) * p.nr + (F.kph - 1), F.ew);
+    if (do_census) census_record(p, F, rng);
+    if (literal) {
+        int dummy = 0;
+        const double wtF = 1.e-10 * ((p.split1 - nscat) * T0.ew);
+        const int end = fly<MODE_F0>(p, F, rng, wtF, 0.0, nullptr, dummy);
         if (end == END_COLLISION) count(p, CNT_FATAL);
     }
 }
@@ -330,6 +341,13 @@ __device__ __forceinline__ void history(const Params &p, bool active, const Phot
 template <int SRC>
 __global__ void __launch_bounds__(C2D_HIST_THREADS, C2D_HIST_MINB) k_history(const __grid_constant__ Params p, long long first, long long n, long long stride)
 {
+#ifndef C2D_EMU
+    __shared__ BlockTally s_bt;
+    bt_init(s_bt);
+    BlockTally *bt = &s_bt;
+#else
+    BlockTally *bt = nullptr;
+#endif
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool active = idx < n;
     Photon P0 = {1.0, 0.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1, 1, 0, 0, 1};
@@ -375,7 +393,69 @@ __global__ void __launch_bounds__(C2D_HIST_THREADS, C2D_HIST_MINB) k_history(con
         S_entry = p.in.sid[h];
     }
     if (SRC != 1 && p.bins_off) { P0.jgpsp = 0; P0.jgplc = 0; P0.jgpmu = 0; }
-    history(p, active, P0, S_entry);
+    history(p, active, P0, S_entry, bt);
+#ifndef C2D_EMU
+    bt_flush(p, s_bt);
+#endif
+}
+
+// Absorption-point draws (imctrk2d.f:451-459) of the collision-free trials of one queued history: a warp re-traces the ray
+// (every lane the same ray) and, for each crossing with sigabs L > 1e-5, spreads the split1 trials over its lanes -- one
+// uniform per (trial, absorbing crossing) from the trial's stream, two trials per Philox call -- leaving out the literal
+// trials, which made their own draws.  Only prdep moves.
+__device__ __forceinline__ void absdraw_task(const Params &p, const AbsTask &a)
+{
+    const int lane = lane_id();
+    const uint64_t S = a.S_trials;
+    const int nlit = a.nlit;
+    const int *lit = p.lit_pool + a.lit_off;
+    Photon Q = a.p;
+    double wm = Q.wmu;
+    if (wm > 1.0) wm = 1.0;
+    if (wm < -1.0) wm = -1.0;
+    FlightCtx fc;
+    flight_begin(p, Q.xnu, fc);
+    Rng dummy; dummy.stream(0);
+    uint32_t k = 0;
+    for (;;) {
+        if (Q.ew < 1.e-40) break;
+        if (Q.wmu > 1.0) Q.wmu = 1.0;
+        if (Q.wmu < -1.0) Q.wmu = -1.0;
+        Seg g; int s = 0, ns = 0; double colmfp = 0.0;
+        const int r = fly_step<MODE_PRE>(p, Q, dummy, a.wtmin, colmfp, 0.0, fc, &g, s, ns);
+        if (!(g.sigabs * g.L <= .00001)) {
+            double acc = 0.0;
+            const double frac = g.dele / g.ew, inv_sa = 1.0 / g.sigabs, rp = g.rpre;   // hoisted out of the trial loop (<= 1 ulp on prdep)
+            for (int t2 = 2 * lane; t2 < p.split1; t2 += 2 * kWarp) {                  // trials t2, t2 + 1: one Philox call
+                uint32_t o[4];
+                philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), (uint32_t)t2 >> 1, 2u + k, p.key0, p.key1, o);
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const int t = t2 + h;
+                    if (t >= p.split1) continue;
+                    bool is_lit = false;
+                    for (int m = 0; m < nlit; m++) is_lit |= (lit[m] == t);
+                    if (is_lit) continue;
+                    const double mb_ran = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
+                    const double sstar = -log(1. - mb_ran * frac) * inv_sa;
+                    const double denom = sqrt(rp * rp + 2. * wm * rp * sstar + sstar * sstar);
+                    acc += g.dele * ((wm * rp + sstar) / denom) * kCLight;
+                }
+            }
+            acc = warp_sum(acc);
+            if (lane == 0) atomic_add_f64(p.prdep + g.zi, acc);
+            k++;
+        }
+        if (r != STEP_CONT) break;
+    }
+}
+// persistent warps over a task count that lives on the device (k_history has just written it: no host round trip)
+__global__ void __launch_bounds__(128) k_absdraw(const __grid_constant__ Params p, const AbsTask *q, const unsigned long long *n_dev)
+{
+    const unsigned long long n = *n_dev;
+    const unsigned long long w0 = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) / kWarp;
+    const unsigned long long nw = ((unsigned long long)gridDim.x * blockDim.x) / kWarp;
+    for (unsigned long long w = w0; w < n && w < p.qabs_cap; w += nw) absdraw_task(p, q[w]);
 }
 
 // scattered photon after compb2d: tallies of imctrk2d.f:657-661 / 672-677, then the scat_flag = 1 flight
@@ -605,6 +685,10 @@ void launch_history_census(const Params &p, long long first, long long n, long l
     const int threads = C2D_HIST_THREADS;
     const long long blocks = (n + threads - 1) / threads;
     k_history<1><<<(unsigned)blocks, threads, 0, st>>>(p, first, n, stride);
+}
+void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int n_sm, cudaStream_t st)
+{
+    k_absdraw<<<n_sm * 8, 128, 0, st>>>(p, q, n_dev);
 }
 void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st)
 {

@@ -147,7 +147,7 @@ def snapshot_points(trace):
         elif state == "redist" and t["op"] == "bcast" and t["dtype"] >= 1000:
             pts.append((t["idx"], f"c{cyc}_E"))
             state = "fp"
-        elif state == "fp" and sig == ("reduce", 4, 17):
+        elif state == "fp" and t["op"] == "reduce" and t["dtype"] == 17:      # E_add_up's first reduce: erlki, count nz (update2d.f:2023)
             pts.append((t["idx"], f"c{cyc}_F"))
             state = None
         i += 1
@@ -260,7 +260,11 @@ def main(name):
         for fn in ("log.txt", "output/lcb_01.dat", "output/temp_b.dat", "output/spb.dat", "output/phb.dat", "stdout.txt"):
             f = rd / fn
             if f.exists():
-                out["file/" + fn] = np.array(f.read_text()[-200000:])
+                txt = f.read_text()
+                if len(txt) > 200000:          # log.txt: keep the per-cycle summary lines, not the per-zone chatter
+                    keys = ("time step", "bingo", "Luminosity", "Delta E", "dT_max", "Total energy", "dt_new", "Total heat", "Acceleration rate")
+                    txt = "".join(l + "\n" for l in txt.splitlines() if any(k in l for k in keys))
+                out["file/" + fn] = np.array(txt)
     # the worker's event file as the binary formatted it (format 105 of imcleak2d.f:181), first 600 records: pins the
     # e14.7 formatter of the library's reference-format writers (c2d_events_write / c2d_census_write)
     if name == "dense":

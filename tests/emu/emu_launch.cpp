@@ -19,6 +19,11 @@ template <int SRC> static void run_hist(const Params &p, long long first, long l
 void launch_history_volume(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<0>(p, first, n, stride); }
 void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<2>(p, first, n, stride); }
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t) { if (n > 0) run_hist<1>(p, first, n, stride); }
+void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int, cudaStream_t)
+{
+    blockDim.x = 1; gridDim.x = 1; blockIdx.x = 0; threadIdx.x = 0;       // one serial "warp" walks the whole queue
+    k_absdraw(p, q, n_dev);
+}
 template <class F> static void run_grid(long long n, F body)
 {
     blockDim.x = 128;
@@ -50,7 +55,7 @@ void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nod
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
                         double *coef, cudaStream_t)
 {
-    run_grid(p.nzone, [&] { k_sigma_prefix(p, W, AB); });
+    run_grid(p.nzone, [&] { k_sigma_prefix(p, W, AB, const_cast<double *>(p.sig_NB), const_cast<int *>(p.sig_if)); });
     run_grid((long long)n_nodes * ((p.nzone + kSigZG - 1) / kSigZG), [&] { k_sigma_nodes(p, W, Kn, n_nodes, T); });
     const long long ni = (long long)p.nzone * (n_nodes / kSigDeg);
     run_grid(ni, [&] { k_sigma_coef(T, M, ni, coef); });
