@@ -83,66 +83,94 @@ void Ctx::timer_collect()
     ev_used = 0; ev_which.clear();
 }
 
-// run the scattering work queue dry: every generation of collisions spawns split2 children whose own
-// collisions ('multiple scattering', imctrk2d.f:614) form the next generation
+// Run the scattering cascade dry, once per step (c2d_sync): the history kernels of the census, volume and surface phases
+// have queued their collisions; every generation of collisions spawns split2 children (k_children) whose own collisions
+// ('multiple scattering', imctrk2d.f:614) form the next generation, and children that trigger the 3rd split go through
+// k_split3_attempts -> k_split3_hard -> k_split3_flights.
+//   * device-driven: k_children and k_split3_hard read their work counts from device memory; the host looks at the counts
+//     ONCE per generation (it has to size the attempt launches and to know when the cascade has ended);
+//   * across ranks: the counts and the 3rd-split tasks of all ranks are all-gathered and every rank takes every world-th
+//     sub-child of the concatenated list (S3Map).  The 3rd split's cost per task varies over six decades; without the
+//     re-deal the ranks wait for the unluckiest one at the step's all-reduce (SCALE_r01: 57 % efficiency at 8 GPUs).
+//     Collective: with world > 1 every rank must call c2d_sync the same number of times per step.
 static int drain_queue(Ctx *c)
 {
+    if (!c->cascade_dirty) return 0;                               // nothing was tracked since the last drain (and no collective is due)
+    c->cascade_dirty = false;
+    const int world = comm_world(c), rank = comm_rank(c);
+    if (!c->d_cnt3) {
+        CU(cudaMalloc(&c->d_cnt3, (size_t)(3 + 3 * 8) * 8));
+    }
     for (int gen = 0; gen < 1000; gen++) {
-        unsigned long long n = 0;
-        CU(cudaMemcpyAsync(&n, c->d_qcount + c->q_cur, 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        if (n == 0) return 0;
-        if (n > (unsigned long long)c->q_cap)
-            return fail(C2D_EINVAL, "collision queue overflow: %llu tasks > collision_capacity %lld", n, (long long)c->q_cap);
-        c->q_peak = std::max<long long>(c->q_peak, (long long)n);
         const int other = c->q_cur ^ 1;
-        CU(cudaMemsetAsync(c->d_qcount + other, 0, 8, c->stream));
         Params p = c->P;
         p.q_out = c->d_q[other]; p.q_out_count = c->d_qcount + other;
-        CU(cudaMemsetAsync(c->d_qcount + 2, 0, 8, c->stream));
         c->timer_begin(1);
-        launch_children(p, c->d_q[c->q_cur], (long long)n, c->stream);
+        launch_children(p, c->d_q[c->q_cur], c->d_qcount + c->q_cur, c->n_sm, c->stream);
         c->timer_end();
         CU(cudaGetLastError());
-        unsigned long long n3 = 0;
-        CU(cudaMemcpyAsync(&n3, c->d_qcount + 2, 8, cudaMemcpyDeviceToHost, c->stream));
+        // [collisions processed, 3rd-split tasks] of every rank
+        unsigned long long *mine = c->d_cnt3, *all = c->d_cnt3 + 3;
+        CU(cudaMemcpyAsync(mine, c->d_qcount + c->q_cur, 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(mine + 1, c->d_qcount + 2, 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (world > 1) { c->timer_begin(10); int rc = comm_allgather(c, mine, all, 16); c->timer_end(); if (rc) return rc; }
+        else CU(cudaMemcpyAsync(all, mine, 16, cudaMemcpyDeviceToDevice, c->stream));
+        unsigned long long h[16];
+        CU(cudaMemcpyAsync(h, all, (size_t)world * 16, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        if (n3 > (unsigned long long)c->q_cap)
-            return fail(C2D_EINVAL, "split3 queue overflow: %llu tasks > collision_capacity %lld", n3, (long long)c->q_cap);
-        if (n3) {
-            // chunks of split3 tasks: attempts (one warp per sub-child) -> flight buffer -> flights
+        unsigned long long n_any = 0, n3_tot = 0, n3_max = 0;
+        for (int r = 0; r < world; r++) { n_any += h[2 * r]; n3_tot += h[2 * r + 1]; n3_max = std::max(n3_max, h[2 * r + 1]); }
+        const unsigned long long n = h[2 * rank], n3 = h[2 * rank + 1];
+        if (n > (unsigned long long)c->q_cap)
+            return fail(C2D_EINVAL, "collision queue overflow: %llu tasks > collision_capacity %lld", n, (long long)c->q_cap);
+        if (n3_max > (unsigned long long)c->q_cap)
+            return fail(C2D_EINVAL, "split3 queue overflow: %llu tasks > collision_capacity %lld", n3_max, (long long)c->q_cap);
+        if (n_any == 0) return 0;                                  // no rank had a collision left: the cascade has ended
+        c->q_peak = std::max<long long>(c->q_peak, (long long)n);
+        if (n3_tot) {
+            S3Map m;
+            memset(&m, 0, sizeof m);
+            m.world = world; m.rank = rank;
+            for (int r = 0; r < world; r++) m.prefix[r + 1] = m.prefix[r] + (long long)h[2 * r + 1];
+            if (world > 1) {
+                const size_t need = (size_t)world * n3_max;
+                if (need > c->q3all_cap) {
+                    cudaFree(c->d_q3_all); c->d_q3_all = nullptr; c->q3all_cap = 0;
+                    CU(cudaMalloc(&c->d_q3_all, need * sizeof(CollTask)));
+                    c->q3all_cap = need;
+                }
+                c->timer_begin(10);
+                int rc = comm_allgather(c, c->d_q3, c->d_q3_all, (size_t)n3_max * sizeof(CollTask));
+                c->timer_end();
+                if (rc) return rc;
+                m.base = c->d_q3_all; m.stride = (long long)n3_max;
+            } else { m.base = c->d_q3; m.stride = (long long)n3; }
+            // this rank's sub-children: global sub-child rank, rank + world, ...
+            const long long G = (long long)n3_tot * p.split3;
+            const long long n_mine = (G > rank) ? (G - rank + world - 1) / world : 0;
             if (!c->d_flights) {
                 c->flight_cap = std::max<int64_t>((int64_t)p.split3, (int64_t)1 << 20);
                 CU(cudaMalloc(&c->d_flights, (size_t)c->flight_cap * sizeof(FlightTask)));
                 CU(cudaMalloc(&c->d_hard, (size_t)c->flight_cap * sizeof(unsigned)));
             }
-            const long long per = std::max<long long>(1, c->flight_cap / p.split3);
-            for (long long t0 = 0; t0 < (long long)n3; t0 += per) {
-                const long long nt = std::min<long long>(per, (long long)n3 - t0);
+            for (long long i0 = 0; i0 < n_mine; i0 += c->flight_cap) {
+                const long long ns = std::min<long long>(c->flight_cap, n_mine - i0);
                 CU(cudaMemsetAsync(c->d_qcount + 3, 0, 8, c->stream));
                 c->timer_begin(2);
-                launch_split3_attempts(p, c->d_q3 + t0, nt, c->d_flights, c->split3_rounds, c->d_hard, c->d_qcount + 3, c->stream);
+                launch_split3_attempts(p, m, i0, ns, c->d_flights, c->split3_rounds, c->d_hard, c->d_qcount + 3, c->stream);
+                if (c->split3_rounds > 0)
+                    launch_split3_hard(p, m, i0, c->d_hard, c->d_qcount + 3, c->d_flights, (unsigned long long)c->split3_rounds * kWarp,
+                                       c->n_sm, c->stream);
                 c->timer_end();
                 CU(cudaGetLastError());
-                if (c->split3_rounds > 0) {
-                    unsigned long long nh = 0;
-                    CU(cudaMemcpyAsync(&nh, c->d_qcount + 3, 8, cudaMemcpyDeviceToHost, c->stream));
-                    CU(cudaStreamSynchronize(c->stream));
-                    if (nh) {
-                        c->timer_begin(2);
-                        launch_split3_hard(p, c->d_q3 + t0, c->d_hard, (long long)nh, c->d_flights,
-                                           (unsigned long long)c->split3_rounds * kWarp, c->stream);
-                        c->timer_end();
-                        CU(cudaGetLastError());
-                    }
-                }
                 c->timer_begin(6);
-                launch_split3_flights(p, c->d_flights, nt * p.split3, c->stream);
+                launch_split3_flights(p, c->d_flights, ns, c->stream);
                 c->timer_end();
                 CU(cudaGetLastError());
             }
         }
         CU(cudaMemsetAsync(c->d_qcount + c->q_cur, 0, 8, c->stream));
+        CU(cudaMemsetAsync(c->d_qcount + 2, 0, 8, c->stream));
         c->q_cur = other;
         c->P.q_out = c->d_q[c->q_cur]; c->P.q_out_count = c->d_qcount + c->q_cur;
     }
@@ -221,12 +249,12 @@ int Ctx::sigma_setup()
     CU(cudaMemcpy(d_sig_M, M.data(), D * D * 8, cudaMemcpyHostToDevice));
     CU(cudaMalloc(&d_sig_ms, (size_t)sig_nodes * 4));
     CU(cudaMemcpy(d_sig_ms, ms.data(), (size_t)sig_nodes * 4, cudaMemcpyHostToDevice));
-    const size_t n_step = (size_t)nzone * N * 4 + (size_t)nzone * sig_nodes * 2 + (((size_t)nzone + 1) & ~size_t(1));
+    const size_t n_step = (size_t)nzone * N * 5 + (size_t)nzone * sig_nodes * 2 + (((size_t)nzone + 1) & ~size_t(1));
     CU(cudaMalloc(&d_sig_step, n_step * 8));
     d_sig_W = d_sig_step; d_sig_AB = d_sig_W + (size_t)nzone * N; d_sig_T = d_sig_AB + (size_t)nzone * N * 2;
     d_sig_coef = d_sig_T + (size_t)nzone * sig_nodes;
     double *d_NB = d_sig_coef + (size_t)nzone * sig_nodes;
-    P.sig_NB = d_NB; P.sig_if = reinterpret_cast<const int *>(d_NB + (size_t)nzone * N);
+    P.sig_NB = d_NB; P.sig_CW = d_NB + (size_t)nzone * N; P.sig_if = reinterpret_cast<const int *>(d_NB + (size_t)2 * nzone * N);
     P.sig_coef = d_sig_coef; P.sig_AB = d_sig_AB; P.sig_W = d_sig_W; P.sig_lo = d_lo; P.sig_iw = d_iw;
     P.sig_nint = n_int; P.sig_nsub = nsub; P.sig_t0 = t0; P.sig_inv_h = 1.0 / h;
     launch_sigma_kn(P, d_xs, d_sig_ms, sig_nodes, d_sig_Kn, stream);
@@ -415,7 +443,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
-    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool);
+    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all);
     cudaFree(c->d_fout_total); cudaFree(c->d_cnt_global); cudaFree(c->d_plasma); cudaFree(c->d_fpx);
     comm_free(c);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
@@ -695,12 +723,12 @@ int c2d_imcfield(c2d_ctx *h)
     if (!c || !c->step_open) return fail(C2D_ESTATE, "c2d_step_begin has not been called");
     if (c->field_done) return fail(C2D_ESTATE, "c2d_imcfield called twice in one step");
     CU(cudaSetDevice(c->device));
-    c->field_done = true; c->step_tracked = true;
+    c->field_done = true; c->step_tracked = true; c->cascade_dirty = true;
     if (int rc = c->sigma_ensure()) return rc;
     if (int rc = launch_history_chunks(c, 1, 0, c->n_census, 1)) return rc;
     c->histories += c->n_census;
     c->n_census = 0;
-    return drain_queue(c);
+    return 0;                                                     // collisions stay queued until c2d_sync
 }
 
 int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
@@ -712,11 +740,11 @@ int c2d_imcvol(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     if (stride < 1 || first < 0) return fail(C2D_EINVAL, "bad shard first=%lld stride=%lld", (long long)first, (long long)stride);
     int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
     if (count < 0 || count > avail) count = avail;
-    c->step_tracked = true;
+    c->step_tracked = true; c->cascade_dirty = true;
     if (int rc = c->sigma_ensure()) return rc;
     if (int rc = launch_history_chunks(c, 0, first, count, stride)) return rc;
     c->histories += count;
-    return drain_queue(c);
+    return 0;
 }
 
 int c2d_surf_begin(c2d_ctx *h, const c2d_surf_in *in)
@@ -796,11 +824,11 @@ int c2d_imcsurf(c2d_ctx *h, int64_t first, int64_t count, int64_t stride)
     const int64_t total = c->surf_total;
     int64_t avail = (first < total) ? (total - first + stride - 1) / stride : 0;
     if (count < 0 || count > avail) count = avail;
-    c->step_tracked = true;
+    c->step_tracked = true; c->cascade_dirty = true;
     if (int rc = c->sigma_ensure()) return rc;
     if (int rc = launch_history_chunks(c, 2, first, count, stride)) return rc;
     c->histories += count;
-    return drain_queue(c);
+    return 0;
 }
 
 int c2d_sync(c2d_ctx *h)

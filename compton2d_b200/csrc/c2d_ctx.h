@@ -43,7 +43,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;
     c2d_dims dims{};
     int nzone = 0;
-    bool inited = false, step_open = false, field_done = false, step_tracked = false;
+    bool inited = false, step_open = false, field_done = false, step_tracked = false, cascade_dirty = false;
     int64_t census_cap = 0, event_cap = 0, q_cap = 0, n_census = 0, vol_next = 0, histories = 0;
     long long q_peak = 0;
     // device memory
@@ -65,6 +65,9 @@ struct Ctx {
     // census bank sort (c2d_bank.cu) and the absorption-draw queue of k_history (c2d_track.cu)
     bool sort_bank = true;                 // C2D_SORT_BANK=0 keeps the bank in arrival order (A/B measurements)
     unsigned long long *d_sortkeys = nullptr;
+    unsigned long long *d_cnt3 = nullptr;  // cascade counts: [mine x3 | all ranks]
+    CollTask *d_q3_all = nullptr;          // all-gathered 3rd-split tasks
+    size_t q3all_cap = 0;
     AbsTask *d_qabs = nullptr;
     int *d_litpool = nullptr;
     int64_t qabs_cap = 0, lit_cap = 0;

@@ -65,6 +65,13 @@ struct FlightTask {          // a scattered photon (after compb2d) waiting for i
     double ewold;
 };
 
+struct S3Map {               // the all-gathered 3rd-split tasks and this rank's share of their sub-children (split3_sub)
+    const CollTask *base;
+    long long stride;        // tasks per rank slot
+    long long prefix[9];     // prefix[r] = tasks of ranks < r (world <= 8)
+    int world, rank;
+};
+
 struct Bank {                // census bank, SoA (commonblock.f:8,72 dbuf/ibuf record, imctrk2d.f:566-580)
     double *rpre, *zpre, *wmu, *phi, *ew, *xnu;
     uint32_t *bins;          // jgpsp | jgplc << 16 | jgpmu << 24
@@ -113,7 +120,8 @@ struct Params {
     const double *sig_AB;              // [nzone][num_nt][2] prefix sums of the Thomson-branch bins
     const double *sig_W;               // [nzone][num_nt] f_nt * dgamma
     const double *sig_lo, *sig_iw;     // [sig_nint] interval lower bound in ln(x) and 2 / width
-    const double *sig_NB;              // [nzone][num_nt] suffix sums bounding the rounding-noise terms of bins >= i (sig_noise_zone)
+    const double *sig_NB;              // [nzone][num_nt] suffix sums bounding the rounding-noise terms of bins >= i (comtot_table_zone)
+    const double *sig_CW;              // [nzone][num_nt] kn_cb[i] * sig_W[z][i]
     const int *sig_if;                 // [nzone] first bin with f_nt > 0
     int sig_nint, sig_nsub; double sig_t0, sig_inv_h;
     // tallies
@@ -136,14 +144,14 @@ struct Params {
     unsigned long long *lit_count, lit_cap;
 };
 
-constexpr int kSortE = 8;              // energy classes of the bank's sort key
-// energy class of a census photon: roughly one per decade of photon energy below ~1 keV (three binary orders each) -- the
-// Thomson-branch count m(x) of comtot, and with it the length of the sigma table's noise loop, is a function of log x
+constexpr int kSortE = 24;             // energy classes of the bank's sort key
+// energy class of a census photon: one per octave of photon energy from 1 keV down -- the Thomson-branch count m(x) of
+// comtot, and with it the length of the sigma table's noise loop, is a function of log x (7 electron bins per octave)
 __device__ __forceinline__ int sort_class(double xnu)
 {
     int e2;
     (void)frexp(xnu, &e2);
-    int c = (1 - e2) / 3;
+    int c = 1 - e2;
     if (c < 0) c = 0;
     if (c > kSortE - 1) c = kSortE - 1;
     return c;
@@ -259,13 +267,13 @@ struct Rng {
 
 // The xi of the trial flights of a history with trial stream S: u_t = (K_t + 0.5) 2^-52, K_t = coarse8 << 44 | fine44.
 //   Which trials have coarse = 0xFF ("candidates", 1 trial in 256, independently) is decided by the GAPS between them:
-//       gap_j = floor(ln U_j / ln(255/256)),  U_j = word pair (j & 1) of philox(S, j >> 1, 3),
+//       gap_j = floor(ln U_j * (1 / ln(255/256))),  U_j = word pair (j & 1) of philox(S, j >> 1, 3),
 //       candidate_j = candidate_{j-1} + 1 + gap_j  -- a Bernoulli(1/256) process has geometric gaps;
 //   every other trial has coarse = (w * 255) >> 32 in [0, 254], w = word (t & 3) of philox(S, t >> 2, 0);
 //   fine = word 0 and the low 12 bits of word 1 of philox(S, t, 1).
 // A trial collides only if u exceeds a threshold close to 1, so an optically thin ray (tau < 1/256) only has to look at
 // its ~split1/256 candidates: history() jumps from candidate to candidate instead of drawing split1 numbers.
-constexpr double kLnQ = -3.9138993211363287e-3;      // ln(255/256)
+constexpr double kInvLnQ = -255.49967384180653;      // 1 / ln(255/256)
 __device__ __forceinline__ uint64_t trial_fine44(const Params &p, uint64_t S, uint32_t t)
 {
     uint32_t o[4];
@@ -281,7 +289,7 @@ struct TrialGen {
         uint32_t o[4];
         philox4x32_10((uint32_t)S, (uint32_t)(S >> 32), j >> 1, 3u, p.key0, p.key1, o);
         const double U = (j & 1u) ? u52(o[2], o[3]) : u52(o[0], o[1]);
-        const double gap = floor(log(U) / kLnQ);
+        const double gap = floor(log(U) * kInvLnQ);
         j++;
         next_c = (gap > 1.e9) ? (1ll << 40) : next_c + 1 + (long long)gap;
     }
@@ -634,15 +642,21 @@ __device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCt
 #pragma unroll
         for (int q = 6; q >= 1; q--) { b0 = fma(s2, b1, c2d_ldg(kk + q)) - b2; b2 = b1; b1 = b0; }
         v = v + (fma(c.s, b1, c2d_ldg(kk)) - b2);
-        // noise: sum_{i >= m} noise_i(x) W[z][i]
+        // noise: sum_{i >= m} noise_i(x) W[z][i], bins [i0, i_end) where the bound still exceeds 1e-13 |v|
         const double x = c.x, inv_x = 1.0 / x;
-        const double *w = p.sig_W + (size_t)z * N, *nb = p.sig_NB + (size_t)z * N;
+        const double *w = p.sig_W + (size_t)z * N, *nb = p.sig_NB + (size_t)z * N, *cw = p.sig_CW + (size_t)z * N;
         const double thr = fabs(v) * (x * x * x) * 8.0e2;          // bound * 1.2e-16 / x^3 <= 1e-13 |v|
         int i = c.m;
         const int ifz = p.sig_if[z];
         if (i < ifz) i = ifz;
         double e0 = 0.0;
         if (i < N - 1 && c2d_ldg(nb + i) > thr) {
+            int i_end;
+            {   // first bin whose suffix bound is below the threshold (NB is non-increasing)
+                int lo = i + 1, hi = N - 1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (c2d_ldg(nb + mid) > thr) lo = mid + 1; else hi = mid; }
+                i_end = lo;
+            }
             int ia, ib;
             {   // ia = first bin with a1_i x >= 0.1 ; ib = first bin with a2_i x < 1e-3
                 int lo = c.m, hi = N - 1;
@@ -653,7 +667,7 @@ __device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCt
                 ib = lo;
             }
             const int i_fast = (ia > ib) ? ia : ib;
-            for (; i < i_fast && i < N - 1; i++) {               // the full expressions (few bins)
+            for (; i < i_fast && i < i_end; i++) {               // the full expressions (few bins)
                 const double yb = p.kn_a2[i] * x;
                 double q;
                 if (i >= ib) {
@@ -663,14 +677,22 @@ __device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCt
                 if (i < ia) q = q + p.kn_pref[i] * kn_eta(p.kn_a1[i] * x);
                 e0 = fma(q, w[i], e0);
             }
-            const double *a2 = p.kn_a2, *cb = p.kn_cb;
-            for (; i < N - 1; i++) {                              // b side only, division-free, branch-free
-                if ((i & 7) == 0 && !(c2d_ldg(nb + i) > thr)) break;
-                const double yb = c2d_ldg(a2 + i) * x;
-                const double s = 1.0 + yb, e = (s - 1.0) - yb;
-                const double q = -(c2d_ldg(cb + i) * inv_x) * (e * fma(0.125, yb, 1.0));
-                e0 = fma(q, c2d_ldg(w + i), e0);
+            // b side only: -(cb_i W_i / x) e_i (1 + y_i / 8), e_i = (fl(1 + y_i) - 1) - y_i the rounding error of 1 + y_i.
+            // cb_i W_i is tabulated per zone (sig_CW); two independent accumulators, -1 / x applied once.
+            const double *a2 = p.kn_a2;
+            double s0 = 0.0, s1 = 0.0;
+            for (; i + 1 < i_end; i += 2) {
+                const double y0 = c2d_ldg(a2 + i) * x, y1 = c2d_ldg(a2 + i + 1) * x;
+                const double t0 = 1.0 + y0, t1 = 1.0 + y1;
+                const double r0 = (t0 - 1.0) - y0, r1 = (t1 - 1.0) - y1;
+                s0 = fma(c2d_ldg(cw + i), r0 * fma(0.125, y0, 1.0), s0);
+                s1 = fma(c2d_ldg(cw + i + 1), r1 * fma(0.125, y1, 1.0), s1);
             }
+            if (i < i_end) {
+                const double y0 = c2d_ldg(a2 + i) * x, t0 = 1.0 + y0, r0 = (t0 - 1.0) - y0;
+                s0 = fma(c2d_ldg(cw + i), r0 * fma(0.125, y0, 1.0), s0);
+            }
+            e0 = e0 - (s0 + s1) * inv_x;
         }
         v = v + e0 * (inv_x * inv_x);
     }

@@ -8,11 +8,11 @@ void launch_history_volume(const Params &p, long long first, long long n, long l
 void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
-void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st);
-void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
+void launch_children(const Params &p, const CollTask *q_in, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
+void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st);
-void launch_split3_hard(const Params &p, const CollTask *q3_in, const unsigned *hard, long long n_hard, FlightTask *out,
-                        unsigned long long first_attempt, cudaStream_t st);
+void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, const unsigned long long *n_hard_dev,
+                        FlightTask *out, unsigned long long first_attempt, int n_sm, cudaStream_t st);
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st);
 void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t st);
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,

@@ -29,7 +29,7 @@ __global__ void k_sigma_kn(const __grid_constant__ Params p, const double *xs, c
     Kn[idx] = (i >= ms[node]) ? sigma_kn_smooth(p, i, xs[node]) : 0.0;
 }
 
-__global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, double *AB, double *NB, int *IF)
+__global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, double *AB, double *NB, int *IF, double *CW)
 {
     const int z = blockIdx.x * blockDim.x + threadIdx.x;
     if (z >= p.nzone) return;
@@ -56,8 +56,10 @@ __global__ void k_sigma_prefix(const __grid_constant__ Params p, double *W, doub
         const double w = fabs(W[(size_t)z * N + i]);
         nb = nb + (1.125 * p.kn_cb[i] + 9.0 * p.kn_pref[i] / p.kn_a1[i]) * w;
         NB[(size_t)z * N + i] = nb;
+        CW[(size_t)z * N + i] = p.kn_cb[i] * W[(size_t)z * N + i];
         if (w > 0.0) first = i;
     }
+    CW[(size_t)z * N + (N - 1)] = 0.0;
     IF[z] = first;
 }
 
@@ -119,7 +121,7 @@ void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nod
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
                         double *coef, cudaStream_t st)
 {
-    k_sigma_prefix<<<(p.nzone + 63) / 64, 64, 0, st>>>(p, W, AB, const_cast<double *>(p.sig_NB), const_cast<int *>(p.sig_if));
+    k_sigma_prefix<<<(p.nzone + 63) / 64, 64, 0, st>>>(p, W, AB, const_cast<double *>(p.sig_NB), const_cast<int *>(p.sig_if), const_cast<double *>(p.sig_CW));
     const long long n = (long long)n_nodes * ((p.nzone + kSigZG - 1) / kSigZG);
     k_sigma_nodes<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, W, Kn, n_nodes, T);
     const long long ni = (long long)p.nzone * (n_nodes / kSigDeg);

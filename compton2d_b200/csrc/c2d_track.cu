@@ -22,41 +22,45 @@ __device__ __forceinline__ void push_collision(const Params &p, const Photon &P,
 }
 
 // ------------------------------------------------------------------------------------------ tally hierarchy
-// The per-zone tallies of a history (edep, prdep per crossing; npcen, ecens at census) go warp -> block -> HBM: when the lanes
-// of a warp agree on the zone (the census bank is kept sorted by zone, so they usually do) their contributions are summed
-// with shuffles and lane 0 adds the sum to the block's shared-memory slot of that zone; each slot is committed to HBM with one
-// atomic per tally at block end.  Lanes that disagree, and zones that find no free slot, fall back to global atomics.
-constexpr int kTallySlots = 16;
-struct BlockTally {
+// The per-zone tallies of a history (edep, prdep per crossing; npcen, ecens at census) go warp -> shared memory -> HBM: when
+// the lanes of a warp agree on the zone (the census bank is kept sorted by zone, so they usually do) their contributions
+// are summed with shuffles and lane 0 adds the sum to the warp's shared-memory slot of that zone; each slot is committed to
+// HBM with one atomic per tally when the warp retires.  Lanes that disagree, and zones that find no free slot, fall back to
+// global atomics.  The slots are per WARP, not per block: a block-wide cache needs a barrier before its flush, and the
+// warps of a block finish their histories at very different times (measured: 10 % of the stall samples at that barrier).
+constexpr int kTallySlots = 8;
+struct BlockTally {                                      // one per warp
     int key[kTallySlots];                                // zone, -1 = free
+    unsigned cen_n[kTallySlots];                         // npcen
     double dep_e[kTallySlots], dep_p[kTallySlots];       // edep, prdep
     double cen_e[kTallySlots];                           // ecens
-    unsigned cen_n[kTallySlots];                         // npcen
 };
 #ifndef C2D_EMU
 __device__ __forceinline__ void bt_init(BlockTally &bt)
 {
-    if (threadIdx.x < kTallySlots) {
-        bt.key[threadIdx.x] = -1; bt.dep_e[threadIdx.x] = 0.0; bt.dep_p[threadIdx.x] = 0.0; bt.cen_e[threadIdx.x] = 0.0; bt.cen_n[threadIdx.x] = 0u;
-    }
-    __syncthreads();
+    const int l = lane_id();
+    if (l < kTallySlots) { bt.key[l] = -1; bt.dep_e[l] = 0.0; bt.dep_p[l] = 0.0; bt.cen_e[l] = 0.0; bt.cen_n[l] = 0u; }
+    __syncwarp();
 }
+// lane 0 only
 __device__ __forceinline__ int bt_slot(BlockTally &bt, int z)
 {
     int s = z & (kTallySlots - 1);
 #pragma unroll 1
     for (int k = 0; k < kTallySlots; k++) {
-        const int old = atomicCAS(&bt.key[s], -1, z);
-        if (old == -1 || old == z) return s;
+        const int old = bt.key[s];
+        if (old == z) return s;
+        if (old == -1) { bt.key[s] = z; return s; }
         s = (s + 1) & (kTallySlots - 1);
     }
     return -1;
 }
 __device__ __forceinline__ void bt_flush(const Params &p, BlockTally &bt)
 {
-    __syncthreads();
-    if (threadIdx.x < kTallySlots && bt.key[threadIdx.x] >= 0) {
-        const int z = bt.key[threadIdx.x], s = threadIdx.x;
+    __syncwarp();
+    const int s = lane_id();
+    if (s < kTallySlots && bt.key[s] >= 0) {
+        const int z = bt.key[s];
         if (bt.dep_e[s] != 0.0) atomic_add_f64(p.edep + z, bt.dep_e[s]);
         if (bt.dep_p[s] != 0.0) atomic_add_f64(p.prdep + z, bt.dep_p[s]);
         if (bt.cen_n[s]) { atomicAdd(p.npcen + z, (unsigned long long)bt.cen_n[s]); atomic_add_f64(p.ecens + z, bt.cen_e[s]); }
@@ -74,7 +78,7 @@ __device__ __forceinline__ void tally_dep(const Params &p, BlockTally *bt, bool 
         a = warp_sum(valid ? a : 0.0); b = warp_sum(valid ? b : 0.0);
         if (lane_id() == 0) {
             const int s = bt_slot(*bt, z0);
-            if (s >= 0) { atomicAdd(&bt->dep_e[s], a); atomicAdd(&bt->dep_p[s], b); }
+            if (s >= 0) { bt->dep_e[s] += a; bt->dep_p[s] += b; }
             else { atomic_add_f64(p.edep + z0, a); atomic_add_f64(p.prdep + z0, b); }
         }
         return;
@@ -94,7 +98,7 @@ __device__ __forceinline__ void tally_census_zone(const Params &p, BlockTally *b
         ew = warp_sum(valid ? ew : 0.0);
         if (lane_id() == 0) {
             const int s = bt_slot(*bt, z0);
-            if (s >= 0) { atomicAdd(&bt->cen_e[s], ew); atomicAdd(&bt->cen_n[s], (unsigned)__popc(m)); }
+            if (s >= 0) { bt->cen_e[s] += ew; bt->cen_n[s] += (unsigned)__popc(m); }
             else { atomicAdd(p.npcen + z0, (unsigned long long)__popc(m)); atomic_add_f64(p.ecens + z0, ew); }
         }
         return;
@@ -342,9 +346,9 @@ template <int SRC>
 __global__ void __launch_bounds__(C2D_HIST_THREADS, C2D_HIST_MINB) k_history(const __grid_constant__ Params p, long long first, long long n, long long stride)
 {
 #ifndef C2D_EMU
-    __shared__ BlockTally s_bt;
-    bt_init(s_bt);
-    BlockTally *bt = &s_bt;
+    __shared__ BlockTally s_bt[C2D_HIST_THREADS / 32];
+    BlockTally *bt = &s_bt[threadIdx.x >> 5];
+    bt_init(*bt);
 #else
     BlockTally *bt = nullptr;
 #endif
@@ -395,7 +399,7 @@ __global__ void __launch_bounds__(C2D_HIST_THREADS, C2D_HIST_MINB) k_history(con
     if (SRC != 1 && p.bins_off) { P0.jgpsp = 0; P0.jgplc = 0; P0.jgpmu = 0; }
     history(p, active, P0, S_entry, bt);
 #ifndef C2D_EMU
-    bt_flush(p, s_bt);
+    bt_flush(p, *bt);
 #endif
 }
 
@@ -477,10 +481,8 @@ __device__ __forceinline__ void child_flight(const Params &p, Photon &P, Rng &rn
 
 // one thread per (collision, child ii): the split2 loop of imctrk2d.f:619-689.  Children that trigger
 // the 3rd split (l.639) are queued for k_split3 instead of looping split3 times in one thread.
-__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const CollTask *q_in, long long n_in)
+__device__ __forceinline__ void children_one(const Params &p, const CollTask *q_in, long long idx)
 {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n_in * p.split2) return;
     const CollTask &task = q_in[idx / p.split2];
     const int ii = (int)(idx % p.split2) + 1;
     const double ewcsv = task.p.ew / p.split2;                    // l.617
@@ -501,6 +503,16 @@ __global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params
     }
     child_flight(p, P, rng, zi, ewold, i_gam);
 }
+// The number of queued collisions is read on the device (the kernels that queued them have just finished on this stream): a
+// fixed grid strides over collisions x split2 children, no host round trip in front of the launch.
+__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const CollTask *q_in, const unsigned long long *n_dev)
+{
+    unsigned long long n = *n_dev;
+    if (n > p.q_cap) n = p.q_cap;                                  // the overflow itself was counted as fatal by push_collision
+    const long long total = (long long)n * p.split2;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+        children_one(p, q_in, idx);
+}
 
 // 3rd split, imctrk2d.f:641-669: every sub-child ii2 repeats compb2d until the scattered photon again exceeds
 // the trigger.  In Philox replay mode each pass of that rejection loop owns the stream mix64(S_sub, attempt), so
@@ -517,9 +529,17 @@ struct Split3Sub {
     double ewcsv, ewold, trigger, gain_min, znu;
     uint64_t S_sub;
 };
-__device__ __forceinline__ void split3_sub(const Params &p, const CollTask *q3_in, long long w, Split3Sub &u)
+// Which sub-children a rank works on.  The 3rd-split tasks of all ranks are all-gathered (rank r's n_r tasks at
+// base + r * stride) and dealt out again sub-child by sub-child: rank `rank` takes the global sub-children rank, rank + world,
+// ... of the concatenated list -- a task's 300 sub-children share an acceptance rate that varies over six decades between
+// tasks, so this is what evens out the ranks' tails.  Streams are keyed by ancestry: who computes a sub-child changes nothing.
+__device__ __forceinline__ void split3_sub(const Params &p, const S3Map &m, long long i, Split3Sub &u)
 {
-    u.task = q3_in + w / p.split3;
+    const long long w = (long long)m.rank + (long long)m.world * i;          // global sub-child
+    const long long tg = w / p.split3;                                       // global task
+    int r = 0;
+    while (r + 1 < m.world && tg >= m.prefix[r + 1]) r++;
+    u.task = m.base + (size_t)r * m.stride + (size_t)(tg - m.prefix[r]);
     const int ii2 = (int)(w % p.split3) + 1;
     u.ewcsv = u.task->p.ew / p.split2;
     u.ewold = u.ewcsv / p.split3;
@@ -582,7 +602,7 @@ constexpr int kHistWarp = 256;      // bins of the per-warp nelectron copy of k_
 #ifndef C2D_S3_MINB
 #define C2D_S3_MINB 16
 #endif
-__global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __grid_constant__ Params p, const CollTask *q3_in, long long n_sub, FlightTask *out,
+__global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __grid_constant__ Params p, const S3Map m, long long i0, long long n_sub, FlightTask *out,
                                                          int max_rounds, unsigned *hard, unsigned long long *hard_count)
 {
     // every warp keeps its own shared-memory copy of nelectron and flushes it by itself: no block barrier, so a warp
@@ -599,7 +619,7 @@ __global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __gr
     if (w >= n_sub) return;                                       // whole warps together
     const int lane = lane_id();
     Split3Sub u;
-    split3_sub(p, q3_in, w, u);
+    split3_sub(p, m, i0 + w, u);
     Rng rng; Photon P; int i_gam = 0; ElRec rec;
     uint64_t base = 0;
     bool done = false;
@@ -624,29 +644,33 @@ __global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __gr
 }
 
 #ifndef C2D_EMU
-__global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Params p, const CollTask *q3_in, const unsigned *hard, FlightTask *out,
-                                                     unsigned long long first_attempt)
+__global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *hard,
+                                                     const unsigned long long *n_hard_dev, FlightTask *out, unsigned long long first_attempt)
 {
     __shared__ int win;
     C2D_HIST_BEGIN(p)
-    const long long w = hard[blockIdx.x];
-    Split3Sub u;
-    split3_sub(p, q3_in, w, u);
-    Rng rng; Photon P; int i_gam = 0; ElRec rec;
-    for (uint64_t base = first_attempt;; base += blockDim.x) {
-        if (threadIdx.x == 0) win = 0x7fffffff;
-        __syncthreads();
-        const uint64_t attempt = base + threadIdx.x + 1;
-        const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
-        if (ok) atomicMin(&win, (int)threadIdx.x);
-        __syncthreads();
-        const int first = win;
-        if ((int)threadIdx.x <= first) split3_commit(p, u, attempt, rec, hist);
-        if (first != 0x7fffffff) {
-            if ((int)threadIdx.x == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, attempt); }
-            break;
+    const unsigned long long n_hard = *n_hard_dev;                // written by k_split3_attempts just before on this stream
+    for (unsigned long long b = blockIdx.x; b < n_hard; b += gridDim.x) {
+        const long long w = hard[b];
+        Split3Sub u;
+        split3_sub(p, m, i0 + w, u);
+        Rng rng; Photon P; int i_gam = 0; ElRec rec;
+        for (uint64_t base = first_attempt;; base += blockDim.x) {
+            if (threadIdx.x == 0) win = 0x7fffffff;
+            __syncthreads();
+            const uint64_t attempt = base + threadIdx.x + 1;
+            const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
+            if (ok) atomicMin(&win, (int)threadIdx.x);
+            __syncthreads();
+            const int first = win;
+            if ((int)threadIdx.x <= first) split3_commit(p, u, attempt, rec, hist);
+            if (first != 0x7fffffff) {
+                if ((int)threadIdx.x == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, attempt); }
+                break;
+            }
+            __syncthreads();                                      // everyone has read `win` before it is reset
         }
-        __syncthreads();                                          // everyone has read `win` before it is reset
+        __syncthreads();                                          // ... and before the next sub-child's first reset
     }
     C2D_HIST_END(p)
 }
@@ -690,23 +714,21 @@ void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long 
 {
     k_absdraw<<<n_sm * 8, 128, 0, st>>>(p, q, n_dev);
 }
-void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t st)
+void launch_children(const Params &p, const CollTask *q_in, const unsigned long long *n_dev, int n_sm, cudaStream_t st)
 {
-    if (n_in <= 0) return;
-    const long long n = n_in * p.split2;
-    k_children<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q_in, n_in);
+    k_children<<<n_sm * 8, 128, 0, st>>>(p, q_in, n_dev);
 }
-void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
+void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st)
 {
-    if (n_tasks <= 0) return;
-    const long long n = n_tasks * p.split3 * kWarp;               // one warp per sub-child
-    k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, q3_in, n_tasks * p.split3, out, max_rounds, hard, hard_count);
+    if (n_sub <= 0) return;
+    const long long n = n_sub * kWarp;                            // one warp per sub-child
+    k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, m, i0, n_sub, out, max_rounds, hard, hard_count);
 }
-void launch_split3_hard(const Params &p, const CollTask *q3_in, const unsigned *hard, long long n_hard, FlightTask *out,
-                        unsigned long long first_attempt, cudaStream_t st)
+void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, const unsigned long long *n_hard_dev,
+                        FlightTask *out, unsigned long long first_attempt, int n_sm, cudaStream_t st)
 {
-    if (n_hard > 0) k_split3_hard<<<(unsigned)n_hard, 512, 0, st>>>(p, q3_in, hard, out, first_attempt);
+    k_split3_hard<<<n_sm * 2, 512, 0, st>>>(p, m, i0, hard, n_hard_dev, out, first_attempt);
 }
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st)
 {

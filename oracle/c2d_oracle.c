@@ -201,7 +201,7 @@ double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d)
 /* Philox replay mode: the xi of the trial flights of a history with trial stream S.  u_t = (K_t + 0.5) 2^-52 with
  * K_t = coarse8 << 44 | fine44, three independent Philox outputs:
  *   which trials have coarse = 0xFF ("candidates": 1 trial in 256, independently) is decided by the GAPS between them,
- *       gap_j = floor(ln U_j / ln(255/256)),  U_j = word pair (j & 1) of philox(ctr = (S_lo, S_hi, j >> 1, 3)),
+ *       gap_j = floor(ln U_j * (1 / ln(255/256))),  U_j = word pair (j & 1) of philox(ctr = (S_lo, S_hi, j >> 1, 3)),
  *       candidate_j = candidate_{j-1} + 1 + gap_j  (candidate_{-1} = -1): a Bernoulli(1/256) process has geometric gaps;
  *   every other trial has coarse = (w * 255) >> 32 in [0, 254], w = word (t & 3) of philox(ctr = (S_lo, S_hi, t >> 2, 0));
  *   fine = word 0 and the low 12 bits of word 1 of philox(ctr = (S_lo, S_hi, t, 1)).
@@ -209,14 +209,14 @@ double orc_philox_uniform(const uint32_t key[2], uint64_t sid, uint32_t d)
  * candidates need to be looked at: the CUDA path jumps from candidate to candidate instead of drawing split1 numbers.
  * The generator must be asked for non-decreasing t. */
 typedef struct { uint64_t S; int64_t next_c; uint32_t j; } orc_trialgen;
-#define ORC_LN_Q (-3.9138993211363287e-3)      /* ln(255/256) */
+#define ORC_INV_LN_Q (-255.49967384180653)     /* 1 / ln(255/256) */
 static void trialgen_advance(const uint32_t key[2], orc_trialgen *g)
 {
     uint32_t c[4] = {(uint32_t)g->S, (uint32_t)(g->S >> 32), g->j >> 1, 3u}, o[4];
     orc_philox4x32(c, key, o);
     const uint64_t w = (g->j & 1u) ? (((uint64_t)o[3] << 32) | o[2]) : (((uint64_t)o[1] << 32) | o[0]);
     const double U = ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
-    const double gap = floor(log(U) / ORC_LN_Q);
+    const double gap = floor(log(U) * ORC_INV_LN_Q);
     g->j++;
     g->next_c = (gap > 1.e9) ? (int64_t)1 << 40 : g->next_c + 1 + (int64_t)gap;
 }

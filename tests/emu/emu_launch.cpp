@@ -34,16 +34,19 @@ template <class F> static void run_grid(long long n, F body)
             body();
         }
 }
-void launch_children(const Params &p, const CollTask *q_in, long long n_in, cudaStream_t)
+void launch_children(const Params &p, const CollTask *q_in, const unsigned long long *n_dev, int, cudaStream_t)
 {
-    if (n_in > 0) run_grid(n_in * p.split2, [&] { k_children(p, q_in, n_in); });
+    const long long n_in = (long long)*n_dev;
+    for (long long idx = 0; idx < n_in * p.split2; idx++) children_one(p, q_in, idx);
 }
-void launch_split3_attempts(const Params &p, const CollTask *q3_in, long long n_tasks, FlightTask *out, int max_rounds,
+void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t)
 {   // kWarp == 1 in this build: one serial "warp" per sub-child, no round limit
-    if (n_tasks > 0) run_grid(n_tasks * p.split3, [&] { k_split3_attempts(p, q3_in, n_tasks * p.split3, out, 0, hard, hard_count); });
+    (void)max_rounds;
+    if (n_sub > 0) run_grid(n_sub, [&] { k_split3_attempts(p, m, i0, n_sub, out, 0, hard, hard_count); });
 }
-void launch_split3_hard(const Params &, const CollTask *, const unsigned *, long long, FlightTask *, unsigned long long, cudaStream_t) {}
+void launch_split3_hard(const Params &, const S3Map &, long long, const unsigned *, const unsigned long long *, FlightTask *, unsigned long long, int,
+                        cudaStream_t) {}
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t)
 {
     if (n > 0) run_grid(n, [&] { k_split3_flights(p, fl, n); });
@@ -55,7 +58,7 @@ void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nod
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
                         double *coef, cudaStream_t)
 {
-    run_grid(p.nzone, [&] { k_sigma_prefix(p, W, AB, const_cast<double *>(p.sig_NB), const_cast<int *>(p.sig_if)); });
+    run_grid(p.nzone, [&] { k_sigma_prefix(p, W, AB, const_cast<double *>(p.sig_NB), const_cast<int *>(p.sig_if), const_cast<double *>(p.sig_CW)); });
     run_grid((long long)n_nodes * ((p.nzone + kSigZG - 1) / kSigZG), [&] { k_sigma_nodes(p, W, Kn, n_nodes, T); });
     const long long ni = (long long)p.nzone * (n_nodes / kSigDeg);
     run_grid(ni, [&] { k_sigma_coef(T, M, ni, coef); });

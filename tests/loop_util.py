@@ -32,6 +32,8 @@ def initial_state(g, cens_cap=400000, ev_cap=400000):
     a = o.a
     if F is E:
         a.turb_lev = g.snap("c2_E").turb_lev
+        a.F_IC[:] = 0.0
+        o.L.orc_IC_loss(o.p)                     # the worker has not received F_IC yet at E: icloss2d.f restated (pinned to 1e-8)
     for v in ("f_nt", "pnt", "n_e", "amxwl", "gmin", "gmax", "p_nth", "te_new", "f_pair"):
         setattr(a, cname(v), E[v])
     nzone = o.dims["nzone"]

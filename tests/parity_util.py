@@ -74,11 +74,18 @@ def oracle_surface(o, S):
     o.surf_all()
 
 
+def _step_tbbl(P, surf):
+    """tbbl(k, ti) is ONE COMMON array in the reference: the lower-face leak test of imcleak (imcleak2d.f:95) reads the values the
+    surface source uses, in every phase of the step."""
+    return surf["tbbl"] if surf is not None and surf.get("tbbl") is not None else P["tbbl"]
+
+
 def oracle_step(o, P, ncycle, time=None, field=True, vol=True, surf=None):
     a = o.a
     for k in ("kappa_tot", "eps_tot", "eps_th", "k_gg", "f_nt", "Pnt", "n_e", "tea", "f_pair", "nsv", "ewsv",
-              "Eloss_th", "Eloss_tot", "zsurf", "tbbl"):
+              "Eloss_th", "Eloss_tot", "zsurf"):
         setattr(a, k, P[k])
+    a.tbbl = _step_tbbl(P, surf)
     o["dt"] = P["dt"]; o["time"] = P["time"] if time is None else time; o["ncycle"] = ncycle
     o.philox_key(o.rseed, ncycle)
     o.step_zero()
@@ -123,7 +130,7 @@ def gpu_step(g, P, ncycle, time=None, field=True, vol=True, surf=None):
     g.imcgen2d(ncycle=ncycle, time=P["time"] if time is None else time, dt=P["dt"], kappa_tot=P["kappa_tot"],
                eps_tot=P["eps_tot"], eps_th=P["eps_th"], f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"],
                f_pair=P["f_pair"], k_gg=P["k_gg"], nsv=P["nsv"], ewsv=P["ewsv"], Eloss_th=P["Eloss_th"],
-               Eloss_tot=P["Eloss_tot"], zsurf=P["zsurf"], tbbl=P["tbbl"])
+               Eloss_tot=P["Eloss_tot"], zsurf=P["zsurf"], tbbl=_step_tbbl(P, surf))
     if field:
         g.imcfield2d()
     if vol:

@@ -67,7 +67,9 @@ def test_long_rays_slow_path():
     """mcdt = 30: rays cross more zones than the fast path holds -> literal per-trial flights."""
     P = make_problem(nz=24, nr=20, nst=400, ngroups=32, split=(8, 4, 2, 10), mcdt=30.0, n_e=3.0e5)
     rg = _run(P, cycles=(1,))
-    assert rg["counters"]["segovf"] > 0
+    # (round 1's history kernel kept <= 12 crossings per ray and flew longer ones trial by trial; the streaming kernel has no
+    # such limit -- these rays must simply replay)
+    assert rg["counters"]["segments"] > 12 * rg["counters"]["histories"] and rg["counters"]["segovf"] == 0
 
 
 def test_energy_conservation_and_determinism_full_size():
