@@ -161,7 +161,8 @@ def reference_arm(args):
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                      "data": "synthetic", "config": workload_config(args, ref=True),
+                      "data": "synthetic", "config": dict(workload_config(args, ref=True), nst_per_gpu=None, nst_per_instance=nst,
+                                                          instances=ncores, note="bounded sample of the same workload shape: nst per instance as stated"),
                       "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
                       "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}))
@@ -191,8 +192,7 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64, bins=200):
     q = (1.1^198)^(1/510), the binary's spectrum resampled onto it (as tests/test_gpu_configs.py does)."""
     import numpy as np
     from golden_util import Golden
-    from parity_util import make_gpu
-    from synth import make_problem
+    from compton2d_b200.synth import context_for as make_gpu, make_problem
     E = Golden("small").snap("c2_E")
     P = make_problem(nz=nz, nr=nr, nst=1000, ngroups=100)
     nzone = nz * nr
@@ -289,12 +289,107 @@ def lc_bench(g, hbm, n_events=100_000_000):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-def our_arm(args):
+FAM = {"k_history": 0, "k_children": 1, "k_split3_attempts": 2, "k_split3_flights": 6, "k_sigma_table": 4, "bank_sort": 11,
+       "tally_allreduce": 8, "cascade_exchange": 10}      # c2d_kernel_time_ms families (tally_allreduce includes the wait for the slowest rank)
+
+
+def run_tracking(args, dist, rank, world, local, nz, nr, groups, nst, steps, warmup, sampler=None):
+    """K timed IMC steps of the tracking hot path on one workload.  Every step goes through the public host API with HOST
+    buffers: c2d_step_begin uploads the step's tables (H2D), imcfield2d + imcvol2d track, graphics_collect drains the cascade
+    and all-reduces the tallies inside the library (NCCL), tallies() reads them back (D2H).
+      value = histories / device time of [imcfield2d .. graphics_collect] (CUDA events on the library's stream)
+      e2e   = the same histories / host wall clock of the whole loop, copies included -- the same K cycles."""
     import numpy as np
     import torch
+    from compton2d_b200.synth import context_for, make_problem
+    P = make_problem(nz=nz, nr=nr, nst=nst * world, ngroups=groups)
+    per_step = int(P["nsv"].sum()) // world + 1
+    cap = int(per_step * (steps + warmup + 2) * 1.1) + 1000
+    g = context_for(P, sigma_mode=args.sigma_mode, census_capacity=cap, event_capacity=max(per_step, 1000),
+                    device=local, rank=rank, world=world, collision_capacity=1 << 18)
+    if world > 1:
+        g.comm_init()
+    g.timing(True)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(cyc):
+        g.imcgen2d(ncycle=cyc, time=cyc * P["dt"], dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"],
+                   eps_th=P["eps_th"], f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"], f_pair=P["f_pair"],
+                   k_gg=P["k_gg"], nsv=P["nsv"], ewsv=P["ewsv"], Eloss_th=P["Eloss_th"], Eloss_tot=P["Eloss_tot"],
+                   zsurf=P["zsurf"], tbbl=P["tbbl"])
+        g.timing_reset()
+        g.mark()                                   # CUDA events on the library's stream bracket the tracked region
+        g.imcfield2d()
+        g.imcvol2d()
+        g.graphics_collect()
+        g.mark(stop=True)
+        fam = {k: g.kernel_time(i) for k, i in FAM.items()}
+        ms = g.kernel_time(7)[0]
+        t = g.tallies()
+        return ms, fam, t
+
+    cyc = 1
+    for _ in range(warmup):
+        step(cyc); cyc += 1
+    if sampler is not None:
+        sampler.start()
+    barrier()
+    dev_ms, hist, launches = 0.0, 0, 0
+    fam_ms = {k: 0.0 for k in FAM}
+    seg = ndx = nev = 0
+    wall0 = time.perf_counter()
+    for _ in range(steps):
+        h0 = g.census_count()
+        ms, fam, t = step(cyc); cyc += 1
+        dev_ms += ms
+        for k, (m, n) in fam.items():
+            fam_ms[k] += m
+            if k not in ("tally_allreduce", "cascade_exchange"):
+                launches += n
+        hist += h0 + (int(P["nsv"].sum()) - rank + world - 1) // world
+        c = t["counters"]
+        seg += c["segments"]; ndx += c["ndxout"]; nev += c["nevents"]
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler is not None else None
+    red = torch.tensor([dev_ms, wall], dtype=torch.float64, device="cuda")
+    cnt = torch.tensor([hist, launches], dtype=torch.float64, device="cuda")
+    per_rank = [dict(fam_ms, device_ms=dev_ms, histories=hist)]
+    if dist is not None:
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
+    dev_ms_max, wall_max = red.tolist()
+    hist_all, launches_all = cnt.tolist()
+    nfl = P["E_field"].size
+    h2d = 8 * sum(int(np.asarray(P[k]).size) for k in ("kappa_tot", "eps_tot", "eps_th", "f_nt", "Pnt", "n_e", "tea",
+                                                       "f_pair", "k_gg", "ewsv", "Eloss_th", "Eloss_tot", "zsurf",
+                                                       "tbbl")) + 4 * P["nsv"].size
+    d2h = 8 * (P["nzone"] * (4 + nfl + P["E_gg"].size) + P["gnt"].size * 2 + 2 * 32 * (P["hu"].size - 1) + 32 * 16 + 64)
+    # algorithmic bytes of the history kernel on this rank (DESIGN.md "bytes per history"): census record read 68 B, census
+    # record written 68 B, deposition RMW 2 x 16 B per zone crossing, census tallies (npcen, ecens, n_field) 3 x 16 B,
+    # escape (erlk, fout, edout RMW + 56 B record)
+    n_in = hist - per_step * steps
+    bytes_all = 68.0 * n_in + 68.0 * ndx + 32.0 * seg + 48.0 * ndx + (48.0 + 56.0) * nev
+    stats = {k: {"min": min(r[k] for r in per_rank) / steps, "mean": sum(r[k] for r in per_rank) / len(per_rank) / steps,
+                 "max": max(r[k] for r in per_rank) / steps} for k in list(FAM) + ["device_ms"]}
+    out = dict(value=hist_all / (dev_ms_max * 1e-3), ms_per_step=dev_ms_max / steps, e2e=hist_all / wall_max,
+               wall_ms_per_step=1e3 * wall_max / steps, histories_per_step=hist_all / steps, launches=int(launches_all),
+               h2d=h2d, d2h=d2h, kernel_ms_per_step={k: fam_ms[k] / steps for k in FAM}, per_rank_ms_per_step=stats,
+               bytes_per_step=bytes_all / steps, hist_kernel_ms=fam_ms["k_history"] / steps, census_in_per_step=n_in / steps,
+               sources_per_step=per_step, counters=t["counters"], clocks=clocks)
+    return g, P, out
+
+
+def our_arm(args):
+    import torch
     from compton2d_b200.host import Compton2d  # noqa: F401  (fails loudly without the CUDA library)
-    from parity_util import make_gpu
-    from synth import make_problem
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -309,83 +404,8 @@ def our_arm(args):
         dist = None
 
     # weak scaling: nst grows with the GPU count, every rank tracks h = rank (mod world)
-    P = make_problem(nz=args.nz, nr=args.nr, nst=args.nst * world, ngroups=args.groups)
-    per_step = int(P["nsv"].sum()) // world + 1
-    cap = int(per_step * (args.steps + args.warmup + 2) * 1.1) + 1000
-    g = make_gpu(P, sigma_mode=args.sigma_mode, census_capacity=cap, event_capacity=max(per_step // 2, 1000),
-                 device=local, rank=rank, world=world, collision_capacity=1 << 18)
-    g.timing(True)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def step(cyc, e2e):
-        """-> (histories of this rank, device ms of the tracked region, host seconds of the whole call)"""
-        t0 = time.perf_counter()
-        if e2e:
-            g.timing_reset()
-        g.imcgen2d(ncycle=cyc, time=cyc * P["dt"], dt=P["dt"], kappa_tot=P["kappa_tot"], eps_tot=P["eps_tot"],
-                   eps_th=P["eps_th"], f_nt=P["f_nt"], Pnt=P["Pnt"], n_e=P["n_e"], tea=P["tea"], f_pair=P["f_pair"],
-                   k_gg=P["k_gg"], nsv=P["nsv"], ewsv=P["ewsv"], Eloss_th=P["Eloss_th"], Eloss_tot=P["Eloss_tot"],
-                   zsurf=P["zsurf"], tbbl=P["tbbl"])
-        if not e2e:
-            g.timing_reset()
-        g.mark()                                   # CUDA events on the library's stream bracket the tracked region
-        g.imcfield2d()
-        g.imcvol2d()
-        g.graphics_collect()
-        g.mark(stop=True)
-        ms = g.kernel_time(7)[0]
-        nl = sum(g.kernel_time(w)[1] for w in (0, 1, 2, 4, 6))
-        t = g.tallies() if e2e else None
-        return ms, nl, time.perf_counter() - t0, t
-
-    cyc = 1
-    for _ in range(args.warmup):
-        step(cyc, False); cyc += 1
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    # ---- timed: K steps, inputs resident (tables uploaded before the timed bracket of each step)
-    barrier()
-    dev_ms, launches, hist = 0.0, 0, 0
-    wall0 = time.perf_counter()
-    hist_ms = coll_ms = s3_ms = s3f_ms = sig_ms = 0.0
-    for _ in range(args.steps):
-        h0 = g.census_count()
-        ms, nl, _, _ = step(cyc, False); cyc += 1
-        hist_ms += g.kernel_time(0)[0]; coll_ms += g.kernel_time(1)[0]; s3_ms += g.kernel_time(2)[0]
-        s3f_ms += g.kernel_time(6)[0]; sig_ms += g.kernel_time(4)[0]
-        dev_ms += ms; launches += nl
-        hist += h0 + (int(P["nsv"].sum()) - rank + world - 1) // world
-    barrier()
-    wall = time.perf_counter() - wall0
-    t_last = g.tallies()
-    # ---- e2e: the same steps through the public call sequence with host buffers: per-step table upload (H2D)
-    #      and tally read-back (D2H) inside the timed region, host wall clock
-    barrier()
-    e_hist, e0 = 0, time.perf_counter()
-    for _ in range(max(1, args.steps // 2)):
-        h0 = g.census_count()
-        step(cyc, True); cyc += 1
-        e_hist += h0 + (int(P["nsv"].sum()) - rank + world - 1) // world
-    barrier()
-    e_wall = time.perf_counter() - e0
-    clocks = sampler.stop() if rank == 0 else None
-
-    red = torch.tensor([dev_ms, wall, e_wall], dtype=torch.float64, device="cuda")
-    cnt = torch.tensor([hist, e_hist, launches], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    dev_ms, wall, e_wall = red.tolist()
-    hist_all, e_hist_all, launches_all = cnt.tolist()
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return
+    sampler = ClockSampler(local) if rank == 0 else None
+    g, P, r = run_tracking(args, dist, rank, world, local, args.nz, args.nr, args.groups, args.nst, args.steps, args.warmup, sampler)
 
     peaks = {}
     try:
@@ -393,54 +413,63 @@ def our_arm(args):
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
-    c = t_last["counters"]
-    nfl = P["E_field"].size
-    # algorithmic bytes of the history kernel per step on this rank (DESIGN.md "bytes per history"):
-    #   census record read 68 B, census record written 68 B, deposition RMW 2 x 16 B per zone crossing,
-    #   census tallies (npcen, ecens, n_field) 3 x 16 B, escape (erlk, fout, edout RMW + 56 B record)
-    n_in = hist / args.steps - per_step
-    seg = c.get("segments", 0) or 1.5 * (hist / args.steps)
-    bytes_step = 68.0 * n_in + 68.0 * c["ndxout"] + 32.0 * seg + 48.0 * c["ndxout"] + (48.0 + 56.0) * c["nevents"]
-    k_ms = hist_ms / max(1, args.steps)
-    achieved = bytes_step / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
-    # DRAM traffic of the same launches: per-history figures measured with ncu (profiles/r01_traffic.json)
-    traffic = None
-    try:
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
-        traffic = tj["k_history_census_dram_bytes_per_history"] * n_in + tj["k_history_volume_dram_bytes_per_history"] * per_step
-    except Exception:
-        pass
-    value = hist_all / (dev_ms * 1e-3)
-    h2d = 8 * sum(int(np.asarray(P[k]).size) for k in ("kappa_tot", "eps_tot", "eps_th", "f_nt", "Pnt", "n_e", "tea",
-                                                       "f_pair", "k_gg", "ewsv", "Eloss_th", "Eloss_tot", "zsurf",
-                                                       "tbbl")) + 4 * P["nsv"].size
-    d2h = 8 * (P["nzone"] * (4 + nfl + P["E_gg"].size) + P["gnt"].size * 2 + 32 * (P["hu"].size - 1 + 16) + 64)
-    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+    k_ms = r["hist_kernel_ms"]
+    achieved = r["bytes_per_step"] / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
+    # DRAM traffic of the same launches: per-history figures measured with ncu (profiles/r02_traffic.json)
+    traffic, tsrc = None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            tj = json.loads((ROOT / "profiles" / name).read_text())
+            traffic = tj["k_history_census_dram_bytes_per_history"] * r["census_in_per_step"] + \
+                tj["k_history_volume_dram_bytes_per_history"] * r["sources_per_step"]
+            tsrc = f"profiles/{name} (ncu dram bytes per history x histories of the step)"
+            break
+        except Exception:
+            pass
+    out = {"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f64", "data": "synthetic", "config": workload_config(args),
-           "histories_per_step": hist_all / args.steps, "trial_flights_per_s": value * 1000,
-           "wall_ms_per_step": 1e3 * wall / args.steps,
-           "e2e": {"value": e_hist_all / e_wall, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-           "gpu_launches": int(launches_all),
-           "kernel_ms_per_step": {"k_history": hist_ms / args.steps, "k_children": coll_ms / args.steps,
-                                  "k_split3_attempts": s3_ms / args.steps, "k_split3_flights": s3f_ms / args.steps,
-                                  "k_sigma_table": sig_ms / args.steps},
+           "histories_per_step": r["histories_per_step"], "trial_flights_per_s": r["value"] * 1000,
+           "wall_ms_per_step": r["wall_ms_per_step"],
+           "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                   "note": "the same K cycles as `value`: host tables uploaded and tallies read back every step, host wall clock"},
+           "gpu_launches": r["launches"],
+           "kernel_ms_per_step": r["kernel_ms_per_step"], "per_rank_ms_per_step": r["per_rank_ms_per_step"],
            "roofline": {"bound": "hbm", "kernel": "k_history", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                        "frac": achieved / hbm, "traffic": traffic,
-                        "traffic_source": "profiles/r01_traffic.json (ncu dram bytes per history x histories of the step)",
+                        "frac": achieved / hbm, "traffic": traffic, "traffic_source": tsrc,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
-                        "bytes_per_step": bytes_step},
-           "counters": c, "clocks": clocks}
-    if not args.no_fp and world == 1:
+                        "bytes_per_step": r["bytes_per_step"],
+                        "note": "instruction-bound kernel (DESIGN.md 4): the HBM fraction is reported because the task asks for it"},
+           "counters": r["counters"], "clocks": r["clocks"]}
+    if rank == 0 and not args.no_fp and world == 1:
+        for leg, fn in (("lc", lambda: lc_bench(g, hbm)),):
+            try:
+                out[leg] = fn()
+            except Exception as e:
+                out[leg] = {"error": repr(e)[:300]}
+    g.close()
+    del g
+    torch.cuda.empty_cache()
+    # BASELINE configs[3] shape (64 x 64 zones, 200 groups, 1.25e8 sources per step and GPU: 1e9 histories per step on 8 GPUs),
+    # a short leg sized so that its census fits HBM next to nothing else
+    if not args.no_c3 and args.workload == "c1":
         try:
-            out["tally"] = tally_bench(g, hbm)
+            a3 = argparse.Namespace(**vars(args))
+            g3, P3, r3 = run_tracking(a3, dist, rank, world, local, 64, 64, 200, args.c3_nst, args.c3_steps, 2)
+            g3.close()
+            del g3
+            torch.cuda.empty_cache()
+            out["c3"] = {"workload": "BASELINE configs[3] shape: 64x64 zones, 200 groups, %d volume sources/step/GPU + census, split 1000/1000/300"
+                                     % (args.c3_nst // 2), "steps": args.c3_steps, "warmup": 2,
+                         "value": r3["value"], "unit": UNIT, "ms_per_step": r3["ms_per_step"], "e2e": r3["e2e"],
+                         "histories_per_step": r3["histories_per_step"], "kernel_ms_per_step": r3["kernel_ms_per_step"],
+                         "per_rank_ms_per_step": r3["per_rank_ms_per_step"]}
         except Exception as e:
-            out["tally"] = {"error": repr(e)[:300]}
-    if not args.no_fp and world == 1:
-        try:
-            out["lc"] = lc_bench(g, hbm)
-        except Exception as e:
-            out["lc"] = {"error": repr(e)[:300]}
+            out["c3"] = {"error": repr(e)[:300]}
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     if not args.no_fp and world == 1:
         try:
             out["fp"] = fp_bench(local, hbm)
@@ -448,10 +477,10 @@ def our_arm(args):
         except Exception as e:                     # the FP leg must never take the headline down with it
             out["fp"] = {"error": repr(e)[:300]}
     if not args.no_cpu_baseline and not args.no_fp and world == 1 and isinstance(out.get("fp"), dict) and "value" in out["fp"]:
-        r = run_reference_sample(1000, ncores=1, warm=0, timed=2, fp=True, nz=4, nr=4)
+        r = run_reference_sample(3000, ncores=1, warm=0, timed=1, fp=True, nz=8, nr=8)
         if r and "fp_zone_steps_per_s" in r:
             out["fp"]["cpu_baseline"] = {"value": r["fp_zone_steps_per_s"], "unit": "zone-steps/s", "cores": 1, "kind": "reference",
-                                         "sample": f"FP farm of cycle 1 of the prebuilt reference binary, 4x4 zones x 200 bins: "
+                                         "sample": f"FP farm of cycle 1 of the prebuilt reference binary, 8x8 zones x 200 bins: "
                                                    f"{r['fp_zone_steps']} zone-steps in {r['fp_seconds']:.1f} s on 1 worker core"}
     if not args.no_cpu_baseline and world == 1:
         r = run_reference_sample(args.cpu_nst, ncores=1, warm=0, timed=2)
@@ -469,8 +498,7 @@ def our_arm(args):
 def legs_only(args):
     """--only fp,lc,tally: the stand-alone kernel legs without the tracking headline (profiling runs)."""
     import torch
-    from parity_util import make_gpu
-    from synth import make_problem
+    from compton2d_b200.synth import context_for as make_gpu, make_problem
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product has no CPU path)")
     peaks = {}
@@ -510,6 +538,9 @@ def main():
     ap.add_argument("--no-fp", action="store_true", help="skip the Fokker-Planck zone-steps/s leg")
     ap.add_argument("--workload", default="c1", choices=["c1", "c3"],
                     help="c1 = BASELINE configs[1] (the bench line); c3 = configs[3] shape, 64x64 zones x 200 groups, 1.25e8 sources/GPU")
+    ap.add_argument("--no-c3", action="store_true", help="skip the short BASELINE configs[3]-shape leg")
+    ap.add_argument("--c3-nst", type=int, default=250_000_000, help="nst per GPU of the configs[3] leg (sources = nst/2)")
+    ap.add_argument("--c3-steps", type=int, default=3)
     ap.add_argument("--only", default="", help="comma list of stand-alone legs (fp, lc, tally) to run instead of the bench line")
     args = ap.parse_args()
     args.nz, args.nr, args.groups = (64, 64, 200) if args.workload == "c3" else (16, 16, 100)

@@ -115,15 +115,9 @@ def oracle_step(o, P, ncycle, time=None, field=True, vol=True, surf=None):
                 census=(d, i, s), events=o.events())
 
 
-def make_gpu(P, rseed=9857, sigma_mode=0, census_capacity=400000, event_capacity=400000, device=0, rank=0, world=1,
-             collision_capacity=65536):
-    from compton2d_b200.host import Compton2d
-    return Compton2d(nz=P["nz"], nr=P["nr"], z=P["z"], r=P["r"], rmin=P["rmin"], zmin=P["zmin"], E_ph=P["E_ph"],
-                     E_field=P["E_field"], E_gg=P["E_gg"], gnt=P["gnt"], hu=P["hu"], Elcmin=P["Elcmin"],
-                     Elcmax=P["Elcmax"], mu=P["mu"], pair_switch=P["pair_switch"], spec_switch=P["spec_switch"], cr_sent=P.get("cr_sent", 0),
-                     E_ref=P.get("E_ref"), P_ref=P.get("P_ref"), W_abs=P.get("W_abs"),
-                     split=P["split"], rseed=rseed, census_capacity=census_capacity, event_capacity=event_capacity,
-                     collision_capacity=collision_capacity, sigma_mode=sigma_mode, device=device, rank=rank, world=world)
+def make_gpu(P, **kw):
+    from compton2d_b200.synth import context_for
+    return context_for(P, **kw)
 
 
 def gpu_step(g, P, ncycle, time=None, field=True, vol=True, surf=None):
