@@ -540,7 +540,7 @@ def main():
                     help="c1 = BASELINE configs[1] (the bench line); c3 = configs[3] shape, 64x64 zones x 200 groups, 1.25e8 sources/GPU")
     ap.add_argument("--no-c3", action="store_true", help="skip the short BASELINE configs[3]-shape leg")
     ap.add_argument("--c3-nst", type=int, default=250_000_000, help="nst per GPU of the configs[3] leg (sources = nst/2)")
-    ap.add_argument("--c3-steps", type=int, default=3)
+    ap.add_argument("--c3-steps", type=int, default=2)
     ap.add_argument("--only", default="", help="comma list of stand-alone legs (fp, lc, tally) to run instead of the bench line")
     args = ap.parse_args()
     args.nz, args.nr, args.groups = (64, 64, 200) if args.workload == "c3" else (16, 16, 100)

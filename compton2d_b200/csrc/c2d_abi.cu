@@ -389,7 +389,9 @@ int begin_common(Ctx *c, int ncycle, double time, double dt)
     CU(cudaMemsetAsync(c->d_i64, 0, c->n_i64 * 8, c->stream));
     // census: last step's output bank becomes this step's input (no 360 MB copy as in imcfield2d.f:96-97) -- sorted by
     // (zone, energy class) into the other bank on the way (c2d_bank.cu), in which case the roles stay as they are
-    const int sorted = bank_sort(c, c->n_census);
+    // (c2d_tally_reduce has usually done it already at the end of the previous step)
+    const int sorted = c->bank_sorted ? 1 : bank_sort(c, c->n_census);
+    c->bank_sorted = false;
     if (sorted < 0) return C2D_ECUDA;
     if (!sorted) c->cur_out ^= 1;
     c->P.out = c->bank[c->cur_out]; c->P.in = c->bank[c->cur_out ^ 1];
@@ -925,6 +927,14 @@ int c2d_tally_reduce(c2d_ctx *h, c2d_tallies *t)
         }
         if (int rc = add_into(c, c->d_fout_total, c->d_f64 + c->t_fout, (size_t)C2D_NMUMAX * c->dims.nphtotal)) return rc;
         c->step_reduced = true;
+        // the step's census is final: sort it by (zone, energy class) for the next step's re-tracking (c2d_bank.cu) while
+        // it is still this step's cost
+        if (c->step_open && !c->bank_sorted) {
+            if (int rc = latch_census(c)) return rc;
+            const int sorted = bank_sort(c, c->n_census);
+            if (sorted < 0) return C2D_ECUDA;
+            c->bank_sorted = sorted == 1;
+        }
         CU(cudaStreamSynchronize(c->stream));
     }
     return t ? c2d_tally_read(h, t) : 0;
@@ -954,7 +964,7 @@ int c2d_census_export(c2d_ctx *h, double *dbuf, int32_t *ibuf, uint64_t *sid, in
     if (n_out) *n_out = n;
     if (n > cap) return fail(C2D_EINVAL, "export buffer holds %lld records, census has %lld", (long long)cap, (long long)n);
     if (n == 0) return 0;
-    const Bank &b = c->bank[c->cur_out];
+    const Bank &b = c->bank[c->bank_sorted ? c->cur_out ^ 1 : c->cur_out];
     std::vector<double> col(n);
     const double *cols[6] = {b.rpre, b.zpre, b.wmu, b.phi, b.ew, b.xnu};
     if (dbuf)
@@ -997,6 +1007,7 @@ int c2d_census_import(c2d_ctx *h, const double *dbuf, const int32_t *ibuf, const
     // between steps the photons go where the last step left its census; right after c2d_step_begin (banks swapped, count
     // latched, nothing tracked yet) they are this step's census input
     const bool into_input = c->step_open && !c->step_tracked;
+    c->bank_sorted = c->bank_sorted && into_input;                // a census imported between steps replaces the sorted copy
     Bank &b = into_input ? c->bank[c->cur_out ^ 1] : c->bank[c->cur_out];
     if (n) {
         std::vector<double> col(n);

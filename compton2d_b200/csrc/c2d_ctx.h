@@ -64,6 +64,7 @@ struct Ctx {
     int cur_out = 0, q_cur = 0;
     // census bank sort (c2d_bank.cu) and the absorption-draw queue of k_history (c2d_track.cu)
     bool sort_bank = true;                 // C2D_SORT_BANK=0 keeps the bank in arrival order (A/B measurements)
+    bool bank_sorted = false;              // the census lives sorted in bank[cur_out ^ 1] (c2d_tally_reduce did it)
     unsigned long long *d_sortkeys = nullptr;
     unsigned long long *d_cnt3 = nullptr;  // cascade counts: [mine x3 | all ranks]
     CollTask *d_q3_all = nullptr;          // all-gathered 3rd-split tasks

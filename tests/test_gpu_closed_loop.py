@@ -130,7 +130,10 @@ def test_configs0_as_shipped_matches_reference_binary():
         g.close()
     # the photon budget is deterministic: every source photon of cycle 0 is banked unflown (quirk_cycle0)
     assert reps[0]["n_volume"] == ref_census[0] == 399870 and census[0] == ref_census[0]
-    assert [r["n_volume"] for r in reps[1:]] == [int(gd.snap(f"c{c}_C").nsv.sum()) for c in (1, 2)]
+    ref_nvol = [int(gd.snap(f"c{c}_C").nsv.sum()) for c in (1, 2)]
+    assert reps[1]["n_volume"] == ref_nvol[0]                     # same plasma as cycle 0
+    assert abs(reps[2]["n_volume"] - ref_nvol[1]) <= 30           # after an update: nsv = int(0.5 nst Eloss / sum) per zone moves with the
+                                                                  # tallied photon field that cooled the electrons (270 truncations)
     # census after cycles 1, 2: sources + survivors; the random part is the number that escaped (Poisson) -- the scattered
     # children that reach census are a few correlated thousands, inside the 6 sigma
     for c in (1, 2):
