@@ -112,6 +112,17 @@ class StepReport(C.Structure):
         [("ms", C.c_double * 12)]
 
 
+class Common(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("jmax", "kmax", "ntmax", "nmumax", "nphomax", "nphlcmax", "ti")] + \
+        [(n, dp) for n in ("kappa_tot", "eps_tot", "eps_th", "f_nt", "Pnt", "n_e", "tea", "tna", "B_field", "f_pair", "k_gg")] + \
+        [("nsv", ip)] + [(n, dp) for n in ("ewsv", "Eloss_th", "Eloss_tot", "zsurf", "tbbl", "edep", "prdep", "ecens")] + \
+        [("npcen", ip)] + [(n, dp) for n in ("n_field", "n_ph", "E_IC")] + [("nelectron", ip)] + \
+        [(n, dp) for n in ("fout", "edout", "erlki", "erlko", "erlku", "erlkl", "Ed_in", "Ed_ref")] + \
+        [(n, ip) for n in ("ndxout", "cmcount1", "cmcount2", "lkcount")] + \
+        [(n, dp) for n in ("vol", "Eloss_sy", "ec_old", "turb_lev", "gmin", "gmax", "p_nth", "amxwl", "Te_new", "dT_max", "E_tot_old",
+                           "E_tot_new", "hr_total", "hr_st_total", "dr", "dz", "f_t_implicit")]
+
+
 ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p)
 ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
@@ -142,7 +153,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_lc_select", "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar",
            "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7", "c2d_tally_reduce", "c2d_finalize",
            "c2d_comm_unique_id", "c2d_comm_init", "c2d_comm_init_ext", "c2d_comm_info", "c2d_comm_destroy",
-           "c2d_plasma_set", "c2d_plasma_get", "c2d_step"]
+           "c2d_plasma_set", "c2d_plasma_get", "c2d_step", "c2d_common_step_begin", "c2d_common_collect", "c2d_common_update"]
 
 _lib = None
 
@@ -209,6 +220,9 @@ def load():
     L.c2d_plasma_set.argtypes = [vp, C.POINTER(Plasma)]
     L.c2d_plasma_get.argtypes = [vp, C.POINTER(PlasmaOut)]
     L.c2d_step.argtypes = [vp, C.POINTER(Run), C.c_int, C.c_double, C.c_double, C.POINTER(StepReport)]
+    L.c2d_common_step_begin.argtypes = [vp, C.POINTER(Common), C.c_int, C.c_double, C.c_double]
+    L.c2d_common_collect.argtypes = [vp, C.POINTER(Common)]
+    L.c2d_common_update.argtypes = [vp, C.POINTER(Common), C.POINTER(FpIn)]
     for fn in ("c2d_pack_bin_first", "c2d_unpack_bin_first"):
         getattr(L, fn).argtypes = [vp] + [C.c_int] * 6 + [vp]
         getattr(L, fn).restype = None

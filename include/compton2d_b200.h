@@ -395,6 +395,53 @@ int c2d_step(c2d_ctx *ctx, const c2d_run *run, int ncycle, double time, double d
         /* collective when c2d_comm_init was called with world > 1.  The host advances the clock as xec does
            (xec2d.f:94-103): if ncycle > 0 then time += dt; ncycle += 1. */
 
+/* ---- the COMMON-block side: what a Fortran shim hands over --------------------------------------------
+ * Addresses of the reference's COMMON members as they lie (column-major, padded compile-time extents of general.pa:7-31;
+ * a(jmax,kmax): element (j,k) at (k-1) jmax + (j-1); a(nbin,jmax,kmax) and a(jmax,kmax,nbin) likewise) -- `c_loc(edep)` etc.
+ * from integration/c2d_shim.f90.  Members that are NULL are skipped.  The three calls pack into the dense layout above, call
+ * the entry points above and scatter the results back where the reference's own subroutines leave them. */
+typedef struct {
+    int jmax, kmax, ntmax;                    /* general.pa:10-12 (99, 99, 100) */
+    int nmumax, nphomax, nphlcmax;            /* general.pa:20-22 (32, 128, 10) */
+    int ti;                                   /* current time interval of the boundary temperatures (1-based; imcgen2d.f:113-119) */
+    /* step inputs: what imcgen2d leaves for the tracker */
+    const double *kappa_tot, *eps_tot, *eps_th;   /* (n_vol, jmax, kmax)   /vol_em/ */
+    double *f_nt, *Pnt;                       /* (jmax, kmax, num_nt)  /Pnth/           (in; out of c2d_common_update) */
+    double *n_e, *tea;                        /* (jmax, kmax)          /zone_quantities/ (in; out of c2d_common_update) */
+    const double *tna, *B_field;              /* (jmax, kmax) */
+    double *f_pair;                           /* (jmax, kmax) */
+    const double *k_gg;                       /* (n_gg, jmax, kmax) */
+    const int32_t *nsv;                       /* (jmax, kmax) */
+    const double *ewsv, *Eloss_th, *Eloss_tot, *zsurf;   /* (jmax, kmax) */
+    const double *tbbl;                       /* (kmax, ntmax): column ti is used */
+    /* tallies: where cens_add_up / E_add_up / xec_add / graphics_collect leave them on the master */
+    double *edep, *prdep, *ecens;             /* (jmax, kmax) */
+    int32_t *npcen;                           /* (jmax, kmax) */
+    double *n_field;                          /* (nphfield, jmax, kmax) */
+    double *n_ph;                             /* (n_gg, jmax, kmax) */
+    double *E_IC;                             /* (num_nt) */
+    int32_t *nelectron;                       /* (num_nt) */
+    double *fout;                             /* (nmumax, nphomax): the run-long sum (xec2d.f:389-394) */
+    double *edout;                            /* (nmumax, nphlcmax) */
+    double *erlki, *erlko;                    /* (jmax) */
+    double *erlku, *erlkl, *Ed_in, *Ed_ref;   /* (kmax) */
+    int32_t *ndxout, *cmcount1, *cmcount2, *lkcount;   /* scalars of /counters/ etc. */
+    /* Fokker-Planck */
+    const double *vol, *Eloss_sy, *ec_old, *turb_lev;    /* (jmax, kmax) */
+    double *gmin, *gmax, *p_nth, *amxwl, *Te_new;        /* (jmax, kmax)  /nontherm/, /d_update/ */
+    double *dT_max, *E_tot_old, *E_tot_new, *hr_total, *hr_st_total, *dr, *dz, *f_t_implicit;   /* scalars */
+} c2d_common;
+
+int c2d_common_step_begin(c2d_ctx *ctx, const c2d_common *cm, int ncycle, double time, double dt);
+        /* pack + c2d_step_begin: called by the shim's imcfield2d (the first tracking subroutine xec calls, xec2d.f:71,167) */
+int c2d_common_collect(c2d_ctx *ctx, c2d_common *cm);
+        /* c2d_tally_reduce + scatter into COMMON: the shim's graphics_collect (xec2d.f:91,183; also stands in for xec_add,
+           cens_add_up and E_add_up, whose sums it delivers) */
+int c2d_common_update(c2d_ctx *ctx, c2d_common *cm, const c2d_fp_in *scalars);
+        /* the shim's update (update2d.f:7-334): FP_calc for every zone from the reduced tallies in HBM; scalars = the
+           non-pointer members of c2d_fp_in, i.e. what FP_bcast ships (fp_mpi.f:579-600); f_nt, Pnt, n_e, tea, gmin, gmax, p_nth, amxwl, Te_new
+           and the sums of E_add_up land in COMMON */
+
 /* ---- COMMON <-> dense packing helpers (host code) ------------------------------------------- */
 void c2d_pack_bin_first(const double *common, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *dense);
 void c2d_pack_bin_last(const double *common, int jmax, int kmax, int nbin, int nz, int nr, double *dense);

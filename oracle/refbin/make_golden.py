@@ -253,6 +253,15 @@ def main(name):
         out["events_t_hist"] = np.histogram(ev[:, 0], bins=64)[0]; out["events_t_edges"] = np.histogram(ev[:, 0], bins=64)[1]
         out["events_lnE_hist"], out["events_lnE_edges"] = np.histogram(np.log10(ev[:, 1]), bins=np.linspace(-10, 12, 89))
         out["events_lnE_ew"] = np.histogram(np.log10(ev[:, 1]), bins=np.linspace(-10, 12, 89), weights=ev[:, 2])[0]
+        # unscattered (synchrotron) escapes: source photons carry the zone's ewsv and soft energies, Compton children are far
+        # lighter or far harder (tests/test_statistical_parity.py:_is_unscattered); per cycle by t_bound
+        w_med = float(np.median(ev[:, 2])); dt1 = float(out[[k for k in out if k.endswith("/dt")][-1]][0])
+        heavy = (ev[:, 2] > 0.3 * w_med) & (ev[:, 2] < 3.0 * w_med) & (ev[:, 1] < 10.0)
+        in_cyc = lambda c: (ev[:, 0] >= (c - 1) * dt1) & (ev[:, 0] < c * dt1)
+        out["events_w_median"] = np.array(w_med); out["events_unscattered_count"] = np.array(int(heavy.sum()))
+        out["events_unscattered_sum_ew"] = np.array(float(ev[heavy, 2].sum()))
+        out["events_unscattered_per_cycle"] = np.array([int((heavy & in_cyc(c)).sum()) for c in (1, 2)])
+        out["events_per_cycle"] = np.array([int(in_cyc(c).sum()) for c in (1, 2)])
         ev = ev[: cfg["events_head"]]
     out["events"] = ev
     if cfg.get("keep_logs"):

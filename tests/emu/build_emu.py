@@ -13,7 +13,8 @@ LIB = HERE / "libc2d_emu.so"
 def build(force=False):
     srcs = [HERE / "emu_launch.cpp", ROOT / "compton2d_b200/csrc/c2d_abi.cu", ROOT / "compton2d_b200/csrc/c2d_fp.cu", ROOT / "compton2d_b200/csrc/c2d_tally.cu",
             ROOT / "compton2d_b200/csrc/c2d_lc.cu", ROOT / "compton2d_b200/csrc/c2d_io.cu", ROOT / "compton2d_b200/csrc/c2d_step.cu",
-            ROOT / "compton2d_b200/csrc/c2d_comm.cu", ROOT / "compton2d_b200/csrc/c2d_bank.cu"]
+            ROOT / "compton2d_b200/csrc/c2d_comm.cu", ROOT / "compton2d_b200/csrc/c2d_bank.cu",
+            ROOT / "compton2d_b200/csrc/c2d_common.cu"]
     deps = srcs + list((ROOT / "compton2d_b200/csrc").glob("*")) + [HERE / "fake/cuda_runtime.h"]
     if not force and LIB.exists() and LIB.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
         return LIB

@@ -63,7 +63,9 @@ def test_struct_layouts_match_header(lib):
         return names
 
     for cls, name in ((L.Dims, "c2d_dims"), (L.StepIn, "c2d_step_in"), (L.Tallies, "c2d_tallies"), (L.FpIn, "c2d_fp_in"),
-                      (L.FpOut, "c2d_fp_out"), (L.LcConfig, "c2d_lc_config"), (L.GenIn, "c2d_gen_in"), (L.SurfIn, "c2d_surf_in")):
+                      (L.FpOut, "c2d_fp_out"), (L.LcConfig, "c2d_lc_config"), (L.GenIn, "c2d_gen_in"), (L.SurfIn, "c2d_surf_in"),
+                      (L.Plasma, "c2d_plasma"), (L.PlasmaOut, "c2d_plasma_out"), (L.SurfRun, "c2d_surf_run"), (L.Run, "c2d_run"),
+                      (L.StepReport, "c2d_step_report"), (L.Common, "c2d_common")):
         assert [f[0] for f in cls._fields_] == fields(name), name
 
 
