@@ -143,17 +143,20 @@ def test_configs0_as_shipped_matches_reference_binary():
     assert reps[1]["n_volume"] == ref_nvol[0]                     # same plasma as cycle 0
     assert abs(reps[2]["n_volume"] - ref_nvol[1]) <= 30           # after an update: nsv = int(0.5 nst Eloss / sum) per zone moves with the
                                                                   # tallied photon field that cooled the electrons (270 truncations)
-    # The UNSCATTERED photons (~4e5 independent histories per cycle) are the Poisson part: the number that escaped per cycle, and
-    # with it the unscattered census  c_u[c] = c_u[c-1] + n_volume - escaped_u[c]  (a photon that collides keeps flying with the
-    # un-collided (split1 - nscat) / split1 of its weight).  Binary: 24 306 / 36 429 escapes.
-    ref_esc_u = [int(x) for x in gd.d["events_unscattered_per_cycle"]]
-    for i, c in enumerate((1, 2)):
-        assert abs(esc_u[c] - ref_esc_u[i]) < 5.0 * np.sqrt(esc_u[c] + ref_esc_u[i]), (c, esc_u[c], ref_esc_u[i])
-    ref_cens_u = ref_census[0]
-    for i, c in enumerate((1, 2)):
-        ref_cens_u = ref_cens_u + ref_nvol[i] - ref_esc_u[i]
-        assert abs(cens_u[c] - ref_cens_u) < 5.0 * np.sqrt(2.0 * ref_esc_u[i]) + 60, (c, cens_u[c], ref_cens_u)
-    assert abs(sum_ew_u / float(gd.d["events_unscattered_sum_ew"]) - 1.0) < 5.0 * np.sqrt(2.0 / sum(ref_esc_u)) + 5e-3
+    # The UNSCATTERED photons (~4e5 independent histories per cycle) are the Poisson part: how many escaped, and with that the
+    # unscattered census c_u = sources - escaped_u (a photon that collides keeps flying with the un-collided (split1 - nscat) /
+    # split1 of its weight).  Binary: 60 735 unscattered escape records over cycles 1-2.  Compared over BOTH cycles: the
+    # binary's records cannot be split by cycle from their t_bound -- a photon leaving through the lower face is written with
+    # the t_bound of the previous escape (imcleak2d.f:171, DESIGN.md deviation 1), and cycle 2 starts with ~1 500 lower-face
+    # escapes from the bottom row of zones; its leak counts per cycle (lkcount 25 751 / 39 114) include the Compton children.
+    ref_esc_u = int(gd.d["events_unscattered_count"])
+    got_esc_u = esc_u[1] + esc_u[2]
+    assert abs(got_esc_u - ref_esc_u) < 5.0 * np.sqrt(got_esc_u + ref_esc_u), (esc_u, ref_esc_u)
+    ref_lk = [int(gd.snap(f"c{c}_D").lkcount) for c in (1, 2)]
+    unrecorded = sum(ref_lk) - ref_events                         # leaks without a record: upper face, wmu >= 0.98 (imcleak2d.f:303)
+    ref_cens_u = ref_census[0] + sum(ref_nvol) - ref_esc_u - unrecorded
+    assert abs(cens_u[2] - ref_cens_u) < 5.0 * np.sqrt(2.0 * ref_esc_u) + 0.1 * unrecorded + 60, (cens_u, ref_cens_u)
+    assert abs(sum_ew_u / float(gd.d["events_unscattered_sum_ew"]) - 1.0) < 5.0 * np.sqrt(2.0 / ref_esc_u) + 5e-3
     # The census and the event list as a whole (the golden 860 676 / 1 343 819 / 64 350) also hold the Compton children: 23 and 33
     # primary collisions in the binary's cycles 1 and 2 fanned out into 86 687 and 122 401 correlated children (split2 = 1000,
     # split3 = 300).  That is a compound Poisson number with a relative spread of ~ 2 / sqrt(primaries); the totals must agree
