@@ -137,6 +137,12 @@ def test_configs0_as_shipped_matches_reference_binary():
         plasma = g.plasma_get()
     finally:
         g.close()
+    # replay: the CPU oracle ran the same closed loop at this size once (tests/golden/oracle_c0_replay.json, ~10 min): every
+    # integer of cycle 1 must be the same on the device (sigma_mode 1 here against the oracle's bin-by-bin comtot)
+    import json
+    orc1 = json.loads((GOLD / "oracle_c0_replay.json").read_text())["cycle1"]
+    assert (reps[1]["ndxout"], reps[1]["nevents"], reps[1]["cmcount1"], reps[1]["cmcount2"], esc_u[1]) == \
+        (orc1["ndxout"], orc1["nevents"], orc1["cmcount1"], orc1["cmcount2"], orc1["unscattered_escapes"])
     # the photon budget is deterministic: every source photon of cycle 0 is banked unflown (quirk_cycle0)
     assert reps[0]["n_volume"] == ref_census[0] == 399870 and census[0] == ref_census[0]
     ref_nvol = [int(gd.snap(f"c{c}_C").nsv.sum()) for c in (1, 2)]
