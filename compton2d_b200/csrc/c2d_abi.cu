@@ -101,50 +101,69 @@ static int drain_queue(Ctx *c)
     if (!c->d_cnt3) {
         CU(cudaMalloc(&c->d_cnt3, (size_t)(3 + 3 * 8) * 8));
     }
+    auto gather_counts = [&](const unsigned long long *dev_count, unsigned long long *h, int fam) -> int {
+        unsigned long long *mine = c->d_cnt3, *all = c->d_cnt3 + 3;
+        CU(cudaMemcpyAsync(mine, dev_count, 8, cudaMemcpyDeviceToDevice, c->stream));
+        if (world > 1) { c->timer_begin(fam); int rc = comm_allgather(c, mine, all, 8); c->timer_end(); if (rc) return rc; }
+        else CU(cudaMemcpyAsync(all, mine, 8, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(h, all, (size_t)world * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return 0;
+    };
+    // the tasks of all ranks, rank r's at slot r (n_max each); one rank: the queue itself
+    auto gather_tasks = [&](const CollTask *mine_q, const unsigned long long *h, S3Map &m) -> int {
+        memset(&m, 0, sizeof m);
+        m.world = world; m.rank = rank;
+        unsigned long long n_max = 0;
+        for (int r = 0; r < world; r++) { m.prefix[r + 1] = m.prefix[r] + (long long)h[r]; n_max = std::max(n_max, h[r]); }
+        if (world == 1) { m.base = mine_q; m.stride = (long long)h[0]; return 0; }
+        const size_t need = (size_t)world * n_max;
+        if (need > c->q3all_cap) {
+            cudaFree(c->d_q3_all); c->d_q3_all = nullptr; c->q3all_cap = 0;
+            CU(cudaMalloc(&c->d_q3_all, need * sizeof(CollTask)));
+            c->q3all_cap = need;
+        }
+        c->timer_begin(10);
+        int rc = comm_allgather(c, mine_q, c->d_q3_all, (size_t)n_max * sizeof(CollTask));
+        c->timer_end();
+        if (rc) return rc;
+        m.base = c->d_q3_all; m.stride = (long long)n_max;
+        return 0;
+    };
     for (int gen = 0; gen < 1000; gen++) {
         const int other = c->q_cur ^ 1;
         Params p = c->P;
         p.q_out = c->d_q[other]; p.q_out_count = c->d_qcount + other;
-        c->timer_begin(1);
-        launch_children(p, c->d_q[c->q_cur], c->d_qcount + c->q_cur, c->n_sm, c->stream);
-        c->timer_end();
-        CU(cudaGetLastError());
-        // [collisions processed, 3rd-split tasks] of every rank
-        unsigned long long *mine = c->d_cnt3, *all = c->d_cnt3 + 3;
-        CU(cudaMemcpyAsync(mine, c->d_qcount + c->q_cur, 8, cudaMemcpyDeviceToDevice, c->stream));
-        CU(cudaMemcpyAsync(mine + 1, c->d_qcount + 2, 8, cudaMemcpyDeviceToDevice, c->stream));
-        if (world > 1) { c->timer_begin(10); int rc = comm_allgather(c, mine, all, 16); c->timer_end(); if (rc) return rc; }
-        else CU(cudaMemcpyAsync(all, mine, 16, cudaMemcpyDeviceToDevice, c->stream));
-        unsigned long long h[16];
-        CU(cudaMemcpyAsync(h, all, (size_t)world * 16, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        unsigned long long n_any = 0, n3_tot = 0, n3_max = 0;
-        for (int r = 0; r < world; r++) { n_any += h[2 * r]; n3_tot += h[2 * r + 1]; n3_max = std::max(n3_max, h[2 * r + 1]); }
-        const unsigned long long n = h[2 * rank], n3 = h[2 * rank + 1];
-        if (n > (unsigned long long)c->q_cap)
-            return fail(C2D_EINVAL, "collision queue overflow: %llu tasks > collision_capacity %lld", n, (long long)c->q_cap);
+        // this generation's collisions on every rank (the first look of a step is where a rank waits for the others' history
+        // kernels: that wait is part of family 10's time)
+        unsigned long long h[8];
+        if (int rc = gather_counts(c->d_qcount + c->q_cur, h, 10)) return rc;
+        unsigned long long n_tot = 0, n3_tot = 0;
+        for (int r = 0; r < world; r++) {
+            if (h[r] > (unsigned long long)c->q_cap)
+                return fail(C2D_EINVAL, "collision queue overflow: %llu tasks > collision_capacity %lld", h[r], (long long)c->q_cap);
+            n_tot += h[r];
+        }
+        if (n_tot == 0) return 0;                                  // no rank has a collision left: the cascade has ended
+        c->q_peak = std::max<long long>(c->q_peak, (long long)h[rank]);
+        {
+            S3Map mq;
+            if (int rc = gather_tasks(c->d_q[c->q_cur], h, mq)) return rc;
+            const long long G = (long long)n_tot * p.split2;
+            const long long n_mine = (G > rank) ? (G - rank + world - 1) / world : 0;
+            c->timer_begin(1);
+            launch_children(p, mq, n_mine, c->n_sm, c->stream);
+            c->timer_end();
+            CU(cudaGetLastError());
+        }
+        if (int rc = gather_counts(c->d_qcount + 2, h, 10)) return rc;
+        unsigned long long n3_max = 0;
+        for (int r = 0; r < world; r++) { n3_tot += h[r]; n3_max = std::max(n3_max, h[r]); }
         if (n3_max > (unsigned long long)c->q_cap)
             return fail(C2D_EINVAL, "split3 queue overflow: %llu tasks > collision_capacity %lld", n3_max, (long long)c->q_cap);
-        if (n_any == 0) return 0;                                  // no rank had a collision left: the cascade has ended
-        c->q_peak = std::max<long long>(c->q_peak, (long long)n);
         if (n3_tot) {
             S3Map m;
-            memset(&m, 0, sizeof m);
-            m.world = world; m.rank = rank;
-            for (int r = 0; r < world; r++) m.prefix[r + 1] = m.prefix[r] + (long long)h[2 * r + 1];
-            if (world > 1) {
-                const size_t need = (size_t)world * n3_max;
-                if (need > c->q3all_cap) {
-                    cudaFree(c->d_q3_all); c->d_q3_all = nullptr; c->q3all_cap = 0;
-                    CU(cudaMalloc(&c->d_q3_all, need * sizeof(CollTask)));
-                    c->q3all_cap = need;
-                }
-                c->timer_begin(10);
-                int rc = comm_allgather(c, c->d_q3, c->d_q3_all, (size_t)n3_max * sizeof(CollTask));
-                c->timer_end();
-                if (rc) return rc;
-                m.base = c->d_q3_all; m.stride = (long long)n3_max;
-            } else { m.base = c->d_q3; m.stride = (long long)n3; }
+            if (int rc = gather_tasks(c->d_q3, h, m)) return rc;
             // this rank's sub-children: global sub-child rank, rank + world, ...
             const long long G = (long long)n3_tot * p.split3;
             const long long n_mine = (G > rank) ? (G - rank + world - 1) / world : 0;

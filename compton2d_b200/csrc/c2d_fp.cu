@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace c2d {
@@ -37,6 +38,8 @@ struct FpParams {
     const double *gtab;            // gamma_bar on a uniform grid in ln(Theta): the predictor of the temperature search
     int gtab_n;
     double gtab_x0, gtab_ih;       // first node, 1 / spacing
+    unsigned long long *gc_key;    // memo of the quadrature: gamma_bar is a pure function of the bits of Theta, and the zones of
+    double *gc_val;                // a run walk the SAME temperature lattice (c2d_fp.cu:gamma_bar_memo); kGcSlots entries
     // per zone, in
     const double *f_nt_in, *Pnt_in, *n_field, *ecens, *n_e_in, *B_field, *tea, *tna, *vol, *f_pair_in, *Eloss_sy,
         *ec_old, *turb_lev;
@@ -54,7 +57,10 @@ struct FpState {
     double *d_gtab = nullptr;     // [kGtabN] gamma_bar(exp(x0 + i h)), built once by k_gbar_table
     double *d_FICt = nullptr;     // [nf][N]
     double *d_quad = nullptr;     // [kQuadRounds * 32]: (ts^2-1)^(3/2)
+    unsigned long long *d_gc_key = nullptr;   // gamma_bar memo (kGcSlots keys / values), kept for the life of the context
+    double *d_gc_val = nullptr;
 };
+constexpr int kGcSlots = 1 << 16;
 constexpr int kQuadRounds = 1024;                                 // 32768 lattice points t = 1.001^n: covers z >= 1e-12
 constexpr int kGtabN = 640;
 constexpr double kGtabX0 = -1.7, kGtabH = 0.02;                   // Theta = 0.183 ... 6.5e4
@@ -167,6 +173,39 @@ __device__ double warp_gamma_bar(double Theta, int lane, const QuadTab tab, bool
     return g;
 }
 
+// gamma_bar through a memo.  The quadrature is a pure function of the BITS of Theta, the electron temperatures of a run
+// live on a few lattices Theta_0 * 1.005^n (update2d.f:1446-1463; every zone that hits the 5 / 1000 keV clamp of
+// update2d.f:268-274 restarts from the same Theta_0), and the walk of one sub-step re-evaluates points its neighbours and
+// its own previous sub-steps already evaluated: measured, the quadrature was 40 % of the kernel's instructions.  A hit
+// returns the value the quadrature itself produced for exactly this argument -- bit-identical, no tolerance involved.
+// Open addressing in global memory; a slot whose value has not landed yet reads as a miss.
+__device__ double gamma_bar_memo(const FpParams &q, double Theta, int lane, const QuadTab tab)
+{
+    if (Theta < (double)0.2f || !q.gc_key) return warp_gamma_bar(Theta, lane, tab);
+    const unsigned long long key = (unsigned long long)__double_as_longlong(Theta);
+    unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    unsigned slot = (unsigned)h & (kGcSlots - 1);
+    double g = 0.0;
+    int found = -1;                                               // lane 0 probes, the warp follows
+    if (lane == 0) {
+        for (int k = 0; k < 8; k++) {
+            const unsigned long long kk = *((volatile unsigned long long *)(q.gc_key + slot));
+            if (kk == key) { g = *((volatile double *)(q.gc_val + slot)); found = (g != 0.0) ? 1 : 0; break; }
+            if (kk == 0ull) { found = -1 - (int)k; break; }
+            slot = (slot + 1) & (kGcSlots - 1);
+            found = -100;                                         // probe sequence exhausted: compute, do not insert
+        }
+    }
+    found = __shfl_sync(0xffffffffu, found, 0);
+    if (found == 1) return __shfl_sync(0xffffffffu, g, 0);
+    g = warp_gamma_bar(Theta, lane, tab);
+    if (lane == 0 && found < 0 && found > -100) {
+        if (atomicCAS(q.gc_key + slot, 0ull, key) == 0ull) *((volatile double *)(q.gc_val + slot)) = g;
+    }
+    return g;
+}
+
 // the quadrature lattice: lane l of round r holds t = 1.001^l (l sequential products) times (1.001^32)^r (r products)
 __global__ void k_quad_table(double *x15_out, int rounds)
 {
@@ -199,16 +238,43 @@ __device__ __forceinline__ double theta_lattice(double Theta0, int n)
     return t;
 }
 
+// The same lattice with check points: lane L keeps Theta_0 * c^(32 L) (the same sequential products), so a point costs a
+// shuffle and at most 31 multiplications instead of n.  Built once per search; covers |n| < 1024, beyond it falls back.
+struct ThetaLattice {
+    double Theta0, ckpt;
+    int dir;
+    __device__ __forceinline__ void build(double t0, int d, int lane)
+    {
+        const double c = (double)1.005f;
+        Theta0 = t0; dir = d;
+        double t = t0;
+        ckpt = t0;
+        if (d < 0) return;                                        // cooling walks are short (and a division per step): direct
+        for (int i = 1; i <= 32 * 31; i++) {
+            t = t * c;
+            if (i == 32 * lane) ckpt = t;
+        }
+    }
+    __device__ __forceinline__ double at(int n) const          // n >= 0 steps in direction dir; every lane calls
+    {
+        if (n >= 1024 || dir < 0) return theta_lattice(Theta0, dir * n);
+        const double c = (double)1.005f;
+        double t = __shfl_sync(0xffffffffu, ckpt, n >> 5);
+        for (int i = 0; i < (n & 31); i++) t = t * c;
+        return t;
+    }
+};
+
 // First n >= 1 on the temperature lattice at which the reference's walk stops (update2d.f:1446-1463):
 //   dir = +1: Theta_n = Theta_0 * 1.005^n, stop when !(gbar > gamma_bar(Theta_n))
 //   dir = -1: Theta_n = Theta_0 / 1.005^n, stop when !(gbar < gamma_bar(Theta_n)) or Theta_n < 1e-2
 // gamma_bar is monotone on the lattice, so "stops at n" is monotone in n and a bracketing search started
 // at `guess` returns the same n as the step-by-step walk.
-__device__ int lattice_search(int dir, double Th_e, double gbar, int guess, int lane, const QuadTab tab, double &g_out)
+__device__ int lattice_search(const FpParams &q, const ThetaLattice &L, int dir, double gbar, int guess, int lane, const QuadTab tab, double &g_out)
 {
     auto stops = [&](int n, double &g) {
-        const double th = theta_lattice(Th_e, dir * n);
-        g = warp_gamma_bar(th, lane, tab);
+        const double th = L.at(n);
+        g = gamma_bar_memo(q, th, lane, tab);
         return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
     };
     int lo = 0, hi = -1, n = max(1, guess), s = 1;
@@ -262,10 +328,10 @@ __device__ double gamma_bar_approx(const FpParams &q, double Theta, bool &in_tab
 }
 
 // lattice_search with the predictor in place of the quadrature: the n the exact search will most likely return
-__device__ int lattice_predict(const FpParams &q, int dir, double Th_e, double gbar, int guess)
+__device__ int lattice_predict(const FpParams &q, const ThetaLattice &L, int dir, double gbar, int guess)
 {
     auto stops = [&](int n) {
-        const double th = theta_lattice(Th_e, dir * n);
+        const double th = L.at(n);
         bool in_table;
         const double g = gamma_bar_approx(q, th, in_table);
         return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
@@ -306,26 +372,28 @@ __device__ double temperature_search(const FpParams &q, double Th_e, double g_av
         const double tstar = gbar / 2.985;                          // K3/K2 - Theta -> 3 Theta for Theta >> 1
         if (tstar > Th_e) guess = max(1, (int)(log(tstar / Th_e) / log((double)1.005f)));
     }
-    int n = lattice_predict(q, dir, Th_e, gbar, guess);
+    ThetaLattice L;
+    L.build(Th_e, dir, lane);
+    int n = lattice_predict(q, L, dir, gbar, guess);
     const QuadTab tab{q.qt_x15};
     auto stops = [&](int m, double &g) {
-        const double th = theta_lattice(Th_e, dir * m);
-        g = warp_gamma_bar(th, lane, tab);
+        const double th = L.at(m);
+        g = gamma_bar_memo(q, th, lane, tab);
         return (dir > 0) ? !(gbar > g) : (!(gbar < g) || th < 1.e-2);
     };
     // the walk must not stop at n - 1: confirmed by the quadrature unless the predictor clears gbar by kGtabMargin there
     bool sure_m = false;
     if (n > 1) {
         bool in_table;
-        const double g_pred = gamma_bar_approx(q, theta_lattice(Th_e, dir * (n - 1)), in_table);
+        const double g_pred = gamma_bar_approx(q, L.at(n - 1), in_table);
         sure_m = in_table && fabs(g_pred - gbar) > kGtabMargin * gbar;
     }
     double g_n, g_m;
     bool ok = stops(n, g_n);                                      // the exact value at n is the next sub-step's g_av
     if (ok && n > 1 && !sure_m) ok = !stops(n - 1, g_m);
     if (ok) g_av_out = g_n;
-    else n = lattice_search(dir, Th_e, gbar, n, lane, tab, g_av_out);
-    return theta_lattice(Th_e, dir * n);
+    else n = lattice_search(q, L, dir, gbar, n, lane, tab, g_av_out);
+    return L.at(n);
 }
 
 // one warp per node of the predictor table
@@ -440,7 +508,7 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
     const double dr = (k == 1) ? q.r[k - 1] - q.rmin : q.r[k - 1] - q.r[k - 2];
     const double dz = (j == 1) ? q.z[j - 1] - q.zmin : q.z[j - 1] - q.z[j - 2];
     double sum_E = 0.0, sum_last = 1.0;
-    double g_av = warp_gamma_bar(Th_e, lane, QuadTab{q.qt_x15});
+    double g_av = gamma_bar_memo(q, Th_e, lane, QuadTab{q.qt_x15});
     for (;;) {                                                    // label 200 (g_av = gamma_bar(Th_e), l.600)
         double hr_th_c = 0.0;
         for (int i = lane; i < N - 1; i += 32)
@@ -797,6 +865,7 @@ void Ctx::fp_free()
 {
     if (!fp) return;
     cudaFree(fp->d_FIC); cudaFree(fp->d_io); cudaFree(fp->d_gtab); cudaFree(fp->d_FICt); cudaFree(fp->d_quad);
+    cudaFree(fp->d_gc_key); cudaFree(fp->d_gc_val);
     delete fp;
     fp = nullptr;
 }
@@ -812,6 +881,10 @@ static int fp_state(Ctx *c)
     CUF(cudaMalloc(&c->fp->d_FICt, (size_t)c->dims.num_nt * c->dims.nphfield * 8));
     CUF(cudaMalloc(&c->fp->d_gtab, (size_t)kGtabN * 8));
     CUF(cudaMalloc(&c->fp->d_quad, (size_t)kQuadRounds * 32 * 8));
+    CUF(cudaMalloc(&c->fp->d_gc_key, (size_t)kGcSlots * 8));
+    CUF(cudaMalloc(&c->fp->d_gc_val, (size_t)kGcSlots * 8));
+    CUF(cudaMemsetAsync(c->fp->d_gc_key, 0, (size_t)kGcSlots * 8, c->stream));
+    CUF(cudaMemsetAsync(c->fp->d_gc_val, 0, (size_t)kGcSlots * 8, c->stream));
     launch_gbar_table(c->fp->d_gtab, c->fp->d_quad, c->stream);
     CUF(cudaGetLastError());
     return 0;
@@ -837,6 +910,7 @@ static void fp_fill_scalars(Ctx *c, const c2d_fp_in *in, FpParams &q)
     q.F_ICt = c->fp->d_FICt;
     q.qt_x15 = c->fp->d_quad;
     q.gtab = c->fp->d_gtab; q.gtab_n = kGtabN; q.gtab_x0 = kGtabX0; q.gtab_ih = 1.0 / kGtabH;
+    q.gc_key = getenv("C2D_FP_NO_MEMO") ? nullptr : c->fp->d_gc_key; q.gc_val = c->fp->d_gc_val;
 }
 
 // ---- the Fokker-Planck update on the resident plasma state (c2d_step.cu), zones dealt out rank::world, and the exchange of

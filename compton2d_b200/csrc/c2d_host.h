@@ -8,7 +8,7 @@ void launch_history_volume(const Params &p, long long first, long long n, long l
 void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
-void launch_children(const Params &p, const CollTask *q_in, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
+void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, cudaStream_t st);
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st);
 void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, const unsigned long long *n_hard_dev,

@@ -11,6 +11,8 @@
 //                    attempts spread over the lanes; k_split3_flights: one thread per accepted sub-child.
 #include "c2d_host.h"
 
+#include <algorithm>
+
 namespace c2d {
 
 __device__ __forceinline__ void push_collision(const Params &p, const Photon &P, uint64_t sid)
@@ -481,9 +483,13 @@ __device__ __forceinline__ void child_flight(const Params &p, Photon &P, Rng &rn
 
 // one thread per (collision, child ii): the split2 loop of imctrk2d.f:619-689.  Children that trigger
 // the 3rd split (l.639) are queued for k_split3 instead of looping split3 times in one thread.
-__device__ __forceinline__ void children_one(const Params &p, const CollTask *q_in, long long idx)
+__device__ __forceinline__ void children_one(const Params &p, const S3Map &m, long long i)
 {
-    const CollTask &task = q_in[idx / p.split2];
+    const long long idx = (long long)m.rank + (long long)m.world * i;      // global child: this rank takes every world-th one
+    const long long tg = idx / p.split2;
+    int r = 0;
+    while (r + 1 < m.world && tg >= m.prefix[r + 1]) r++;
+    const CollTask &task = m.base[(size_t)r * m.stride + (size_t)(tg - m.prefix[r])];
     const int ii = (int)(idx % p.split2) + 1;
     const double ewcsv = task.p.ew / p.split2;                    // l.617
     const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
@@ -503,15 +509,13 @@ __device__ __forceinline__ void children_one(const Params &p, const CollTask *q_
     }
     child_flight(p, P, rng, zi, ewold, i_gam);
 }
-// The number of queued collisions is read on the device (the kernels that queued them have just finished on this stream): a
-// fixed grid strides over collisions x split2 children, no host round trip in front of the launch.
-__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const CollTask *q_in, const unsigned long long *n_dev)
+// The collisions of all ranks are all-gathered and their children dealt out child by child (S3Map, as for the 3rd split):
+// a collision of a hard photon deep in the Klein-Nishina regime costs 10^3-10^4 rejection-loop iterations per child, and
+// which rank it happens on is luck.  A fixed grid strides over this rank's n_mine children.
+__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const S3Map m, long long n_mine)
 {
-    unsigned long long n = *n_dev;
-    if (n > p.q_cap) n = p.q_cap;                                  // the overflow itself was counted as fatal by push_collision
-    const long long total = (long long)n * p.split2;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
-        children_one(p, q_in, idx);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_mine; i += (long long)gridDim.x * blockDim.x)
+        children_one(p, m, i);
 }
 
 // 3rd split, imctrk2d.f:641-669: every sub-child ii2 repeats compb2d until the scattered photon again exceeds
@@ -714,9 +718,11 @@ void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long 
 {
     k_absdraw<<<n_sm * 8, 128, 0, st>>>(p, q, n_dev);
 }
-void launch_children(const Params &p, const CollTask *q_in, const unsigned long long *n_dev, int n_sm, cudaStream_t st)
+void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, cudaStream_t st)
 {
-    k_children<<<n_sm * 8, 128, 0, st>>>(p, q_in, n_dev);
+    if (n_mine <= 0) return;
+    const long long blocks = std::min<long long>((n_mine + 127) / 128, (long long)n_sm * 8);
+    k_children<<<(unsigned)blocks, 128, 0, st>>>(p, m, n_mine);
 }
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st)

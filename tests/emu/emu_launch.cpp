@@ -34,10 +34,9 @@ template <class F> static void run_grid(long long n, F body)
             body();
         }
 }
-void launch_children(const Params &p, const CollTask *q_in, const unsigned long long *n_dev, int, cudaStream_t)
+void launch_children(const Params &p, const S3Map &m, long long n_mine, int, cudaStream_t)
 {
-    const long long n_in = (long long)*n_dev;
-    for (long long idx = 0; idx < n_in * p.split2; idx++) children_one(p, q_in, idx);
+    for (long long i = 0; i < n_mine; i++) children_one(p, m, i);
 }
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t)
