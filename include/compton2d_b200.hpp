@@ -46,15 +46,18 @@ struct Options {
 // dense copies of the step's tallies
 struct Tallies {
     std::vector<double> edep, prdep, ecens, n_field, n_ph, E_IC, fout, edout, erlki, erlko, erlku, erlkl, Ed_in, Ed_ref;
+    std::vector<double> fout_total;                 // escaping spectrum summed over the run and the ranks (xec2d.f:389-394)
     std::vector<int64_t> npcen, nelectron;
-    int64_t counters[16] = {0};
+    int64_t counters[16] = {0}, counters_global[16] = {0};
 };
 
 class Compton2d {
   public:
-    // the per-step reduction over ranks (cens_add_up + E_add_up + xec_add + graphics_collect, update2d.f:1931-2083,
-    // xec2d.f:325-394): sum-all-reduce the two DEVICE buffers in place (NCCL / CUDA-aware MPI)
-    using AllReduce = std::function<void(double *dev_f64, int64_t n_f64, int64_t *dev_i64, int64_t n_i64)>;
+    // Ranks: one Compton2d per GPU.  comm_init joins them: rank 0 makes the NCCL id (unique_id()), the host ships its 128 bytes
+    // with whatever it has (MPI_Bcast in the reference's setting), every rank passes it here.  All later collectives -- the
+    // tally all-reduce, the FP all-gather, the re-dealing of the scattering cascade -- run inside the library.
+    static std::vector<char> unique_id() { std::vector<char> id(C2D_COMM_ID_BYTES); check(c2d_comm_unique_id(id.data())); return id; }
+    void comm_init(const std::vector<char> &id) { check(c2d_comm_init(h_, id.data(), opt_.rank, opt_.world)); }
 
     Compton2d(const Grid &g, const Options &o) : grid_(g), opt_(o), nzone_(g.nz * g.nr)
     {
@@ -108,14 +111,23 @@ class Compton2d {
     }
     void imcredist() {}                       // imcredist.f: histories are sharded statically, census photons never move
     void sync() { check(c2d_sync(h_)); }
-    void graphics_collect(const AllReduce &all_reduce = nullptr)
+    // cens_add_up + E_add_up + xec_add + graphics_collect (update2d.f:1931-2083, xec2d.f:325-394): c2d_tally_reduce -- the
+    // cascade is drained, the two packed tally buffers are all-reduced in place over the ranks of comm_init
+    void graphics_collect() { check(c2d_tally_reduce(h_, nullptr)); }
+
+    // ---- the closed step on a device-resident plasma (c2d_step): what the whole body of xec's loop does ----------
+    void plasma_set(const c2d_plasma &p) { check(c2d_plasma_set(h_, &p)); }
+    void plasma_get(c2d_plasma_out &p) { check(c2d_plasma_get(h_, &p)); }
+    c2d_step_report step(const c2d_run &run, double dt)
     {
-        sync();
-        if (opt_.world == 1 || !all_reduce) return;
-        double *f = nullptr; int64_t *i = nullptr; int64_t nf = 0, ni = 0;
-        check(c2d_tally_device(h_, &f, &nf, &i, &ni));
-        all_reduce(f, nf, i, ni);
+        c2d_step_report rep{};
+        check(c2d_step(h_, &run, ncycle_, time_, dt, &rep));
+        if (ncycle_ > 0) time_ += dt;                                                    // xec2d.f:94-103
+        ncycle_++;
+        return rep;
     }
+    int ncycle() const { return ncycle_; }
+    double time() const { return time_; }
     // update minus MPI (update2d.f:7-334): FP_calc for the zones rank, rank + world, ...; the caller all-gathers the outputs
     void update(c2d_fp_in in, c2d_fp_out &out)
     {
@@ -138,14 +150,15 @@ class Compton2d {
         t.n_field.assign(nzn * nf, 0); t.n_ph.assign(nzn * ng, 0); t.E_IC.assign(N, 0); t.nelectron.assign(N + 2, 0);
         t.fout.assign((size_t)C2D_NMUMAX * nph, 0); t.edout.assign((size_t)C2D_NMUMAX * C2D_NLCMAX, 0);
         t.erlki.assign(grid_.nz, 0); t.erlko.assign(grid_.nz, 0); t.erlku.assign(grid_.nr, 0); t.erlkl.assign(grid_.nr, 0);
-        t.Ed_in.assign(grid_.nr, 0); t.Ed_ref.assign(grid_.nr, 0);
+        t.Ed_in.assign(grid_.nr, 0); t.Ed_ref.assign(grid_.nr, 0); t.fout_total.assign((size_t)C2D_NMUMAX * nph, 0);
         c2d_tallies c{};
+        c.fout_total = t.fout_total.data();
         c.edep = t.edep.data(); c.prdep = t.prdep.data(); c.ecens = t.ecens.data(); c.npcen = t.npcen.data();
         c.n_field = t.n_field.data(); c.n_ph = t.n_ph.data(); c.E_IC = t.E_IC.data(); c.nelectron = t.nelectron.data();
         c.fout = t.fout.data(); c.edout = t.edout.data(); c.erlki = t.erlki.data(); c.erlko = t.erlko.data();
         c.erlku = t.erlku.data(); c.erlkl = t.erlkl.data(); c.Ed_in = t.Ed_in.data(); c.Ed_ref = t.Ed_ref.data();
         check(c2d_tally_read(h_, &c));
-        for (int k = 0; k < 16; k++) t.counters[k] = c.counters[k];
+        for (int k = 0; k < 16; k++) { t.counters[k] = c.counters[k]; t.counters_global[k] = c.counters_global[k]; }
         return t;
     }
     int64_t census_count() { int64_t n = 0; check(c2d_census_count(h_, &n)); return n; }
@@ -198,6 +211,8 @@ class Compton2d {
     int nzone_;
     int64_t n_volume_ = 0;
     size_t lc_cells_ = 0;
+    int ncycle_ = 0;
+    double time_ = 0.0;
     c2d_ctx *h_ = nullptr;
 };
 

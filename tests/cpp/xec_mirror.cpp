@@ -43,9 +43,32 @@ int main(int argc, char **argv)
     o.split1 = (int)sc["split1"]; o.split2 = (int)sc["split2"]; o.split3 = (int)sc["split3"]; o.spl3_trg = (int)sc["spl3_trg"];
     o.pair_switch = (int)sc["pair_switch"]; o.spec_switch = (int)sc["spec_switch"]; o.rseed = (uint32_t)sc["rseed"];
     o.census_capacity = 400000; o.event_capacity = 400000;
-    o.cr_sent = argc > 2 ? std::atoi(argv[2]) : 0;
+    const bool closed = argc > 2 && std::string(argv[2]) == "closed";
+    o.cr_sent = (argc > 2 && !closed) ? std::atoi(argv[2]) : 0;
     try {
         c2d::Compton2d x(g, o);
+        if (closed) {
+            // the closed time step on the resident plasma: xec's loop body as ONE library call per cycle (c2d_step)
+            const auto f_nt = F("f_nt"), Pnt = F("Pnt"), n_e = F("n_e"), tea = F("tea"), tna = F("tna"), B = F("B_field"), gmin = F("gmin"),
+                       gmax = F("gmax"), p_nth = F("p_nth"), amxwl = F("amxwl"), turb = F("turb_lev"), vol = F("vol"), zsurf = F("zsurf");
+            c2d_plasma pl{};
+            pl.f_nt = f_nt.data(); pl.Pnt = Pnt.data(); pl.n_e = n_e.data(); pl.tea = tea.data(); pl.tna = tna.data(); pl.B_field = B.data();
+            pl.gmin = gmin.data(); pl.gmax = gmax.data(); pl.p_nth = p_nth.data(); pl.amxwl = amxwl.data(); pl.turb_lev = turb.data();
+            pl.vol = vol.data(); pl.zsurf = zsurf.data();
+            x.plasma_set(pl);
+            c2d_run run{};
+            run.nst = (int64_t)sc["nst"]; run.T_const = (int)sc["T_const"]; run.quirk_cycle0 = 1; run.r_esc = 0.3; run.r_acc = 1.0;
+            std::vector<int64_t> ndx; std::vector<double> bingo;
+            for (int c = 0; c < 3; c++) {
+                const c2d_step_report rep = x.step(run, sc["dt"]);
+                ndx.push_back(rep.ndxout); ndx.push_back(rep.nevents); ndx.push_back(rep.n_volume); ndx.push_back(rep.histories);
+                bingo.push_back(rep.bingo); bingo.push_back(rep.luminosity);
+            }
+            const c2d::Tallies t = x.tallies();
+            save("closed_counts", ndx); save("closed_bingo", bingo); save("closed_ecens", t.ecens); save("closed_fout_total", t.fout_total);
+            std::printf("xec_mirror closed: ncycle %d, time %.17g\n", x.ncycle(), x.time());
+            return 0;
+        }
         const auto kappa = F("kappa_tot"), et = F("eps_tot"), eh = F("eps_th"), f_nt = F("f_nt"), Pnt = F("Pnt"), n_e = F("n_e"), tea = F("tea"),
                    f_pair = F("f_pair"), k_gg = F("k_gg"), ewsv = F("ewsv"), elth = F("Eloss_th"), eltot = F("Eloss_tot"), zsurf = F("zsurf"),
                    tbbl = F("tbbl");

@@ -32,19 +32,22 @@ def _run_pair(P, cycles=(1, 2)):
     return dense, bridged, fc, t
 
 
-def _check_tallies(P, fc, t):
+def _check_tallies(P, fc, t, exact=True):
+    """exact: the serial emu build sums in one order; on the device the two contexts commit their FP64 atomics in different
+    orders, so sums agree to rounding (1e-12) and only the integers are identical."""
     nz, nr = P["nz"], P["nr"]
     a = fc.a
+    same = np.array_equal if exact else (lambda x, y: np.allclose(x, y, rtol=1e-12, atol=0.0))
     for k in ("edep", "prdep", "ecens"):
-        assert np.array_equal(a[k][:nz, :nr].ravel(), t[k]), k
+        assert same(a[k][:nz, :nr].ravel(), t[k]), k
     assert np.array_equal(a["npcen"][:nz, :nr].ravel(), t["npcen"])
-    assert np.array_equal(np.transpose(a["n_field"][:, :nz, :nr], (1, 2, 0)).reshape(nz * nr, -1), t["n_field"])
-    assert np.array_equal(a["E_IC"], t["E_IC"]) and np.array_equal(a["nelectron"], t["nelectron"][1:-1])
+    assert same(np.transpose(a["n_field"][:, :nz, :nr], (1, 2, 0)).reshape(nz * nr, -1), t["n_field"])
+    assert same(a["E_IC"], t["E_IC"]) and np.array_equal(a["nelectron"], t["nelectron"][1:-1])
     npt, nlc, nmu = P["hu"].size - 1, P["Elcmin"].size, P["mu"].size
-    assert np.array_equal(a["fout"][:nmu, :npt], t["fout_total"][:nmu]) and t["fout_total"].sum() > 0
-    assert np.array_equal(a["edout"][:nmu, :nlc], t["edout"][:nmu, :nlc])
+    assert same(a["fout"][:nmu, :npt], t["fout_total"][:nmu]) and t["fout_total"].sum() > 0
+    assert same(a["edout"][:nmu, :nlc], t["edout"][:nmu, :nlc])
     for k, n in (("erlki", nz), ("erlko", nz), ("erlku", nr), ("erlkl", nr)):
-        assert np.array_equal(a[k][:n], t[k]), k
+        assert same(a[k][:n], t[k]), k
     assert int(a["ndxout"][0]) == t["counters"]["ndxout"] and int(a["cmcount2"][0]) == t["counters"]["cmcount2"]
     # nothing outside the used extent was touched
     assert a["edep"][nz:, :].min() > 0 and a["edep"][:, nr:].min() > 0 and a["n_field"][:, nz:, :].min() > 0
@@ -83,7 +86,7 @@ def test_common_bridge_step_and_update_gpu():
     del o
     dense, bridged, fc, t = _run_pair(P, cycles=(1, 2))
     try:
-        _check_tallies(P, fc, t)
+        _check_tallies(P, fc, t, exact=False)
         nz, nr, nzone = P["nz"], P["nr"], P["nzone"]
         N = P["gnt"].size
         Eloss_sy = np.linspace(1.0, 2.0, nzone) * 1e40
@@ -106,11 +109,14 @@ def test_common_bridge_step_and_update_gpu():
                     flare_amp=10.0)
         cm = fc.struct()
         L.check(bridged.L.c2d_common_update(bridged.h, C.byref(cm), C.byref(fi)))
+        # (each context cools its electrons with its OWN photon-field tally, equal to the other's up to summation order)
         for k in ("f_nt", "Pnt"):
-            assert np.array_equal(a[k][:nz, :nr, :].reshape(nzone, N), ref[k]), k
-        for k in ("n_e", "gmin", "gmax", "p_nth", "amxwl", "Te_new", "tea"):
+            assert np.allclose(a[k][:nz, :nr, :].reshape(nzone, N), ref[k], rtol=1e-9, atol=1e-300), k
+        for k in ("gmin", "gmax", "p_nth", "tea"):
             assert np.array_equal(a[k][:nz, :nr].ravel(), ref[k]), k
-        assert float(a["dT_max"][0]) == ref["dT_max"] and float(a["E_tot_new"][0]) == ref["E_tot_new"]
+        for k in ("n_e", "amxwl", "Te_new"):
+            assert np.allclose(a[k][:nz, :nr].ravel(), ref[k], rtol=1e-10, atol=0), k
+        assert abs(float(a["dT_max"][0]) / ref["dT_max"] - 1) < 1e-10 and abs(float(a["E_tot_new"][0]) / ref["E_tot_new"] - 1) < 1e-10
         assert (a["tea"][:nz, :nr] <= 1.0e3).all() and a["f_nt"][nz:, :, :].min() > 0
     finally:
         dense.close(); bridged.close()

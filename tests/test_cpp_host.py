@@ -72,3 +72,38 @@ def test_cpp_mirror_error_behaviour(exe, tmp_path):
     _dump(P, tmp_path)
     r = subprocess.run([str(exe), str(tmp_path), "2"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 12 and "cr_sent" in r.stderr
+
+
+def test_cpp_closed_step_equals_python(exe, tmp_path, monkeypatch):
+    """c2d::Compton2d::step (the closed time step, c2d_step) against compton2d_b200.host.Compton2d.step on the same library:
+    three cycles on the resident plasma, T_const = 1 (the emu build has no FP kernel)."""
+    import build_emu
+    from compton2d_b200 import lib as L
+    monkeypatch.setattr(L, "LIBPATH", build_emu.build())
+    monkeypatch.setattr(L, "_lib", None)
+    from golden_util import Golden
+    from loop_util import gpu_closed, initial_state
+    o, st, P, scal = initial_state(Golden("small"))
+    del o
+    scal = dict(scal, nst=1200, inj=dict(scal["inj"], inj_switch=0, pick_sw=0))
+    g = gpu_closed(P, st, scal, T_const=1)
+    reps = [g.step(scal["dt"]) for _ in range(3)]
+    t = g.tallies()
+    g.close()
+    monkeypatch.setattr(L, "_lib", None)
+    _dump(dict(P, **{k: st[k] for k in ("f_nt", "Pnt", "n_e", "tea", "zsurf")}), tmp_path)
+    for k in ("tna", "B_field", "gmin", "gmax", "p_nth", "amxwl", "turb_lev", "vol"):
+        np.ascontiguousarray(st[k], dtype=np.float64).tofile(tmp_path / f"{k}.f64")
+    with open(tmp_path / "scalars.txt", "a") as f:
+        f.write(f"nst {float(scal['nst'])!r}\nT_const 1.0\n")
+    lines = [l for l in (tmp_path / "scalars.txt").read_text().splitlines() if not l.startswith(("dt ", "rseed "))]
+    (tmp_path / "scalars.txt").write_text("\n".join(lines) + f"\ndt {scal['dt']!r}\nrseed {float(scal['rseed'])!r}\n")
+    r = subprocess.run([str(exe), str(tmp_path), "closed"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    cnt = np.fromfile(tmp_path / "out_closed_counts", dtype=np.int64).reshape(3, 4)
+    assert np.array_equal(cnt, [[x["ndxout"], x["nevents"], x["n_volume"], x["histories"]] for x in reps])
+    bl = np.fromfile(tmp_path / "out_closed_bingo", dtype=np.float64).reshape(3, 2)
+    assert np.array_equal(bl, [[x["bingo"], x["luminosity"]] for x in reps])
+    assert np.array_equal(np.fromfile(tmp_path / "out_closed_ecens", dtype=np.float64), t["ecens"])
+    assert np.array_equal(np.fromfile(tmp_path / "out_closed_fout_total", dtype=np.float64), t["fout_total"].ravel())
+    assert "ncycle 3" in r.stdout
