@@ -23,9 +23,10 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and LIB.exists() and LIB.stat().st_mtime >= max(p.stat().st_mtime for p in deps):
         return LIB
     extra = os.environ.get("C2D_NVCC_EXTRA", "").split()       # experiments, e.g. -DC2D_HIST_MINB=5
-    cmd = ["nvcc", *FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB), *map(str, srcs)]
+    out = Path(os.environ.get("C2D_LIB_OUT", LIB))              # ... built next to the product library (C2D_LIBPATH selects it)
+    cmd = ["nvcc", *FLAGS, *extra, *(["-Xptxas", "-v"] if verbose else []), "-o", str(out), *map(str, srcs)]
     subprocess.check_call(cmd)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -185,13 +185,14 @@ def test_configs0_as_shipped_matches_reference_binary():
         assert abs(reps[c]["dE_fraction"] - ref_dE[i]) < 5e-3, (c, reps[c]["dE_fraction"], ref_dE[i])
         assert abs(reps[c]["dT_max"] - ref_dT[i]) < 2e-3, (c, reps[c]["dT_max"], ref_dT[i])
         assert reps[c]["fp_steps_min"] == reps[c]["fp_steps_max"] == 5
-    # output/lcb_01.dat (graphics2d.f:200-232: edout(1, band) of the cycle, two rows per cycle): the synchrotron bands 1-2 hold
+    # output/lcb_01.dat (graphics2d.f:176-177,200-232: edout(1, band) / (Elcmax - Elcmin) of the cycle, two rows per cycle): the synchrotron bands 1-2 hold
     # ~3e4 escaping photons per cycle (none of cycle 0's: they carry jgplc = 0); bands 3-5 are built from a few dozen primary
     # Compton events fanned out 1000-fold and are not comparable bin by bin (SURVEY.md 8 notes)
     lcb = np.array([[float(x) for x in l.split()] for l in str(gd.d["file/output/lcb_01.dat"]).splitlines() if l.strip()])
     for i, c in enumerate((1, 2)):
         ref_row = lcb[2 * i, 1:6]
-        assert np.abs(edout[c][:2] / ref_row[:2] - 1.0).max() < 0.04, (c, edout[c], ref_row)
+        got_row = edout[c] / (P["Elcmax"] - P["Elcmin"])
+        assert np.abs(got_row[:2] / ref_row[:2] - 1.0).max() < 0.04, (c, got_row, ref_row)
     # every zone hits the temp_max = 1000 keV clamp (output/temp_b.dat), and the electron spectrum after two updates agrees
     # with the binary's zone by zone (the photon field that cools it is a tally of ~4e5 photons per zone row: ~1e-3)
     assert np.all(plasma["tea"] == 1.0e3)
