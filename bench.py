@@ -247,21 +247,6 @@ def fp_bench(local, hbm, reps=3, nz=64, nr=64, bins=200):
         g.close()
 
 
-def tally_bench(g, hbm, n_events=100_000_000):
-    """Stand-alone tally-commit kernel (csrc/c2d_tally.cu) on a generated list of deposition events, zones hashed:
-    achieved algorithmic GB/s (56 B/event) against the measured HBM peak."""
-    g.tally_bench(n_events // 10, 0)               # warm-up
-    best = None
-    for _ in range(3):
-        ms, nb = g.tally_bench(n_events, 0)
-        best = ms if best is None else min(best, ms)
-    ach = 56.0 * n_events / (best * 1e-3) / 1e9
-    ms_s, _ = g.tally_bench(n_events, 0x20)
-    return {"kernel": "k_tally_deposit", "events": n_events, "ms": best, "events_per_s": n_events / (best * 1e-3),
-            "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm, "traffic": None},
-            "sorted_by_zone_ms": ms_s}
-
-
 MRK421_LC = "p001_evb.dat\n33\n1e16\nlc07_ev0.dat\n1\nlc07_ev0.dat\n0.99944\n0.99964\n7e2\n0\n7e4\n7\n" + \
     "".join(f"{a}\n{b}\n1\n0\n" for a, b in ((1e-3, 3e-3), (2, 4), (9, 15), (15, 20), (20, 60), (5e5, 5e7), (1e9, 1e10)))
 
@@ -509,13 +494,11 @@ def legs_only(args):
     hbm = peaks.get("hbm_gbs", 6650.0)
     out = {}
     legs = args.only.split(",")
-    if "lc" in legs or "tally" in legs:
+    if "lc" in legs:
         P = make_problem(nz=16, nr=16, nst=1000, ngroups=100)
         g = make_gpu(P, census_capacity=1000, event_capacity=1000)
         if "lc" in legs:
             out["lc"] = lc_bench(g, hbm)
-        if "tally" in legs:
-            out["tally"] = tally_bench(g, hbm)
         g.close()
     if "fp" in legs:
         out["fp"] = fp_bench(0, hbm)
@@ -541,7 +524,7 @@ def main():
     ap.add_argument("--no-c3", action="store_true", help="skip the short BASELINE configs[3]-shape leg")
     ap.add_argument("--c3-nst", type=int, default=250_000_000, help="nst per GPU of the configs[3] leg (sources = nst/2)")
     ap.add_argument("--c3-steps", type=int, default=2)
-    ap.add_argument("--only", default="", help="comma list of stand-alone legs (fp, lc, tally) to run instead of the bench line")
+    ap.add_argument("--only", default="", help="comma list of stand-alone legs (fp, fp512, lc) to run instead of the bench line")
     args = ap.parse_args()
     args.nz, args.nr, args.groups = (64, 64, 200) if args.workload == "c3" else (16, 16, 100)
     if args.workload == "c3" and args.nst == 20_000_000:

@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "libcompton2d_b200.so"
-SOURCES = ["c2d_track.cu", "c2d_abi.cu", "c2d_fp.cu", "c2d_sigma.cu", "c2d_tally.cu", "c2d_gen.cu", "c2d_lc.cu", "c2d_io.cu", "c2d_step.cu", "c2d_comm.cu", "c2d_bank.cu", "c2d_common.cu"]
+SOURCES = ["c2d_track.cu", "c2d_abi.cu", "c2d_fp.cu", "c2d_sigma.cu", "c2d_gen.cu", "c2d_lc.cu", "c2d_io.cu", "c2d_step.cu", "c2d_comm.cu", "c2d_bank.cu", "c2d_common.cu"]
 # -fmad=false: the tracker replays against the CPU oracle decision by decision; contraction into FMAs
 # is enabled only where a kernel asks for it explicitly (fma()).
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",

@@ -569,12 +569,6 @@ class Compton2d:
         """Record the start / stop CUDA event of a timed bracket on the library's stream (kernel_time(7))."""
         _l.check(self.L.c2d_kernel_time_ms(self.h, -4 if stop else -3, None, None))
 
-    def tally_bench(self, n_events, kind=0):
-        """-> (ms, algorithmic bytes) of the stand-alone tally-commit kernel (csrc/c2d_tally.cu) on n generated events."""
-        ms, nb = C.c_float(), C.c_int64()
-        _l.check(self.L.c2d_tally_bench(self.h, int(n_events), int(kind), C.byref(ms), C.byref(nb)))
-        return ms.value, nb.value
-
     def timing_reset(self):
         _l.check(self.L.c2d_kernel_time_ms(self.h, -2, None, None))
 

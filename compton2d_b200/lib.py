@@ -132,7 +132,7 @@ class CommExt(C.Structure):
 
 
 COMM_ID_BYTES = 128
-FAMILIES = ["k_history", "k_children", "k_split3_attempts", "k_fp_zones", "k_sigma_table", "tally_bench", "k_split3_flights",
+FAMILIES = ["k_history", "k_children", "k_split3_attempts", "k_fp_zones", "k_sigma_table", "(unused)", "k_split3_flights",
             "bracket", "tally_allreduce", "fp_allgather", "cascade_exchange", "bank_sort"]
 
 
@@ -149,7 +149,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
-           "c2d_kernel_time_ms", "c2d_tally_bench", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
+           "c2d_kernel_time_ms", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
            "c2d_lc_select", "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar",
            "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7", "c2d_tally_reduce", "c2d_finalize",
            "c2d_comm_unique_id", "c2d_comm_init", "c2d_comm_init_ext", "c2d_comm_info", "c2d_comm_destroy",
@@ -198,7 +198,6 @@ def load():
     L.c2d_update_fp.argtypes = [vp, C.POINTER(FpIn), C.POINTER(FpOut)]
     L.c2d_comtot.argtypes = [vp, C.c_int64, vp, vp, C.c_int, vp]
     L.c2d_kernel_time_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float), lp]
-    L.c2d_tally_bench.argtypes = [vp, C.c_int64, C.c_int, C.POINTER(C.c_float), lp]
     L.c2d_census_write.argtypes = [vp, C.c_char_p, lp]
     L.c2d_census_read.argtypes = [vp, C.c_char_p, C.c_int64]
     L.c2d_events_write.argtypes = [vp, C.c_char_p, C.c_int, lp]

@@ -451,13 +451,9 @@ void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int 
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
 int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);
         /* CUDA-event time per kernel family on the library's stream.  which >= 0: read family (0 k_history, 1 k_children,
-           2 k_split3_attempts/_hard, 3 FP, 4 sigma table, 5 tally bench, 6 k_split3_flights, 7 bracket);
-           -1 enable, -2 reset, -3 / -4 record the start / stop event of a bracket (accumulated in family 7) */
-int c2d_tally_bench(c2d_ctx *ctx, int64_t n_events, int kind, float *ms, int64_t *bytes);
-        /* stand-alone tally-commit kernel on a generated event list (csrc/c2d_tally.cu): kind 0 deposition (edep, prdep;
-           56 algorithmic B/event), kind 1 census (bank record + npcen, ecens, n_field; 112 B/event); | 0x10 without the
-           warp-level pre-reduction, | 0x20 events sorted by zone.  Adds into the context's tallies; returns the kernel's
-           CUDA-event time and the algorithmic bytes */
+           2 k_split3_attempts/_hard, 3 FP, 4 sigma table, 6 k_split3_flights, 7 bracket, 8 tally all-reduce, 9 FP all-gather,
+           10 cascade exchange (incl. the wait for the other ranks), 11 census-bank sort);
+           -1 enable, -5 disable, -2 reset, -3 / -4 record the start / stop event of a bracket (accumulated in family 7) */
 
 #ifdef __cplusplus
 }

@@ -11,7 +11,7 @@ LIB = HERE / "libc2d_emu.so"
 
 
 def build(force=False):
-    srcs = [HERE / "emu_launch.cpp", ROOT / "compton2d_b200/csrc/c2d_abi.cu", ROOT / "compton2d_b200/csrc/c2d_fp.cu", ROOT / "compton2d_b200/csrc/c2d_tally.cu",
+    srcs = [HERE / "emu_launch.cpp", ROOT / "compton2d_b200/csrc/c2d_abi.cu", ROOT / "compton2d_b200/csrc/c2d_fp.cu",
             ROOT / "compton2d_b200/csrc/c2d_lc.cu", ROOT / "compton2d_b200/csrc/c2d_io.cu", ROOT / "compton2d_b200/csrc/c2d_step.cu",
             ROOT / "compton2d_b200/csrc/c2d_comm.cu", ROOT / "compton2d_b200/csrc/c2d_bank.cu",
             ROOT / "compton2d_b200/csrc/c2d_common.cu"]
