@@ -161,8 +161,9 @@ def reference_arm(args):
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                      "data": "synthetic", "config": dict(workload_config(args, ref=True), nst_per_gpu=None, nst_per_instance=nst,
-                                                          instances=ncores, note="bounded sample of the same workload shape: nst per instance as stated"),
+                      "data": "synthetic", "config": dict(workload_config(args, ref=True), nst_per_gpu=nst, nst_per_instance=nst, instances=ncores,
+                                                          note="bounded sample of the same workload shape (grid, groups, splits): nst is what "
+                                                               "each single-worker instance of the CPU binary ran, not the GPU arm's 2e7"),
                       "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": ncores, "kind": "reference", "sample": sample},
                       "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}))

@@ -520,7 +520,8 @@ __device__ __forceinline__ double comtot_zone_warp(const Params &p, double xnu, 
 // Thomson bins and S_z(m, .) -- the sum of the exact branch over bins >= m, a smooth function of x on the interval
 // where m(x) = m -- is a degree-7 Chebyshev series in ln x on that interval (m = 0: sub-intervals of width 1/sig_inv_h).
 // The table reproduces the per-history evaluation to ~1e-11 (the cancellation noise of the exact branch itself).
-struct SigCtx { int m, j; double x, s; };      // j = -1: all bins on the Thomson branch; j = -2: outside the table
+struct SigCtx { int m, j, ia, ib; double x, s; };      // j = -1: all bins on the Thomson branch; j = -2: outside the table;
+                                                        // ia / ib: see comtot_table_zone (functions of x only)
 
 __device__ __forceinline__ void sig_begin(const Params &p, double xnu, SigCtx &c)
 {
@@ -541,6 +542,15 @@ __device__ __forceinline__ void sig_begin(const Params &p, double xnu, SigCtx &c
         c.j = p.num_nt - 1 + sub;
     }
     c.s = (t - p.sig_lo[c.j]) * p.sig_iw[c.j] - 1.0;
+    {   // ia = first bin with a1_i x >= 0.1 ; ib = first bin with a2_i x < 1e-3 (a1 grows, a2 falls with the bin index)
+        const int N = p.num_nt;
+        int lo = c.m, hi = N - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a1[mid] * c.x < 0.1) lo = mid + 1; else hi = mid; }
+        c.ia = lo;
+        lo = c.m; hi = N - 1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a2[mid] * c.x < 1.e-3) hi = mid; else lo = mid + 1; }
+        c.ib = lo;
+    }
 }
 
 // Rounding-noise term of one electron bin (see kn_eta): pref_i (eta(a1_i x) - eta(a2_i x)).  The a-side noise is
@@ -657,25 +667,32 @@ __device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCt
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (c2d_ldg(nb + mid) > thr) lo = mid + 1; else hi = mid; }
                 i_end = lo;
             }
-            int ia, ib;
-            {   // ia = first bin with a1_i x >= 0.1 ; ib = first bin with a2_i x < 1e-3
-                int lo = c.m, hi = N - 1;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a1[mid] * x < 0.1) lo = mid + 1; else hi = mid; }
-                ia = lo;
-                lo = c.m; hi = N - 1;
-                while (lo < hi) { const int mid = (lo + hi) >> 1; if (p.kn_a2[mid] * x < 1.e-3) hi = mid; else lo = mid + 1; }
-                ib = lo;
-            }
-            const int i_fast = (ia > ib) ? ia : ib;
-            for (; i < i_fast && i < i_end; i++) {               // the full expressions (few bins)
-                const double yb = p.kn_a2[i] * x;
-                double q;
-                if (i >= ib) {
-                    const double s = 1.0 + yb, e = (s - 1.0) - yb;
-                    q = -(p.kn_cb[i] * inv_x) * (e * fma(0.125, yb, 1.0));
-                } else q = -(p.kn_pref[i] * kn_eta(yb));
+            const int ia = c.ia, ib = c.ib;
+            const int i_full = (ib < i_end) ? ib : i_end;
+            for (; i < i_full; i++) {                             // a2_i x >= 1e-3 (hard photons, lowest-gamma bins): both sides in full
+                double q = -(p.kn_pref[i] * kn_eta(p.kn_a2[i] * x));
                 if (i < ia) q = q + p.kn_pref[i] * kn_eta(p.kn_a1[i] * x);
                 e0 = fma(q, w[i], e0);
+            }
+            // bins just above the branch switch (a1_i x < 0.1, ~17 of them): the a side as well.  eta(y) = (8 + y (9 + y)) e /
+            // (y (1 + y)); the noise term needs 1e-4 relative at most (it is <= 2e-4 of sigma, wanted to 1e-10): the reciprocal
+            // is taken in single precision, only e -- the rounding error of 1 + y itself -- is exact.
+            {
+                const int i_a = (ia < i_end) ? ia : i_end;
+                double sa = 0.0, sb = 0.0;
+                for (; i < i_a; i++) {
+                    const double ya = c2d_ldg(p.kn_a1 + i) * x, yb = c2d_ldg(p.kn_a2 + i) * x;
+                    const double ta = 1.0 + ya, tb = 1.0 + yb;
+                    const double ea = (ta - 1.0) - ya, eb = (tb - 1.0) - yb;
+#ifdef C2D_EMU
+                    const double ra = (double)(1.0f / (float)(ya * ta));
+#else
+                    const double ra = (double)__frcp_rn((float)(ya * ta));
+#endif
+                    sa = fma(c2d_ldg(p.kn_pref + i) * c2d_ldg(w + i), fma(ya, 9.0 + ya, 8.0) * (ea * ra), sa);
+                    sb = fma(c2d_ldg(cw + i), eb * fma(0.125, yb, 1.0), sb);
+                }
+                e0 = e0 + sa - sb * inv_x;
             }
             // b side only: -(cb_i W_i / x) e_i (1 + y_i / 8), e_i = (fl(1 + y_i) - 1) - y_i the rounding error of 1 + y_i.
             // cb_i W_i is tabulated per zone (sig_CW); two independent accumulators, -1 / x applied once.
