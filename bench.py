@@ -332,6 +332,9 @@ def run_tracking(args, dist, rank, world, local, nz, nr, groups, nst, steps, war
         h0 = g.census_count()
         ms, fam, t = step(cyc); cyc += 1
         dev_ms += ms
+        if os.environ.get("BENCH_TRACE"):
+            print(f"[bench r{rank}] cycle {cyc - 1} device {ms:.2f} ms, families " +
+                  " ".join(f"{k}={m:.2f}/{n}" for k, (m, n) in fam.items()), file=sys.stderr)
         for k, (m, n) in fam.items():
             fam_ms[k] += m
             if k not in ("tally_allreduce", "cascade_exchange"):

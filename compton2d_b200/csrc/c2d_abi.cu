@@ -4,6 +4,7 @@
 #include "c2d_ctx.h"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -98,8 +99,15 @@ static int drain_queue(Ctx *c)
     if (!c->cascade_dirty) return 0;                               // nothing was tracked since the last drain (and no collective is due)
     c->cascade_dirty = false;
     const int world = comm_world(c), rank = comm_rank(c);
+    static const bool trace = getenv("C2D_TRACE") != nullptr;     // host clock at every look at the device (each follows a stream sync)
+    const auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what, int gen, unsigned long long n) {
+        if (trace) fprintf(stderr, "[c2d drain r%d] gen %d %-10s n=%llu t=%.3f ms\n", rank, gen, what, n,
+                           std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    };
     if (!c->d_cnt3) {
         CU(cudaMalloc(&c->d_cnt3, (size_t)(3 + 3 * 8) * 8));
+        CU(cudaMalloc(&c->d_casc, 16 * 8));
     }
     auto gather_counts = [&](const unsigned long long *dev_count, unsigned long long *h, int fam) -> int {
         unsigned long long *mine = c->d_cnt3, *all = c->d_cnt3 + 3;
@@ -117,9 +125,8 @@ static int drain_queue(Ctx *c)
         unsigned long long n_max = 0;
         for (int r = 0; r < world; r++) { m.prefix[r + 1] = m.prefix[r] + (long long)h[r]; n_max = std::max(n_max, h[r]); }
         if (world == 1) { m.base = mine_q; m.stride = (long long)h[0]; return 0; }
-        const size_t need = (size_t)world * n_max;
-        if (need > c->q3all_cap) {
-            cudaFree(c->d_q3_all); c->d_q3_all = nullptr; c->q3all_cap = 0;
+        if (!c->d_q3_all) {                                        // once, at the queues' capacity: an allocation (or a free) inside a step
+            const size_t need = (size_t)world * (size_t)c->q_cap;  // stalls the stream for 10 .. 900 ms (measured on the B200 box)
             CU(cudaMalloc(&c->d_q3_all, need * sizeof(CollTask)));
             c->q3all_cap = need;
         }
@@ -144,6 +151,7 @@ static int drain_queue(Ctx *c)
                 return fail(C2D_EINVAL, "collision queue overflow: %llu tasks > collision_capacity %lld", h[r], (long long)c->q_cap);
             n_tot += h[r];
         }
+        lap("collisions", gen, n_tot);
         if (n_tot == 0) return 0;                                  // no rank has a collision left: the cascade has ended
         c->q_peak = std::max<long long>(c->q_peak, (long long)h[rank]);
         {
@@ -151,14 +159,20 @@ static int drain_queue(Ctx *c)
             if (int rc = gather_tasks(c->d_q[c->q_cur], h, mq)) return rc;
             const long long G = (long long)n_tot * p.split2;
             const long long n_mine = (G > rank) ? (G - rank + world - 1) / world : 0;
+            if (!c->d_chard) {                                     // fixed size: a child that finds the list full finishes its loop itself
+                c->chard_cap = (size_t)1 << 20;
+                CU(cudaMalloc(&c->d_chard, c->chard_cap * sizeof(unsigned)));
+            }
+            CU(cudaMemsetAsync(c->d_casc, 0, 16, c->stream));
             c->timer_begin(1);
-            launch_children(p, mq, n_mine, c->n_sm, c->stream);
+            launch_children(p, mq, n_mine, c->n_sm, c->d_chard, (unsigned long long)c->chard_cap, c->d_casc, c->stream);
             c->timer_end();
             CU(cudaGetLastError());
         }
         if (int rc = gather_counts(c->d_qcount + 2, h, 10)) return rc;
         unsigned long long n3_max = 0;
         for (int r = 0; r < world; r++) { n3_tot += h[r]; n3_max = std::max(n3_max, h[r]); }
+        lap("split3", gen, n3_tot);
         if (n3_max > (unsigned long long)c->q_cap)
             return fail(C2D_EINVAL, "split3 queue overflow: %llu tasks > collision_capacity %lld", n3_max, (long long)c->q_cap);
         if (n3_tot) {
@@ -171,21 +185,33 @@ static int drain_queue(Ctx *c)
                 c->flight_cap = std::max<int64_t>((int64_t)p.split3, (int64_t)1 << 20);
                 CU(cudaMalloc(&c->d_flights, (size_t)c->flight_cap * sizeof(FlightTask)));
                 CU(cudaMalloc(&c->d_hard, (size_t)c->flight_cap * sizeof(unsigned)));
+                CU(cudaMalloc(&c->d_ultra, (size_t)c->flight_cap * sizeof(unsigned)));
             }
             for (long long i0 = 0; i0 < n_mine; i0 += c->flight_cap) {
                 const long long ns = std::min<long long>(c->flight_cap, n_mine - i0);
-                CU(cudaMemsetAsync(c->d_qcount + 3, 0, 8, c->stream));
+                CU(cudaMemsetAsync(c->d_casc + 2, 0, 24, c->stream));
+                CU(cudaMemsetAsync(c->d_casc + 8, 0xFF, 24, c->stream));
                 c->timer_begin(2);
-                launch_split3_attempts(p, m, i0, ns, c->d_flights, c->split3_rounds, c->d_hard, c->d_qcount + 3, c->stream);
-                if (c->split3_rounds > 0)
-                    launch_split3_hard(p, m, i0, c->d_hard, c->d_qcount + 3, c->d_flights, (unsigned long long)c->split3_rounds * kWarp,
-                                       c->n_sm, c->stream);
+                launch_split3_attempts(p, m, i0, ns, c->d_flights, c->split3_rounds, c->d_hard, c->d_casc + 2, c->stream);
+                if (c->split3_rounds > 0) {
+                    // the ladder: warp team -> block team (k_split3_hard) -> the whole grid (k_split3_ultra, cooperative launch)
+                    const int e = launch_split3_hard(p, m, i0, c->d_hard, c->d_ultra, c->d_casc + 2, c->d_casc + 8, c->d_flights,
+                                                     (unsigned long long)c->split3_rounds * kWarp, c->split3_hard_rounds, c->n_sm, c->stream);
+                    if (e) { c->timer_end(); return fail(C2D_ECUDA, "cooperative launch of k_split3_ultra failed: %s", cudaGetErrorString((cudaError_t)e)); }
+                }
                 c->timer_end();
                 CU(cudaGetLastError());
                 c->timer_begin(6);
                 launch_split3_flights(p, c->d_flights, ns, c->stream);
                 c->timer_end();
                 CU(cudaGetLastError());
+                if (trace) {
+                    unsigned long long hc[8];
+                    CU(cudaMemcpyAsync(hc, c->d_casc, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
+                    CU(cudaStreamSynchronize(c->stream));
+                    fprintf(stderr, "[c2d drain r%d]   hard children %llu, hard sub-children %llu, grid-team sub-children %llu\n", rank, hc[0], hc[2], hc[4]);
+                    lap("flights", gen, (unsigned long long)ns);
+                }
             }
         }
         CU(cudaMemsetAsync(c->d_qcount + c->q_cur, 0, 8, c->stream));
@@ -450,6 +476,8 @@ int c2d_create(c2d_ctx **out, int device)
     c->split3_rounds = 0;                                         // the serial debug build has no block-team kernel
 #else
     if (const char *e = getenv("C2D_SPLIT3_ROUNDS")) c->split3_rounds = std::max(1, atoi(e));
+    if (const char *e = getenv("C2D_SPLIT3_HARD_ROUNDS")) c->split3_hard_rounds = atoi(e);      // < 0: block teams without limit, no grid team
+    if (const char *e = getenv("C2D_KN_CAP")) c->kn_cap = std::max(1, atoi(e));
 #endif
     *out = reinterpret_cast<c2d_ctx *>(c);
     return 0;
@@ -464,7 +492,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
-    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all);
+    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all); cudaFree(c->d_casc); cudaFree(c->d_chard); cudaFree(c->d_ultra);
     cudaFree(c->d_fout_total); cudaFree(c->d_cnt_global); cudaFree(c->d_plasma); cudaFree(c->d_fpx);
     comm_free(c);
     free_bank(c->bank[0]); free_bank(c->bank[1]);
@@ -589,6 +617,7 @@ int c2d_init(c2d_ctx *h, const c2d_dims *d)
 
     Params &P = c->P;
     memset(&P, 0, sizeof P);
+    P.kn_cap = c->kn_cap;
     P.nz = d->nz; P.nr = d->nr; P.nzone = nzone; P.n_vol = d->n_vol; P.num_nt = d->num_nt; P.nphfield = d->nphfield;
     P.n_gg = d->n_gg; P.nphtotal = d->nphtotal; P.nph_lc = d->nph_lc; P.nmu = d->nmu;
     P.pair_switch = d->pair_switch; P.spec_switch = d->spec_switch; P.cr_sent = d->cr_sent;

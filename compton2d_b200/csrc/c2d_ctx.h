@@ -59,6 +59,13 @@ struct Ctx {
     FlightTask *d_flights = nullptr;       // accepted 3rd-split sub-children of one chunk of split3 tasks
     int64_t flight_cap = 0;
     unsigned *d_hard = nullptr;            // sub-children the warp phase of the 3rd split left unresolved
+    unsigned *d_ultra = nullptr;           // ... and those the block teams of k_split3_hard gave up on (k_split3_ultra: the whole grid)
+    unsigned *d_chard = nullptr;           // children whose K-N rejection loop outlasted kn_cap trips (k_children_hard)
+    size_t chard_cap = 0;
+    unsigned long long *d_casc = nullptr;  // [0] hard children [1] their fetch cursor [2] hard sub-children [3] fetch cursor [4] ultra list
+                                           // [8..10] k_split3_ultra's winner slots
+    int kn_cap = 64;                       // trips of the K-N rejection loop a thread makes before a block team takes the child (C2D_KN_CAP)
+    int split3_hard_rounds = 128;          // block-team rounds before a sub-child goes to the grid team (C2D_SPLIT3_HARD_ROUNDS)
     int split3_rounds = 64;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS; measured 8..128)
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;

@@ -44,7 +44,7 @@ enum { MODE_PRE = 2, MODE_TRIAL = -1, MODE_TRIAL_SLOW = -2, MODE_F0 = 0, MODE_CH
 enum { END_KILLED = 0, END_CENSUS = 1, END_LEAK = 2, END_DROPPED = 3, END_COLLISION = 4, END_LOWEW = 5,
        END_OVERFLOW = 6, END_FATAL = 7 };
 enum { CNT_NDXOUT = 0, CNT_CMCOUNT1, CNT_CMCOUNT2, CNT_LKCOUNT, CNT_NEVENTS, CNT_HISTORIES, CNT_TRIALS,
-       CNT_MULTIPLE, CNT_KILLED, CNT_SEGOVF, CNT_LITERAL, CNT_QPEAK, CNT_FATAL, CNT_SEGMENTS, CNT_S3PASSES, CNT_S3HARD, CNT_N };   // CNT_N == 16
+       CNT_MULTIPLE, CNT_KILLED, CNT_TEAMS, CNT_LITERAL, CNT_QPEAK, CNT_FATAL, CNT_SEGMENTS, CNT_S3PASSES, CNT_S3HARD, CNT_N };   // CNT_N == 16
 
 struct Photon {
     double xnu, wmu, phi, rpre, zpre, dcen, ew;
@@ -140,6 +140,7 @@ struct Params {
     unsigned long long q_cap;
     AbsTask *qabs;                     // histories waiting for k_absdraw
     unsigned long long *qabs_count, qabs_cap;
+    int kn_cap;              // trips of the K-N rejection loop a thread makes before it hands its child to a block team (C2D_KN_CAP)
     int *lit_pool;                     // trial indices of the literal trials of queued histories
     unsigned long long *lit_count, lit_cap;
 };
@@ -754,30 +755,40 @@ __device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double 
 
 // compb_2d.f:55-95 (label 100): draw the electron and the collision cosine, K-N rejection
 struct ElDraw { double gamm, betb, omeg, znue; };
-__device__ __forceinline__ void compb2d_electron(const Params &p, Rng &rng, int zi, double znu, ElDraw &e, int &i_gam, ElRec *rec)
+// one trip through label 100: true = accepted.  Draws: 2 (nth2d) + omeg + tl [+ 1 for the K-N test unless znue < 1e-10].
+__device__ __forceinline__ bool compb2d_electron_once(const Params &p, Rng &rng, int zi, double znu, ElDraw &e, int &i_gam, ElRec *rec)
 {
-    for (;;) {                                       // label 100
-        nth2d(p, rng, zi, e.gamm, e.betb, i_gam, rec);
-        e.omeg = 2.0 * rng.next(p) - 1.0;
-        C2D_CLAMP8(e.omeg);
-        const double tl = rng.next(p);
-        const double tr = 0.5 * (1.0 - e.betb * e.omeg);
-        if (tl > tr) e.omeg = -e.omeg;
-        C2D_CLAMP8(e.omeg);
-        e.znue = (1. - e.betb * e.omeg) * znu * e.gamm;
-        if (e.znue < 1.e-10) continue;
-        double xknot;
-        if (e.znue <= 1.e-2) {
-            xknot = 1.0 - e.znue * (2.0 - e.znue * (5.2 - e.znue * (13.3 - 1.144e3 * e.znue / 3.5e1)));
-        } else {
-            const double znue3 = e.znue * e.znue * e.znue;
-            const double betz = 1.0 + 2.0 * e.znue;
-            const double gamz = e.znue * (e.znue - 2.0) - 2.0;
-            const double xxx = 4.0 * e.znue + 2.0 * znue3 * (1.0 + e.znue) / (betz * betz) + gamz * log(betz);
-            xknot = 3.75e-1 * xxx / znue3;
-        }
-        if (rng.next(p) > xknot) continue;
-        break;
+    nth2d(p, rng, zi, e.gamm, e.betb, i_gam, rec);
+    e.omeg = 2.0 * rng.next(p) - 1.0;
+    C2D_CLAMP8(e.omeg);
+    const double tl = rng.next(p);
+    const double tr = 0.5 * (1.0 - e.betb * e.omeg);
+    if (tl > tr) e.omeg = -e.omeg;
+    C2D_CLAMP8(e.omeg);
+    e.znue = (1. - e.betb * e.omeg) * znu * e.gamm;
+    if (e.znue < 1.e-10) return false;
+    double xknot;
+    if (e.znue <= 1.e-2) {
+        xknot = 1.0 - e.znue * (2.0 - e.znue * (5.2 - e.znue * (13.3 - 1.144e3 * e.znue / 3.5e1)));
+    } else {
+        const double znue3 = e.znue * e.znue * e.znue;
+        const double betz = 1.0 + 2.0 * e.znue;
+        const double gamz = e.znue * (e.znue - 2.0) - 2.0;
+        const double xxx = 4.0 * e.znue + 2.0 * znue3 * (1.0 + e.znue) / (betz * betz) + gamz * log(betz);
+        xknot = 3.75e-1 * xxx / znue3;
+    }
+    return !(rng.next(p) > xknot);
+}
+// For znu >= kKnTeamZnu every trip consumes exactly 5 draws (znue >= (1 - 0.99999999) znu gamma >= 1e-10 always), so trip k of a
+// stream starts at draw 5 k and a TEAM of threads can try trips in parallel (k_children_hard): the rejection loop of a hard
+// photon deep in the Klein-Nishina regime takes 1 / <sigma_KN / sigma_T> ~ 10^3 .. 10^6 trips.
+constexpr double kKnTeamZnu = 2.e-2;
+// max_iter > 0: give up after that many rejected trips (returns false; their nth2d tallies are made, the cursor is at 5 max_iter)
+__device__ __forceinline__ bool compb2d_electron(const Params &p, Rng &rng, int zi, double znu, ElDraw &e, int &i_gam, ElRec *rec, int max_iter = 0)
+{
+    for (int it = 0;; it++) {                        // label 100
+        if (max_iter > 0 && it >= max_iter) return false;
+        if (compb2d_electron_once(p, rng, zi, znu, e, i_gam, rec)) return true;
     }
 }
 

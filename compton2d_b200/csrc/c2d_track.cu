@@ -12,6 +12,9 @@
 #include "c2d_host.h"
 
 #include <algorithm>
+#ifndef C2D_EMU
+#include <cooperative_groups.h>
+#endif
 
 namespace c2d {
 
@@ -110,6 +113,25 @@ __device__ __forceinline__ void tally_census_zone(const Params &p, BlockTally *b
 #endif
     if (valid) census_zone_tally(p, z, ew);
 }
+
+// per-block shared-memory copy of nelectron for the team kernels (the passes hammer a handful of low-gamma bins, which global
+// atomics would serialise); flushed once per block
+constexpr int kHistMax = 1024;
+#ifdef C2D_EMU
+#define C2D_HIST_BEGIN(p) unsigned *hist = nullptr;
+#define C2D_HIST_END(p)
+#else
+#define C2D_HIST_BEGIN(p)                                                                             \
+    __shared__ unsigned s_hist[kHistMax];                                                             \
+    unsigned *hist = ((p).num_nt + 2 <= kHistMax) ? s_hist : nullptr;                                 \
+    if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x) s_hist[i_] = 0u;      \
+    __syncthreads();
+#define C2D_HIST_END(p)                                                                               \
+    __syncthreads();                                                                                  \
+    if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x)                       \
+        if (s_hist[i_]) atomicAdd((p).nelectron + i_, (unsigned long long)s_hist[i_]);
+#endif
+
 
 // ------------------------------------------------------------------------------------------ rare paths of a history
 // A trial flight that may collide is flown literally (imctrk2d.f:126-695 body for scat_flag = -1) with comtot evaluated per
@@ -483,40 +505,110 @@ __device__ __forceinline__ void child_flight(const Params &p, Photon &P, Rng &rn
 
 // one thread per (collision, child ii): the split2 loop of imctrk2d.f:619-689.  Children that trigger
 // the 3rd split (l.639) are queued for k_split3 instead of looping split3 times in one thread.
-__device__ __forceinline__ void children_one(const Params &p, const S3Map &m, long long i)
+struct ChildCtx { const CollTask *task; int ii, zi; double ewold; uint64_t S_child; };
+__device__ __forceinline__ void child_ctx(const Params &p, const S3Map &m, long long i, ChildCtx &c)
 {
     const long long idx = (long long)m.rank + (long long)m.world * i;      // global child: this rank takes every world-th one
     const long long tg = idx / p.split2;
     int r = 0;
     while (r + 1 < m.world && tg >= m.prefix[r + 1]) r++;
-    const CollTask &task = m.base[(size_t)r * m.stride + (size_t)(tg - m.prefix[r])];
-    const int ii = (int)(idx % p.split2) + 1;
-    const double ewcsv = task.p.ew / p.split2;                    // l.617
-    const int zi = (task.p.jph - 1) * p.nr + (task.p.kph - 1);
-    const uint64_t S_child = mix64(task.sid, (uint64_t)ii);
-    Rng rng; rng.stream(S_child);
-    Photon P = task.p;
-    P.ew = ewcsv;
-    const double ewold = P.ew;
-    int i_gam = 0;
-    compb2d(p, rng, P, i_gam);
-    if (P.ew > ewold * p.split2 * p.split1 * p.spl3_trg) {         // 3rd split, l.639-669
+    c.task = m.base + (size_t)r * m.stride + (size_t)(tg - m.prefix[r]);
+    c.ii = (int)(idx % p.split2) + 1;
+    c.ewold = c.task->p.ew / p.split2;                            // l.617
+    c.zi = (c.task->p.jph - 1) * p.nr + (c.task->p.kph - 1);
+    c.S_child = mix64(c.task->sid, (uint64_t)c.ii);
+}
+// after the electron is drawn: the rest of compb2d, the 3rd-split test (l.639), the scat_flag = 1 flight
+__device__ __forceinline__ void child_finish(const Params &p, const ChildCtx &c, Rng &rng, const ElDraw &e, int i_gam)
+{
+    Photon P = c.task->p;
+    P.ew = c.ewold;
+    compb2d_finish(p, rng, P, e);
+    if (P.ew > c.ewold * p.split2 * p.split1 * p.spl3_trg) {       // 3rd split, l.639-669
         const unsigned long long n = atomicAdd(p.q3_count, 1ull);
         if (n >= p.q_cap) { count(p, CNT_FATAL); return; }
         CollTask &t = p.q3[n];
-        t.p = task.p; t.pad = 0; t.sid = S_child;
+        t.p = c.task->p; t.pad = 0; t.sid = c.S_child;
         return;
     }
-    child_flight(p, P, rng, zi, ewold, i_gam);
+    child_flight(p, P, rng, c.zi, c.ewold, i_gam);
+}
+__device__ __forceinline__ void children_one(const Params &p, const S3Map &m, long long i, unsigned *hard, unsigned long long hard_cap,
+                                             unsigned long long *hard_count)
+{
+    ChildCtx c;
+    child_ctx(p, m, i, c);
+    Rng rng; rng.stream(c.S_child);
+    const double znu = c.task->p.xnu / 5.11e2;
+    ElDraw e; int i_gam = 0;
+    // a hard photon's K-N rejection loop can run for 10^3 .. 10^6 trips: after kn_cap of them the child goes to a block team
+    const bool team_ok = hard != nullptr && znu >= kKnTeamZnu;
+    if (!compb2d_electron(p, rng, c.zi, znu, e, i_gam, nullptr, team_ok ? p.kn_cap : 0)) {
+        const unsigned long long slot = atomicAdd(hard_count, 1ull);
+        if (slot < hard_cap) {
+            hard[slot] = (unsigned)i;
+            count(p, CNT_TEAMS);
+            return;
+        }
+        compb2d_electron(p, rng, c.zi, znu, e, i_gam, nullptr, 0);      // list full: carry on from trip kn_cap in this thread
+    }
+    child_finish(p, c, rng, e, i_gam);
 }
 // The collisions of all ranks are all-gathered and their children dealt out child by child (S3Map, as for the 3rd split):
 // a collision of a hard photon deep in the Klein-Nishina regime costs 10^3-10^4 rejection-loop iterations per child, and
 // which rank it happens on is luck.  A fixed grid strides over this rank's n_mine children.
-__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const S3Map m, long long n_mine)
+__global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params p, const S3Map m, long long n_mine, unsigned *hard,
+                                                  unsigned long long hard_cap, unsigned long long *hard_count)
 {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_mine; i += (long long)gridDim.x * blockDim.x)
-        children_one(p, m, i);
+        children_one(p, m, i, hard, hard_cap, hard_count);
 }
+#ifndef C2D_EMU
+// One block per listed child: thread t of the team makes trip base + t of the child's electron loop (draws 5 k .. 5 k + 4 of its
+// stream), the lowest accepted trip wins, the nth2d tallies of the trips up to it are committed -- exactly the draws the
+// sequential loop makes.  Blocks fetch children from a device-side counter (the loops' lengths differ by orders of magnitude).
+__global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ Params p, const S3Map m, const unsigned *hard,
+                                                       unsigned long long hard_cap, const unsigned long long *n_hard_dev,
+                                                       unsigned long long *fetch)
+{
+    __shared__ int win;
+    __shared__ unsigned long long s_b;
+    C2D_HIST_BEGIN(p)
+    const unsigned long long n_hard = min(*n_hard_dev, hard_cap);
+    for (;;) {
+        if (threadIdx.x == 0) s_b = atomicAdd(fetch, 1ull);
+        __syncthreads();
+        const unsigned long long b = s_b;
+        if (b >= n_hard) break;
+        ChildCtx c;
+        child_ctx(p, m, (long long)hard[b], c);
+        const double znu = c.task->p.xnu / 5.11e2;
+        Rng rng; ElDraw e; int i_gam = 0; ElRec rec;
+        for (unsigned long long base = (unsigned long long)p.kn_cap;; base += blockDim.x) {
+            if (threadIdx.x == 0) win = 0x7fffffff;
+            __syncthreads();
+            const unsigned long long k = base + threadIdx.x;
+            rng.stream(c.S_child); rng.d = (uint32_t)(5ull * k);
+            rec.bins = 0ull; rec.n = 0;
+            const bool ok = compb2d_electron_once(p, rng, c.zi, znu, e, i_gam, &rec);
+            if (ok) atomicMin(&win, (int)threadIdx.x);
+            __syncthreads();
+            const int first = win;
+            if ((int)threadIdx.x <= first) {
+                const unsigned bin = (unsigned)(rec.bins & 0xFFFFull);
+                if (hist) atomicAdd(hist + bin, 1u); else atomicAdd(p.nelectron + bin, 1ull);
+            }
+            if (first != 0x7fffffff) {
+                if ((int)threadIdx.x == first) child_finish(p, c, rng, e, i_gam);
+                break;
+            }
+            __syncthreads();                                      // everyone has read `win` before it is reset
+        }
+        __syncthreads();
+    }
+    C2D_HIST_END(p)
+}
+#endif
 
 // 3rd split, imctrk2d.f:641-669: every sub-child ii2 repeats compb2d until the scattered photon again exceeds
 // the trigger.  In Philox replay mode each pass of that rejection loop owns the stream mix64(S_sub, attempt), so
@@ -586,22 +678,6 @@ __device__ __forceinline__ void split3_store(FlightTask &f, const Photon &P, int
 {
     f.p = P; f.i_gam = i_gam; f.sid = rng.sid; f.d = rng.d; f.zi = u.zi; f.ewold = u.ewold;
 }
-constexpr int kHistMax = 1024;
-#ifdef C2D_EMU
-#define C2D_HIST_BEGIN(p) unsigned *hist = nullptr;
-#define C2D_HIST_END(p)
-#else
-#define C2D_HIST_BEGIN(p)                                                                             \
-    __shared__ unsigned s_hist[kHistMax];                                                             \
-    unsigned *hist = ((p).num_nt + 2 <= kHistMax) ? s_hist : nullptr;                                 \
-    if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x) s_hist[i_] = 0u;      \
-    __syncthreads();
-#define C2D_HIST_END(p)                                                                               \
-    __syncthreads();                                                                                  \
-    if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x)                       \
-        if (s_hist[i_]) atomicAdd((p).nelectron + i_, (unsigned long long)s_hist[i_]);
-#endif
-
 constexpr int kHistWarp = 256;      // bins of the per-warp nelectron copy of k_split3_attempts
 #ifndef C2D_S3_MINB
 #define C2D_S3_MINB 16
@@ -649,17 +725,25 @@ __global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __gr
 
 #ifndef C2D_EMU
 __global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *hard,
-                                                     const unsigned long long *n_hard_dev, FlightTask *out, unsigned long long first_attempt)
+                                                     const unsigned long long *n_hard_dev, FlightTask *out, unsigned long long first_attempt,
+                                                     int max_rounds, unsigned *ultra, unsigned long long *ultra_count, unsigned long long *fetch)
 {
     __shared__ int win;
+    __shared__ unsigned long long s_b;
     C2D_HIST_BEGIN(p)
-    const unsigned long long n_hard = *n_hard_dev;                // written by k_split3_attempts just before on this stream
-    for (unsigned long long b = blockIdx.x; b < n_hard; b += gridDim.x) {
+    for (;;) {
+        // blocks fetch sub-children from a device-side counter: their costs differ by orders of magnitude
+        if (threadIdx.x == 0) s_b = atomicAdd(fetch, 1ull);
+        __syncthreads();
+        const unsigned long long b = s_b;
+        if (b >= *n_hard_dev) break;                              // written by k_split3_attempts just before on this stream
         const long long w = hard[b];
         Split3Sub u;
         split3_sub(p, m, i0 + w, u);
         Rng rng; Photon P; int i_gam = 0; ElRec rec;
-        for (uint64_t base = first_attempt;; base += blockDim.x) {
+        bool resolved = false;
+        uint64_t base = first_attempt;
+        for (int round = 0; round < max_rounds; round++, base += blockDim.x) {
             if (threadIdx.x == 0) win = 0x7fffffff;
             __syncthreads();
             const uint64_t attempt = base + threadIdx.x + 1;
@@ -670,11 +754,54 @@ __global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Par
             if ((int)threadIdx.x <= first) split3_commit(p, u, attempt, rec, hist);
             if (first != 0x7fffffff) {
                 if ((int)threadIdx.x == first) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, attempt); }
+                resolved = true;
                 break;
             }
             __syncthreads();                                      // everyone has read `win` before it is reset
         }
-        __syncthreads();                                          // ... and before the next sub-child's first reset
+        // acceptance below ~1e-5 per pass: the whole grid takes over at attempt `base` (k_split3_ultra)
+        if (!resolved && threadIdx.x == 0) { ultra[atomicAdd(ultra_count, 1ull)] = (unsigned)w; count(p, CNT_TEAMS); }
+        __syncthreads();
+    }
+    C2D_HIST_END(p)
+}
+
+// The last rung: sub-children still unresolved after first_attempt passes (acceptance 1e-5 .. 1e-8 per pass: a child that
+// barely triggered the 3rd split, imctrk2d.f:639, must repeat the feat for each of its split3 sub-children).  The reference
+// grinds through them one pass at a time; here the WHOLE GRID is one team: thread g of gridDim.x * blockDim.x tries attempt
+// base + g + 1, the lowest accepted attempt wins (atomicMin in global memory between grid-wide barriers), the tallies of the
+// passes up to the winner are committed.  One cooperative launch walks the list.  Three winner slots rotate so that one
+// grid barrier per super-round suffices: slot (it + 2) % 3 is reset after the barrier of super-round it, i.e. after its last
+// reader and one barrier before its next writer.
+__global__ void __launch_bounds__(512) k_split3_ultra(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *ultra,
+                                                      const unsigned long long *n_ultra_dev, FlightTask *out, unsigned long long first_attempt,
+                                                      unsigned long long *g_win)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    C2D_HIST_BEGIN(p)
+    const unsigned long long n = *n_ultra_dev;
+    const unsigned long long gsize = (unsigned long long)gridDim.x * blockDim.x, gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned it = 0;
+    for (unsigned long long b = 0; b < n; b++) {
+        const long long w = ultra[b];
+        Split3Sub u;
+        split3_sub(p, m, i0 + w, u);
+        Rng rng; Photon P; int i_gam = 0; ElRec rec;
+        for (unsigned long long base = first_attempt;; base += gsize, it++) {
+            const unsigned long long attempt = base + gtid + 1;
+            const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
+            if (ok) atomicMin(g_win + (it % 3u), attempt);
+            grid.sync();
+            const unsigned long long wn = *((volatile unsigned long long *)(g_win + (it % 3u)));
+            if (gtid == 0) g_win[(it + 2u) % 3u] = ~0ull;
+            if (attempt <= wn) split3_commit(p, u, attempt, rec, hist);
+            if (wn != ~0ull) {
+                if (attempt == wn) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, attempt); }
+                it++;
+                break;
+            }
+        }
     }
     C2D_HIST_END(p)
 }
@@ -718,11 +845,13 @@ void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long 
 {
     k_absdraw<<<n_sm * 8, 128, 0, st>>>(p, q, n_dev);
 }
-void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, cudaStream_t st)
-{
+void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, unsigned *hard, unsigned long long hard_cap,
+                     unsigned long long *counts, cudaStream_t st)
+{   // counts[0] = hard children, counts[1] = the team kernel's fetch cursor (both zeroed by the caller)
     if (n_mine <= 0) return;
     const long long blocks = std::min<long long>((n_mine + 127) / 128, (long long)n_sm * 8);
-    k_children<<<(unsigned)blocks, 128, 0, st>>>(p, m, n_mine);
+    k_children<<<(unsigned)blocks, 128, 0, st>>>(p, m, n_mine, hard, hard_cap, counts);
+    k_children_hard<<<n_sm * 4, 256, 0, st>>>(p, m, hard, hard_cap, counts, counts + 1);
 }
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st)
@@ -731,10 +860,22 @@ void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long 
     const long long n = n_sub * kWarp;                            // one warp per sub-child
     k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, m, i0, n_sub, out, max_rounds, hard, hard_count);
 }
-void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, const unsigned long long *n_hard_dev,
-                        FlightTask *out, unsigned long long first_attempt, int n_sm, cudaStream_t st)
+// counts: [0] hard list length (written by k_split3_attempts), [1] fetch cursor, [2] ultra list length; g_win: 3 slots = ~0
+int launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, unsigned *ultra, unsigned long long *counts,
+                       unsigned long long *g_win, FlightTask *out, unsigned long long first_attempt, int hard_rounds, int n_sm, cudaStream_t st)
 {
-    k_split3_hard<<<n_sm * 2, 512, 0, st>>>(p, m, i0, hard, n_hard_dev, out, first_attempt);
+    k_split3_hard<<<n_sm * 2, 512, 0, st>>>(p, m, i0, hard, counts, out, first_attempt, hard_rounds < 0 ? 0x7fffffff : hard_rounds, ultra, counts + 2,
+                                            counts + 1);
+    if (hard_rounds < 0) return 0;
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_split3_ultra, 512, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 1;
+    }
+    const unsigned long long first_ultra = first_attempt + (unsigned long long)hard_rounds * 512ull;
+    const unsigned long long *n_ultra = counts + 2;
+    void *args[] = {(void *)&p, (void *)&m, (void *)&i0, (void *)&ultra, (void *)&n_ultra, (void *)&out, (void *)&first_ultra, (void *)&g_win};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_split3_ultra, dim3((unsigned)(n_sm * blocks_per_sm)), dim3(512), args, 0, st);
+    return e == cudaSuccess ? 0 : (int)e;
 }
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st)
 {

@@ -143,7 +143,7 @@ class LcConfig(C.Structure):
 
 
 COUNTERS = ["ndxout", "cmcount1", "cmcount2", "lkcount", "nevents", "histories", "trials", "multiple", "killed",
-            "segovf", "literal", "qpeak", "fatal", "segments", "s3passes", "s3hard"]
+            "teams", "literal", "qpeak", "fatal", "segments", "s3passes", "s3hard"]
 
 EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_version", "c2d_step_begin",
            "c2d_imcfield", "c2d_imcvol", "c2d_sync", "c2d_tally_read", "c2d_tally_device", "c2d_census_count",

@@ -164,7 +164,7 @@ enum {
     C2D_CNT_TRIALS = 6,      /* split1 trial flights evaluated */
     C2D_CNT_MULTIPLE = 7,    /* 'multiple scattering' events (imctrk2d.f:614) */
     C2D_CNT_KILLED = 8,      /* flights ended by ew <= wtmin (imctrk2d.f:470) */
-    C2D_CNT_SEGOVF = 9,      /* histories whose ray crossed more zones than the fast path holds */
+    C2D_CNT_TEAMS = 9,       /* children finished by k_children_hard + 3rd-split sub-children finished by k_split3_ultra */
     C2D_CNT_LITERAL = 10,    /* trial flights executed literally (collision candidates) */
     C2D_CNT_QPEAK = 11,      /* peak number of queued collision tasks */
     C2D_CNT_FATAL = 12,      /* device-side fatal conditions (0 on success) */

@@ -34,9 +34,9 @@ template <class F> static void run_grid(long long n, F body)
             body();
         }
 }
-void launch_children(const Params &p, const S3Map &m, long long n_mine, int, cudaStream_t)
+void launch_children(const Params &p, const S3Map &m, long long n_mine, int, unsigned *, unsigned long long, unsigned long long *, cudaStream_t)
 {
-    for (long long i = 0; i < n_mine; i++) children_one(p, m, i);
+    for (long long i = 0; i < n_mine; i++) children_one(p, m, i, nullptr, 0ull, nullptr);     // no team kernels in the serial build
 }
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t)
@@ -44,8 +44,8 @@ void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long 
     (void)max_rounds;
     if (n_sub > 0) run_grid(n_sub, [&] { k_split3_attempts(p, m, i0, n_sub, out, 0, hard, hard_count); });
 }
-void launch_split3_hard(const Params &, const S3Map &, long long, const unsigned *, const unsigned long long *, FlightTask *, unsigned long long, int,
-                        cudaStream_t) {}
+int launch_split3_hard(const Params &, const S3Map &, long long, const unsigned *, unsigned *, unsigned long long *, unsigned long long *, FlightTask *,
+                       unsigned long long, int, int, cudaStream_t) { return 0; }
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t)
 {
     if (n > 0) run_grid(n, [&] { k_split3_flights(p, fl, n); });

@@ -70,7 +70,7 @@ def test_long_rays_slow_path():
     # (round 1's history kernel kept <= 12 crossings per ray and flew longer ones trial by trial; the streaming kernel has no
     # such limit -- these rays must simply replay)
     c = rg["counters"]
-    assert c["segments"] > 8 * c["histories"] and c["segovf"] == 0          # 8.6 crossings per ray on average, the longest > 30
+    assert c["segments"] > 8 * c["histories"]          # 8.6 crossings per ray on average, the longest > 30
 
 
 def test_energy_conservation_and_determinism_full_size():

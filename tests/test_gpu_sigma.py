@@ -94,3 +94,51 @@ def test_third_split_block_teams(monkeypatch):
         assert rg["counters"]["cmcount2"] > rg["counters"]["cmcount1"] * P["split"][1]      # 3rd split happened
     finally:
         g.close()
+
+
+@pytest.mark.parametrize("hard_rounds", [0, 1])
+def test_third_split_grid_team(monkeypatch, hard_rounds):
+    """The last rung of the 3rd-split ladder: after 32 warp passes and hard_rounds * 512 block-team passes a sub-child is
+    handed to k_split3_ultra, where the whole (cooperatively launched) grid tries one pass per thread between grid-wide
+    barriers.  Replay parity must not change: the lowest accepted pass wins, the tallies of the passes before it count."""
+    monkeypatch.setenv("C2D_SPLIT3_ROUNDS", "1")
+    monkeypatch.setenv("C2D_SPLIT3_HARD_ROUNDS", str(hard_rounds))
+    P = make_problem(nz=3, nr=3, nst=600, ngroups=64, split=(20, 10, 4, 1000), n_e=4.0e7)
+    o, g = make_oracle(P), make_gpu(P)
+    try:
+        for cyc in (1, 2):
+            ro = oracle_step(o, P, cyc, field=cyc > 1)
+            rg = gpu_step(g, P, cyc, field=cyc > 1)
+            bad = compare(rg, ro, tol=1e-10, census_tol=1e-4)
+            assert not bad, (cyc, bad)
+            c = rg["counters"]
+            if hard_rounds == 0:                                    # the grid team finished what the warps left
+                assert c["teams"] == c["s3hard"]
+            else:
+                assert c["teams"] <= c["s3hard"]
+        assert c["s3hard"] > 0
+    finally:
+        g.close()
+
+
+@pytest.mark.parametrize("kn_cap", [1, 8])
+def test_children_block_teams(monkeypatch, kn_cap):
+    """C2D_KN_CAP: a child whose first kn_cap trips through the electron / Klein-Nishina rejection loop (compb_2d.f label 100)
+    fail, and whose photon has h nu >= 0.02 m c^2, is finished by a 256-thread team of k_children_hard (thread t makes trip
+    base + t on draws 5 k .. 5 k + 4 of the child's stream).  Hard photons: 100 keV Planckian boundaries (imcsurf2d), ~12 trips
+    per child on average.  Replay parity incl. the nelectron tally of every rejected trip."""
+    from synth import make_surface
+    monkeypatch.setenv("C2D_KN_CAP", str(kn_cap))
+    P = make_problem(nz=6, nr=6, nst=600, ngroups=100, split=(100, 10, 4, 10), n_e=2.0e7, rmin=0.1e16)
+    S = make_surface(P, 3000, "planck", tbb=100.0)
+    o, g = make_oracle(P), make_gpu(P, sigma_mode=1)
+    try:
+        for cyc in (1, 2):
+            ro = oracle_step(o, P, cyc, field=cyc > 1, surf=S)
+            rg = gpu_step(g, P, cyc, field=cyc > 1, surf=S)
+            bad = compare(rg, ro, tol=1e-10, census_tol=1e-5)
+            assert not bad, (cyc, bad)
+            assert rg["counters"]["teams"] > 100                    # children that went to the block teams
+            assert ro["nelectron"].sum() > 5 * ro["counters"]["cmcount2"]
+    finally:
+        g.close()
