@@ -275,7 +275,8 @@ def lc_bench(g, hbm, n_events=100_000_000):
 
 
 # ------------------------------------------------------------------------------------------ our arm
-FAM = {"k_history": 0, "k_children": 1, "k_split3_attempts": 2, "k_split3_flights": 6, "k_sigma_table": 4, "bank_sort": 11,
+FAM = {"k_history": 0, "k_children": 1, "k_children_teams": 5, "k_split3_attempts": 2, "k_split3_hard": 12, "k_split3_ultra": 13,
+       "k_split3_flights": 6, "k_sigma_table": 4, "bank_sort": 11,
        "tally_allreduce": 8, "cascade_exchange": 10}      # c2d_kernel_time_ms families (tally_allreduce includes the wait for the slowest rank)
 
 

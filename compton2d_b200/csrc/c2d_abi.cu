@@ -162,12 +162,27 @@ static int drain_queue(Ctx *c)
             if (!c->d_chard) {                                     // fixed size: a child that finds the list full finishes its loop itself
                 c->chard_cap = (size_t)1 << 20;
                 CU(cudaMalloc(&c->d_chard, c->chard_cap * sizeof(unsigned)));
+                CU(cudaMalloc(&c->d_cultra, c->chard_cap * sizeof(GridItem)));
             }
-            CU(cudaMemsetAsync(c->d_casc, 0, 16, c->stream));
+            // d_casc: [0] hard children [1] fetch cursor [2] grid-team children | [3] hard sub-children [4] cursor [5] grid-team sub-children
+            CU(cudaMemsetAsync(c->d_casc, 0, 24, c->stream));
+            CU(cudaMemsetAsync(c->d_casc + 8, 0xFF, 24, c->stream));
             c->timer_begin(1);
             launch_children(p, mq, n_mine, c->n_sm, c->d_chard, (unsigned long long)c->chard_cap, c->d_casc, c->stream);
             c->timer_end();
             CU(cudaGetLastError());
+#ifndef C2D_EMU
+            if (n_mine > 0) {
+                // the ladder of the electron / Klein-Nishina rejection loop: thread -> block team -> the whole grid
+                c->timer_begin(5);
+                launch_children_hard(p, mq, c->d_chard, (unsigned long long)c->chard_cap, c->d_cultra, c->d_casc, c->kn_hard_rounds, c->kn_drain_rounds,
+                                     c->n_sm, c->stream);
+                const int e = launch_children_ultra(p, mq, c->d_cultra, c->d_casc + 2, c->d_casc + 8, c->n_sm, c->stream);
+                c->timer_end();
+                if (e) return fail(C2D_ECUDA, "cooperative launch of k_children_ultra failed: %s", cudaGetErrorString((cudaError_t)e));
+                CU(cudaGetLastError());
+            }
+#endif
         }
         if (int rc = gather_counts(c->d_qcount + 2, h, 10)) return rc;
         unsigned long long n3_max = 0;
@@ -182,25 +197,38 @@ static int drain_queue(Ctx *c)
             const long long G = (long long)n3_tot * p.split3;
             const long long n_mine = (G > rank) ? (G - rank + world - 1) / world : 0;
             if (!c->d_flights) {
-                c->flight_cap = std::max<int64_t>((int64_t)p.split3, (int64_t)1 << 20);
+                // one launch sequence per chunk of this many sub-children: every chunk ends with the tail of its hardest sub-children,
+                // so few large chunks (0.9 GB of flight tasks) beat many small ones
+                int64_t want = (int64_t)1 << 23;
+                if (const char *e = getenv("C2D_FLIGHT_CAP")) want = std::max<int64_t>(1024, atoll(e));
+                c->flight_cap = std::max<int64_t>((int64_t)p.split3, want);
                 CU(cudaMalloc(&c->d_flights, (size_t)c->flight_cap * sizeof(FlightTask)));
                 CU(cudaMalloc(&c->d_hard, (size_t)c->flight_cap * sizeof(unsigned)));
-                CU(cudaMalloc(&c->d_ultra, (size_t)c->flight_cap * sizeof(unsigned)));
+                CU(cudaMalloc(&c->d_ultra, (size_t)c->flight_cap * sizeof(GridItem)));
             }
             for (long long i0 = 0; i0 < n_mine; i0 += c->flight_cap) {
                 const long long ns = std::min<long long>(c->flight_cap, n_mine - i0);
-                CU(cudaMemsetAsync(c->d_casc + 2, 0, 24, c->stream));
+                CU(cudaMemsetAsync(c->d_casc + 3, 0, 24, c->stream));
                 CU(cudaMemsetAsync(c->d_casc + 8, 0xFF, 24, c->stream));
                 c->timer_begin(2);
-                launch_split3_attempts(p, m, i0, ns, c->d_flights, c->split3_rounds, c->d_hard, c->d_casc + 2, c->stream);
-                if (c->split3_rounds > 0) {
-                    // the ladder: warp team -> block team (k_split3_hard) -> the whole grid (k_split3_ultra, cooperative launch)
-                    const int e = launch_split3_hard(p, m, i0, c->d_hard, c->d_ultra, c->d_casc + 2, c->d_casc + 8, c->d_flights,
-                                                     (unsigned long long)c->split3_rounds * kWarp, c->split3_hard_rounds, c->n_sm, c->stream);
-                    if (e) { c->timer_end(); return fail(C2D_ECUDA, "cooperative launch of k_split3_ultra failed: %s", cudaGetErrorString((cudaError_t)e)); }
-                }
+                launch_split3_attempts(p, m, i0, ns, c->d_flights, c->split3_rounds, c->d_hard, c->d_casc + 3, c->stream);
                 c->timer_end();
                 CU(cudaGetLastError());
+                if (c->split3_rounds > 0) {
+                    // the ladder: warp team -> block team (k_split3_hard) -> the whole grid (k_split3_ultra, cooperative launch)
+                    const unsigned long long first_hard = (unsigned long long)c->split3_rounds * kWarp;
+                    c->timer_begin(12);
+                    launch_split3_hard(p, m, i0, c->d_hard, c->d_ultra, c->d_casc + 3, c->d_flights, first_hard, c->split3_hard_rounds,
+                                       c->split3_drain_rounds, c->n_sm, c->stream);
+                    c->timer_end();
+                    CU(cudaGetLastError());
+                    if (c->split3_hard_rounds >= 0) {
+                        c->timer_begin(13);
+                        const int e = launch_split3_ultra(p, m, i0, c->d_ultra, c->d_casc + 5, c->d_flights, c->d_casc + 8, c->n_sm, c->stream);
+                        c->timer_end();
+                        if (e) return fail(C2D_ECUDA, "cooperative launch of k_split3_ultra failed: %s", cudaGetErrorString((cudaError_t)e));
+                    }
+                }
                 c->timer_begin(6);
                 launch_split3_flights(p, c->d_flights, ns, c->stream);
                 c->timer_end();
@@ -209,7 +237,7 @@ static int drain_queue(Ctx *c)
                     unsigned long long hc[8];
                     CU(cudaMemcpyAsync(hc, c->d_casc, sizeof hc, cudaMemcpyDeviceToHost, c->stream));
                     CU(cudaStreamSynchronize(c->stream));
-                    fprintf(stderr, "[c2d drain r%d]   hard children %llu, hard sub-children %llu, grid-team sub-children %llu\n", rank, hc[0], hc[2], hc[4]);
+                    fprintf(stderr, "[c2d drain r%d]   hard children %llu, hard sub-children %llu, grid-team sub-children %llu\n", rank, hc[0], hc[3], hc[5]);
                     lap("flights", gen, (unsigned long long)ns);
                 }
             }
@@ -477,6 +505,9 @@ int c2d_create(c2d_ctx **out, int device)
 #else
     if (const char *e = getenv("C2D_SPLIT3_ROUNDS")) c->split3_rounds = std::max(1, atoi(e));
     if (const char *e = getenv("C2D_SPLIT3_HARD_ROUNDS")) c->split3_hard_rounds = atoi(e);      // < 0: block teams without limit, no grid team
+    if (const char *e = getenv("C2D_KN_HARD_ROUNDS")) c->kn_hard_rounds = std::max(0, atoi(e));
+    if (const char *e = getenv("C2D_KN_DRAIN_ROUNDS")) c->kn_drain_rounds = std::max(0, atoi(e));
+    if (const char *e = getenv("C2D_SPLIT3_DRAIN_ROUNDS")) c->split3_drain_rounds = std::max(0, atoi(e));
     if (const char *e = getenv("C2D_KN_CAP")) c->kn_cap = std::max(1, atoi(e));
 #endif
     *out = reinterpret_cast<c2d_ctx *>(c);
@@ -492,7 +523,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
-    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all); cudaFree(c->d_casc); cudaFree(c->d_chard); cudaFree(c->d_ultra);
+    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all); cudaFree(c->d_casc); cudaFree(c->d_chard); cudaFree(c->d_cultra); cudaFree(c->d_ultra);
     cudaFree(c->d_fout_total); cudaFree(c->d_cnt_global); cudaFree(c->d_plasma); cudaFree(c->d_fpx);
     comm_free(c);
     free_bank(c->bank[0]); free_bank(c->bank[1]);

@@ -59,13 +59,18 @@ struct Ctx {
     FlightTask *d_flights = nullptr;       // accepted 3rd-split sub-children of one chunk of split3 tasks
     int64_t flight_cap = 0;
     unsigned *d_hard = nullptr;            // sub-children the warp phase of the 3rd split left unresolved
-    unsigned *d_ultra = nullptr;           // ... and those the block teams of k_split3_hard gave up on (k_split3_ultra: the whole grid)
+    GridItem *d_ultra = nullptr;           // ... and those the block teams of k_split3_hard gave up on (k_split3_ultra: the whole grid)
+    GridItem *d_cultra = nullptr;          // ... and those the block teams gave up on (k_children_ultra)
     unsigned *d_chard = nullptr;           // children whose K-N rejection loop outlasted kn_cap trips (k_children_hard)
     size_t chard_cap = 0;
     unsigned long long *d_casc = nullptr;  // [0] hard children [1] their fetch cursor [2] hard sub-children [3] fetch cursor [4] ultra list
                                            // [8..10] k_split3_ultra's winner slots
     int kn_cap = 64;                       // trips of the K-N rejection loop a thread makes before a block team takes the child (C2D_KN_CAP)
-    int split3_hard_rounds = 128;          // block-team rounds before a sub-child goes to the grid team (C2D_SPLIT3_HARD_ROUNDS)
+    // block teams -> grid team: after *_hard_rounds rounds whatever happens (tests force the path with 0), or after *_drain_rounds
+    // rounds once half the blocks have run out of work (C2D_KN_HARD_ROUNDS, C2D_KN_DRAIN_ROUNDS, C2D_SPLIT3_HARD_ROUNDS, C2D_SPLIT3_DRAIN_ROUNDS)
+    int kn_hard_rounds = 1 << 22, kn_drain_rounds = 128;          // x 256 trips
+    int split3_drain_rounds = 128;                                 // x 512 passes
+    int split3_hard_rounds = 1 << 21;          // block-team rounds before a sub-child goes to the grid team (C2D_SPLIT3_HARD_ROUNDS)
     int split3_rounds = 64;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS; measured 8..128)
     Bank bank[2]{};
     int cur_out = 0, q_cur = 0;
@@ -124,7 +129,8 @@ struct Ctx {
     size_t lc_stage_cap = 0;
     void lc_free(int slot);
     void lc_free_all();
-    // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3_attempts, 3 FP, 4 sigma table, 5 tally bench,
+    // CUDA-event timing per kernel family: 0 k_history, 1 k_children, 2 k_split3_attempts, 3 FP, 4 sigma table, 5 k_children_hard / _ultra,
+    // 12 k_split3_hard, 13 k_split3_ultra,
     // 6 k_split3_flights, 7 bracket, 8 tally all-reduce (includes the wait for the slowest rank), 9 FP all-gather,
     // 10 cascade exchange (all-gather of the 3rd-split tasks), 11 bank sort
     bool timing = false;
@@ -132,7 +138,7 @@ struct Ctx {
     std::vector<int> ev_which;
     size_t ev_used = 0;
     cudaEvent_t ev_mark[2] = {nullptr, nullptr};
-    static constexpr int kFamilies = 12;
+    static constexpr int kFamilies = 16;
     double k_ms[kFamilies] = {0};
     int64_t k_launches[kFamilies] = {0};
     void timer_begin(int which);

@@ -65,6 +65,8 @@ struct FlightTask {          // a scattered photon (after compb2d) waiting for i
     double ewold;
 };
 
+// an item a block team hands to the grid team: where the team stopped (next attempt / trip) and which item
+struct GridItem { unsigned long long first; unsigned idx, pad; };
 struct S3Map {               // the all-gathered 3rd-split tasks and this rank's share of their sub-children (split3_sub)
     const CollTask *base;
     long long stride;        // tasks per rank slot

@@ -9,11 +9,17 @@ void launch_history_surface(const Params &p, long long first, long long n, long 
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
 void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, unsigned *hard, unsigned long long hard_cap,
-                     unsigned long long *counts, cudaStream_t st);
+                     unsigned long long *hard_count, cudaStream_t st);
+void launch_children_hard(const Params &p, const S3Map &m, const unsigned *hard, unsigned long long hard_cap, GridItem *ultra,
+                          unsigned long long *counts, int max_rounds, int drain_rounds, int n_sm, cudaStream_t st);
+int launch_children_ultra(const Params &p, const S3Map &m, const GridItem *ultra, const unsigned long long *n_ultra, unsigned long long *g_win,
+                          int n_sm, cudaStream_t st);
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st);
-int launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, unsigned *ultra, unsigned long long *counts,
-                       unsigned long long *g_win, FlightTask *out, unsigned long long first_attempt, int hard_rounds, int n_sm, cudaStream_t st);
+void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, GridItem *ultra, unsigned long long *counts,
+                        FlightTask *out, unsigned long long first_attempt, int max_rounds, int drain_rounds, int n_sm, cudaStream_t st);
+int launch_split3_ultra(const Params &p, const S3Map &m, long long i0, const GridItem *ultra, const unsigned long long *n_ultra, FlightTask *out,
+                        unsigned long long *g_win, int n_sm, cudaStream_t st);
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st);
 void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t st);
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,

@@ -313,7 +313,7 @@ int c2d_step(c2d_ctx *h, const c2d_run *run, int ncycle, double time, double dt,
     } else {
         rep->dt_new = dt;
     }
-    for (int k = 0; k < Ctx::kFamilies && k < 12; k++) { c->timer_collect(); rep->ms[k] = c->k_ms[k]; }
+    for (int k = 0; k < Ctx::kFamilies && k < 16; k++) { c->timer_collect(); rep->ms[k] = c->k_ms[k]; }
     return 0;
 }
 

@@ -129,7 +129,7 @@ constexpr int kHistMax = 1024;
 #define C2D_HIST_END(p)                                                                               \
     __syncthreads();                                                                                  \
     if (hist) for (int i_ = threadIdx.x; i_ < (p).num_nt + 2; i_ += blockDim.x)                       \
-        if (s_hist[i_]) atomicAdd((p).nelectron + i_, (unsigned long long)s_hist[i_]);
+        if (s_hist[i_]) atomicAdd((p).nelectron + i_, (unsigned long long)(long long)(int)s_hist[i_]);   /* signed: the grid teams take tallies back */
 #endif
 
 
@@ -569,14 +569,15 @@ __global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params
 // sequential loop makes.  Blocks fetch children from a device-side counter (the loops' lengths differ by orders of magnitude).
 __global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ Params p, const S3Map m, const unsigned *hard,
                                                        unsigned long long hard_cap, const unsigned long long *n_hard_dev,
-                                                       unsigned long long *fetch)
+                                                       unsigned long long *fetch, int max_rounds, int drain_rounds, GridItem *ultra,
+                                                       unsigned long long *ultra_count)
 {
-    __shared__ int win;
+    __shared__ int win, s_drain;
     __shared__ unsigned long long s_b;
     C2D_HIST_BEGIN(p)
     const unsigned long long n_hard = min(*n_hard_dev, hard_cap);
     for (;;) {
-        if (threadIdx.x == 0) s_b = atomicAdd(fetch, 1ull);
+        if (threadIdx.x == 0) { s_b = atomicAdd(fetch, 1ull); s_drain = 0; }
         __syncthreads();
         const unsigned long long b = s_b;
         if (b >= n_hard) break;
@@ -584,9 +585,17 @@ __global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ P
         child_ctx(p, m, (long long)hard[b], c);
         const double znu = c.task->p.xnu / 5.11e2;
         Rng rng; ElDraw e; int i_gam = 0; ElRec rec;
-        for (unsigned long long base = (unsigned long long)p.kn_cap;; base += blockDim.x) {
-            if (threadIdx.x == 0) win = 0x7fffffff;
+        bool resolved = false;
+        unsigned long long base = (unsigned long long)p.kn_cap;
+        for (int round = 0; round < max_rounds; round++, base += blockDim.x) {
+            if (threadIdx.x == 0) {
+                win = 0x7fffffff;
+                // half the blocks have found the list dry and this child is still unresolved after drain_rounds rounds: the GPU is emptying, so the
+                // grid team is the faster way to finish it (while other blocks still have children to fetch, carrying on costs nothing)
+                if (round >= drain_rounds && (round & 63) == 0) s_drain = *((volatile unsigned long long *)fetch) >= n_hard + gridDim.x / 2;
+            }
             __syncthreads();
+            if (s_drain) break;
             const unsigned long long k = base + threadIdx.x;
             rng.stream(c.S_child); rng.d = (uint32_t)(5ull * k);
             rec.bins = 0ull; rec.n = 0;
@@ -600,11 +609,70 @@ __global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ P
             }
             if (first != 0x7fffffff) {
                 if ((int)threadIdx.x == first) child_finish(p, c, rng, e, i_gam);
+                resolved = true;
                 break;
             }
             __syncthreads();                                      // everyone has read `win` before it is reset
         }
+        // <sigma_KN / sigma_T> below ~1e-4 (a GeV photon meeting the gamma ~ 1e5 tail): the whole grid takes over at trip `base`
+        if (!resolved && threadIdx.x == 0) { GridItem &g = ultra[atomicAdd(ultra_count, 1ull)]; g.first = base; g.idx = hard[b]; g.pad = 0u; }
         __syncthreads();
+    }
+    C2D_HIST_END(p)
+}
+
+// children the block teams gave up on: the grid is the team (see k_split3_ultra for the batching and the winner slots)
+constexpr int kGridBatchMax = 64;
+__device__ __forceinline__ void tally_bin(const Params &p, unsigned *hist, unsigned bin, int sign)
+{
+    if (hist) atomicAdd(hist + bin, (unsigned)sign); else atomicAdd(p.nelectron + bin, (unsigned long long)(long long)sign);
+}
+__global__ void __launch_bounds__(256) k_children_ultra(const __grid_constant__ Params p, const S3Map m, const GridItem *ultra,
+                                                        const unsigned long long *n_ultra_dev, unsigned long long *g_win)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    C2D_HIST_BEGIN(p)
+    const unsigned long long n = *n_ultra_dev;
+    const unsigned long long gsize = (unsigned long long)gridDim.x * blockDim.x, gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned it = 0;
+    for (unsigned long long b = 0; b < n; b++) {
+        ChildCtx c;
+        child_ctx(p, m, (long long)ultra[b].idx, c);
+        const double znu = c.task->p.xnu / 5.11e2;
+        Rng rng; ElDraw e; int i_gam = 0; ElRec rec;
+        int batch = 1;
+        for (unsigned long long base = ultra[b].first;; base += gsize * batch, batch = min(2 * batch, kGridBatchMax), it++) {
+            unsigned long long mine = ~0ull;
+            int n_done = 0;
+            for (int i = 0; i < batch; i++) {                    // trips base + gtid + i gsize, tallied as they are made
+                const unsigned long long k = base + gtid + (unsigned long long)i * gsize;
+                rng.stream(c.S_child); rng.d = (uint32_t)(5ull * k);
+                rec.bins = 0ull; rec.n = 0;
+                const bool ok = compb2d_electron_once(p, rng, c.zi, znu, e, i_gam, &rec);
+                tally_bin(p, hist, (unsigned)(rec.bins & 0xFFFFull), 1);
+                n_done++;
+                if (ok) { mine = k; break; }
+            }
+            if (mine != ~0ull) atomicMin(g_win + (it % 3u), mine);
+            grid.sync();
+            const unsigned long long wn = *((volatile unsigned long long *)(g_win + (it % 3u)));
+            if (gtid == 0) g_win[(it + 2u) % 3u] = ~0ull;
+            if (wn != ~0ull) {
+                for (int i = 0; i < n_done; i++) {                // the sequential loop never made the trips after the winner
+                    const unsigned long long k = base + gtid + (unsigned long long)i * gsize;
+                    if (k <= wn) continue;
+                    Rng r2; ElDraw e2; int ig2; ElRec rec2;
+                    r2.stream(c.S_child); r2.d = (uint32_t)(5ull * k);
+                    rec2.bins = 0ull; rec2.n = 0;
+                    compb2d_electron_once(p, r2, c.zi, znu, e2, ig2, &rec2);
+                    tally_bin(p, hist, (unsigned)(rec2.bins & 0xFFFFull), -1);
+                }
+                if (mine == wn) child_finish(p, c, rng, e, i_gam);
+                it++;
+                break;
+            }
+        }
     }
     C2D_HIST_END(p)
 }
@@ -726,17 +794,19 @@ __global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __gr
 #ifndef C2D_EMU
 __global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *hard,
                                                      const unsigned long long *n_hard_dev, FlightTask *out, unsigned long long first_attempt,
-                                                     int max_rounds, unsigned *ultra, unsigned long long *ultra_count, unsigned long long *fetch)
+                                                     int max_rounds, int drain_rounds, GridItem *ultra, unsigned long long *ultra_count,
+                                                     unsigned long long *fetch)
 {
-    __shared__ int win;
+    __shared__ int win, s_drain;
     __shared__ unsigned long long s_b;
     C2D_HIST_BEGIN(p)
     for (;;) {
         // blocks fetch sub-children from a device-side counter: their costs differ by orders of magnitude
-        if (threadIdx.x == 0) s_b = atomicAdd(fetch, 1ull);
+        if (threadIdx.x == 0) { s_b = atomicAdd(fetch, 1ull); s_drain = 0; }
         __syncthreads();
         const unsigned long long b = s_b;
-        if (b >= *n_hard_dev) break;                              // written by k_split3_attempts just before on this stream
+        const unsigned long long n_hard = *n_hard_dev;            // written by k_split3_attempts just before on this stream
+        if (b >= n_hard) break;
         const long long w = hard[b];
         Split3Sub u;
         split3_sub(p, m, i0 + w, u);
@@ -744,8 +814,12 @@ __global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Par
         bool resolved = false;
         uint64_t base = first_attempt;
         for (int round = 0; round < max_rounds; round++, base += blockDim.x) {
-            if (threadIdx.x == 0) win = 0x7fffffff;
+            if (threadIdx.x == 0) {
+                win = 0x7fffffff;
+                if (round >= drain_rounds && (round & 63) == 0) s_drain = *((volatile unsigned long long *)fetch) >= n_hard + gridDim.x / 2;
+            }
             __syncthreads();
+            if (s_drain) break;
             const uint64_t attempt = base + threadIdx.x + 1;
             const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
             if (ok) atomicMin(&win, (int)threadIdx.x);
@@ -760,22 +834,37 @@ __global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Par
             __syncthreads();                                      // everyone has read `win` before it is reset
         }
         // acceptance below ~1e-5 per pass: the whole grid takes over at attempt `base` (k_split3_ultra)
-        if (!resolved && threadIdx.x == 0) { ultra[atomicAdd(ultra_count, 1ull)] = (unsigned)w; count(p, CNT_TEAMS); }
+        if (!resolved && threadIdx.x == 0) {
+            GridItem &g = ultra[atomicAdd(ultra_count, 1ull)];
+            g.first = base; g.idx = (unsigned)w; g.pad = 0u;
+            count(p, CNT_TEAMS);
+        }
         __syncthreads();
     }
     C2D_HIST_END(p)
 }
 
-// The last rung: sub-children still unresolved after first_attempt passes (acceptance 1e-5 .. 1e-8 per pass: a child that
+// The last rung: sub-children still unresolved when the block teams hand over (acceptance 1e-5 .. 1e-9 per pass: a child that
 // barely triggered the 3rd split, imctrk2d.f:639, must repeat the feat for each of its split3 sub-children).  The reference
-// grinds through them one pass at a time; here the WHOLE GRID is one team: thread g of gridDim.x * blockDim.x tries attempt
-// base + g + 1, the lowest accepted attempt wins (atomicMin in global memory between grid-wide barriers), the tallies of the
-// passes up to the winner are committed.  One cooperative launch walks the list.  Three winner slots rotate so that one
-// grid barrier per super-round suffices: slot (it + 2) % 3 is reset after the barrier of super-round it, i.e. after its last
-// reader and one barrier before its next writer.
-__global__ void __launch_bounds__(512) k_split3_ultra(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *ultra,
-                                                      const unsigned long long *n_ultra_dev, FlightTask *out, unsigned long long first_attempt,
-                                                      unsigned long long *g_win)
+// grinds through them one pass at a time; here the WHOLE GRID is one team.  Super-round j: thread g makes the passes
+// base + 1 + g + i G (i < batch_j = 1, 2, 4 .. 64; G = threads of the grid) up to its first accepted one, tallying their nth2d
+// draws as it goes; the lowest accepted pass of the grid wins (atomicMin in global memory, one grid-wide barrier per
+// super-round); the threads then take back the tallies of the passes they made beyond the winner -- the sequential loop never
+// made those.  The doubling batch keeps the barrier (5 - 7 us) off the critical path of the really hard sub-children and
+// wastes at most one batch on the easy ones.  Three winner slots rotate so that one barrier per super-round suffices: slot
+// (it + 2) % 3 is reset after the barrier of super-round it, i.e. after its last reader and one barrier before its next writer.
+__device__ __forceinline__ void split3_tally(const Params &p, const Split3Sub &u, uint64_t attempt, unsigned *hist, int sign)
+{   // the nth2d draws of one pass (its K-N rejection loop, label 100), replayed
+    Rng r; r.stream(mix64(u.S_sub, attempt));
+    for (;;) {
+        ElDraw e; int ig; ElRec rec; rec.bins = 0ull; rec.n = 0;
+        const bool ok = compb2d_electron_once(p, r, u.zi, u.znu, e, ig, &rec);
+        tally_bin(p, hist, (unsigned)(rec.bins & 0xFFFFull), sign);
+        if (ok) break;
+    }
+}
+__global__ void __launch_bounds__(512) k_split3_ultra(const __grid_constant__ Params p, const S3Map m, long long i0, const GridItem *ultra,
+                                                      const unsigned long long *n_ultra_dev, FlightTask *out, unsigned long long *g_win)
 {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
@@ -784,20 +873,31 @@ __global__ void __launch_bounds__(512) k_split3_ultra(const __grid_constant__ Pa
     const unsigned long long gsize = (unsigned long long)gridDim.x * blockDim.x, gtid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
     unsigned it = 0;
     for (unsigned long long b = 0; b < n; b++) {
-        const long long w = ultra[b];
+        const long long w = ultra[b].idx;
         Split3Sub u;
         split3_sub(p, m, i0 + w, u);
         Rng rng; Photon P; int i_gam = 0; ElRec rec;
-        for (unsigned long long base = first_attempt;; base += gsize, it++) {
-            const unsigned long long attempt = base + gtid + 1;
-            const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
-            if (ok) atomicMin(g_win + (it % 3u), attempt);
+        int batch = 1;
+        for (unsigned long long base = ultra[b].first;; base += gsize * batch, batch = min(2 * batch, kGridBatchMax), it++) {
+            unsigned long long mine = ~0ull;
+            int n_done = 0;
+            for (int i = 0; i < batch; i++) {
+                const unsigned long long attempt = base + gtid + 1 + (unsigned long long)i * gsize;
+                const bool ok = split3_pass(p, u, attempt, rng, P, i_gam, rec);
+                split3_commit(p, u, attempt, rec, hist);
+                n_done++;
+                if (ok) { mine = attempt; break; }
+            }
+            if (mine != ~0ull) atomicMin(g_win + (it % 3u), mine);
             grid.sync();
             const unsigned long long wn = *((volatile unsigned long long *)(g_win + (it % 3u)));
             if (gtid == 0) g_win[(it + 2u) % 3u] = ~0ull;
-            if (attempt <= wn) split3_commit(p, u, attempt, rec, hist);
             if (wn != ~0ull) {
-                if (attempt == wn) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, attempt); }
+                for (int i = 0; i < n_done; i++) {
+                    const unsigned long long attempt = base + gtid + 1 + (unsigned long long)i * gsize;
+                    if (attempt > wn) split3_tally(p, u, attempt, hist, -1);
+                }
+                if (mine == wn) { split3_store(out[w], P, i_gam, rng, u); count(p, CNT_S3PASSES, wn); }
                 it++;
                 break;
             }
@@ -845,13 +945,38 @@ void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long 
 {
     k_absdraw<<<n_sm * 8, 128, 0, st>>>(p, q, n_dev);
 }
+static int coop_blocks_per_sm(const void *kernel, int threads)
+{
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, threads, 0) != cudaSuccess || b < 1) b = 1;
+    return b;
+}
+// blocks of a grid team: all that fit (cooperative launch), or C2D_GRID_TEAM_BLOCKS (tests: a small team needs many super-rounds)
+static unsigned coop_grid(int n_sm, int per_sm)
+{
+    if (const char *e = getenv("C2D_GRID_TEAM_BLOCKS")) return (unsigned)std::min(std::max(1, atoi(e)), n_sm * per_sm);
+    return (unsigned)(n_sm * per_sm);
+}
 void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, unsigned *hard, unsigned long long hard_cap,
-                     unsigned long long *counts, cudaStream_t st)
-{   // counts[0] = hard children, counts[1] = the team kernel's fetch cursor (both zeroed by the caller)
+                     unsigned long long *hard_count, cudaStream_t st)
+{
     if (n_mine <= 0) return;
     const long long blocks = std::min<long long>((n_mine + 127) / 128, (long long)n_sm * 8);
-    k_children<<<(unsigned)blocks, 128, 0, st>>>(p, m, n_mine, hard, hard_cap, counts);
-    k_children_hard<<<n_sm * 4, 256, 0, st>>>(p, m, hard, hard_cap, counts, counts + 1);
+    k_children<<<(unsigned)blocks, 128, 0, st>>>(p, m, n_mine, hard, hard_cap, hard_count);
+}
+// counts: [0] hard list length (k_children), [1] fetch cursor, [2] grid-team list length; all zero before k_children
+void launch_children_hard(const Params &p, const S3Map &m, const unsigned *hard, unsigned long long hard_cap, GridItem *ultra,
+                          unsigned long long *counts, int max_rounds, int drain_rounds, int n_sm, cudaStream_t st)
+{
+    k_children_hard<<<n_sm * 4, 256, 0, st>>>(p, m, hard, hard_cap, counts, counts + 1, max_rounds, drain_rounds, ultra, counts + 2);
+}
+int launch_children_ultra(const Params &p, const S3Map &m, const GridItem *ultra, const unsigned long long *n_ultra, unsigned long long *g_win,
+                          int n_sm, cudaStream_t st)
+{
+    static const int per_sm = coop_blocks_per_sm((const void *)k_children_ultra, 256);
+    void *args[] = {(void *)&p, (void *)&m, (void *)&ultra, (void *)&n_ultra, (void *)&g_win};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_children_ultra, dim3(coop_grid(n_sm, per_sm)), dim3(256), args, 0, st);
+    return e == cudaSuccess ? 0 : (int)e;
 }
 void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long long n_sub, FlightTask *out, int max_rounds,
                             unsigned *hard, unsigned long long *hard_count, cudaStream_t st)
@@ -860,21 +985,20 @@ void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long 
     const long long n = n_sub * kWarp;                            // one warp per sub-child
     k_split3_attempts<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(p, m, i0, n_sub, out, max_rounds, hard, hard_count);
 }
-// counts: [0] hard list length (written by k_split3_attempts), [1] fetch cursor, [2] ultra list length; g_win: 3 slots = ~0
-int launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, unsigned *ultra, unsigned long long *counts,
-                       unsigned long long *g_win, FlightTask *out, unsigned long long first_attempt, int hard_rounds, int n_sm, cudaStream_t st)
+// counts: [0] hard list length (written by k_split3_attempts), [1] fetch cursor, [2] grid-team list length
+void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, GridItem *ultra, unsigned long long *counts,
+                        FlightTask *out, unsigned long long first_attempt, int max_rounds, int drain_rounds, int n_sm, cudaStream_t st)
 {
-    k_split3_hard<<<n_sm * 2, 512, 0, st>>>(p, m, i0, hard, counts, out, first_attempt, hard_rounds < 0 ? 0x7fffffff : hard_rounds, ultra, counts + 2,
-                                            counts + 1);
-    if (hard_rounds < 0) return 0;
-    static int blocks_per_sm = 0;
-    if (!blocks_per_sm) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_split3_ultra, 512, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 1;
-    }
-    const unsigned long long first_ultra = first_attempt + (unsigned long long)hard_rounds * 512ull;
-    const unsigned long long *n_ultra = counts + 2;
-    void *args[] = {(void *)&p, (void *)&m, (void *)&i0, (void *)&ultra, (void *)&n_ultra, (void *)&out, (void *)&first_ultra, (void *)&g_win};
-    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_split3_ultra, dim3((unsigned)(n_sm * blocks_per_sm)), dim3(512), args, 0, st);
+    k_split3_hard<<<n_sm * 2, 512, 0, st>>>(p, m, i0, hard, counts, out, first_attempt, max_rounds < 0 ? 0x7fffffff : max_rounds, drain_rounds, ultra,
+                                            counts + 2, counts + 1);
+}
+// g_win: 3 slots = ~0
+int launch_split3_ultra(const Params &p, const S3Map &m, long long i0, const GridItem *ultra, const unsigned long long *n_ultra, FlightTask *out,
+                        unsigned long long *g_win, int n_sm, cudaStream_t st)
+{
+    static const int per_sm = coop_blocks_per_sm((const void *)k_split3_ultra, 512);
+    void *args[] = {(void *)&p, (void *)&m, (void *)&i0, (void *)&ultra, (void *)&n_ultra, (void *)&out, (void *)&g_win};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)k_split3_ultra, dim3(coop_grid(n_sm, per_sm)), dim3(512), args, 0, st);
     return e == cudaSuccess ? 0 : (int)e;
 }
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st)

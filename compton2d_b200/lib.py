@@ -109,7 +109,7 @@ class StepReport(C.Structure):
         [(n, C.c_double) for n in ("bingo", "Emiss_tot", "fbias", "luminosity")] + \
         [(n, C.c_int) for n in ("fp_ran", "fp_steps_min", "fp_steps_max")] + \
         [(n, C.c_double) for n in ("E_tot_old", "E_tot_new", "dE_fraction", "dT_max", "dt_new", "hr_total", "hr_st_total")] + \
-        [("ms", C.c_double * 12)]
+        [("ms", C.c_double * 16)]
 
 
 class Common(C.Structure):
@@ -132,8 +132,9 @@ class CommExt(C.Structure):
 
 
 COMM_ID_BYTES = 128
-FAMILIES = ["k_history", "k_children", "k_split3_attempts", "k_fp_zones", "k_sigma_table", "(unused)", "k_split3_flights",
-            "bracket", "tally_allreduce", "fp_allgather", "cascade_exchange", "bank_sort"]
+FAMILIES = ["k_history", "k_children", "k_split3_attempts", "k_fp_zones", "k_sigma_table", "k_children_teams", "k_split3_flights",
+            "bracket", "tally_allreduce", "fp_allgather", "cascade_exchange", "bank_sort", "k_split3_hard", "k_split3_ultra",
+            "(unused)", "(unused)"]
 
 
 class LcConfig(C.Structure):

@@ -386,7 +386,7 @@ typedef struct {                      /* what the reference prints to log.txt / 
     double luminosity;                /* E_add_up: sum(erlk*) / dt (update2d.f:2068) */
     int fp_ran, fp_steps_min, fp_steps_max;
     double E_tot_old, E_tot_new, dE_fraction, dT_max, dt_new, hr_total, hr_st_total;   /* update2d.f:206-243 */
-    double ms[12];                    /* CUDA-event ms per kernel family since timing was enabled (c2d_kernel_time_ms) */
+    double ms[16];                    /* CUDA-event ms per kernel family since timing was enabled (c2d_kernel_time_ms) */
 } c2d_step_report;
 
 int c2d_plasma_set(c2d_ctx *ctx, const c2d_plasma *p);
@@ -452,7 +452,8 @@ void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int 
 int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);
         /* CUDA-event time per kernel family on the library's stream.  which >= 0: read family (0 k_history, 1 k_children,
            2 k_split3_attempts/_hard, 3 FP, 4 sigma table, 6 k_split3_flights, 7 bracket, 8 tally all-reduce, 9 FP all-gather,
-           10 cascade exchange (incl. the wait for the other ranks), 11 census-bank sort);
+           10 cascade exchange (incl. the wait for the other ranks), 11 census-bank sort, 5 block / grid teams of k_children,
+           12 k_split3_hard, 13 k_split3_ultra);
            -1 enable, -5 disable, -2 reset, -3 / -4 record the start / stop event of a bracket (accumulated in family 7) */
 
 #ifdef __cplusplus

@@ -44,8 +44,12 @@ void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long 
     (void)max_rounds;
     if (n_sub > 0) run_grid(n_sub, [&] { k_split3_attempts(p, m, i0, n_sub, out, 0, hard, hard_count); });
 }
-int launch_split3_hard(const Params &, const S3Map &, long long, const unsigned *, unsigned *, unsigned long long *, unsigned long long *, FlightTask *,
-                       unsigned long long, int, int, cudaStream_t) { return 0; }
+void launch_children_hard(const Params &, const S3Map &, const unsigned *, unsigned long long, GridItem *, unsigned long long *, int, int, int, cudaStream_t) {}
+int launch_children_ultra(const Params &, const S3Map &, const GridItem *, const unsigned long long *, unsigned long long *, int, cudaStream_t) { return 0; }
+void launch_split3_hard(const Params &, const S3Map &, long long, const unsigned *, GridItem *, unsigned long long *, FlightTask *, unsigned long long,
+                        int, int, int, cudaStream_t) {}
+int launch_split3_ultra(const Params &, const S3Map &, long long, const GridItem *, const unsigned long long *, FlightTask *, unsigned long long *, int,
+                        cudaStream_t) { return 0; }
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t)
 {
     if (n > 0) run_grid(n, [&] { k_split3_flights(p, fl, n); });

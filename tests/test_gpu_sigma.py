@@ -96,13 +96,18 @@ def test_third_split_block_teams(monkeypatch):
         g.close()
 
 
-@pytest.mark.parametrize("hard_rounds", [0, 1])
-def test_third_split_grid_team(monkeypatch, hard_rounds):
+@pytest.mark.parametrize("hard_rounds,grid_blocks", [(0, 0), (1, 0), (0, 1)])
+def test_third_split_grid_team(monkeypatch, hard_rounds, grid_blocks):
     """The last rung of the 3rd-split ladder: after 32 warp passes and hard_rounds * 512 block-team passes a sub-child is
     handed to k_split3_ultra, where the whole (cooperatively launched) grid tries one pass per thread between grid-wide
-    barriers.  Replay parity must not change: the lowest accepted pass wins, the tallies of the passes before it count."""
+    barriers.  Replay parity must not change: the lowest accepted pass wins, the tallies of the passes before it count.
+    grid_blocks = 1 shrinks the grid team to one block so that sub-children need several super-rounds (batches of 1, 2, 4 ..
+    passes per thread, tallies of the passes beyond the winner taken back)."""
+    if grid_blocks:
+        monkeypatch.setenv("C2D_GRID_TEAM_BLOCKS", str(grid_blocks))
     monkeypatch.setenv("C2D_SPLIT3_ROUNDS", "1")
     monkeypatch.setenv("C2D_SPLIT3_HARD_ROUNDS", str(hard_rounds))
+    monkeypatch.setenv("C2D_KN_CAP", "1000000000")                  # no child goes to a team: counter 9 counts sub-children only
     P = make_problem(nz=3, nr=3, nst=600, ngroups=64, split=(20, 10, 4, 1000), n_e=4.0e7)
     o, g = make_oracle(P), make_gpu(P)
     try:
@@ -121,14 +126,18 @@ def test_third_split_grid_team(monkeypatch, hard_rounds):
         g.close()
 
 
-@pytest.mark.parametrize("kn_cap", [1, 8])
-def test_children_block_teams(monkeypatch, kn_cap):
+@pytest.mark.parametrize("kn_cap,hard_rounds,grid_blocks", [(1, 32, 0), (8, 0, 0), (1, 1, 0), (1, 0, 1)])
+def test_children_block_teams(monkeypatch, kn_cap, hard_rounds, grid_blocks):
     """C2D_KN_CAP: a child whose first kn_cap trips through the electron / Klein-Nishina rejection loop (compb_2d.f label 100)
     fail, and whose photon has h nu >= 0.02 m c^2, is finished by a 256-thread team of k_children_hard (thread t makes trip
-    base + t on draws 5 k .. 5 k + 4 of the child's stream).  Hard photons: 100 keV Planckian boundaries (imcsurf2d), ~12 trips
+    base + t on draws 5 k .. 5 k + 4 of the child's stream), and after hard_rounds rounds of it by the whole grid
+    (k_children_ultra, cooperative launch).  Hard photons: 100 keV Planckian boundaries (imcsurf2d), ~12 trips
     per child on average.  Replay parity incl. the nelectron tally of every rejected trip."""
     from synth import make_surface
     monkeypatch.setenv("C2D_KN_CAP", str(kn_cap))
+    monkeypatch.setenv("C2D_KN_HARD_ROUNDS", str(hard_rounds))
+    if grid_blocks:
+        monkeypatch.setenv("C2D_GRID_TEAM_BLOCKS", str(grid_blocks))
     P = make_problem(nz=6, nr=6, nst=600, ngroups=100, split=(100, 10, 4, 10), n_e=2.0e7, rmin=0.1e16)
     S = make_surface(P, 3000, "planck", tbb=100.0)
     o, g = make_oracle(P), make_gpu(P, sigma_mode=1)
