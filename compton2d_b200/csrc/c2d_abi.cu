@@ -105,6 +105,14 @@ static int drain_queue(Ctx *c)
         if (trace) fprintf(stderr, "[c2d drain r%d] gen %d %-10s n=%llu t=%.3f ms\n", rank, gen, what, n,
                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
     };
+    auto lap_count = [&](const char *what, int gen, const unsigned long long *dev) -> int {
+        if (!trace) return 0;
+        unsigned long long v = 0;
+        if (dev) CU(cudaMemcpyAsync(&v, dev, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        lap(what, gen, v);
+        return 0;
+    };
     if (!c->d_cnt3) {
         CU(cudaMalloc(&c->d_cnt3, (size_t)(3 + 3 * 8) * 8));
         CU(cudaMalloc(&c->d_casc, 16 * 8));
@@ -171,16 +179,19 @@ static int drain_queue(Ctx *c)
             launch_children(p, mq, n_mine, c->n_sm, c->d_chard, (unsigned long long)c->chard_cap, c->d_casc, c->stream);
             c->timer_end();
             CU(cudaGetLastError());
+            if (int rc = lap_count("children", gen, c->d_casc)) return rc;
 #ifndef C2D_EMU
             if (n_mine > 0) {
                 // the ladder of the electron / Klein-Nishina rejection loop: thread -> block team -> the whole grid
                 c->timer_begin(5);
                 launch_children_hard(p, mq, c->d_chard, (unsigned long long)c->chard_cap, c->d_cultra, c->d_casc, c->kn_hard_rounds, c->kn_drain_rounds,
                                      c->n_sm, c->stream);
+                if (int rc = lap_count("c_hard", gen, c->d_casc + 2)) return rc;
                 const int e = launch_children_ultra(p, mq, c->d_cultra, c->d_casc + 2, c->d_casc + 8, c->n_sm, c->stream);
                 c->timer_end();
                 if (e) return fail(C2D_ECUDA, "cooperative launch of k_children_ultra failed: %s", cudaGetErrorString((cudaError_t)e));
                 CU(cudaGetLastError());
+                if (int rc = lap_count("c_ultra", gen, nullptr)) return rc;
             }
 #endif
         }
@@ -214,6 +225,7 @@ static int drain_queue(Ctx *c)
                 launch_split3_attempts(p, m, i0, ns, c->d_flights, c->split3_rounds, c->d_hard, c->d_casc + 3, c->stream);
                 c->timer_end();
                 CU(cudaGetLastError());
+                if (int rc = lap_count("attempts", gen, c->d_casc + 3)) return rc;
                 if (c->split3_rounds > 0) {
                     // the ladder: warp team -> block team (k_split3_hard) -> the whole grid (k_split3_ultra, cooperative launch)
                     const unsigned long long first_hard = (unsigned long long)c->split3_rounds * kWarp;
@@ -222,11 +234,13 @@ static int drain_queue(Ctx *c)
                                        c->split3_drain_rounds, c->n_sm, c->stream);
                     c->timer_end();
                     CU(cudaGetLastError());
+                    if (int rc = lap_count("s3_hard", gen, c->d_casc + 5)) return rc;
                     if (c->split3_hard_rounds >= 0) {
                         c->timer_begin(13);
                         const int e = launch_split3_ultra(p, m, i0, c->d_ultra, c->d_casc + 5, c->d_flights, c->d_casc + 8, c->n_sm, c->stream);
                         c->timer_end();
                         if (e) return fail(C2D_ECUDA, "cooperative launch of k_split3_ultra failed: %s", cudaGetErrorString((cudaError_t)e));
+                        if (int rc = lap_count("s3_ultra", gen, nullptr)) return rc;
                     }
                 }
                 c->timer_begin(6);
@@ -338,8 +352,19 @@ int Ctx::sigma_setup()
 
 int Ctx::sigma_ensure()
 {
-    if (dims.sigma_mode != 1 || sigma_ready) return 0;
+    if (sigma_ready) return 0;                                    // once per step: the tables that follow Pnt / f_nt / n_e
     sigma_ready = true;
+#ifndef C2D_EMU
+    if (dims.num_nt < 65536 && !getenv("C2D_NO_NT_GUIDE")) {
+        if (!d_nt_guide) CU(cudaMalloc(&d_nt_guide, (size_t)dims.nz * dims.nr * kNtGuide * sizeof(uint32_t)));
+        P.nt_guide = d_nt_guide;
+        timer_begin(4);
+        launch_nt_guide(P, d_nt_guide, stream);
+        timer_end();
+        CU(cudaGetLastError());
+    }
+#endif
+    if (dims.sigma_mode != 1) return 0;
     return sigma_build();
 }
 
@@ -523,7 +548,7 @@ int c2d_destroy(c2d_ctx *h)
     cudaFree(c->d_ref); cudaFree(c->d_static); cudaFree(c->d_step); cudaFree(c->d_prefix); cudaFree(c->d_surf); cudaFree(c->d_gen); cudaFree(c->d_f64); cudaFree(c->d_i64);
     cudaFree(c->d_events); cudaFree(c->d_q[0]); cudaFree(c->d_q[1]); cudaFree(c->d_q3); cudaFree(c->d_flights); cudaFree(c->d_hard); cudaFree(c->d_qcount);
     cudaFree(c->d_sig_static); cudaFree(c->d_sig_step); cudaFree(c->d_sig_ms);
-    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all); cudaFree(c->d_casc); cudaFree(c->d_chard); cudaFree(c->d_cultra); cudaFree(c->d_ultra);
+    cudaFree(c->d_sortkeys); cudaFree(c->d_qabs); cudaFree(c->d_litpool); cudaFree(c->d_cnt3); cudaFree(c->d_q3_all); cudaFree(c->d_nt_guide); cudaFree(c->d_casc); cudaFree(c->d_chard); cudaFree(c->d_cultra); cudaFree(c->d_ultra);
     cudaFree(c->d_fout_total); cudaFree(c->d_cnt_global); cudaFree(c->d_plasma); cudaFree(c->d_fpx);
     comm_free(c);
     free_bank(c->bank[0]); free_bank(c->bank[1]);

@@ -114,6 +114,7 @@ struct Ctx {
     double *d_sig_W = nullptr, *d_sig_AB = nullptr, *d_sig_T = nullptr, *d_sig_coef = nullptr, *d_sig_Kn = nullptr, *d_sig_M = nullptr;
     std::vector<double> h_gam0, h_opb;
     bool sigma_ready = false;
+    uint32_t *d_nt_guide = nullptr;        // nth2d's bisection brackets, rebuilt with the step tables (k_nt_guide)
     int sigma_setup();
     int sigma_build();
     int sigma_ensure();                    // builds the table on the step's first use

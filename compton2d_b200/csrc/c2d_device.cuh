@@ -142,6 +142,7 @@ struct Params {
     unsigned long long q_cap;
     AbsTask *qabs;                     // histories waiting for k_absdraw
     unsigned long long *qabs_count, qabs_cap;
+    const uint32_t *nt_guide;   // [zone][kNtGuide] lo | hi << 16: bracket of nth2d's bisection per 1/kNtGuide of rnum, or null
     int kn_cap;              // trips of the K-N rejection loop a thread makes before it hands its child to a block team (C2D_KN_CAP)
     int *lit_pool;                     // trial indices of the literal trials of queued histories
     unsigned long long *lit_count, lit_cap;
@@ -326,8 +327,10 @@ __device__ __forceinline__ double abs_uniform(const Params &p, uint64_t S, uint3
 // read-only global load (tables that no kernel of the same launch writes)
 #ifdef C2D_EMU
 __device__ __forceinline__ double c2d_ldg(const double *a) { return *a; }
+__device__ __forceinline__ uint32_t c2d_ldg(const uint32_t *a) { return *a; }
 #else
 __device__ __forceinline__ double c2d_ldg(const double *a) { return __ldg(a); }
+__device__ __forceinline__ uint32_t c2d_ldg(const uint32_t *a) { return __ldg(a); }
 #endif
 
 // ------------------------------------------------------------------------------------------ small helpers
@@ -733,14 +736,22 @@ __device__ __forceinline__ double comtot_one(const Params &p, int zi, double xnu
 // passes a record instead of tallying: up to four bins packed 16 bits each, `n` counts every draw.
 struct ElRec { uint64_t bins; int n; };
 
+constexpr int kNtGuide = 256;
 // nontherm2d.f:159-183
 __device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double &gamm, double &betb, int &ibin, ElRec *rec)
 {
     const double *P = p.Pnt + (size_t)zi * p.num_nt;
     double rnum = rng.next(p);
     rnum = (double)(int)(rnum * 1.e6) / 1.e6 + 1.e-6 * rng.next(p);
-    // first i in [2, num_nt] (1-based) with Pnt(i) > rnum; Pnt is a CDF (non-decreasing)
+    // first i in [2, num_nt] (1-based) with Pnt(i) > rnum; Pnt is a CDF (non-decreasing).  The step's guide table (k_nt_guide)
+    // brackets the answer for each 1/256 of rnum: the same bisection, started 0 - 2 steps from its end instead of 8
     int lo = 2, hi = p.num_nt;
+    if (p.nt_guide) {
+        int b = (int)(rnum * (double)kNtGuide);
+        if (b > kNtGuide - 1) b = kNtGuide - 1;
+        const uint32_t g = c2d_ldg(p.nt_guide + (size_t)zi * kNtGuide + b);
+        lo = (int)(g & 0xFFFFu); hi = (int)(g >> 16);
+    }
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         if (P[mid - 1] > rnum) hi = mid; else lo = mid + 1;
@@ -758,9 +769,19 @@ __device__ __forceinline__ void nth2d(const Params &p, Rng &rng, int zi, double 
 // compb_2d.f:55-95 (label 100): draw the electron and the collision cosine, K-N rejection
 struct ElDraw { double gamm, betb, omeg, znue; };
 // one trip through label 100: true = accepted.  Draws: 2 (nth2d) + omeg + tl [+ 1 for the K-N test unless znue < 1e-10].
-__device__ __forceinline__ bool compb2d_electron_once(const Params &p, Rng &rng, int zi, double znu, ElDraw &e, int &i_gam, ElRec *rec)
+// sigma_KN / sigma_T at photon energy znue (electron rest frame), compb_2d.f:75-88
+__device__ __forceinline__ double kn_xknot(double znue)
 {
-    nth2d(p, rng, zi, e.gamm, e.betb, i_gam, rec);
+    if (znue <= 1.e-2) return 1.0 - znue * (2.0 - znue * (5.2 - znue * (13.3 - 1.144e3 * znue / 3.5e1)));
+    const double znue3 = znue * znue * znue;
+    const double betz = 1.0 + 2.0 * znue;
+    const double gamz = znue * (znue - 2.0) - 2.0;
+    const double xxx = 4.0 * znue + 2.0 * znue3 * (1.0 + znue) / (betz * betz) + gamz * log(betz);
+    return 3.75e-1 * xxx / znue3;
+}
+// the trip after its nth2d draws: collision cosine (2 draws), K-N test (1 draw unless znue < 1e-10)
+__device__ __forceinline__ bool compb2d_trip_rest(const Params &p, Rng &rng, double znu, ElDraw &e)
+{
     e.omeg = 2.0 * rng.next(p) - 1.0;
     C2D_CLAMP8(e.omeg);
     const double tl = rng.next(p);
@@ -769,17 +790,12 @@ __device__ __forceinline__ bool compb2d_electron_once(const Params &p, Rng &rng,
     C2D_CLAMP8(e.omeg);
     e.znue = (1. - e.betb * e.omeg) * znu * e.gamm;
     if (e.znue < 1.e-10) return false;
-    double xknot;
-    if (e.znue <= 1.e-2) {
-        xknot = 1.0 - e.znue * (2.0 - e.znue * (5.2 - e.znue * (13.3 - 1.144e3 * e.znue / 3.5e1)));
-    } else {
-        const double znue3 = e.znue * e.znue * e.znue;
-        const double betz = 1.0 + 2.0 * e.znue;
-        const double gamz = e.znue * (e.znue - 2.0) - 2.0;
-        const double xxx = 4.0 * e.znue + 2.0 * znue3 * (1.0 + e.znue) / (betz * betz) + gamz * log(betz);
-        xknot = 3.75e-1 * xxx / znue3;
-    }
-    return !(rng.next(p) > xknot);
+    return !(rng.next(p) > kn_xknot(e.znue));
+}
+__device__ __forceinline__ bool compb2d_electron_once(const Params &p, Rng &rng, int zi, double znu, ElDraw &e, int &i_gam, ElRec *rec)
+{
+    nth2d(p, rng, zi, e.gamm, e.betb, i_gam, rec);
+    return compb2d_trip_rest(p, rng, znu, e);
 }
 // For znu >= kKnTeamZnu every trip consumes exactly 5 draws (znue >= (1 - 0.99999999) znu gamma >= 1e-10 always), so trip k of a
 // stream starts at draw 5 k and a TEAM of threads can try trips in parallel (k_children_hard): the rejection loop of a hard

@@ -21,6 +21,7 @@ void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const uns
 int launch_split3_ultra(const Params &p, const S3Map &m, long long i0, const GridItem *ultra, const unsigned long long *n_ultra, FlightTask *out,
                         unsigned long long *g_win, int n_sm, cudaStream_t st);
 void launch_split3_flights(const Params &p, const FlightTask *fl, long long n, cudaStream_t st);
+void launch_nt_guide(const Params &p, uint32_t *guide, cudaStream_t st);
 void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t st);
 void launch_sigma_build(const Params &p, double *W, double *AB, const double *Kn, int n_nodes, double *T, const double *M,
                         double *coef, cudaStream_t st);

@@ -113,6 +113,39 @@ __global__ void k_comtot_query(const __grid_constant__ Params p, long long n, co
 }
 
 #ifndef C2D_EMU
+// nth2d's guide (c2d_device.cuh): for every zone and every 1/kNtGuide of rnum the bracket [lo, hi] of the bisection
+//   lo = first i with Pnt(i) > b / kNtGuide, hi = first i with Pnt(i) > (b + 1) / kNtGuide   (the answer is monotone in rnum).
+// A zone whose Pnt(1 .. num_nt - 1) is not non-decreasing gets the full range [2, num_nt]: the plain bisection.
+__device__ __forceinline__ int nt_first_above(const double *P, int num_nt, double x)
+{
+    int lo = 2, hi = num_nt;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (P[mid - 1] > x) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+__global__ void __launch_bounds__(kNtGuide) k_nt_guide(const __grid_constant__ Params p, uint32_t *guide)
+{
+    __shared__ int s_bad;
+    const int zi = blockIdx.x, b = threadIdx.x;
+    const double *P = p.Pnt + (size_t)zi * p.num_nt;
+    if (b == 0) s_bad = 0;
+    __syncthreads();
+    for (int i = 1 + b; i < p.num_nt - 1; i += kNtGuide)
+        if (P[i] < P[i - 1]) s_bad = 1;
+    __syncthreads();
+    int lo = 2, hi = p.num_nt;
+    if (!s_bad) {
+        lo = nt_first_above(P, p.num_nt, (double)b / kNtGuide);
+        hi = nt_first_above(P, p.num_nt, (double)(b + 1) / kNtGuide);
+    }
+    guide[(size_t)zi * kNtGuide + b] = (uint32_t)lo | ((uint32_t)hi << 16);
+}
+void launch_nt_guide(const Params &p, uint32_t *guide, cudaStream_t st)
+{
+    k_nt_guide<<<p.nzone, kNtGuide, 0, st>>>(p, guide);
+}
 void launch_sigma_kn(const Params &p, const double *xs, const int *ms, int n_nodes, double *Kn, cudaStream_t st)
 {
     const long long n = (long long)n_nodes * (p.num_nt - 1);

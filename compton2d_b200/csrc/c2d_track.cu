@@ -133,6 +133,11 @@ constexpr int kHistMax = 1024;
 #endif
 
 
+// nelectron tallies of the team kernels: into the block's copy (or global memory when num_nt is too large for it)
+__device__ __forceinline__ void tally_bin(const Params &p, unsigned *hist, unsigned bin, int sign)
+{
+    if (hist) atomicAdd(hist + bin, (unsigned)sign); else atomicAdd(p.nelectron + bin, (unsigned long long)(long long)sign);
+}
 // ------------------------------------------------------------------------------------------ rare paths of a history
 // A trial flight that may collide is flown literally (imctrk2d.f:126-695 body for scat_flag = -1) with comtot evaluated per
 // crossing (the same values as the per-history cache comac_ar of l.175-183).  It makes its own deposits, so the share the
@@ -603,10 +608,7 @@ __global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ P
             if (ok) atomicMin(&win, (int)threadIdx.x);
             __syncthreads();
             const int first = win;
-            if ((int)threadIdx.x <= first) {
-                const unsigned bin = (unsigned)(rec.bins & 0xFFFFull);
-                if (hist) atomicAdd(hist + bin, 1u); else atomicAdd(p.nelectron + bin, 1ull);
-            }
+            if ((int)threadIdx.x <= first) tally_bin(p, hist, (unsigned)(rec.bins & 0xFFFFull), 1);
             if (first != 0x7fffffff) {
                 if ((int)threadIdx.x == first) child_finish(p, c, rng, e, i_gam);
                 resolved = true;
@@ -623,10 +625,6 @@ __global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ P
 
 // children the block teams gave up on: the grid is the team (see k_split3_ultra for the batching and the winner slots)
 constexpr int kGridBatchMax = 64;
-__device__ __forceinline__ void tally_bin(const Params &p, unsigned *hist, unsigned bin, int sign)
-{
-    if (hist) atomicAdd(hist + bin, (unsigned)sign); else atomicAdd(p.nelectron + bin, (unsigned long long)(long long)sign);
-}
 __global__ void __launch_bounds__(256) k_children_ultra(const __grid_constant__ Params p, const S3Map m, const GridItem *ultra,
                                                         const unsigned long long *n_ultra_dev, unsigned long long *g_win)
 {
@@ -722,6 +720,9 @@ __device__ __forceinline__ bool split3_pass(const Params &p, const Split3Sub &u,
     ElDraw e;
     compb2d_electron(p, rng, u.zi, u.znu, e, i_gam, &rec);
     if (!(4.0 * e.gamm * e.gamm * (1.0 + 1.e-9) > u.gain_min)) return false;
+    // (measured on the B200: moving the 2 % of the passes that get here out of line, warp-aggregating the tallies, or deciding
+    // the K-N test of a hopeless trip from bounds on znue without its two cosine draws all make k_split3_attempts slower --
+    // it runs at 32 registers and 64 warps / SM and is bound by latency, not by instruction count)
     P = u.task->p;
     P.ew = u.ewcsv / p.split3;
     if (!compb2d_finish(p, rng, P, e, u.trigger)) return false;
@@ -732,10 +733,7 @@ __device__ __forceinline__ bool split3_pass(const Params &p, const Split3Sub &u,
 __device__ __forceinline__ void split3_commit(const Params &p, const Split3Sub &u, uint64_t attempt, const ElRec &rec, unsigned *hist)
 {
     if (rec.n <= 4) {
-        for (int k = 0; k < rec.n; k++) {
-            const unsigned bin = (unsigned)((rec.bins >> (16 * k)) & 0xFFFFull);
-            if (hist) atomicAdd(hist + bin, 1u); else atomicAdd(p.nelectron + bin, 1ull);
-        }
+        for (int k = 0; k < rec.n; k++) tally_bin(p, hist, (unsigned)((rec.bins >> (16 * k)) & 0xFFFFull), 1);
     } else {                                                      // > 4 K-N rejections in one pass: replay it, tallying
         Rng r2; r2.stream(mix64(u.S_sub, attempt));
         ElDraw e2; int ig2;
