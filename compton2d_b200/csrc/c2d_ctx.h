@@ -68,7 +68,7 @@ struct Ctx {
     int kn_cap = 64;                       // trips of the K-N rejection loop a thread makes before a block team takes the child (C2D_KN_CAP)
     // block teams -> grid team: after *_hard_rounds rounds whatever happens (tests force the path with 0), or after *_drain_rounds
     // rounds once half the blocks have run out of work (C2D_KN_HARD_ROUNDS, C2D_KN_DRAIN_ROUNDS, C2D_SPLIT3_HARD_ROUNDS, C2D_SPLIT3_DRAIN_ROUNDS)
-    int kn_hard_rounds = 1 << 22, kn_drain_rounds = 128;          // x 256 trips
+    int kn_hard_rounds = 1 << 22, kn_drain_rounds = 1024;          // x 256 trips
     int split3_drain_rounds = 128;                                 // x 512 passes
     int split3_hard_rounds = 1 << 21;          // block-team rounds before a sub-child goes to the grid team (C2D_SPLIT3_HARD_ROUNDS)
     int split3_rounds = 64;                // warp rounds before a sub-child goes to k_split3_hard (C2D_SPLIT3_ROUNDS; measured 8..128)
