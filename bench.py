@@ -259,7 +259,8 @@ def lc_bench(g, hbm, n_events=100_000_000):
     cfg = parse_lc_input(MRK421_LC)
     per_rec = None
     try:
-        per_rec = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())["k_lc_reduce_dram_bytes_per_record"]
+        tf = ROOT / "profiles" / "r02_traffic.json"
+        per_rec = json.loads((tf if tf.exists() else ROOT / "profiles" / "r01_traffic.json").read_text())["k_lc_reduce_dram_bytes_per_record"]
     except Exception:
         pass
     out = {"kernel": "k_lc_reduce", "events": n_events, "bins": "postprocessing/mrk421_lc.input (1 mu window, 7 bands)"}
