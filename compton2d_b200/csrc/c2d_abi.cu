@@ -1183,6 +1183,25 @@ int c2d_comtot(c2d_ctx *h, int64_t n, const int32_t *zone, const double *xnu, in
     return 0;
 }
 
+int c2d_selftest_gap(c2d_ctx *h, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *slow_path)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c || !c->inited) return fail(C2D_ESTATE, "context not initialised");
+    if (n < 0 || !mismatches) return fail(C2D_EINVAL, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    unsigned long long *d = nullptr, host[2] = {0, 0};
+    CU(cudaMalloc(&d, 16));
+    CU(cudaMemsetAsync(d, 0, 16, c->stream));
+    if (n > 0) launch_selftest_gap(c->P, n, seed, d, c->n_sm, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(host, d, 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    *mismatches = (int64_t)host[0];
+    if (slow_path) *slow_path = (int64_t)host[1];
+    return 0;
+}
+
 int c2d_kernel_time_ms(c2d_ctx *h, int which, float *ms, int64_t *launches)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);

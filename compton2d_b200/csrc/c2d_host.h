@@ -8,6 +8,7 @@ void launch_history_volume(const Params &p, long long first, long long n, long l
 void launch_history_surface(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_history_census(const Params &p, long long first, long long n, long long stride, cudaStream_t st);
 void launch_absdraw(const Params &p, const AbsTask *q, const unsigned long long *n_dev, int n_sm, cudaStream_t st);
+void launch_selftest_gap(const Params &p, long long n, unsigned long long seed, unsigned long long *out, int n_sm, cudaStream_t st);
 void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, unsigned *hard, unsigned long long hard_cap,
                      unsigned long long *hard_count, cudaStream_t st);
 void launch_children_hard(const Params &p, const S3Map &m, const unsigned *hard, unsigned long long hard_cap, GridItem *ultra,

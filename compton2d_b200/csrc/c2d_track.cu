@@ -955,6 +955,27 @@ static unsigned coop_grid(int n_sm, int per_sm)
     if (const char *e = getenv("C2D_GRID_TEAM_BLOCKS")) return (unsigned)std::min(std::max(1, atoi(e)), n_sm * per_sm);
     return (unsigned)(n_sm * per_sm);
 }
+__global__ void k_selftest_gap(const __grid_constant__ Params p, long long n, unsigned long long seed, unsigned long long *out)
+{
+    unsigned long long bad = 0, slow = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        uint32_t o[4];
+        philox4x32_10((uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)i, (uint32_t)(i >> 32), p.key0, p.key1, o);
+        for (int h = 0; h < 2; h++) {
+            const double U = h ? u52(o[2], o[3]) : u52(o[0], o[1]);
+            const double exact = floor(log(U) * kInvLnQ);
+            if (trial_gap(U) != exact) bad++;
+            const float tf = __logf((float)U) * (float)kInvLnQ, fr = tf - floorf(tf);
+            if (!(fr > 5.e-3f && fr < 1.f - 5.e-3f)) slow++;
+        }
+    }
+    if (bad) atomicAdd(out, bad);
+    if (slow) atomicAdd(out + 1, slow);
+}
+void launch_selftest_gap(const Params &p, long long n, unsigned long long seed, unsigned long long *out, int n_sm, cudaStream_t st)
+{
+    k_selftest_gap<<<n_sm * 8, 256, 0, st>>>(p, n, seed, out);
+}
 void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm, unsigned *hard, unsigned long long hard_cap,
                      unsigned long long *hard_count, cudaStream_t st)
 {

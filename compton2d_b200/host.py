@@ -286,6 +286,13 @@ class Compton2d:
         _l.check(self.L.c2d_gamma_bar(self.h, th.size, th.ctypes.data, g.ctypes.data, gt.ctypes.data))
         return g, gt
 
+    def selftest_gap(self, n, seed=1):
+        """Candidate gaps of the trial uniforms: fast path vs the double-precision expression over 2 n uniforms
+        -> (mismatches, uniforms that took the slow path)."""
+        bad, slow = C.c_int64(0), C.c_int64(0)
+        _l.check(self.L.c2d_selftest_gap(self.h, int(n), int(seed), C.byref(bad), C.byref(slow)))
+        return bad.value, slow.value
+
     def update(self, *, time, dt, f_nt, Pnt, n_e, B_field, tea, tna, vol, Eloss_sy, ec_old, turb_lev, gmin, gmax,
                p_nth, amxwl, f_pair=None, n_field=None, ecens=None, F_IC=None, lnL=20.0, r_esc=0.3, r_acc=1.0,
                inj=None, flare=None, group=None):

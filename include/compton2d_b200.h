@@ -448,6 +448,12 @@ void c2d_pack_bin_last(const double *common, int jmax, int kmax, int nbin, int n
 void c2d_unpack_bin_first(const double *dense, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *common);
 void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int nz, int nr, double *common);
 
+/* ---- self-tests of the device arithmetic --------------------------------------------------- */
+int c2d_selftest_gap(c2d_ctx *ctx, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *slow_path);
+        /* candidate gaps of the trial uniforms, floor(ln U / ln(255/256)): the single-precision fast path of the tracker
+           against the double-precision expression it stands for, over 2 n uniforms of Philox stream `seed`;
+           mismatches must come back 0; slow_path = how many uniforms fell back to the double-precision log */
+
 /* ---- measurement hooks (bench.py) ------------------------------------------------------------ */
 int c2d_kernel_time_ms(c2d_ctx *ctx, int which, float *ms, int64_t *launches);
         /* CUDA-event time per kernel family on the library's stream.  which >= 0: read family (0 k_history, 1 k_children,

@@ -34,6 +34,7 @@ template <class F> static void run_grid(long long n, F body)
             body();
         }
 }
+void launch_selftest_gap(const Params &, long long, unsigned long long, unsigned long long *, int, cudaStream_t) {}   // one path only in this build
 void launch_children(const Params &p, const S3Map &m, long long n_mine, int, unsigned *, unsigned long long, unsigned long long *, cudaStream_t)
 {
     for (long long i = 0; i < n_mine; i++) children_one(p, m, i, nullptr, 0ull, nullptr);     // no team kernels in the serial build

@@ -183,3 +183,17 @@ def test_replay_parity_compton_reflection(cr_sent, sigma_mode):
     if cr_sent != 1:
         ev = rg["events"]
         assert ((ev[:, 4] == 0) & (ev[:, 5] > 0) & (ev[:, 1] >= 1.0)).sum() > 10      # reflected at the outer disk
+
+
+def test_candidate_gap_fast_path_is_exact():
+    """TrialGen's gaps floor(ln U / ln(255/256)) come from the hardware's single-precision logarithm whenever the product is
+    5e-3 away from an integer (error bound 2.3e-3, c2d_device.cuh:trial_gap); the double-precision expression decides the
+    rest.  1e9 Philox uniforms: no disagreement, about 1 % on the slow path."""
+    P = make_problem(nz=3, nr=3, nst=600, ngroups=64)
+    g = make_gpu(P)
+    try:
+        bad, slow = g.selftest_gap(500_000_000, seed=12345)
+        assert bad == 0
+        assert 0.005 < slow / 1.0e9 < 0.02
+    finally:
+        g.close()
