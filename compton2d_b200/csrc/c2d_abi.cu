@@ -1183,6 +1183,24 @@ int c2d_comtot(c2d_ctx *h, int64_t n, const int32_t *zone, const double *xnu, in
     return 0;
 }
 
+int c2d_pref_calc(c2d_ctx *h, int n_ref, double *E_ref, double *P_ref)
+{
+    Ctx *c = reinterpret_cast<Ctx *>(h);
+    if (!c) return fail(C2D_EINVAL, "NULL ctx");
+    if (n_ref < 2 || !E_ref || !P_ref) return fail(C2D_EINVAL, "c2d_pref_calc: n_ref = %d, E_ref / P_ref must not be NULL", n_ref);
+    CU(cudaSetDevice(c->device));
+    double *d = nullptr;
+    const size_t n = (size_t)n_ref * n_ref + n_ref;
+    CU(cudaMalloc(&d, n * 8));
+    launch_pref_calc(n_ref, d, d + n_ref, c->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(E_ref, d, (size_t)n_ref * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(P_ref, d + n_ref, (size_t)n_ref * n_ref * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d);
+    return 0;
+}
+
 int c2d_selftest_gap(c2d_ctx *h, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *slow_path)
 {
     Ctx *c = reinterpret_cast<Ctx *>(h);

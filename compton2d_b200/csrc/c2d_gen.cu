@@ -121,7 +121,52 @@ __global__ void __launch_bounds__(64) k_volume_cdf(const __grid_constant__ GenPa
     q.sum_g1[zi] = sum_g_1;
 }
 
+// == Pref_calc (ref_matrix.f:7-89): the Green's function of Compton reflection off cold matter (White, Lightman & Zdziarski
+// 1988) on the grid E_ref(n) = 10^(3 (n-1) / n_ref) keV, as the cumulative distribution over the outgoing energy that
+// imcleak samples (imcleak2d.f:126-146): P_ref(n_out, n_in), column n_in contiguous.  Below E_trans = 20 keV a photon keeps
+// its energy (a step at n_out = n_in).  One thread per incoming energy: the column is a running sum.  The REAL*4 literals
+// of the source (1.12, the exponents 0.785 1.04 .51 .824 .85) are kept as the single-precision values Fortran promotes.
+__global__ void k_pref_calc(int n_ref, double *E_ref, double *P_ref)
+{
+    const int n_in = (int)(blockIdx.x * blockDim.x + threadIdx.x);           // 0-based
+    if (n_in >= n_ref) return;
+    const double dE = exp(log(1.e3) / (double)n_ref), e_trans = 20.0;
+    double e_in = 1.0;
+    for (int n = 1; n <= n_in; n++) e_in = e_in * dE;                         // E_ref(n) = E_ref(n-1) dE, as the reference rounds it
+    E_ref[n_in] = e_in;                                                       // (every thread writes its own entry)
+    double *col = P_ref + (size_t)n_in * n_ref;
+    for (int n_out = n_in + 1; n_out < n_ref; n_out++) col[n_out] = 1.0;
+    if (e_in <= e_trans) {
+        for (int n_out = 0; n_out < n_in; n_out++) col[n_out] = 0.0;
+        col[n_in] = 1.0;
+        return;
+    }
+    const double x0 = 1.957e-3 * e_in, y0 = 1.0 / x0, dyc = 1.e3 - y0;
+    const double A = 5.6e-1 + (double)1.12f / pow(y0, (double)0.785f) - 3.4e-1 / pow(y0, (double)1.04f);
+    const double al = -3.e-1 / pow(y0, (double).51f) + 6.e-2 / pow(y0, (double).824f);
+    const double beta = 3.7e-1 - pow(y0, (double).85f);
+    const double tail = (fabs(al + .5) < 1.e-4) ? (2.0 + log(.5 * dyc)) : (2.0 + (pow(.5 * dyc, al + .5) - 1.0) / (al + .5));
+    const double B = (1.0 - A * tail / sqrt(dyc))
+                     / (pow(y0, 1.0 - beta) * pow(y0 + 2.0, beta) * (pow(1.0 + 2.0 / y0, 1.0 - beta) - 1.0)) * (1.0 - beta);
+    double sum = 0.0, e_out = 1.0;
+    for (int n_out = 0; n_out <= n_in; n_out++) {
+        if (n_out > 0) e_out = e_out * dE;
+        const double x1 = 1.957e-3 * e_out, dy = 1.0 / x1 - y0;
+        double Gy;
+        if (dy < 2.0) Gy = B * pow((y0 + 2.0) / (y0 + dy), beta);
+        else if (dy < dyc) Gy = A * pow(dyc / dy, al) / pow(dy, 1.5);
+        else Gy = A / pow(dy, 1.5);
+        sum = sum + (Gy / (x1 * x1)) * (dE * x1);
+        col[n_out] = sum;
+    }
+    for (int n_out = 0; n_out <= n_in; n_out++) col[n_out] = col[n_out] / sum;
+}
+
 #ifndef C2D_EMU
+void launch_pref_calc(int n_ref, double *E_ref, double *P_ref, cudaStream_t st)
+{
+    k_pref_calc<<<(n_ref + 63) / 64, 64, 0, st>>>(n_ref, E_ref, P_ref);
+}
 void launch_volume_em(const GenParams &q, cudaStream_t st)
 {
     const long long n = (long long)q.nzone * q.nv;

@@ -39,6 +39,7 @@ struct GenParams {
     double *sum_th, *sum_g1;                        // [zone] raw thermalised emissivity sum, sum_g_1
 };
 void launch_volume_em(const GenParams &q, cudaStream_t st);
+void launch_pref_calc(int n_ref, double *E_ref, double *P_ref, cudaStream_t st);
 
 // Fokker-Planck (c2d_fp.cu)
 struct FpParams;

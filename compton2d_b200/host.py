@@ -44,6 +44,20 @@ class _CudaView:
                                          "version": 2, "strides": None}
 
 
+def pref_calc(n_ref=500, device=0):
+    """== Pref_calc (ref_matrix.f:7-89) on the device -> (E_ref [n_ref], P_ref [n_in][n_out], i.e. COMMON /reflection/ P_ref(n_out,
+    n_in) as it lies in memory): the Compton-reflection Green's function tables Compton2d(cr_sent=..., E_ref=, P_ref=) takes."""
+    L = _l.load()
+    h = C.c_void_p()
+    _l.check(L.c2d_create(C.byref(h), int(device)))
+    try:
+        E, P = np.zeros(n_ref), np.zeros((n_ref, n_ref))
+        _l.check(L.c2d_pref_calc(h, int(n_ref), E.ctypes.data, P.ctypes.data))
+    finally:
+        L.c2d_destroy(h)
+    return E, P
+
+
 class Compton2d:
     def __init__(self, *, nz, nr, z, r, rmin=0.0, zmin=0.0, E_ph, E_field, E_gg, gnt, hu, Elcmin=(), Elcmax=(),
                  mu=(1.0,), pair_switch=0, cr_sent=0, spec_switch=0, E_ref=None, P_ref=None, W_abs=None, split=(1000, 1000, 300, 10), rseed=9857,

@@ -151,7 +151,7 @@ EXPORTS = ["c2d_create", "c2d_init", "c2d_destroy", "c2d_last_error", "c2d_versi
            "c2d_census_export", "c2d_census_import", "c2d_events_drain", "c2d_ic_loss", "c2d_update_fp",
            "c2d_pack_bin_first", "c2d_pack_bin_last", "c2d_unpack_bin_first", "c2d_unpack_bin_last",
            "c2d_kernel_time_ms", "c2d_comtot", "c2d_surf_begin", "c2d_imcsurf", "c2d_step_begin_gen", "c2d_step_tables_read",
-           "c2d_lc_select", "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar", "c2d_selftest_gap",
+           "c2d_lc_select", "c2d_lc_begin", "c2d_lc_accumulate", "c2d_lc_accumulate_events", "c2d_lc_read", "c2d_lc_device", "c2d_lc_bench", "c2d_gamma_bar", "c2d_selftest_gap", "c2d_pref_calc",
            "c2d_census_write", "c2d_census_read", "c2d_events_write", "c2d_format_e14_7", "c2d_tally_reduce", "c2d_finalize",
            "c2d_comm_unique_id", "c2d_comm_init", "c2d_comm_init_ext", "c2d_comm_info", "c2d_comm_destroy",
            "c2d_plasma_set", "c2d_plasma_get", "c2d_step", "c2d_common_step_begin", "c2d_common_collect", "c2d_common_update"]
@@ -206,6 +206,7 @@ def load():
     L.c2d_format_e14_7.restype = None
     L.c2d_gamma_bar.argtypes = [vp, C.c_int64, vp, vp, vp]
     L.c2d_selftest_gap.argtypes = [vp, C.c_int64, C.c_uint64, vp, vp]
+    L.c2d_pref_calc.argtypes = [vp, C.c_int, vp, vp]
     L.c2d_lc_select.argtypes = [vp, C.c_int]
     L.c2d_lc_begin.argtypes = [vp, C.POINTER(LcConfig)]
     L.c2d_lc_accumulate.argtypes = [vp]

@@ -448,6 +448,13 @@ void c2d_pack_bin_last(const double *common, int jmax, int kmax, int nbin, int n
 void c2d_unpack_bin_first(const double *dense, int nbin_pad, int jmax, int kmax, int nbin, int nz, int nr, double *common);
 void c2d_unpack_bin_last(const double *dense, int jmax, int kmax, int nbin, int nz, int nr, double *common);
 
+int c2d_pref_calc(c2d_ctx *ctx, int n_ref, double *E_ref, double *P_ref);
+        /* == Pref_calc (ref_matrix.f:7-89): E_ref[n_ref] and the reflection Green's function P_ref(n_out, n_in) as COMMON
+           /reflection/ holds it (column n_in contiguous), built on the device -> host arrays the caller hands to c2d_init in
+           c2d_dims when cr_sent = 2 / 4 or a hot lower boundary reflects (imcleak2d.f:124-158).  The ctx only needs
+           c2d_create.  W_abs (Wref_calc, ref_matrix.f:101-499: photo-absorption of a partially ionised disk, 400 lines of
+           atomic DATA) is not rebuilt: it stays an input. */
+
 /* ---- self-tests of the device arithmetic --------------------------------------------------- */
 int c2d_selftest_gap(c2d_ctx *ctx, int64_t n, uint64_t seed, int64_t *mismatches, int64_t *slow_path);
         /* candidate gaps of the trial uniforms, floor(ln U / ln(255/256)): the single-precision fast path of the tracker

@@ -74,6 +74,10 @@ void launch_volume_em(const GenParams &q, cudaStream_t)
     for (int b = 0; b < (q.nzone + 63) / 64; b++)
         for (unsigned t = 0; t < 64; t++) { blockIdx.x = (unsigned)b; threadIdx.x = t; k_volume_cdf(q); }
 }
+void launch_pref_calc(int n_ref, double *E_ref, double *P_ref, cudaStream_t)
+{
+    run_grid(n_ref, [&] { k_pref_calc(n_ref, E_ref, P_ref); });
+}
 void launch_comtot_query(const Params &p, long long n, const int *zone, const double *xnu, double *out, cudaStream_t)
 {
     if (n > 0) run_grid(n, [&] { k_comtot_query(p, n, zone, xnu, out); });

@@ -48,3 +48,17 @@ def test_step_prologue_rejects_foreign_energy_grid():
         assert e.value.code == 2
     finally:
         gpu.close()
+
+
+@pytest.mark.gpu
+def test_pref_calc_on_the_device_matches_reference_binary():
+    """k_pref_calc on the B200 against the binary's COMMON /reflection/ (see tests/test_host_logic_cpu.py for the g++ build)."""
+    from pathlib import Path
+    from compton2d_b200.host import pref_calc
+    g = np.load(Path(__file__).resolve().parent / "golden" / "refbin_reflect.npz")
+    E, P = pref_calc(500)
+    ref = g["c0_A/p_ref"]
+    ref = ref if np.all(ref[0, 1:] == 1.0) else ref.T
+    assert np.abs(E / g["c0_A/e_ref"] - 1.0).max() < 1e-13
+    assert np.array_equal(P == 1.0, ref == 1.0) and np.array_equal(P == 0.0, ref == 0.0)
+    assert np.abs(P - ref).max() < 1e-12

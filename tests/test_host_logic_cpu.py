@@ -465,3 +465,18 @@ def test_closed_step_two_ranks_library_collectives(emu, tmp_path):
     assert int(two["global_ndxout"]) == rep["ndxout"] and 0 < int(two["local_ndxout"]) < rep["ndxout"]
     for k in ("edep", "ecens", "n_field", "fout_total"):
         assert np.abs(two[k] - one[k]).max() <= 1e-12 * np.abs(one[k]).max(), k
+
+
+def test_pref_calc_matches_reference_binary(emu):
+    """c2d_pref_calc (k_pref_calc, csrc/c2d_gen.cu) == Pref_calc (ref_matrix.f:7-89): E_ref and the 500 x 500 reflection Green's
+    function against COMMON /reflection/ of the unmodified binary (tests/golden/refbin_reflect.npz, snapshot c0_A).  ifort's pow
+    and glibc's differ in the last bits: 1e-12."""
+    from compton2d_b200.host import pref_calc
+    g = np.load(ROOT / "tests" / "golden" / "refbin_reflect.npz")
+    E, P = pref_calc(500)
+    assert np.abs(E / g["c0_A/e_ref"] - 1.0).max() < 1e-13
+    ref = g["c0_A/p_ref"]
+    ref = ref if np.all(ref[0, 1:] == 1.0) else ref.T          # [n_in][n_out]: above the incoming energy the CDF is 1
+    assert np.array_equal(P == 1.0, ref == 1.0) and np.array_equal(P == 0.0, ref == 0.0)
+    assert np.abs(P - ref).max() < 1e-12
+    assert (np.diff(P, axis=1) >= 0).all()
