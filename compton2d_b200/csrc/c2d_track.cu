@@ -510,6 +510,13 @@ __device__ __forceinline__ void child_flight(const Params &p, Photon &P, Rng &rn
 
 // one thread per (collision, child ii): the split2 loop of imctrk2d.f:619-689.  Children that trigger
 // the 3rd split (l.639) are queued for k_split3 instead of looping split3 times in one thread.
+// resident blocks per SM the team kernels are compiled for (registers = 65536 / (blocks x threads)); measured, see DESIGN.md
+#ifndef C2D_TEAM_MINB
+#define C2D_TEAM_MINB 1
+#endif
+#ifndef C2D_KN_MINB
+#define C2D_KN_MINB 2
+#endif
 struct ChildCtx { const CollTask *task; int ii, zi; double ewold; uint64_t S_child; };
 __device__ __forceinline__ void child_ctx(const Params &p, const S3Map &m, long long i, ChildCtx &c)
 {
@@ -572,7 +579,7 @@ __global__ void __launch_bounds__(128) k_children(const __grid_constant__ Params
 // One block per listed child: thread t of the team makes trip base + t of the child's electron loop (draws 5 k .. 5 k + 4 of its
 // stream), the lowest accepted trip wins, the nth2d tallies of the trips up to it are committed -- exactly the draws the
 // sequential loop makes.  Blocks fetch children from a device-side counter (the loops' lengths differ by orders of magnitude).
-__global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ Params p, const S3Map m, const unsigned *hard,
+__global__ void __launch_bounds__(256, C2D_KN_MINB) k_children_hard(const __grid_constant__ Params p, const S3Map m, const unsigned *hard,
                                                        unsigned long long hard_cap, const unsigned long long *n_hard_dev,
                                                        unsigned long long *fetch, int max_rounds, int drain_rounds, GridItem *ultra,
                                                        unsigned long long *ultra_count)
@@ -625,7 +632,7 @@ __global__ void __launch_bounds__(256) k_children_hard(const __grid_constant__ P
 
 // children the block teams gave up on: the grid is the team (see k_split3_ultra for the batching and the winner slots)
 constexpr int kGridBatchMax = 64;
-__global__ void __launch_bounds__(256) k_children_ultra(const __grid_constant__ Params p, const S3Map m, const GridItem *ultra,
+__global__ void __launch_bounds__(256, C2D_KN_MINB) k_children_ultra(const __grid_constant__ Params p, const S3Map m, const GridItem *ultra,
                                                         const unsigned long long *n_ultra_dev, unsigned long long *g_win)
 {
     namespace cg = cooperative_groups;
@@ -790,7 +797,7 @@ __global__ void __launch_bounds__(128, C2D_S3_MINB) k_split3_attempts(const __gr
 }
 
 #ifndef C2D_EMU
-__global__ void __launch_bounds__(512) k_split3_hard(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *hard,
+__global__ void __launch_bounds__(512, C2D_TEAM_MINB) k_split3_hard(const __grid_constant__ Params p, const S3Map m, long long i0, const unsigned *hard,
                                                      const unsigned long long *n_hard_dev, FlightTask *out, unsigned long long first_attempt,
                                                      int max_rounds, int drain_rounds, GridItem *ultra, unsigned long long *ultra_count,
                                                      unsigned long long *fetch)
@@ -861,7 +868,7 @@ __device__ __forceinline__ void split3_tally(const Params &p, const Split3Sub &u
         if (ok) break;
     }
 }
-__global__ void __launch_bounds__(512) k_split3_ultra(const __grid_constant__ Params p, const S3Map m, long long i0, const GridItem *ultra,
+__global__ void __launch_bounds__(512, C2D_TEAM_MINB) k_split3_ultra(const __grid_constant__ Params p, const S3Map m, long long i0, const GridItem *ultra,
                                                       const unsigned long long *n_ultra_dev, FlightTask *out, unsigned long long *g_win)
 {
     namespace cg = cooperative_groups;
@@ -987,7 +994,7 @@ void launch_children(const Params &p, const S3Map &m, long long n_mine, int n_sm
 void launch_children_hard(const Params &p, const S3Map &m, const unsigned *hard, unsigned long long hard_cap, GridItem *ultra,
                           unsigned long long *counts, int max_rounds, int drain_rounds, int n_sm, cudaStream_t st)
 {
-    k_children_hard<<<n_sm * 4, 256, 0, st>>>(p, m, hard, hard_cap, counts, counts + 1, max_rounds, drain_rounds, ultra, counts + 2);
+    k_children_hard<<<n_sm * 2 * C2D_KN_MINB, 256, 0, st>>>(p, m, hard, hard_cap, counts, counts + 1, max_rounds, drain_rounds, ultra, counts + 2);
 }
 int launch_children_ultra(const Params &p, const S3Map &m, const GridItem *ultra, const unsigned long long *n_ultra, unsigned long long *g_win,
                           int n_sm, cudaStream_t st)
@@ -1008,7 +1015,7 @@ void launch_split3_attempts(const Params &p, const S3Map &m, long long i0, long 
 void launch_split3_hard(const Params &p, const S3Map &m, long long i0, const unsigned *hard, GridItem *ultra, unsigned long long *counts,
                         FlightTask *out, unsigned long long first_attempt, int max_rounds, int drain_rounds, int n_sm, cudaStream_t st)
 {
-    k_split3_hard<<<n_sm * 2, 512, 0, st>>>(p, m, i0, hard, counts, out, first_attempt, max_rounds < 0 ? 0x7fffffff : max_rounds, drain_rounds, ultra,
+    k_split3_hard<<<n_sm * 2 * C2D_TEAM_MINB, 512, 0, st>>>(p, m, i0, hard, counts, out, first_attempt, max_rounds < 0 ? 0x7fffffff : max_rounds, drain_rounds, ultra,
                                             counts + 2, counts + 1);
 }
 // g_win: 3 slots = ~0
