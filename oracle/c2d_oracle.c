@@ -258,12 +258,130 @@ double orc_abs_uniform(const uint32_t key[2], uint64_t S, uint32_t t, uint32_t k
     return ((double)(w >> 12) + 0.5) * (1.0 / 4503599627370496.0);
 }
 
-/* rand.f:195-223 fibran (rand_switch=2 branch) / Philox extension */
+/* ---- rand_switch = 1: Knuth's lagged-Fibonacci generator (The Art of Computer Programming vol. 2, 3rd ed., 3.6: ranf_array /
+ * ranf_start with lags 100 and 37, including the 2002 modification), as rand.f:230-316 has it, and the reference's integer
+ * variant with lags 19937 / 7083 that deals out one seed per zone and per boundary ring (seed_zone, rand.f:9-88). ---- */
+#define KN_KK 100
+#define KN_LL 37
+static double frac1(double y) { return y - (double)(int)y; }          /* Y - IDINT(Y), Y >= 0 */
+
+/* rand.f:235-257 RNFARR: n >= 100 numbers into aa, state advanced */
+static void kn_array(orc_rng *g, double *aa, int n)
+{
+    int j;
+    for (j = 0; j < KN_KK; j++) aa[j] = g->ranx[j];
+    for (j = KN_KK; j < n; j++) aa[j] = frac1(aa[j - KN_KK] + aa[j - KN_LL]);
+    for (j = 0; j < KN_LL; j++) g->ranx[j] = frac1(aa[n + j - KN_KK] + aa[n + j - KN_LL]);
+    for (j = KN_LL; j < KN_KK; j++) g->ranx[j] = frac1(aa[n + j - KN_KK] + g->ranx[j - KN_LL]);
+}
+
+/* rand.f:262-316 RNFSTR */
+static void kn_start(orc_rng *g, int seed)
+{
+    const int MM = 1 << 30, KKK = 2 * KN_KK - 1;
+    const double ULP = 1.0 / 4503599627370496.0;
+    double u[2 * KN_KK - 1 + KN_KK], ss;            /* the 10 warm-up calls write KKK numbers into u */
+    int j, s, t, sseed;
+    sseed = (seed < 0) ? MM - 1 - ((-1 - seed) % MM) : seed % MM;
+    ss = 2.0 * ULP * (double)(sseed + 2);
+    for (j = 0; j < KN_KK; j++) {
+        u[j] = ss;
+        ss = ss + ss;
+        if (ss >= 1.0) ss = ss - 1.0 + 2 * ULP;
+    }
+    for (j = KN_KK; j < KKK; j++) u[j] = 0.0;
+    u[1] = u[1] + ULP;
+    s = sseed; t = 70 - 1;
+    while (t > 0) {
+        for (j = KN_KK - 1; j >= 1; j--) { u[2 * j] = u[j]; u[2 * j - 1] = 0.0; }
+        for (j = KKK - 1; j >= KN_KK; j--) {
+            u[j - (KN_KK - KN_LL)] = frac1(u[j - (KN_KK - KN_LL)] + u[j]);
+            u[j - KN_KK] = frac1(u[j - KN_KK] + u[j]);
+        }
+        if (s % 2 == 1) {
+            for (j = KN_KK - 1; j >= 0; j--) u[j + 1] = u[j];
+            u[0] = u[KN_KK];
+            u[KN_LL] = frac1(u[KN_LL] + u[KN_KK]);
+        }
+        if (s != 0) s = s / 2; else t = t - 1;
+    }
+    for (j = 0; j < KN_LL; j++) g->ranx[j + KN_KK - KN_LL] = u[j];
+    for (j = KN_LL; j < KN_KK; j++) g->ranx[j - KN_LL] = u[j];
+    for (j = 0; j < 10; j++) kn_array(g, u, KKK);
+}
+
+/* rand.f:99-186 initialize_rand / _zrand / _rrand: a fresh generator per zone job, per boundary ring, per census photon */
+static void kn_initialize(orc_state *s, int seed)
+{
+    if (s->rng.mode != 1) return;
+    kn_start(&s->rng, seed);
+    kn_array(&s->rng, s->rng.randlist, 10000);
+    s->rng.randcounter = 1;
+}
+
+/* rand.f:9-88 seed_zone: the integer generator (lags 19937 / 7083, mod 2^30) deals seeds(j,k), zseeds(j); rseeds(k) all get
+ * the same value nz nr + nz + 1 (l.81-84 never advance i); *seed_io leaves as seeds(1,1) (l.85), so the next step differs. */
+void orc_seed_zone(orc_state *s, int *seed_io)
+{
+    enum { KK = 19937, LL = 7083, KKK = 2 * KK - 1 };
+    const int MM = 1 << 30;
+    int *x = (int *)malloc(sizeof(int) * (size_t)(KKK + 1));
+    int j, k, i, ss, t, sseed, seed = *seed_io;
+    sseed = (seed < 0) ? MM - 1 - ((-1 - seed) % MM) : seed % MM;
+    ss = sseed - sseed % 2 + 2;
+    for (j = 0; j < KK; j++) {
+        x[j] = ss;
+        ss = ss + ss;
+        if (ss >= MM) ss = ss - MM + 2;
+    }
+    for (j = KK; j <= KKK; j++) x[j] = 0;
+    x[1] = x[1] + 1;
+    ss = sseed; t = 70 - 1;
+    while (t > 0) {
+        for (j = KK - 1; j >= 1; j--) { x[2 * j] = x[j]; x[2 * j - 1] = 0; }
+        for (j = KKK - 1; j >= KK; j--) {
+            x[j - (KK - LL)] -= x[j]; if (x[j - (KK - LL)] < 0) x[j - (KK - LL)] += MM;
+            x[j - KK] -= x[j];        if (x[j - KK] < 0) x[j - KK] += MM;
+        }
+        if (ss % 2 == 1) {
+            for (j = KK - 1; j >= 0; j--) x[j + 1] = x[j];
+            x[0] = x[KK];
+            x[LL] -= x[KK]; if (x[LL] < 0) x[LL] += MM;
+        }
+        if (ss != 0) ss = ss / 2; else t = t - 1;
+    }
+    i = 0;
+    for (j = 1; j <= s->nz; j++)
+        for (k = 1; k <= s->nr; k++) s->seeds[ZI(j, k)] = x[i++];
+    for (j = 1; j <= s->nz; j++) s->zseeds[j - 1] = x[i++];
+    for (k = 1; k <= s->nr; k++) s->rseeds[k - 1] = i + 1;
+    *seed_io = s->seeds[ZI(1, 1)];
+    free(x);
+}
+void orc_knuth_get(orc_state *s, double *ranx, double *randlist, int *randcounter)
+{
+    memcpy(ranx, s->rng.ranx, sizeof s->rng.ranx);
+    memcpy(randlist, s->rng.randlist, sizeof s->rng.randlist);
+    *randcounter = s->rng.randcounter;
+}
+void orc_knuth_set(orc_state *s, const double *ranx, const double *randlist, int randcounter)
+{
+    memcpy(s->rng.ranx, ranx, sizeof s->rng.ranx);
+    memcpy(s->rng.randlist, randlist, sizeof s->rng.randlist);
+    s->rng.randcounter = randcounter;
+}
+
+/* rand.f:195-223 fibran / Philox extension */
 double orc_fibran(orc_state *s)
 {
     orc_rng *g = &s->rng;
     g->ndraw++;
     if (g->mode == 2) return ran1(g);
+    if (g->mode == 1) {                              /* l.211-221: refill when the list is used up */
+        if (g->randcounter >= 10000) { kn_array(g, g->randlist, 10000); g->randcounter = 1; }
+        else g->randcounter++;
+        return g->randlist[g->randcounter - 1];
+    }
     if (g->has_pending) { g->has_pending = 0; return g->pending; }
     return orc_philox_uniform(g->key, g->sid, g->d++);
 }
@@ -919,6 +1037,7 @@ void orc_vol_calc(orc_state *s, int zone)
     f_lower = f_upper + f_lower;
     (void)f_lower;
     const uint64_t S_zone = orc_mix64(0x766F6Cull, (uint64_t)zone);
+    kn_initialize(s, s->seeds[zi]);                                      /* imcvol2d_para.f:115 initialize_rand(jv, kv) */
 
     for (ivol = 1; ivol <= more && !s->fatal; ivol++) {
         if (s->rng.mode == 3) rng_stream(s, orc_mix64(S_zone, (uint64_t)ivol));
@@ -1055,6 +1174,7 @@ void orc_z_surf_calc(orc_state *s, int js)
 {
     int nxs;
     double x1, x2;
+    kn_initialize(s, s->zseeds[js - 1]);                                 /* imcsurf2d_para.f:242 initialize_zrand(js) */
     for (nxs = 1; nxs <= s->nsurfi[js - 1] && !s->fatal; nxs++) {
         if (s->rng.mode == 3) rng_stream(s, orc_mix64(orc_mix64(0x73726600ull, (uint64_t)js), (uint64_t)nxs));
         s->jph = js;
@@ -1105,6 +1225,7 @@ void orc_r_surf_calc(orc_state *s, int ks)
     int nxs;
     double psi;
     const double rlo = (ks == 1) ? s->rmin : RR(ks - 1), rhi = RR(ks);
+    kn_initialize(s, s->rseeds[ks - 1]);                                 /* imcsurf2d_para.f:372 initialize_rrand(ks) */
     for (nxs = 1; nxs <= s->nsurfu[ks - 1] && !s->fatal; nxs++) {
         if (s->rng.mode == 3) rng_stream(s, orc_mix64(orc_mix64(0x73726602ull, (uint64_t)ks), (uint64_t)nxs));
         s->kph = ks;
@@ -1212,6 +1333,10 @@ void orc_field_calc(orc_state *s)
         s->rpre = d[0]; s->zpre = d[1]; s->wmu = d[2]; s->phi = d[3]; s->ew = d[4]; s->xnu = d[5];
         s->jgpsp = ib[0]; s->jgplc = ib[1]; s->jgpmu = ib[2]; s->jph = ib[3]; s->kph = ib[4];
         if (s->rng.mode == 3) rng_stream(s, s->sidin[n]);
+        if (s->rng.mode == 1) {                                          /* imcfield2d.f:115-116: the photon carries its seed */
+            s->seeds[ZI(s->jph, s->kph)] = ib[5];
+            kn_initialize(s, ib[5]);
+        }
         s->dcen = C_LIGHT * s->dt;
         if (s->wmu > 1.0) s->wmu = 1.0;
         if (s->wmu < -1.0) s->wmu = -1.0;

@@ -32,7 +32,10 @@ extern "C" {
 #endif
 
 typedef struct {
-    int mode;                 /* 2 = ran1, 3 = philox */
+    int mode;                 /* 1 = Knuth lagged Fibonacci (rand_switch = 1), 2 = ran1 (rand_switch = 2), 3 = philox */
+    /* Knuth ranf_array state: COMMON /RSTATE/ RANX(100), /rlist/ randlist(randmax = 10000), /rcount/ randcounter (rand.f:230-316) */
+    double ranx[100], randlist[10000];
+    int randcounter;
     /* ran1 state (rand.f:330-343) */
     int idum, iv[32], iy;
     /* philox */
@@ -67,6 +70,8 @@ typedef struct {
     X(nfile, int, ORC_NSPEC) X(E_file, double, ORC_NSPEC * ORC_NFMAX) X(F_file, double, ORC_NSPEC * ORC_NFMAX) \
     X(P_file, double, ORC_NSPEC * ORC_NFMAX) X(a1_file, double, ORC_NSPEC * ORC_NFMAX) \
     X(I_file, double, ORC_NSPEC * ORC_NFMAX) \
+    /* COMMON /random/ seeds(j,k), zseeds(j), rseeds(k) of the lagged-Fibonacci generator (commonblock.f:9-10,130) */ \
+    X(seeds, int, nzone) X(zseeds, int, nz) X(rseeds, int, nr) \
     X(nsv, int, nzone) X(ewsv, double, nzone) X(Eloss_th, double, nzone) X(Eloss_tot, double, nzone) \
     X(zsurf, double, nzone) \
     X(edep, double, nzone) X(prdep, double, nzone) X(ecens, double, nzone) X(npcen, int64_t, nzone) \
@@ -136,6 +141,10 @@ double orc_get_scalar(orc_state *s, const char *name);
 /* RNG */
 void orc_ran1_seed(orc_state *s, int idum, const int *iv, int iy);   /* restore rand.f SAVE state */
 void orc_ran1_get(orc_state *s, int *idum, int *iv, int *iy);
+/* rand_switch = 1 (o["rand_switch"] = 1 selects it): seed_zone (rand.f:9-88; *seed_io <- seeds(1,1)), RANX / randlist / randcounter */
+void orc_seed_zone(orc_state *s, int *seed_io);
+void orc_knuth_get(orc_state *s, double *ranx, double *randlist, int *randcounter);
+void orc_knuth_set(orc_state *s, const double *ranx, const double *randlist, int randcounter);
 void orc_philox_key(orc_state *s, uint32_t seed, uint32_t cycle);
 void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 uint64_t orc_mix64(uint64_t a, uint64_t b);

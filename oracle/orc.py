@@ -41,6 +41,9 @@ def lib():
         L.orc_ran1_seed.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
         L.orc_ran1_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.orc_philox_key.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_seed_zone.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_knuth_get.argtypes = [C.c_void_p] * 4
+        L.orc_knuth_set.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_mix64.restype = C.c_uint64
         L.orc_mix64.argtypes = [C.c_uint64, C.c_uint64]
         L.orc_philox_uniform.restype = C.c_double
@@ -122,6 +125,21 @@ class Oracle:
         iv = np.zeros(32, np.int32)
         self.L.orc_ran1_get(self.p, C.byref(idum), iv.ctypes.data, C.byref(iy))
         return idum.value, iv, iy.value
+
+    def seed_zone(self, seed):
+        """rand.f:9-88: fills o.a.seeds / zseeds / rseeds from `seed`; -> the seed of the next step (seeds(1,1))."""
+        v = C.c_int(int(seed))
+        self.L.orc_seed_zone(self.p, C.byref(v))
+        return v.value
+
+    def knuth_get(self):
+        ranx, lst, cnt = np.zeros(100), np.zeros(10000), C.c_int()
+        self.L.orc_knuth_get(self.p, ranx.ctypes.data, lst.ctypes.data, C.byref(cnt))
+        return ranx, lst, cnt.value
+
+    def knuth_set(self, ranx, randlist, randcounter):
+        ranx, lst = np.ascontiguousarray(ranx, dtype=np.float64), np.ascontiguousarray(randlist, dtype=np.float64)
+        self.L.orc_knuth_set(self.p, ranx.ctypes.data, lst.ctypes.data, int(randcounter))
 
     def philox_key(self, seed, cycle):
         self.L.orc_philox_key(self.p, int(seed), int(cycle))

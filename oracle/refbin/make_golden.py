@@ -59,6 +59,10 @@ CONFIGS = {
     # pair_switch = 1, T_const = 0), cycles 0-2 (tstop = 1e3 as in SURVEY.md 8 "golden values").  ~20 min per pass on one
     # core; only the first 2000 census records of each snapshot are kept, and the first 4000 event records.
     "c0": dict(over=dict(tstop="1.e+3"), zone={}, ncens=2000, census_head=True, events_head=4000, keep_logs=True),
+    # rand_switch = 1: Knuth's lagged-Fibonacci generator, re-seeded per zone job and per census photon (rand.f:9-316);
+    # the generator state (COMMON /RSTATE/ RANX, /rlist/, /rcount/) and the seeds are dumped too
+    "knuth": dict(over=dict(nz=4, nr=3, nst=6000, tstop="1.e+3", rand_switch=1), zone={}, knuth=True,
+                  extra=[("seeds", (4, 3)), ("zseeds", (4,)), ("rseeds", (3,)), ("randlist", (10000,)), ("randcounter", None)]),
     # external-Compton seed photons (BASELINE configs[2]): upper and lower disk sources sampled from a spectrum
     # file (the only live surface-source path of the reference: nsurf* > 0 requires tbb* < 0, imcgen2d.f:441-442)
     "surface": dict(over=dict(nz=3, nr=4, nst=1200, tstop="1.e+3", **{"t0(1)": "0.d0", "t1(1)": "1.d20"}), zone={},
@@ -191,6 +195,9 @@ def main(name):
     # ran1 SAVE state (rand.f:339-343): iv(32), iy
     spec += ["R ran1_$IV.0.1 0 128", "R ran1_$IY.0.1 0 4"]
     layout += [("ran1_iv", 4, (32,), 128), ("ran1_iy", 4, (), 4)]
+    if cfg.get("knuth"):
+        spec += ["R rstate_ 0 800"]
+        layout += [("knuth_ranx", 8, (100,), 800)]
     specf = rd / "snapspec.txt"
     specf.write_text("".join(f"AT 1 {i} {lab}\n" for i, lab in pts) + "\n".join(spec) + "\n")
 

@@ -223,3 +223,58 @@ def test_volume_em_and_budget_match_reference_binary(name, cyc):
         assert rel(getattr(a, k)[:nzone], ref[k]) < 1e-13, k
     for k in ("kappa_tot", "eps_tot", "eps_th"):
         assert rel(getattr(a, k)[: nzone * 400], ref[k]) < 1e-13, k
+
+
+# ---- rand_switch = 1: Knuth's lagged-Fibonacci generator (rand.f:9-316), tests/golden/refbin_knuth.npz ----
+def test_seed_zone_matches_reference_binary():
+    """seed_zone (rand.f:9-88) on the master deals one seed per zone every step and leaves seeds(1,1) as the next step's
+    rseed; the worker's COMMON /random/ seeds after the volume phase of cycle c are the master's seeds of that cycle
+    (vol_mpi.f:107,188)."""
+    g = Golden("knuth")
+    s = g.snap("c0_C")
+    o = new_oracle(s)
+    o["rand_switch"] = 1
+    seed = 9857                                   # input.dat:77; the master is rank 0 (fp_mpi.f:68: rseed + 84725 myid)
+    for cyc in (0, 1, 2):
+        seed = o.seed_zone(seed)
+        got = g.snap(f"c{cyc}_C").seeds
+        assert np.array_equal(o.a.seeds.reshape(got.shape), got), cyc
+        assert seed == int(got[0, 0])
+    assert (o.a.rseeds == o.dims["nz"] * o.dims["nr"] + o.dims["nz"] + 1).all()       # rand.f:81-84
+
+
+@pytest.mark.parametrize("cyc,phase", [(c, ph) for c in (1, 2) for ph in ("field", "vol")])
+def test_phase_matches_reference_binary_knuth(cyc, phase):
+    """The tracking phases with rand_switch = 1: a fresh generator per zone job (initialize_rand, imcvol2d_para.f:115) and per
+    census photon, seeded by the integer the photon carries in ibuf(6) (imcfield2d.f:115-116).  Same bar as the ran1 cases;
+    the generator's end state (RANX, randlist, randcounter) is compared instead of ran1's."""
+    g = Golden("knuth")
+    l0, l1 = (f"c{cyc}_A", f"c{cyc}_B") if phase == "field" else (f"c{cyc}_B", f"c{cyc}_C")
+    s0, s1 = g.snap(l0), g.snap(l1)
+    assert int(s0.rand_switch) == 1
+    o = new_oracle(s0)
+    load_snapshot(o, s0)
+    o.knuth_set(s0.knuth_ranx, s0.randlist, int(s0.randcounter))
+    o.a.seeds = s0.seeds
+    if phase == "vol":
+        a = o.a
+        for v in ("nsv", "zsurf", "eloss_th", "eloss_tot", "ewsv"):
+            setattr(a, cname(v), s1[v])
+        a.E_ph = s1.e_ph
+        for v in ("eps_tot", "eps_th"):
+            setattr(a, v, np.transpose(s1[v], (1, 2, 0)))
+        a.seeds = s1.seeds                         # arrive with the zone jobs (vol_mpi.f:188)
+        o.vol_all()
+    else:
+        o.field_calc()
+    assert int(o["fatal"]) == 0
+    bad = compare_tracking(o, s1)
+    d = bad.pop("dbufout", None)
+    assert not bad, bad
+    ranx, lst, cnt = o.knuth_get()
+    assert cnt == int(s1.randcounter) and np.array_equal(ranx, s1.knuth_ranx) and np.array_equal(lst, s1.randlist)
+    assert np.array_equal(o.a.seeds.reshape(s1.seeds.shape), s1.seeds)
+    if d is not None:
+        n = int(s1.ndxout)
+        r = np.abs(o.a.dbufout[: 6 * n].reshape(n, 6) - s1.dbufout[: 6 * n].reshape(n, 6)) / np.maximum(np.abs(s1.dbufout[: 6 * n].reshape(n, 6)), 1e-300)
+        assert r.max() < 1e-4 and (r.max(axis=1) > 1e-7).mean() < 0.01
