@@ -1,5 +1,5 @@
 #!/bin/bash
-# final validation of the round on one B200 (run through gpurun)
+# the commands behind profiles/r02_*: final validation of the round on one B200 (run through gpurun from the repo root)
 mkdir -p gpurun_out/final
 timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/final/tests.log 2>&1; tail -3 gpurun_out/final/tests.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/final/smoke.log 2>&1; tail -2 gpurun_out/final/smoke.log
