@@ -148,6 +148,11 @@ struct Params {
     unsigned long long *lit_count, lit_cap;
 };
 
+// software pipelining depth of the sigma-table noise loops (same arithmetic in the same order; measured)
+#ifndef C2D_NOISE_UNROLL
+#define C2D_NOISE_UNROLL 2
+#endif
+constexpr int kNoiseUnroll = C2D_NOISE_UNROLL;
 constexpr int kSortE = 24;             // energy classes of the bank's sort key
 // energy class of a census photon: one per octave of photon energy from 1 keV down -- the Thomson-branch count m(x) of
 // comtot, and with it the length of the sigma table's noise loop, is a function of log x (7 electron bins per octave)
@@ -700,6 +705,7 @@ __device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCt
             {
                 const int i_a = (ia < i_end) ? ia : i_end;
                 double sa = 0.0, sb = 0.0;
+#pragma unroll kNoiseUnroll
                 for (; i < i_a; i++) {
                     const double ya = c2d_ldg(p.kn_a1 + i) * x, yb = c2d_ldg(p.kn_a2 + i) * x;
                     const double ta = 1.0 + ya, tb = 1.0 + yb;
@@ -718,6 +724,7 @@ __device__ __forceinline__ double comtot_table_zone(const Params &p, const SigCt
             // cb_i W_i is tabulated per zone (sig_CW); two independent accumulators, -1 / x applied once.
             const double *a2 = p.kn_a2;
             double s0 = 0.0, s1 = 0.0;
+#pragma unroll kNoiseUnroll
             for (; i + 1 < i_end; i += 2) {
                 const double y0 = c2d_ldg(a2 + i) * x, y1 = c2d_ldg(a2 + i + 1) * x;
                 const double t0 = 1.0 + y0, t1 = 1.0 + y1;
