@@ -25,6 +25,9 @@
 
 namespace c2d {
 
+#ifndef C2D_FP_FAT
+#define C2D_FP_LEAN 1                  // 4 shared-memory arrays per zone instead of 9 (see k_fp_zones)
+#endif
 struct FpParams {
     int nz, nr, N, nf, pair_switch;
     int first_zone, n_zones, zone_stride;
@@ -47,6 +50,7 @@ struct FpParams {
     double *f_nt, *Pnt, *n_e, *Te_new, *gmin, *gmax, *p_nth, *amxwl, *f_pair;
     int *fp_steps;
     double *zE_old, *zE_new, *z_hr, *z_hrst, *z_dT, *z_misc;   // z_misc: [zone][3] = dr, dz, f_t_implicit
+    double *scratch;                                           // C2D_FP_LEAN: [zone slot][2 N] dg_ic | dgdt (L1 / L2 resident)
 };
 
 struct FpState {
@@ -59,6 +63,8 @@ struct FpState {
     double *d_quad = nullptr;     // [kQuadRounds * 32]: (ts^2-1)^(3/2)
     unsigned long long *d_gc_key = nullptr;   // gamma_bar memo (kGcSlots keys / values), kept for the life of the context
     double *d_gc_val = nullptr;
+    double *d_scr = nullptr;      // k_fp_zones' global scratch (C2D_FP_LEAN)
+    size_t scr_cap = 0;
 };
 constexpr int kGcSlots = 1 << 16;
 constexpr int kQuadRounds = 1024;                                 // 32768 lattice points t = 1.001^n: covers z >= 1e-12
@@ -405,8 +411,19 @@ __global__ void __launch_bounds__(128) k_gbar_table(double *tab, int n, double x
     if ((threadIdx.x & 31) == 0) tab[i] = g;
 }
 
-// shared-memory layout per warp: 9 arrays of N doubles
-__global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
+// shared-memory layout per warp: 9 arrays of N doubles; C2D_FP_LEAN: 4 (f, a_i, b_i, c_i) -- f_new lives in f_old (the Thomas
+// sweeps work in place), the interface quantities bigC / smw are recomputed where they are used (same expressions, same
+// values), gam(i) of tridag goes where a_i(i) has just been consumed, dg_ic / dgdt sit in a global scratch row
+// Measured on the B200 (4096 zones, ms per call): 9 arrays 1.258 (N = 200) / 5.465 (N = 512); 4 arrays at 128 registers
+// 1.146 / 3.738, at 96 registers 1.205 / 3.910, at 72 registers (28 warps / SM: all 4096 zones of a 64 x 64 grid resident
+// at once) 1.034 / 4.240 -- so the kernel is instantiated twice and the launcher picks by N.
+#ifdef C2D_FP_LEAN
+constexpr int kFpArrays = 4;
+#else
+constexpr int kFpArrays = 9;
+#endif
+template <int MINB>
+__global__ void __launch_bounds__(64, MINB) k_fp_zones(const FpParams q)
 {
     extern __shared__ double smem[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -414,8 +431,13 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
     if (slot >= q.n_zones) return;
     const int zi = q.first_zone + slot * q.zone_stride;
     const int N = q.N, nf = q.nf;
-    double *f_old = smem + (size_t)w * 9 * N, *f_new = f_old + N, *a_i = f_new + N, *b_i = a_i + N, *c_i = b_i + N,
+#ifdef C2D_FP_LEAN
+    double *f_old = smem + (size_t)w * kFpArrays * N, *f_new = f_old, *a_i = f_old + N, *b_i = a_i + N, *c_i = b_i + N,
+           *dg_ic = q.scratch + (size_t)slot * 2 * N, *dgdt = dg_ic + N;
+#else
+    double *f_old = smem + (size_t)w * kFpArrays * N, *f_new = f_old + N, *a_i = f_new + N, *b_i = a_i + N, *c_i = b_i + N,
            *dg_ic = c_i + N, *dgdt = dg_ic + N, *bigC = dgdt + N, *smw = bigC + N;
+#endif
     // disp_A(i) = gamma^2/t_acc/2 is recomputed where needed; bigW = smw/(exp(smw)-1) likewise
     const double *gnt = q.gnt;
     const int j = zi / q.nr + 1, k = zi - q.nr * (j - 1) + 1;
@@ -617,37 +639,52 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
         n_lept = n_lept * t_esc / (t_esc + d_t);
         __syncwarp();
         // Chang-Cooper coefficients (l.1319-1391): interface quantities bigC, smw first
-        for (int i = lane; i < N - 1; i += 32) {                      // interface i (0-based) between bins i, i+1
-            const double g0 = gnt[i] + 1.0, g1 = gnt[i + 1] + 1.0;
+        // interface m (0-based) between bins m, m + 1: bigC, smw
+        auto iface = [&](int m, double &C_m, double &w_m) {
+            const double g0 = gnt[m] + 1.0, g1 = gnt[m + 1] + 1.0;
             const double disp0 = g0 * g0 / t_acc / 2.0, disp1 = g1 * g1 / t_acc / 2.0;
-            const double bigB = (i == 0) ? -(dgdt[0] + dgdt[1]) : -(dgdt[i] + dgdt[i + 1]) / 2.0;
-            bigC[i] = (disp0 + disp1) / 2.0;
-            smw[i] = (gnt[i + 1] - gnt[i]) * bigB / bigC[i];
-        }
+            const double bigB = (m == 0) ? -(dgdt[0] + dgdt[1]) : -(dgdt[m] + dgdt[m + 1]) / 2.0;
+            C_m = (disp0 + disp1) / 2.0;
+            w_m = (gnt[m + 1] - gnt[m]) * bigB / C_m;
+        };
+#ifndef C2D_FP_LEAN
+        for (int i = lane; i < N - 1; i += 32) iface(i, bigC[i], smw[i]);
         __syncwarp();
+#endif
         for (int i = lane; i < N; i += 32) {
             if (i == 0 || i == N - 1) { a_i[i] = 0.0; b_i[i] = 1.0; c_i[i] = 0.0; continue; }
             const double D_gminus = gnt[i] - gnt[i - 1], D_gplus = gnt[i + 1] - gnt[i];
             const double Delta_g = sqrt(gnt[i] / gnt[i - 1]) * D_gminus;
-            const double bigW_i = smw[i] / (exp(smw[i]) - 1.0), bigW_m = smw[i - 1] / (exp(smw[i - 1]) - 1.0);
-            c_i[i] = -d_t * (bigC[i] * smw[i] / (1.0 - exp(-smw[i])) / Delta_g / D_gplus);
-            b_i[i] = 1.0 + d_t / Delta_g * (bigC[i] * bigW_i / D_gplus +
-                                            bigC[i - 1] * smw[i - 1] / (1.0 - exp(-smw[i - 1])) / D_gminus) + d_t / t_esc;
-            a_i[i] = -d_t / Delta_g * bigC[i - 1] * bigW_m / D_gminus;
+#ifdef C2D_FP_LEAN
+            double C_i, w_i, C_m, w_m;
+            iface(i, C_i, w_i); iface(i - 1, C_m, w_m);
+#else
+            const double C_i = bigC[i], w_i = smw[i], C_m = bigC[i - 1], w_m = smw[i - 1];
+#endif
+            const double bigW_i = w_i / (exp(w_i) - 1.0), bigW_m = w_m / (exp(w_m) - 1.0);
+            c_i[i] = -d_t * (C_i * w_i / (1.0 - exp(-w_i)) / Delta_g / D_gplus);
+            b_i[i] = 1.0 + d_t / Delta_g * (C_i * bigW_i / D_gplus +
+                                            C_m * w_m / (1.0 - exp(-w_m)) / D_gminus) + d_t / t_esc;
+            a_i[i] = -d_t / Delta_g * C_m * bigW_m / D_gminus;
         }
         __syncwarp();
         // tridag (update2d.f:2485-2528): sequential recurrences, lane 0; gam(i) is kept in dgdt[]
         if (lane == 0) {
+#ifdef C2D_FP_LEAN
+            double *gam = a_i;                                    // a_i(i) is dead once row i has been eliminated
+#else
+            double *gam = dgdt;
+#endif
             double bet = b_i[0];
             f_new[0] = f_old[0] / bet;
             for (int i = 1; i < N; i++) {
-                const double gm = c_i[i - 1] / bet;
-                dgdt[i] = gm;
-                bet = b_i[i] - a_i[i] * gm;
-                f_new[i] = (f_old[i] - a_i[i] * f_new[i - 1]) / bet;
+                const double gm = c_i[i - 1] / bet, ai = a_i[i];
+                gam[i] = gm;
+                bet = b_i[i] - ai * gm;
+                f_new[i] = (f_old[i] - ai * f_new[i - 1]) / bet;
             }
             for (int i = N - 2; i >= 0; i--) {
-                f_new[i] = f_new[i] - dgdt[i + 1] * f_new[i + 1];
+                f_new[i] = f_new[i] - gam[i + 1] * f_new[i + 1];
                 if (f_new[i + 1] < 0.0) f_new[i + 1] = 0.0;
             }
             f_new[N - 1] = 0.0;
@@ -726,7 +763,11 @@ __global__ void __launch_bounds__(64, 7) k_fp_zones(const FpParams q)
         // update2d.f:1700-1738: scan p_nth = 0.1, 0.15, ... for the power law whose mean energy matches <gamma>.
         // gamma^-p is carried from step to step by one multiplication with gamma^-0.05 and exp(-gamma/gmax) is hoisted
         // (the reference calls gam**p_nth and exp(y) for every bin and step: same values to ~1e-14)
+#ifdef C2D_FP_LEAN
+        double *ipw = a_i, *ipstep = b_i, *wq = c_i;              // c_i (the running CDF) has been written out above
+#else
         double *ipw = a_i, *ipstep = b_i, *wq = bigC;
+#endif
         __syncwarp();
         for (int i = lane; i < N; i += 32) {
             const int i1 = i + 1;
@@ -843,11 +884,18 @@ void launch_transpose(const double *in, int rows, int cols, double *out, cudaStr
 }
 void launch_fp(const FpParams &q, cudaStream_t st)
 {
-    const int warps = 2;                                          // 14.4 kB of shared memory per warp (N = 200): 7 blocks / SM
-    const size_t smem = (size_t)warps * 9 * q.N * sizeof(double);
-    cudaFuncSetAttribute(k_fp_zones, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int warps = 2;                                          // 6.4 kB of shared memory per warp at N = 200 (4 arrays)
+    const size_t smem = (size_t)warps * kFpArrays * q.N * sizeof(double);
     const int blocks = (q.n_zones + warps - 1) / warps;
-    k_fp_zones<<<blocks, warps * 32, smem, st>>>(q);
+#ifdef C2D_FP_LEAN
+    if (q.N <= 256) {                                             // 72 registers, 14 blocks / SM
+        cudaFuncSetAttribute(k_fp_zones<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_fp_zones<14><<<blocks, warps * 32, smem, st>>>(q);
+        return;
+    }
+#endif
+    cudaFuncSetAttribute(k_fp_zones<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_fp_zones<7><<<blocks, warps * 32, smem, st>>>(q);
 }
 void launch_ic_loss(const double *gnt, const double *E_field, int N, int nf, double *F_IC, cudaStream_t st)
 {
@@ -865,7 +913,7 @@ void Ctx::fp_free()
 {
     if (!fp) return;
     cudaFree(fp->d_FIC); cudaFree(fp->d_io); cudaFree(fp->d_gtab); cudaFree(fp->d_FICt); cudaFree(fp->d_quad);
-    cudaFree(fp->d_gc_key); cudaFree(fp->d_gc_val);
+    cudaFree(fp->d_gc_key); cudaFree(fp->d_gc_val); cudaFree(fp->d_scr);
     delete fp;
     fp = nullptr;
 }
@@ -956,6 +1004,24 @@ __global__ void k_fp_unpack(const double *recv, int world, int n_slot, int rec, 
 }
 #endif
 
+// global scratch rows of k_fp_zones (C2D_FP_LEAN): 2 N doubles per zone of the launch, grown to the largest launch seen
+static int fp_scratch(Ctx *c, FpParams &q)
+{
+    q.scratch = nullptr;
+#ifdef C2D_FP_LEAN
+    const size_t need = (size_t)std::max(q.n_zones, 1) * 2 * (size_t)q.N;
+    if (need > c->fp->scr_cap) {
+        cudaFree(c->fp->d_scr); c->fp->d_scr = nullptr; c->fp->scr_cap = 0;
+        CUF(cudaMalloc(&c->fp->d_scr, need * 8));
+        c->fp->scr_cap = need;
+    }
+    q.scratch = c->fp->d_scr;
+#else
+    (void)c;
+#endif
+    return 0;
+}
+
 int fp_resident(Ctx *c, const c2d_fp_in *in, double *zinfo_host)
 {
 #ifdef C2D_EMU
@@ -1008,6 +1074,7 @@ int fp_resident(Ctx *c, const c2d_fp_in *in, double *zinfo_host)
     q.p_nth = D + p_pn; q.amxwl = D + p_am; q.f_pair = D + p_fp;
     q.zE_old = D + p_Eo; q.zE_new = D + p_En; q.z_hr = D + p_hr; q.z_hrst = D + p_hs; q.z_dT = D + p_dT; q.z_misc = D + p_misc;
     q.fp_steps = reinterpret_cast<int *>(D + p_steps);
+    if (int rc = fp_scratch(c, q)) return rc;
     if (n_own > 0) {
         c->timer_begin(3);
         launch_fp(q, c->stream);
@@ -1161,6 +1228,7 @@ int c2d_update_fp(c2d_ctx *h, const c2d_fp_in *in, c2d_fp_out *out)
     q.p_nth = D + p_pn; q.amxwl = D + p_am; q.f_pair = D + p_fp;
     q.zE_old = D + p_Eo; q.zE_new = D + p_En; q.z_hr = D + p_hr; q.z_hrst = D + p_hs; q.z_dT = D + p_dT; q.z_misc = D + p_misc;
     q.fp_steps = reinterpret_cast<int *>(D + p_steps);
+    if (int rc2 = fp_scratch(c, q)) return rc2;
     if (n_zones > 0) {
         c->timer_begin(3);
         launch_fp(q, c->stream);
