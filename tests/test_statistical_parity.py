@@ -11,6 +11,8 @@ realisations a, b of the same mean give z = (a - b) / sqrt(a + b) ~ N(0, 1).  Bo
 a + b >= 25, chi^2 = sum z^2 < n + 5 sqrt(2 n) over those n bins; energies (sums of ~equal weights) within 5 sigma of
 the count noise.  The unscattered (synchrotron) component carries ~3000 independent histories per cycle; the scattered
 component is built from O(1) primary collisions per cycle and is not tested bin by bin (SURVEY.md 8 notes)."""
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -135,3 +137,52 @@ def test_oracle_philox_vs_reference_binary(name):
 @pytest.mark.parametrize("name", ["small", "annulus"])
 def test_cuda_vs_reference_binary(name):
     _run_two_cycles(name, _gpu_runner)
+
+
+# ---- the scattered (inverse-Compton) component over an ensemble of seeds (SURVEY.md 8 notes: >= 30 seeds) ----
+def _two_sample_z(x, y):
+    x, y = np.asarray(x, float), np.asarray(y, float)
+    se = np.sqrt(x.var(axis=0, ddof=1) / len(x) + y.var(axis=0, ddof=1) / len(y))
+    return (x.mean(axis=0) - y.mean(axis=0)) / se
+
+
+def test_scattered_component_ensemble_matches_reference_binary():
+    """32 runs of the unmodified binary (oracle/refbin/make_ic_ensemble.py: `dense` inputs, rand_switch = 1 so that rseed takes
+    effect, cycles 1-2) against 32 closed-loop runs of the oracle with Philox streams (tests/golden/make_ic_ensemble_oracle.py)
+    -- what the CUDA path reproduces draw by draw.  A run has ~25 primary collisions per cycle, each fanning out into ~300
+    correlated children, so single runs cannot be compared; the ensemble means can.  Stated error model: the per-seed values
+    of each statistic are i.i.d.; z = (mean_a - mean_b) / sqrt(s_a^2 / n_a + s_b^2 / n_b) ~ N(0, 1).  Bounds: |z| < 4 for each
+    of the 20 statistics, chi^2 = sum z^2 < n + 5 sqrt(2 n)."""
+    gold = Path(__file__).resolve().parent / "golden"
+    b, o = np.load(gold / "ic_ensemble_dense.npz"), np.load(gold / "ic_ensemble_oracle.npz")
+    assert len(b["seeds"]) >= 30 and len(o["seeds"]) >= 30
+    zs = {}
+    for k in ("cm1", "cm2", "n_sc", "w_sc", "n_un", "w_un"):            # collisions, children, scattered / unscattered escapes
+        for c, z in enumerate(_two_sample_z(b[k], o[k])):
+            zs[f"{k}[cycle {c + 1}]"] = float(z)
+    for i, z in enumerate(_two_sample_z(b["spec_sc"], o["spec_sc"])):   # spectrum of the scattered escapes, 8 bands over 21 decades
+        zs[f"spec_sc[{i}]"] = float(z)
+    bad = {k: z for k, z in zs.items() if not abs(z) < 4.0}
+    assert not bad, bad
+    n = len(zs)
+    assert sum(z * z for z in zs.values()) < n + 5.0 * np.sqrt(2.0 * n), zs
+    # children per collision in the cycle whose collisions are all first collisions of source photons: split2 * (1 + 3rd split)
+    r_b, r_o = b["cm2"][:, 0].sum() / b["cm1"][:, 0].sum(), o["cm2"][:, 0].sum() / o["cm1"][:, 0].sum()
+    assert abs(r_b / r_o - 1.0) < 0.02, (r_b, r_o)
+    assert b["cm1"].sum() > 1500 and o["cm1"].sum() > 1500           # the ensembles do hold ~1600 collisions each
+
+
+def test_oracle_ensemble_fixture_is_reproducible():
+    """Two members of tests/golden/ic_ensemble_oracle.npz recomputed by the live oracle: the fixture is what the committed
+    script produces (integers exactly, weights to rounding)."""
+    import sys
+    sys.path.insert(0, str(Path(__file__).resolve().parent / "golden"))
+    import make_ic_ensemble_oracle as mk
+    fx = np.load(Path(__file__).resolve().parent / "golden" / "ic_ensemble_oracle.npz")
+    o, st, scal, ens = mk.setup()
+    for i in (0, 7):
+        m = mk.member(o, st, scal, int(fx["seeds"][i]), ens)
+        for k in ("cm1", "cm2", "n_sc", "n_un"):
+            assert np.array_equal(m[k], fx[k][i]), (i, k)
+        for k in ("w_sc", "w_un", "spec_sc"):
+            assert np.allclose(m[k], fx[k][i], rtol=1e-12, atol=0), (i, k)
