@@ -17,6 +17,21 @@ from loop_util import PLASMA, initial_state, oracle_cycle  # noqa: E402
 NST = 1200          # input.dat nst of the `dense` configuration (the worker's copy of nst is 0 in the snapshots)
 
 
+def new_stats(ens):
+    return dict(cm1=np.zeros(2, np.int64), cm2=np.zeros(2, np.int64), n_sc=np.zeros(2, np.int64), w_sc=np.zeros(2),
+                n_un=np.zeros(2, np.int64), w_un=np.zeros(2), spec_sc=np.zeros(len(ens["edges"]) - 1))
+
+
+def add_cycle(out, c, counters, ev, ens):
+    """Fold cycle c + 1 (c = 0, 1) into the ensemble statistics: the step's collision counters and its escape records."""
+    w_med, edges = float(ens["w_median"]), ens["edges"]
+    heavy = (ev[:, 2] > 0.3 * w_med) & (ev[:, 2] < 3.0 * w_med) & (ev[:, 1] < 10.0)
+    out["cm1"][c] = counters["cmcount1"]; out["cm2"][c] = counters["cmcount2"]
+    out["n_sc"][c] = int((~heavy).sum()); out["w_sc"][c] = float(ev[~heavy, 2].sum())
+    out["n_un"][c] = int(heavy.sum()); out["w_un"][c] = float(ev[heavy, 2].sum())
+    out["spec_sc"] += np.histogram(np.log10(ev[~heavy, 1]), bins=edges, weights=ev[~heavy, 2])[0]
+
+
 def member(o, st, scal, seed, ens):
     """Cycles 0-2 from the initial plasma with Philox seed `seed` -> the per-cycle statistics of the ensemble fixture."""
     a = o.a
@@ -25,21 +40,13 @@ def member(o, st, scal, seed, ens):
     a.ecens[:] = 0.0; a.fout[:] = 0.0; a.ec_old[:] = 0.0
     o["ndxout"] = 0
     o.rseed = int(seed)
-    dt, w_med, edges = float(ens["dt"]), float(ens["w_median"]), ens["edges"]
-    out = dict(cm1=np.zeros(2, np.int64), cm2=np.zeros(2, np.int64), n_sc=np.zeros(2, np.int64), w_sc=np.zeros(2),
-               n_un=np.zeros(2, np.int64), w_un=np.zeros(2), spec_sc=np.zeros(len(edges) - 1))
+    out = new_stats(ens)
     time = 0.0
     for cyc in range(3):
         res = oracle_cycle(o, cyc, time, scal, T_const=scal["T_const"])
         if cyc > 0:
             time += scal["dt"]
-            c = cyc - 1
-            ev = res["events"]
-            heavy = (ev[:, 2] > 0.3 * w_med) & (ev[:, 2] < 3.0 * w_med) & (ev[:, 1] < 10.0)
-            out["cm1"][c] = res["counters"]["cmcount1"]; out["cm2"][c] = res["counters"]["cmcount2"]
-            out["n_sc"][c] = int((~heavy).sum()); out["w_sc"][c] = float(ev[~heavy, 2].sum())
-            out["n_un"][c] = int(heavy.sum()); out["w_un"][c] = float(ev[heavy, 2].sum())
-            out["spec_sc"] += np.histogram(np.log10(ev[~heavy, 1]), bins=edges, weights=ev[~heavy, 2])[0]
+            add_cycle(out, cyc - 1, res["counters"], res["events"], ens)
     return out
 
 

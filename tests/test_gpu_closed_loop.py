@@ -201,3 +201,29 @@ def test_configs0_as_shipped_matches_reference_binary():
     m = f_ref > 1e-6 * f_ref.max(axis=1, keepdims=True)
     assert np.abs(plasma["f_nt"][m] / f_ref[m] - 1.0).max() < 2e-2
     assert np.abs(plasma["n_e"] / np.asarray(F.n_e).ravel() - 1.0).max() < 1e-6
+
+
+def test_gpu_reproduces_members_of_the_oracle_ensemble():
+    """tests/test_statistical_parity.py compares 32 Philox runs of the oracle's closed loop with 32 runs of the reference binary
+    (the scattered component).  The CUDA path replays those Philox streams: two members of that ensemble (other seeds than
+    the goldens'), run by c2d_step, give the fixture's collision counts, child counts and escape counts exactly and its
+    escape weights / spectrum to rounding."""
+    import sys
+    sys.path.insert(0, str(GOLD))
+    import make_ic_ensemble_oracle as mk
+    fx, ens = np.load(GOLD / "ic_ensemble_oracle.npz"), np.load(GOLD / "ic_ensemble_dense.npz")
+    o, st, P, scal = initial_state(Golden("dense"))
+    for i in (3, 11):
+        g = gpu_closed(P, st, dict(scal, nst=mk.NST, rseed=int(fx["seeds"][i])))
+        try:
+            out = mk.new_stats(ens)
+            for cyc in range(3):
+                rg = gpu_cycle(g, scal["dt"])
+                if cyc > 0:
+                    mk.add_cycle(out, cyc - 1, rg["counters"], rg["events"], ens)
+        finally:
+            g.close()
+        for k in ("cm1", "cm2", "n_sc", "n_un"):
+            assert np.array_equal(out[k], fx[k][i]), (i, k, out[k], fx[k][i])
+        for k in ("w_sc", "w_un", "spec_sc"):
+            assert np.allclose(out[k], fx[k][i], rtol=1e-7, atol=0), (i, k)
