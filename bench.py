@@ -430,7 +430,7 @@ def our_arm(args):
                         "frac": achieved / hbm, "traffic": traffic, "traffic_source": tsrc,
                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if "hbm_gbs" in peaks else "fallback 6650",
                         "bytes_per_step": r["bytes_per_step"],
-                        "note": "instruction-bound kernel (DESIGN.md 4): the HBM fraction is reported because the task asks for it"},
+                        "note": "latency-bound kernel (dependent L1/L2 loads at 28 warps / SM, issue slots 41 % busy: DESIGN.md 4, profiles/r02_ncu_summary.md); the HBM fraction is reported because the contract asks for it"},
            "counters": r["counters"], "clocks": r["clocks"]}
     if rank == 0 and not args.no_fp and world == 1:
         for leg, fn in (("lc", lambda: lc_bench(g, hbm)),):
