@@ -51,6 +51,17 @@ struct Tallies {
     int64_t counters[16] = {0}, counters_global[16] = {0};
 };
 
+// == Pref_calc (ref_matrix.f:7-89) on device `device`: E_ref [n_ref], P_ref(n_out, n_in) with column n_in contiguous
+inline void pref_calc(int device, int n_ref, std::vector<double> &E_ref, std::vector<double> &P_ref)
+{
+    c2d_ctx *h = nullptr;
+    check(c2d_create(&h, device));
+    E_ref.assign((size_t)n_ref, 0.0); P_ref.assign((size_t)n_ref * n_ref, 0.0);
+    const int rc = c2d_pref_calc(h, n_ref, E_ref.data(), P_ref.data());
+    c2d_destroy(h);
+    check(rc);
+}
+
 class Compton2d {
   public:
     // Ranks: one Compton2d per GPU.  comm_init joins them: rank 0 makes the NCCL id (unique_id()), the host ships its 128 bytes
